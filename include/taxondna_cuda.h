@@ -1,0 +1,187 @@
+/*
+ * taxondna_cuda.h -- C ABI of the B200 (sm_100a) all-vs-all pairwise-distance engine that
+ * replaces the bodies of TaxonDNA's Sequence.getPairwise family and the O(N^2) loops of its
+ * consumers.  The reference is 100% Java and has no native interface for this path
+ * (SURVEY.md section 8b), so each entry point below cites the *Java method(s)* whose body a host
+ * layer (java/ via Panama FFM; taxondna_b200/host in this repo) replaces with a call to it.
+ * Paths are relative to src/main/java/com/ggvaidya/TaxonDNA/ of the reference.
+ *
+ * Conventions
+ *  - C99, no C++ types, no exceptions.  Every function returns int32_t: 0 = TDNA_OK, else a
+ *    TDNA_E_* code; tdna_last_error() gives the text (owned by the library, valid until the next
+ *    call on the same thread).
+ *  - Buffers are caller-allocated and caller-owned; the library never keeps a caller pointer
+ *    after the call returns.  Output pointers may be HOST or DEVICE addresses (the copy uses
+ *    cudaMemcpyDefault / UVA), so a torch tensor's data_ptr() works as well as a Java
+ *    MemorySegment.  Input pointers likewise.
+ *  - One context per GPU and per process ("one process per GPU"); a context owns one CUDA
+ *    stream.  Calls on one context are serialised by the caller (the reference serialises all
+ *    analyses behind SequenceList's static lock, Common/DNA/SequenceList.java:403-480).
+ *  - There is NO CPU fallback: without a CUDA device tdna_init fails with TDNA_E_CUDA.
+ *  - Row index == position in the SequenceList order the host layer passed (SORT_BYNAME in the
+ *    GUI, SpeciesIdentifier/SequencePanel.java:46,177-249).
+ */
+#ifndef TAXONDNA_CUDA_H
+#define TAXONDNA_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDNA_ABI_VERSION 1
+
+enum {
+    TDNA_OK = 0,
+    TDNA_E_CUDA = 1,     /* CUDA runtime error (incl. "no device") */
+    TDNA_E_ARG = 2,      /* bad argument */
+    TDNA_E_SYMBOL = 3,   /* a symbol outside the normalised alphabet (Sequence.changeSequence would throw) */
+    TDNA_E_STATE = 4,    /* call order (e.g. labels needed but not set) */
+    TDNA_E_TOO_LARGE = 5,/* a device-resident result does not fit the memory budget */
+    TDNA_E_CANCELLED = 6 /* tdna_cancel() was called (DelayAbortedException, Common/DelayCallback.java:48) */
+};
+
+/* Sequence.PDM_* (Common/DNA/Sequence.java:53-55) */
+enum { TDNA_PDM_UNCORRECTED = 0, TDNA_PDM_K2P = 1, TDNA_PDM_TRANS_ONLY = 2 };
+
+typedef struct tdna_ctx tdna_ctx;
+typedef struct tdna_aln tdna_aln;
+
+/* Integer counts of one pair; which are meaningful depends on the mode:
+ *   shared : Sequence.getSharedLength (Sequence.java:1414-1485), mode-specific
+ *   c1     : uncorrected -> countIdentical (:1322-1341); K2P -> n (:1514-1528); trans-only -> countTransversions (:1352-1371)
+ *   c2, c3 : K2P -> nTransitions, nTransversions (:1530-1541); else 0 */
+typedef struct {
+    int32_t shared, c1, c2, c3;
+} tdna_counts;
+
+/* Per-query summary: everything BestMatch.run (SpeciesIdentifier/BestMatch.java:238-506) and
+ * BlockAnalysis.run (SpeciesIdentifier/BlockAnalysis.java:238-350) read off the list that
+ * SortedSequenceList.sortAgainst (Common/DNA/SortedSequenceList.java:78-128) builds for one
+ * query, in the well-formed case, plus the evidence the host layer needs to
+ * decide that the case IS well formed (near_* / unnamed_* / TDNA_ROW_NONFINITE); rows that are
+ * not are re-resolved on the host from tdna_row_distances with the reference's exact sort.
+ * "valid" = not (d < 0), j != q.  key(j) = (d, j conspecific-to-q ? 0 : 1, j)  -- the order
+ * SortedSequenceComparator (SortedSequenceList.java:197-261) induces when it is consistent. */
+typedef struct {
+    double d_best;   /* distance of the arg-min key over valid j; -1.0 if none ("No match") */
+    double d_con;    /* min over valid NAMED conspecific j (first_con, BestMatch.java:343-347); -1.0 if none */
+    double d_allo;   /* min over valid NAMED allospecific j (first_allo, :348-352); -1.0 if none */
+    double d_other;  /* min key over valid named j with species != species(best), j != best (end of the
+                        BlockAnalysis block, BlockAnalysis.java:282-294); -1.0 if none */
+    int32_t best, con, allo, other;   /* row indices of the above; -1 if none */
+    int32_t shared_con, shared_allo;  /* getSharedLength(query, first_con/first_allo) (BestMatch.java:372,386) */
+    int32_t tie_count;                /* # valid j != best with d == d_best exactly (count_bestMatches, :296-326) */
+    int32_t tie_species_min, tie_species_max; /* species ids over the NAMED ties (excl. best); INT32_MAX / -1 if none */
+    int32_t tie_unnamed;              /* # unnamed ties (the reference NPEs on these, BestMatch.java:319) */
+    int32_t block_count;              /* # valid named j != best of species(best) with key(j) < key(other) */
+    int32_t near_best, near_con, near_allo, near_other; /* # valid j with 0 < |d - d_ref| < 2e-5 */
+    int32_t unnamed_at_con, unnamed_at_allo, unnamed_at_other; /* # unnamed valid j with d == d_ref */
+    int32_t n_valid;                  /* # valid j != q */
+    int32_t flags;                    /* TDNA_ROW_* */
+    int32_t reserved;
+} tdna_row_result;
+
+enum {
+    TDNA_ROW_SELF_VALID = 1, /* d(q,q) is valid, so q itself heads the sorted list */
+    TDNA_ROW_NONFINITE = 2   /* some valid d(q,j) is NaN or +Inf (K2P saturation): host must resolve */
+};
+
+/* Pair classes of PairwiseDistribution (Common/DNA/PairwiseDistribution.java:41-42, 161-203) */
+enum { TDNA_PD_INTRA = 0, TDNA_PD_INTER = 1 };
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int32_t tdna_abi_version(void);
+/* Creates the context for CUDA device `device` (one per process in the torchrun layout). */
+int32_t tdna_init(int32_t device, tdna_ctx **out);
+int32_t tdna_shutdown(tdna_ctx *ctx);
+const char *tdna_last_error(void);
+/* The context's CUDA stream (a cudaStream_t) so that a caller can order its own work/events on it. */
+void *tdna_stream(tdna_ctx *ctx);
+/* Bytes of HBM the library may use for device-resident N x N results (default 64 GiB). */
+int32_t tdna_set_memory_budget(tdna_ctx *ctx, int64_t bytes);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t tdna_launch_count(tdna_ctx *ctx);
+
+/* ---- alignment ------------------------------------------------------------------------ */
+/* symbols: n rows of `row_stride` bytes, alphabet after Sequence.changeSequence
+ * (Common/DNA/Sequence.java:751-853): ACGT RYKMSWBDHVN - _ ? ; lengths[i] <= L is the row's own
+ * length (shorter rows behave as '?'-padded: the reference loops to min(len1,len2),
+ * Sequence.java:1326-1327); lengths may be NULL (all L).  The symbols are copied to the device
+ * and packed there into bit-planes; nothing of the caller's memory is retained. */
+int32_t tdna_alignment_create(tdna_ctx *ctx, const uint8_t *symbols, int64_t n, int32_t L,
+                              int64_t row_stride, const int32_t *lengths, tdna_aln **out);
+int32_t tdna_alignment_destroy(tdna_aln *aln);
+/* Labels per row, all computed by the host layer from the names:
+ *   species_id   : id of getSpeciesName() (Sequence.java:446-450), -1 = null (unnamed)
+ *   genus_id     : id of getGenusName() (:453), any int (the empty genus is an id too)
+ *   epithet_rank : rank of getSpeciesNameOnly() (:458) under String.compareTo (equal strings equal rank)
+ *   fullname_rank: rank of getFullName() under String.compareTo (equal strings equal rank)
+ * Needed by tdna_best_match / tdna_class_distances only. */
+int32_t tdna_alignment_set_labels(tdna_aln *aln, const int32_t *species_id, const int32_t *genus_id,
+                                  const int32_t *epithet_rank, const int32_t *fullname_rank);
+/* The three Sequence statics (Sequence.java:53-66, setters :86-136). Re-packs the planes. */
+int32_t tdna_set_config(tdna_aln *aln, int32_t mode, int32_t min_overlap, int32_t ambiguous_allowed);
+/* Multi-GPU: this context computes query rows [row_begin,row_end) only (all columns); results for
+ * other rows are left untouched.  Default: all rows.  See DESIGN.md "Multi-GPU". */
+int32_t tdna_set_row_range(tdna_aln *aln, int64_t row_begin, int64_t row_end);
+
+/* ---- per-pair / per-row (Sequence.*, SortedSequenceList, QuerySequence) ----------------- */
+/* Sequence.getPairwiseNoBuffer / getSharedLength / countIdentical / countTransversions /
+ * getK2PDistance (Sequence.java:1322-1717): one pair, a one-warp launch. counts or d may be NULL. */
+int32_t tdna_pair(tdna_aln *aln, int64_t i, int64_t j, tdna_counts *counts, double *d);
+/* d[j] = query.getPairwise(seq_j) for all j (what SortedSequenceList.sortAgainst evaluates,
+ * SortedSequenceList.java:104-118); shared may be NULL. */
+int32_t tdna_row_distances(tdna_aln *aln, int64_t q, double *d, int32_t *shared);
+
+/* ---- full matrix (config C2; Cluster.java:605-626 prints one per cluster) ---------------- */
+/* d: (row_end-row_begin) x n doubles, row-major, ld = n.  counts (optional): same shape. */
+int32_t tdna_matrix(tdna_aln *aln, double *d, tdna_counts *counts);
+/* Device-resident variant: computes into library memory (TDNA_E_TOO_LARGE if over budget);
+ * *d_dev receives the device pointer (valid until the alignment/config changes). */
+int32_t tdna_matrix_compute(tdna_aln *aln, const double **d_dev);
+
+/* ---- Best Match / Best Close Match / All Species Barcodes -------------------------------- */
+/* out: n records (only rows in the row range are written).  Streams row bands through HBM when
+ * the N x N matrix exceeds the budget, so n = 1,000,000 works. */
+int32_t tdna_best_match(tdna_aln *aln, tdna_row_result *out);
+/* Same, results left on the device; *out_dev receives the device pointer to n records. */
+int32_t tdna_best_match_compute(tdna_aln *aln, const tdna_row_result **out_dev);
+
+/* ---- Pairwise Summary / threshold percentile --------------------------------------------- */
+/* All distances of one PairwiseDistribution class as (float)d, -1 dropped, UNSORTED multiset
+ * (PairwiseDistribution.java:77-103, 161-203):
+ *   INTRA: unordered named conspecific pairs, once per pair (twice when the two full names are equal, :172)
+ *   INTER: same genus id, different epithet, once per pair (:191-198)
+ * Two-call protocol: with out == NULL only *n_out is written (the count).  */
+int32_t tdna_class_distances(tdna_aln *aln, int32_t klass, float *out, int64_t cap, int64_t *n_out);
+
+/* ---- Cluster ---------------------------------------------------------------------------- */
+/* All unordered pairs i<j with 0 <= d <= t (Cluster.java:797-804), unsorted.  Two-call protocol
+ * as above (ii == NULL -> count only). */
+int32_t tdna_edges_below(tdna_aln *aln, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap,
+                         int64_t *n_out);
+
+/* ---- SpeciesDetail ----------------------------------------------------- */
+/* has_valid[i] = 1 iff some OTHER row of the same species has getSharedLength >= minOverlap
+ * (SpeciesDetail.getSequencesWithValidConspecificsCount, Common/DNA/SpeciesDetail.java:78-95). */
+int32_t tdna_valid_conspecifics(tdna_aln *aln, uint8_t *has_valid);
+
+/* ---- progress / cancel (DelayCallback, Common/DelayCallback.java:34-56) -------------------- */
+typedef void (*tdna_progress_fn)(int64_t done, int64_t total, void *user);
+int32_t tdna_set_progress(tdna_ctx *ctx, tdna_progress_fn fn, void *user);
+int32_t tdna_cancel(tdna_ctx *ctx);
+
+/* ---- measurement helpers (bench.py; not part of the drop-in surface) ---------------------- */
+/* Launches only the count+distance kernel over the current row range into the resident matrix
+ * `reps` times and returns the mean device time per launch in milliseconds (CUDA events on the
+ * context's stream). */
+int32_t tdna_time_matrix_kernel(tdna_aln *aln, int32_t reps, float *ms_per_launch);
+/* Integer-pipe micro-benchmarks: results/s of dependent-free POPC and LOP3 streams over all SMs. */
+int32_t tdna_measure_int_peaks(tdna_ctx *ctx, double *popc_per_s, double *lop3_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAXONDNA_CUDA_H */

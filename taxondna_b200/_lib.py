@@ -1,0 +1,234 @@
+"""ctypes binding of the C ABI in include/taxondna_cuda.h (the same entry points the Java host
+layer binds through Panama FFM -- see INTEGRATION.md).  No CPU fallback: if the CUDA library is
+missing or no GPU is visible, every compute path raises."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtaxondna_cuda.so")
+
+PDM_UNCORRECTED, PDM_K2P, PDM_TRANS_ONLY = 0, 1, 2
+PD_INTRA, PD_INTER = 0, 1
+ROW_SELF_VALID, ROW_NONFINITE = 1, 2
+
+
+class TdnaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("taxondna_cuda error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Counts(ctypes.Structure):
+    _fields_ = [("shared", ctypes.c_int32), ("c1", ctypes.c_int32), ("c2", ctypes.c_int32), ("c3", ctypes.c_int32)]
+
+
+COUNTS_DTYPE = np.dtype([("shared", "<i4"), ("c1", "<i4"), ("c2", "<i4"), ("c3", "<i4")])
+
+ROW_RESULT_DTYPE = np.dtype([
+    ("d_best", "<f8"), ("d_con", "<f8"), ("d_allo", "<f8"), ("d_other", "<f8"),
+    ("best", "<i4"), ("con", "<i4"), ("allo", "<i4"), ("other", "<i4"),
+    ("shared_con", "<i4"), ("shared_allo", "<i4"),
+    ("tie_count", "<i4"), ("tie_species_min", "<i4"), ("tie_species_max", "<i4"), ("tie_unnamed", "<i4"),
+    ("block_count", "<i4"),
+    ("near_best", "<i4"), ("near_con", "<i4"), ("near_allo", "<i4"), ("near_other", "<i4"),
+    ("unnamed_at_con", "<i4"), ("unnamed_at_allo", "<i4"), ("unnamed_at_other", "<i4"),
+    ("n_valid", "<i4"), ("flags", "<i4"), ("reserved", "<i4"),
+], align=True)
+assert ROW_RESULT_DTYPE.itemsize == 120, ROW_RESULT_DTYPE.itemsize
+
+# every symbol include/taxondna_cuda.h declares (tests/test_abi.py checks the .so exports them all)
+EXPORTS = [
+    "tdna_abi_version", "tdna_init", "tdna_shutdown", "tdna_last_error", "tdna_stream", "tdna_set_memory_budget",
+    "tdna_launch_count", "tdna_alignment_create", "tdna_alignment_destroy", "tdna_alignment_set_labels",
+    "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_row_distances", "tdna_matrix", "tdna_matrix_compute",
+    "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
+    "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
+]
+
+PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
+
+_lib = None
+
+
+def load():
+    """Loads libtaxondna_cuda.so (built in-tree by __graft_entry__.build / csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TdnaError(-1, "CUDA library not built: %s is missing (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                            "there is no CPU fallback" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+    L.tdna_abi_version.restype = i32
+    L.tdna_last_error.restype = ctypes.c_char_p
+    L.tdna_init.argtypes = [i32, ctypes.POINTER(vp)]
+    L.tdna_shutdown.argtypes = [vp]
+    L.tdna_stream.argtypes = [vp]
+    L.tdna_stream.restype = vp
+    L.tdna_set_memory_budget.argtypes = [vp, i64]
+    L.tdna_launch_count.argtypes = [vp]
+    L.tdna_launch_count.restype = i64
+    L.tdna_alignment_create.argtypes = [vp, vp, i64, i32, i64, vp, ctypes.POINTER(vp)]
+    L.tdna_alignment_destroy.argtypes = [vp]
+    L.tdna_alignment_set_labels.argtypes = [vp, vp, vp, vp, vp]
+    L.tdna_set_config.argtypes = [vp, i32, i32, i32]
+    L.tdna_set_row_range.argtypes = [vp, i64, i64]
+    L.tdna_pair.argtypes = [vp, i64, i64, ctypes.POINTER(Counts), ctypes.POINTER(dbl)]
+    L.tdna_row_distances.argtypes = [vp, i64, vp, vp]
+    L.tdna_matrix.argtypes = [vp, vp, vp]
+    L.tdna_matrix_compute.argtypes = [vp, ctypes.POINTER(vp)]
+    L.tdna_best_match.argtypes = [vp, vp]
+    L.tdna_best_match_compute.argtypes = [vp, ctypes.POINTER(vp)]
+    L.tdna_class_distances.argtypes = [vp, i32, vp, i64, ctypes.POINTER(i64)]
+    L.tdna_edges_below.argtypes = [vp, dbl, vp, vp, vp, i64, ctypes.POINTER(i64)]
+    L.tdna_valid_conspecifics.argtypes = [vp, vp]
+    L.tdna_set_progress.argtypes = [vp, PROGRESS_FN, vp]
+    L.tdna_cancel.argtypes = [vp]
+    L.tdna_time_matrix_kernel.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
+    L.tdna_measure_int_peaks.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise TdnaError(rc, load().tdna_last_error().decode("utf-8", "replace"))
+
+
+class Context:
+    """tdna_ctx: one per GPU per process."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        self.h = ctypes.c_void_p()
+        check(self.L.tdna_init(device, ctypes.byref(self.h)))
+        self.device = device
+        self._cb = None
+
+    def close(self):
+        if self.h:
+            self.L.tdna_shutdown(self.h)
+            self.h = ctypes.c_void_p()
+
+    def stream_ptr(self):
+        return self.L.tdna_stream(self.h)
+
+    def set_memory_budget(self, nbytes):
+        check(self.L.tdna_set_memory_budget(self.h, int(nbytes)))
+
+    def launch_count(self):
+        return int(self.L.tdna_launch_count(self.h))
+
+    def set_progress(self, fn):
+        self._cb = PROGRESS_FN(lambda done, total, user: fn(done, total)) if fn else PROGRESS_FN()
+        check(self.L.tdna_set_progress(self.h, self._cb, None))
+
+    def cancel(self):
+        check(self.L.tdna_cancel(self.h))
+
+    def measure_int_peaks(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        check(self.L.tdna_measure_int_peaks(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+
+class Alignment:
+    """tdna_aln over a normalised symbol matrix (numpy uint8 [n, L])."""
+
+    def __init__(self, ctx, symbols, lengths=None):
+        self.ctx, self.L = ctx, ctx.L
+        symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+        self.n, self.ncols = symbols.shape
+        self.h = ctypes.c_void_p()
+        lp = None
+        if lengths is not None:
+            lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+            lp = lengths.ctypes.data
+        check(self.L.tdna_alignment_create(ctx.h, symbols.ctypes.data, self.n, self.ncols, symbols.strides[0], lp,
+                                           ctypes.byref(self.h)))
+        self.row_begin, self.row_end = 0, self.n
+
+    def close(self):
+        if self.h:
+            self.L.tdna_alignment_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def set_labels(self, species_id, genus_id, epithet_rank, fullname_rank):
+        arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (species_id, genus_id, epithet_rank, fullname_rank)]
+        assert all(a.shape == (self.n,) for a in arrs)
+        check(self.L.tdna_alignment_set_labels(self.h, *[a.ctypes.data for a in arrs]))
+
+    def set_config(self, mode, min_overlap, ambiguous_allowed=True):
+        check(self.L.tdna_set_config(self.h, int(mode), int(min_overlap), 1 if ambiguous_allowed else 0))
+
+    def set_row_range(self, b, e):
+        check(self.L.tdna_set_row_range(self.h, int(b), int(e)))
+        self.row_begin, self.row_end = int(b), int(e)
+
+    def pair(self, i, j):
+        c, d = Counts(), ctypes.c_double()
+        check(self.L.tdna_pair(self.h, i, j, ctypes.byref(c), ctypes.byref(d)))
+        return (c.shared, c.c1, c.c2, c.c3), d.value
+
+    def row_distances(self, q, want_shared=True):
+        d = np.empty(self.n, dtype=np.float64)
+        sh = np.empty(self.n, dtype=np.int32) if want_shared else None
+        check(self.L.tdna_row_distances(self.h, q, d.ctypes.data, sh.ctypes.data if want_shared else None))
+        return d, sh
+
+    def matrix(self, counts=False, out=None):
+        rows = self.row_end - self.row_begin
+        d = out if out is not None else np.empty((rows, self.n), dtype=np.float64)
+        c = np.empty((rows, self.n), dtype=COUNTS_DTYPE) if counts else None
+        check(self.L.tdna_matrix(self.h, d.ctypes.data, c.ctypes.data if counts else None))
+        return (d, c) if counts else d
+
+    def matrix_compute(self):
+        p = ctypes.c_void_p()
+        check(self.L.tdna_matrix_compute(self.h, ctypes.byref(p)))
+        return p.value
+
+    def best_match(self, out=None):
+        r = out if out is not None else np.zeros(self.n, dtype=ROW_RESULT_DTYPE)
+        check(self.L.tdna_best_match(self.h, r.ctypes.data))
+        return r
+
+    def best_match_into(self, ptr):
+        """ptr: host or device address of n tdna_row_result records."""
+        check(self.L.tdna_best_match(self.h, ptr))
+
+    def best_match_compute(self):
+        p = ctypes.c_void_p()
+        check(self.L.tdna_best_match_compute(self.h, ctypes.byref(p)))
+        return p.value
+
+    def class_distances(self, klass):
+        n = ctypes.c_int64()
+        check(self.L.tdna_class_distances(self.h, klass, None, 0, ctypes.byref(n)))
+        out = np.empty(max(n.value, 1), dtype=np.float32)
+        m = ctypes.c_int64()
+        check(self.L.tdna_class_distances(self.h, klass, out.ctypes.data, n.value, ctypes.byref(m)))
+        assert m.value == n.value
+        return out[: n.value]
+
+    def edges_below(self, t):
+        n = ctypes.c_int64()
+        check(self.L.tdna_edges_below(self.h, float(t), None, None, None, 0, ctypes.byref(n)))
+        k = max(n.value, 1)
+        ii, jj, dd = np.empty(k, np.int32), np.empty(k, np.int32), np.empty(k, np.float64)
+        m = ctypes.c_int64()
+        check(self.L.tdna_edges_below(self.h, float(t), ii.ctypes.data, jj.ctypes.data, dd.ctypes.data, n.value, ctypes.byref(m)))
+        return ii[: n.value], jj[: n.value], dd[: n.value]
+
+    def valid_conspecifics(self):
+        v = np.zeros(self.n, dtype=np.uint8)
+        check(self.L.tdna_valid_conspecifics(self.h, v.ctypes.data))
+        return v
+
+    def time_matrix_kernel(self, reps=10):
+        ms = ctypes.c_float()
+        check(self.L.tdna_time_matrix_kernel(self.h, reps, ctypes.byref(ms)))
+        return ms.value

@@ -1,0 +1,711 @@
+// C ABI of the engine (include/taxondna_cuda.h): context/alignment lifetime, band scheduling of the
+// N x N pair space through HBM, kernel launches.  No CPU arithmetic path exists here by design.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tdna_kernels.cuh"
+
+using namespace tdna;
+
+namespace {
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(TDNA_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+#define TRY(call)              \
+    do {                       \
+        int rc_ = (call);      \
+        if (rc_ != TDNA_OK) return rc_; \
+    } while (0)
+
+int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+}  // namespace
+
+struct tdna_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t budget = 64ll << 30;
+    int64_t launches = 0;
+    int sm_count = 148;
+    tdna_progress_fn progress = nullptr;
+    void *progress_user = nullptr;
+    volatile int cancel = 0;
+    unsigned long long *d_counter = nullptr;
+};
+
+struct tdna_aln {
+    tdna_ctx *ctx = nullptr;
+    int64_t n = 0, npad = 0;
+    int L = 0, W = 0, sym_stride = 0;
+    uint8_t *d_sym = nullptr;
+    int32_t *d_len = nullptr;
+    uint32_t *d_planes = nullptr;
+    size_t planes_words = 0;
+    int mode = TDNA_PDM_UNCORRECTED, min_overlap = 300, ambig = 1, kmode = KM_P_AMBIG, P = 0;
+    bool packed = false;
+    int32_t *d_species = nullptr, *d_genus = nullptr, *d_epi = nullptr, *d_full = nullptr;
+    bool has_labels = false;
+    int64_t row_begin = 0, row_end = 0;
+    double *d_mat = nullptr;
+    int64_t mat_cap = 0;  // doubles
+    int64_t ld = 0;
+    bool mat_valid = false;  // d_mat holds the whole row range for the current config
+    tdna_row_result *d_res = nullptr;
+    int64_t *d_prefix = nullptr;
+    int64_t prefix_cap = 0;
+};
+
+namespace {
+
+void build_lut(uint16_t *lut) {
+    for (int i = 0; i < 256; i++) lut[i] = 0x8000;
+    auto set = [&](char ch, int mask) {  // mask: A=1 C=2 T=4 G=8 (Sequence.getint)
+        uint32_t b = SB_V | SB_LET;
+        if (mask & 1) b |= SB_A;
+        if (mask & 2) b |= SB_C;
+        if (mask & 4) b |= SB_T;
+        if (mask & 8) b |= SB_G;
+        lut[(unsigned char)ch] = (uint16_t)b;
+    };
+    set('A', 1); set('C', 2); set('T', 4); set('G', 8);
+    set('R', 9); set('Y', 6); set('K', 12); set('M', 3); set('S', 10); set('W', 5);
+    set('B', 14); set('D', 13); set('H', 7); set('V', 11); set('N', 15);
+    // purine {A,G,R} / pyrimidine {C,T,Y} classes and the K2P within-class code
+    lut['A'] |= SB_U | SB_PU;
+    lut['G'] |= SB_U | SB_PU | SB_C0;
+    lut['R'] |= SB_U | SB_PU | SB_C1;
+    lut['C'] |= SB_U;
+    lut['T'] |= SB_U | SB_C0;
+    lut['Y'] |= SB_U | SB_C1;
+    lut['-'] = SB_D | SB_V;
+    lut['_'] = 0;
+    lut['?'] = 0;
+}
+
+template <int KM> PlaneBits plane_bits() {
+    PlaneBits pb = {};
+    for (int i = 0; i < ModeTraits<KM>::P; i++) pb.b[i] = ModeTraits<KM>::bits[i];
+    return pb;
+}
+
+int pack(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
+    int km;
+    if (a->mode == TDNA_PDM_K2P) km = KM_K2P;
+    else if (a->mode == TDNA_PDM_TRANS_ONLY) km = KM_TRANS;
+    else km = a->ambig ? KM_P_AMBIG : KM_P_NOAMBIG;
+    PlaneBits pb;
+    int P;
+    switch (km) {
+        case KM_P_AMBIG: pb = plane_bits<KM_P_AMBIG>(); P = ModeTraits<KM_P_AMBIG>::P; break;
+        case KM_P_NOAMBIG: pb = plane_bits<KM_P_NOAMBIG>(); P = ModeTraits<KM_P_NOAMBIG>::P; break;
+        case KM_K2P: pb = plane_bits<KM_K2P>(); P = ModeTraits<KM_K2P>::P; break;
+        default: pb = plane_bits<KM_TRANS>(); P = ModeTraits<KM_TRANS>::P; break;
+    }
+    size_t words = (size_t)a->npad * P * a->W;
+    if (words > a->planes_words) {
+        if (a->d_planes) CU(cudaFree(a->d_planes));
+        a->d_planes = nullptr;
+        CU(cudaMalloc(&a->d_planes, words * 4));
+        a->planes_words = words;
+    }
+    int *d_err = reinterpret_cast<int *>(c->d_counter);
+    CU(cudaMemsetAsync(d_err, 0, 8, c->stream));
+    int64_t total = a->npad * a->W;
+    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->npad, a->sym_stride, a->W, P, pb,
+                                                                       a->d_planes, d_err);
+    c->launches++;
+    CU(cudaGetLastError());
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (err) return fail(TDNA_E_SYMBOL, "a symbol outside the normalised alphabet ACGT RYKMSWBDHVN - _ ?");
+    a->kmode = km;
+    a->P = P;
+    a->packed = true;
+    a->mat_valid = false;
+    return TDNA_OK;
+}
+
+template <int KM, bool WC> int launch_tiles_t(tdna_aln *a, int64_t b0, int64_t b1, bool symmetric, double *out, int64_t ld, tdna_counts *counts) {
+    using Cfg = TileCfg<KM>;
+    tdna_ctx *c = a->ctx;
+    TileParams p;
+    p.planes = a->d_planes;
+    p.W = a->W;
+    p.n = a->n;
+    p.min_overlap = a->min_overlap;
+    p.row_begin = b0;
+    p.row_end = b1;
+    p.symmetric = symmetric ? 1 : 0;
+    p.nct = (int)((a->n + Cfg::TN - 1) / Cfg::TN);
+    int nrt = (int)((b1 - b0 + TM - 1) / TM);
+    p.tile_prefix = nullptr;
+    if (symmetric) {
+        std::vector<int64_t> prefix(nrt + 1);
+        prefix[0] = 0;
+        for (int t = 0; t < nrt; t++) {
+            int64_t first = (int64_t)t * (TM / Cfg::TN);
+            prefix[t + 1] = prefix[t] + (p.nct > first ? p.nct - first : 0);
+        }
+        if (a->prefix_cap < nrt + 1) {
+            if (a->d_prefix) CU(cudaFree(a->d_prefix));
+            a->d_prefix = nullptr;
+            CU(cudaMalloc(&a->d_prefix, (size_t)(nrt + 1) * 8));
+            a->prefix_cap = nrt + 1;
+        }
+        CU(cudaMemcpyAsync(a->d_prefix, prefix.data(), (size_t)(nrt + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));  // prefix is a stack-lifetime host buffer
+        p.tile_prefix = a->d_prefix;
+        p.num_tiles = prefix[nrt];
+    } else {
+        p.num_tiles = (int64_t)nrt * p.nct;
+    }
+    p.out = out;
+    p.ld = ld;
+    p.counts = counts;
+    auto kern = count_tile_kernel<KM, WC>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    int64_t grid = p.num_tiles < c->sm_count ? p.num_tiles : c->sm_count;
+    if (grid < 1) return TDNA_OK;
+    kern<<<(unsigned)grid, 256, Cfg::SMEM, c->stream>>>(p);
+    c->launches++;
+    CU(cudaGetLastError());
+    return TDNA_OK;
+}
+
+int launch_tiles(tdna_aln *a, int64_t b0, int64_t b1, bool symmetric, double *out, int64_t ld, tdna_counts *counts) {
+    switch (a->kmode) {
+        case KM_P_AMBIG: return counts ? launch_tiles_t<KM_P_AMBIG, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_t<KM_P_AMBIG, false>(a, b0, b1, symmetric, out, ld, counts);
+        case KM_P_NOAMBIG: return counts ? launch_tiles_t<KM_P_NOAMBIG, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_t<KM_P_NOAMBIG, false>(a, b0, b1, symmetric, out, ld, counts);
+        case KM_K2P: return counts ? launch_tiles_t<KM_K2P, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_t<KM_K2P, false>(a, b0, b1, symmetric, out, ld, counts);
+        default: return counts ? launch_tiles_t<KM_TRANS, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_t<KM_TRANS, false>(a, b0, b1, symmetric, out, ld, counts);
+    }
+}
+
+int ensure_packed(tdna_aln *a) {
+    if (!a) return fail(TDNA_E_ARG, "null alignment");
+    if (!a->packed) TRY(pack(a));
+    return TDNA_OK;
+}
+
+// rows per band so that band x ld doubles fit the budget (multiple of 128, at least 128)
+int64_t band_rows_for(tdna_aln *a) {
+    int64_t rows = a->row_end - a->row_begin;
+    int64_t maxb = a->ctx->budget / (a->ld * 8);
+    maxb = maxb / TM * TM;
+    if (maxb < TM) maxb = TM;
+    return rows < maxb ? rows : maxb;
+}
+
+int ensure_mat(tdna_aln *a, int64_t rows) {
+    int64_t need = round_up(rows, TM) * a->ld;
+    if (need > a->mat_cap) {
+        if (a->d_mat) CU(cudaFree(a->d_mat));
+        a->d_mat = nullptr;
+        a->mat_cap = 0;
+        CU(cudaMalloc(&a->d_mat, (size_t)need * 8));
+        a->mat_cap = need;
+        a->mat_valid = false;
+    }
+    return TDNA_OK;
+}
+
+// Runs the count kernel band by band over the row range and hands each finished band (device
+// resident) to `consume(b0, b1)`.  When the whole matrix is one band and the row range is
+// everything, only the upper-triangle tiles are computed and mirrored.
+template <class F> int for_each_band(tdna_aln *a, F consume) {
+    TRY(ensure_packed(a));
+    tdna_ctx *c = a->ctx;
+    int64_t rows = a->row_end - a->row_begin;
+    if (rows <= 0) return TDNA_OK;
+    if (a->row_begin % TM != 0) return fail(TDNA_E_ARG, "row_begin must be a multiple of 128");
+    int64_t band = band_rows_for(a);
+    TRY(ensure_mat(a, band));
+    bool whole = (band == rows);
+    for (int64_t b0 = a->row_begin; b0 < a->row_end; b0 += band) {
+        int64_t b1 = b0 + band < a->row_end ? b0 + band : a->row_end;
+        if (c->cancel) { c->cancel = 0; return fail(TDNA_E_CANCELLED, "cancelled"); }
+        if (!(whole && a->mat_valid)) {
+            bool symmetric = whole && a->row_begin == 0 && a->row_end == a->n;
+            TRY(launch_tiles(a, b0, b1, symmetric, a->d_mat, a->ld, nullptr));
+            a->mat_valid = whole;
+        }
+        TRY(consume(b0, b1));
+        if (c->progress) {
+            CU(cudaStreamSynchronize(c->stream));
+            c->progress(b1 - a->row_begin, rows, c->progress_user);
+        }
+    }
+    return TDNA_OK;
+}
+
+int need_labels(tdna_aln *a) {
+    if (!a->has_labels) return fail(TDNA_E_STATE, "tdna_alignment_set_labels has not been called");
+    return TDNA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t tdna_abi_version(void) { return TDNA_ABI_VERSION; }
+const char *tdna_last_error(void) { return g_err.c_str(); }
+
+int32_t tdna_init(int32_t device, tdna_ctx **out) {
+    if (!out) return fail(TDNA_E_ARG, "out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(TDNA_E_CUDA, std::string("no CUDA device: this library has no CPU fallback (") + cudaGetErrorString(e) + ")");
+    if (device < 0 || device >= count) return fail(TDNA_E_ARG, "device out of range");
+    CU(cudaSetDevice(device));
+    tdna_ctx *c = new tdna_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->d_counter, 64));
+    uint16_t lut[256];
+    build_lut(lut);
+    CU(cudaMemcpyToSymbol(c_symlut, lut, sizeof(lut)));
+    *out = c;
+    return TDNA_OK;
+}
+
+int32_t tdna_shutdown(tdna_ctx *c) {
+    if (!c) return TDNA_OK;
+    cudaSetDevice(c->device);
+    if (c->d_counter) cudaFree(c->d_counter);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return TDNA_OK;
+}
+
+void *tdna_stream(tdna_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int32_t tdna_set_memory_budget(tdna_ctx *c, int64_t bytes) {
+    if (!c || bytes < (1 << 20)) return fail(TDNA_E_ARG, "bad budget");
+    c->budget = bytes;
+    return TDNA_OK;
+}
+int64_t tdna_launch_count(tdna_ctx *c) { return c ? c->launches : 0; }
+
+int32_t tdna_set_progress(tdna_ctx *c, tdna_progress_fn fn, void *user) {
+    if (!c) return fail(TDNA_E_ARG, "null ctx");
+    c->progress = fn;
+    c->progress_user = user;
+    return TDNA_OK;
+}
+int32_t tdna_cancel(tdna_ctx *c) {
+    if (!c) return fail(TDNA_E_ARG, "null ctx");
+    c->cancel = 1;
+    return TDNA_OK;
+}
+
+int32_t tdna_alignment_create(tdna_ctx *c, const uint8_t *symbols, int64_t n, int32_t L, int64_t row_stride, const int32_t *lengths,
+                              tdna_aln **out) {
+    if (!c || !symbols || !out) return fail(TDNA_E_ARG, "null argument");
+    if (n < 1 || n > 0x7fffffff) return fail(TDNA_E_ARG, "n out of range");
+    if (L < 1 || L > 65535) return fail(TDNA_E_ARG, "L must be in [1, 65535] (two 16-bit counts share an accumulator)");
+    if (row_stride < L) return fail(TDNA_E_ARG, "row_stride < L");
+    CU(cudaSetDevice(c->device));
+    tdna_aln *a = new tdna_aln();
+    a->ctx = c;
+    a->n = n;
+    a->L = L;
+    a->W = (L + 31) / 32;
+    a->sym_stride = a->W * 32;
+    a->npad = round_up(n, TM);
+    a->ld = round_up(n, 16);
+    a->row_begin = 0;
+    a->row_end = n;
+    CU(cudaMalloc(&a->d_sym, (size_t)n * a->sym_stride));
+    CU(cudaMemsetAsync(a->d_sym, '?', (size_t)n * a->sym_stride, c->stream));
+    CU(cudaMemcpy2DAsync(a->d_sym, a->sym_stride, symbols, row_stride, L, n, cudaMemcpyDefault, c->stream));
+    CU(cudaMalloc(&a->d_len, (size_t)n * 4));
+    if (lengths) {
+        CU(cudaMemcpyAsync(a->d_len, lengths, (size_t)n * 4, cudaMemcpyDefault, c->stream));
+    } else {
+        std::vector<int32_t> l((size_t)n, L);
+        CU(cudaMemcpyAsync(a->d_len, l.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    int rc = pack(a);
+    if (rc != TDNA_OK) {
+        tdna_alignment_destroy(a);
+        return rc;
+    }
+    *out = a;
+    return TDNA_OK;
+}
+
+int32_t tdna_alignment_destroy(tdna_aln *a) {
+    if (!a) return TDNA_OK;
+    cudaSetDevice(a->ctx->device);
+    cudaStreamSynchronize(a->ctx->stream);
+    void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_mat, a->d_res, a->d_prefix};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    delete a;
+    return TDNA_OK;
+}
+
+int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const int32_t *genus_id, const int32_t *epithet_rank,
+                                  const int32_t *fullname_rank) {
+    if (!a || !species_id || !genus_id || !epithet_rank || !fullname_rank) return fail(TDNA_E_ARG, "null argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    size_t bytes = (size_t)a->n * 4;
+    int32_t **dst[] = {&a->d_species, &a->d_genus, &a->d_epi, &a->d_full};
+    const int32_t *src[] = {species_id, genus_id, epithet_rank, fullname_rank};
+    for (int i = 0; i < 4; i++) {
+        if (!*dst[i]) CU(cudaMalloc(dst[i], bytes));
+        CU(cudaMemcpyAsync(*dst[i], src[i], bytes, cudaMemcpyDefault, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    a->has_labels = true;
+    return TDNA_OK;
+}
+
+int32_t tdna_set_config(tdna_aln *a, int32_t mode, int32_t min_overlap, int32_t ambiguous_allowed) {
+    if (!a) return fail(TDNA_E_ARG, "null alignment");
+    if (mode < 0 || mode > 2) return fail(TDNA_E_ARG, "mode must be 0, 1 or 2");
+    CU(cudaSetDevice(a->ctx->device));
+    bool repack = !a->packed || mode != a->mode || (mode == TDNA_PDM_UNCORRECTED && (ambiguous_allowed != 0) != (a->ambig != 0));
+    a->mode = mode;
+    a->min_overlap = min_overlap;
+    a->ambig = ambiguous_allowed ? 1 : 0;
+    a->mat_valid = false;
+    if (repack) TRY(pack(a));
+    return TDNA_OK;
+}
+
+int32_t tdna_set_row_range(tdna_aln *a, int64_t row_begin, int64_t row_end) {
+    if (!a || row_begin < 0 || row_end > a->n || row_begin > row_end) return fail(TDNA_E_ARG, "bad row range");
+    if (row_begin % TM != 0) return fail(TDNA_E_ARG, "row_begin must be a multiple of 128");
+    a->row_begin = row_begin;
+    a->row_end = row_end;
+    a->mat_valid = false;
+    return TDNA_OK;
+}
+
+static int row_query(tdna_aln *a, int64_t q, int64_t j0, int64_t j1, double *d_dev, int32_t *sh_dev, tdna_counts *cnt_dev) {
+    tdna_ctx *c = a->ctx;
+    unsigned grid = (unsigned)((j1 - j0 + 255) / 256);
+    switch (a->kmode) {
+        case KM_P_AMBIG: row_from_planes_kernel<KM_P_AMBIG><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, q, j0, j1, a->min_overlap, d_dev, sh_dev, cnt_dev); break;
+        case KM_P_NOAMBIG: row_from_planes_kernel<KM_P_NOAMBIG><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, q, j0, j1, a->min_overlap, d_dev, sh_dev, cnt_dev); break;
+        case KM_K2P: row_from_planes_kernel<KM_K2P><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, q, j0, j1, a->min_overlap, d_dev, sh_dev, cnt_dev); break;
+        default: row_from_planes_kernel<KM_TRANS><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, q, j0, j1, a->min_overlap, d_dev, sh_dev, cnt_dev); break;
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    return TDNA_OK;
+}
+
+int32_t tdna_pair(tdna_aln *a, int64_t i, int64_t j, tdna_counts *counts, double *d) {
+    TRY(ensure_packed(a));
+    if (i < 0 || j < 0 || i >= a->n || j >= a->n) return fail(TDNA_E_ARG, "index out of range");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    struct Scratch { double d; tdna_counts c; } *dev;
+    CU(cudaMalloc(&dev, sizeof(Scratch)));
+    int rc = row_query(a, i, j, j + 1, &dev->d, nullptr, &dev->c);
+    if (rc == TDNA_OK) {
+        Scratch h;
+        cudaError_t e = cudaMemcpyAsync(&h, dev, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
+        else {
+            if (d) *d = h.d;
+            if (counts) *counts = h.c;
+        }
+    }
+    cudaFree(dev);
+    return rc;
+}
+
+int32_t tdna_row_distances(tdna_aln *a, int64_t q, double *d, int32_t *shared) {
+    TRY(ensure_packed(a));
+    if (q < 0 || q >= a->n || !d) return fail(TDNA_E_ARG, "bad argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    double *dd;
+    int32_t *ds = nullptr;
+    CU(cudaMalloc(&dd, (size_t)a->n * 8));
+    if (shared) CU(cudaMalloc(&ds, (size_t)a->n * 4));
+    int rc = row_query(a, q, 0, a->n, dd, ds, nullptr);
+    if (rc == TDNA_OK) {
+        cudaError_t e = cudaMemcpyAsync(d, dd, (size_t)a->n * 8, cudaMemcpyDefault, c->stream);
+        if (e == cudaSuccess && shared) e = cudaMemcpyAsync(shared, ds, (size_t)a->n * 4, cudaMemcpyDefault, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(dd);
+    if (ds) cudaFree(ds);
+    return rc;
+}
+
+int32_t tdna_matrix(tdna_aln *a, double *d, tdna_counts *counts) {
+    if (!a || !d) return fail(TDNA_E_ARG, "null argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    if (counts) {  // diagnostic path: rectangular bands with the integer tuples as well
+        TRY(ensure_packed(a));
+        int64_t band = band_rows_for(a);
+        int64_t cb = c->budget / (a->n * 16) / TM * TM;
+        if (cb < TM) cb = TM;
+        if (band > cb) band = cb;
+        TRY(ensure_mat(a, band));
+        a->mat_valid = false;
+        tdna_counts *dc;
+        CU(cudaMalloc(&dc, (size_t)band * a->n * sizeof(tdna_counts)));
+        int rc = TDNA_OK;
+        for (int64_t b0 = a->row_begin; b0 < a->row_end && rc == TDNA_OK; b0 += band) {
+            int64_t b1 = b0 + band < a->row_end ? b0 + band : a->row_end;
+            rc = launch_tiles(a, b0, b1, false, a->d_mat, a->ld, dc);
+            if (rc != TDNA_OK) break;
+            cudaError_t e = cudaMemcpy2DAsync(d + (b0 - a->row_begin) * a->n, (size_t)a->n * 8, a->d_mat, (size_t)a->ld * 8, (size_t)a->n * 8,
+                                              (size_t)(b1 - b0), cudaMemcpyDefault, c->stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(counts + (b0 - a->row_begin) * a->n, dc, (size_t)(b1 - b0) * a->n * sizeof(tdna_counts), cudaMemcpyDefault, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
+        }
+        cudaFree(dc);
+        return rc;
+    }
+    TRY(for_each_band(a, [&](int64_t b0, int64_t b1) -> int {
+        CU(cudaMemcpy2DAsync(d + (b0 - a->row_begin) * a->n, (size_t)a->n * 8, a->d_mat, (size_t)a->ld * 8, (size_t)a->n * 8, (size_t)(b1 - b0),
+                             cudaMemcpyDefault, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return TDNA_OK;
+    }));
+    return TDNA_OK;
+}
+
+int32_t tdna_matrix_compute(tdna_aln *a, const double **d_dev) {
+    if (!a) return fail(TDNA_E_ARG, "null alignment");
+    CU(cudaSetDevice(a->ctx->device));
+    TRY(ensure_packed(a));
+    if (band_rows_for(a) != a->row_end - a->row_begin) return fail(TDNA_E_TOO_LARGE, "matrix exceeds the memory budget");
+    TRY(for_each_band(a, [&](int64_t, int64_t) -> int { return TDNA_OK; }));
+    if (d_dev) *d_dev = a->d_mat;
+    return TDNA_OK;
+}
+
+int32_t tdna_best_match_compute(tdna_aln *a, const tdna_row_result **out_dev) {
+    if (!a) return fail(TDNA_E_ARG, "null alignment");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(need_labels(a));
+    if (!a->d_res) CU(cudaMalloc(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+    TRY(for_each_band(a, [&](int64_t b0, int64_t b1) -> int {
+        row_summary_kernel<<<(unsigned)(b1 - b0), 256, 0, c->stream>>>(a->d_mat, a->ld, a->n, b0, a->d_species, a->d_res);
+        c->launches++;
+        CU(cudaGetLastError());
+        return TDNA_OK;
+    }));
+    int64_t rows = a->row_end - a->row_begin;
+    if (rows > 0) {
+        unsigned grid = (unsigned)((rows * 2 + 255) / 256);
+        switch (a->kmode) {
+            case KM_P_AMBIG: fill_shared_kernel<KM_P_AMBIG><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, a->row_begin, a->row_end, a->d_res); break;
+            case KM_P_NOAMBIG: fill_shared_kernel<KM_P_NOAMBIG><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, a->row_begin, a->row_end, a->d_res); break;
+            case KM_K2P: fill_shared_kernel<KM_K2P><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, a->row_begin, a->row_end, a->d_res); break;
+            default: fill_shared_kernel<KM_TRANS><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, a->row_begin, a->row_end, a->d_res); break;
+        }
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    if (out_dev) *out_dev = a->d_res;
+    return TDNA_OK;
+}
+
+int32_t tdna_best_match(tdna_aln *a, tdna_row_result *out) {
+    if (!out) return fail(TDNA_E_ARG, "out is null");
+    TRY(tdna_best_match_compute(a, nullptr));
+    tdna_ctx *c = a->ctx;
+    int64_t rows = a->row_end - a->row_begin;
+    if (rows > 0)
+        CU(cudaMemcpyAsync(out + a->row_begin, a->d_res + a->row_begin, (size_t)rows * sizeof(tdna_row_result), cudaMemcpyDefault, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TDNA_OK;
+}
+
+int32_t tdna_class_distances(tdna_aln *a, int32_t klass, float *out, int64_t cap, int64_t *n_out) {
+    if (!a || !n_out) return fail(TDNA_E_ARG, "null argument");
+    if (klass != TDNA_PD_INTRA && klass != TDNA_PD_INTER) return fail(TDNA_E_ARG, "bad class");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(need_labels(a));
+    CU(cudaMemsetAsync(c->d_counter, 0, 8, c->stream));
+    float *dout = nullptr;
+    if (out && cap > 0) CU(cudaMalloc(&dout, (size_t)cap * 4));
+    int rc = for_each_band(a, [&](int64_t b0, int64_t b1) -> int {
+        unsigned gy = (unsigned)((a->n + 256 * 8 - 1) / (256 * 8));
+        if (gy > 65535) gy = 65535;
+        dim3 grid((unsigned)(b1 - b0), gy);
+        class_distances_kernel<<<grid, 256, 0, c->stream>>>(a->d_mat, a->ld, a->n, b0, b1 - b0, klass, a->d_species, a->d_genus, a->d_epi, a->d_full,
+                                                           dout, cap, c->d_counter);
+        c->launches++;
+        CU(cudaGetLastError());
+        return TDNA_OK;
+    });
+    unsigned long long cnt = 0;
+    if (rc == TDNA_OK) {
+        cudaError_t e = cudaMemcpyAsync(&cnt, c->d_counter, 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess && dout) {
+            int64_t m = (int64_t)cnt < cap ? (int64_t)cnt : cap;
+            e = cudaMemcpy(out, dout, (size_t)m * 4, cudaMemcpyDefault);
+        }
+        if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
+    }
+    if (dout) cudaFree(dout);
+    *n_out = (int64_t)cnt;
+    return rc;
+}
+
+int32_t tdna_edges_below(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out) {
+    if (!a || !n_out) return fail(TDNA_E_ARG, "null argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->d_counter, 0, 8, c->stream));
+    int32_t *di = nullptr, *dj = nullptr;
+    double *dd = nullptr;
+    bool want = ii && jj && d && cap > 0;
+    if (want) {
+        CU(cudaMalloc(&di, (size_t)cap * 4));
+        CU(cudaMalloc(&dj, (size_t)cap * 4));
+        CU(cudaMalloc(&dd, (size_t)cap * 8));
+    }
+    int rc = for_each_band(a, [&](int64_t b0, int64_t b1) -> int {
+        unsigned gy = (unsigned)((a->n + 256 * 8 - 1) / (256 * 8));
+        if (gy > 65535) gy = 65535;
+        dim3 grid((unsigned)(b1 - b0), gy);
+        edges_kernel<<<grid, 256, 0, c->stream>>>(a->d_mat, a->ld, a->n, b0, b1 - b0, t, di, dj, dd, cap, c->d_counter);
+        c->launches++;
+        CU(cudaGetLastError());
+        return TDNA_OK;
+    });
+    unsigned long long cnt = 0;
+    if (rc == TDNA_OK) {
+        cudaError_t e = cudaMemcpyAsync(&cnt, c->d_counter, 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess && want) {
+            int64_t m = (int64_t)cnt < cap ? (int64_t)cnt : cap;
+            e = cudaMemcpy(ii, di, (size_t)m * 4, cudaMemcpyDefault);
+            if (e == cudaSuccess) e = cudaMemcpy(jj, dj, (size_t)m * 4, cudaMemcpyDefault);
+            if (e == cudaSuccess) e = cudaMemcpy(d, dd, (size_t)m * 8, cudaMemcpyDefault);
+        }
+        if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
+    }
+    if (di) cudaFree(di);
+    if (dj) cudaFree(dj);
+    if (dd) cudaFree(dd);
+    *n_out = (int64_t)cnt;
+    return rc;
+}
+
+int32_t tdna_valid_conspecifics(tdna_aln *a, uint8_t *has_valid) {
+    if (!a || !has_valid) return fail(TDNA_E_ARG, "null argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(need_labels(a));
+    uint8_t *dv;
+    CU(cudaMalloc(&dv, (size_t)a->n));
+    CU(cudaMemsetAsync(dv, 0, (size_t)a->n, c->stream));
+    int rc = for_each_band(a, [&](int64_t b0, int64_t b1) -> int {
+        valid_consp_kernel<<<(unsigned)(b1 - b0), 256, 0, c->stream>>>(a->d_mat, a->ld, a->n, b0, a->d_species, dv);
+        c->launches++;
+        CU(cudaGetLastError());
+        return TDNA_OK;
+    });
+    if (rc == TDNA_OK) {
+        int64_t rows = a->row_end - a->row_begin;
+        cudaError_t e = cudaMemcpyAsync(has_valid + a->row_begin, dv + a->row_begin, (size_t)rows, cudaMemcpyDefault, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(dv);
+    return rc;
+}
+
+int32_t tdna_time_matrix_kernel(tdna_aln *a, int32_t reps, float *ms_per_launch) {
+    if (!a || !ms_per_launch || reps < 1) return fail(TDNA_E_ARG, "bad argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(ensure_packed(a));
+    int64_t rows = a->row_end - a->row_begin;
+    if (band_rows_for(a) != rows) return fail(TDNA_E_TOO_LARGE, "matrix exceeds the memory budget");
+    TRY(ensure_mat(a, rows));
+    bool symmetric = a->row_begin == 0 && a->row_end == a->n;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    TRY(launch_tiles(a, a->row_begin, a->row_end, symmetric, a->d_mat, a->ld, nullptr));  // warm
+    CU(cudaEventRecord(e0, c->stream));
+    for (int r = 0; r < reps; r++) TRY(launch_tiles(a, a->row_begin, a->row_end, symmetric, a->d_mat, a->ld, nullptr));
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    a->mat_valid = true;
+    *ms_per_launch = ms / reps;
+    return TDNA_OK;
+}
+
+int32_t tdna_measure_int_peaks(tdna_ctx *c, double *popc_per_s, double *lop3_per_s) {
+    if (!c) return fail(TDNA_E_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    const int blocks = c->sm_count * 8, iters = 4096;
+    uint32_t *out;
+    CU(cudaMalloc(&out, (size_t)blocks * 256 * 4));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double res[2];
+    for (int which = 0; which < 2; which++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            CU(cudaEventRecord(e0, c->stream));
+            if (which == 0) int_peak_kernel<0><<<blocks, 256, 0, c->stream>>>(out, iters, 12345u + rep);
+            else int_peak_kernel<1><<<blocks, 256, 0, c->stream>>>(out, iters, 12345u + rep);
+            c->launches++;
+            CU(cudaEventRecord(e1, c->stream));
+            CU(cudaEventSynchronize(e1));
+            float ms;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        res[which] = (double)blocks * 256 * iters * 32.0 / (best * 1e-3);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (popc_per_s) *popc_per_s = res[0];
+    if (lop3_per_s) *lop3_per_s = res[1];
+    return TDNA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,552 @@
+// Kernels of the pairwise-distance engine (sm_100a).  See DESIGN.md for the roofline of each.
+#pragma once
+#include "tdna_device.cuh"
+#include "../../include/taxondna_cuda.h"
+
+namespace tdna {
+
+// ------------------------------------------------------------------------------------------
+// pack: normalised symbols -> bit-planes.  HBM-bound, one pass.
+// thread <-> (word k, row) with row fastest, so the 32-byte symbol reads are one sector each and
+// the plane writes are contiguous within a 64-row panel.
+// ------------------------------------------------------------------------------------------
+struct PlaneBits {
+    uint32_t b[6];
+};
+__constant__ uint16_t c_symlut[256];  // symbol -> SymBit set; 0x8000 = not in the alphabet
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len,
+                                                   int64_t n, int64_t npad, int sym_stride, int W, int P, PlaneBits bits,
+                                                   uint32_t *__restrict__ planes, int *__restrict__ err) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npad * W) return;
+    int64_t row = idx % npad;
+    int k = (int)(idx / npad);
+    uint32_t w[6] = {0, 0, 0, 0, 0, 0};
+    if (row < n) {
+        int l = len[row];
+        const uint4 *src = reinterpret_cast<const uint4 *>(sym + row * (int64_t)sym_stride + 32 * k);
+        uint4 v0 = src[0], v1 = src[1];
+        uint32_t raw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        bool bad = false;
+#pragma unroll
+        for (int b = 0; b < 32; b++) {
+            uint32_t s = (raw[b >> 2] >> (8 * (b & 3))) & 0xffu;
+            uint32_t cls = c_symlut[s];
+            if (32 * k + b >= l) cls = 0;  // beyond the row's own length == '?' (Sequence.java:1326-1327)
+            bad |= (cls & 0x8000u) != 0;
+#pragma unroll
+            for (int p = 0; p < 6; p++) w[p] |= ((cls & bits.b[p]) ? 1u : 0u) << b;
+        }
+        if (bad) atomicOr(err, 1);
+    }
+    for (int p = 0; p < P; p++) planes[plane_index(row, p, k, P, W)] = w[p];
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier + bulk-copy (TMA unit, 1-D) primitives
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// count + distance tile kernel (the hot kernel).
+//
+// CTA = 256 threads = 16 (ty) x 16 (tx); tile = 128 rows x TN columns of the pair matrix
+// (TN = 128, or 64 for modes with two accumulator words per pair); thread = 8 rows x CN columns
+// register-blocked, two 16-bit counts per 32-bit accumulator.  Operand words come from shared
+// memory staged by 1-D bulk async copies (one per (panel, plane) K-chunk) signalling an mbarrier;
+// NST stages are in flight across the flattened (tile, K-chunk) sequence of a persistent CTA.
+// Integer-issue bound: see DESIGN.md.
+// ------------------------------------------------------------------------------------------
+constexpr int TM = 128;
+constexpr int KC = 8;    // words (256 sites) per K-chunk
+constexpr int NST = 3;   // pipeline stages
+
+template <int KM> struct TileCfg {
+    static constexpr int P = ModeTraits<KM>::P;
+    static constexpr int NACC = ModeTraits<KM>::NACC;
+    static constexpr int CN = (NACC == 1) ? 8 : 4;
+    static constexpr int TN = 16 * CN;
+    static constexpr int XW = P * (TM / PR) * KC * PR;  // words per stage, x side
+    static constexpr int YW = P * (TN / PR) * KC * PR;
+    static constexpr int STAGE_WORDS = XW + YW;
+    static constexpr size_t SMEM = (size_t)NST * STAGE_WORDS * 4 + 64;
+};
+
+struct TileParams {
+    const uint32_t *planes;
+    int W;
+    int64_t n;          // sequences
+    int min_overlap;
+    int64_t row_begin;  // first row of the band (multiple of 128)
+    int64_t row_end;    // one past the last row of the band
+    int symmetric;      // band == whole matrix: only tiles touching j >= i are computed, both halves written
+    int64_t num_tiles;
+    const int64_t *tile_prefix;  // [row tiles + 1]; symmetric mode only
+    int nct;                     // column tiles
+    double *out;                 // band matrix, row-major, leading dimension ld
+    int64_t ld;
+    tdna_counts *counts;         // optional, same shape, ld = n
+};
+
+template <int KM> __device__ __forceinline__ void tile_coords(const TileParams &p, int64_t t, int &ti, int &tj) {
+    constexpr int TN = TileCfg<KM>::TN;
+    if (!p.symmetric) {
+        ti = (int)(t / p.nct);
+        tj = (int)(t % p.nct);
+    } else {
+        int nrt = (int)((p.row_end - p.row_begin + TM - 1) / TM);
+        int lo = 0, hi = nrt;  // largest ti with prefix[ti] <= t
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (p.tile_prefix[mid] <= t) lo = mid; else hi = mid;
+        }
+        ti = lo;
+        tj = (int)(t - p.tile_prefix[lo]) + ti * (TM / TN);
+    }
+}
+
+template <int KM, bool WRITE_COUNTS>
+__global__ void __launch_bounds__(256, 1) count_tile_kernel(TileParams p) {
+    using Cfg = TileCfg<KM>;
+    constexpr int P = Cfg::P, NACC = Cfg::NACC, CN = Cfg::CN, TN = Cfg::TN;
+    extern __shared__ __align__(128) uint32_t smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + NST * Cfg::STAGE_WORDS);
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int nchunks = (p.W + KC - 1) / KC;
+    // tiles of this CTA: blockIdx.x, +gridDim.x, ...
+    const int64_t my_tiles = (p.num_tiles > blockIdx.x) ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * nchunks;
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t it) {  // one thread: stage (tile, chunk) `it` into slot it % NST
+        int64_t t = blockIdx.x + (it / nchunks) * gridDim.x;
+        int c = (int)(it % nchunks);
+        int ti, tj;
+        tile_coords<KM>(p, t, ti, tj);
+        int k0 = c * KC, kc = min(KC, p.W - k0);
+        int slot = (int)(it % NST);
+        uint32_t *xs = smem + slot * Cfg::STAGE_WORDS, *ys = xs + Cfg::XW;
+        uint32_t bytes = (uint32_t)kc * PR * 4;
+        mbar_expect_tx(&full[slot], bytes * P * (TM / PR + TN / PR));
+        int64_t xpanel = (p.row_begin + (int64_t)ti * TM) / PR, ypanel = ((int64_t)tj * TN) / PR;
+#pragma unroll
+        for (int h = 0; h < TM / PR; h++)
+            for (int pl = 0; pl < P; pl++)
+                bulk_g2s(xs + ((pl * (TM / PR) + h) * KC) * PR, p.planes + (((xpanel + h) * P + pl) * p.W + k0) * PR, bytes, &full[slot]);
+#pragma unroll
+        for (int h = 0; h < TN / PR; h++)
+            for (int pl = 0; pl < P; pl++)
+                bulk_g2s(ys + ((pl * (TN / PR) + h) * KC) * PR, p.planes + (((ypanel + h) * P + pl) * p.W + k0) * PR, bytes, &full[slot]);
+    };
+
+    if (tid == 0)
+        for (int64_t it = 0; it < NST - 1 && it < total; it++) issue(it);
+
+    uint32_t acc[NACC][8][CN];
+    const int xh = ty >> 3, xr = (ty & 7) * 8;  // panel half and first row within it
+
+    for (int64_t it = 0; it < total; it++) {
+        const int c = (int)(it % nchunks);
+        const int slot = (int)(it % NST);
+        if (tid == 0 && it + NST - 1 < total) issue(it + NST - 1);  // slot freed by the barrier ending iteration it-1
+        if (c == 0) {
+#pragma unroll
+            for (int a = 0; a < NACC; a++)
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+#pragma unroll
+                    for (int cc = 0; cc < CN; cc++) acc[a][r][cc] = 0;
+        }
+        mbar_wait(&full[slot], (uint32_t)((it / NST) & 1));
+        const uint32_t *xs = smem + slot * Cfg::STAGE_WORDS, *ys = xs + Cfg::XW;
+        const int kc = min(KC, p.W - c * KC);
+        for (int k = 0; k < kc; k++) {
+            uint32_t x[P][8], y[P][CN];
+#pragma unroll
+            for (int pl = 0; pl < P; pl++) {
+                const uint4 *xp = reinterpret_cast<const uint4 *>(xs + ((pl * (TM / PR) + xh) * KC + k) * PR + xr);
+                uint4 a = xp[0], b = xp[1];
+                x[pl][0] = a.x; x[pl][1] = a.y; x[pl][2] = a.z; x[pl][3] = a.w;
+                x[pl][4] = b.x; x[pl][5] = b.y; x[pl][6] = b.z; x[pl][7] = b.w;
+#pragma unroll
+                for (int h = 0; h < CN / 4; h++) {
+                    uint4 v = *reinterpret_cast<const uint4 *>(ys + ((pl * (TN / PR) + h) * KC + k) * PR + 4 * tx);
+                    y[pl][4 * h + 0] = v.x; y[pl][4 * h + 1] = v.y; y[pl][4 * h + 2] = v.z; y[pl][4 * h + 3] = v.w;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int cc = 0; cc < CN; cc++) {
+                    uint32_t xv[P], yv[P];
+#pragma unroll
+                    for (int pl = 0; pl < P; pl++) { xv[pl] = x[pl][r]; yv[pl] = y[pl][cc]; }
+                    uint32_t a1 = 0;
+                    if constexpr (NACC == 2) {
+                        accumulate_word<KM>(xv, yv, acc[0][r][cc], acc[1][r][cc]);
+                    } else {
+                        accumulate_word<KM>(xv, yv, acc[0][r][cc], a1);
+                    }
+                }
+        }
+        if (c == nchunks - 1) {  // epilogue: counts -> fp64 distance -> band matrix
+            int64_t t = blockIdx.x + (it / nchunks) * gridDim.x;
+            int ti, tj;
+            tile_coords<KM>(p, t, ti, tj);
+            const int64_t i0 = p.row_begin + (int64_t)ti * TM + ty * 8, j0 = (int64_t)tj * TN;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int64_t i = i0 + r;
+                if (i >= p.row_end) continue;
+#pragma unroll
+                for (int h = 0; h < CN / 4; h++) {
+                    const int64_t jb = j0 + h * PR + 4 * tx;
+                    double dv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        uint32_t a1 = 0;
+                        if constexpr (NACC == 2) a1 = acc[1][r][4 * h + e];
+                        Counts cn = unpack_counts<KM>(acc[0][r][4 * h + e], a1);
+                        dv[e] = distance_from_counts<KM>(cn, p.min_overlap);
+                        if constexpr (WRITE_COUNTS) {
+                            if (jb + e < p.n) {
+                                tdna_counts o = {cn.shared, cn.c1, cn.c2, cn.c3};
+                                p.counts[(i - p.row_begin) * p.n + jb + e] = o;
+                            }
+                        }
+                    }
+                    double *dst = p.out + (i - p.row_begin) * p.ld + jb;
+                    if (jb + 3 < p.n) {  // ld and jb are multiples of 4 doubles: 32-byte aligned
+                        reinterpret_cast<double2 *>(dst)[0] = make_double2(dv[0], dv[1]);
+                        reinterpret_cast<double2 *>(dst)[1] = make_double2(dv[2], dv[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            if (jb + e < p.n) dst[e] = dv[e];
+                    }
+                    if (p.symmetric) {  // mirror (band == whole matrix, row_begin == 0)
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            if (jb + e < p.n && jb + e > i) p.out[(jb + e) * p.ld + i] = dv[e];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// one query row straight from the planes (SortedSequenceList.sortAgainst's N getPairwise calls,
+// tdna_pair with n_cols == 1).  thread <-> column j; the query's words are broadcast loads.
+// ------------------------------------------------------------------------------------------
+template <int KM>
+__global__ void __launch_bounds__(256) row_from_planes_kernel(const uint32_t *__restrict__ planes, int W, int64_t q, int64_t j_begin,
+                                                              int64_t j_end, int min_overlap, double *__restrict__ d_out,
+                                                              int32_t *__restrict__ shared_out, tdna_counts *__restrict__ counts_out) {
+    int64_t j = j_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= j_end) return;
+    Counts c = pair_counts_global<KM>(planes, q, j, W);
+    if (d_out) d_out[j - j_begin] = distance_from_counts<KM>(c, min_overlap);
+    if (shared_out) shared_out[j - j_begin] = c.shared;
+    if (counts_out) {
+        tdna_counts o = {c.shared, c.c1, c.c2, c.c3};
+        counts_out[j - j_begin] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-query summary over one band of the distance matrix (HBM/L2-bound: three sweeps of the
+// query's row, the 2nd and 3rd from L2).  One CTA per query row.
+// ------------------------------------------------------------------------------------------
+struct Key {
+    unsigned long long hi, lo;  // hi = bits of d (valid finite d >= 0: bit order == numeric order); lo = rank<<32 | j
+};
+#define TDNA_KEY_NONE 0xffffffffffffffffull
+__device__ __forceinline__ bool key_less(const Key &a, const Key &b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+__device__ __forceinline__ Key key_min(const Key &a, const Key &b) { return key_less(b, a) ? b : a; }
+__device__ __forceinline__ Key key_shfl_xor(const Key &k, int m) {
+    Key r;
+    r.hi = __shfl_xor_sync(0xffffffffu, k.hi, m);
+    r.lo = __shfl_xor_sync(0xffffffffu, k.lo, m);
+    return r;
+}
+// all threads get the block-wide min; scratch: >= 8 Keys
+__device__ __forceinline__ Key block_key_min(Key k, Key *scratch) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) k = key_min(k, key_shfl_xor(k, m));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = k;
+    __syncthreads();
+    Key r = scratch[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = key_min(r, scratch[w]);
+    return r;
+}
+__device__ __forceinline__ int block_sum(int v, int *scratch) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += scratch[w];
+    return r;
+}
+__device__ __forceinline__ int block_min_i(int v, int *scratch) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, m));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = scratch[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = min(r, scratch[w]);
+    return r;
+}
+__device__ __forceinline__ int block_max_i(int v, int *scratch) { return -block_min_i(-v, scratch); }
+
+#define TDNA_NEAR 2e-5  // twice Settings' 1e-5 quantum (Settings.java:48): see DESIGN.md "near ties"
+
+__device__ __forceinline__ bool is_near(double d, double ref) {
+    double diff = fabs(d - ref);
+    return d != ref && diff < TDNA_NEAR;
+}
+
+__global__ void __launch_bounds__(256) row_summary_kernel(const double *__restrict__ mat, int64_t ld, int64_t n, int64_t row_begin,
+                                                          const int32_t *__restrict__ species, tdna_row_result *__restrict__ out) {
+    __shared__ Key kscratch[8];
+    __shared__ int iscratch[8];
+    const int64_t q = row_begin + blockIdx.x;
+    const double *row = mat + (int64_t)blockIdx.x * ld;
+    const int spq = species[q];
+    const bool qnamed = spq >= 0;
+
+    // ---- sweep 1: arg-min keys --------------------------------------------------------------
+    Key kb = {TDNA_KEY_NONE, TDNA_KEY_NONE}, kc = kb, ka = kb;
+    int nvalid = 0, nonfinite = 0;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+        double d = row[j];
+        if (j == q || d < 0) continue;
+        nvalid++;
+        if (!(d < __longlong_as_double(0x7ff0000000000000LL))) { nonfinite = 1; if (d != d) continue; }
+        unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+        int spj = species[j];
+        bool consp = qnamed && spj == spq;  // SortedSequenceComparator: conspecific-to-query first (:236-255)
+        Key k = {bits, ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
+        kb = key_min(kb, k);
+        if (qnamed && spj >= 0) {
+            Key k2 = {bits, (unsigned long long)j};
+            if (consp) kc = key_min(kc, k2); else ka = key_min(ka, k2);
+        }
+    }
+    kb = block_key_min(kb, kscratch);
+    kc = block_key_min(kc, kscratch);
+    ka = block_key_min(ka, kscratch);
+    nvalid = block_sum(nvalid, iscratch);
+    nonfinite = block_sum(nonfinite, iscratch);
+    const bool has_b = kb.hi != TDNA_KEY_NONE, has_c = kc.hi != TDNA_KEY_NONE, has_a = ka.hi != TDNA_KEY_NONE;
+    const int jb = has_b ? (int)(kb.lo & 0xffffffffu) : -1;
+    const double db = has_b ? __longlong_as_double((long long)kb.hi) : -1.0;
+    const double dc = has_c ? __longlong_as_double((long long)kc.hi) : -1.0;
+    const double da = has_a ? __longlong_as_double((long long)ka.hi) : -1.0;
+    const int spb = has_b ? species[jb] : -1;
+
+    // ---- sweep 2: tie class of the best match, near-tie windows, end of the species block ------
+    int ties = 0, tie_unnamed = 0, smin = 0x7fffffff, smax = -1;
+    int near_b = 0, near_c = 0, near_a = 0, un_c = 0, un_a = 0;
+    Key ko = {TDNA_KEY_NONE, TDNA_KEY_NONE};
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+        double d = row[j];
+        if (j == q || d < 0 || d != d) continue;
+        int spj = species[j];
+        if (has_b) {
+            if (d == db && j != jb) {
+                ties++;
+                if (spj < 0) tie_unnamed++; else { smin = min(smin, spj); smax = max(smax, spj); }
+            }
+            near_b += is_near(d, db);
+            if (spj >= 0 && spj != spb && j != jb) {
+                bool consp = qnamed && spj == spq;
+                Key k = {(unsigned long long)__double_as_longlong(d), ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
+                ko = key_min(ko, k);
+            }
+        }
+        if (has_c) { near_c += is_near(d, dc); un_c += (spj < 0 && d == dc); }
+        if (has_a) { near_a += is_near(d, da); un_a += (spj < 0 && d == da); }
+    }
+    ties = block_sum(ties, iscratch);
+    tie_unnamed = block_sum(tie_unnamed, iscratch);
+    smin = block_min_i(smin, iscratch);
+    smax = block_max_i(smax, iscratch);
+    near_b = block_sum(near_b, iscratch);
+    near_c = block_sum(near_c, iscratch);
+    near_a = block_sum(near_a, iscratch);
+    un_c = block_sum(un_c, iscratch);
+    un_a = block_sum(un_a, iscratch);
+    ko = block_key_min(ko, kscratch);
+    const bool has_o = ko.hi != TDNA_KEY_NONE;
+    const double dother = has_o ? __longlong_as_double((long long)ko.hi) : -1.0;
+
+    // ---- sweep 3: length of the leading same-species run (BlockAnalysis.java:282-294) ----------
+    int block = 0, near_o = 0, un_o = 0;
+    if (has_b) {
+        for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+            double d = row[j];
+            if (j == q || d < 0 || d != d) continue;
+            int spj = species[j];
+            if (has_o) { near_o += is_near(d, dother); un_o += (spj < 0 && d == dother); }
+            if (j != jb && spj >= 0 && spj == spb) {
+                bool consp = qnamed && spj == spq;
+                Key k = {(unsigned long long)__double_as_longlong(d), ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
+                if (!has_o || key_less(k, ko)) block++;
+            }
+        }
+    }
+    block = block_sum(block, iscratch);
+    near_o = block_sum(near_o, iscratch);
+    un_o = block_sum(un_o, iscratch);
+
+    if (threadIdx.x == 0) {
+        tdna_row_result r;
+        r.d_best = db; r.d_con = dc; r.d_allo = da; r.d_other = dother;
+        r.best = jb;
+        r.con = has_c ? (int)(kc.lo & 0xffffffffu) : -1;
+        r.allo = has_a ? (int)(ka.lo & 0xffffffffu) : -1;
+        r.other = has_o ? (int)(ko.lo & 0xffffffffu) : -1;
+        r.shared_con = 0; r.shared_allo = 0;  // filled by fill_shared_kernel
+        r.tie_count = ties; r.tie_species_min = smin; r.tie_species_max = smax; r.tie_unnamed = tie_unnamed;
+        r.block_count = block;
+        r.near_best = near_b; r.near_con = near_c; r.near_allo = near_a; r.near_other = near_o;
+        r.unnamed_at_con = un_c; r.unnamed_at_allo = un_a; r.unnamed_at_other = un_o;
+        r.n_valid = nvalid;
+        double dself = row[q];
+        r.flags = (!(dself < 0) ? TDNA_ROW_SELF_VALID : 0) | (nonfinite ? TDNA_ROW_NONFINITE : 0);
+        r.reserved = 0;
+        out[q] = r;
+    }
+}
+
+// getSharedLength(query, first_con / first_allo) for the listing (BestMatch.java:372,386)
+template <int KM>
+__global__ void fill_shared_kernel(const uint32_t *__restrict__ planes, int W, int64_t row_begin, int64_t row_end,
+                                   tdna_row_result *__restrict__ res) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t q = row_begin + (idx >> 1);
+    if (q >= row_end) return;
+    int which = (int)(idx & 1);
+    int j = which ? res[q].allo : res[q].con;
+    int sh = 0;
+    if (j >= 0) sh = pair_counts_global<KM>(planes, q, j, W).shared;
+    if (which) res[q].shared_allo = sh; else res[q].shared_con = sh;
+}
+
+// ------------------------------------------------------------------------------------------
+// PairwiseDistribution classes and Cluster edges: compaction sweeps over a band (HBM-bound)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) class_distances_kernel(const double *__restrict__ mat, int64_t ld, int64_t n, int64_t row_begin,
+                                                              int64_t rows, int klass, const int32_t *__restrict__ species,
+                                                              const int32_t *__restrict__ genus, const int32_t *__restrict__ epi,
+                                                              const int32_t *__restrict__ full, float *__restrict__ out, int64_t cap,
+                                                              unsigned long long *__restrict__ counter) {
+    const int64_t qb = blockIdx.x;  // grid.x = band rows, grid.y = column slices
+    if (qb >= rows) return;
+    const int64_t q = row_begin + qb;
+    const int spq = species[q], gq = genus[q], eq = epi[q], fq = full[q];
+    for (int64_t j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.y * blockDim.x) {
+        if (j == q) continue;
+        bool in;
+        if (klass == TDNA_PD_INTRA)  // _addIntra (PairwiseDistribution.java:161-177)
+            in = spq >= 0 && species[j] == spq && !(full[j] < fq);
+        else                         // _addInter (:183-203)
+            in = genus[j] == gq && epi[j] != eq && eq < epi[j];
+        if (!in) continue;
+        float f = (float)mat[qb * ld + j];
+        if (f == -1.0f) continue;  // distances_push drops -1 (:79)
+        unsigned long long pos = atomicAdd(counter, 1ull);
+        if (out && (int64_t)pos < cap) out[pos] = f;
+    }
+}
+
+__global__ void __launch_bounds__(256) edges_kernel(const double *__restrict__ mat, int64_t ld, int64_t n, int64_t row_begin, int64_t rows,
+                                                    double t, int32_t *__restrict__ ii, int32_t *__restrict__ jj, double *__restrict__ dd,
+                                                    int64_t cap, unsigned long long *__restrict__ counter) {
+    const int64_t qb = blockIdx.x;
+    if (qb >= rows) return;
+    const int64_t q = row_begin + qb;
+    for (int64_t j = q + 1 + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.y * blockDim.x) {
+        double d = mat[qb * ld + j];
+        if (d >= 0 && d <= t) {  // Cluster.java:797-804
+            unsigned long long pos = atomicAdd(counter, 1ull);
+            if (ii && (int64_t)pos < cap) { ii[pos] = (int32_t)q; jj[pos] = (int32_t)j; dd[pos] = d; }
+        }
+    }
+}
+
+// SpeciesDetail.getSequencesWithValidConspecificsCount's inner test (SpeciesDetail.java:78-95):
+// shared >= minOverlap  <=>  the distance is not the -1.0 sentinel.
+__global__ void __launch_bounds__(256) valid_consp_kernel(const double *__restrict__ mat, int64_t ld, int64_t n, int64_t row_begin,
+                                                          const int32_t *__restrict__ species, uint8_t *__restrict__ has_valid) {
+    __shared__ int iscratch[8];
+    const int64_t q = row_begin + blockIdx.x;
+    const int spq = species[q];
+    int any = 0;
+    if (spq >= 0)
+        for (int64_t j = threadIdx.x; j < n; j += blockDim.x)
+            if (j != q && species[j] == spq && mat[(int64_t)blockIdx.x * ld + j] != -1.0) any = 1;
+    any = block_sum(any, iscratch);
+    if (threadIdx.x == 0) has_valid[q] = any ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// integer-pipe micro-benchmarks (roofline denominators for the count kernel)
+// ------------------------------------------------------------------------------------------
+template <int WHICH> __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
+    uint32_t a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = seed * (threadIdx.x + 1) + i * 0x9e3779b9u;
+    uint32_t b = seed ^ 0x5bd1e995u, c = seed * 7u + 3u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (WHICH == 0) a[i] = __popc(a[i]) + b;          // POPC (+ one IADD that keeps the value alive)
+                else a[i] = (a[i] & b) | (a[i] ^ c);              // one LOP3 per result
+            }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace tdna

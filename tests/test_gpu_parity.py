@@ -1,0 +1,162 @@
+"""GPU parity: the CUDA library (through its C ABI) against the CPU oracle, bit for bit."""
+import gzip
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import consumers as C
+
+pytestmark = pytest.mark.gpu
+
+SYMS = b"ACGTRYKMSWBDHVN-_?"
+MODES = [(0, True), (0, False), (1, True), (2, True)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import taxondna_b200 as t
+    c = t.Context(0)
+    yield c
+    c.close()
+
+
+def u64(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def check_against_oracle(ctx, sym, lens, min_overlap, modes=MODES, budget=None):
+    import taxondna_b200 as t
+    n = sym.shape[0]
+    aln = t.Alignment(ctx, sym, lens)
+    try:
+        for mode, ambig in modes:
+            aln.set_config(mode, min_overlap, ambig)
+            d, c = aln.matrix(counts=True)
+            ref = oracle.all_pairs(sym, lens if lens is not None else np.full(n, sym.shape[1], np.int32), mode, min_overlap, ambig, threads=8)
+            assert np.array_equal(c["shared"], ref["shared"]), (mode, ambig, "shared")
+            assert np.array_equal(c["c1"], ref["c1"]), (mode, ambig, "c1")
+            assert np.array_equal(c["c2"], ref["c2"]), (mode, ambig, "c2")
+            assert np.array_equal(c["c3"], ref["c3"]), (mode, ambig, "c3")
+            assert np.array_equal(u64(d), u64(ref["dist"])), (mode, ambig, "dist")
+            d2 = aln.matrix()  # the symmetric (upper-triangle + mirror) path
+            assert np.array_equal(u64(d2), u64(ref["dist"])), (mode, ambig, "dist-symmetric")
+    finally:
+        aln.close()
+
+
+def test_symbol_pair_truth_table(ctx):
+    # 18 x 18 symbol pairs, every mode: one-column alignment, row r = symbol r
+    sym = np.frombuffer(SYMS, dtype=np.uint8).reshape(-1, 1).copy()
+    for mo in (0, 1):
+        check_against_oracle(ctx, sym, None, mo)
+
+
+def test_kats_through_the_abi(ctx):
+    import taxondna_b200 as t
+    s1 = oracle.normalise("AAAAAAAAAAAAAAAAAAAAAAAAA" + "-" * 75)
+    s2 = oracle.normalise("----------AAAAATTTTT?????" + "-" * 75)
+    rows, lens = oracle.pack_rows([s1, s2])
+    aln = t.Alignment(ctx, rows, lens)
+    aln.set_config(t.PDM_UNCORRECTED, 1, True)
+    (shared, ident, _, _), d = aln.pair(0, 1)
+    assert shared == 10 and d == 0.50  # KAT-1, Sequence.java:1913-1936
+    aln.close()
+    s1 = oracle.normalise("AAA---CCCCCCTTTTTTTTTTTTTTTTTTTTTTTT---TTTTTTTTTTTT")
+    s2 = oracle.normalise("AAA---CCCCCCTTTTT----------------------------------")
+    rows, lens = oracle.pack_rows([s1, s2])
+    aln = t.Alignment(ctx, rows, lens)
+    aln.set_config(t.PDM_UNCORRECTED, 1, True)
+    assert aln.pair(0, 1)[0][0] == 17  # KAT-2, Sequence.java:1942-1955
+    aln.close()
+    a, b = oracle.normalise("--ATCCCTGGTA"), oracle.normalise("ACCGCCCT--CG")
+    rows, lens = oracle.pack_rows([a, b])
+    aln = t.Alignment(ctx, rows, lens)
+    aln.set_config(t.PDM_TRANS_ONLY, 1, True)
+    (shared, tv, _, _), d = aln.pair(0, 1)
+    assert (shared, tv, d) == (10, 2, 0.2)  # KAT-3, Testing.java:73-87
+    aln.close()
+
+
+def random_alignment(rng, n, L, ragged=False, p_special=0.25):
+    base = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=L)
+    sym = np.tile(base, (n, 1))
+    mut = rng.random((n, L)) < 0.15
+    sym[mut] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(mut.sum()))
+    sp = rng.random((n, L)) < p_special
+    sym[sp] = rng.choice(np.frombuffer(SYMS, dtype=np.uint8), size=int(sp.sum()))
+    lens = None
+    if ragged:
+        lens = rng.integers(max(1, L // 2), L + 1, size=n).astype(np.int32)
+        lens[0] = L
+    return sym, lens
+
+
+@pytest.mark.parametrize("n,L,ragged", [(1, 5, False), (2, 31, False), (3, 32, False), (65, 33, True), (128, 64, False),
+                                        (129, 257, True), (200, 658, False), (300, 700, True), (257, 1539, False)])
+def test_random_alignments_all_modes(ctx, n, L, ragged):
+    rng = np.random.default_rng(n * 1000 + L)
+    sym, lens = random_alignment(rng, n, L, ragged)
+    check_against_oracle(ctx, sym, lens, min_overlap=max(1, L // 3))
+
+
+def test_banded_path_equals_single_band(ctx):
+    import taxondna_b200 as t
+    rng = np.random.default_rng(99)
+    sym, _ = random_alignment(rng, 700, 300)
+    aln = t.Alignment(ctx, sym)
+    aln.set_config(t.PDM_K2P, 100, True)
+    full = aln.matrix()
+    ctx.set_memory_budget(2 << 20)  # 2 MiB -> 128-row bands (rectangular tiles, no mirroring)
+    try:
+        aln.set_config(t.PDM_K2P, 100, True)
+        banded = aln.matrix()
+    finally:
+        ctx.set_memory_budget(64 << 30)
+    assert np.array_equal(u64(full), u64(banded))
+    aln.set_row_range(256, 600)
+    part = aln.matrix()
+    assert np.array_equal(u64(part), u64(full[256:600]))
+    aln.close()
+
+
+def test_golden_fixture_checksums(ctx, golden_dir):
+    import taxondna_b200 as t
+    sums = json.load(open(os.path.join(golden_dir, "checksums.json")))
+    for key in ("diptera_small_nogaps", "diptera_coi"):
+        seqs = C.read_fasta(os.path.join(golden_dir, key + ".fasta.gz"))
+        rows, lens = oracle.pack_rows([s.seq for s in seqs])
+        aln = t.Alignment(ctx, rows, lens)
+        iu = np.triu_indices(len(seqs), 1)
+        for mode, nm in ((0, "p"), (1, "k2p"), (2, "trans")):
+            aln.set_config(mode, 300, True)
+            d, c = aln.matrix(counts=True)
+            e = sums[key][nm]
+            assert int(c["shared"][iu].sum()) == e["sum_shared"]
+            assert int(c["c1"][iu].sum()) == e["sum_c1"]
+            assert int(c["c2"][iu].sum()) == e["sum_c2"] and int(c["c3"][iu].sum()) == e["sum_c3"]
+            du = np.ascontiguousarray(d[iu])
+            assert int((~(du < 0)).sum()) == e["valid_pairs"] and int((du == 0).sum()) == e["exact_zero"]
+            assert hashlib.sha256(du.tobytes()).hexdigest() == e["sha256_dist_upper"], (key, nm)
+        aln.close()
+
+
+def test_row_distances_and_errors(ctx):
+    import taxondna_b200 as t
+    rng = np.random.default_rng(5)
+    sym, lens = random_alignment(rng, 150, 400, ragged=True)
+    aln = t.Alignment(ctx, sym, lens)
+    aln.set_config(t.PDM_UNCORRECTED, 100, True)
+    ref = oracle.all_pairs(sym, lens, 0, 100, True)
+    for q in (0, 77, 149):
+        d, sh = aln.row_distances(q)
+        assert np.array_equal(u64(d), u64(ref["dist"][q])) and np.array_equal(sh, ref["shared"][q])
+    aln.close()
+    bad = sym.copy()
+    bad[3, 7] = ord("X")
+    with pytest.raises(t.TdnaError) as ei:
+        t.Alignment(ctx, bad)
+    assert ei.value.code == 3  # TDNA_E_SYMBOL
