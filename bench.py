@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract.
+
+  python bench.py --gpus N --steps K --warmup W [--workload C2|C3|H|C4] [--impl reference]
+
+A "step" is one pass of the hot path over one synthetic alignment of a BASELINE.json shape:
+  C2 (default, configs[1]): 2,185 x 2,664, uncorrected p: full fp64 pairwise matrix + the two Pairwise
+      Summary classes (intra / congeneric inter distance extraction)
+  C3: 8,000 x 658, K2P: per-query Best Close Match summaries + intraspecific distances (threshold percentile)
+  H : 50,000 x 658, p: per-query Best Match summaries (the north-star headline shape)
+metric = unordered pairs i<j per second (Gpairs/s).  `value`: inputs (bit-planes, labels) resident
+in HBM, results left in HBM, each step timed with CUDA events on the library's stream, L2 flushed
+between steps.  `e2e`: the same work through the C ABI with HOST buffers (symbols in, results out),
+host<->device copies inside the timed region.
+
+N > 1 (torchrun, one rank per GPU): the query rows are split into row bands, one per rank, every
+rank holds the whole packed alignment; the per-row results are exchanged with one NCCL all_gather
+at the end of the step.  Weak scaling: the alignment grows as sqrt(N) so pairs per GPU stay fixed.
+
+--impl reference: the reference's CPU algorithm (oracle/ C restatement of Sequence.getPairwise --
+the reference is Java and no JVM exists in this image) on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "C2": dict(config="C2", mode=0, kind="matrix+summary", desc="2,185 x 2,664 bp synthetic multi-gene alignment, uncorrected p: full pairwise matrix + Pairwise Summary classes"),
+    "C3": dict(config="C3", mode=1, kind="bestmatch+intra", desc="8,000 x 658 bp synthetic COI, K2P: Best Close Match + intraspecific distances for the 95th-percentile threshold"),
+    "C4": dict(config="C4", mode=0, kind="matrix+summary", desc="5,000 x 2,664 bp gappy/ambiguous alignment (20% ?/-/IUPAC), uncorrected p: matrix + Pairwise Summary classes"),
+    "H": dict(config="H", mode=0, kind="bestmatch", desc="50,000 x 658 bp synthetic COI, uncorrected p: streaming per-query Best Match summaries"),
+}
+POPC_PER_PAIR_WORD = {0: 2, 1: 4, 2: 2}  # C = 2 (p), 4 (K2P), 2 (trans-only)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def cpu_reference_leg(data, mode, seconds, threads):
+    """Times the oracle's getPairwiseNoBuffer restatement on a bounded sample of the same workload."""
+    import oracle
+    sym = data["symbols"]
+    n, L = sym.shape
+    lens = np.full(n, L, dtype=np.int32)
+    # calibrate on a few rows, then size the sample for ~`seconds` of wall time
+    t0 = time.perf_counter()
+    _, cnt = oracle.bench_pairs(sym, lens, mode, 300, True, 0, min(n, 2 * max(1, threads)), threads)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    rate = cnt / dt
+    want = rate * seconds
+    rows = 1
+    acc = 0
+    while rows < n and acc < want:
+        acc += n - rows
+        rows += 1
+    t0 = time.perf_counter()
+    _, cnt = oracle.bench_pairs(sym, lens, mode, 300, True, 0, rows, threads)
+    dt = time.perf_counter() - t0
+    return cnt / dt, cnt, dt, rows
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from taxondna_b200 import synth
+    wl = WORKLOADS[args.workload]
+    data = synth.generate(wl["config"], names=False)
+    n, L = data["symbols"].shape
+    threads = os.cpu_count() or 1
+    per_step = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_reference_leg(data, wl["mode"], per_step, threads)
+    rates, pairs, secs = [], 0, 0.0
+    for _ in range(args.steps):
+        r, cnt, dt, rows = cpu_reference_leg(data, wl["mode"], per_step, threads)
+        rates.append(r)
+        pairs += cnt
+        secs += dt
+    v = pairs / secs / 1e9
+    line = {
+        "impl": "reference", "metric": "pairwise distances/s", "value": v, "unit": "Gpairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / max(1, args.steps) * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "int32 counts + f64 distance", "data": "synthetic",
+        "config": {"workload": wl["desc"], "n": n, "L": L, "mode": wl["mode"]},
+        "cpu_baseline": {"value": v, "unit": "Gpairs/s", "cores": threads, "kind": "port",
+                         "sample": "first %d query rows x all later columns per step (%d pairs/step), C restatement of Sequence.getPairwiseNoBuffer (no JVM in image), %d pthreads" % (rows, pairs // max(1, args.steps), threads)},
+        "e2e": {"value": v, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import taxondna_b200 as t
+    from taxondna_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    wl = WORKLOADS[args.workload]
+    mode = wl["mode"]
+    base = synth.CONFIGS[wl["config"]]
+    n1 = base["genera"] * base["species"] * base["reps"]
+    scale_n = None
+    if world > 1 and args.scaling == "weak":
+        scale_n = n1 * (world ** 0.5)  # rectangular row bands: (n/world) x n ordered pairs per GPU stays fixed
+    data = synth.generate(wl["config"], names=False, scale_n=scale_n)
+    sym = data["symbols"]
+    n, L = sym.shape
+    pairs = n * (n - 1) // 2
+    W32 = (L + 31) // 32
+
+    ctx = t.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
+    sym_pinned = torch.from_numpy(sym).pin_memory()
+    labels = [data[k] for k in ("species_id", "genus_id", "epithet_rank", "fullname_rank")]
+    aln = t.Alignment(ctx, sym_pinned.numpy())
+    aln.set_labels(*labels)
+    aln.set_config(mode, 300, True)
+    # row band of this rank (multiples of 128 rows)
+    if world > 1:
+        per = -(-n // world)
+        per = -(-per // 128) * 128
+        b0, b1 = min(n, rank * per), min(n, (rank + 1) * per)
+        aln.set_row_range(b0, b1)
+    else:
+        b0, b1 = 0, n
+    kind = wl["kind"]
+    dev = torch.device("cuda", local)
+
+    # device-resident outputs for the kernel-timed steps
+    n_intra = n_inter = 0
+    if "summary" in kind or "intra" in kind:
+        # sizes are a property of the labels only; ask once
+        import ctypes
+        cnt = ctypes.c_int64()
+        t.load().tdna_class_distances(aln.h, t.PD_INTRA, None, 0, ctypes.byref(cnt))
+        n_intra = cnt.value
+        if "summary" in kind:
+            t.load().tdna_class_distances(aln.h, t.PD_INTER, None, 0, ctypes.byref(cnt))
+            n_inter = cnt.value
+    d_intra = torch.empty(max(1, n_intra), dtype=torch.float32, device=dev)
+    d_inter = torch.empty(max(1, n_inter), dtype=torch.float32, device=dev)
+    RS = t.ROW_RESULT_DTYPE.itemsize
+    per_rows = (-(-(-(-n // world)) // 128) * 128) if world > 1 else n
+    res_all = torch.empty((world * per_rows, RS), dtype=torch.uint8, device=dev) if world > 1 else None
+    mine = torch.zeros((per_rows, RS), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    class _DevBuf:  # zero-copy torch view of library-owned device memory
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    import ctypes
+    c64 = ctypes.c_int64()
+    L_ = t.load()
+
+    def step_device():
+        aln.set_config(mode, 300, True)  # invalidates the cached matrix: every step recomputes everything
+        if kind.startswith("matrix"):
+            aln.matrix_compute()
+            t.check(L_.tdna_class_distances(aln.h, t.PD_INTRA, d_intra.data_ptr(), n_intra, ctypes.byref(c64)))
+            t.check(L_.tdna_class_distances(aln.h, t.PD_INTER, d_inter.data_ptr(), n_inter, ctypes.byref(c64)))
+        else:
+            p = aln.best_match_compute()
+            if "intra" in kind:
+                t.check(L_.tdna_class_distances(aln.h, t.PD_INTRA, d_intra.data_ptr(), n_intra, ctypes.byref(c64)))
+            if world > 1:
+                # the exchange step: every rank gets every row's summary (one NCCL all_gather over NVLink)
+                lib_res = torch.as_tensor(_DevBuf(p, n * RS), device=dev).view(n, RS)
+                mine[: b1 - b0].copy_(lib_res[b0:b1])
+                dist.all_gather_into_tensor(res_all.view(-1), mine.view(-1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    step_ms = []
+    t_region0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)  # L2 flush between timed iterations (on torch's stream; joined below)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            step_device()
+            e1.record(stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+    barrier()
+    t_region = time.perf_counter() - t_region0
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(sum(step_ms))
+    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms = float(tm.item())
+    ms_per_step = total_ms / args.steps
+    value = pairs / (ms_per_step * 1e-3) / 1e9
+
+    # ---- the dominant kernel alone, timed live with CUDA events on the library's stream ----
+    kern_ms = aln.time_matrix_kernel(max(3, min(20, args.steps)))
+    rows_mine = b1 - b0
+    kern_pairs = pairs if world == 1 else rows_mine * n  # symmetric triangle vs rectangular band
+    popc_alg = kern_pairs * POPC_PER_PAIR_WORD[mode] * W32
+    popc_peak, lop3_peak = ctx.measure_int_peaks()
+    achieved = popc_alg / (kern_ms * 1e-3)
+    peaks, peak_src = measured_peaks()
+    prof = {}
+    pj = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(pj):
+        prof = json.load(open(pj)).get(args.workload, {})
+    roofline = {
+        "bound": "int-issue (POPC, quarter-rate on the ALU pipe)", "kernel": "count_tile_kernel",
+        "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": achieved / popc_peak,
+        "peak_source": "measured live by tdna_measure_int_peaks (no POPC figure in MEASURED_PEAKS.json); LOP3 peak %.2f T/s" % (lop3_peak / 1e12),
+        "kernel_ms": kern_ms, "kernel_gpairs_per_s": kern_pairs / (kern_ms * 1e-3) / 1e9,
+        "algorithmic_popc32_per_pair": POPC_PER_PAIR_WORD[mode] * W32,
+        "traffic": prof.get("dram_bytes_per_launch"),
+        "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_src,
+        "matrix_write_gbs": (rows_mine * n * 8) / (kern_ms * 1e-3) / 1e9,
+    }
+
+    # ---- e2e: the same step through the C ABI with host buffers --------------------------------
+    e2e_steps = max(1, min(args.steps, 5))
+    h2d = sym.nbytes + 4 * 4 * n
+    if kind.startswith("matrix"):
+        out_host = torch.empty((rows_mine, n), dtype=torch.float64).pin_memory()
+        d2h = out_host.numel() * 8 + 4 * (n_intra + n_inter)
+    else:
+        out_host = torch.empty((n, t.ROW_RESULT_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+        d2h = rows_mine * t.ROW_RESULT_DTYPE.itemsize + 4 * n_intra
+    h_intra = torch.empty(max(1, n_intra), dtype=torch.float32).pin_memory()
+    h_inter = torch.empty(max(1, n_inter), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        a2 = t.Alignment(ctx, sym_pinned.numpy())  # H2D of the symbols + pack
+        a2.set_labels(*labels)
+        a2.set_config(mode, 300, True)
+        if world > 1:
+            a2.set_row_range(b0, b1)
+        if kind.startswith("matrix"):
+            t.check(L_.tdna_matrix(a2.h, out_host.data_ptr(), None))
+            t.check(L_.tdna_class_distances(a2.h, t.PD_INTRA, h_intra.data_ptr(), n_intra, ctypes.byref(c64)))
+            t.check(L_.tdna_class_distances(a2.h, t.PD_INTER, h_inter.data_ptr(), n_inter, ctypes.byref(c64)))
+        else:
+            t.check(L_.tdna_best_match(a2.h, out_host.data_ptr()))
+            if "intra" in kind:
+                t.check(L_.tdna_class_distances(a2.h, t.PD_INTRA, h_intra.data_ptr(), n_intra, ctypes.byref(c64)))
+        a2.close()
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e = {"value": pairs / e2e_s / 1e9, "unit": "Gpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, cnt, dt, rows = cpu_reference_leg(data, mode, args.cpu_seconds, threads)
+        v1, cnt1, dt1, rows1 = cpu_reference_leg(data, mode, min(4.0, args.cpu_seconds), 1)
+        cpu = {"value": v / 1e9, "unit": "Gpairs/s", "cores": threads, "kind": "port",
+               "sample": "first %d query rows x all later columns of the same alignment: %d pairs in %.1f s; C restatement of the reference's Sequence.getPairwiseNoBuffer (oracle/tdna_oracle.c; the reference is Java and no JVM exists in the image)" % (rows, cnt, dt),
+               "single_thread_value": v1 / 1e9}
+
+    if rank == 0:
+        line = {
+            "metric": "pairwise distances/s", "value": value, "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "u32 bit-planes -> int32 counts -> f64 distance", "data": "synthetic",
+            "config": {"workload": wl["desc"], "n": n, "L": L, "mode": ["uncorrected", "K2P", "trans-only"][mode], "min_overlap": 300,
+                       "pairs": pairs, "step": kind, "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": "row bands, %d rank(s), rows [%d,%d) on rank 0" % (world, b0, b1)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "region_wall_s": t_region,
+        }
+        print(json.dumps(line), flush=True)
+    aln.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,11 @@ int fail(int code, const std::string &msg) {
 int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 }  // namespace
 
+// Per-alignment buffers come from the device's stream-ordered pool (release threshold = never), so
+// creating and destroying an alignment per analysis costs microseconds, not cudaMalloc/cudaFree syncs.
+#define DMALLOC(ptr, bytes) cudaMallocAsync((void **)(ptr), (bytes), c->stream)
+#define DFREE(ptr) cudaFreeAsync((ptr), c->stream)
+
 struct tdna_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -42,12 +47,18 @@ struct tdna_ctx {
     void *progress_user = nullptr;
     volatile int cancel = 0;
     unsigned long long *d_counter = nullptr;
+    // the N x N (or band x N) distance buffer is pooled per context: alignments come and go (one per
+    // analysis in the host layer) but 10s of GB of cudaMalloc/cudaFree per call would dominate e2e.
+    double *d_mat = nullptr;
+    int64_t mat_cap = 0;              // doubles
+    const void *mat_owner = nullptr;  // alignment whose whole-range matrix currently sits in d_mat
 };
 
 struct tdna_aln {
     tdna_ctx *ctx = nullptr;
     int64_t n = 0, npad = 0;
-    int L = 0, W = 0, sym_stride = 0;
+    int L = 0, W = 0;
+    int64_t sym_stride = 0;
     uint8_t *d_sym = nullptr;
     int32_t *d_len = nullptr;
     uint32_t *d_planes = nullptr;
@@ -57,13 +68,14 @@ struct tdna_aln {
     int32_t *d_species = nullptr, *d_genus = nullptr, *d_epi = nullptr, *d_full = nullptr;
     bool has_labels = false;
     int64_t row_begin = 0, row_end = 0;
-    double *d_mat = nullptr;
-    int64_t mat_cap = 0;  // doubles
+    double *d_mat = nullptr;  // == ctx->d_mat once ensure_mat ran
     int64_t ld = 0;
-    bool mat_valid = false;  // d_mat holds the whole row range for the current config
+    bool mat_valid = false;  // ctx->d_mat holds the whole row range of THIS alignment for the current config
     tdna_row_result *d_res = nullptr;
     int64_t *d_prefix = nullptr;
     int64_t prefix_cap = 0;
+    void *d_scratch = nullptr;  // grow-only staging for host-destined compaction outputs
+    size_t scratch_cap = 0;
 };
 
 namespace {
@@ -115,9 +127,9 @@ int pack(tdna_aln *a) {
     }
     size_t words = (size_t)a->npad * P * a->W;
     if (words > a->planes_words) {
-        if (a->d_planes) CU(cudaFree(a->d_planes));
+        if (a->d_planes) CU(DFREE(a->d_planes));
         a->d_planes = nullptr;
-        CU(cudaMalloc(&a->d_planes, words * 4));
+        CU(DMALLOC(&a->d_planes, words * 4));
         a->planes_words = words;
     }
     int *d_err = reinterpret_cast<int *>(c->d_counter);
@@ -160,9 +172,9 @@ template <int KM, bool WC> int launch_tiles_t(tdna_aln *a, int64_t b0, int64_t b
             prefix[t + 1] = prefix[t] + (p.nct > first ? p.nct - first : 0);
         }
         if (a->prefix_cap < nrt + 1) {
-            if (a->d_prefix) CU(cudaFree(a->d_prefix));
+            if (a->d_prefix) CU(DFREE(a->d_prefix));
             a->d_prefix = nullptr;
-            CU(cudaMalloc(&a->d_prefix, (size_t)(nrt + 1) * 8));
+            CU(DMALLOC(&a->d_prefix, (size_t)(nrt + 1) * 8));
             a->prefix_cap = nrt + 1;
         }
         CU(cudaMemcpyAsync(a->d_prefix, prefix.data(), (size_t)(nrt + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -214,15 +226,18 @@ int64_t band_rows_for(tdna_aln *a) {
 }
 
 int ensure_mat(tdna_aln *a, int64_t rows) {
+    tdna_ctx *c = a->ctx;
     int64_t need = round_up(rows, TM) * a->ld;
-    if (need > a->mat_cap) {
-        if (a->d_mat) CU(cudaFree(a->d_mat));
-        a->d_mat = nullptr;
-        a->mat_cap = 0;
-        CU(cudaMalloc(&a->d_mat, (size_t)need * 8));
-        a->mat_cap = need;
-        a->mat_valid = false;
+    if (need > c->mat_cap) {
+        if (c->d_mat) CU(cudaFree(c->d_mat));
+        c->d_mat = nullptr;
+        c->mat_cap = 0;
+        c->mat_owner = nullptr;
+        CU(cudaMalloc(&c->d_mat, (size_t)need * 8));
+        c->mat_cap = need;
     }
+    if (c->mat_owner != a) a->mat_valid = false;
+    a->d_mat = c->d_mat;
     return TDNA_OK;
 }
 
@@ -243,6 +258,7 @@ template <class F> int for_each_band(tdna_aln *a, F consume) {
         if (c->cancel) { c->cancel = 0; return fail(TDNA_E_CANCELLED, "cancelled"); }
         if (!(whole && a->mat_valid)) {
             bool symmetric = whole && a->row_begin == 0 && a->row_end == a->n;
+            c->mat_owner = a;
             TRY(launch_tiles(a, b0, b1, symmetric, a->d_mat, a->ld, nullptr));
             a->mat_valid = whole;
         }
@@ -251,6 +267,27 @@ template <class F> int for_each_band(tdna_aln *a, F consume) {
             CU(cudaStreamSynchronize(c->stream));
             c->progress(b1 - a->row_begin, rows, c->progress_user);
         }
+    }
+    return TDNA_OK;
+}
+
+bool is_device_ptr(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice;
+}
+
+int ensure_scratch(tdna_aln *a, size_t bytes) {
+    if (bytes > a->scratch_cap) {
+        tdna_ctx *c = a->ctx;
+        if (a->d_scratch) CU(DFREE(a->d_scratch));
+        a->d_scratch = nullptr;
+        a->scratch_cap = 0;
+        CU(DMALLOC(&a->d_scratch, bytes));
+        a->scratch_cap = bytes;
     }
     return TDNA_OK;
 }
@@ -282,6 +319,10 @@ int32_t tdna_init(int32_t device, tdna_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&c->d_counter, 64));
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     uint16_t lut[256];
     build_lut(lut);
     CU(cudaMemcpyToSymbol(c_symlut, lut, sizeof(lut)));
@@ -293,6 +334,7 @@ int32_t tdna_shutdown(tdna_ctx *c) {
     if (!c) return TDNA_OK;
     cudaSetDevice(c->device);
     if (c->d_counter) cudaFree(c->d_counter);
+    if (c->d_mat) cudaFree(c->d_mat);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return TDNA_OK;
@@ -330,15 +372,15 @@ int32_t tdna_alignment_create(tdna_ctx *c, const uint8_t *symbols, int64_t n, in
     a->n = n;
     a->L = L;
     a->W = (L + 31) / 32;
-    a->sym_stride = a->W * 32;
+    a->sym_stride = row_stride;  // one contiguous copy at PCIe speed; the pack kernel reads the caller's layout
     a->npad = round_up(n, TM);
     a->ld = round_up(n, 16);
     a->row_begin = 0;
     a->row_end = n;
-    CU(cudaMalloc(&a->d_sym, (size_t)n * a->sym_stride));
-    CU(cudaMemsetAsync(a->d_sym, '?', (size_t)n * a->sym_stride, c->stream));
-    CU(cudaMemcpy2DAsync(a->d_sym, a->sym_stride, symbols, row_stride, L, n, cudaMemcpyDefault, c->stream));
-    CU(cudaMalloc(&a->d_len, (size_t)n * 4));
+    size_t sym_bytes = (size_t)(n - 1) * row_stride + L;
+    CU(DMALLOC(&a->d_sym, sym_bytes));
+    CU(cudaMemcpyAsync(a->d_sym, symbols, sym_bytes, cudaMemcpyDefault, c->stream));
+    CU(DMALLOC(&a->d_len, (size_t)n * 4));
     if (lengths) {
         CU(cudaMemcpyAsync(a->d_len, lengths, (size_t)n * 4, cudaMemcpyDefault, c->stream));
     } else {
@@ -358,11 +400,12 @@ int32_t tdna_alignment_create(tdna_ctx *c, const uint8_t *symbols, int64_t n, in
 
 int32_t tdna_alignment_destroy(tdna_aln *a) {
     if (!a) return TDNA_OK;
-    cudaSetDevice(a->ctx->device);
-    cudaStreamSynchronize(a->ctx->stream);
-    void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_mat, a->d_res, a->d_prefix};
+    tdna_ctx *c = a->ctx;
+    cudaSetDevice(c->device);
+    if (c->mat_owner == a) c->mat_owner = nullptr;
+    void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch};
     for (void *p : ptrs)
-        if (p) cudaFree(p);
+        if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
     delete a;
     return TDNA_OK;
 }
@@ -376,7 +419,7 @@ int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const 
     int32_t **dst[] = {&a->d_species, &a->d_genus, &a->d_epi, &a->d_full};
     const int32_t *src[] = {species_id, genus_id, epithet_rank, fullname_rank};
     for (int i = 0; i < 4; i++) {
-        if (!*dst[i]) CU(cudaMalloc(dst[i], bytes));
+        if (!*dst[i]) CU(DMALLOC(dst[i], bytes));
         CU(cudaMemcpyAsync(*dst[i], src[i], bytes, cudaMemcpyDefault, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
@@ -426,7 +469,7 @@ int32_t tdna_pair(tdna_aln *a, int64_t i, int64_t j, tdna_counts *counts, double
     tdna_ctx *c = a->ctx;
     CU(cudaSetDevice(c->device));
     struct Scratch { double d; tdna_counts c; } *dev;
-    CU(cudaMalloc(&dev, sizeof(Scratch)));
+    CU(DMALLOC(&dev, sizeof(Scratch)));
     int rc = row_query(a, i, j, j + 1, &dev->d, nullptr, &dev->c);
     if (rc == TDNA_OK) {
         Scratch h;
@@ -438,7 +481,7 @@ int32_t tdna_pair(tdna_aln *a, int64_t i, int64_t j, tdna_counts *counts, double
             if (counts) *counts = h.c;
         }
     }
-    cudaFree(dev);
+    DFREE(dev);
     return rc;
 }
 
@@ -449,8 +492,8 @@ int32_t tdna_row_distances(tdna_aln *a, int64_t q, double *d, int32_t *shared) {
     CU(cudaSetDevice(c->device));
     double *dd;
     int32_t *ds = nullptr;
-    CU(cudaMalloc(&dd, (size_t)a->n * 8));
-    if (shared) CU(cudaMalloc(&ds, (size_t)a->n * 4));
+    CU(DMALLOC(&dd, (size_t)a->n * 8));
+    if (shared) CU(DMALLOC(&ds, (size_t)a->n * 4));
     int rc = row_query(a, q, 0, a->n, dd, ds, nullptr);
     if (rc == TDNA_OK) {
         cudaError_t e = cudaMemcpyAsync(d, dd, (size_t)a->n * 8, cudaMemcpyDefault, c->stream);
@@ -458,8 +501,8 @@ int32_t tdna_row_distances(tdna_aln *a, int64_t q, double *d, int32_t *shared) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
     }
-    cudaFree(dd);
-    if (ds) cudaFree(ds);
+    DFREE(dd);
+    if (ds) DFREE(ds);
     return rc;
 }
 
@@ -475,8 +518,9 @@ int32_t tdna_matrix(tdna_aln *a, double *d, tdna_counts *counts) {
         if (band > cb) band = cb;
         TRY(ensure_mat(a, band));
         a->mat_valid = false;
+        c->mat_owner = nullptr;
         tdna_counts *dc;
-        CU(cudaMalloc(&dc, (size_t)band * a->n * sizeof(tdna_counts)));
+        CU(DMALLOC(&dc, (size_t)band * a->n * sizeof(tdna_counts)));
         int rc = TDNA_OK;
         for (int64_t b0 = a->row_begin; b0 < a->row_end && rc == TDNA_OK; b0 += band) {
             int64_t b1 = b0 + band < a->row_end ? b0 + band : a->row_end;
@@ -489,7 +533,7 @@ int32_t tdna_matrix(tdna_aln *a, double *d, tdna_counts *counts) {
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
             if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
         }
-        cudaFree(dc);
+        DFREE(dc);
         return rc;
     }
     TRY(for_each_band(a, [&](int64_t b0, int64_t b1) -> int {
@@ -516,9 +560,10 @@ int32_t tdna_best_match_compute(tdna_aln *a, const tdna_row_result **out_dev) {
     tdna_ctx *c = a->ctx;
     CU(cudaSetDevice(c->device));
     TRY(need_labels(a));
-    if (!a->d_res) CU(cudaMalloc(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+    if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
     TRY(for_each_band(a, [&](int64_t b0, int64_t b1) -> int {
-        row_summary_kernel<<<(unsigned)(b1 - b0), 256, 0, c->stream>>>(a->d_mat, a->ld, a->n, b0, a->d_species, a->d_res);
+        int64_t grid = (b1 - b0) < c->sm_count ? (b1 - b0) : c->sm_count;
+        row_summary_kernel<<<(unsigned)grid, RS_THREADS, 0, c->stream>>>(a->d_mat, a->ld, a->n, b0, b1 - b0, a->d_species, a->d_res);
         c->launches++;
         CU(cudaGetLastError());
         return TDNA_OK;
@@ -558,7 +603,15 @@ int32_t tdna_class_distances(tdna_aln *a, int32_t klass, float *out, int64_t cap
     TRY(need_labels(a));
     CU(cudaMemsetAsync(c->d_counter, 0, 8, c->stream));
     float *dout = nullptr;
-    if (out && cap > 0) CU(cudaMalloc(&dout, (size_t)cap * 4));
+    bool direct = false;
+    if (out && cap > 0) {
+        direct = is_device_ptr(out);  // a device destination is written by the kernel itself
+        if (direct) dout = out;
+        else {
+            TRY(ensure_scratch(a, (size_t)cap * 4));
+            dout = reinterpret_cast<float *>(a->d_scratch);
+        }
+    }
     int rc = for_each_band(a, [&](int64_t b0, int64_t b1) -> int {
         unsigned gy = (unsigned)((a->n + 256 * 8 - 1) / (256 * 8));
         if (gy > 65535) gy = 65535;
@@ -573,13 +626,13 @@ int32_t tdna_class_distances(tdna_aln *a, int32_t klass, float *out, int64_t cap
     if (rc == TDNA_OK) {
         cudaError_t e = cudaMemcpyAsync(&cnt, c->d_counter, 8, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e == cudaSuccess && dout) {
+        if (e == cudaSuccess && dout && !direct) {
             int64_t m = (int64_t)cnt < cap ? (int64_t)cnt : cap;
-            e = cudaMemcpy(out, dout, (size_t)m * 4, cudaMemcpyDefault);
+            e = cudaMemcpyAsync(out, dout, (size_t)m * 4, cudaMemcpyDefault, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         }
         if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
     }
-    if (dout) cudaFree(dout);
     *n_out = (int64_t)cnt;
     return rc;
 }
@@ -593,9 +646,9 @@ int32_t tdna_edges_below(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double
     double *dd = nullptr;
     bool want = ii && jj && d && cap > 0;
     if (want) {
-        CU(cudaMalloc(&di, (size_t)cap * 4));
-        CU(cudaMalloc(&dj, (size_t)cap * 4));
-        CU(cudaMalloc(&dd, (size_t)cap * 8));
+        CU(DMALLOC(&di, (size_t)cap * 4));
+        CU(DMALLOC(&dj, (size_t)cap * 4));
+        CU(DMALLOC(&dd, (size_t)cap * 8));
     }
     int rc = for_each_band(a, [&](int64_t b0, int64_t b1) -> int {
         unsigned gy = (unsigned)((a->n + 256 * 8 - 1) / (256 * 8));
@@ -618,9 +671,9 @@ int32_t tdna_edges_below(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double
         }
         if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
     }
-    if (di) cudaFree(di);
-    if (dj) cudaFree(dj);
-    if (dd) cudaFree(dd);
+    if (di) DFREE(di);
+    if (dj) DFREE(dj);
+    if (dd) DFREE(dd);
     *n_out = (int64_t)cnt;
     return rc;
 }
@@ -631,7 +684,7 @@ int32_t tdna_valid_conspecifics(tdna_aln *a, uint8_t *has_valid) {
     CU(cudaSetDevice(c->device));
     TRY(need_labels(a));
     uint8_t *dv;
-    CU(cudaMalloc(&dv, (size_t)a->n));
+    CU(DMALLOC(&dv, (size_t)a->n));
     CU(cudaMemsetAsync(dv, 0, (size_t)a->n, c->stream));
     int rc = for_each_band(a, [&](int64_t b0, int64_t b1) -> int {
         valid_consp_kernel<<<(unsigned)(b1 - b0), 256, 0, c->stream>>>(a->d_mat, a->ld, a->n, b0, a->d_species, dv);
@@ -645,7 +698,7 @@ int32_t tdna_valid_conspecifics(tdna_aln *a, uint8_t *has_valid) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
     }
-    cudaFree(dv);
+    DFREE(dv);
     return rc;
 }
 
@@ -661,6 +714,7 @@ int32_t tdna_time_matrix_kernel(tdna_aln *a, int32_t reps, float *ms_per_launch)
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
+    c->mat_owner = a;
     TRY(launch_tiles(a, a->row_begin, a->row_end, symmetric, a->d_mat, a->ld, nullptr));  // warm
     CU(cudaEventRecord(e0, c->stream));
     for (int r = 0; r < reps; r++) TRY(launch_tiles(a, a->row_begin, a->row_end, symmetric, a->d_mat, a->ld, nullptr));

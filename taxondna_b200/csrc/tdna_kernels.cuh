@@ -16,7 +16,7 @@ struct PlaneBits {
 __constant__ uint16_t c_symlut[256];  // symbol -> SymBit set; 0x8000 = not in the alphabet
 
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len,
-                                                   int64_t n, int64_t npad, int sym_stride, int W, int P, PlaneBits bits,
+                                                   int64_t n, int64_t npad, int64_t sym_stride, int W, int P, PlaneBits bits,
                                                    uint32_t *__restrict__ planes, int *__restrict__ err) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= npad * W) return;
@@ -25,15 +25,12 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ s
     uint32_t w[6] = {0, 0, 0, 0, 0, 0};
     if (row < n) {
         int l = len[row];
-        const uint4 *src = reinterpret_cast<const uint4 *>(sym + row * (int64_t)sym_stride + 32 * k);
-        uint4 v0 = src[0], v1 = src[1];
-        uint32_t raw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const uint8_t *src = sym + row * sym_stride + 32 * k;  // rows keep the caller's stride: no alignment assumed
         bool bad = false;
 #pragma unroll
         for (int b = 0; b < 32; b++) {
-            uint32_t s = (raw[b >> 2] >> (8 * (b & 3))) & 0xffu;
-            uint32_t cls = c_symlut[s];
-            if (32 * k + b >= l) cls = 0;  // beyond the row's own length == '?' (Sequence.java:1326-1327)
+            uint32_t cls = 0;  // beyond the row's own length == '?' (Sequence.java:1326-1327)
+            if (32 * k + b < l) cls = c_symlut[__ldg(src + b)];
             bad |= (cls & 0x8000u) != 0;
 #pragma unroll
             for (int p = 0; p < 6; p++) w[p] |= ((cls & bits.b[p]) ? 1u : 0u) << b;
@@ -341,117 +338,230 @@ __device__ __forceinline__ bool is_near(double d, double ref) {
     return d != ref && diff < TDNA_NEAR;
 }
 
-__global__ void __launch_bounds__(256) row_summary_kernel(const double *__restrict__ mat, int64_t ld, int64_t n, int64_t row_begin,
-                                                          const int32_t *__restrict__ species, tdna_row_result *__restrict__ out) {
-    __shared__ Key kscratch[8];
-    __shared__ int iscratch[8];
-    const int64_t q = row_begin + blockIdx.x;
-    const double *row = mat + (int64_t)blockIdx.x * ld;
-    const int spq = species[q];
-    const bool qnamed = spq >= 0;
+// (key, species) pairs: the two smallest keys among NAMED columns with DISTINCT species.  Mergeable,
+// so one sweep yields both the best named match and the first entry of another species (the end of
+// BlockAnalysis' leading run) without knowing species(best) in advance.
+struct Top2 {
+    Key k1, k2;
+    int s1, s2;
+};
+__device__ __forceinline__ void top2_insert(Top2 &t, const Key &k, int s) {
+    if (k.hi == TDNA_KEY_NONE) return;
+    if (s == t.s1) { if (key_less(k, t.k1)) t.k1 = k; }
+    else if (key_less(k, t.k1)) { t.k2 = t.k1; t.s2 = t.s1; t.k1 = k; t.s1 = s; }
+    else if (s == t.s2) { if (key_less(k, t.k2)) t.k2 = k; }
+    else if (key_less(k, t.k2)) { t.k2 = k; t.s2 = s; }
+}
+__device__ __forceinline__ Top2 top2_shfl_xor(const Top2 &t, int m) {
+    Top2 r;
+    r.k1 = key_shfl_xor(t.k1, m);
+    r.k2 = key_shfl_xor(t.k2, m);
+    r.s1 = __shfl_xor_sync(0xffffffffu, t.s1, m);
+    r.s2 = __shfl_xor_sync(0xffffffffu, t.s2, m);
+    return r;
+}
 
-    // ---- sweep 1: arg-min keys --------------------------------------------------------------
-    Key kb = {TDNA_KEY_NONE, TDNA_KEY_NONE}, kc = kb, ka = kb;
-    int nvalid = 0, nonfinite = 0;
-    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-        double d = row[j];
-        if (j == q || d < 0) continue;
-        nvalid++;
-        if (!(d < __longlong_as_double(0x7ff0000000000000LL))) { nonfinite = 1; if (d != d) continue; }
-        unsigned long long bits = (unsigned long long)__double_as_longlong(d);
-        int spj = species[j];
-        bool consp = qnamed && spj == spq;  // SortedSequenceComparator: conspecific-to-query first (:236-255)
-        Key k = {bits, ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
-        kb = key_min(kb, k);
-        if (qnamed && spj >= 0) {
-            Key k2 = {bits, (unsigned long long)j};
-            if (consp) kc = key_min(kc, k2); else ka = key_min(ka, k2);
+constexpr int RS_THREADS = 512;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_UNROLL = 4;  // independent 16-byte loads in flight per thread (64 KB per SM)
+
+struct RowAgg {  // everything sweep 1 produces
+    Key kb, kc, ka;
+    Top2 t2;
+    int nvalid, nonfinite;
+};
+__device__ __forceinline__ void agg_merge(RowAgg &a, const RowAgg &o) {
+    a.kb = key_min(a.kb, o.kb);
+    a.kc = key_min(a.kc, o.kc);
+    a.ka = key_min(a.ka, o.ka);
+    top2_insert(a.t2, o.t2.k1, o.t2.s1);
+    top2_insert(a.t2, o.t2.k2, o.t2.s2);
+    a.nvalid += o.nvalid;
+    a.nonfinite |= o.nonfinite;
+}
+__device__ __forceinline__ RowAgg agg_shfl_xor(const RowAgg &a, int m) {
+    RowAgg r;
+    r.kb = key_shfl_xor(a.kb, m);
+    r.kc = key_shfl_xor(a.kc, m);
+    r.ka = key_shfl_xor(a.ka, m);
+    r.t2 = top2_shfl_xor(a.t2, m);
+    r.nvalid = __shfl_xor_sync(0xffffffffu, a.nvalid, m);
+    r.nonfinite = __shfl_xor_sync(0xffffffffu, a.nonfinite, m);
+    return r;
+}
+
+// Two sweeps per query row, the second one out of L2: the grid is persistent with ONE 512-thread CTA
+// per SM so that the rows in flight (148 x N x 8 B) stay L2-resident between the sweeps.
+__global__ void __launch_bounds__(RS_THREADS, 1) row_summary_kernel(const double *__restrict__ mat, int64_t ld, int64_t n, int64_t row_begin,
+                                                                   int64_t rows, const int32_t *__restrict__ species,
+                                                                   tdna_row_result *__restrict__ out) {
+    __shared__ RowAgg s_agg[RS_WARPS];
+    __shared__ RowAgg s_final;
+    __shared__ int s_cnt[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const int64_t stride = (int64_t)RS_THREADS * 2;
+
+    for (int64_t qb = blockIdx.x; qb < rows; qb += gridDim.x) {
+        const int64_t q = row_begin + qb;
+        const double *row = mat + qb * ld;
+        const int spq = species[q];
+        const bool qnamed = spq >= 0;
+
+        // ---- sweep 1 (HBM): arg-min keys -------------------------------------------------------
+        Key none = {TDNA_KEY_NONE, TDNA_KEY_NONE};
+        RowAgg g = {none, none, none, {none, none, -2, -2}, 0, 0};
+        for (int64_t base = (int64_t)threadIdx.x * 2; base < n; base += stride * RS_UNROLL) {
+            double2 v[RS_UNROLL];
+            int2 sp2[RS_UNROLL];
+#pragma unroll
+            for (int u = 0; u < RS_UNROLL; u++) {
+                const int64_t j0 = base + u * stride;
+                if (j0 < n) {  // ld is a multiple of 16: the pair is in bounds and 16-byte aligned
+                    v[u] = *reinterpret_cast<const double2 *>(row + j0);
+                    sp2[u] = (j0 + 1 < n) ? *reinterpret_cast<const int2 *>(species + j0) : make_int2(species[j0], -1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RS_UNROLL; u++) {
+                const int64_t j0 = base + u * stride;
+                if (j0 >= n) continue;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int64_t j = j0 + e;
+                    const double d = e ? v[u].y : v[u].x;
+                    const int spj = e ? sp2[u].y : sp2[u].x;
+                    if (j >= n || j == q || d < 0) continue;
+                    g.nvalid++;
+                    if (!(d < INF)) { g.nonfinite = 1; if (d != d) continue; }
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+                    const bool consp = qnamed && spj == spq;  // SortedSequenceComparator: conspecific-to-query first (:236-255)
+                    // fast reject: larger than every running minimum this column could still replace (NONE = all ones)
+                    unsigned long long thr = g.kb.hi;
+                    if (spj >= 0) {
+                        thr = max(thr, g.t2.k2.hi);
+                        if (qnamed) thr = max(thr, consp ? g.kc.hi : g.ka.hi);
+                    }
+                    if (bits > thr) continue;
+                    Key k = {bits, ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
+                    g.kb = key_min(g.kb, k);
+                    if (spj >= 0) {
+                        top2_insert(g.t2, k, spj);
+                        if (qnamed) {
+                            Key k2 = {bits, (unsigned long long)j};
+                            if (consp) g.kc = key_min(g.kc, k2); else g.ka = key_min(g.ka, k2);
+                        }
+                    }
+                }
+            }
         }
-    }
-    kb = block_key_min(kb, kscratch);
-    kc = block_key_min(kc, kscratch);
-    ka = block_key_min(ka, kscratch);
-    nvalid = block_sum(nvalid, iscratch);
-    nonfinite = block_sum(nonfinite, iscratch);
-    const bool has_b = kb.hi != TDNA_KEY_NONE, has_c = kc.hi != TDNA_KEY_NONE, has_a = ka.hi != TDNA_KEY_NONE;
-    const int jb = has_b ? (int)(kb.lo & 0xffffffffu) : -1;
-    const double db = has_b ? __longlong_as_double((long long)kb.hi) : -1.0;
-    const double dc = has_c ? __longlong_as_double((long long)kc.hi) : -1.0;
-    const double da = has_a ? __longlong_as_double((long long)ka.hi) : -1.0;
-    const int spb = has_b ? species[jb] : -1;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) { RowAgg o = agg_shfl_xor(g, m); agg_merge(g, o); }
+        __syncthreads();  // the previous row's readers of the shared arrays are done
+        if (lane == 0) s_agg[warp] = g;
+        if (threadIdx.x < 16) s_cnt[threadIdx.x] = (threadIdx.x == 2) ? 0x7fffffff : (threadIdx.x == 3 ? -1 : 0);
+        __syncthreads();
+        if (warp == 0) {  // one warp folds the 32 per-warp partials
+            RowAgg ident = {none, none, none, {none, none, -2, -2}, 0, 0};
+            g = lane < RS_WARPS ? s_agg[lane] : ident;
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) { RowAgg o = agg_shfl_xor(g, m); agg_merge(g, o); }
+            if (lane == 0) s_final = g;
+        }
+        __syncthreads();
+        g = s_final;
+        const Key kb = g.kb, kc = g.kc, ka = g.ka;
+        const bool has_b = kb.hi != TDNA_KEY_NONE, has_c = kc.hi != TDNA_KEY_NONE, has_a = ka.hi != TDNA_KEY_NONE;
+        const int jb = has_b ? (int)(kb.lo & 0xffffffffu) : -1;
+        const double db = has_b ? __longlong_as_double((long long)kb.hi) : -1.0;
+        const double dc = has_c ? __longlong_as_double((long long)kc.hi) : -1.0;
+        const double da = has_a ? __longlong_as_double((long long)ka.hi) : -1.0;
+        const int spb = has_b ? species[jb] : -1;
+        // first named entry of a species other than species(best): if best is named it IS t2.k1
+        const Key ko = (has_b && spb >= 0) ? g.t2.k2 : g.t2.k1;
+        const bool has_o = has_b && ko.hi != TDNA_KEY_NONE;
+        const double dother = has_o ? __longlong_as_double((long long)ko.hi) : -1.0;
 
-    // ---- sweep 2: tie class of the best match, near-tie windows, end of the species block ------
-    int ties = 0, tie_unnamed = 0, smin = 0x7fffffff, smax = -1;
-    int near_b = 0, near_c = 0, near_a = 0, un_c = 0, un_a = 0;
-    Key ko = {TDNA_KEY_NONE, TDNA_KEY_NONE};
-    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-        double d = row[j];
-        if (j == q || d < 0 || d != d) continue;
-        int spj = species[j];
+        // ---- sweep 2 (L2): tie class, near-tie windows, leading same-species run ----------------
         if (has_b) {
-            if (d == db && j != jb) {
-                ties++;
-                if (spj < 0) tie_unnamed++; else { smin = min(smin, spj); smax = max(smax, spj); }
+            int ties = 0, tie_unnamed = 0, smin = 0x7fffffff, smax = -1;
+            int near_b = 0, near_c = 0, near_a = 0, near_o = 0, un_c = 0, un_a = 0, un_o = 0, block = 0;
+            // nothing beyond the largest reference distance plus the near-tie window is ever counted
+            const double dmax = fmax(fmax(db, dc), fmax(da, dother)) + TDNA_NEAR;
+            for (int64_t base = (int64_t)threadIdx.x * 2; base < n; base += stride * RS_UNROLL) {
+                double2 v[RS_UNROLL];
+                int2 sp2[RS_UNROLL];
+#pragma unroll
+                for (int u = 0; u < RS_UNROLL; u++) {
+                    const int64_t j0 = base + u * stride;
+                    if (j0 < n) {
+                        v[u] = *reinterpret_cast<const double2 *>(row + j0);
+                        sp2[u] = (j0 + 1 < n) ? *reinterpret_cast<const int2 *>(species + j0) : make_int2(species[j0], -1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < RS_UNROLL; u++) {
+                    const int64_t j0 = base + u * stride;
+                    if (j0 >= n) continue;
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int64_t j = j0 + e;
+                        const double d = e ? v[u].y : v[u].x;
+                        const int spj = e ? sp2[u].y : sp2[u].x;
+                        if (j >= n || j == q || d < 0 || !(d <= dmax)) continue;
+                        if (d == db && j != jb) {
+                            ties++;
+                            if (spj < 0) tie_unnamed++; else { smin = min(smin, spj); smax = max(smax, spj); }
+                        }
+                        near_b += is_near(d, db);
+                        if (has_c) { near_c += is_near(d, dc); un_c += (spj < 0 && d == dc); }
+                        if (has_a) { near_a += is_near(d, da); un_a += (spj < 0 && d == da); }
+                        if (has_o) { near_o += is_near(d, dother); un_o += (spj < 0 && d == dother); }
+                        if (j != jb && spj >= 0 && spj == spb) {
+                            const bool consp = qnamed && spj == spq;
+                            Key k = {(unsigned long long)__double_as_longlong(d), ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
+                            if (!has_o || key_less(k, ko)) block++;
+                        }
+                    }
+                }
             }
-            near_b += is_near(d, db);
-            if (spj >= 0 && spj != spb && j != jb) {
-                bool consp = qnamed && spj == spq;
-                Key k = {(unsigned long long)__double_as_longlong(d), ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
-                ko = key_min(ko, k);
+            int vals[10] = {ties, tie_unnamed, near_b, near_c, near_a, near_o, un_c, un_a, un_o, block};
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+                for (int i = 0; i < 10; i++) vals[i] += __shfl_xor_sync(0xffffffffu, vals[i], m);
+                smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, m));
+                smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, m));
+            }
+            if (lane == 0) {
+                if (vals[0]) atomicAdd(&s_cnt[0], vals[0]);
+                if (vals[1]) atomicAdd(&s_cnt[1], vals[1]);
+                if (smin != 0x7fffffff) atomicMin(&s_cnt[2], smin);
+                if (smax >= 0) atomicMax(&s_cnt[3], smax);
+#pragma unroll
+                for (int i = 2; i < 10; i++)
+                    if (vals[i]) atomicAdd(&s_cnt[2 + i], vals[i]);
             }
         }
-        if (has_c) { near_c += is_near(d, dc); un_c += (spj < 0 && d == dc); }
-        if (has_a) { near_a += is_near(d, da); un_a += (spj < 0 && d == da); }
-    }
-    ties = block_sum(ties, iscratch);
-    tie_unnamed = block_sum(tie_unnamed, iscratch);
-    smin = block_min_i(smin, iscratch);
-    smax = block_max_i(smax, iscratch);
-    near_b = block_sum(near_b, iscratch);
-    near_c = block_sum(near_c, iscratch);
-    near_a = block_sum(near_a, iscratch);
-    un_c = block_sum(un_c, iscratch);
-    un_a = block_sum(un_a, iscratch);
-    ko = block_key_min(ko, kscratch);
-    const bool has_o = ko.hi != TDNA_KEY_NONE;
-    const double dother = has_o ? __longlong_as_double((long long)ko.hi) : -1.0;
-
-    // ---- sweep 3: length of the leading same-species run (BlockAnalysis.java:282-294) ----------
-    int block = 0, near_o = 0, un_o = 0;
-    if (has_b) {
-        for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-            double d = row[j];
-            if (j == q || d < 0 || d != d) continue;
-            int spj = species[j];
-            if (has_o) { near_o += is_near(d, dother); un_o += (spj < 0 && d == dother); }
-            if (j != jb && spj >= 0 && spj == spb) {
-                bool consp = qnamed && spj == spq;
-                Key k = {(unsigned long long)__double_as_longlong(d), ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
-                if (!has_o || key_less(k, ko)) block++;
-            }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tdna_row_result r;
+            r.d_best = db; r.d_con = dc; r.d_allo = da; r.d_other = dother;
+            r.best = jb;
+            r.con = has_c ? (int)(kc.lo & 0xffffffffu) : -1;
+            r.allo = has_a ? (int)(ka.lo & 0xffffffffu) : -1;
+            r.other = has_o ? (int)(ko.lo & 0xffffffffu) : -1;
+            r.shared_con = 0; r.shared_allo = 0;  // filled by fill_shared_kernel
+            r.tie_count = s_cnt[0]; r.tie_unnamed = s_cnt[1]; r.tie_species_min = s_cnt[2]; r.tie_species_max = s_cnt[3];
+            r.near_best = s_cnt[4]; r.near_con = s_cnt[5]; r.near_allo = s_cnt[6]; r.near_other = s_cnt[7];
+            r.unnamed_at_con = s_cnt[8]; r.unnamed_at_allo = s_cnt[9]; r.unnamed_at_other = s_cnt[10];
+            r.block_count = s_cnt[11];
+            r.n_valid = g.nvalid;
+            double dself = row[q];
+            r.flags = (!(dself < 0) ? TDNA_ROW_SELF_VALID : 0) | (g.nonfinite ? TDNA_ROW_NONFINITE : 0);
+            r.reserved = 0;
+            out[q] = r;
         }
-    }
-    block = block_sum(block, iscratch);
-    near_o = block_sum(near_o, iscratch);
-    un_o = block_sum(un_o, iscratch);
-
-    if (threadIdx.x == 0) {
-        tdna_row_result r;
-        r.d_best = db; r.d_con = dc; r.d_allo = da; r.d_other = dother;
-        r.best = jb;
-        r.con = has_c ? (int)(kc.lo & 0xffffffffu) : -1;
-        r.allo = has_a ? (int)(ka.lo & 0xffffffffu) : -1;
-        r.other = has_o ? (int)(ko.lo & 0xffffffffu) : -1;
-        r.shared_con = 0; r.shared_allo = 0;  // filled by fill_shared_kernel
-        r.tie_count = ties; r.tie_species_min = smin; r.tie_species_max = smax; r.tie_unnamed = tie_unnamed;
-        r.block_count = block;
-        r.near_best = near_b; r.near_con = near_c; r.near_allo = near_a; r.near_other = near_o;
-        r.unnamed_at_con = un_c; r.unnamed_at_allo = un_a; r.unnamed_at_other = un_o;
-        r.n_valid = nvalid;
-        double dself = row[q];
-        r.flags = (!(dself < 0) ? TDNA_ROW_SELF_VALID : 0) | (nonfinite ? TDNA_ROW_NONFINITE : 0);
-        r.reserved = 0;
-        out[q] = r;
     }
 }
 

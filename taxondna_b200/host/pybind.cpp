@@ -1,0 +1,158 @@
+// pybind11 view of the host layer so that the parity tests read like the reference's own tests
+// (Sequence("1", "AAAA...").getSharedLength(seq2) == 10, BestMatch(list).run(), ...).
+#include <pybind11/functional.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "taxondna_host.hpp"
+
+namespace py = pybind11;
+using namespace taxondna;
+
+PYBIND11_MODULE(_host, m) {
+    m.doc() = "TaxonDNA distance-path host layer over libtaxondna_cuda.so";
+    py::register_exception<SequenceException>(m, "SequenceException");
+    py::register_exception<NullPointerException>(m, "NullPointerException");
+    py::register_exception<EngineError>(m, "EngineError");
+    py::register_exception<DelayAbortedException>(m, "DelayAbortedException");
+
+    py::class_<Settings>(m, "Settings")
+        .def_static("makeLongFromDouble", &Settings::makeLongFromDouble)
+        .def_static("roundOff", &Settings::roundOff)
+        .def_static("percentage", &Settings::percentage)
+        .def_static("identical", &Settings::identical);
+    m.def("javaDouble", &javaDouble);
+    m.def("javaFloat", &javaFloat);
+    m.def("javaSort", [](std::vector<int> a, const std::function<int(int, int)> &cmp) {
+        javaSort(a, cmp);
+        return a;
+    });
+    m.def("launchCount", &DistanceEngine::launchCount);
+
+    py::class_<Sequence, SequencePtr>(m, "Sequence")
+        .def(py::init<const std::string &, const std::string &>())
+        .def_readonly_static("PDM_UNCORRECTED", &Sequence::PDM_UNCORRECTED)
+        .def_readonly_static("PDM_K2P", &Sequence::PDM_K2P)
+        .def_readonly_static("PDM_TRANS_ONLY", &Sequence::PDM_TRANS_ONLY)
+        .def_static("setMinOverlap", &Sequence::setMinOverlap)
+        .def_static("getMinOverlap", &Sequence::getMinOverlap)
+        .def_static("ambiguousBasesAllowed", &Sequence::ambiguousBasesAllowed)
+        .def_static("areAmbiguousBasesAllowed", &Sequence::areAmbiguousBasesAllowed)
+        .def_static("setPairwiseDistanceMethod", &Sequence::setPairwiseDistanceMethod)
+        .def_static("getPairwiseDistanceMethod", &Sequence::getPairwiseDistanceMethod)
+        .def_static("clearPairwiseCache", &Sequence::clearPairwiseCache)
+        .def_static("isValid", &Sequence::isValid)
+        .def_static("isAmbiguous", &Sequence::isAmbiguous)
+        .def_static("isPurine", &Sequence::isPurine)
+        .def_static("isPyrimidine", &Sequence::isPyrimidine)
+        .def("getFullName", &Sequence::getFullName)
+        .def("getDisplayName", &Sequence::getDisplayName)
+        .def("getSpeciesName", &Sequence::getSpeciesName)
+        .def("getGenusName", &Sequence::getGenusName)
+        .def("getSpeciesNameOnly", &Sequence::getSpeciesNameOnly)
+        .def("getSubspeciesName", &Sequence::getSubspeciesName)
+        .def("getGI", &Sequence::getGI)
+        .def("getWarningFlag", &Sequence::getWarningFlag)
+        .def("getLength", &Sequence::getLength)
+        .def("getSequence", &Sequence::getSequence)
+        .def("getSequenceRaw", &Sequence::getSequenceRaw)
+        .def("getPairwise", &Sequence::getPairwise)
+        .def("getPairwiseNoBuffer", &Sequence::getPairwiseNoBuffer)
+        .def("getSharedLength", &Sequence::getSharedLength)
+        .def("getOverlap", &Sequence::getOverlap)
+        .def("countIdentical", &Sequence::countIdentical)
+        .def("countTransversions", &Sequence::countTransversions)
+        .def("getK2PDistance", &Sequence::getK2PDistance)
+        .def("hasMinOverlap", &Sequence::hasMinOverlap);
+
+    py::class_<SequenceList>(m, "SequenceList")
+        .def(py::init<>())
+        .def(py::init<const std::vector<SequencePtr> &>())
+        .def_static("readFasta", &SequenceList::readFasta)
+        .def_static("fromFastaText", &SequenceList::fromFastaText)
+        .def_readonly_static("SORT_BYNAME", &SequenceList::SORT_BYNAME)
+        .def("add", &SequenceList::add)
+        .def("count", &SequenceList::count)
+        .def("get", &SequenceList::get)
+        .def("resort", &SequenceList::resort)
+        .def("names", [](const SequenceList &l) {
+            std::vector<std::string> v;
+            for (auto &s : l.sequences()) v.push_back(s->getFullName());
+            return v;
+        })
+        .def("matrix", [](const SequenceList &l) {
+            auto d = l.engine().matrix();
+            int64_t n = l.count();
+            py::array_t<double> a({n, n});
+            std::memcpy(a.mutable_data(), d.data(), d.size() * 8);
+            return a;
+        })
+        .def("speciesIds", [](const SequenceList &l) { return l.engine().speciesId(); });
+
+    py::class_<SortedSequenceList>(m, "SortedSequenceList")
+        .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
+        .def("sortAgainst", [](SortedSequenceList &s, const SequencePtr &q) { s.sortAgainst(q, nullptr); })
+        .def("count", &SortedSequenceList::count)
+        .def("get", &SortedSequenceList::get)
+        .def("getQuery", &SortedSequenceList::getQuery)
+        .def("getDistance", &SortedSequenceList::getDistance)
+        .def("position", &SortedSequenceList::position);
+
+    py::class_<PairwiseDistribution, std::shared_ptr<PairwiseDistribution>>(m, "PairwiseDistribution")
+        .def(py::init([](const SequenceList &l, int type) { return std::make_shared<PairwiseDistribution>(l, type, nullptr); }))
+        .def_readonly_static("PD_INTRA", &PairwiseDistribution::PD_INTRA)
+        .def_readonly_static("PD_INTER", &PairwiseDistribution::PD_INTER)
+        .def("countSequences", &PairwiseDistribution::countSequences)
+        .def("countValidComparisons", &PairwiseDistribution::countValidComparisons)
+        .def("getZero", &PairwiseDistribution::getZero)
+        .def("getOne", &PairwiseDistribution::getOne)
+        .def("getDistributionAsString", &PairwiseDistribution::getDistributionAsString)
+        .def("getBetween", &PairwiseDistribution::getBetween)
+        .def("getBetweenIncl", &PairwiseDistribution::getBetweenIncl)
+        .def("getMaximumDistance", &PairwiseDistribution::getMaximumDistance)
+        .def("getMinimumDistance", &PairwiseDistribution::getMinimumDistance)
+        .def("getDistancesBetween", &PairwiseDistribution::getDistancesBetween);
+
+    py::class_<BestMatch>(m, "BestMatch")
+        .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
+        .def("setThreshold", &BestMatch::setThreshold)
+        .def("run", [](BestMatch &b) { return b.run(nullptr); })
+        .def_readwrite("force_exact", &BestMatch::force_exact)
+        .def_readonly("rows_resolved_on_host", &BestMatch::rows_resolved_on_host)
+        .def_readonly("best_match_correct", &BestMatch::best_match_correct)
+        .def_readonly("best_match_ambiguous", &BestMatch::best_match_ambiguous)
+        .def_readonly("best_match_incorrect", &BestMatch::best_match_incorrect)
+        .def_readonly("best_close_match_correct", &BestMatch::best_close_match_correct)
+        .def_readonly("best_close_match_nomatch", &BestMatch::best_close_match_nomatch)
+        .def_readonly("count_no_matches", &BestMatch::count_no_matches);
+
+    py::class_<BlockAnalysis>(m, "BlockAnalysis")
+        .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
+        .def("setThreshold", &BlockAnalysis::setThreshold)
+        .def("run", [](BlockAnalysis &b) { return b.run(nullptr); })
+        .def_readwrite("force_exact", &BlockAnalysis::force_exact)
+        .def_readonly("rows_resolved_on_host", &BlockAnalysis::rows_resolved_on_host)
+        .def_readonly("block_correct", &BlockAnalysis::block_correct)
+        .def_readonly("block_ambiguous", &BlockAnalysis::block_ambiguous);
+
+    py::class_<PairwiseSummary>(m, "PairwiseSummary")
+        .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
+        .def("run", [](PairwiseSummary &p) { return p.run(nullptr); })
+        .def("getFivePercentCutoff", &PairwiseSummary::getFivePercentCutoff)
+        .def("getPD_intra", &PairwiseSummary::getPD_intra)
+        .def("getPD_inter", &PairwiseSummary::getPD_inter);
+
+    py::class_<Cluster::Stat>(m, "ClusterStat")
+        .def_readonly("size", &Cluster::Stat::size)
+        .def_readonly("largest_pairwise", &Cluster::Stat::largest_pairwise)
+        .def_readonly("valid_comparisons", &Cluster::Stat::valid_comparisons)
+        .def_readonly("valid_comparisons_over", &Cluster::Stat::valid_comparisons_over)
+        .def_readonly("percentage", &Cluster::Stat::percentage);
+    py::class_<Cluster>(m, "Cluster")
+        .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
+        .def("setThreshold", &Cluster::setThreshold)
+        .def("run", [](Cluster &c) { c.run(nullptr); })
+        .def("clusters", &Cluster::clusters)
+        .def("stats", &Cluster::stats);
+}

@@ -1,0 +1,1390 @@
+// Implementation of the host layer (see taxondna_host.hpp).  Reference lines are cited per function.
+#include "taxondna_host.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <regex>
+#include <sstream>
+#include <unordered_map>
+
+namespace taxondna {
+
+// ------------------------------------------------------------------------------------------------
+// Settings (Common/DNA/Settings.java:69-97)
+// ------------------------------------------------------------------------------------------------
+static int64_t javaD2L(double d) {  // JLS 5.1.3 narrowing: NaN -> 0, saturating
+    if (d != d) return 0;
+    if (d >= 9223372036854775807.0) return INT64_MAX;
+    if (d <= -9223372036854775808.0) return INT64_MIN;
+    return (int64_t)d;
+}
+int64_t Settings::makeLongFromDouble(double d) { return javaD2L(d * 100000); }
+double Settings::makeDoubleFromLong(int64_t i) { return (double)i / (double)100000; }
+double Settings::roundOff(double d) { return makeDoubleFromLong(makeLongFromDouble(d)); }
+double Settings::percentage(double x, double y) {
+    if (y == 0) return 0;
+    return (double)(javaD2L(roundOff(x / y) * 100 * 100)) / 100;
+}
+bool Settings::identical(double d1, double d2) { return makeLongFromDouble(d1) == makeLongFromDouble(d2); }
+
+// ------------------------------------------------------------------------------------------------
+// Double.toString / Float.toString: shortest digits that round-trip (JDK >= 19), Java's layout
+// ------------------------------------------------------------------------------------------------
+template <class T> static std::string javaFloating(T x) {
+    if (x != x) return "NaN";
+    if (std::isinf(x)) return x > 0 ? "Infinity" : "-Infinity";
+    std::string sign = std::signbit(x) ? "-" : "";
+    T ax = std::fabs(x);
+    if (ax == 0) return sign + "0.0";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, ax, std::chars_format::scientific);
+    std::string s(buf, r.ptr);  // d.ddddde[+-]XX, shortest
+    size_t e = s.find('e');
+    std::string mant = s.substr(0, e);
+    int exp10 = std::atoi(s.c_str() + e + 1);
+    std::string digits;
+    for (char ch : mant)
+        if (ch != '.') digits.push_back(ch);
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    int pointPos = exp10 + 1;  // value = 0.DIGITS * 10^pointPos
+    if (ax >= (T)1e-3 && ax < (T)1e7) {
+        std::string body;
+        if (pointPos <= 0) body = "0." + std::string(-pointPos, '0') + digits;
+        else if (pointPos >= (int)digits.size()) body = digits + std::string(pointPos - digits.size(), '0') + ".0";
+        else body = digits.substr(0, pointPos) + "." + digits.substr(pointPos);
+        return sign + body;
+    }
+    std::string m = digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : "0");
+    return sign + m + "E" + std::to_string(exp10);
+}
+std::string javaDouble(double x) { return javaFloating<double>(x); }
+std::string javaFloat(float x) { return javaFloating<float>(x); }
+
+// ------------------------------------------------------------------------------------------------
+// Sequence: statics
+// ------------------------------------------------------------------------------------------------
+static std::atomic<int> g_method{Sequence::PDM_UNCORRECTED}, g_minOverlap{300};
+static std::atomic<bool> g_ambig{true};
+static std::atomic<uint64_t> g_nextId{1};
+
+void Sequence::setMinOverlap(int v) { g_minOverlap = v; }
+int Sequence::getMinOverlap() { return g_minOverlap; }
+bool Sequence::areAmbiguousBasesAllowed() { return g_ambig; }
+void Sequence::ambiguousBasesAllowed(bool now) { g_ambig = now; }
+int Sequence::getPairwiseDistanceMethod() { return g_method; }
+void Sequence::setPairwiseDistanceMethod(int m) { g_method = m; }
+void Sequence::clearPairwiseCache() {}
+
+// ------------------------------------------------------------------------------------------------
+// Sequence: characters (Sequence.java:927-1237)
+// ------------------------------------------------------------------------------------------------
+bool Sequence::isValid(char ch) {
+    if (ch > 'a' && ch < 'z') ch = (char)(ch - ('a' - 'A'));
+    return std::strchr("ACTGRYKMSNBDHVW-?_", ch) != nullptr && ch != 0;
+}
+bool Sequence::isAmbiguous(char ch) {
+    if (ch > 'a' && ch < 'z') ch = (char)(ch - ('a' - 'A'));
+    return std::strchr("RYKMSNBDHVW", ch) != nullptr && ch != 0;
+}
+bool Sequence::isPurine(char ch) { return ch == 'R' || ch == 'A' || ch == 'G'; }
+bool Sequence::isPyrimidine(char ch) { return ch == 'Y' || ch == 'T' || ch == 'C'; }
+int Sequence::getint(char ch) {
+    if (ch >= 'a' && ch <= 'z') ch = (char)(ch - ('a' - 'A'));
+    int r = 0;
+    if (std::strchr("ARMNDHVW", ch) && ch) r |= 1;
+    if (std::strchr("CYMSNBHV", ch) && ch) r |= 2;
+    if (std::strchr("TYKNBDHW", ch) && ch) r |= 4;
+    if (std::strchr("GRKSNBDV", ch) && ch) r |= 8;
+    return r;
+}
+char Sequence::getcode(int v) {
+    static const char tbl[17] = "-ACMTWYHGRSVKDBN";
+    return tbl[v & 15];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sequence: names (Sequence.java:668-742, 236-271, 446-471)
+// ------------------------------------------------------------------------------------------------
+static std::string trim(const std::string &s) {  // String.trim(): chars <= ' '
+    size_t a = 0, b = s.size();
+    while (a < b && (unsigned char)s[a] <= ' ') a++;
+    while (b > a && (unsigned char)s[b - 1] <= ' ') b--;
+    return s.substr(a, b - a);
+}
+
+Sequence::Sequence(const std::string &name, const std::string &seq) {
+    changeName(name);
+    std::string up = seq;
+    for (auto &ch : up)
+        if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);
+    changeSequence(trim(up));
+}
+
+void Sequence::changeName(const std::string &nameIn) {
+    static const std::regex p3("([A-Z][a-z]+) ([a-z]+) ([a-z]+)\\b"), p2("([A-Z][a-z]+) ([a-z]+)\\b"),
+        psp("([A-Z][a-z]+) ([a-z]+)\\.\\b"), pgi("gi\\|([0-9]+)[\\|:]"), pfam("\\(family:\\s*([A-Za-z]+)\\s*\\)");
+    std::string name = nameIn;
+    std::replace(name.begin(), name.end(), '\n', ' ');
+    name = trim(name);
+    name_ = name;
+    genus_ = species_ = subspecies_ = gi_ = family_ = "";
+    warning_ = false;
+    std::smatch m;
+    if (std::regex_search(name, m, p3)) {
+        genus_ = m[1];
+        species_ = m[2];
+        subspecies_ = m[3];
+    } else if (std::regex_search(name, m, p2)) {
+        genus_ = m[1];
+        species_ = m[2];
+    } else if (std::regex_search(name, m, psp)) {
+        genus_ = m[1];
+        species_ = m[2];
+        warning_ = true;
+    }
+    if (genus_.empty()) warning_ = true;
+    if (std::regex_search(name, m, pgi)) gi_ = m[1];
+    if (std::regex_search(name, m, pfam)) family_ = m[1];
+}
+
+void Sequence::changeSequence(const std::string &in) {
+    std::string seq = in;
+    for (auto &ch : seq)
+        if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);
+    std::string buf;
+    for (size_t x = 0; x < seq.size(); x++) {
+        char ch = seq[x];
+        if (ch == '(' || ch == '[') {  // :761-796
+            int single = 0;
+            for (size_t y = x + 1; y < seq.size(); y++, x++) {
+                ch = seq[y];
+                if (ch == '(' || ch == '[')
+                    throw SequenceException(name_ + ": Character '" + ch + "' found unexpectedly while inside a ambiguous base");
+                else if (ch == ')' || ch == ']') break;
+                else {
+                    if (!isValid(ch)) throw SequenceException(name_ + ": Invalid character '" + ch + "' found in sequence.");
+                    single |= getint(ch);
+                }
+            }
+            x++;
+            buf.push_back(getcode(single));
+        } else buf.push_back(ch);
+    }
+    int stopped = 0;
+    for (size_t x = 0; x < buf.size(); x++) {  // :806-823
+        if (buf[x] == '_') throw SequenceException(name_ + ": You may not use '_' in a sequence (index " + std::to_string(x) + ")");
+        else if (buf[x] == '-') { stopped = (int)x; buf[x] = '_'; }
+        else if (buf[x] == '?') continue;
+        else break;
+    }
+    for (int x = (int)buf.size() - 1; x >= 0; x--) {  // :825-840
+        if (buf[x] == '_') {
+            if (stopped == x) break;
+            throw SequenceException(name_ + ": You may not use '_' in a sequence (index " + std::to_string(x) + ")");
+        } else if (buf[x] == '-') buf[x] = '_';
+        else if (buf[x] == '?') continue;
+        else break;
+    }
+    for (size_t x = 0; x < buf.size(); x++) {  // doSanityChecks :1727-1763
+        if (buf[x] == 'U' || buf[x] == 'u') throw SequenceException(name_ + ": Uracil at index " + std::to_string(x));
+        if (!isValid(buf[x])) throw SequenceException(name_ + ": An illegal base '" + buf[x] + "' at index " + std::to_string(x));
+    }
+    seq_ = buf;
+    id_ = g_nextId++;  // a new UUID (:848-852): any device binding is stale now
+    home_ = nullptr;
+    home_row_ = -1;
+}
+
+std::optional<std::string> Sequence::getSpeciesName() const {
+    if (species_.empty() || genus_.empty()) return std::nullopt;
+    return genus_ + " " + species_;
+}
+std::optional<std::string> Sequence::getGI() const {
+    if (gi_.empty()) return std::nullopt;
+    return gi_;
+}
+std::string Sequence::getDisplayName() const {
+    if (warning_) return "{" + name_.substr(0, std::min<size_t>(name_.size(), 80)) + "}";
+    if (!getGI()) return name_;
+    if (auto sp = getSpeciesName()) {
+        std::string n = *sp;
+        if (!subspecies_.empty()) n += " (" + subspecies_ + ")";
+        if (!family_.empty()) n += " (Family " + family_ + ")";
+        n += " (gi:" + gi_ + ")";
+        return n;
+    }
+    return name_;
+}
+std::string Sequence::getSequence() const {
+    std::string s = seq_;
+    std::replace(s.begin(), s.end(), '_', '-');
+    return s;
+}
+static int compareToIgnoreCase(const std::string &a, const std::string &b) {  // String.compareToIgnoreCase (ASCII)
+    size_t n = std::min(a.size(), b.size());
+    for (size_t i = 0; i < n; i++) {
+        unsigned char ca = a[i], cb = b[i];
+        if (ca != cb) {
+            int ua = std::toupper(ca), ub = std::toupper(cb);
+            if (ua != ub) {
+                int la = std::tolower(ua), lb = std::tolower(ub);
+                if (la != lb) return la - lb;
+            }
+        }
+    }
+    return (int)a.size() - (int)b.size();
+}
+int Sequence::compareByDisplayName(const Sequence &o) const {
+    if (o.warning_ && !warning_) return -1;
+    if (!o.warning_ && warning_) return 1;
+    return compareToIgnoreCase(getDisplayName(), o.getDisplayName());
+}
+
+// ------------------------------------------------------------------------------------------------
+// the CUDA library
+// ------------------------------------------------------------------------------------------------
+static void ck(int rc) {
+    if (rc != TDNA_OK) {
+        if (rc == TDNA_E_CANCELLED) throw DelayAbortedException();
+        throw EngineError(std::string("taxondna_cuda: ") + tdna_last_error());
+    }
+}
+static tdna_ctx *g_ctx = nullptr;
+static std::atomic<uint64_t> g_gen{1};
+tdna_ctx *DistanceEngine::context() {
+    if (!g_ctx) {
+        const char *dev = std::getenv("TDNA_DEVICE");
+        ck(tdna_init(dev ? std::atoi(dev) : 0, &g_ctx));  // throws without a GPU: there is no CPU path
+    }
+    return g_ctx;
+}
+int64_t DistanceEngine::launchCount() { return g_ctx ? tdna_launch_count(g_ctx) : 0; }
+
+// builds the normalised, '?'-padded symbol matrix of a set of sequences
+static void packSymbols(const std::vector<const Sequence *> &seqs, std::vector<uint8_t> &sym, std::vector<int32_t> &len, int &L) {
+    L = 1;
+    for (auto s : seqs) L = std::max(L, s->getLength());
+    sym.assign((size_t)seqs.size() * L, (uint8_t)'?');
+    len.resize(seqs.size());
+    for (size_t i = 0; i < seqs.size(); i++) {
+        const std::string &r = seqs[i]->getSequenceRaw();
+        std::memcpy(&sym[i * (size_t)L], r.data(), r.size());
+        len[i] = (int32_t)r.size();
+    }
+}
+
+DistanceEngine::DistanceEngine(const SequenceList &list) {
+    n_ = list.count();
+    gen_ = g_gen++;
+    if (n_ == 0) return;
+    std::vector<const Sequence *> ptrs;
+    for (auto &s : list.sequences()) ptrs.push_back(s.get());
+    std::vector<uint8_t> sym;
+    std::vector<int32_t> len;
+    int L;
+    packSymbols(ptrs, sym, len, L);
+    ck(tdna_alignment_create(context(), sym.data(), n_, L, L, len.data(), &aln_));
+    // labels: ids of species / genus strings, ranks of epithets and full names under String.compareTo
+    std::map<std::string, int> spIds, genIds;
+    std::vector<int32_t> genus(n_), epi(n_), full(n_);
+    species_id_.resize(n_);
+    std::vector<std::string> epis, fulls;
+    for (auto s : ptrs) {
+        epis.push_back(s->getSpeciesNameOnly());
+        fulls.push_back(s->getFullName());
+    }
+    auto ranks = [](std::vector<std::string> v) {
+        std::vector<std::string> u = v;
+        std::sort(u.begin(), u.end());  // byte order == String.compareTo for ASCII / Latin-1 names
+        u.erase(std::unique(u.begin(), u.end()), u.end());
+        std::vector<int32_t> r(v.size());
+        for (size_t i = 0; i < v.size(); i++) r[i] = (int32_t)(std::lower_bound(u.begin(), u.end(), v[i]) - u.begin());
+        return r;
+    };
+    epi = ranks(epis);
+    full = ranks(fulls);
+    for (int64_t i = 0; i < n_; i++) {
+        auto sp = ptrs[i]->getSpeciesName();
+        species_id_[i] = sp ? spIds.emplace(*sp, (int)spIds.size()).first->second : -1;
+        genus[i] = genIds.emplace(ptrs[i]->getGenusName(), (int)genIds.size()).first->second;
+        ptrs[i]->home_ = this;
+        ptrs[i]->home_row_ = i;
+        ptrs[i]->home_gen_ = gen_;
+    }
+    ck(tdna_alignment_set_labels(aln_, species_id_.data(), genus.data(), epi.data(), full.data()));
+}
+DistanceEngine::~DistanceEngine() {
+    if (aln_) tdna_alignment_destroy(aln_);
+}
+void DistanceEngine::syncConfig() const {
+    int m = g_method, o = g_minOverlap, a = g_ambig ? 1 : 0;
+    if (m != cfg_mode_ || o != cfg_overlap_ || a != cfg_ambig_) {
+        ck(tdna_set_config(aln_, m, o, a));
+        cfg_mode_ = m;
+        cfg_overlap_ = o;
+        cfg_ambig_ = a;
+    }
+}
+tdna_counts DistanceEngine::pair(int64_t i, int64_t j, double *d) const {
+    syncConfig();
+    tdna_counts c;
+    ck(tdna_pair(aln_, i, j, &c, d));
+    return c;
+}
+void DistanceEngine::rowDistances(int64_t q, std::vector<double> &d, std::vector<int32_t> *shared) const {
+    syncConfig();
+    d.resize(n_);
+    if (shared) shared->resize(n_);
+    ck(tdna_row_distances(aln_, q, d.data(), shared ? shared->data() : nullptr));
+}
+std::vector<double> DistanceEngine::matrix() const {
+    syncConfig();
+    std::vector<double> d((size_t)n_ * n_);
+    ck(tdna_matrix(aln_, d.data(), nullptr));
+    return d;
+}
+std::vector<tdna_row_result> DistanceEngine::bestMatch() const {
+    syncConfig();
+    std::vector<tdna_row_result> r(n_);
+    ck(tdna_best_match(aln_, r.data()));
+    return r;
+}
+std::vector<float> DistanceEngine::classDistances(int klass) const {
+    syncConfig();
+    int64_t cnt = 0;
+    ck(tdna_class_distances(aln_, klass, nullptr, 0, &cnt));
+    std::vector<float> out((size_t)std::max<int64_t>(cnt, 1));
+    int64_t got = 0;
+    ck(tdna_class_distances(aln_, klass, out.data(), cnt, &got));
+    out.resize((size_t)cnt);
+    return out;
+}
+void DistanceEngine::edgesBelow(double t, std::vector<int32_t> &ii, std::vector<int32_t> &jj, std::vector<double> &d) const {
+    syncConfig();
+    int64_t cnt = 0;
+    ck(tdna_edges_below(aln_, t, nullptr, nullptr, nullptr, 0, &cnt));
+    ii.resize((size_t)std::max<int64_t>(cnt, 1));
+    jj.resize(ii.size());
+    d.resize(ii.size());
+    int64_t got = 0;
+    ck(tdna_edges_below(aln_, t, ii.data(), jj.data(), d.data(), cnt, &got));
+    ii.resize((size_t)cnt);
+    jj.resize((size_t)cnt);
+    d.resize((size_t)cnt);
+}
+std::vector<uint8_t> DistanceEngine::validConspecifics() const {
+    syncConfig();
+    std::vector<uint8_t> v(n_);
+    ck(tdna_valid_conspecifics(aln_, v.data()));
+    return v;
+}
+
+// One pair.  If both sequences sit in the same live device alignment it is one tdna_pair call on it;
+// free-standing sequences (the reference's own KATs build two and compare them, Sequence.java:1913-1955)
+// get a transient two-row alignment.  Either way the arithmetic is the CUDA library's.
+tdna_counts Sequence::pairCounts(const Sequence &o, double *d, int mode) const {
+    if (home_ && home_ == o.home_ && home_gen_ == home_->generation() && o.home_gen_ == home_gen_ && mode == g_method)
+        return home_->pair(home_row_, o.home_row_, d);
+    std::vector<uint8_t> sym;
+    std::vector<int32_t> len;
+    int L;
+    packSymbols({this, &o}, sym, len, L);
+    tdna_aln *a = nullptr;
+    ck(tdna_alignment_create(DistanceEngine::context(), sym.data(), 2, L, L, len.data(), &a));
+    tdna_counts c;
+    int rc = tdna_set_config(a, mode, g_minOverlap, g_ambig ? 1 : 0);
+    if (rc == TDNA_OK) rc = tdna_pair(a, 0, 1, &c, d);
+    tdna_alignment_destroy(a);
+    ck(rc);
+    return c;
+}
+double Sequence::getPairwiseNoBuffer(const Sequence &o) const {
+    double d;
+    pairCounts(o, &d, g_method);
+    return d;
+}
+double Sequence::getPairwise(const Sequence &o) const { return getPairwiseNoBuffer(o); }  // the cache (:1587-1672) is gone: one launch is cheaper than its Hashtable
+int Sequence::getSharedLength(const Sequence &o) const { return pairCounts(o, nullptr, g_method).shared; }
+int Sequence::countIdentical(const Sequence &o) const { return pairCounts(o, nullptr, PDM_UNCORRECTED).c1; }
+int Sequence::countTransversions(const Sequence &o) const { return pairCounts(o, nullptr, PDM_TRANS_ONLY).c1; }
+double Sequence::getK2PDistance(const Sequence &o) const {
+    // getK2PDistance itself has no overlap gate (:1498-1573): evaluate with minOverlap 0
+    std::vector<uint8_t> sym;
+    std::vector<int32_t> len;
+    int L;
+    packSymbols({this, &o}, sym, len, L);
+    tdna_aln *a = nullptr;
+    ck(tdna_alignment_create(DistanceEngine::context(), sym.data(), 2, L, L, len.data(), &a));
+    double d = 0;
+    int rc = tdna_set_config(a, PDM_K2P, 0, g_ambig ? 1 : 0);
+    if (rc == TDNA_OK) rc = tdna_pair(a, 0, 1, nullptr, &d);
+    tdna_alignment_destroy(a);
+    ck(rc);
+    return d;
+}
+bool Sequence::hasMinOverlap(const Sequence &o) const { return getOverlap(o) >= g_minOverlap; }
+
+// ------------------------------------------------------------------------------------------------
+// SequenceList
+// ------------------------------------------------------------------------------------------------
+void SequenceList::modified() {
+    sortedBy_ = SORT_UNSORTED;
+    engine_.reset();
+}
+int SequenceList::resort(int method) {
+    int prev = sortedBy_;
+    if (method == SORT_BYNAME && sortedBy_ != SORT_BYNAME) {
+        std::stable_sort(seqs_.begin(), seqs_.end(), [](const SequencePtr &a, const SequencePtr &b) { return a->compareByDisplayName(*b) < 0; });
+        engine_.reset();
+    }
+    sortedBy_ = method;
+    return prev;
+}
+DistanceEngine &SequenceList::engine() const {
+    if (!engine_) engine_ = std::make_shared<DistanceEngine>(*this);
+    return *engine_;
+}
+SequenceList SequenceList::fromFastaText(const std::string &text) {
+    SequenceList out;
+    std::string name, seq;
+    auto flush = [&]() {
+        if (name.empty()) return;
+        std::string nm = name;
+        std::replace(nm.begin(), nm.end(), '_', ' ');  // makeSequence (FastaFile.java:268-270)
+        std::string s;
+        for (char ch : seq) {
+            if (std::isspace((unsigned char)ch)) continue;
+            if (ch == 'U') ch = 'T';
+            if (ch == 'u') ch = 't';
+            s.push_back(ch);
+        }
+        out.seqs_.push_back(std::make_shared<Sequence>(nm, s));
+    };
+    std::istringstream in(text);
+    std::string line;
+    auto blank = [](const std::string &l) { return std::all_of(l.begin(), l.end(), [](char c) { return std::isspace((unsigned char)c); }); };
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (blank(line)) continue;
+        size_t f = line.find_first_not_of(" \t");
+        if (line[f] == '#') continue;
+        if (line[0] == '>') {
+            flush();
+            std::string nm = line.substr(1);
+            size_t a = nm.find_first_not_of(" \t\f\v");
+            nm = a == std::string::npos ? "" : nm.substr(a);
+            name = nm.empty() ? "No name specified in file" : nm;
+            seq.clear();
+        } else seq += trim(line);
+    }
+    flush();
+    out.modified();
+    return out;
+}
+SequenceList SequenceList::readFasta(const std::string &path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return fromFastaText(ss.str());
+}
+
+// ------------------------------------------------------------------------------------------------
+// java.util.TimSort (see the header).  MIN_MERGE 32, MIN_GALLOP 7, post-JDK-8072909 mergeCollapse.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct TimSort {
+    using Cmp = std::function<int(int, int)>;
+    std::vector<int> &a;
+    const Cmp &c;
+    int minGallop = 7;
+    std::vector<int> runBase, runLen, tmp;
+    TimSort(std::vector<int> &a_, const Cmp &c_) : a(a_), c(c_) {}
+
+    static void binarySort(std::vector<int> &a, int lo, int hi, int start, const Cmp &c) {
+        if (start == lo) start++;
+        for (; start < hi; start++) {
+            int pivot = a[start];
+            int left = lo, right = start;
+            while (left < right) {
+                int mid = (int)(((unsigned)left + (unsigned)right) >> 1);
+                if (c(pivot, a[mid]) < 0) right = mid; else left = mid + 1;
+            }
+            for (int k = start; k > left; k--) a[k] = a[k - 1];
+            a[left] = pivot;
+        }
+    }
+    static int countRunAndMakeAscending(std::vector<int> &a, int lo, int hi, const Cmp &c) {
+        int runHi = lo + 1;
+        if (runHi == hi) return 1;
+        if (c(a[runHi++], a[lo]) < 0) {
+            while (runHi < hi && c(a[runHi], a[runHi - 1]) < 0) runHi++;
+            std::reverse(a.begin() + lo, a.begin() + runHi);
+        } else {
+            while (runHi < hi && c(a[runHi], a[runHi - 1]) >= 0) runHi++;
+        }
+        return runHi - lo;
+    }
+    static int minRunLength(int n) {
+        int r = 0;
+        while (n >= 32) { r |= (n & 1); n >>= 1; }
+        return n + r;
+    }
+    static int gallopLeft(int key, const int *a, int base, int len, int hint, const Cmp &c) {
+        int lastOfs = 0, ofs = 1;
+        if (c(key, a[base + hint]) > 0) {
+            int maxOfs = len - hint;
+            while (ofs < maxOfs && c(key, a[base + hint + ofs]) > 0) { lastOfs = ofs; ofs = (ofs << 1) + 1; if (ofs <= 0) ofs = maxOfs; }
+            if (ofs > maxOfs) ofs = maxOfs;
+            lastOfs += hint; ofs += hint;
+        } else {
+            int maxOfs = hint + 1;
+            while (ofs < maxOfs && c(key, a[base + hint - ofs]) <= 0) { lastOfs = ofs; ofs = (ofs << 1) + 1; if (ofs <= 0) ofs = maxOfs; }
+            if (ofs > maxOfs) ofs = maxOfs;
+            int t = lastOfs; lastOfs = hint - ofs; ofs = hint - t;
+        }
+        lastOfs++;
+        while (lastOfs < ofs) {
+            int m = lastOfs + ((ofs - lastOfs) >> 1);
+            if (c(key, a[base + m]) > 0) lastOfs = m + 1; else ofs = m;
+        }
+        return ofs;
+    }
+    static int gallopRight(int key, const int *a, int base, int len, int hint, const Cmp &c) {
+        int ofs = 1, lastOfs = 0;
+        if (c(key, a[base + hint]) < 0) {
+            int maxOfs = hint + 1;
+            while (ofs < maxOfs && c(key, a[base + hint - ofs]) < 0) { lastOfs = ofs; ofs = (ofs << 1) + 1; if (ofs <= 0) ofs = maxOfs; }
+            if (ofs > maxOfs) ofs = maxOfs;
+            int t = lastOfs; lastOfs = hint - ofs; ofs = hint - t;
+        } else {
+            int maxOfs = len - hint;
+            while (ofs < maxOfs && c(key, a[base + hint + ofs]) >= 0) { lastOfs = ofs; ofs = (ofs << 1) + 1; if (ofs <= 0) ofs = maxOfs; }
+            if (ofs > maxOfs) ofs = maxOfs;
+            lastOfs += hint; ofs += hint;
+        }
+        lastOfs++;
+        while (lastOfs < ofs) {
+            int m = lastOfs + ((ofs - lastOfs) >> 1);
+            if (c(key, a[base + m]) < 0) ofs = m; else lastOfs = m + 1;
+        }
+        return ofs;
+    }
+    void mergeCollapse() {
+        while (runLen.size() > 1) {
+            int n = (int)runLen.size() - 2;
+            if ((n > 0 && runLen[n - 1] <= runLen[n] + runLen[n + 1]) || (n > 1 && runLen[n - 2] <= runLen[n] + runLen[n - 1])) {
+                if (runLen[n - 1] < runLen[n + 1]) n--;
+            } else if (n < 0 || runLen[n] > runLen[n + 1]) break;
+            mergeAt(n);
+        }
+    }
+    void mergeForceCollapse() {
+        while (runLen.size() > 1) {
+            int n = (int)runLen.size() - 2;
+            if (n > 0 && runLen[n - 1] < runLen[n + 1]) n--;
+            mergeAt(n);
+        }
+    }
+    void mergeAt(int i) {
+        int base1 = runBase[i], len1 = runLen[i], base2 = runBase[i + 1], len2 = runLen[i + 1];
+        runLen[i] = len1 + len2;
+        runBase.erase(runBase.begin() + i + 1);
+        runLen.erase(runLen.begin() + i + 1);
+        int k = gallopRight(a[base2], a.data(), base1, len1, 0, c);
+        base1 += k; len1 -= k;
+        if (len1 == 0) return;
+        len2 = gallopLeft(a[base1 + len1 - 1], a.data(), base2, len2, len2 - 1, c);
+        if (len2 == 0) return;
+        if (len1 <= len2) mergeLo(base1, len1, base2, len2); else mergeHi(base1, len1, base2, len2);
+    }
+    [[noreturn]] static void violated() { throw std::invalid_argument("Comparison method violates its general contract!"); }
+    void mergeLo(int base1, int len1, int base2, int len2) {
+        tmp.assign(a.begin() + base1, a.begin() + base1 + len1);
+        int cursor1 = 0, cursor2 = base2, dest = base1;
+        a[dest++] = a[cursor2++];
+        if (--len2 == 0) { std::copy(tmp.begin() + cursor1, tmp.begin() + cursor1 + len1, a.begin() + dest); return; }
+        if (len1 == 1) { std::copy(a.begin() + cursor2, a.begin() + cursor2 + len2, a.begin() + dest); a[dest + len2] = tmp[cursor1]; return; }
+        int mg = minGallop;
+        bool done = false;
+        while (!done) {
+            int count1 = 0, count2 = 0;
+            do {
+                if (c(a[cursor2], tmp[cursor1]) < 0) {
+                    a[dest++] = a[cursor2++]; count2++; count1 = 0;
+                    if (--len2 == 0) { done = true; break; }
+                } else {
+                    a[dest++] = tmp[cursor1++]; count1++; count2 = 0;
+                    if (--len1 == 1) { done = true; break; }
+                }
+            } while ((count1 | count2) < mg);
+            if (done) break;
+            do {
+                count1 = gallopRight(a[cursor2], tmp.data(), cursor1, len1, 0, c);
+                if (count1 != 0) {
+                    std::copy(tmp.begin() + cursor1, tmp.begin() + cursor1 + count1, a.begin() + dest);
+                    dest += count1; cursor1 += count1; len1 -= count1;
+                    if (len1 <= 1) { done = true; break; }
+                }
+                a[dest++] = a[cursor2++];
+                if (--len2 == 0) { done = true; break; }
+                count2 = gallopLeft(tmp[cursor1], a.data(), cursor2, len2, 0, c);
+                if (count2 != 0) {
+                    std::copy(a.begin() + cursor2, a.begin() + cursor2 + count2, a.begin() + dest);  // forward copy, dest < cursor2
+                    dest += count2; cursor2 += count2; len2 -= count2;
+                    if (len2 == 0) { done = true; break; }
+                }
+                a[dest++] = tmp[cursor1++];
+                if (--len1 == 1) { done = true; break; }
+                mg--;
+            } while (count1 >= 7 || count2 >= 7);
+            if (done) break;
+            if (mg < 0) mg = 0;
+            mg += 2;
+        }
+        minGallop = mg < 1 ? 1 : mg;
+        if (len1 == 1) {
+            std::copy(a.begin() + cursor2, a.begin() + cursor2 + len2, a.begin() + dest);
+            a[dest + len2] = tmp[cursor1];
+        } else if (len1 == 0) violated();
+        else std::copy(tmp.begin() + cursor1, tmp.begin() + cursor1 + len1, a.begin() + dest);
+    }
+    void mergeHi(int base1, int len1, int base2, int len2) {
+        tmp.assign(a.begin() + base2, a.begin() + base2 + len2);
+        int cursor1 = base1 + len1 - 1, cursor2 = len2 - 1, dest = base2 + len2 - 1;
+        a[dest--] = a[cursor1--];
+        if (--len1 == 0) { std::copy(tmp.begin(), tmp.begin() + len2, a.begin() + dest - (len2 - 1)); return; }
+        if (len2 == 1) {
+            dest -= len1; cursor1 -= len1;
+            std::copy_backward(a.begin() + cursor1 + 1, a.begin() + cursor1 + 1 + len1, a.begin() + dest + 1 + len1);
+            a[dest] = tmp[cursor2];
+            return;
+        }
+        int mg = minGallop;
+        bool done = false;
+        while (!done) {
+            int count1 = 0, count2 = 0;
+            do {
+                if (c(tmp[cursor2], a[cursor1]) < 0) {
+                    a[dest--] = a[cursor1--]; count1++; count2 = 0;
+                    if (--len1 == 0) { done = true; break; }
+                } else {
+                    a[dest--] = tmp[cursor2--]; count2++; count1 = 0;
+                    if (--len2 == 1) { done = true; break; }
+                }
+            } while ((count1 | count2) < mg);
+            if (done) break;
+            do {
+                count1 = len1 - gallopRight(tmp[cursor2], a.data(), base1, len1, len1 - 1, c);
+                if (count1 != 0) {
+                    dest -= count1; cursor1 -= count1; len1 -= count1;
+                    std::copy_backward(a.begin() + cursor1 + 1, a.begin() + cursor1 + 1 + count1, a.begin() + dest + 1 + count1);
+                    if (len1 == 0) { done = true; break; }
+                }
+                a[dest--] = tmp[cursor2--];
+                if (--len2 == 1) { done = true; break; }
+                count2 = len2 - gallopLeft(a[cursor1], tmp.data(), 0, len2, len2 - 1, c);
+                if (count2 != 0) {
+                    dest -= count2; cursor2 -= count2; len2 -= count2;
+                    std::copy(tmp.begin() + cursor2 + 1, tmp.begin() + cursor2 + 1 + count2, a.begin() + dest + 1);
+                    if (len2 <= 1) { done = true; break; }
+                }
+                a[dest--] = a[cursor1--];
+                if (--len1 == 0) { done = true; break; }
+                mg--;
+            } while (count1 >= 7 || count2 >= 7);
+            if (done) break;
+            if (mg < 0) mg = 0;
+            mg += 2;
+        }
+        minGallop = mg < 1 ? 1 : mg;
+        if (len2 == 1) {
+            dest -= len1; cursor1 -= len1;
+            std::copy_backward(a.begin() + cursor1 + 1, a.begin() + cursor1 + 1 + len1, a.begin() + dest + 1 + len1);
+            a[dest] = tmp[cursor2];
+        } else if (len2 == 0) violated();
+        else std::copy(tmp.begin(), tmp.begin() + len2, a.begin() + dest - (len2 - 1));
+    }
+};
+}  // namespace
+
+void javaSort(std::vector<int> &a, const std::function<int(int, int)> &cmp) {
+    int lo = 0, hi = (int)a.size(), n = hi;
+    if (n < 2) return;
+    if (n < 32) {
+        int init = TimSort::countRunAndMakeAscending(a, lo, hi, cmp);
+        TimSort::binarySort(a, lo, hi, lo + init, cmp);
+        return;
+    }
+    TimSort ts(a, cmp);
+    int minRun = TimSort::minRunLength(n);
+    do {
+        int runLen = TimSort::countRunAndMakeAscending(a, lo, hi, cmp);
+        if (runLen < minRun) {
+            int force = n <= minRun ? n : minRun;
+            TimSort::binarySort(a, lo, lo + force, lo + runLen, cmp);
+            runLen = force;
+        }
+        ts.runBase.push_back(lo);
+        ts.runLen.push_back(runLen);
+        ts.mergeCollapse();
+        lo += runLen;
+        n -= runLen;
+    } while (n != 0);
+    ts.mergeForceCollapse();
+}
+
+// ------------------------------------------------------------------------------------------------
+// SortedSequenceList (SortedSequenceList.java:78-128, comparator :197-261)
+// ------------------------------------------------------------------------------------------------
+void SortedSequenceList::sortAgainst(const SequencePtr &query, DelayCallback *delay) {
+    if (!original_ || !query) throw std::runtime_error("sortAgainst called on a SortedSequenceList which hasn't been set up properly!");
+    query_ = query;
+    const auto &seqs = original_->sequences();
+    const int n = (int)seqs.size();
+    int q = -1;
+    for (int i = 0; i < n; i++)
+        if (seqs[i]->getId() == query->getId()) { q = i; break; }
+    if (delay) delay->begin();
+    if (q >= 0) {
+        original_->engine().rowDistances(q, dist_, nullptr);  // one launch: the row the reference builds with N getPairwise calls
+    } else {  // a query that is not in the list (QuerySequence): N single-pair calls against a transient pair
+        dist_.resize(n);
+        for (int i = 0; i < n; i++) dist_[i] = seqs[i]->getPairwise(*query);
+    }
+    sorted_.clear();
+    for (int i = 0; i < n; i++) {
+        if (delay) delay->delay(i + 1, n);
+        if (!(dist_[i] < 0)) sorted_.push_back(i);  // :114
+    }
+    std::vector<std::optional<std::string>> names(n);
+    for (int i = 0; i < n; i++) names[i] = seqs[i]->getSpeciesName();
+    auto qname = query->getSpeciesName();
+    const std::vector<double> &d = dist_;
+    javaSort(sorted_, [&](int o1, int o2) -> int {
+        double d1 = d[o1], d2 = d[o2];
+        if (d1 < 0) return +1;
+        if (d2 < 0) return -1;
+        int64_t diff = Settings::makeLongFromDouble(d1 - d2);
+        if (diff == 0) {
+            bool q1 = (o1 == q), q2 = (o2 == q);
+            if (q1 && q2) return 0;
+            else if (q1) return -1;
+            else if (q2) return +1;
+            if (!names[o1] || !names[o2]) return 0;
+            bool c1 = qname && *names[o1] == *qname, c2 = qname && *names[o2] == *qname;
+            if (c1 && c2) return 0;
+            if (c1) return -1;
+            else if (c2) return +1;
+            return 0;
+        }
+        return (int)diff;  // (int)(long): low 32 bits (:260)
+    });
+    if (delay) delay->end();
+}
+SequencePtr SortedSequenceList::get(int x) const {
+    if (x < 0 || x >= (int)sorted_.size()) return nullptr;
+    return original_->get(sorted_[x]);
+}
+double SortedSequenceList::getDistance(int x) const {
+    if (!query_) return -1;
+    return dist_[sorted_.at(x)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// PairwiseDistribution (PairwiseDistribution.java:109-152, 161-203, 247-297, 357-396)
+// ------------------------------------------------------------------------------------------------
+PairwiseDistribution::PairwiseDistribution(const SequenceList &list, int type, DelayCallback *delay) {
+    if (type != PD_INTRA && type != PD_INTER) throw std::runtime_error("Programmer Error in PairwiseDistribution");
+    if (delay) delay->begin();
+    count_sequences_ = list.count();
+    if (list.count() > 0) {
+        if (type == PD_INTRA) {
+            // conspecificIterator walks the FIRST contiguous run of the species in BYNAME order
+            // (SequenceList.java:614-658, 983-1030); the device class is "same species id", which is
+            // the same thing iff conspecifics are contiguous.  Refuse rather than differ.
+            const auto &sp = list.engine().speciesId();
+            std::unordered_map<int, int> last;
+            for (int i = 0; i < (int)sp.size(); i++) {
+                if (sp[i] < 0) continue;
+                auto it = last.find(sp[i]);
+                if (it != last.end() && it->second != i - 1)
+                    throw EngineError("conspecific sequences are not contiguous in list order (resort(SORT_BYNAME) first)");
+                last[sp[i]] = i;
+            }
+        }
+        d_ = list.engine().classDistances(type == PD_INTRA ? TDNA_PD_INTRA : TDNA_PD_INTER);
+        // Arrays.sort(float[]): numeric order, -0.0 < 0.0, NaN last
+        std::sort(d_.begin(), d_.end(), [](float a, float b) {
+            bool na = a != a, nb = b != b;
+            if (na || nb) return !na && nb;
+            if (a == b) return std::signbit(a) && !std::signbit(b);
+            return a < b;
+        });
+    }
+    if (delay) delay->end();
+}
+static bool pdIdentical(float x, float y) { return (y - x) < 0.0000001; }  // :393-396 (one-sided, float vs double literal)
+int PairwiseDistribution::getZero() const {
+    int c = 0;
+    for (float v : d_) {
+        if (pdIdentical(v, 0.0f)) c++; else break;
+    }
+    return c;
+}
+int PairwiseDistribution::getOne() const {
+    int c = 0;
+    for (int x = (int)d_.size() - 1; x >= 0; x--) {
+        if (pdIdentical(d_[x], 1.0f)) c++; else break;
+    }
+    return c;
+}
+std::vector<float> PairwiseDistribution::getDistancesBetween(double from, double to) const {
+    std::vector<float> v;
+    bool count = false;
+    for (float x : d_) {
+        if ((double)x >= from) count = true;
+        if ((double)x > to) count = false;
+        if (count) v.push_back(x);
+    }
+    return v;
+}
+int PairwiseDistribution::getBetween(double from, double to) const { return (int)getDistancesBetween(from, to - 0.000001).size(); }
+int PairwiseDistribution::getBetweenIncl(float from, float to) const { return (int)getDistancesBetween((double)from, (double)to).size(); }
+float PairwiseDistribution::getMaximumDistance() const { return d_.empty() ? 0.0f : d_.back(); }
+float PairwiseDistribution::getMinimumDistance() const { return d_.empty() ? 0.0f : d_.front(); }
+std::string PairwiseDistribution::getDistributionAsString(double d_from, double d_to, double d_interval, char dir) const {
+    bool forward = dir != CUMUL_BACKWARD;
+    std::string str;
+    auto entry = [&](const std::string &a, const std::string &b, const std::string &c, const std::string &d) { str += a + "\t" + b + "\t" + c + "\t" + d + "\t\n"; };
+    auto pc = [](double x, double y) { return javaDouble(Settings::percentage(x, y)); };
+    entry("Distances", "Freq.", "Perc.", "Cumulative");
+    int count = (int)d_.size();
+    int f_from = getBetweenIncl(0, (float)d_from);
+    float cumul = ((float)f_from / count);
+    if (!forward) cumul = 1.0f - cumul;
+    entry("<= " + pc(d_from, 1.0) + "%", std::to_string(f_from), pc(f_from, count), pc(cumul, 1.0));
+    for (double x = d_from + 0.000001; x < d_to; x += d_interval) {
+        double d_next = x + d_interval;
+        f_from = getBetweenIncl((float)x, (float)d_next);
+        if (forward) cumul += ((float)f_from / count); else cumul -= ((float)f_from / count);
+        entry(pc(x, 1) + "% to " + pc(d_next, 1) + "%", std::to_string(f_from), pc(f_from, count), pc(cumul, 1.0));
+    }
+    f_from = getBetweenIncl((float)(d_to + 0.000001), (float)1.0);
+    if (forward) cumul += ((float)f_from / count); else cumul -= ((float)f_from / count);
+    entry("> " + pc(d_to, 1.0) + "%", std::to_string(f_from), pc(f_from, count), pc(cumul, 1.0));
+    return str;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SpeciesDetails
+// ------------------------------------------------------------------------------------------------
+SpeciesDetails::SpeciesDetails(const SequenceList &list) {
+    if (list.count() == 0) return;
+    auto valid = list.engine().validConspecifics();
+    std::unordered_map<std::string, int> idx;
+    for (int i = 0; i < list.count(); i++) {
+        auto sp = list.get(i)->getSpeciesName();
+        if (!sp) continue;
+        auto it = idx.find(*sp);
+        int k;
+        if (it == idx.end()) {
+            k = (int)names.size();
+            idx[*sp] = k;
+            names.push_back(*sp);
+            sequences_count.push_back(0);
+            valid_conspecifics_count.push_back(0);
+        } else k = it->second;
+        sequences_count[k]++;
+        valid_conspecifics_count[k] += valid[i] ? 1 : 0;
+    }
+}
+int SpeciesDetails::indexOf(const std::string &name) const {
+    for (size_t i = 0; i < names.size(); i++)
+        if (names[i] == name) return (int)i;
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BestMatch.run (BestMatch.java:164-582)
+// ------------------------------------------------------------------------------------------------
+namespace {
+// What the three loops of BestMatch.run read off the sorted list for one query.
+struct QueryOutcome {
+    bool has_best = false;
+    int best = -1;
+    double best_d = 0;
+    int count_bestMatches = 0;
+    bool clean_block = false, mixed_block = false;
+    int first_con = -1, first_allo = -1;
+    double con_d = 0, allo_d = 0;
+    int con_shared = 0, allo_shared = 0;
+};
+
+// Is the streamed per-row summary provably what the reference's sort would yield?  (DESIGN.md "near ties")
+bool summaryIsExact(const tdna_row_result &r, const std::vector<int32_t> &sp) {
+    if (r.flags & TDNA_ROW_NONFINITE) return false;
+    if (r.n_valid == 0) return true;
+    if (!(r.flags & TDNA_ROW_SELF_VALID)) return false;
+    if (r.near_best != 0) return false;
+    if (!(r.d_best == 0.0 || r.d_best >= 2e-5)) return false;  // nothing may crowd the query's own 0
+    if (r.tie_count > 0 && (r.tie_unnamed > 0 || sp[r.best] < 0)) return false;
+    if (r.con >= 0 && (r.near_con != 0 || r.unnamed_at_con != 0)) return false;
+    if (r.allo >= 0 && (r.near_allo != 0 || r.unnamed_at_allo != 0)) return false;
+    return true;
+}
+}  // namespace
+
+std::string BestMatch::run(DelayCallback *delay) {
+    best_match_correct = best_match_ambiguous = best_match_incorrect = 0;
+    best_close_match_correct = best_close_match_ambiguous = best_close_match_incorrect = best_close_match_nomatch = 0;
+    count_no_matches = count_zero_percent_matches = count_allo_at_zero = count_seqs_with_valid_conspecific_matches = 0;
+    count_sequences_without_species_names = 0;
+    rows_resolved_on_host = 0;
+    const SequenceList &set = *list_;
+    const int total = set.count();
+    double threshold = threshold_percent_;
+    threshold /= 100;
+    std::string listing = "Query\tMatch\tIdentification\n";
+    if (delay) delay->begin();
+    std::vector<tdna_row_result> rows;
+    if (total > 0) rows = set.engine().bestMatch();  // ONE device pass replaces N sortAgainst calls
+    const auto &sp = set.engine().speciesId();
+    SortedSequenceList sset(set);
+    auto pc = [](double x, double y) { return javaDouble(Settings::percentage(x, y)); };
+    for (int x = 0; x < total; x++) {
+        const SequencePtr &query = set.get(x);
+        if (delay) delay->delay(x, total);
+        auto qname = query->getSpeciesName();
+        if (!qname) { count_sequences_without_species_names++; continue; }
+        QueryOutcome o;
+        const tdna_row_result &r = rows[x];
+        if (!force_exact && summaryIsExact(r, sp)) {
+            if (r.n_valid > 0) {
+                o.has_best = true;
+                o.best = r.best;
+                o.best_d = r.d_best;
+                o.count_bestMatches = r.tie_count;
+                if (r.tie_count > 0) {
+                    int spb = sp[r.best];
+                    if (r.tie_species_min == r.tie_species_max) { o.clean_block = (r.tie_species_min == spb); o.mixed_block = !o.clean_block; }
+                    else o.mixed_block = true;
+                }
+                o.first_con = r.con; o.con_d = r.d_con; o.con_shared = r.shared_con;
+                o.first_allo = r.allo; o.allo_d = r.d_allo; o.allo_shared = r.shared_allo;
+            }
+        } else {  // the reference's own procedure on this query's row (exact TimSort order)
+            rows_resolved_on_host++;
+            sset.sortAgainst(query, nullptr);
+            int cs = sset.count();
+            SequencePtr bm = sset.get(1);
+            if (bm && sset.getDistance(1) != -1) {
+                o.has_best = true;
+                o.best = sset.position(1);
+                o.best_d = sset.getDistance(1);
+                for (int y = 2; y < cs; y++) {
+                    SequencePtr match = sset.get(y);
+                    if (!Settings::identical(sset.getDistance(y), o.best_d)) break;
+                    o.count_bestMatches++;
+                    auto mn = match->getSpeciesName();
+                    if (!mn) throw NullPointerException("BestMatch.java:319: a tied match has no species name");
+                    if (bm->getSpeciesName() && *mn == *bm->getSpeciesName()) o.clean_block = true; else o.mixed_block = true;
+                }
+                std::vector<int32_t> shared;
+                bool haveShared = false;
+                std::vector<double> dd;
+                for (int y = 1; y < cs; y++) {
+                    SequencePtr match = sset.get(y);
+                    auto mn = match->getSpeciesName();
+                    if (!mn) continue;
+                    if (sset.getDistance(y) >= 0) {
+                        if (o.first_con < 0 && *mn == *qname) { o.first_con = sset.position(y); o.con_d = sset.getDistance(y); }
+                        else if (o.first_allo < 0 && *mn != *qname) { o.first_allo = sset.position(y); o.allo_d = sset.getDistance(y); }
+                        if (o.first_con >= 0 && o.first_allo >= 0) break;
+                    }
+                }
+                if (o.first_con >= 0 || o.first_allo >= 0) {
+                    set.engine().rowDistances(x, dd, &shared);
+                    haveShared = true;
+                }
+                if (haveShared && o.first_con >= 0) o.con_shared = shared[o.first_con];
+                if (haveShared && o.first_allo >= 0) o.allo_shared = shared[o.first_allo];
+            }
+        }
+        listing += query->getDisplayName();
+        if (!o.has_best) {
+            listing += "\t\tNo match.\n";
+            count_no_matches++;
+            continue;
+        }
+        const SequencePtr &bestMatch = set.get(o.best);
+        double bd = o.best_d;
+        if (Settings::identical(bd, 0)) count_zero_percent_matches++;
+        if (o.first_con >= 0) count_seqs_with_valid_conspecific_matches++;
+        if (o.first_con < 0) listing += "\tNo conspecific in database\t---\t0";
+        else listing += "\t" + set.get(o.first_con)->getDisplayName() + "\t" + pc(o.con_d, 1) + "\t" + std::to_string(o.con_shared);
+        if (o.first_allo < 0) listing += "\tNo allospecific in database\t---\t0";
+        else listing += "\t" + set.get(o.first_allo)->getDisplayName() + "\t" + pc(o.allo_d, 1) + "\t" + std::to_string(o.allo_shared);
+        bool conspecific = bestMatch->getSpeciesName() && *bestMatch->getSpeciesName() == *qname;
+        bool within = bd <= threshold;
+        const char *tail = within ? " (within threshold)\n" : " (outside threshold)\n";
+        if (!o.clean_block && !o.mixed_block) {
+            listing += "\t" + bestMatch->getDisplayName();
+            if (conspecific) {
+                listing += "\tSuccessful match at " + pc(bd, 1) + "%";
+                best_match_correct++;
+                if (within) best_close_match_correct++; else best_close_match_nomatch++;
+            } else {
+                if (Settings::identical(bd, 0)) count_allo_at_zero++;
+                listing += "\tIncorrect match at " + pc(bd, 1) + "%";
+                best_match_incorrect++;
+                if (within) best_close_match_incorrect++; else best_close_match_nomatch++;
+            }
+            listing += tail;
+        } else if (o.clean_block && !o.mixed_block) {
+            listing += "\t" + bestMatch->getDisplayName() + " and " + std::to_string(o.count_bestMatches) + " others";
+            if (conspecific) {
+                listing += "\tSuccessful match at " + pc(bd, 1) + "%";
+                best_match_correct++;
+                if (within) best_close_match_correct++; else best_close_match_nomatch++;
+            } else {
+                if (Settings::identical(bd, 0)) count_allo_at_zero++;
+                listing += "\tIncorrect match at " + pc(bd, 1) + "%";
+                best_match_incorrect++;
+                if (within) best_close_match_incorrect++; else best_close_match_nomatch++;
+            }
+            listing += tail;
+        } else {
+            if (Settings::identical(bd, 0)) count_allo_at_zero++;
+            listing += "\t" + bestMatch->getDisplayName() + " and " + std::to_string(o.count_bestMatches) +
+                       " others from different species\tMultiple species found at " + pc(bd, 1) + "%, identification with certainty is impossible";
+            best_match_ambiguous++;
+            if (within) best_close_match_ambiguous++; else best_close_match_nomatch++;
+            listing += tail;
+        }
+    }
+    int valid = total - count_no_matches - count_sequences_without_species_names;
+    auto S = [](int v) { return std::to_string(v); };
+    std::string text = "Sequences:\t" + S(total) + "\n" +
+        "Sequences without recognizable species names (ignored in all subsequent counts):\t" + S(count_sequences_without_species_names) +
+        "\nSequences with atleast one matching sequence in the data set:\t" + S(valid) + "\n" +
+        "Sequences with atleast one matching conspecific sequence in the data set:\t" + S(count_seqs_with_valid_conspecific_matches) +
+        "\nSequences with a closest match at 0%:\t" + S(count_zero_percent_matches) +
+        "\nAllospecific matches at 0%:\t" + S(count_allo_at_zero) + "\t(" + pc(count_allo_at_zero, count_zero_percent_matches) + "% of all matches at 0%)" +
+        "\n\nCorrect identifications according to \"Best Match\":\t" + S(best_match_correct) + " (" + pc(best_match_correct, valid) + "%)" +
+        "\nAmbiguous according to \"Best Match\":\t" + S(best_match_ambiguous) + " (" + pc(best_match_ambiguous, valid) + "%)" +
+        "\nIncorrect identifications according to \"Best Match\":\t" + S(best_match_incorrect) + " (" + pc(best_match_incorrect, valid) + "%)" +
+        "\n\nCorrect identifications according to \"Best Close Match\":\t" + S(best_close_match_correct) + " (" + pc(best_close_match_correct, valid) + "%)" +
+        "\nAmbiguous according to \"Best Close Match\":\t" + S(best_close_match_ambiguous) + " (" + pc(best_close_match_ambiguous, valid) + "%)" +
+        "\nIncorrect identifications according to \"Best Close Match\":\t" + S(best_close_match_incorrect) + " (" + pc(best_close_match_incorrect, valid) + "%)" +
+        "\nSequences without any match closer than " + pc(threshold, 1) + "%:\t" + S(best_close_match_nomatch) + " (" + pc(best_close_match_nomatch, valid) + "%)" +
+        "\n\n" + listing;
+    if (delay) delay->end();
+    return text;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BlockAnalysis.run (BlockAnalysis.java:179-387)
+// ------------------------------------------------------------------------------------------------
+std::string BlockAnalysis::run(DelayCallback *delay) {
+    block_correct = block_incorrect = block_ambiguous = block_nomatch = block_noseq = count_seq_without_species_name = 0;
+    rows_resolved_on_host = 0;
+    const SequenceList &set = *list_;
+    const int count_sequences = set.count();
+    double threshold = threshold_percent_;
+    threshold /= 100;
+    std::string listing = "Query\tFound in a complete block?\n", nonames = "Sequences without an identifiable species name\n";
+    SpeciesDetails sd(set);
+    if (delay) delay->begin();
+    std::vector<tdna_row_result> rows;
+    if (count_sequences > 0) rows = set.engine().bestMatch();
+    const auto &sp = set.engine().speciesId();
+    SortedSequenceList sset(set);
+    auto pc = [](double x, double y) { return javaDouble(Settings::percentage(x, y)); };
+    for (int x = 0; x < count_sequences; x++) {
+        const SequencePtr &query = set.get(x);
+        auto name_query = query->getSpeciesName();
+        if (!name_query) {
+            count_seq_without_species_name++;
+            nonames += query->getFullName() + "\n";
+            continue;
+        }
+        if (delay) delay->delay(x, count_sequences);
+        const tdna_row_result &r = rows[x];
+        int sorted_count;   // sset.count()
+        int first = -1;     // list position of sset.get(1)
+        double first_d = 0;
+        int block_size = 1;
+        bool exact_ok = !force_exact && !(r.flags & TDNA_ROW_NONFINITE) &&
+                        (r.n_valid == 0 ||
+                         ((r.flags & TDNA_ROW_SELF_VALID) && r.near_best == 0 && (r.d_best == 0.0 || r.d_best >= 2e-5) &&
+                          !(r.tie_count > 0 && (r.tie_unnamed > 0 || sp[r.best] < 0)) &&
+                          (r.other < 0 || (r.near_other == 0 && r.unnamed_at_other == 0))));
+        bool is_correct = false, is_incorrect = false, nomatches = false;
+        std::optional<std::string> name_first;
+        if (exact_ok) {
+            sorted_count = r.n_valid + ((r.flags & TDNA_ROW_SELF_VALID) ? 1 : 0);
+            if (sorted_count > 0) {
+                if (r.n_valid == 0) throw NullPointerException("BlockAnalysis.java:275: only the query survived sortAgainst");
+                first = r.best;
+                first_d = r.d_best;
+                name_first = set.get(first)->getSpeciesName();
+                if (!(first_d > threshold)) block_size = name_first ? 1 + r.block_count : 1;
+            }
+        } else {
+            rows_resolved_on_host++;
+            sset.sortAgainst(query, nullptr);
+            sorted_count = sset.count();
+            if (sorted_count > 0) {
+                if (sorted_count < 2) throw NullPointerException("BlockAnalysis.java:275: only the query survived sortAgainst");
+                first = sset.position(1);
+                first_d = sset.getDistance(1);
+                name_first = sset.get(1)->getSpeciesName();
+                if (!(first_d > threshold)) {
+                    for (int y = 2; y < sorted_count; y++) {
+                        auto mn = sset.get(y)->getSpeciesName();
+                        if (!mn) continue;
+                        if (!name_first || *mn != *name_first) break;
+                        block_size++;
+                    }
+                }
+            }
+        }
+        if (sorted_count == 0) block_noseq++;
+        else if (first_d > threshold) nomatches = true;
+        else {
+            if (block_size <= 1) block_ambiguous++;
+            else {
+                int k = sd.indexOf(*name_first);
+                int vc = sd.valid_conspecifics_count[k];
+                if (block_size == vc) {
+                    if (*name_first != *name_query) { block_incorrect++; is_incorrect = true; } else block_ambiguous++;
+                } else if (block_size == vc - 1) {
+                    if (*name_first == *name_query) { block_correct++; is_correct = true; } else block_ambiguous++;
+                } else block_ambiguous++;
+            }
+        }
+        listing += query->getFullName();
+        if (is_correct) listing += "\tcorrect\t";
+        else if (is_incorrect) listing += "\tincorrect\t";
+        else if (nomatches) { listing += "\tno match\t"; block_nomatch++; }
+        else listing += "\tambiguous\t";
+        listing += "\n";
+    }
+    int valid = count_sequences - block_noseq;
+    auto S = [](int v) { return std::to_string(v); };
+    std::string text = "Sequences:\t" + S(count_sequences) + "\nSequences without valid species names:\t" + S(count_seq_without_species_name) +
+        "\nSequences with atleast one sequence with an overlap of " + S(Sequence::getMinOverlap()) + " base pairs:\t" + S(valid) +
+        "\n\nCorrect identifications according to \"All Species Barcodes\":\t" + S(block_correct) + " (" + pc(block_correct, valid) + "%)" +
+        "\nAmbiguous according to \"All Species Barcodes\":\t" + S(block_ambiguous) + " (" + pc(block_ambiguous, valid) + "%)" +
+        "\nIncorrect identifications according to \"All Species Barcodes\":\t" + S(block_incorrect) + " (" + pc(block_incorrect, valid) + "%)" +
+        "\nSequences with no match closer than " + pc(threshold, 1) + "%:\t" + S(block_nomatch) + " (" + pc(block_nomatch, valid) + "%)" +
+        "\n\n" + listing + "\n\n" + nonames;
+    if (delay) delay->end();
+    return text;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PairwiseSummary.run (PairwiseSummary.java:109-485)
+// ------------------------------------------------------------------------------------------------
+static void padln(std::string &main, const std::string &x) {
+    main += x;
+    if (x.size() < 30) main += std::string(30 - x.size(), ' ');
+    main += "\n";
+}
+static void padln(std::string &main, const std::string &x, const std::string &y) {
+    main += x;
+    if (x.size() < 30) main += std::string(30 - x.size(), ' ');
+    main += "\t" + y + "\n";
+}
+
+std::string PairwiseSummary::run(DelayCallback *delay) {
+    const SequenceList &set = *list_;
+    five_ = 0;
+    if (set.count() < 2) return "Pairwise distributions cannot be determined for less than two sequences";
+    intra_ = std::make_shared<PairwiseDistribution>(set, PairwiseDistribution::PD_INTRA, delay);
+    inter_ = std::make_shared<PairwiseDistribution>(set, PairwiseDistribution::PD_INTER, delay);
+    PairwiseDistribution &intra = *intra_, &inter = *inter_;
+    std::map<std::string, int> species;
+    for (auto &s : set.sequences())
+        if (auto n = s->getSpeciesName()) species[*n] = 1;
+    std::string str;
+    std::string mo = std::to_string(Sequence::getMinOverlap());
+    auto pc = [](double x, double y) { return javaDouble(Settings::percentage(x, y)); };
+    padln(str, "COUNTS");
+    padln(str, "No of sequences:", std::to_string(set.count()) + "\tsequences");
+    padln(str, "No of species:", std::to_string(species.size()) + "\tspecies");
+    padln(str, "Note that minimum overlap is set to " + mo + " bp: pairs of sequences with less that " + mo +
+                   " bp overlap will not be counted as a pairwise distance for this analysis.");
+    padln(str, "\nRANGES");
+    padln(str, "WARNING: These calculations are new to Species Identifier as of June 14, 2012, and have not been comprehensively tested yet. Please use with caution!\n");
+    auto trimIntra = [](const std::vector<float> &dl) {
+        float mx = dl[dl.size() - 1];
+        size_t x = 1;
+        while (x < dl.size()) {
+            float dist = dl[dl.size() - x];
+            if ((double)((float)x / dl.size()) > 0.05) break;
+            mx = dist;
+            x++;
+        }
+        return mx;
+    };
+    auto trimInter = [](const std::vector<float> &dl, float start) {
+        float mn = start;
+        int x = 0;
+        for (float dist : dl) {
+            if ((double)((float)x / dl.size()) > 0.05) break;
+            mn = dist;
+            x++;
+        }
+        return mn;
+    };
+    if (intra.countValidComparisons() == 0) {
+        padln(str, "There are no valid intraspecific pairwise distances (i.e. no two sequences have less than " + mo + " bp overlap).");
+    } else {
+        std::vector<float> dl = intra.getDistancesBetween(0, 1);
+        if (dl.empty()) throw NullPointerException("PairwiseSummary.java:204: no intraspecific distance in [0,1]");
+        float mx = trimIntra(dl);
+        padln(str, "Intraspecific pairwise distances range between " + pc(intra.getMinimumDistance(), 1) + "% and " + pc(intra.getMaximumDistance(), 1) +
+                       "% (contains " + pc(intra.getBetweenIncl(intra.getMinimumDistance(), intra.getMaximumDistance()), intra.countValidComparisons()) +
+                       "% of all valid intraspecific pairwise distances)");
+        padln(str, "  Removing the largest 5% of intraspecific distances reduces that range to " + pc(intra.getMinimumDistance(), 1) + "% and " + pc(mx, 1) +
+                       "% (contains " + pc(intra.getBetweenIncl(intra.getMinimumDistance(), mx), intra.countValidComparisons()) +
+                       "% of all valid intraspecific pairwise distances)");
+    }
+    if (inter.countValidComparisons() == 0) {
+        padln(str, "There are no valid interspecific pairwise distances (i.e. no two sequences have less than " + mo + " bp overlap).");
+    } else {
+        std::vector<float> dl = inter.getDistancesBetween(0, 1);
+        float mn = trimInter(dl, inter.getMinimumDistance());
+        padln(str, "Interspecific, intrageneric pairwise distances range between " + pc(inter.getMinimumDistance(), 1) + "% and " + pc(inter.getMaximumDistance(), 1) +
+                       "% (contains " + pc(inter.getBetweenIncl(inter.getMinimumDistance(), inter.getMaximumDistance()), inter.countValidComparisons()) +
+                       "% of all valid interspecific, intrageneric pairwise distances)");
+        padln(str, "  Removing the largest 5% of interspecific, intrageneric distances reduces that range to " + pc(inter.getMinimumDistance(), 1) + "% and " + pc(mn, 1) +
+                       "% (contains " + pc(inter.getBetweenIncl(mn, inter.getMaximumDistance()), inter.countValidComparisons()) +
+                       "% of all valid interspecific, intrageneric pairwise distances)");
+    }
+    padln(str, "\nPERCENTAGES");
+    float min_inter = inter.getMinimumDistance(), max_intra = intra.getMaximumDistance();
+    int count_comparisons = inter.countValidComparisons() + intra.countValidComparisons();
+    float overlap = std::fabs(max_intra - min_inter);
+    if (inter.countValidComparisons() == 0) {
+        padln(str, "Total overlap:\tNo interspecific, intrageneric comparisons.\n              \tIntraspecific comparisons range from " + pc(intra.getMinimumDistance(), 1) +
+                       "% to " + pc(intra.getMaximumDistance(), 1) + "% (total width: " + pc(intra.getMaximumDistance() - intra.getMinimumDistance(), 1) + "%)");
+    } else {
+        int within = intra.getBetweenIncl(min_inter, max_intra) + inter.getBetweenIncl(min_inter, max_intra);
+        std::vector<float> dl_intra = intra.getDistancesBetween(0, 1), dl_inter = inter.getDistancesBetween(0, 1);
+        if (dl_intra.empty()) {
+            padln(str, "Total overlap:\t No intraspecific distances present.");
+            padln(str, "Overlap with 5% error margs on both ends:\t No intraspecific distances present.");
+        } else if (dl_inter.empty()) {
+            padln(str, "Total overlap:\t No interspecific distances present.");
+            padln(str, "Overlap with 5% error margs on both ends:\t No interspecific distances present.");
+        } else {
+            padln(str, "Total overlap:\t" + pc(overlap, 1) + "% (from " + pc(min_inter, 1) + "% to " + pc(max_intra, 1) + "%, covering " + pc(within, count_comparisons) +
+                           "% of all intra and interspecific but intrageneric sequences)");
+            min_inter = trimInter(dl_inter, min_inter);
+            size_t x = 1;
+            while (x < dl_intra.size()) {
+                float dist = dl_intra[dl_intra.size() - x];
+                if ((double)((float)x / dl_intra.size()) > 0.05) break;
+                max_intra = dist;
+                x++;
+            }
+            overlap = std::fabs(max_intra - min_inter);
+            within = inter.getBetweenIncl(min_inter, max_intra) + intra.getBetweenIncl(min_inter, max_intra);
+            five_ = (float)Settings::percentage(max_intra, 1);
+            padln(str, "Overlap with 5% error margins on both ends:\t " + pc(overlap, 1) + "% (from " + pc(min_inter, 1) + "% to " + pc(max_intra, 1) + "%, covering " +
+                           pc(within, count_comparisons) + "% of intra and interspecific but intrageneric sequences)");
+            padln(str, "Five percent intraspecific cutoff:\t " + javaFloat(five_) + "%");
+        }
+    }
+    padln(str, "\nDISTRIBUTION FOR ALL INTRASPECIFIC DISTANCES (FROM 0.0 TO 0.20)");
+    padln(str, intra.getDistributionAsString(0.0, 0.20, 0.005, PairwiseDistribution::CUMUL_BACKWARD));
+    padln(str, "\nDISTRIBUTION FOR ALL INTRASPECIFIC DISTANCES (FROM 0.0 TO 0.30) AT 1% intervals");
+    padln(str, intra.getDistributionAsString(0.0, 0.30, 0.01, PairwiseDistribution::CUMUL_BACKWARD));
+    padln(str, "\nDISTRIBUTION FOR ALL INTRASPECIFIC DISTANCES");
+    padln(str, intra.getDistributionAsString(0.0, 1.0, 0.05, PairwiseDistribution::CUMUL_BACKWARD));
+    padln(str, "\nDISTRIBUTION FOR ALL INTERSPECIFIC DISTANCES WITHIN A GENUS (FROM 0.0 to 0.20)");
+    padln(str, inter.getDistributionAsString(0.0, 0.20, 0.005, PairwiseDistribution::CUMUL_FORWARD));
+    padln(str, "\nDISTRIBUTION FOR ALL INTERSPECIFIC DISTANCES WITHIN A GENUS (FROM 0.0 TO 0.30) AT 1% intervals");
+    padln(str, inter.getDistributionAsString(0.0, 0.30, 0.01, PairwiseDistribution::CUMUL_FORWARD));
+    padln(str, "\nDISTRIBUTION FOR ALL INTERSPECIFIC DISTANCES WITHIN A GENUS");
+    padln(str, inter.getDistributionAsString(0.0, 1.0, 0.05, PairwiseDistribution::CUMUL_FORWARD));
+    return str;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cluster.run (Cluster.java:741-867): the device yields the edge set {0 <= d <= t}; the sequential
+// merge that fixes cluster and member ORDER is replayed on the host from the adjacency lists.
+// ------------------------------------------------------------------------------------------------
+void Cluster::run(DelayCallback *delay) {
+    const SequenceList &set = *list_;
+    const int n = set.count();
+    clusters_.clear();
+    stats_.clear();
+    if (n == 0) return;
+    if (delay) delay->begin();
+    std::vector<int32_t> ii, jj;
+    std::vector<double> dd;
+    set.engine().edgesBelow(max_pairwise_, ii, jj, dd);
+    std::vector<std::vector<int>> earlier(n);  // neighbours with a smaller list position
+    for (size_t e = 0; e < ii.size(); e++) earlier[std::max(ii[e], jj[e])].push_back(std::min(ii[e], jj[e]));
+    std::vector<std::shared_ptr<std::vector<int>>> cl;  // `clusters` Vector, in order
+    std::vector<std::shared_ptr<std::vector<int>>> owner(n);
+    for (int s = 0; s < n; s++) {
+        if (delay) delay->delay(s, n);
+        // clusters that contain a neighbour, visited from the last cluster to the first (:797-855)
+        std::vector<std::vector<int> *> hit;
+        for (int nb : earlier[s]) hit.push_back(owner[nb].get());
+        std::sort(hit.begin(), hit.end());
+        hit.erase(std::unique(hit.begin(), hit.end()), hit.end());
+        if (hit.empty()) {
+            auto v = std::make_shared<std::vector<int>>(1, s);
+            cl.push_back(v);
+            owner[s] = v;
+            continue;
+        }
+        std::shared_ptr<std::vector<int>> acc;
+        for (int ci = (int)cl.size() - 1; ci >= 0; ci--) {
+            if (!std::binary_search(hit.begin(), hit.end(), cl[ci].get())) continue;
+            if (!acc) {
+                cl[ci]->push_back(s);
+                acc = cl[ci];
+                owner[s] = acc;
+            } else {
+                for (int m : *cl[ci]) { acc->push_back(m); owner[m] = acc; }
+                cl.erase(cl.begin() + ci);
+            }
+        }
+    }
+    for (auto &c : cl) clusters_.push_back(*c);
+    // per-cluster statistics (:188-260) from the full matrix rows of the members
+    std::vector<double> row;
+    for (auto &b : clusters_) {
+        Stat st{(int)b.size(), 0.0, 0, 0, 0.0};
+        for (int a : b) {
+            if (b.size() > 1) set.engine().rowDistances(a, row, nullptr);
+            for (int c : b) {
+                if (set.get(a)->getFullName() == set.get(c)->getFullName()) continue;
+                st.valid_comparisons++;
+                double d = row[c];
+                if (d < 0) continue;
+                if (d > st.largest_pairwise) st.largest_pairwise = d;
+                if (d > max_pairwise_) st.valid_comparisons_over++;
+            }
+        }
+        if (st.valid_comparisons != 0) st.percentage = Settings::percentage(st.valid_comparisons_over, st.valid_comparisons);
+        stats_.push_back(st);
+    }
+    if (delay) delay->end();
+}
+
+}  // namespace taxondna

@@ -7,10 +7,13 @@ import os
 import numpy as np
 import pytest
 
+import sys
+
 import oracle
 from oracle import consumers as C
 
 pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 SYMS = b"ACGTRYKMSWBDHVN-_?"
 MODES = [(0, True), (0, False), (1, True), (2, True)]
@@ -160,3 +163,103 @@ def test_row_distances_and_errors(ctx):
     with pytest.raises(t.TdnaError) as ei:
         t.Alignment(ctx, bad)
     assert ei.value.code == 3  # TDNA_E_SYMBOL
+
+
+def labelled_alignment(rng, n_species, reps, L, unnamed=0, dup=0, gappy=True):
+    """Rows grouped by species (list order == BYNAME order), optional unnamed rows and exact duplicates."""
+    base = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=L)
+    rows, sp, gen = [], [], []
+    for s in range(n_species):
+        spseq = base.copy()
+        m = rng.random(L) < 0.04
+        spseq[m] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(m.sum()))
+        for _ in range(reps):
+            x = spseq.copy()
+            m = rng.random(L) < 0.01
+            x[m] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(m.sum()))
+            if gappy:
+                m = rng.random(L) < 0.05
+                x[m] = rng.choice(np.frombuffer(SYMS, dtype=np.uint8), size=int(m.sum()))
+            rows.append(x)
+            sp.append(s)
+            gen.append(s // 3)
+    for k in range(dup):  # exact duplicates of existing rows under ANOTHER species -> ties, mixed blocks
+        src = int(rng.integers(0, len(rows)))
+        rows.append(rows[src].copy())
+        sp.append((sp[src] + 1) % n_species)
+        gen.append(((sp[src] + 1) % n_species) // 3)
+    for k in range(unnamed):
+        src = int(rng.integers(0, len(rows)))
+        x = rows[src].copy()
+        x[rng.integers(0, L, size=3)] = ord("A")
+        rows.append(x)
+        sp.append(-1)
+        gen.append(10 ** 6)
+    sym = np.stack(rows)
+    species = np.array(sp, dtype=np.int32)
+    genus = np.array(gen, dtype=np.int32)
+    n = len(rows)
+    return sym, species, genus, species.copy(), np.arange(n, dtype=np.int32)
+
+
+@pytest.mark.parametrize("mode,n_species,reps,L,unnamed,dup", [(0, 6, 5, 400, 0, 0), (0, 9, 6, 700, 4, 8), (1, 9, 6, 700, 3, 6),
+                                                              (2, 5, 4, 330, 2, 2), (0, 40, 10, 658, 5, 20), (1, 40, 10, 658, 5, 20)])
+def test_row_summaries(ctx, mode, n_species, reps, L, unnamed, dup):
+    import taxondna_b200 as t
+    from ref_rows import compare, row_results
+    rng = np.random.default_rng(mode * 77 + n_species)
+    sym, sp, gen, epi, full = labelled_alignment(rng, n_species, reps, L, unnamed, dup)
+    n = sym.shape[0]
+    aln = t.Alignment(ctx, sym)
+    aln.set_labels(sp, gen, epi, full)
+    aln.set_config(mode, 200, True)
+    ref = oracle.all_pairs(sym, np.full(n, L, np.int32), mode, 200, True, threads=8)
+    exp = row_results(ref["dist"], sp)
+    res = aln.best_match()
+    compare(res, exp, ref["shared"])
+    # banded: same answers when the matrix is streamed through 128-row bands
+    ctx.set_memory_budget(1 << 20)
+    try:
+        aln.set_config(mode, 200, True)
+        res2 = aln.best_match()
+    finally:
+        ctx.set_memory_budget(64 << 30)
+    assert res2.tobytes() == res.tobytes()
+    aln.close()
+
+
+def test_class_distances_edges_and_valid_conspecifics(ctx):
+    import taxondna_b200 as t
+    rng = np.random.default_rng(11)
+    sym, sp, gen, epi, full = labelled_alignment(rng, 12, 5, 500, unnamed=3, dup=5)
+    n = sym.shape[0]
+    full = rng.permutation(n).astype(np.int32)  # arbitrary full-name order
+    full[3] = full[4]                           # two rows with EQUAL full names: pushed twice (PairwiseDistribution.java:172)
+    aln = t.Alignment(ctx, sym)
+    aln.set_labels(sp, gen, epi, full)
+    for mode in (0, 1):
+        aln.set_config(mode, 150, True)
+        D = oracle.all_pairs(sym, np.full(n, 500, np.int32), mode, 150, True, threads=8)["dist"]
+        intra, inter = [], []
+        for q in range(n):
+            for j in range(n):
+                if j == q:
+                    continue
+                f = np.float32(D[q, j])
+                if sp[q] >= 0 and sp[j] == sp[q] and not (full[j] < full[q]) and f != np.float32(-1):
+                    intra.append(f)
+                if gen[j] == gen[q] and epi[j] != epi[q] and epi[q] < epi[j] and f != np.float32(-1):
+                    inter.append(f)
+        got_intra = np.sort(aln.class_distances(t.PD_INTRA))
+        got_inter = np.sort(aln.class_distances(t.PD_INTER))
+        assert np.array_equal(got_intra.view(np.uint32), np.sort(np.array(intra, np.float32)).view(np.uint32))
+        assert np.array_equal(got_inter.view(np.uint32), np.sort(np.array(inter, np.float32)).view(np.uint32))
+        thr = 0.03
+        ii, jj, dd = aln.edges_below(thr)
+        exp = sorted((i, j, D[i, j]) for i in range(n) for j in range(i + 1, n) if 0 <= D[i, j] <= thr)
+        got = sorted(zip(ii.tolist(), jj.tolist(), dd.tolist()))
+        assert got == exp
+        v = aln.valid_conspecifics()
+        expv = [int(sp[i] >= 0 and any(j != i and sp[j] == sp[i] and D[i, j] != -1.0 for j in range(n))) for i in range(n)]
+        assert v.tolist() == expv
+    aln.close()
