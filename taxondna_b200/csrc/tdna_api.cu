@@ -150,8 +150,8 @@ int pack(tdna_aln *a) {
     return TDNA_OK;
 }
 
-template <int KM, bool WC> int launch_tiles_t(tdna_aln *a, int64_t b0, int64_t b1, bool symmetric, double *out, int64_t ld, tdna_counts *counts) {
-    using Cfg = TileCfg<KM>;
+template <int KM, int CN, bool WC> int launch_tiles_t(tdna_aln *a, int64_t b0, int64_t b1, bool symmetric, double *out, int64_t ld, tdna_counts *counts) {
+    using Cfg = TileCfg<KM, CN>;
     tdna_ctx *c = a->ctx;
     TileParams p;
     p.planes = a->d_planes;
@@ -163,6 +163,7 @@ template <int KM, bool WC> int launch_tiles_t(tdna_aln *a, int64_t b0, int64_t b
     p.symmetric = symmetric ? 1 : 0;
     p.nct = (int)((a->n + Cfg::TN - 1) / Cfg::TN);
     int nrt = (int)((b1 - b0 + TM - 1) / TM);
+    p.nrt = nrt;
     p.tile_prefix = nullptr;
     if (symmetric) {
         std::vector<int64_t> prefix(nrt + 1);
@@ -187,26 +188,42 @@ template <int KM, bool WC> int launch_tiles_t(tdna_aln *a, int64_t b0, int64_t b
     p.out = out;
     p.ld = ld;
     p.counts = counts;
-    auto kern = count_tile_kernel<KM, WC>;
+    auto kern = count_tile_kernel<KM, CN, WC>;
     static bool attr_set = false;
     if (!attr_set) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set = true;
     }
-    int64_t grid = p.num_tiles < c->sm_count ? p.num_tiles : c->sm_count;
+    int64_t slots = (int64_t)c->sm_count * Cfg::MIN_CTAS;
+    int64_t grid = p.num_tiles < slots ? p.num_tiles : slots;
     if (grid < 1) return TDNA_OK;
-    kern<<<(unsigned)grid, 256, Cfg::SMEM, c->stream>>>(p);
+    kern<<<(unsigned)grid, TILE_THREADS, Cfg::SMEM, c->stream>>>(p);
     c->launches++;
     CU(cudaGetLastError());
     return TDNA_OK;
 }
 
+// Tile shape: 128 x 128 (one CTA per SM) when there are plenty of tiles; 128 x 64 with two CTAs per
+// SM when the problem is small (tile quantisation) or the mode needs two accumulator words per pair.
+template <int KM, bool WC> int launch_tiles_km(tdna_aln *a, int64_t b0, int64_t b1, bool symmetric, double *out, int64_t ld, tdna_counts *counts) {
+    if constexpr (ModeTraits<KM>::NACC == 2) {
+        return launch_tiles_t<KM, 4, WC>(a, b0, b1, symmetric, out, ld, counts);
+    } else {
+        int64_t nrt = (b1 - b0 + TM - 1) / TM, nct = (a->n + 127) / 128;
+        int64_t tiles = symmetric ? nrt * (nct + 1) / 2 : nrt * nct;
+        const char *force = getenv("TDNA_TILE_CN");
+        int cn = force ? atoi(force) : (tiles < 8 * (int64_t)a->ctx->sm_count ? 4 : 8);
+        if (cn == 4) return launch_tiles_t<KM, 4, WC>(a, b0, b1, symmetric, out, ld, counts);
+        return launch_tiles_t<KM, 8, WC>(a, b0, b1, symmetric, out, ld, counts);
+    }
+}
+
 int launch_tiles(tdna_aln *a, int64_t b0, int64_t b1, bool symmetric, double *out, int64_t ld, tdna_counts *counts) {
     switch (a->kmode) {
-        case KM_P_AMBIG: return counts ? launch_tiles_t<KM_P_AMBIG, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_t<KM_P_AMBIG, false>(a, b0, b1, symmetric, out, ld, counts);
-        case KM_P_NOAMBIG: return counts ? launch_tiles_t<KM_P_NOAMBIG, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_t<KM_P_NOAMBIG, false>(a, b0, b1, symmetric, out, ld, counts);
-        case KM_K2P: return counts ? launch_tiles_t<KM_K2P, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_t<KM_K2P, false>(a, b0, b1, symmetric, out, ld, counts);
-        default: return counts ? launch_tiles_t<KM_TRANS, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_t<KM_TRANS, false>(a, b0, b1, symmetric, out, ld, counts);
+        case KM_P_AMBIG: return counts ? launch_tiles_km<KM_P_AMBIG, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_km<KM_P_AMBIG, false>(a, b0, b1, symmetric, out, ld, counts);
+        case KM_P_NOAMBIG: return counts ? launch_tiles_km<KM_P_NOAMBIG, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_km<KM_P_NOAMBIG, false>(a, b0, b1, symmetric, out, ld, counts);
+        case KM_K2P: return counts ? launch_tiles_km<KM_K2P, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_km<KM_K2P, false>(a, b0, b1, symmetric, out, ld, counts);
+        default: return counts ? launch_tiles_km<KM_TRANS, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_km<KM_TRANS, false>(a, b0, b1, symmetric, out, ld, counts);
     }
 }
 

@@ -105,7 +105,7 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 
-__device__ __noinline__ double strict_log(double x) {
+__device__ __forceinline__ double strict_log(double x) {
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
                  two54 = 1.80143985094819840000e+16, Lg1 = 6.666666666666735130e-01,
                  Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
@@ -158,6 +158,9 @@ __device__ __noinline__ double strict_log(double x) {
     return dsub(dmul(dk, ln2_hi), dsub(dsub(dmul(s, dsub(f, R)), dmul(dk, ln2_lo)), f));
 }
 
+// out-of-line copy for the tile epilogue (64 pairs per thread: inlining 128 logs would bloat the kernel)
+__device__ __noinline__ double strict_log_call(double x) { return strict_log(x); }
+
 // ---- distance from counts -----------------------------------------------------------------
 // getPairwiseNoBuffer (:1699-1717): gate on the mode-specific shared length, then the mode's
 // formula in Java's left-to-right order; -1.0 = inadequate overlap.
@@ -172,7 +175,7 @@ template <int KM> __device__ __forceinline__ double distance_from_counts(const C
         if (c.c2 == 0 && c.c3 == 0 && c.c1 > 0) return 0.0;  // w1 = w2 = 1: log(1) = 0 exactly -> -0 - 0 -> folded to +0 (:1569)
         double w1 = dsub(dsub(1.0, ddiv(dmul(2.0, ts), n)), ddiv(tv, n));  // :1559
         double w2 = dsub(1.0, ddiv(dmul(2.0, tv), n));                     // :1560
-        double d = dsub(dmul(-0.5, strict_log(w1)), dmul(0.25, strict_log(w2)));  // :1564
+        double d = dsub(dmul(-0.5, strict_log_call(w1)), dmul(0.25, strict_log_call(w2)));  // :1564
         if (d <= 0) return 0.0;                                             // :1569-1570
         return d;
     }

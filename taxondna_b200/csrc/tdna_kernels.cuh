@@ -61,6 +61,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// producer-side wait: the lane is far ahead of the consumers by design, so it sleeps between
+// probes instead of burning the issue slots of the SM sub-partition it shares with a consumer warp
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(400);
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
@@ -71,26 +87,32 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // ------------------------------------------------------------------------------------------
 // count + distance tile kernel (the hot kernel).
 //
-// CTA = 256 threads = 16 (ty) x 16 (tx); tile = 128 rows x TN columns of the pair matrix
-// (TN = 128, or 64 for modes with two accumulator words per pair); thread = 8 rows x CN columns
-// register-blocked, two 16-bit counts per 32-bit accumulator.  Operand words come from shared
-// memory staged by 1-D bulk async copies (one per (panel, plane) K-chunk) signalling an mbarrier;
-// NST stages are in flight across the flattened (tile, K-chunk) sequence of a persistent CTA.
-// Integer-issue bound: see DESIGN.md.
+// CTA = 8 consumer warps (16 ty x 16 tx threads) + 1 producer warp.  Tile = 128 rows x TN columns
+// of the pair matrix, TN = 16*CN; a consumer thread owns 8 rows x CN columns, register-blocked, two
+// 16-bit counts per 32-bit accumulator.  The producer warp's elected lane stages K-chunks of the
+// operand planes into shared memory with 1-D bulk async copies (TMA unit; one copy per (panel,
+// plane)) that complete on a "full" mbarrier; consumer warps release a stage by arriving on its
+// "empty" mbarrier.  There is no CTA-wide barrier in steady state, so warps drift apart and the
+// fp64 epilogue of one warp overlaps the integer main loop of the others.  Persistent grid over a
+// flattened (tile, K-chunk) sequence.  Integer-issue bound (POPC on the XU pipe): DESIGN.md.
 // ------------------------------------------------------------------------------------------
 constexpr int TM = 128;
-constexpr int KC = 8;    // words (256 sites) per K-chunk
-constexpr int NST = 3;   // pipeline stages
+constexpr int KC = 8;     // words (256 sites) per K-chunk
+constexpr int NST = 3;    // pipeline stages
+constexpr int CONSUMER_WARPS = 8;
+constexpr int TILE_THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int PREFIX_SMEM = 512;  // row-tile prefix entries cached in shared memory
 
-template <int KM> struct TileCfg {
+template <int KM, int CN> struct TileCfg {
     static constexpr int P = ModeTraits<KM>::P;
     static constexpr int NACC = ModeTraits<KM>::NACC;
-    static constexpr int CN = (NACC == 1) ? 8 : 4;
     static constexpr int TN = 16 * CN;
     static constexpr int XW = P * (TM / PR) * KC * PR;  // words per stage, x side
     static constexpr int YW = P * (TN / PR) * KC * PR;
     static constexpr int STAGE_WORDS = XW + YW;
-    static constexpr size_t SMEM = (size_t)NST * STAGE_WORDS * 4 + 64;
+    static constexpr size_t SMEM = (size_t)NST * STAGE_WORDS * 4 + 2 * NST * 8 + PREFIX_SMEM * 8 + 64;
+    // 2 CTAs per SM when the accumulators are small enough (more warps to hide the epilogue's latency)
+    static constexpr int MIN_CTAS = (CN * NACC <= 4) ? 2 : 1;
 };
 
 struct TileParams {
@@ -103,79 +125,93 @@ struct TileParams {
     int symmetric;      // band == whole matrix: only tiles touching j >= i are computed, both halves written
     int64_t num_tiles;
     const int64_t *tile_prefix;  // [row tiles + 1]; symmetric mode only
+    int nrt;                     // row tiles
     int nct;                     // column tiles
     double *out;                 // band matrix, row-major, leading dimension ld
     int64_t ld;
     tdna_counts *counts;         // optional, same shape, ld = n
 };
 
-template <int KM> __device__ __forceinline__ void tile_coords(const TileParams &p, int64_t t, int &ti, int &tj) {
-    constexpr int TN = TileCfg<KM>::TN;
+template <int TN> __device__ __forceinline__ void tile_coords(const TileParams &p, const int64_t *prefix, int64_t t, int &ti, int &tj) {
     if (!p.symmetric) {
         ti = (int)(t / p.nct);
         tj = (int)(t % p.nct);
     } else {
-        int nrt = (int)((p.row_end - p.row_begin + TM - 1) / TM);
-        int lo = 0, hi = nrt;  // largest ti with prefix[ti] <= t
+        int lo = 0, hi = p.nrt;  // largest ti with prefix[ti] <= t
         while (hi - lo > 1) {
             int mid = (lo + hi) >> 1;
-            if (p.tile_prefix[mid] <= t) lo = mid; else hi = mid;
+            if (prefix[mid] <= t) lo = mid; else hi = mid;
         }
         ti = lo;
-        tj = (int)(t - p.tile_prefix[lo]) + ti * (TM / TN);
+        tj = (int)(t - prefix[lo]) + ti * (TM / TN);
     }
 }
 
-template <int KM, bool WRITE_COUNTS>
-__global__ void __launch_bounds__(256, 1) count_tile_kernel(TileParams p) {
-    using Cfg = TileCfg<KM>;
-    constexpr int P = Cfg::P, NACC = Cfg::NACC, CN = Cfg::CN, TN = Cfg::TN;
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int KM, int CN, bool WRITE_COUNTS>
+__global__ void __launch_bounds__(TILE_THREADS, TileCfg<KM, CN>::MIN_CTAS) count_tile_kernel(TileParams p) {
+    using Cfg = TileCfg<KM, CN>;
+    constexpr int P = Cfg::P, NACC = Cfg::NACC, TN = Cfg::TN;
     extern __shared__ __align__(128) uint32_t smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + NST * Cfg::STAGE_WORDS);
+    uint64_t *empty = full + NST;
+    int64_t *s_prefix = reinterpret_cast<int64_t *>(empty + NST);
 
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int nchunks = (p.W + KC - 1) / KC;
     // tiles of this CTA: blockIdx.x, +gridDim.x, ...
     const int64_t my_tiles = (p.num_tiles > blockIdx.x) ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total = my_tiles * nchunks;
 
+    const bool prefix_in_smem = p.symmetric && p.nrt + 1 <= PREFIX_SMEM;
+    if (prefix_in_smem)
+        for (int i = tid; i <= p.nrt; i += TILE_THREADS) s_prefix[i] = p.tile_prefix[i];
+    const int64_t *prefix = prefix_in_smem ? s_prefix : p.tile_prefix;
     if (tid == 0) {
-        for (int s = 0; s < NST; s++) mbar_init(&full[s], 1);
+        for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CONSUMER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    auto issue = [&](int64_t it) {  // one thread: stage (tile, chunk) `it` into slot it % NST
-        int64_t t = blockIdx.x + (it / nchunks) * gridDim.x;
-        int c = (int)(it % nchunks);
-        int ti, tj;
-        tile_coords<KM>(p, t, ti, tj);
-        int k0 = c * KC, kc = min(KC, p.W - k0);
-        int slot = (int)(it % NST);
-        uint32_t *xs = smem + slot * Cfg::STAGE_WORDS, *ys = xs + Cfg::XW;
-        uint32_t bytes = (uint32_t)kc * PR * 4;
-        mbar_expect_tx(&full[slot], bytes * P * (TM / PR + TN / PR));
-        int64_t xpanel = (p.row_begin + (int64_t)ti * TM) / PR, ypanel = ((int64_t)tj * TN) / PR;
+    if (warp == CONSUMER_WARPS) {
+        // ===== producer warp: one elected lane feeds the ring =====
+        if ((tid & 31) == 0) {
+            for (int64_t it = 0; it < total; it++) {
+                const int slot = (int)(it % NST);
+                if (it >= NST) mbar_wait_backoff(&empty[slot], (uint32_t)(((it / NST) - 1) & 1));
+                const int64_t t = blockIdx.x + (it / nchunks) * gridDim.x;
+                const int c = (int)(it % nchunks);
+                int ti, tj;
+                tile_coords<TN>(p, prefix, t, ti, tj);
+                const int k0 = c * KC, kc = min(KC, p.W - k0);
+                uint32_t *xs = smem + slot * Cfg::STAGE_WORDS, *ys = xs + Cfg::XW;
+                const uint32_t bytes = (uint32_t)kc * PR * 4;
+                mbar_expect_tx(&full[slot], bytes * P * (TM / PR + TN / PR));
+                const int64_t xpanel = (p.row_begin + (int64_t)ti * TM) / PR, ypanel = ((int64_t)tj * TN) / PR;
 #pragma unroll
-        for (int h = 0; h < TM / PR; h++)
-            for (int pl = 0; pl < P; pl++)
-                bulk_g2s(xs + ((pl * (TM / PR) + h) * KC) * PR, p.planes + (((xpanel + h) * P + pl) * p.W + k0) * PR, bytes, &full[slot]);
+                for (int h = 0; h < TM / PR; h++)
+                    for (int pl = 0; pl < P; pl++)
+                        bulk_g2s(xs + ((pl * (TM / PR) + h) * KC) * PR, p.planes + (((xpanel + h) * P + pl) * p.W + k0) * PR, bytes, &full[slot]);
 #pragma unroll
-        for (int h = 0; h < TN / PR; h++)
-            for (int pl = 0; pl < P; pl++)
-                bulk_g2s(ys + ((pl * (TN / PR) + h) * KC) * PR, p.planes + (((ypanel + h) * P + pl) * p.W + k0) * PR, bytes, &full[slot]);
-    };
+                for (int h = 0; h < TN / PR; h++)
+                    for (int pl = 0; pl < P; pl++)
+                        bulk_g2s(ys + ((pl * (TN / PR) + h) * KC) * PR, p.planes + (((ypanel + h) * P + pl) * p.W + k0) * PR, bytes, &full[slot]);
+            }
+        }
+        return;
+    }
 
-    if (tid == 0)
-        for (int64_t it = 0; it < NST - 1 && it < total; it++) issue(it);
-
+    // ===== consumer warps =====
+    const int tx = tid & 15, ty = tid >> 4;
     uint32_t acc[NACC][8][CN];
     const int xh = ty >> 3, xr = (ty & 7) * 8;  // panel half and first row within it
 
     for (int64_t it = 0; it < total; it++) {
         const int c = (int)(it % nchunks);
         const int slot = (int)(it % NST);
-        if (tid == 0 && it + NST - 1 < total) issue(it + NST - 1);  // slot freed by the barrier ending iteration it-1
         if (c == 0) {
 #pragma unroll
             for (int a = 0; a < NACC; a++)
@@ -216,50 +252,53 @@ __global__ void __launch_bounds__(256, 1) count_tile_kernel(TileParams p) {
                     }
                 }
         }
-        if (c == nchunks - 1) {  // epilogue: counts -> fp64 distance -> band matrix
-            int64_t t = blockIdx.x + (it / nchunks) * gridDim.x;
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[slot]);  // this warp is done reading the stage
+        if (c == nchunks - 1) {  // epilogue: counts -> fp64 distance -> band matrix (registers only)
+            const int64_t t = blockIdx.x + (it / nchunks) * gridDim.x;
             int ti, tj;
-            tile_coords<KM>(p, t, ti, tj);
+            tile_coords<TN>(p, prefix, t, ti, tj);
             const int64_t i0 = p.row_begin + (int64_t)ti * TM + ty * 8, j0 = (int64_t)tj * TN;
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
+            for (int r = 0; r < 8; r++) {  // fully unrolled: acc[][][] must stay in registers
                 const int64_t i = i0 + r;
-                if (i >= p.row_end) continue;
+                const bool row_ok = i < p.row_end;
+                double dv[CN];
+#pragma unroll
+                for (int e = 0; e < CN; e++) {
+                    uint32_t a1 = 0;
+                    if constexpr (NACC == 2) a1 = acc[1][r][e];
+                    Counts cn = unpack_counts<KM>(acc[0][r][e], a1);
+                    dv[e] = distance_from_counts<KM>(cn, p.min_overlap);
+                    if constexpr (WRITE_COUNTS) {
+                        const int64_t j = j0 + (e >> 2) * PR + 4 * tx + (e & 3);
+                        if (row_ok && j < p.n) {
+                            tdna_counts o = {cn.shared, cn.c1, cn.c2, cn.c3};
+                            p.counts[(i - p.row_begin) * p.n + j] = o;
+                        }
+                    }
+                }
+                if (!row_ok) continue;
 #pragma unroll
                 for (int h = 0; h < CN / 4; h++) {
                     const int64_t jb = j0 + h * PR + 4 * tx;
-                    double dv[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        uint32_t a1 = 0;
-                        if constexpr (NACC == 2) a1 = acc[1][r][4 * h + e];
-                        Counts cn = unpack_counts<KM>(acc[0][r][4 * h + e], a1);
-                        dv[e] = distance_from_counts<KM>(cn, p.min_overlap);
-                        if constexpr (WRITE_COUNTS) {
-                            if (jb + e < p.n) {
-                                tdna_counts o = {cn.shared, cn.c1, cn.c2, cn.c3};
-                                p.counts[(i - p.row_begin) * p.n + jb + e] = o;
-                            }
-                        }
-                    }
                     double *dst = p.out + (i - p.row_begin) * p.ld + jb;
                     if (jb + 3 < p.n) {  // ld and jb are multiples of 4 doubles: 32-byte aligned
-                        reinterpret_cast<double2 *>(dst)[0] = make_double2(dv[0], dv[1]);
-                        reinterpret_cast<double2 *>(dst)[1] = make_double2(dv[2], dv[3]);
+                        reinterpret_cast<double2 *>(dst)[0] = make_double2(dv[4 * h + 0], dv[4 * h + 1]);
+                        reinterpret_cast<double2 *>(dst)[1] = make_double2(dv[4 * h + 2], dv[4 * h + 3]);
                     } else {
 #pragma unroll
                         for (int e = 0; e < 4; e++)
-                            if (jb + e < p.n) dst[e] = dv[e];
+                            if (jb + e < p.n) dst[e] = dv[4 * h + e];
                     }
                     if (p.symmetric) {  // mirror (band == whole matrix, row_begin == 0)
 #pragma unroll
                         for (int e = 0; e < 4; e++)
-                            if (jb + e < p.n && jb + e > i) p.out[(jb + e) * p.ld + i] = dv[e];
+                            if (jb + e < p.n && jb + e > i) p.out[(jb + e) * p.ld + i] = dv[4 * h + e];
                     }
                 }
             }
         }
-        __syncthreads();
     }
 }
 
