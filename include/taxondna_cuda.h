@@ -80,7 +80,7 @@ typedef struct {
     int32_t unnamed_at_con, unnamed_at_allo, unnamed_at_other; /* # unnamed valid j with d == d_ref */
     int32_t n_valid;                  /* # valid j != q */
     int32_t flags;                    /* TDNA_ROW_* */
-    int32_t reserved;
+    int32_t reserved, reserved2;      /* zero; the record is exactly 120 bytes with no padding */
 } tdna_row_result;
 
 enum {
@@ -149,6 +149,37 @@ int32_t tdna_best_match(tdna_aln *aln, tdna_row_result *out);
 /* Same, results left on the device; *out_dev receives the device pointer to n records. */
 int32_t tdna_best_match_compute(tdna_aln *aln, const tdna_row_result **out_dev);
 
+/* ---- streaming Best Match, in parts (multi-GPU) ------------------------------------------------ */
+/* tdna_best_match on the whole row range does NOT materialise the N x N matrix: one pass over the
+ * triangle of tiles keeps, per query row, only the CANDIDATE columns whose distance is not above a
+ * per-row bound that provably covers every distance tdna_row_result refers to (+ the near-tie
+ * window), and the exact two-sweep summary then runs on those short lists (DESIGN.md "streaming
+ * Best Match").  The two halves are exposed so that several GPUs can share one pass:
+ *   part k of m takes every m-th tile of the triangle; its candidates / per-row invalid-pair counts /
+ *   per-row flags stay on the device (pointers in *out, valid until the next call on the alignment);
+ *   the caller concatenates the candidate records of all parts (NCCL all_gather), sums the invalid
+ *   counts and ORs the flags (NCCL all_reduce), and hands the union to tdna_best_match_merge. */
+typedef struct {
+    const int32_t *cand_row;      /* device, n_cand: query row q */
+    const int32_t *cand_col;      /* device, n_cand: column j */
+    const double *cand_d;         /* device, n_cand: d(q, j), valid and finite */
+    int64_t n_cand;
+    const int32_t *invalid_count; /* device, n: # j != q with getSharedLength < minOverlap seen by this part */
+    const int32_t *flags;         /* device, n: TDNA_ROW_* seen by this part */
+} tdna_stream_part;
+int32_t tdna_best_match_part(tdna_aln *aln, int32_t part, int32_t nparts, tdna_stream_part *out);
+/* Inputs are DEVICE pointers (the part's own, or gathered); out: n records, host or device. */
+int32_t tdna_best_match_merge(tdna_aln *aln, const int32_t *cand_row, const int32_t *cand_col, const double *cand_d,
+                              int64_t n_cand, const int32_t *invalid_count, const int32_t *flags, tdna_row_result *out);
+
+/* ---- options ------------------------------------------------------------------------------------ */
+enum { TDNA_OPT_BEST_MATCH_PATH = 1, /* TDNA_PATH_*: how tdna_best_match computes a whole-range request */
+       TDNA_OPT_TILE_COLUMNS = 2     /* 0 = automatic, 64 or 128: column width of a count tile */ };
+enum { TDNA_PATH_AUTO = 0,   /* streaming; falls back to the dense path if the candidate buffer overflows */
+       TDNA_PATH_DENSE = 1,  /* materialise row bands of the fp64 matrix, sweep them */
+       TDNA_PATH_STREAM = 2  /* streaming only (TDNA_E_TOO_LARGE on overflow) */ };
+int32_t tdna_set_option(tdna_ctx *ctx, int32_t key, int64_t value);
+
 /* ---- Pairwise Summary / threshold percentile --------------------------------------------- */
 /* All distances of one PairwiseDistribution class as (float)d, -1 dropped, UNSORTED multiset
  * (PairwiseDistribution.java:77-103, 161-203):
@@ -178,6 +209,9 @@ int32_t tdna_cancel(tdna_ctx *ctx);
  * `reps` times and returns the mean device time per launch in milliseconds (CUDA events on the
  * context's stream). */
 int32_t tdna_time_matrix_kernel(tdna_aln *aln, int32_t reps, float *ms_per_launch);
+/* Device time (CUDA events on the context's stream) of the most recent count-tile pass -- the tile
+ * kernel launch(es) of the last matrix band or streaming pass; waits for it to finish. */
+int32_t tdna_last_tile_pass_ms(tdna_ctx *ctx, float *ms);
 /* Integer-pipe micro-benchmarks: results/s of dependent-free POPC and LOP3 streams over all SMs. */
 int32_t tdna_measure_int_peaks(tdna_ctx *ctx, double *popc_per_s, double *lop3_per_s);
 

@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(_HERE, "libtaxondna_cuda.so")
 PDM_UNCORRECTED, PDM_K2P, PDM_TRANS_ONLY = 0, 1, 2
 PD_INTRA, PD_INTER = 0, 1
 ROW_SELF_VALID, ROW_NONFINITE = 1, 2
+OPT_BEST_MATCH_PATH, OPT_TILE_COLUMNS = 1, 2
+PATH_AUTO, PATH_DENSE, PATH_STREAM = 0, 1, 2
 
 
 class TdnaError(RuntimeError):
@@ -24,6 +26,12 @@ class Counts(ctypes.Structure):
     _fields_ = [("shared", ctypes.c_int32), ("c1", ctypes.c_int32), ("c2", ctypes.c_int32), ("c3", ctypes.c_int32)]
 
 
+class StreamPart(ctypes.Structure):
+    """tdna_stream_part: device pointers to one part's streaming Best-Match output."""
+    _fields_ = [("cand_row", ctypes.c_void_p), ("cand_col", ctypes.c_void_p), ("cand_d", ctypes.c_void_p),
+                ("n_cand", ctypes.c_int64), ("invalid_count", ctypes.c_void_p), ("flags", ctypes.c_void_p)]
+
+
 COUNTS_DTYPE = np.dtype([("shared", "<i4"), ("c1", "<i4"), ("c2", "<i4"), ("c3", "<i4")])
 
 ROW_RESULT_DTYPE = np.dtype([
@@ -34,7 +42,7 @@ ROW_RESULT_DTYPE = np.dtype([
     ("block_count", "<i4"),
     ("near_best", "<i4"), ("near_con", "<i4"), ("near_allo", "<i4"), ("near_other", "<i4"),
     ("unnamed_at_con", "<i4"), ("unnamed_at_allo", "<i4"), ("unnamed_at_other", "<i4"),
-    ("n_valid", "<i4"), ("flags", "<i4"), ("reserved", "<i4"),
+    ("n_valid", "<i4"), ("flags", "<i4"), ("reserved", "<i4"), ("reserved2", "<i4"),
 ], align=True)
 assert ROW_RESULT_DTYPE.itemsize == 120, ROW_RESULT_DTYPE.itemsize
 
@@ -45,6 +53,7 @@ EXPORTS = [
     "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_row_distances", "tdna_matrix", "tdna_matrix_compute",
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
+    "tdna_best_match_part", "tdna_best_match_merge", "tdna_set_option", "tdna_last_tile_pass_ms",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -89,6 +98,10 @@ def load():
     L.tdna_cancel.argtypes = [vp]
     L.tdna_time_matrix_kernel.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
     L.tdna_measure_int_peaks.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
+    L.tdna_best_match_part.argtypes = [vp, i32, i32, ctypes.POINTER(StreamPart)]
+    L.tdna_best_match_merge.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
+    L.tdna_set_option.argtypes = [vp, i32, i64]
+    L.tdna_last_tile_pass_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     _lib = L
     return L
 
@@ -128,6 +141,14 @@ class Context:
 
     def cancel(self):
         check(self.L.tdna_cancel(self.h))
+
+    def set_option(self, key, value):
+        check(self.L.tdna_set_option(self.h, int(key), int(value)))
+
+    def last_tile_pass_ms(self):
+        ms = ctypes.c_float()
+        check(self.L.tdna_last_tile_pass_ms(self.h, ctypes.byref(ms)))
+        return ms.value
 
     def measure_int_peaks(self):
         a, b = ctypes.c_double(), ctypes.c_double()
@@ -204,6 +225,18 @@ class Alignment:
         p = ctypes.c_void_p()
         check(self.L.tdna_best_match_compute(self.h, ctypes.byref(p)))
         return p.value
+
+    def best_match_part(self, part, nparts):
+        """Streaming pass over every nparts-th tile of the triangle; returns a StreamPart of DEVICE pointers."""
+        sp = StreamPart()
+        check(self.L.tdna_best_match_part(self.h, int(part), int(nparts), ctypes.byref(sp)))
+        return sp
+
+    def best_match_merge(self, cand_row, cand_col, cand_d, n_cand, invalid_count, flags, out=None):
+        """All inputs are device addresses (ints); returns the n row records (host)."""
+        r = out if out is not None else np.zeros(self.n, dtype=ROW_RESULT_DTYPE)
+        check(self.L.tdna_best_match_merge(self.h, cand_row, cand_col, cand_d, int(n_cand), invalid_count, flags, r.ctypes.data))
+        return r
 
     def class_distances(self, klass):
         n = ctypes.c_int64()

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "tdna_kernels.cuh"
@@ -52,6 +53,10 @@ struct tdna_ctx {
     double *d_mat = nullptr;
     int64_t mat_cap = 0;              // doubles
     const void *mat_owner = nullptr;  // alignment whose whole-range matrix currently sits in d_mat
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the most recent tile pass (tdna_last_tile_pass_ms)
+    bool ev_valid = false;
+    int opt_best_match_path = TDNA_PATH_AUTO;
+    int opt_tile_cn = 0;  // 0 = automatic
 };
 
 struct tdna_aln {
@@ -76,6 +81,20 @@ struct tdna_aln {
     int64_t prefix_cap = 0;
     void *d_scratch = nullptr;  // grow-only staging for host-destined compaction outputs
     size_t scratch_cap = 0;
+    // streaming Best Match (tdna_kernels.cuh "stream epilogue")
+    uint8_t *d_needc = nullptr;
+    StreamParams sp = {};
+    bool stream_alloc = false;
+    void *d_stream_u64 = nullptr;  // ncand + overflow
+    int64_t *d_sprefix[2] = {nullptr, nullptr};
+    int64_t sprefix_tiles[2] = {0, 0};
+    int sprefix_cn = 0;
+    long long *d_ptr = nullptr;  // CSR row pointers [n + 1]
+    int *d_cursor = nullptr;
+    int32_t *d_lj = nullptr;
+    double *d_ld = nullptr;
+    long long list_cap = 0;
+    long long last_ncand = 0;
 };
 
 namespace {
@@ -150,10 +169,27 @@ int pack(tdna_aln *a) {
     return TDNA_OK;
 }
 
+template <int KM, int CN, int EPI> int launch_kernel(tdna_ctx *c, const TileParams &p) {
+    using Cfg = TileCfg<KM, CN>;
+    auto kern = count_tile_kernel<KM, CN, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    int64_t slots = (int64_t)c->sm_count * Cfg::MIN_CTAS;
+    int64_t grid = p.num_tiles < slots ? p.num_tiles : slots;
+    if (grid < 1) return TDNA_OK;
+    kern<<<(unsigned)grid, TILE_THREADS, Cfg::SMEM, c->stream>>>(p);
+    c->launches++;
+    CU(cudaGetLastError());
+    return TDNA_OK;
+}
+
 template <int KM, int CN, bool WC> int launch_tiles_t(tdna_aln *a, int64_t b0, int64_t b1, bool symmetric, double *out, int64_t ld, tdna_counts *counts) {
     using Cfg = TileCfg<KM, CN>;
     tdna_ctx *c = a->ctx;
-    TileParams p;
+    TileParams p = {};
     p.planes = a->d_planes;
     p.W = a->W;
     p.n = a->n;
@@ -161,6 +197,10 @@ template <int KM, int CN, bool WC> int launch_tiles_t(tdna_aln *a, int64_t b0, i
     p.row_begin = b0;
     p.row_end = b1;
     p.symmetric = symmetric ? 1 : 0;
+    p.sched = symmetric ? SCHED_SYMMETRIC : SCHED_RECT;
+    p.first_col_extra = 0;
+    p.t_offset = 0;
+    p.t_stride = 1;
     p.nct = (int)((a->n + Cfg::TN - 1) / Cfg::TN);
     int nrt = (int)((b1 - b0 + TM - 1) / TM);
     p.nrt = nrt;
@@ -188,18 +228,10 @@ template <int KM, int CN, bool WC> int launch_tiles_t(tdna_aln *a, int64_t b0, i
     p.out = out;
     p.ld = ld;
     p.counts = counts;
-    auto kern = count_tile_kernel<KM, CN, WC>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
-    int64_t slots = (int64_t)c->sm_count * Cfg::MIN_CTAS;
-    int64_t grid = p.num_tiles < slots ? p.num_tiles : slots;
-    if (grid < 1) return TDNA_OK;
-    kern<<<(unsigned)grid, TILE_THREADS, Cfg::SMEM, c->stream>>>(p);
-    c->launches++;
-    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_k0, c->stream));
+    TRY((launch_kernel<KM, CN, WC ? EPI_MATRIX_COUNTS : EPI_MATRIX>(c, p)));
+    CU(cudaEventRecord(c->ev_k1, c->stream));
+    c->ev_valid = true;
     return TDNA_OK;
 }
 
@@ -211,8 +243,7 @@ template <int KM, bool WC> int launch_tiles_km(tdna_aln *a, int64_t b0, int64_t 
     } else {
         int64_t nrt = (b1 - b0 + TM - 1) / TM, nct = (a->n + 127) / 128;
         int64_t tiles = symmetric ? nrt * (nct + 1) / 2 : nrt * nct;
-        const char *force = getenv("TDNA_TILE_CN");
-        int cn = force ? atoi(force) : (tiles < 8 * (int64_t)a->ctx->sm_count ? 4 : 8);
+        int cn = a->ctx->opt_tile_cn ? a->ctx->opt_tile_cn : (tiles < 8 * (int64_t)a->ctx->sm_count ? 4 : 8);
         if (cn == 4) return launch_tiles_t<KM, 4, WC>(a, b0, b1, symmetric, out, ld, counts);
         return launch_tiles_t<KM, 8, WC>(a, b0, b1, symmetric, out, ld, counts);
     }
@@ -224,6 +255,89 @@ int launch_tiles(tdna_aln *a, int64_t b0, int64_t b1, bool symmetric, double *ou
         case KM_P_NOAMBIG: return counts ? launch_tiles_km<KM_P_NOAMBIG, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_km<KM_P_NOAMBIG, false>(a, b0, b1, symmetric, out, ld, counts);
         case KM_K2P: return counts ? launch_tiles_km<KM_K2P, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_km<KM_K2P, false>(a, b0, b1, symmetric, out, ld, counts);
         default: return counts ? launch_tiles_km<KM_TRANS, true>(a, b0, b1, symmetric, out, ld, counts) : launch_tiles_km<KM_TRANS, false>(a, b0, b1, symmetric, out, ld, counts);
+    }
+}
+
+// ---- streaming Best Match: the tile pass --------------------------------------------------------
+// Triangle tiles in two launches: the diagonal blocks first (list neighbours -- conspecifics and
+// congeners when the list is sorted by name -- so the per-row thresholds are tight before the bulk),
+// then everything right of them, row-tile major.  Part k of m takes global tiles k, k+m, k+2m, ...
+template <int CN> int stream_prefixes(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
+    constexpr int TN = 16 * CN, R = TM / TN;
+    if (a->sprefix_cn == CN && a->d_sprefix[0]) return TDNA_OK;
+    int nrt = (int)((a->n + TM - 1) / TM);
+    int64_t nct = (a->n + TN - 1) / TN;
+    std::vector<int64_t> pre[2];
+    for (int ph = 0; ph < 2; ph++) {
+        pre[ph].resize(nrt + 1);
+        pre[ph][0] = 0;
+        for (int t = 0; t < nrt; t++) {
+            int64_t first = (int64_t)t * R;
+            int64_t diag = nct - first < R ? nct - first : R;
+            if (diag < 0) diag = 0;
+            int64_t rest = nct - first - R;
+            if (rest < 0) rest = 0;
+            pre[ph][t + 1] = pre[ph][t] + (ph == 0 ? diag : rest);
+        }
+        if (a->d_sprefix[ph]) CU(DFREE(a->d_sprefix[ph]));
+        a->d_sprefix[ph] = nullptr;
+        CU(DMALLOC(&a->d_sprefix[ph], (size_t)(nrt + 1) * 8));
+        CU(cudaMemcpyAsync(a->d_sprefix[ph], pre[ph].data(), (size_t)(nrt + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        a->sprefix_tiles[ph] = pre[ph][nrt];
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    a->sprefix_cn = CN;
+    return TDNA_OK;
+}
+
+template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts) {
+    using Cfg = TileCfg<KM, CN>;
+    tdna_ctx *c = a->ctx;
+    TRY(stream_prefixes<CN>(a));
+    CU(cudaMemcpyToSymbolAsync(c_sp, &a->sp, sizeof(StreamParams), 0, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev_k0, c->stream));
+    for (int ph = 0; ph < 2; ph++) {
+        TileParams p = {};
+        p.planes = a->d_planes;
+        p.W = a->W;
+        p.n = a->n;
+        p.min_overlap = a->min_overlap;
+        p.row_begin = 0;
+        p.row_end = a->n;
+        p.symmetric = 0;
+        p.sched = SCHED_STREAM;
+        p.first_col_extra = ph ? TM / Cfg::TN : 0;
+        p.t_offset = part;
+        p.t_stride = nparts;
+        p.nct = (int)((a->n + Cfg::TN - 1) / Cfg::TN);
+        p.nrt = (int)((a->n + TM - 1) / TM);
+        p.tile_prefix = a->d_sprefix[ph];
+        int64_t total = a->sprefix_tiles[ph];
+        p.num_tiles = total > part ? (total - part + nparts - 1) / nparts : 0;
+        TRY((launch_kernel<KM, CN, EPI_STREAM>(c, p)));
+    }
+    CU(cudaEventRecord(c->ev_k1, c->stream));
+    c->ev_valid = true;
+    return TDNA_OK;
+}
+
+template <int KM> int launch_stream_km(tdna_aln *a, int part, int nparts) {
+    if constexpr (ModeTraits<KM>::NACC == 2) {
+        return launch_stream_t<KM, 4>(a, part, nparts);
+    } else {
+        int cn = a->ctx->opt_tile_cn ? a->ctx->opt_tile_cn : 4;
+        if (cn == 4) return launch_stream_t<KM, 4>(a, part, nparts);
+        return launch_stream_t<KM, 8>(a, part, nparts);
+    }
+}
+
+int launch_stream(tdna_aln *a, int part, int nparts) {
+    switch (a->kmode) {
+        case KM_P_AMBIG: return launch_stream_km<KM_P_AMBIG>(a, part, nparts);
+        case KM_P_NOAMBIG: return launch_stream_km<KM_P_NOAMBIG>(a, part, nparts);
+        case KM_K2P: return launch_stream_km<KM_K2P>(a, part, nparts);
+        default: return launch_stream_km<KM_TRANS>(a, part, nparts);
     }
 }
 
@@ -336,6 +450,8 @@ int32_t tdna_init(int32_t device, tdna_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&c->d_counter, 64));
+    CU(cudaEventCreate(&c->ev_k0));
+    CU(cudaEventCreate(&c->ev_k1));
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     unsigned long long keep = ~0ull;
@@ -352,6 +468,8 @@ int32_t tdna_shutdown(tdna_ctx *c) {
     cudaSetDevice(c->device);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_mat) cudaFree(c->d_mat);
+    if (c->ev_k0) cudaEventDestroy(c->ev_k0);
+    if (c->ev_k1) cudaEventDestroy(c->ev_k1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return TDNA_OK;
@@ -420,7 +538,9 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
     cudaSetDevice(c->device);
     if (c->mat_owner == a) c->mat_owner = nullptr;
-    void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch};
+    void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
+                    a->d_needc, a->sp.thr, a->sp.mC, a->sp.mPar, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
+                    a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_cursor, a->d_lj, a->d_ld};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
     delete a;
@@ -439,6 +559,18 @@ int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const 
         if (!*dst[i]) CU(DMALLOC(dst[i], bytes));
         CU(cudaMemcpyAsync(*dst[i], src[i], bytes, cudaMemcpyDefault, c->stream));
     }
+    CU(cudaStreamSynchronize(c->stream));
+    // needc[q]: q is named and its species has another member (the streaming thresholds wait for a
+    // conspecific only where one can exist)
+    std::vector<int32_t> hs((size_t)a->n);
+    CU(cudaMemcpy(hs.data(), a->d_species, bytes, cudaMemcpyDeviceToHost));
+    std::unordered_map<int32_t, int> members;
+    for (int32_t v : hs)
+        if (v >= 0) members[v]++;
+    std::vector<uint8_t> need((size_t)a->n);
+    for (int64_t i = 0; i < a->n; i++) need[i] = (hs[i] >= 0 && members[hs[i]] > 1) ? 1 : 0;
+    if (!a->d_needc) CU(DMALLOC(&a->d_needc, (size_t)a->n));
+    CU(cudaMemcpyAsync(a->d_needc, need.data(), (size_t)a->n, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     a->has_labels = true;
     return TDNA_OK;
@@ -572,12 +704,24 @@ int32_t tdna_matrix_compute(tdna_aln *a, const double **d_dev) {
     return TDNA_OK;
 }
 
-int32_t tdna_best_match_compute(tdna_aln *a, const tdna_row_result **out_dev) {
-    if (!a) return fail(TDNA_E_ARG, "null alignment");
+static int fill_shared(tdna_aln *a, int64_t r0, int64_t r1) {
     tdna_ctx *c = a->ctx;
-    CU(cudaSetDevice(c->device));
-    TRY(need_labels(a));
-    if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+    int64_t rows = r1 - r0;
+    if (rows <= 0) return TDNA_OK;
+    unsigned grid = (unsigned)((rows * 2 + 255) / 256);
+    switch (a->kmode) {
+        case KM_P_AMBIG: fill_shared_kernel<KM_P_AMBIG><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, r0, r1, a->d_res); break;
+        case KM_P_NOAMBIG: fill_shared_kernel<KM_P_NOAMBIG><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, r0, r1, a->d_res); break;
+        case KM_K2P: fill_shared_kernel<KM_K2P><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, r0, r1, a->d_res); break;
+        default: fill_shared_kernel<KM_TRANS><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, r0, r1, a->d_res); break;
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    return TDNA_OK;
+}
+
+static int best_match_dense(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
     TRY(for_each_band(a, [&](int64_t b0, int64_t b1) -> int {
         int64_t grid = (b1 - b0) < c->sm_count ? (b1 - b0) : c->sm_count;
         row_summary_kernel<<<(unsigned)grid, RS_THREADS, 0, c->stream>>>(a->d_mat, a->ld, a->n, b0, b1 - b0, a->d_species, a->d_res);
@@ -585,18 +729,144 @@ int32_t tdna_best_match_compute(tdna_aln *a, const tdna_row_result **out_dev) {
         CU(cudaGetLastError());
         return TDNA_OK;
     }));
-    int64_t rows = a->row_end - a->row_begin;
-    if (rows > 0) {
-        unsigned grid = (unsigned)((rows * 2 + 255) / 256);
-        switch (a->kmode) {
-            case KM_P_AMBIG: fill_shared_kernel<KM_P_AMBIG><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, a->row_begin, a->row_end, a->d_res); break;
-            case KM_P_NOAMBIG: fill_shared_kernel<KM_P_NOAMBIG><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, a->row_begin, a->row_end, a->d_res); break;
-            case KM_K2P: fill_shared_kernel<KM_K2P><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, a->row_begin, a->row_end, a->d_res); break;
-            default: fill_shared_kernel<KM_TRANS><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, a->row_begin, a->row_end, a->d_res); break;
-        }
+    return fill_shared(a, a->row_begin, a->row_end);
+}
+
+static int ensure_stream_state(tdna_aln *a) {
+    if (a->stream_alloc) return TDNA_OK;
+    tdna_ctx *c = a->ctx;
+    size_t n = (size_t)a->n;
+    long long cap = (long long)n * 64;
+    if (cap < (1ll << 22)) cap = 1ll << 22;
+    if (cap * 16 > c->budget / 2) cap = c->budget / 32;
+    StreamParams &sp = a->sp;
+    CU(DMALLOC(&sp.thr, n * 4));
+    CU(DMALLOC(&sp.mC, n * 8));
+    CU(DMALLOC(&sp.mPar, n * 16));
+    CU(DMALLOC(&sp.inval, n * 4));
+    CU(DMALLOC(&sp.flags, n * 4));
+    CU(DMALLOC(&sp.cnt, n * 4));
+    CU(DMALLOC(&sp.cq, (size_t)cap * 4));
+    CU(DMALLOC(&sp.cj, (size_t)cap * 4));
+    CU(DMALLOC(&sp.cd, (size_t)cap * 8));
+    CU(DMALLOC(&a->d_stream_u64, 16));
+    sp.ncand = reinterpret_cast<unsigned long long *>(a->d_stream_u64);
+    sp.overflow = reinterpret_cast<int *>(reinterpret_cast<char *>(a->d_stream_u64) + 8);
+    sp.cap = cap;
+    sp.species = a->d_species;
+    CU(DMALLOC(&a->d_ptr, (n + 1) * 8));
+    CU(DMALLOC(&a->d_cursor, n * 4));
+    a->stream_alloc = true;
+    return TDNA_OK;
+}
+
+// rc TDNA_E_TOO_LARGE: the candidate buffer overflowed (thresholds never tightened: e.g. one species only)
+static int stream_part(tdna_aln *a, int part, int nparts, long long *ncand_out) {
+    tdna_ctx *c = a->ctx;
+    TRY(ensure_packed(a));
+    TRY(ensure_stream_state(a));
+    a->sp.species = a->d_species;
+    stream_init_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n, a->d_needc);
+    c->launches++;
+    CU(cudaGetLastError());
+    TRY(launch_stream(a, part, nparts));
+    struct { unsigned long long ncand; int overflow; int pad; } h;
+    CU(cudaMemcpyAsync(&h, a->d_stream_u64, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (h.overflow) return fail(TDNA_E_TOO_LARGE, "streaming Best Match: candidate buffer overflow");
+    a->last_ncand = (long long)h.ncand;
+    if (ncand_out) *ncand_out = (long long)h.ncand;
+    return TDNA_OK;
+}
+
+// candidate records (device) -> per-row lists -> exact summaries into a->d_res
+static int stream_merge(tdna_aln *a, const int32_t *cq, const int32_t *cj, const double *cd, long long ncand, const int32_t *inval,
+                        const int32_t *flags, bool counts_ready) {
+    tdna_ctx *c = a->ctx;
+    TRY(ensure_stream_state(a));
+    if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+    size_t n = (size_t)a->n;
+    unsigned gr = (unsigned)((ncand + 255) / 256);
+    if (gr > 65535u * 4) gr = 65535u * 4;
+    if (gr < 1) gr = 1;
+    int *cnt = a->sp.cnt;
+    if (!counts_ready) {  // gathered records: recount per row
+        CU(cudaMemsetAsync(cnt, 0, n * 4, c->stream));
+        count_rows_kernel<<<gr, 256, 0, c->stream>>>(cq, ncand, cnt);
         c->launches++;
-        CU(cudaGetLastError());
     }
+    exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(cnt, a->n, a->d_ptr);
+    c->launches++;
+    if (ncand > a->list_cap) {
+        if (a->d_lj) CU(DFREE(a->d_lj));
+        if (a->d_ld) CU(DFREE(a->d_ld));
+        a->d_lj = nullptr;
+        a->d_ld = nullptr;
+        long long cap = ncand + ncand / 4 + 1024;
+        CU(DMALLOC(&a->d_lj, (size_t)cap * 4));
+        CU(DMALLOC(&a->d_ld, (size_t)cap * 8));
+        a->list_cap = cap;
+    }
+    CU(cudaMemsetAsync(a->d_cursor, 0, n * 4, c->stream));
+    if (ncand > 0) {
+        stream_scatter_kernel<<<gr, 256, 0, c->stream>>>(cq, cj, cd, ncand, a->d_ptr, a->d_cursor, a->d_lj, a->d_ld);
+        c->launches++;
+    }
+    stream_finalize_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, inval, flags, a->d_species, a->n,
+                                                                                    a->d_res);
+    c->launches++;
+    CU(cudaGetLastError());
+    return fill_shared(a, 0, a->n);
+}
+
+int32_t tdna_best_match_part(tdna_aln *a, int32_t part, int32_t nparts, tdna_stream_part *out) {
+    if (!a || !out || nparts < 1 || part < 0 || part >= nparts) return fail(TDNA_E_ARG, "bad argument");
+    CU(cudaSetDevice(a->ctx->device));
+    TRY(need_labels(a));
+    long long ncand = 0;
+    TRY(stream_part(a, part, nparts, &ncand));
+    out->cand_row = a->sp.cq;
+    out->cand_col = a->sp.cj;
+    out->cand_d = a->sp.cd;
+    out->n_cand = ncand;
+    out->invalid_count = a->sp.inval;
+    out->flags = a->sp.flags;
+    return TDNA_OK;
+}
+
+int32_t tdna_best_match_merge(tdna_aln *a, const int32_t *cand_row, const int32_t *cand_col, const double *cand_d, int64_t n_cand,
+                              const int32_t *invalid_count, const int32_t *flags, tdna_row_result *out) {
+    if (!a || !invalid_count || !flags || n_cand < 0 || (n_cand > 0 && (!cand_row || !cand_col || !cand_d)))
+        return fail(TDNA_E_ARG, "bad argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(need_labels(a));
+    TRY(ensure_packed(a));
+    TRY(stream_merge(a, cand_row, cand_col, cand_d, n_cand, invalid_count, flags, false));
+    if (out) CU(cudaMemcpyAsync(out, a->d_res, (size_t)a->n * sizeof(tdna_row_result), cudaMemcpyDefault, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TDNA_OK;
+}
+
+int32_t tdna_best_match_compute(tdna_aln *a, const tdna_row_result **out_dev) {
+    if (!a) return fail(TDNA_E_ARG, "null alignment");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(need_labels(a));
+    if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+    bool whole = a->row_begin == 0 && a->row_end == a->n;
+    bool done = false;
+    if (whole && c->opt_best_match_path != TDNA_PATH_DENSE) {
+        long long ncand = 0;
+        int rc = stream_part(a, 0, 1, &ncand);
+        if (rc == TDNA_OK) {
+            TRY(stream_merge(a, a->sp.cq, a->sp.cj, a->sp.cd, ncand, a->sp.inval, a->sp.flags, true));
+            done = true;
+        } else if (rc != TDNA_E_TOO_LARGE || c->opt_best_match_path == TDNA_PATH_STREAM) {
+            return rc;
+        }
+    }
+    if (!done) TRY(best_match_dense(a));
     if (out_dev) *out_dev = a->d_res;
     return TDNA_OK;
 }
@@ -743,6 +1013,30 @@ int32_t tdna_time_matrix_kernel(tdna_aln *a, int32_t reps, float *ms_per_launch)
     cudaEventDestroy(e1);
     a->mat_valid = true;
     *ms_per_launch = ms / reps;
+    return TDNA_OK;
+}
+
+int32_t tdna_set_option(tdna_ctx *c, int32_t key, int64_t value) {
+    if (!c) return fail(TDNA_E_ARG, "null ctx");
+    switch (key) {
+        case TDNA_OPT_BEST_MATCH_PATH:
+            if (value < TDNA_PATH_AUTO || value > TDNA_PATH_STREAM) return fail(TDNA_E_ARG, "bad path");
+            c->opt_best_match_path = (int)value;
+            return TDNA_OK;
+        case TDNA_OPT_TILE_COLUMNS:
+            if (value != 0 && value != 64 && value != 128) return fail(TDNA_E_ARG, "tile columns must be 0, 64 or 128");
+            c->opt_tile_cn = (int)(value / 16);
+            return TDNA_OK;
+    }
+    return fail(TDNA_E_ARG, "unknown option");
+}
+
+int32_t tdna_last_tile_pass_ms(tdna_ctx *c, float *ms) {
+    if (!c || !ms) return fail(TDNA_E_ARG, "null argument");
+    if (!c->ev_valid) return fail(TDNA_E_STATE, "no tile pass has run yet");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->ev_k1));
+    CU(cudaEventElapsedTime(ms, c->ev_k0, c->ev_k1));
     return TDNA_OK;
 }
 

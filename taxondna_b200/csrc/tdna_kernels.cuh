@@ -5,6 +5,8 @@
 
 namespace tdna {
 
+static_assert(sizeof(tdna_row_result) == 120, "tdna_row_result must be 120 bytes without padding");
+
 // ------------------------------------------------------------------------------------------
 // pack: normalised symbols -> bit-planes.  HBM-bound, one pass.
 // thread <-> (word k, row) with row fastest, so the 32-byte symbol reads are one sector each and
@@ -115,6 +117,26 @@ template <int KM, int CN> struct TileCfg {
     static constexpr int MIN_CTAS = (CN * NACC <= 4) ? 2 : 1;
 };
 
+// Streaming Best-Match state (one pass over the triangle, no matrix): see "stream epilogue" below.
+struct StreamParams {
+    uint32_t *thr;               // [n] per-row candidate threshold, 16.16 fixed point of (needed distance + 2e-5); 65536 = pass all
+    unsigned long long *mC;      // [n] min d (fp64 bits) over valid named conspecifics; 0 when the row has no conspecific in the list
+    unsigned long long *mPar;    // [2n] min d over valid named columns with even / odd species id
+    int *inval;                  // [n] # j != q with shared < minOverlap
+    int *flags;                  // [n] TDNA_ROW_*
+    int *cnt;                    // [n] candidates emitted for the row
+    int32_t *cq, *cj;            // candidate records (row, column, distance), unordered
+    double *cd;
+    unsigned long long *ncand;   // records emitted so far
+    long long cap;               // capacity of cq/cj/cd
+    int *overflow;               // set when a record did not fit
+    const int32_t *species;
+};
+__constant__ StreamParams c_sp;
+
+enum { SCHED_RECT = 0, SCHED_SYMMETRIC = 1, SCHED_STREAM = 2 };
+enum { EPI_MATRIX = 0, EPI_MATRIX_COUNTS = 1, EPI_STREAM = 2 };
+
 struct TileParams {
     const uint32_t *planes;
     int W;
@@ -123,7 +145,10 @@ struct TileParams {
     int64_t row_begin;  // first row of the band (multiple of 128)
     int64_t row_end;    // one past the last row of the band
     int symmetric;      // band == whole matrix: only tiles touching j >= i are computed, both halves written
-    int64_t num_tiles;
+    int sched;          // SCHED_*: how a tile number maps to (row tile, column tile)
+    int first_col_extra;  // SCHED_STREAM off-diagonal phase: column tiles start TM/TN past the diagonal block
+    int64_t t_offset, t_stride;  // this launch computes global tiles t_offset + k * t_stride (multi-GPU: rank + k * world)
+    int64_t num_tiles;  // tiles of THIS launch
     const int64_t *tile_prefix;  // [row tiles + 1]; symmetric mode only
     int nrt;                     // row tiles
     int nct;                     // column tiles
@@ -132,8 +157,10 @@ struct TileParams {
     tdna_counts *counts;         // optional, same shape, ld = n
 };
 
+// local tile number of this launch -> (row tile, column tile)
 template <int TN> __device__ __forceinline__ void tile_coords(const TileParams &p, const int64_t *prefix, int64_t t, int &ti, int &tj) {
-    if (!p.symmetric) {
+    t = p.t_offset + t * p.t_stride;
+    if (p.sched == SCHED_RECT) {
         ti = (int)(t / p.nct);
         tj = (int)(t % p.nct);
     } else {
@@ -143,7 +170,7 @@ template <int TN> __device__ __forceinline__ void tile_coords(const TileParams &
             if (prefix[mid] <= t) lo = mid; else hi = mid;
         }
         ti = lo;
-        tj = (int)(t - prefix[lo]) + ti * (TM / TN);
+        tj = (int)(t - prefix[lo]) + ti * (TM / TN) + p.first_col_extra;
     }
 }
 
@@ -151,7 +178,172 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- matrix epilogue: counts -> fp64 distance -> band matrix (registers only) ----------------
 template <int KM, int CN, bool WRITE_COUNTS>
+__device__ __forceinline__ void matrix_epilogue(const TileParams &p, uint32_t (&acc)[ModeTraits<KM>::NACC][8][CN], int ti, int tj, int tx, int ty) {
+    constexpr int NACC = ModeTraits<KM>::NACC, TN = 16 * CN;
+    const int64_t i0 = p.row_begin + (int64_t)ti * TM + ty * 8, j0 = (int64_t)tj * TN;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {  // fully unrolled: acc[][][] must stay in registers
+        const int64_t i = i0 + r;
+        const bool row_ok = i < p.row_end;
+        double dv[CN];
+#pragma unroll
+        for (int e = 0; e < CN; e++) {
+            uint32_t a1 = 0;
+            if constexpr (NACC == 2) a1 = acc[1][r][e];
+            Counts cn = unpack_counts<KM>(acc[0][r][e], a1);
+            dv[e] = distance_from_counts<KM>(cn, p.min_overlap);
+            if constexpr (WRITE_COUNTS) {
+                const int64_t j = j0 + (e >> 2) * PR + 4 * tx + (e & 3);
+                if (row_ok && j < p.n) {
+                    tdna_counts o = {cn.shared, cn.c1, cn.c2, cn.c3};
+                    p.counts[(i - p.row_begin) * p.n + j] = o;
+                }
+            }
+        }
+        if (!row_ok) continue;
+#pragma unroll
+        for (int h = 0; h < CN / 4; h++) {
+            const int64_t jb = j0 + h * PR + 4 * tx;
+            double *dst = p.out + (i - p.row_begin) * p.ld + jb;
+            if (jb + 3 < p.n) {  // ld and jb are multiples of 4 doubles: 32-byte aligned
+                reinterpret_cast<double2 *>(dst)[0] = make_double2(dv[4 * h + 0], dv[4 * h + 1]);
+                reinterpret_cast<double2 *>(dst)[1] = make_double2(dv[4 * h + 2], dv[4 * h + 3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (jb + e < p.n) dst[e] = dv[4 * h + e];
+            }
+            if (p.symmetric) {  // mirror (band == whole matrix, row_begin == 0)
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (jb + e < p.n && jb + e > i) p.out[(jb + e) * p.ld + i] = dv[4 * h + e];
+            }
+        }
+    }
+}
+
+// ---- stream epilogue: no matrix -----------------------------------------------------------------
+// Every unordered pair i < j is seen exactly once (triangle tiles).  A pair becomes a CANDIDATE of
+// row i (and, separately, of row j) when its distance is not above that row's threshold
+//     thr[q] >= max(min d over named conspecifics, min d over named even-species columns,
+//                   min d over named odd-species columns) + 2e-5,
+// which bounds every distance tdna_row_result refers to (best <= con/allo/other <= that max: two
+// named columns of different parity are of different species, so one of them is not of species(best))
+// plus the near-tie window.  Thresholds only ever decrease, so the candidate list of a row is a
+// superset of {j : d(q,j) <= final threshold} and stream_finalize_kernel can run the exact two-sweep
+// row summary on the list alone.  The per-pair test is integer only (mism << 16 <= thr * den, a
+// conservative statement of d <= thr: for K2P, d >= (ts+tv)/n); fp64 happens on candidates only.
+#define TDNA_THR_ALL 65536u
+#define TDNA_INF_BITS 0x7ff0000000000000ull
+
+__device__ __forceinline__ void stream_emit_side(int q, int o, double d, uint32_t lhs, uint32_t den) {
+    const StreamParams &sp = c_sp;
+    const uint32_t fresh = *reinterpret_cast<volatile uint32_t *>(sp.thr + q);  // other CTAs tighten it all the time
+    if (lhs > fresh * den) return;
+    const unsigned long long pos = atomicAdd(sp.ncand, 1ull);
+    if ((long long)pos >= sp.cap) { *sp.overflow = 1; return; }
+    sp.cq[pos] = q;
+    sp.cj[pos] = o;
+    sp.cd[pos] = d;
+    atomicAdd(sp.cnt + q, 1);
+    const int spo = sp.species[o];
+    if (spo < 0) return;  // unnamed columns bound nothing
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+    if (spo == sp.species[q]) atomicMin(sp.mC + q, bits);
+    atomicMin(sp.mPar + 2 * (int64_t)q + (spo & 1), bits);
+    const unsigned long long mc = *reinterpret_cast<volatile unsigned long long *>(sp.mC + q);
+    const unsigned long long me = *reinterpret_cast<volatile unsigned long long *>(sp.mPar + 2 * (int64_t)q);
+    const unsigned long long mo = *reinterpret_cast<volatile unsigned long long *>(sp.mPar + 2 * (int64_t)q + 1);
+    const unsigned long long m = max(mc, max(me, mo));
+    if (m < TDNA_INF_BITS) {
+        const double T = __longlong_as_double((long long)m) + 2e-5;
+        if (T < 1.0) atomicMin(sp.thr + q, (uint32_t)(T * 65536.0) + 2u);
+    }
+}
+
+template <int KM> __device__ __noinline__ void stream_emit(int i, int j, uint32_t a0, uint32_t a1, uint32_t lhs, uint32_t den, int min_overlap) {
+    Counts cn = unpack_counts<KM>(a0, a1);
+    const double d = distance_from_counts<KM>(cn, min_overlap);
+    if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) {  // NaN / +Inf: the host resolves these rows from tdna_row_distances
+        atomicOr(c_sp.flags + i, TDNA_ROW_NONFINITE);
+        atomicOr(c_sp.flags + j, TDNA_ROW_NONFINITE);
+        return;
+    }
+    stream_emit_side(i, j, d, lhs, den);
+    stream_emit_side(j, i, d, lhs, den);
+}
+
+template <int KM, int CN>
+__device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&acc)[ModeTraits<KM>::NACC][8][CN], int ti, int tj, int tx, int ty) {
+    constexpr int NACC = ModeTraits<KM>::NACC, TN = 16 * CN;
+    const StreamParams &sp = c_sp;
+    const int n = (int)p.n;
+    const int i0 = ti * TM + ty * 8, j0 = tj * TN;
+    uint32_t tfi[8], tfj[CN];
+#pragma unroll
+    for (int r = 0; r < 8; r++) tfi[r] = (i0 + r < n) ? __ldcg(sp.thr + i0 + r) : 0u;
+#pragma unroll
+    for (int e = 0; e < CN; e++) {
+        const int j = j0 + (e >> 2) * PR + 4 * tx + (e & 3);
+        tfj[e] = (j < n) ? __ldcg(sp.thr + j) : 0u;
+    }
+    uint32_t bad_r = 0, bad_c = 0;  // invalid pairs per row / column of this thread, one nibble each (<= 8)
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int i = i0 + r;
+#pragma unroll
+        for (int e = 0; e < CN; e++) {
+            const int j = j0 + (e >> 2) * PR + 4 * tx + (e & 3);
+            const uint32_t a0 = acc[0][r][e];
+            const uint32_t s = a0 >> 16, c1 = a0 & 0xffffu;
+            if (j <= i || j >= n) {
+                if (j == i && i < n && (int)s >= p.min_overlap) atomicOr(sp.flags + i, TDNA_ROW_SELF_VALID);
+                continue;
+            }
+            if ((int)s < p.min_overlap) {  // -1.0 in the reference: not a candidate of anything
+                bad_r += 1u << (4 * r);
+                bad_c += 1u << (4 * e);
+                continue;
+            }
+            uint32_t a1 = 0, mism, den;
+            bool force = false;
+            if constexpr (KM == KM_K2P) {
+                a1 = acc[1][r][e];
+                const uint32_t ts = a1 & 0xffffu, tv = a1 >> 16;
+                mism = ts + tv;  // d_K2P >= P + Q
+                den = c1;
+                force = (2 * ts + tv >= c1) || (2 * tv >= c1);  // w1 <= 0 or w2 <= 0 or n == 0: NaN / Inf must be flagged
+            } else if constexpr (KM == KM_TRANS) {
+                mism = c1;
+                den = s;
+            } else {
+                mism = s - c1;
+                den = s;
+            }
+            const uint32_t lhs = mism << 16;
+            if (lhs <= tfi[r] * den || lhs <= tfj[e] * den || force) stream_emit<KM>(i, j, a0, a1, lhs, den, p.min_overlap);
+        }
+    }
+    if (__any_sync(0xffffffffu, (bad_r | bad_c) != 0)) {  // rare on clean data
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            int v = (int)((bad_r >> (4 * r)) & 15u);
+#pragma unroll
+            for (int m = 8; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);  // the 16 tx lanes of this row
+            if (tx == 0 && v) atomicAdd(sp.inval + i0 + r, v);
+        }
+#pragma unroll
+        for (int e = 0; e < CN; e++) {
+            int v = (int)((bad_c >> (4 * e)) & 15u);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);  // the two ty rows of this warp
+            if ((threadIdx.x & 16) == 0 && v) atomicAdd(sp.inval + j0 + (e >> 2) * PR + 4 * tx + (e & 3), v);
+        }
+    }
+}
+
+template <int KM, int CN, int EPI>
 __global__ void __launch_bounds__(TILE_THREADS, TileCfg<KM, CN>::MIN_CTAS) count_tile_kernel(TileParams p) {
     using Cfg = TileCfg<KM, CN>;
     constexpr int P = Cfg::P, NACC = Cfg::NACC, TN = Cfg::TN;
@@ -166,7 +358,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TileCfg<KM, CN>::MIN_CTAS) count
     const int64_t my_tiles = (p.num_tiles > blockIdx.x) ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total = my_tiles * nchunks;
 
-    const bool prefix_in_smem = p.symmetric && p.nrt + 1 <= PREFIX_SMEM;
+    const bool prefix_in_smem = p.sched != SCHED_RECT && p.nrt + 1 <= PREFIX_SMEM;
     if (prefix_in_smem)
         for (int i = tid; i <= p.nrt; i += TILE_THREADS) s_prefix[i] = p.tile_prefix[i];
     const int64_t *prefix = prefix_in_smem ? s_prefix : p.tile_prefix;
@@ -254,50 +446,12 @@ __global__ void __launch_bounds__(TILE_THREADS, TileCfg<KM, CN>::MIN_CTAS) count
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty[slot]);  // this warp is done reading the stage
-        if (c == nchunks - 1) {  // epilogue: counts -> fp64 distance -> band matrix (registers only)
+        if (c == nchunks - 1) {
             const int64_t t = blockIdx.x + (it / nchunks) * gridDim.x;
             int ti, tj;
             tile_coords<TN>(p, prefix, t, ti, tj);
-            const int64_t i0 = p.row_begin + (int64_t)ti * TM + ty * 8, j0 = (int64_t)tj * TN;
-#pragma unroll
-            for (int r = 0; r < 8; r++) {  // fully unrolled: acc[][][] must stay in registers
-                const int64_t i = i0 + r;
-                const bool row_ok = i < p.row_end;
-                double dv[CN];
-#pragma unroll
-                for (int e = 0; e < CN; e++) {
-                    uint32_t a1 = 0;
-                    if constexpr (NACC == 2) a1 = acc[1][r][e];
-                    Counts cn = unpack_counts<KM>(acc[0][r][e], a1);
-                    dv[e] = distance_from_counts<KM>(cn, p.min_overlap);
-                    if constexpr (WRITE_COUNTS) {
-                        const int64_t j = j0 + (e >> 2) * PR + 4 * tx + (e & 3);
-                        if (row_ok && j < p.n) {
-                            tdna_counts o = {cn.shared, cn.c1, cn.c2, cn.c3};
-                            p.counts[(i - p.row_begin) * p.n + j] = o;
-                        }
-                    }
-                }
-                if (!row_ok) continue;
-#pragma unroll
-                for (int h = 0; h < CN / 4; h++) {
-                    const int64_t jb = j0 + h * PR + 4 * tx;
-                    double *dst = p.out + (i - p.row_begin) * p.ld + jb;
-                    if (jb + 3 < p.n) {  // ld and jb are multiples of 4 doubles: 32-byte aligned
-                        reinterpret_cast<double2 *>(dst)[0] = make_double2(dv[4 * h + 0], dv[4 * h + 1]);
-                        reinterpret_cast<double2 *>(dst)[1] = make_double2(dv[4 * h + 2], dv[4 * h + 3]);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; e++)
-                            if (jb + e < p.n) dst[e] = dv[4 * h + e];
-                    }
-                    if (p.symmetric) {  // mirror (band == whole matrix, row_begin == 0)
-#pragma unroll
-                        for (int e = 0; e < 4; e++)
-                            if (jb + e < p.n && jb + e > i) p.out[(jb + e) * p.ld + i] = dv[4 * h + e];
-                    }
-                }
-            }
+            if constexpr (EPI == EPI_STREAM) stream_epilogue<KM, CN>(p, acc, ti, tj, tx, ty);
+            else matrix_epilogue<KM, CN, EPI == EPI_MATRIX_COUNTS>(p, acc, ti, tj, tx, ty);
         }
     }
 }
@@ -429,8 +583,123 @@ __device__ __forceinline__ RowAgg agg_shfl_xor(const RowAgg &a, int m) {
     return r;
 }
 
-// Two sweeps per query row, the second one out of L2: the grid is persistent with ONE 512-thread CTA
-// per SM so that the rows in flight (148 x N x 8 B) stay L2-resident between the sweeps.
+// ---- the two sweeps of a query's row, element by element (shared by the dense row kernel and the
+// ---- candidate-list finaliser so that both state the same semantics) ---------------------------
+__device__ __forceinline__ RowAgg agg_identity() {
+    Key none = {TDNA_KEY_NONE, TDNA_KEY_NONE};
+    RowAgg g = {none, none, none, {none, none, -2, -2}, 0, 0};
+    return g;
+}
+
+// sweep 1: arg-min keys.  (j, d, spj) is one column of query q's row; the caller skipped j == q and d < 0.
+__device__ __forceinline__ void sweep1_elem(RowAgg &g, int spq, bool qnamed, int64_t j, double d, int spj) {
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    g.nvalid++;
+    if (!(d < INF)) { g.nonfinite = 1; if (d != d) return; }
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+    const bool consp = qnamed && spj == spq;  // SortedSequenceComparator: conspecific-to-query first (:236-255)
+    // fast reject: larger than every running minimum this column could still replace (NONE = all ones)
+    unsigned long long thr = g.kb.hi;
+    if (spj >= 0) {
+        thr = max(thr, g.t2.k2.hi);
+        if (qnamed) thr = max(thr, consp ? g.kc.hi : g.ka.hi);
+    }
+    if (bits > thr) return;
+    Key k = {bits, ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
+    g.kb = key_min(g.kb, k);
+    if (spj >= 0) {
+        top2_insert(g.t2, k, spj);
+        if (qnamed) {
+            Key k2 = {bits, (unsigned long long)j};
+            if (consp) g.kc = key_min(g.kc, k2); else g.ka = key_min(g.ka, k2);
+        }
+    }
+}
+
+struct RowRefs {  // what sweep 2 measures against
+    Key kb, kc, ka, ko;
+    bool has_b, has_c, has_a, has_o;
+    int jb, spb;
+    double db, dc, da, dother, dmax;
+};
+__device__ __forceinline__ RowRefs make_refs(const RowAgg &g, const int32_t *__restrict__ species) {
+    RowRefs f;
+    f.kb = g.kb; f.kc = g.kc; f.ka = g.ka;
+    f.has_b = f.kb.hi != TDNA_KEY_NONE; f.has_c = f.kc.hi != TDNA_KEY_NONE; f.has_a = f.ka.hi != TDNA_KEY_NONE;
+    f.jb = f.has_b ? (int)(f.kb.lo & 0xffffffffu) : -1;
+    f.db = f.has_b ? __longlong_as_double((long long)f.kb.hi) : -1.0;
+    f.dc = f.has_c ? __longlong_as_double((long long)f.kc.hi) : -1.0;
+    f.da = f.has_a ? __longlong_as_double((long long)f.ka.hi) : -1.0;
+    f.spb = f.has_b ? species[f.jb] : -1;
+    // first named entry of a species other than species(best): if best is named it IS t2.k1
+    f.ko = (f.has_b && f.spb >= 0) ? g.t2.k2 : g.t2.k1;
+    f.has_o = f.has_b && f.ko.hi != TDNA_KEY_NONE;
+    f.dother = f.has_o ? __longlong_as_double((long long)f.ko.hi) : -1.0;
+    // nothing beyond the largest reference distance plus the near-tie window is ever counted -- unless no
+    // other species exists at all: then every column of species(best) belongs to the leading run
+    f.dmax = f.has_o ? fmax(fmax(f.db, f.dc), fmax(f.da, f.dother)) + TDNA_NEAR : __longlong_as_double(0x7ff0000000000000LL);
+    return f;
+}
+
+struct Sweep2 {  // tie class, near-tie windows, leading same-species run
+    int v[10];   // ties, tie_unnamed, near_b, near_c, near_a, near_o, un_c, un_a, un_o, block
+    int smin, smax;
+};
+__device__ __forceinline__ Sweep2 sweep2_identity() {
+    Sweep2 s;
+#pragma unroll
+    for (int i = 0; i < 10; i++) s.v[i] = 0;
+    s.smin = 0x7fffffff;
+    s.smax = -1;
+    return s;
+}
+__device__ __forceinline__ void sweep2_elem(Sweep2 &s, const RowRefs &f, int spq, bool qnamed, int64_t j, double d, int spj) {
+    if (!(d <= f.dmax)) return;
+    if (d == f.db && j != f.jb) {
+        s.v[0]++;
+        if (spj < 0) s.v[1]++; else { s.smin = min(s.smin, spj); s.smax = max(s.smax, spj); }
+    }
+    s.v[2] += is_near(d, f.db);
+    if (f.has_c) { s.v[3] += is_near(d, f.dc); s.v[6] += (spj < 0 && d == f.dc); }
+    if (f.has_a) { s.v[4] += is_near(d, f.da); s.v[7] += (spj < 0 && d == f.da); }
+    if (f.has_o) { s.v[5] += is_near(d, f.dother); s.v[8] += (spj < 0 && d == f.dother); }
+    if (j != f.jb && spj >= 0 && spj == f.spb) {
+        const bool consp = qnamed && spj == spq;
+        Key k = {(unsigned long long)__double_as_longlong(d), ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
+        if (!f.has_o || key_less(k, f.ko)) s.v[9]++;
+    }
+}
+__device__ __forceinline__ void sweep2_warp_reduce(Sweep2 &s) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 10; i++) s.v[i] += __shfl_xor_sync(0xffffffffu, s.v[i], m);
+        s.smin = min(s.smin, __shfl_xor_sync(0xffffffffu, s.smin, m));
+        s.smax = max(s.smax, __shfl_xor_sync(0xffffffffu, s.smax, m));
+    }
+}
+__device__ __forceinline__ tdna_row_result make_row_result(const RowRefs &f, const Sweep2 &s, int nvalid, int flags) {
+    tdna_row_result r;
+    r.d_best = f.db; r.d_con = f.dc; r.d_allo = f.da; r.d_other = f.dother;
+    r.best = f.jb;
+    r.con = f.has_c ? (int)(f.kc.lo & 0xffffffffu) : -1;
+    r.allo = f.has_a ? (int)(f.ka.lo & 0xffffffffu) : -1;
+    r.other = f.has_o ? (int)(f.ko.lo & 0xffffffffu) : -1;
+    r.shared_con = 0; r.shared_allo = 0;  // filled by fill_shared_kernel
+    r.tie_count = s.v[0]; r.tie_unnamed = s.v[1]; r.tie_species_min = s.smin; r.tie_species_max = s.smax;
+    r.near_best = s.v[2]; r.near_con = s.v[3]; r.near_allo = s.v[4]; r.near_other = s.v[5];
+    r.unnamed_at_con = s.v[6]; r.unnamed_at_allo = s.v[7]; r.unnamed_at_other = s.v[8];
+    r.block_count = s.v[9];
+    r.n_valid = nvalid;
+    r.flags = flags;
+    r.reserved = 0;
+    r.reserved2 = 0;
+    return r;
+}
+
+// Dense variant: two sweeps per query row of a materialised band, the second one out of L2: the grid
+// is persistent with ONE 512-thread CTA per SM so that the rows in flight (148 x N x 8 B) stay
+// L2-resident between the sweeps.
 __global__ void __launch_bounds__(RS_THREADS, 1) row_summary_kernel(const double *__restrict__ mat, int64_t ld, int64_t n, int64_t row_begin,
                                                                    int64_t rows, const int32_t *__restrict__ species,
                                                                    tdna_row_result *__restrict__ out) {
@@ -438,7 +707,6 @@ __global__ void __launch_bounds__(RS_THREADS, 1) row_summary_kernel(const double
     __shared__ RowAgg s_final;
     __shared__ int s_cnt[16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const int64_t stride = (int64_t)RS_THREADS * 2;
 
     for (int64_t qb = blockIdx.x; qb < rows; qb += gridDim.x) {
@@ -448,8 +716,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) row_summary_kernel(const double
         const bool qnamed = spq >= 0;
 
         // ---- sweep 1 (HBM): arg-min keys -------------------------------------------------------
-        Key none = {TDNA_KEY_NONE, TDNA_KEY_NONE};
-        RowAgg g = {none, none, none, {none, none, -2, -2}, 0, 0};
+        RowAgg g = agg_identity();
         for (int64_t base = (int64_t)threadIdx.x * 2; base < n; base += stride * RS_UNROLL) {
             double2 v[RS_UNROLL];
             int2 sp2[RS_UNROLL];
@@ -471,26 +738,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) row_summary_kernel(const double
                     const double d = e ? v[u].y : v[u].x;
                     const int spj = e ? sp2[u].y : sp2[u].x;
                     if (j >= n || j == q || d < 0) continue;
-                    g.nvalid++;
-                    if (!(d < INF)) { g.nonfinite = 1; if (d != d) continue; }
-                    const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
-                    const bool consp = qnamed && spj == spq;  // SortedSequenceComparator: conspecific-to-query first (:236-255)
-                    // fast reject: larger than every running minimum this column could still replace (NONE = all ones)
-                    unsigned long long thr = g.kb.hi;
-                    if (spj >= 0) {
-                        thr = max(thr, g.t2.k2.hi);
-                        if (qnamed) thr = max(thr, consp ? g.kc.hi : g.ka.hi);
-                    }
-                    if (bits > thr) continue;
-                    Key k = {bits, ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
-                    g.kb = key_min(g.kb, k);
-                    if (spj >= 0) {
-                        top2_insert(g.t2, k, spj);
-                        if (qnamed) {
-                            Key k2 = {bits, (unsigned long long)j};
-                            if (consp) g.kc = key_min(g.kc, k2); else g.ka = key_min(g.ka, k2);
-                        }
-                    }
+                    sweep1_elem(g, spq, qnamed, j, d, spj);
                 }
             }
         }
@@ -498,35 +746,21 @@ __global__ void __launch_bounds__(RS_THREADS, 1) row_summary_kernel(const double
         for (int m = 16; m >= 1; m >>= 1) { RowAgg o = agg_shfl_xor(g, m); agg_merge(g, o); }
         __syncthreads();  // the previous row's readers of the shared arrays are done
         if (lane == 0) s_agg[warp] = g;
-        if (threadIdx.x < 16) s_cnt[threadIdx.x] = (threadIdx.x == 2) ? 0x7fffffff : (threadIdx.x == 3 ? -1 : 0);
+        if (threadIdx.x < 16) s_cnt[threadIdx.x] = (threadIdx.x == 10) ? 0x7fffffff : (threadIdx.x == 11 ? -1 : 0);
         __syncthreads();
-        if (warp == 0) {  // one warp folds the 32 per-warp partials
-            RowAgg ident = {none, none, none, {none, none, -2, -2}, 0, 0};
-            g = lane < RS_WARPS ? s_agg[lane] : ident;
+        if (warp == 0) {  // one warp folds the per-warp partials
+            g = lane < RS_WARPS ? s_agg[lane] : agg_identity();
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) { RowAgg o = agg_shfl_xor(g, m); agg_merge(g, o); }
             if (lane == 0) s_final = g;
         }
         __syncthreads();
         g = s_final;
-        const Key kb = g.kb, kc = g.kc, ka = g.ka;
-        const bool has_b = kb.hi != TDNA_KEY_NONE, has_c = kc.hi != TDNA_KEY_NONE, has_a = ka.hi != TDNA_KEY_NONE;
-        const int jb = has_b ? (int)(kb.lo & 0xffffffffu) : -1;
-        const double db = has_b ? __longlong_as_double((long long)kb.hi) : -1.0;
-        const double dc = has_c ? __longlong_as_double((long long)kc.hi) : -1.0;
-        const double da = has_a ? __longlong_as_double((long long)ka.hi) : -1.0;
-        const int spb = has_b ? species[jb] : -1;
-        // first named entry of a species other than species(best): if best is named it IS t2.k1
-        const Key ko = (has_b && spb >= 0) ? g.t2.k2 : g.t2.k1;
-        const bool has_o = has_b && ko.hi != TDNA_KEY_NONE;
-        const double dother = has_o ? __longlong_as_double((long long)ko.hi) : -1.0;
+        const RowRefs f = make_refs(g, species);
 
         // ---- sweep 2 (L2): tie class, near-tie windows, leading same-species run ----------------
-        if (has_b) {
-            int ties = 0, tie_unnamed = 0, smin = 0x7fffffff, smax = -1;
-            int near_b = 0, near_c = 0, near_a = 0, near_o = 0, un_c = 0, un_a = 0, un_o = 0, block = 0;
-            // nothing beyond the largest reference distance plus the near-tie window is ever counted
-            const double dmax = fmax(fmax(db, dc), fmax(da, dother)) + TDNA_NEAR;
+        if (f.has_b) {
+            Sweep2 s2 = sweep2_identity();
             for (int64_t base = (int64_t)threadIdx.x * 2; base < n; base += stride * RS_UNROLL) {
                 double2 v[RS_UNROLL];
                 int2 sp2[RS_UNROLL];
@@ -547,61 +781,116 @@ __global__ void __launch_bounds__(RS_THREADS, 1) row_summary_kernel(const double
                         const int64_t j = j0 + e;
                         const double d = e ? v[u].y : v[u].x;
                         const int spj = e ? sp2[u].y : sp2[u].x;
-                        if (j >= n || j == q || d < 0 || !(d <= dmax)) continue;
-                        if (d == db && j != jb) {
-                            ties++;
-                            if (spj < 0) tie_unnamed++; else { smin = min(smin, spj); smax = max(smax, spj); }
-                        }
-                        near_b += is_near(d, db);
-                        if (has_c) { near_c += is_near(d, dc); un_c += (spj < 0 && d == dc); }
-                        if (has_a) { near_a += is_near(d, da); un_a += (spj < 0 && d == da); }
-                        if (has_o) { near_o += is_near(d, dother); un_o += (spj < 0 && d == dother); }
-                        if (j != jb && spj >= 0 && spj == spb) {
-                            const bool consp = qnamed && spj == spq;
-                            Key k = {(unsigned long long)__double_as_longlong(d), ((unsigned long long)(consp ? 0 : 1) << 32) | (unsigned long long)j};
-                            if (!has_o || key_less(k, ko)) block++;
-                        }
+                        if (j >= n || j == q || d < 0) continue;
+                        sweep2_elem(s2, f, spq, qnamed, j, d, spj);
                     }
                 }
             }
-            int vals[10] = {ties, tie_unnamed, near_b, near_c, near_a, near_o, un_c, un_a, un_o, block};
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) {
-#pragma unroll
-                for (int i = 0; i < 10; i++) vals[i] += __shfl_xor_sync(0xffffffffu, vals[i], m);
-                smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, m));
-                smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, m));
-            }
+            sweep2_warp_reduce(s2);
             if (lane == 0) {
-                if (vals[0]) atomicAdd(&s_cnt[0], vals[0]);
-                if (vals[1]) atomicAdd(&s_cnt[1], vals[1]);
-                if (smin != 0x7fffffff) atomicMin(&s_cnt[2], smin);
-                if (smax >= 0) atomicMax(&s_cnt[3], smax);
 #pragma unroll
-                for (int i = 2; i < 10; i++)
-                    if (vals[i]) atomicAdd(&s_cnt[2 + i], vals[i]);
+                for (int i = 0; i < 10; i++)
+                    if (s2.v[i]) atomicAdd(&s_cnt[i], s2.v[i]);
+                if (s2.smin != 0x7fffffff) atomicMin(&s_cnt[10], s2.smin);
+                if (s2.smax >= 0) atomicMax(&s_cnt[11], s2.smax);
             }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            tdna_row_result r;
-            r.d_best = db; r.d_con = dc; r.d_allo = da; r.d_other = dother;
-            r.best = jb;
-            r.con = has_c ? (int)(kc.lo & 0xffffffffu) : -1;
-            r.allo = has_a ? (int)(ka.lo & 0xffffffffu) : -1;
-            r.other = has_o ? (int)(ko.lo & 0xffffffffu) : -1;
-            r.shared_con = 0; r.shared_allo = 0;  // filled by fill_shared_kernel
-            r.tie_count = s_cnt[0]; r.tie_unnamed = s_cnt[1]; r.tie_species_min = s_cnt[2]; r.tie_species_max = s_cnt[3];
-            r.near_best = s_cnt[4]; r.near_con = s_cnt[5]; r.near_allo = s_cnt[6]; r.near_other = s_cnt[7];
-            r.unnamed_at_con = s_cnt[8]; r.unnamed_at_allo = s_cnt[9]; r.unnamed_at_other = s_cnt[10];
-            r.block_count = s_cnt[11];
-            r.n_valid = g.nvalid;
+            Sweep2 s2;
+#pragma unroll
+            for (int i = 0; i < 10; i++) s2.v[i] = s_cnt[i];
+            s2.smin = s_cnt[10];
+            s2.smax = s_cnt[11];
             double dself = row[q];
-            r.flags = (!(dself < 0) ? TDNA_ROW_SELF_VALID : 0) | (g.nonfinite ? TDNA_ROW_NONFINITE : 0);
-            r.reserved = 0;
-            out[q] = r;
+            out[q] = make_row_result(f, s2, g.nvalid, (!(dself < 0) ? TDNA_ROW_SELF_VALID : 0) | (g.nonfinite ? TDNA_ROW_NONFINITE : 0));
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// streaming Best Match, after the tile pass: state init, candidate CSR, exact per-row summaries
+// ------------------------------------------------------------------------------------------
+// needc[q] != 0: q is named and another row of its species exists (labels only; set by the host side)
+__global__ void __launch_bounds__(256) stream_init_kernel(StreamParams sp, int64_t n, const uint8_t *__restrict__ needc) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) { *sp.ncand = 0ull; *sp.overflow = 0; }
+    if (q >= n) return;
+    sp.thr[q] = TDNA_THR_ALL;
+    sp.mC[q] = needc[q] ? TDNA_INF_BITS : 0ull;
+    sp.mPar[2 * q] = TDNA_INF_BITS;
+    sp.mPar[2 * q + 1] = TDNA_INF_BITS;
+    sp.inval[q] = 0;
+    sp.flags[q] = 0;
+    sp.cnt[q] = 0;
+}
+
+// exclusive prefix sum of cnt[0..n) into ptr[0..n] (one CTA; n <= a few million)
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int *__restrict__ cnt, int64_t n, long long *__restrict__ ptr) {
+    __shared__ long long s_part[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (n + 1023) / 1024, b = t * per, e = min(n, b + per);
+    long long sum = 0;
+    for (int64_t i = b; i < e; i++) sum += cnt[i];
+    s_part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele over the 1024 partials
+        long long v = t >= off ? s_part[t - off] : 0;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    long long run = s_part[t] - sum;
+    for (int64_t i = b; i < e; i++) { ptr[i] = run; run += cnt[i]; }
+    if (t == 1023) ptr[n] = s_part[1023];
+}
+
+// scatter the unordered records into per-row lists; cursor[] starts at zero
+__global__ void __launch_bounds__(256) stream_scatter_kernel(const int32_t *__restrict__ cq, const int32_t *__restrict__ cj,
+                                                             const double *__restrict__ cd, long long ncand,
+                                                             const long long *__restrict__ ptr, int *__restrict__ cursor,
+                                                             int32_t *__restrict__ lj, double *__restrict__ ld) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < ncand; r += (long long)gridDim.x * blockDim.x) {
+        const int q = cq[r];
+        const long long slot = ptr[q] + atomicAdd(cursor + q, 1);
+        lj[slot] = cj[r];
+        ld[slot] = cd[r];
+    }
+}
+__global__ void __launch_bounds__(256) count_rows_kernel(const int32_t *__restrict__ cq, long long ncand, int *__restrict__ cnt) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < ncand; r += (long long)gridDim.x * blockDim.x)
+        atomicAdd(cnt + cq[r], 1);
+}
+
+// one warp per query row: the two sweeps over the row's candidate list (complete below its threshold)
+__global__ void __launch_bounds__(256) stream_finalize_kernel(const long long *__restrict__ ptr, const int32_t *__restrict__ lj,
+                                                              const double *__restrict__ ld, const int *__restrict__ inval,
+                                                              const int *__restrict__ flags, const int32_t *__restrict__ species,
+                                                              int64_t n, tdna_row_result *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= n) return;
+    const int spq = species[q];
+    const bool qnamed = spq >= 0;
+    const long long b = ptr[q], e = ptr[q + 1];
+    RowAgg g = agg_identity();
+    for (long long k = b + lane; k < e; k += 32) {
+        const int j = lj[k];
+        sweep1_elem(g, spq, qnamed, j, ld[k], species[j]);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { RowAgg o = agg_shfl_xor(g, m); agg_merge(g, o); }
+    const RowRefs f = make_refs(g, species);
+    Sweep2 s2 = sweep2_identity();
+    if (f.has_b) {
+        for (long long k = b + lane; k < e; k += 32) {
+            const int j = lj[k];
+            sweep2_elem(s2, f, spq, qnamed, j, ld[k], species[j]);
+        }
+        sweep2_warp_reduce(s2);
+    }
+    // every valid column is counted through inval[] (the list holds only the near ones)
+    if (lane == 0) out[q] = make_row_result(f, s2, (int)(n - 1) - inval[q], flags[q]);
 }
 
 // getSharedLength(query, first_con / first_allo) for the listing (BestMatch.java:372,386)
