@@ -4,18 +4,21 @@
   python bench.py --gpus N --steps K --warmup W [--workload C2|C3|H|C4] [--impl reference]
 
 A "step" is one pass of the hot path over one synthetic alignment of a BASELINE.json shape:
-  C2 (default, configs[1]): 2,185 x 2,664, uncorrected p: full fp64 pairwise matrix + the two Pairwise
-      Summary classes (intra / congeneric inter distance extraction)
+  H (default): 50,000 x 658, p: per-query Best Match summaries -- the shape BASELINE.json's north_star quotes
+      its target on ("... at 50,000 x 658 bp ..."); fits one GPU
+  C2 (configs[1]): 2,185 x 2,664, uncorrected p: full fp64 pairwise matrix + the two Pairwise Summary
+      classes (intra / congeneric inter distance extraction)
   C3: 8,000 x 658, K2P: per-query Best Close Match summaries + intraspecific distances (threshold percentile)
-  H : 50,000 x 658, p: per-query Best Match summaries (the north-star headline shape)
 metric = unordered pairs i<j per second (Gpairs/s).  `value`: inputs (bit-planes, labels) resident
 in HBM, results left in HBM, each step timed with CUDA events on the library's stream, L2 flushed
 between steps.  `e2e`: the same work through the C ABI with HOST buffers (symbols in, results out),
 host<->device copies inside the timed region.
 
-N > 1 (torchrun, one rank per GPU): the query rows are split into row bands, one per rank, every
-rank holds the whole packed alignment; the per-row results are exchanged with one NCCL all_gather
-at the end of the step.  Weak scaling: the alignment grows as sqrt(N) so pairs per GPU stay fixed.
+N > 1 (torchrun, one rank per GPU): every rank holds the whole packed alignment.  Best-Match steps
+share the triangle of tiles cyclically (rank r takes tiles r, r+N, ...: tdna_best_match_part) and
+exchange their candidate records / per-row counts once per step over NCCL, then merge; matrix steps
+split the query rows into bands (no collective).  Weak scaling: the alignment grows as sqrt(N) so
+pairs per GPU stay fixed.
 
 --impl reference: the reference's CPU algorithm (oracle/ C restatement of Sequence.getPairwise --
 the reference is Java and no JVM exists in this image) on the host cores, bounded sample.
@@ -48,7 +51,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="H", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -163,10 +166,37 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class _DevBuf:
+    """Zero-copy torch view of library-owned device memory (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def exchange_parts(torch, dist, dev, part, n, world):
+    """The multi-GPU exchange step of the streaming path (taxondna_b200.shard.exchange_candidates) on
+    zero-copy views of the library's device buffers."""
+    from taxondna_b200 import shard
+    k = int(part.n_cand)
+    if k:
+        rows = torch.as_tensor(_DevBuf(part.cand_row, k, "<i4"), device=dev)
+        cols = torch.as_tensor(_DevBuf(part.cand_col, k, "<i4"), device=dev)
+        d = torch.as_tensor(_DevBuf(part.cand_d, k, "<f8"), device=dev)
+    else:
+        rows = torch.zeros(0, dtype=torch.int32, device=dev)
+        cols = torch.zeros(0, dtype=torch.int32, device=dev)
+        d = torch.zeros(0, dtype=torch.float64, device=dev)
+    inval = torch.as_tensor(_DevBuf(part.invalid_count, n, "<i4"), device=dev)
+    flags = torch.as_tensor(_DevBuf(part.flags, n, "<i4"), device=dev)
+    return shard.exchange_candidates(rows, cols, d, inval, flags)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+
+    import ctypes
 
     import torch
     import torch.distributed as dist
@@ -180,16 +210,19 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
 
     wl = WORKLOADS[args.workload]
     mode = wl["mode"]
+    kind = wl["kind"]
+    streaming = kind.startswith("bestmatch")
     base = synth.CONFIGS[wl["config"]]
     n1 = base["genera"] * base["species"] * base["reps"]
     scale_n = None
     if world > 1 and args.scaling == "weak":
-        scale_n = n1 * (world ** 0.5)  # rectangular row bands: (n/world) x n ordered pairs per GPU stays fixed
+        scale_n = n1 * (world ** 0.5)  # pairs per GPU stay fixed
     data = synth.generate(wl["config"], names=False, scale_n=scale_n)
     sym = data["symbols"]
     n, L = sym.shape
@@ -197,64 +230,68 @@ def main():
     W32 = (L + 31) // 32
 
     ctx = t.Context(local)
-    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
     sym_pinned = torch.from_numpy(sym).pin_memory()
     labels = [data[k] for k in ("species_id", "genus_id", "epithet_rank", "fullname_rank")]
     aln = t.Alignment(ctx, sym_pinned.numpy())
     aln.set_labels(*labels)
     aln.set_config(mode, 300, True)
-    # row band of this rank (multiples of 128 rows)
-    if world > 1:
+    L_ = t.load()
+    c64 = ctypes.c_int64()
+    RS = t.ROW_RESULT_DTYPE.itemsize
+
+    # ---- how the pair space is shared between ranks ------------------------------------------
+    #  streaming kinds: every rank takes every world-th tile of the triangle (tdna_best_match_part),
+    #                   then one NCCL exchange of the candidate records / per-row counts, then merge.
+    #  matrix kinds:    row bands (each rank owns rows [b0,b1) x all columns); no collective.
+    if world > 1 and not streaming:
         per = -(-n // world)
         per = -(-per // 128) * 128
         b0, b1 = min(n, rank * per), min(n, (rank + 1) * per)
         aln.set_row_range(b0, b1)
     else:
         b0, b1 = 0, n
-    kind = wl["kind"]
-    dev = torch.device("cuda", local)
+    rows_mine = b1 - b0
 
-    # device-resident outputs for the kernel-timed steps
     n_intra = n_inter = 0
     if "summary" in kind or "intra" in kind:
-        # sizes are a property of the labels only; ask once
-        import ctypes
-        cnt = ctypes.c_int64()
-        t.load().tdna_class_distances(aln.h, t.PD_INTRA, None, 0, ctypes.byref(cnt))
-        n_intra = cnt.value
+        L_.tdna_class_distances(aln.h, t.PD_INTRA, None, 0, ctypes.byref(c64))  # sizes depend on the labels only
+        n_intra = c64.value
         if "summary" in kind:
-            t.load().tdna_class_distances(aln.h, t.PD_INTER, None, 0, ctypes.byref(cnt))
-            n_inter = cnt.value
+            L_.tdna_class_distances(aln.h, t.PD_INTER, None, 0, ctypes.byref(c64))
+            n_inter = c64.value
     d_intra = torch.empty(max(1, n_intra), dtype=torch.float32, device=dev)
     d_inter = torch.empty(max(1, n_inter), dtype=torch.float32, device=dev)
-    RS = t.ROW_RESULT_DTYPE.itemsize
-    per_rows = (-(-(-(-n // world)) // 128) * 128) if world > 1 else n
-    res_all = torch.empty((world * per_rows, RS), dtype=torch.uint8, device=dev) if world > 1 else None
-    mine = torch.zeros((per_rows, RS), dtype=torch.uint8, device=dev) if world > 1 else None
-
-    class _DevBuf:  # zero-copy torch view of library-owned device memory
-        def __init__(self, ptr, nbytes):
-            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    import ctypes
-    c64 = ctypes.c_int64()
-    L_ = t.load()
+    tile_ms = []
+    cand_counts = []
+
+    def best_match_step(a, out_ptr=None):
+        """Per-query Best Match summaries for ALL rows, left on the device (or copied to out_ptr)."""
+        if world == 1:
+            if out_ptr is None:
+                a.best_match_compute()
+            else:
+                a.best_match_into(out_ptr)
+            return
+        part = a.best_match_part(rank, world)
+        cand_counts.append(int(part.n_cand))
+        with torch.cuda.stream(stream):
+            rows, cols, d, inval, flags = exchange_parts(torch, dist, dev, part, n, world)
+            stream.synchronize()
+        t.check(L_.tdna_best_match_merge(a.h, rows.data_ptr(), cols.data_ptr(), d.data_ptr(), rows.numel(), inval.data_ptr(),
+                                         flags.data_ptr(), out_ptr))
 
     def step_device():
-        aln.set_config(mode, 300, True)  # invalidates the cached matrix: every step recomputes everything
+        aln.set_config(mode, 300, True)  # invalidates every cached result: each step recomputes everything
         if kind.startswith("matrix"):
             aln.matrix_compute()
             t.check(L_.tdna_class_distances(aln.h, t.PD_INTRA, d_intra.data_ptr(), n_intra, ctypes.byref(c64)))
             t.check(L_.tdna_class_distances(aln.h, t.PD_INTER, d_inter.data_ptr(), n_inter, ctypes.byref(c64)))
         else:
-            p = aln.best_match_compute()
+            best_match_step(aln)
             if "intra" in kind:
                 t.check(L_.tdna_class_distances(aln.h, t.PD_INTRA, d_intra.data_ptr(), n_intra, ctypes.byref(c64)))
-            if world > 1:
-                # the exchange step: every rank gets every row's summary (one NCCL all_gather over NVLink)
-                lib_res = torch.as_tensor(_DevBuf(p, n * RS), device=dev).view(n, RS)
-                mine[: b1 - b0].copy_(lib_res[b0:b1])
-                dist.all_gather_into_tensor(res_all.view(-1), mine.view(-1))
 
     def barrier():
         if world > 1:
@@ -281,6 +318,8 @@ def main():
         e1.synchronize()
         torch.cuda.synchronize()
         step_ms.append(e0.elapsed_time(e1))
+        if streaming:
+            tile_ms.append(ctx.last_tile_pass_ms())  # the count-tile pass of THIS step (CUDA events on the library's stream)
     barrier()
     t_region = time.perf_counter() - t_region0
     launches = ctx.launch_count() - launches0
@@ -293,10 +332,13 @@ def main():
     ms_per_step = total_ms / args.steps
     value = pairs / (ms_per_step * 1e-3) / 1e9
 
-    # ---- the dominant kernel alone, timed live with CUDA events on the library's stream ----
-    kern_ms = aln.time_matrix_kernel(max(3, min(20, args.steps)))
-    rows_mine = b1 - b0
-    kern_pairs = pairs if world == 1 else rows_mine * n  # symmetric triangle vs rectangular band
+    # ---- the dominant kernel: the count-tile pass, timed live with CUDA events on the library's stream ----
+    if streaming:
+        kern_ms = float(np.mean(tile_ms))
+        kern_pairs = pairs / world  # every world-th tile of the triangle
+    else:
+        kern_ms = aln.time_matrix_kernel(max(3, min(20, args.steps)))
+        kern_pairs = pairs if world == 1 else rows_mine * n  # symmetric triangle vs rectangular band
     popc_alg = kern_pairs * POPC_PER_PAIR_WORD[mode] * W32
     popc_peak, lop3_peak = ctx.measure_int_peaks()
     achieved = popc_alg / (kern_ms * 1e-3)
@@ -305,26 +347,30 @@ def main():
     pj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(pj):
         prof = json.load(open(pj)).get(args.workload, {})
+    P_planes = {0: 6, 1: 5, 2: 4}[mode]
+    plane_bytes = n * P_planes * W32 * 4
     roofline = {
-        "bound": "int-issue (POPC, quarter-rate on the ALU pipe)", "kernel": "count_tile_kernel",
+        "bound": "int-issue: POPC on the XU pipe (16 lanes/clk/SM); neither HBM nor tensor bound -- see DESIGN.md",
+        "kernel": "count_tile_kernel" + ("<EPI_STREAM>" if streaming else "<EPI_MATRIX>"),
         "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": achieved / popc_peak,
-        "peak_source": "measured live by tdna_measure_int_peaks (no POPC figure in MEASURED_PEAKS.json); LOP3 peak %.2f T/s" % (lop3_peak / 1e12),
+        "peak_source": "measured live by tdna_measure_int_peaks: dependent-free POPC stream on all SMs (MEASURED_PEAKS.json has no integer-pipe figure); LOP3 stream %.2f T/s (two LOP3 per result)" % (lop3_peak / 1e12),
         "kernel_ms": kern_ms, "kernel_gpairs_per_s": kern_pairs / (kern_ms * 1e-3) / 1e9,
         "algorithmic_popc32_per_pair": POPC_PER_PAIR_WORD[mode] * W32,
         "traffic": prof.get("dram_bytes_per_launch"),
-        "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_src,
-        "matrix_write_gbs": (rows_mine * n * 8) / (kern_ms * 1e-3) / 1e9,
+        "hbm": {"algorithmic_bytes_per_launch": int(plane_bytes if streaming else plane_bytes + rows_mine * n * 8),
+                "achieved_gbs": (plane_bytes if streaming else plane_bytes + rows_mine * n * 8) / (kern_ms * 1e-3) / 1e9,
+                "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},
     }
 
-    # ---- e2e: the same step through the C ABI with host buffers --------------------------------
+    # ---- e2e: the same step through the C ABI with HOST buffers ---------------------------------
     e2e_steps = max(1, min(args.steps, 5))
     h2d = sym.nbytes + 4 * 4 * n
     if kind.startswith("matrix"):
         out_host = torch.empty((rows_mine, n), dtype=torch.float64).pin_memory()
         d2h = out_host.numel() * 8 + 4 * (n_intra + n_inter)
     else:
-        out_host = torch.empty((n, t.ROW_RESULT_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
-        d2h = rows_mine * t.ROW_RESULT_DTYPE.itemsize + 4 * n_intra
+        out_host = torch.empty((n, RS), dtype=torch.uint8).pin_memory()
+        d2h = n * RS + 4 * n_intra
     h_intra = torch.empty(max(1, n_intra), dtype=torch.float32).pin_memory()
     h_inter = torch.empty(max(1, n_inter), dtype=torch.float32).pin_memory()
 
@@ -332,14 +378,14 @@ def main():
         a2 = t.Alignment(ctx, sym_pinned.numpy())  # H2D of the symbols + pack
         a2.set_labels(*labels)
         a2.set_config(mode, 300, True)
-        if world > 1:
+        if world > 1 and not streaming:
             a2.set_row_range(b0, b1)
         if kind.startswith("matrix"):
             t.check(L_.tdna_matrix(a2.h, out_host.data_ptr(), None))
             t.check(L_.tdna_class_distances(a2.h, t.PD_INTRA, h_intra.data_ptr(), n_intra, ctypes.byref(c64)))
             t.check(L_.tdna_class_distances(a2.h, t.PD_INTER, h_inter.data_ptr(), n_inter, ctypes.byref(c64)))
         else:
-            t.check(L_.tdna_best_match(a2.h, out_host.data_ptr()))
+            best_match_step(a2, out_host.data_ptr())
             if "intra" in kind:
                 t.check(L_.tdna_class_distances(a2.h, t.PD_INTRA, h_intra.data_ptr(), n_intra, ctypes.byref(c64)))
         a2.close()
@@ -368,17 +414,22 @@ def main():
                "single_thread_value": v1 / 1e9}
 
     if rank == 0:
+        if streaming:
+            par = ("every %d-th tile of the triangle per rank, one NCCL exchange of candidate records + per-row counts, merge on every rank" % world) if world > 1 else "single GPU, whole triangle"
+        else:
+            par = "row bands, %d rank(s), rows [%d,%d) on rank 0" % (world, b0, b1)
         line = {
             "metric": "pairwise distances/s", "value": value, "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
             "dtype": "u32 bit-planes -> int32 counts -> f64 distance", "data": "synthetic",
             "config": {"workload": wl["desc"], "n": n, "L": L, "mode": ["uncorrected", "K2P", "trans-only"][mode], "min_overlap": 300,
-                       "pairs": pairs, "step": kind, "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": "row bands, %d rank(s), rows [%d,%d) on rank 0" % (world, b0, b1)},
+                       "pairs": pairs, "step": kind, "l2": "flushed between timed steps (256 MiB write)", "parallelism": par},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "region_wall_s": t_region,
         }
+        if cand_counts:
+            line["config"]["candidates_per_rank_per_step"] = int(np.mean(cand_counts))
         print(json.dumps(line), flush=True)
     aln.close()
     ctx.close()

@@ -1,9 +1,12 @@
-"""Multi-GPU plumbing for the row-band decomposition (one process per GPU, torch.distributed).
+"""Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL over NVLink on GPUs, gloo in the
+CPU tests).  Two decompositions of the pair space:
 
-The pair space is sharded by QUERY ROW: rank r owns the contiguous band row_band(n, r, world) and
-computes those rows against every column, so each per-row result is complete on exactly one rank and
-the only exchange is one all_gather of the fixed-size per-row records (NCCL over NVLink on GPUs;
-gloo in the CPU tests).  Histogram-like outputs (class distances, edges) are concatenated."""
+* streaming Best Match: rank r takes tiles r, r+world, ... of the triangle (tdna_best_match_part);
+  the ranks then exchange their candidate records and per-row counters ONCE (exchange_candidates)
+  and every rank finalises all rows from the union (tdna_best_match_merge).
+* matrix-shaped outputs: rank r owns the contiguous row band row_band(n, r, world) against every
+  column; per-row records are all_gathered (gather_rows), variable-length outputs concatenated
+  (gather_varlen)."""
 import numpy as np
 
 TILE = 128  # row bands start on tile boundaries (include/taxondna_cuda.h: tdna_set_row_range)
@@ -50,3 +53,36 @@ def gather_varlen(local, group=None):
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad, group=group)
     return torch.cat([o[: int(c.item())] for o, c in zip(outs, cnts)])
+
+
+def exchange_candidates(rows, cols, d, inval, flags, group=None):
+    """rows/cols: int32 [k], d: float64 [k] -- this rank's candidate records (k may be 0);
+    inval: int32 [n] invalid-pair counts, flags: int32 [n] TDNA_ROW_* bits seen by this rank.
+    Returns (rows, cols, d, inval, flags) of the union: records concatenated in rank order
+    (all_gather), counts summed, flags ORed (all_reduce)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = inval.device
+    k = int(rows.numel())
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, torch.tensor([k], dtype=torch.int64, device=dev), group=group)
+    inval = inval.clone()
+    dist.all_reduce(inval, op=dist.ReduceOp.SUM, group=group)
+    bits = torch.stack([flags & 1, (flags >> 1) & 1])  # NCCL has no bitwise-or reduction: OR == max per bit
+    dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=group)
+    flags = (bits[0] | (bits[1] << 1)).to(torch.int32).contiguous()
+    cl = [int(x) for x in counts.tolist()]
+    m = max(max(cl), 1)
+    rec = torch.zeros((m, 2), dtype=torch.int64, device=dev)  # one padded 16-byte record per candidate
+    if k:
+        rec[:k, 0] = (rows.to(torch.int64) << 32) | cols.to(torch.int64)
+        rec[:k, 1] = d.contiguous().view(torch.int64)
+    allrec = torch.empty((world, m, 2), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allrec.view(-1), rec.view(-1), group=group)
+    pieces = [allrec[w, : cl[w]] for w in range(world) if cl[w]]
+    cat = torch.cat(pieces) if pieces else torch.zeros((0, 2), dtype=torch.int64, device=dev)
+    urows = (cat[:, 0] >> 32).to(torch.int32).contiguous()
+    ucols = (cat[:, 0] & 0xFFFFFFFF).to(torch.int32).contiguous()
+    ud = cat[:, 1].contiguous().view(torch.float64)
+    return urows, ucols, ud, inval.contiguous(), flags

@@ -30,6 +30,27 @@ def _worker(rank, world, port, n, tmp):
     allp = shard.gather_varlen(piece)
     exp = np.concatenate([np.arange(r * 1000, r * 1000 + 7 * (r + 1), dtype=np.float32) for r in range(world)])
     assert np.array_equal(allp.numpy(), exp)
+    # streaming Best Match exchange: records concatenated in rank order, counts summed, flags ORed
+    rng = np.random.default_rng(100 + rank)
+    k = 0 if rank == 1 and world > 2 else 5 + 3 * rank  # one rank may have nothing to contribute
+    rows = torch.from_numpy(rng.integers(0, n, size=k).astype(np.int32))
+    cols = torch.from_numpy(rng.integers(0, n, size=k).astype(np.int32))
+    d = torch.from_numpy(rng.random(k))
+    inval = torch.from_numpy(rng.integers(0, 4, size=n).astype(np.int32))
+    flags = torch.from_numpy(rng.integers(0, 4, size=n).astype(np.int32))
+    ur, uc, ud, ui, uf = shard.exchange_candidates(rows, cols, d, inval, flags)
+    er, ec, ed, ei, ef = [], [], [], np.zeros(n, np.int64), np.zeros(n, np.int64)
+    for r in range(world):
+        g = np.random.default_rng(100 + r)
+        kk = 0 if r == 1 and world > 2 else 5 + 3 * r
+        er.append(g.integers(0, n, size=kk).astype(np.int32))
+        ec.append(g.integers(0, n, size=kk).astype(np.int32))
+        ed.append(g.random(kk))
+        ei += g.integers(0, 4, size=n)
+        ef |= g.integers(0, 4, size=n)
+    assert np.array_equal(ur.numpy(), np.concatenate(er)) and np.array_equal(uc.numpy(), np.concatenate(ec))
+    assert np.array_equal(ud.numpy().view(np.uint64), np.concatenate(ed).view(np.uint64))
+    assert np.array_equal(ui.numpy(), ei) and np.array_equal(uf.numpy(), ef)
     dist.destroy_process_group()
 
 
@@ -50,4 +71,12 @@ def test_two_rank_gather_reassembles_single_rank_answer(tmp_path):
     full = rng.integers(0, 256, size=(n, 120), dtype=np.uint8)
     np.save(os.path.join(tmp_path, "full.npy"), full)
     port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+
+
+def test_three_rank_exchange_with_an_empty_rank(tmp_path):
+    n, world = 200, 3
+    rng = np.random.default_rng(1)
+    np.save(os.path.join(tmp_path, "full.npy"), rng.integers(0, 256, size=(n, 120), dtype=np.uint8))
+    port = 31500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
