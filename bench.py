@@ -274,7 +274,12 @@ def main():
             else:
                 a.best_match_into(out_ptr)
             return
-        part = a.best_match_part(rank, world)
+        mins = a.best_match_seed(rank, world)  # diagonal blocks -> per-row minima
+        with torch.cuda.stream(stream):
+            mt = torch.as_tensor(_DevBuf(mins, 3 * n, "<i8"), device=dev)
+            dist.all_reduce(mt, op=dist.ReduceOp.MIN)  # thresholds from ALL list neighbours on every rank
+            stream.synchronize()
+        part = a.best_match_part(rank, world, seeded=True)
         cand_counts.append(int(part.n_cand))
         with torch.cuda.stream(stream):
             rows, cols, d, inval, flags = exchange_parts(torch, dist, dev, part, n, world)

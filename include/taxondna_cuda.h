@@ -167,7 +167,15 @@ typedef struct {
     const int32_t *invalid_count; /* device, n: # j != q with getSharedLength < minOverlap seen by this part */
     const int32_t *flags;         /* device, n: TDNA_ROW_* seen by this part */
 } tdna_stream_part;
-int32_t tdna_best_match_part(tdna_aln *aln, int32_t part, int32_t nparts, tdna_stream_part *out);
+/* Optional first half of a part: initialises the per-row state and runs the part's share of the
+ * DIAGONAL tile blocks only, then exposes the per-row minima the candidate thresholds are derived
+ * from -- 3n uint64 (fp64 bit patterns; n conspecific minima, then 2n even/odd-species minima) on
+ * the device.  With several parts the caller all-reduces them with MIN (bit patterns of
+ * non-negative doubles order like integers) so that every part starts the bulk of the triangle with
+ * thresholds from ALL list neighbours, then calls tdna_best_match_part(..., seeded = 1, ...). */
+int32_t tdna_best_match_seed(tdna_aln *aln, int32_t part, int32_t nparts, uint64_t **minima_dev);
+/* seeded = 0: the whole part in one call.  seeded = 1: continue after tdna_best_match_seed. */
+int32_t tdna_best_match_part(tdna_aln *aln, int32_t part, int32_t nparts, int32_t seeded, tdna_stream_part *out);
 /* Inputs are DEVICE pointers (the part's own, or gathered); out: n records, host or device. */
 int32_t tdna_best_match_merge(tdna_aln *aln, const int32_t *cand_row, const int32_t *cand_col, const double *cand_d,
                               int64_t n_cand, const int32_t *invalid_count, const int32_t *flags, tdna_row_result *out);

@@ -53,7 +53,7 @@ EXPORTS = [
     "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_row_distances", "tdna_matrix", "tdna_matrix_compute",
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
-    "tdna_best_match_part", "tdna_best_match_merge", "tdna_set_option", "tdna_last_tile_pass_ms",
+    "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_set_option", "tdna_last_tile_pass_ms",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -98,7 +98,8 @@ def load():
     L.tdna_cancel.argtypes = [vp]
     L.tdna_time_matrix_kernel.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
     L.tdna_measure_int_peaks.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
-    L.tdna_best_match_part.argtypes = [vp, i32, i32, ctypes.POINTER(StreamPart)]
+    L.tdna_best_match_seed.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
+    L.tdna_best_match_part.argtypes = [vp, i32, i32, i32, ctypes.POINTER(StreamPart)]
     L.tdna_best_match_merge.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
     L.tdna_set_option.argtypes = [vp, i32, i64]
     L.tdna_last_tile_pass_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
@@ -226,10 +227,16 @@ class Alignment:
         check(self.L.tdna_best_match_compute(self.h, ctypes.byref(p)))
         return p.value
 
-    def best_match_part(self, part, nparts):
+    def best_match_seed(self, part, nparts):
+        """Diagonal blocks of this part; returns the device address of the 3n uint64 per-row minima."""
+        p = ctypes.c_void_p()
+        check(self.L.tdna_best_match_seed(self.h, int(part), int(nparts), ctypes.byref(p)))
+        return p.value
+
+    def best_match_part(self, part, nparts, seeded=False):
         """Streaming pass over every nparts-th tile of the triangle; returns a StreamPart of DEVICE pointers."""
         sp = StreamPart()
-        check(self.L.tdna_best_match_part(self.h, int(part), int(nparts), ctypes.byref(sp)))
+        check(self.L.tdna_best_match_part(self.h, int(part), int(nparts), 1 if seeded else 0, ctypes.byref(sp)))
         return sp
 
     def best_match_merge(self, cand_row, cand_col, cand_d, n_cand, invalid_count, flags, out=None):

@@ -291,13 +291,14 @@ template <int CN> int stream_prefixes(tdna_aln *a) {
     return TDNA_OK;
 }
 
-template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts) {
+template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts, int phases) {
     using Cfg = TileCfg<KM, CN>;
     tdna_ctx *c = a->ctx;
     TRY(stream_prefixes<CN>(a));
     CU(cudaMemcpyToSymbolAsync(c_sp, &a->sp, sizeof(StreamParams), 0, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaEventRecord(c->ev_k0, c->stream));
+    if (phases & 1) CU(cudaEventRecord(c->ev_k0, c->stream));
     for (int ph = 0; ph < 2; ph++) {
+        if (!(phases & (1 << ph))) continue;
         TileParams p = {};
         p.planes = a->d_planes;
         p.W = a->W;
@@ -317,27 +318,30 @@ template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts)
         p.num_tiles = total > part ? (total - part + nparts - 1) / nparts : 0;
         TRY((launch_kernel<KM, CN, EPI_STREAM>(c, p)));
     }
-    CU(cudaEventRecord(c->ev_k1, c->stream));
-    c->ev_valid = true;
+    if (phases & 2) {
+        CU(cudaEventRecord(c->ev_k1, c->stream));
+        c->ev_valid = true;
+    }
     return TDNA_OK;
 }
 
-template <int KM> int launch_stream_km(tdna_aln *a, int part, int nparts) {
+template <int KM> int launch_stream_km(tdna_aln *a, int part, int nparts, int phases) {
     if constexpr (ModeTraits<KM>::NACC == 2) {
-        return launch_stream_t<KM, 4>(a, part, nparts);
+        return launch_stream_t<KM, 4>(a, part, nparts, phases);
     } else {
         int cn = a->ctx->opt_tile_cn ? a->ctx->opt_tile_cn : 4;
-        if (cn == 4) return launch_stream_t<KM, 4>(a, part, nparts);
-        return launch_stream_t<KM, 8>(a, part, nparts);
+        if (cn == 4) return launch_stream_t<KM, 4>(a, part, nparts, phases);
+        return launch_stream_t<KM, 8>(a, part, nparts, phases);
     }
 }
 
-int launch_stream(tdna_aln *a, int part, int nparts) {
+// phases: bit 0 = diagonal blocks, bit 1 = the rest of the triangle
+int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
     switch (a->kmode) {
-        case KM_P_AMBIG: return launch_stream_km<KM_P_AMBIG>(a, part, nparts);
-        case KM_P_NOAMBIG: return launch_stream_km<KM_P_NOAMBIG>(a, part, nparts);
-        case KM_K2P: return launch_stream_km<KM_K2P>(a, part, nparts);
-        default: return launch_stream_km<KM_TRANS>(a, part, nparts);
+        case KM_P_AMBIG: return launch_stream_km<KM_P_AMBIG>(a, part, nparts, phases);
+        case KM_P_NOAMBIG: return launch_stream_km<KM_P_NOAMBIG>(a, part, nparts, phases);
+        case KM_K2P: return launch_stream_km<KM_K2P>(a, part, nparts, phases);
+        default: return launch_stream_km<KM_TRANS>(a, part, nparts, phases);
     }
 }
 
@@ -539,7 +543,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     cudaSetDevice(c->device);
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
-                    a->d_needc, a->sp.thr, a->sp.mC, a->sp.mPar, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
+                    a->d_needc, a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_cursor, a->d_lj, a->d_ld};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
@@ -741,8 +745,8 @@ static int ensure_stream_state(tdna_aln *a) {
     if (cap * 16 > c->budget / 2) cap = c->budget / 32;
     StreamParams &sp = a->sp;
     CU(DMALLOC(&sp.thr, n * 4));
-    CU(DMALLOC(&sp.mC, n * 8));
-    CU(DMALLOC(&sp.mPar, n * 16));
+    CU(DMALLOC(&sp.mC, n * 24));  // mC[n] followed by mPar[2n]: one buffer, so that parts can all-reduce(min) it in one go
+    sp.mPar = sp.mC + n;
     CU(DMALLOC(&sp.inval, n * 4));
     CU(DMALLOC(&sp.flags, n * 4));
     CU(DMALLOC(&sp.cnt, n * 4));
@@ -760,8 +764,8 @@ static int ensure_stream_state(tdna_aln *a) {
     return TDNA_OK;
 }
 
-// rc TDNA_E_TOO_LARGE: the candidate buffer overflowed (thresholds never tightened: e.g. one species only)
-static int stream_part(tdna_aln *a, int part, int nparts, long long *ncand_out) {
+// seed: state init + the diagonal blocks of this part (thresholds from list neighbours)
+static int stream_seed(tdna_aln *a, int part, int nparts) {
     tdna_ctx *c = a->ctx;
     TRY(ensure_packed(a));
     TRY(ensure_stream_state(a));
@@ -769,7 +773,18 @@ static int stream_part(tdna_aln *a, int part, int nparts, long long *ncand_out) 
     stream_init_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n, a->d_needc);
     c->launches++;
     CU(cudaGetLastError());
-    TRY(launch_stream(a, part, nparts));
+    return launch_stream(a, part, nparts, 1);
+}
+
+// bulk: thresholds from the minima (all-reduced by the caller when there are several parts), then the
+// rest of the triangle.  rc TDNA_E_TOO_LARGE: the candidate buffer overflowed (thresholds never
+// tightened: e.g. one species only, or a list order in which neighbours are unrelated)
+static int stream_bulk(tdna_aln *a, int part, int nparts, long long *ncand_out) {
+    tdna_ctx *c = a->ctx;
+    stream_thr_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n);
+    c->launches++;
+    CU(cudaGetLastError());
+    TRY(launch_stream(a, part, nparts, 2));
     struct { unsigned long long ncand; int overflow; int pad; } h;
     CU(cudaMemcpyAsync(&h, a->d_stream_u64, 16, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -777,6 +792,11 @@ static int stream_part(tdna_aln *a, int part, int nparts, long long *ncand_out) 
     a->last_ncand = (long long)h.ncand;
     if (ncand_out) *ncand_out = (long long)h.ncand;
     return TDNA_OK;
+}
+
+static int stream_part(tdna_aln *a, int part, int nparts, long long *ncand_out) {
+    TRY(stream_seed(a, part, nparts));
+    return stream_bulk(a, part, nparts, ncand_out);
 }
 
 // candidate records (device) -> per-row lists -> exact summaries into a->d_res
@@ -819,12 +839,24 @@ static int stream_merge(tdna_aln *a, const int32_t *cq, const int32_t *cj, const
     return fill_shared(a, 0, a->n);
 }
 
-int32_t tdna_best_match_part(tdna_aln *a, int32_t part, int32_t nparts, tdna_stream_part *out) {
+int32_t tdna_best_match_seed(tdna_aln *a, int32_t part, int32_t nparts, uint64_t **minima_dev) {
+    if (!a || nparts < 1 || part < 0 || part >= nparts) return fail(TDNA_E_ARG, "bad argument");
+    CU(cudaSetDevice(a->ctx->device));
+    TRY(need_labels(a));
+    TRY(stream_seed(a, part, nparts));
+    CU(cudaStreamSynchronize(a->ctx->stream));
+    if (minima_dev) *minima_dev = reinterpret_cast<uint64_t *>(a->sp.mC);
+    return TDNA_OK;
+}
+
+int32_t tdna_best_match_part(tdna_aln *a, int32_t part, int32_t nparts, int32_t seeded, tdna_stream_part *out) {
     if (!a || !out || nparts < 1 || part < 0 || part >= nparts) return fail(TDNA_E_ARG, "bad argument");
     CU(cudaSetDevice(a->ctx->device));
     TRY(need_labels(a));
+    if (seeded && !a->stream_alloc) return fail(TDNA_E_STATE, "tdna_best_match_seed has not run");
     long long ncand = 0;
-    TRY(stream_part(a, part, nparts, &ncand));
+    if (seeded) TRY(stream_bulk(a, part, nparts, &ncand));
+    else TRY(stream_part(a, part, nparts, &ncand));
     out->cand_row = a->sp.cq;
     out->cand_col = a->sp.cj;
     out->cand_d = a->sp.cd;

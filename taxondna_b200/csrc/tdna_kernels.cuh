@@ -825,6 +825,19 @@ __global__ void __launch_bounds__(256) stream_init_kernel(StreamParams sp, int64
     sp.cnt[q] = 0;
 }
 
+// thresholds from the (possibly all-reduced) minima: between the diagonal phase and the bulk phase
+__global__ void __launch_bounds__(256) stream_thr_kernel(StreamParams sp, int64_t n) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const unsigned long long m = max(sp.mC[q], max(sp.mPar[2 * q], sp.mPar[2 * q + 1]));
+    uint32_t tf = TDNA_THR_ALL;
+    if (m < TDNA_INF_BITS) {
+        const double T = __longlong_as_double((long long)m) + 2e-5;
+        if (T < 1.0) tf = (uint32_t)(T * 65536.0) + 2u;
+    }
+    sp.thr[q] = min(sp.thr[q], tf);
+}
+
 // exclusive prefix sum of cnt[0..n) into ptr[0..n] (one CTA; n <= a few million)
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int *__restrict__ cnt, int64_t n, long long *__restrict__ ptr) {
     __shared__ long long s_part[1024];

@@ -119,8 +119,16 @@ def test_stream_parts_merge_to_the_single_part_answer(ctx):
                 self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
 
         rows, cols, ds, inval, flags = [], [], [], None, None
+        # diagonal phase of every part first: the per-row minima are MIN-reduced across the parts
+        allmin = None
         for part in range(3):
-            p = aln.best_match_part(part, 3)
+            m = torch.as_tensor(Dev(aln.best_match_seed(part, 3), (3 * n,), "<i8"), device="cuda").clone()
+            allmin = m if allmin is None else torch.minimum(allmin, m)
+        for part in range(3):
+            mp = aln.best_match_seed(part, 3)  # this part's own state again (one device plays all three ranks)
+            torch.as_tensor(Dev(mp, (3 * n,), "<i8"), device="cuda").copy_(allmin)
+            torch.cuda.synchronize()
+            p = aln.best_match_part(part, 3, seeded=True)
             torch.cuda.synchronize()
             k = int(p.n_cand)
             if k:
@@ -131,6 +139,9 @@ def test_stream_parts_merge_to_the_single_part_answer(ctx):
             fl = torch.as_tensor(Dev(p.flags, (n,), "<i4"), device="cuda").clone()
             inval = iv if inval is None else inval + iv
             flags = fl if flags is None else flags | fl
+        # and the unseeded single-call form of a part must agree as well
+        p0 = aln.best_match_part(0, 1)
+        assert int(p0.n_cand) > 0
         r, c_, d_ = torch.cat(rows), torch.cat(cols), torch.cat(ds)
         merged = aln.best_match_merge(r.data_ptr(), c_.data_ptr(), d_.data_ptr(), r.numel(), inval.data_ptr(), flags.data_ptr())
         assert first_difference(merged, whole) is None, (mode, first_difference(merged, whole))
