@@ -293,6 +293,12 @@ def main():
             aln.matrix_compute()
             t.check(L_.tdna_class_distances(aln.h, t.PD_INTRA, d_intra.data_ptr(), n_intra, ctypes.byref(c64)))
             t.check(L_.tdna_class_distances(aln.h, t.PD_INTER, d_inter.data_ptr(), n_inter, ctypes.byref(c64)))
+        elif "intra" in kind and world == 1:
+            # Best Close Match + the intraspecific distances for the percentile from ONE streaming pass
+            io = t.Analysis()
+            io.want = t.WANT_BEST_MATCH | t.WANT_INTRA
+            io.intra, io.intra_cap = d_intra.data_ptr(), n_intra
+            t.check(L_.tdna_analyze(aln.h, ctypes.byref(io)))
         else:
             best_match_step(aln)
             if "intra" in kind:
@@ -389,6 +395,12 @@ def main():
             t.check(L_.tdna_matrix(a2.h, out_host.data_ptr(), None))
             t.check(L_.tdna_class_distances(a2.h, t.PD_INTRA, h_intra.data_ptr(), n_intra, ctypes.byref(c64)))
             t.check(L_.tdna_class_distances(a2.h, t.PD_INTER, h_inter.data_ptr(), n_inter, ctypes.byref(c64)))
+        elif "intra" in kind and world == 1:
+            io = t.Analysis()
+            io.want = t.WANT_BEST_MATCH | t.WANT_INTRA
+            io.rows = out_host.data_ptr()
+            io.intra, io.intra_cap = h_intra.data_ptr(), n_intra
+            t.check(L_.tdna_analyze(a2.h, ctypes.byref(io)))
         else:
             best_match_step(a2, out_host.data_ptr())
             if "intra" in kind:

@@ -180,6 +180,31 @@ int32_t tdna_best_match_part(tdna_aln *aln, int32_t part, int32_t nparts, int32_
 int32_t tdna_best_match_merge(tdna_aln *aln, const int32_t *cand_row, const int32_t *cand_col, const double *cand_d,
                               int64_t n_cand, const int32_t *invalid_count, const int32_t *flags, tdna_row_result *out);
 
+/* ---- one pass, several analyses ------------------------------------------------------------------ */
+/* SpeciesIdentifier runs Pairwise Summary, the threshold percentile, Best (Close) Match and Cluster on the
+ * SAME list one after the other (PairwiseSummary.java:131-151 -> BestMatch.java:107-120 "Compute from
+ * Pairwise Summary" -> BestMatch.run); each of them is O(N^2) getPairwise calls in the reference.  This
+ * entry point produces any subset of their inputs from ONE streaming pass over the triangle. */
+enum { TDNA_WANT_BEST_MATCH = 1, /* tdna_row_result per row (as tdna_best_match) */
+       TDNA_WANT_INTRA = 2,      /* PairwiseDistribution PD_INTRA distances (as tdna_class_distances) */
+       TDNA_WANT_INTER = 4,      /* PairwiseDistribution PD_INTER distances */
+       TDNA_WANT_EDGES = 8       /* pairs with 0 <= d <= edge_threshold (as tdna_edges_below) */ };
+typedef struct {
+    int32_t want;            /* in: TDNA_WANT_* bits */
+    int32_t reserved;
+    tdna_row_result *rows;   /* in: n records, host or device; NULL leaves them on the device (tdna_best_match_compute) */
+    float *intra;            /* in: capacity intra_cap (host or device); NULL = count only */
+    int64_t intra_cap;
+    float *inter;
+    int64_t inter_cap;
+    double edge_threshold;
+    int32_t *edge_i, *edge_j; /* in: capacity edge_cap; NULL = count only */
+    double *edge_d;
+    int64_t edge_cap;
+    int64_t n_intra, n_inter, n_edges; /* out: totals (may exceed the capacities: only the first cap are stored) */
+} tdna_analysis;
+int32_t tdna_analyze(tdna_aln *aln, tdna_analysis *io);
+
 /* ---- options ------------------------------------------------------------------------------------ */
 enum { TDNA_OPT_BEST_MATCH_PATH = 1, /* TDNA_PATH_*: how tdna_best_match computes a whole-range request */
        TDNA_OPT_TILE_COLUMNS = 2     /* 0 = automatic, 64 or 128: column width of a count tile */ };

@@ -26,6 +26,18 @@ class Counts(ctypes.Structure):
     _fields_ = [("shared", ctypes.c_int32), ("c1", ctypes.c_int32), ("c2", ctypes.c_int32), ("c3", ctypes.c_int32)]
 
 
+WANT_BEST_MATCH, WANT_INTRA, WANT_INTER, WANT_EDGES = 1, 2, 4, 8
+
+
+class Analysis(ctypes.Structure):
+    """tdna_analysis: request / result of one streaming pass (tdna_analyze)."""
+    _fields_ = [("want", ctypes.c_int32), ("reserved", ctypes.c_int32), ("rows", ctypes.c_void_p),
+                ("intra", ctypes.c_void_p), ("intra_cap", ctypes.c_int64), ("inter", ctypes.c_void_p), ("inter_cap", ctypes.c_int64),
+                ("edge_threshold", ctypes.c_double), ("edge_i", ctypes.c_void_p), ("edge_j", ctypes.c_void_p),
+                ("edge_d", ctypes.c_void_p), ("edge_cap", ctypes.c_int64),
+                ("n_intra", ctypes.c_int64), ("n_inter", ctypes.c_int64), ("n_edges", ctypes.c_int64)]
+
+
 class StreamPart(ctypes.Structure):
     """tdna_stream_part: device pointers to one part's streaming Best-Match output."""
     _fields_ = [("cand_row", ctypes.c_void_p), ("cand_col", ctypes.c_void_p), ("cand_d", ctypes.c_void_p),
@@ -53,7 +65,7 @@ EXPORTS = [
     "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_row_distances", "tdna_matrix", "tdna_matrix_compute",
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
-    "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_set_option", "tdna_last_tile_pass_ms",
+    "tdna_analyze", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_set_option", "tdna_last_tile_pass_ms",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -98,6 +110,7 @@ def load():
     L.tdna_cancel.argtypes = [vp]
     L.tdna_time_matrix_kernel.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
     L.tdna_measure_int_peaks.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
+    L.tdna_analyze.argtypes = [vp, ctypes.POINTER(Analysis)]
     L.tdna_best_match_seed.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
     L.tdna_best_match_part.argtypes = [vp, i32, i32, i32, ctypes.POINTER(StreamPart)]
     L.tdna_best_match_merge.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
@@ -226,6 +239,43 @@ class Alignment:
         p = ctypes.c_void_p()
         check(self.L.tdna_best_match_compute(self.h, ctypes.byref(p)))
         return p.value
+
+    def analyze(self, best_match=False, intra=False, inter=False, edges=None):
+        """One pass, several analyses (tdna_analyze).  Two calls when class distances / edges are wanted:
+        the first sizes the outputs.  Returns a dict of numpy arrays."""
+        want = (WANT_BEST_MATCH if best_match else 0) | (WANT_INTRA if intra else 0) | (WANT_INTER if inter else 0) | \
+               (WANT_EDGES if edges is not None else 0)
+        io = Analysis()
+        io.want = want
+        io.edge_threshold = float(edges) if edges is not None else 0.0
+        out = {}
+        if want & ~WANT_BEST_MATCH:  # size the variable-length outputs
+            io.want = want & ~WANT_BEST_MATCH
+            check(self.L.tdna_analyze(self.h, ctypes.byref(io)))
+            io.want = want
+        if best_match:
+            out["rows"] = np.zeros(self.n, dtype=ROW_RESULT_DTYPE)
+            io.rows = out["rows"].ctypes.data
+        if intra:
+            out["intra"] = np.empty(max(1, io.n_intra), dtype=np.float32)
+            io.intra, io.intra_cap = out["intra"].ctypes.data, io.n_intra
+        if inter:
+            out["inter"] = np.empty(max(1, io.n_inter), dtype=np.float32)
+            io.inter, io.inter_cap = out["inter"].ctypes.data, io.n_inter
+        if edges is not None:
+            k = max(1, io.n_edges)
+            out["edge_i"], out["edge_j"], out["edge_d"] = np.empty(k, np.int32), np.empty(k, np.int32), np.empty(k, np.float64)
+            io.edge_i, io.edge_j, io.edge_d, io.edge_cap = out["edge_i"].ctypes.data, out["edge_j"].ctypes.data, out["edge_d"].ctypes.data, io.n_edges
+        ni, nn, ne = io.n_intra, io.n_inter, io.n_edges
+        check(self.L.tdna_analyze(self.h, ctypes.byref(io)))
+        assert (not intra or io.n_intra == ni) and (not inter or io.n_inter == nn) and (edges is None or io.n_edges == ne)
+        if intra:
+            out["intra"] = out["intra"][:ni]
+        if inter:
+            out["inter"] = out["inter"][:nn]
+        if edges is not None:
+            out["edge_i"], out["edge_j"], out["edge_d"] = out["edge_i"][:ne], out["edge_j"][:ne], out["edge_d"][:ne]
+        return out
 
     def best_match_seed(self, part, nparts):
         """Diagonal blocks of this part; returns the device address of the 3n uint64 per-row minima."""

@@ -83,6 +83,7 @@ struct tdna_aln {
     size_t scratch_cap = 0;
     // streaming Best Match (tdna_kernels.cuh "stream epilogue")
     uint8_t *d_needc = nullptr;
+    int4 *d_panel_range = nullptr;
     StreamParams sp = {};
     bool stream_alloc = false;
     void *d_stream_u64 = nullptr;  // ncand + overflow
@@ -94,7 +95,7 @@ struct tdna_aln {
     int32_t *d_lj = nullptr;
     double *d_ld = nullptr;
     long long list_cap = 0;
-    long long last_ncand = 0;
+    long long last_ncand = 0, last_ncls[2] = {0, 0}, last_nedge = 0;
 };
 
 namespace {
@@ -543,7 +544,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     cudaSetDevice(c->device);
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
-                    a->d_needc, a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
+                    a->d_needc, a->d_panel_range, a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_cursor, a->d_lj, a->d_ld};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
@@ -575,6 +576,22 @@ int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const 
     for (int64_t i = 0; i < a->n; i++) need[i] = (hs[i] >= 0 && members[hs[i]] > 1) ? 1 : 0;
     if (!a->d_needc) CU(DMALLOC(&a->d_needc, (size_t)a->n));
     CU(cudaMemcpyAsync(a->d_needc, need.data(), (size_t)a->n, cudaMemcpyHostToDevice, c->stream));
+    // per 64-row panel: range of named species ids and of genus ids (tile-level test for class pairs)
+    std::vector<int32_t> hg((size_t)a->n);
+    CU(cudaMemcpy(hg.data(), a->d_genus, bytes, cudaMemcpyDeviceToHost));
+    size_t panels = (size_t)(a->npad / PR);
+    std::vector<int4> pr(panels);
+    for (size_t pnl = 0; pnl < panels; pnl++) {
+        int4 r = make_int4(0x7fffffff, -1, 0x7fffffff, (int)0x80000000);
+        for (int64_t i = (int64_t)pnl * PR; i < (int64_t)(pnl + 1) * PR && i < a->n; i++) {
+            if (hs[i] >= 0) { r.x = hs[i] < r.x ? hs[i] : r.x; r.y = hs[i] > r.y ? hs[i] : r.y; }
+            r.z = hg[i] < r.z ? hg[i] : r.z;
+            r.w = hg[i] > r.w ? hg[i] : r.w;
+        }
+        pr[pnl] = r;
+    }
+    if (!a->d_panel_range) CU(DMALLOC(&a->d_panel_range, panels * sizeof(int4)));
+    CU(cudaMemcpyAsync(a->d_panel_range, pr.data(), panels * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     a->has_labels = true;
     return TDNA_OK;
@@ -753,9 +770,12 @@ static int ensure_stream_state(tdna_aln *a) {
     CU(DMALLOC(&sp.cq, (size_t)cap * 4));
     CU(DMALLOC(&sp.cj, (size_t)cap * 4));
     CU(DMALLOC(&sp.cd, (size_t)cap * 8));
-    CU(DMALLOC(&a->d_stream_u64, 16));
+    CU(DMALLOC(&a->d_stream_u64, 64));  // ncand, overflow, ncls[2], nedge
     sp.ncand = reinterpret_cast<unsigned long long *>(a->d_stream_u64);
     sp.overflow = reinterpret_cast<int *>(reinterpret_cast<char *>(a->d_stream_u64) + 8);
+    sp.ncls = sp.ncand + 2;
+    sp.nedge = sp.ncand + 4;
+    sp.want = TDNA_WANT_BEST_MATCH;
     sp.cap = cap;
     sp.species = a->d_species;
     CU(DMALLOC(&a->d_ptr, (n + 1) * 8));
@@ -770,6 +790,10 @@ static int stream_seed(tdna_aln *a, int part, int nparts) {
     TRY(ensure_packed(a));
     TRY(ensure_stream_state(a));
     a->sp.species = a->d_species;
+    a->sp.genus = a->d_genus;
+    a->sp.epi = a->d_epi;
+    a->sp.full = a->d_full;
+    a->sp.panel_range = a->d_panel_range;
     stream_init_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n, a->d_needc);
     c->launches++;
     CU(cudaGetLastError());
@@ -785,11 +809,14 @@ static int stream_bulk(tdna_aln *a, int part, int nparts, long long *ncand_out) 
     c->launches++;
     CU(cudaGetLastError());
     TRY(launch_stream(a, part, nparts, 2));
-    struct { unsigned long long ncand; int overflow; int pad; } h;
-    CU(cudaMemcpyAsync(&h, a->d_stream_u64, 16, cudaMemcpyDeviceToHost, c->stream));
+    struct { unsigned long long ncand; int overflow; int pad; unsigned long long ncls[2]; unsigned long long nedge; } h;
+    CU(cudaMemcpyAsync(&h, a->d_stream_u64, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (h.overflow) return fail(TDNA_E_TOO_LARGE, "streaming Best Match: candidate buffer overflow");
     a->last_ncand = (long long)h.ncand;
+    a->last_ncls[0] = (long long)h.ncls[0];
+    a->last_ncls[1] = (long long)h.ncls[1];
+    a->last_nedge = (long long)h.nedge;
     if (ncand_out) *ncand_out = (long long)h.ncand;
     return TDNA_OK;
 }
@@ -880,25 +907,166 @@ int32_t tdna_best_match_merge(tdna_aln *a, const int32_t *cand_row, const int32_
     return TDNA_OK;
 }
 
-int32_t tdna_best_match_compute(tdna_aln *a, const tdna_row_result **out_dev) {
-    if (!a) return fail(TDNA_E_ARG, "null alignment");
+static int class_distances_dense(tdna_aln *a, int32_t klass, float *out, int64_t cap, int64_t *n_out);
+static int edges_dense(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out);
+
+// One streaming pass for any subset of {Best Match, intra, inter, edges}.  TDNA_E_TOO_LARGE: candidate overflow.
+static int analyze_stream(tdna_aln *a, tdna_analysis *io) {
     tdna_ctx *c = a->ctx;
-    CU(cudaSetDevice(c->device));
-    TRY(need_labels(a));
-    if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
-    bool whole = a->row_begin == 0 && a->row_end == a->n;
-    bool done = false;
-    if (whole && c->opt_best_match_path != TDNA_PATH_DENSE) {
-        long long ncand = 0;
-        int rc = stream_part(a, 0, 1, &ncand);
-        if (rc == TDNA_OK) {
-            TRY(stream_merge(a, a->sp.cq, a->sp.cj, a->sp.cd, ncand, a->sp.inval, a->sp.flags, true));
-            done = true;
-        } else if (rc != TDNA_E_TOO_LARGE || c->opt_best_match_path == TDNA_PATH_STREAM) {
-            return rc;
+    TRY(ensure_packed(a));
+    TRY(ensure_stream_state(a));
+    StreamParams &sp = a->sp;
+    sp.want = io->want;
+    float *dcls[2] = {nullptr, nullptr};
+    float *hcls[2] = {io->intra, io->inter};
+    int64_t ccap[2] = {io->intra_cap, io->inter_cap};
+    bool own_cls[2] = {false, false};
+    int32_t *dei = nullptr, *dej = nullptr;
+    double *ded = nullptr;
+    bool own_edges = false;
+    int rc = TDNA_OK;
+    auto cleanup = [&]() {
+        for (int k = 0; k < 2; k++)
+            if (own_cls[k] && dcls[k]) DFREE(dcls[k]);
+        if (own_edges) { if (dei) DFREE(dei); if (dej) DFREE(dej); if (ded) DFREE(ded); }
+        sp.want = TDNA_WANT_BEST_MATCH;
+        sp.cls[0] = sp.cls[1] = nullptr;
+        sp.ei = sp.ej = nullptr;
+        sp.ed = nullptr;
+    };
+    for (int k = 0; k < 2; k++) {
+        sp.cls[k] = nullptr;
+        sp.cls_cap[k] = 0;
+        if (!(io->want & (k == 0 ? TDNA_WANT_INTRA : TDNA_WANT_INTER)) || !hcls[k] || ccap[k] <= 0) continue;
+        if (is_device_ptr(hcls[k])) dcls[k] = hcls[k];
+        else {
+            cudaError_t e = DMALLOC(&dcls[k], (size_t)ccap[k] * 4);
+            if (e != cudaSuccess) { cleanup(); return fail(TDNA_E_CUDA, cudaGetErrorString(e)); }
+            own_cls[k] = true;
+        }
+        sp.cls[k] = dcls[k];
+        sp.cls_cap[k] = ccap[k];
+    }
+    sp.ei = sp.ej = nullptr;
+    sp.ed = nullptr;
+    sp.edge_cap = 0;
+    sp.edge_t = io->edge_threshold;
+    sp.edge_tfix = 0;
+    if (io->want & TDNA_WANT_EDGES) {
+        double t = io->edge_threshold;
+        sp.edge_tfix = !(t >= 0) ? 0u : (t >= 1.0 ? TDNA_THR_ALL : (uint32_t)(t * 65536.0) + 2u);
+        if (io->edge_i && io->edge_j && io->edge_d && io->edge_cap > 0) {
+            if (is_device_ptr(io->edge_i) && is_device_ptr(io->edge_j) && is_device_ptr(io->edge_d)) {
+                dei = io->edge_i; dej = io->edge_j; ded = io->edge_d;
+            } else {
+                own_edges = true;
+                cudaError_t e = DMALLOC(&dei, (size_t)io->edge_cap * 4);
+                if (e == cudaSuccess) e = DMALLOC(&dej, (size_t)io->edge_cap * 4);
+                if (e == cudaSuccess) e = DMALLOC(&ded, (size_t)io->edge_cap * 8);
+                if (e != cudaSuccess) { cleanup(); return fail(TDNA_E_CUDA, cudaGetErrorString(e)); }
+            }
+            sp.ei = dei; sp.ej = dej; sp.ed = ded;
+            sp.edge_cap = io->edge_cap;
         }
     }
-    if (!done) TRY(best_match_dense(a));
+    long long ncand = 0;
+    rc = stream_part(a, 0, 1, &ncand);
+    if (rc == TDNA_OK && (io->want & TDNA_WANT_BEST_MATCH)) {
+        if (!a->d_res) {
+            cudaError_t e = DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result));
+            if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
+        }
+        if (rc == TDNA_OK) rc = stream_merge(a, sp.cq, sp.cj, sp.cd, ncand, sp.inval, sp.flags, true);
+        if (rc == TDNA_OK && io->rows) {
+            cudaError_t e = cudaMemcpyAsync(io->rows, a->d_res, (size_t)a->n * sizeof(tdna_row_result), cudaMemcpyDefault, c->stream);
+            if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
+        }
+    }
+    if (rc == TDNA_OK) {
+        io->n_intra = (io->want & TDNA_WANT_INTRA) ? a->last_ncls[0] : 0;
+        io->n_inter = (io->want & TDNA_WANT_INTER) ? a->last_ncls[1] : 0;
+        io->n_edges = (io->want & TDNA_WANT_EDGES) ? a->last_nedge : 0;
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < 2 && e == cudaSuccess; k++)
+            if (own_cls[k]) {
+                int64_t m = a->last_ncls[k] < ccap[k] ? a->last_ncls[k] : ccap[k];
+                if (m > 0) e = cudaMemcpyAsync(hcls[k], dcls[k], (size_t)m * 4, cudaMemcpyDefault, c->stream);
+            }
+        if (e == cudaSuccess && own_edges) {
+            int64_t m = a->last_nedge < io->edge_cap ? a->last_nedge : io->edge_cap;
+            if (m > 0) {
+                e = cudaMemcpyAsync(io->edge_i, dei, (size_t)m * 4, cudaMemcpyDefault, c->stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(io->edge_j, dej, (size_t)m * 4, cudaMemcpyDefault, c->stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(io->edge_d, ded, (size_t)m * 8, cudaMemcpyDefault, c->stream);
+            }
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
+    }
+    cleanup();
+    return rc;
+}
+
+static int analyze_dense(tdna_aln *a, tdna_analysis *io) {
+    tdna_ctx *c = a->ctx;
+    if (io->want & TDNA_WANT_BEST_MATCH) {
+        if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+        TRY(best_match_dense(a));
+        int64_t rows = a->row_end - a->row_begin;
+        if (io->rows && rows > 0)
+            CU(cudaMemcpyAsync(io->rows + a->row_begin, a->d_res + a->row_begin, (size_t)rows * sizeof(tdna_row_result), cudaMemcpyDefault, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    io->n_intra = io->n_inter = io->n_edges = 0;
+    if (io->want & TDNA_WANT_INTRA) TRY(class_distances_dense(a, TDNA_PD_INTRA, io->intra, io->intra_cap, &io->n_intra));
+    if (io->want & TDNA_WANT_INTER) TRY(class_distances_dense(a, TDNA_PD_INTER, io->inter, io->inter_cap, &io->n_inter));
+    if (io->want & TDNA_WANT_EDGES) TRY(edges_dense(a, io->edge_threshold, io->edge_i, io->edge_j, io->edge_d, io->edge_cap, &io->n_edges));
+    return TDNA_OK;
+}
+
+int32_t tdna_analyze(tdna_aln *a, tdna_analysis *io) {
+    if (!a || !io) return fail(TDNA_E_ARG, "null argument");
+    if (io->want == 0 || (io->want & ~(TDNA_WANT_BEST_MATCH | TDNA_WANT_INTRA | TDNA_WANT_INTER | TDNA_WANT_EDGES)))
+        return fail(TDNA_E_ARG, "bad want mask");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    if (io->want & (TDNA_WANT_BEST_MATCH | TDNA_WANT_INTRA | TDNA_WANT_INTER)) TRY(need_labels(a));
+    bool whole = a->row_begin == 0 && a->row_end == a->n;
+    if (whole && c->opt_best_match_path != TDNA_PATH_DENSE && a->has_labels) {
+        int rc = analyze_stream(a, io);
+        if (rc != TDNA_E_TOO_LARGE || c->opt_best_match_path == TDNA_PATH_STREAM) return rc;
+    }
+    return analyze_dense(a, io);
+}
+
+int32_t tdna_class_distances(tdna_aln *a, int32_t klass, float *out, int64_t cap, int64_t *n_out) {
+    if (!a || !n_out) return fail(TDNA_E_ARG, "null argument");
+    if (klass != TDNA_PD_INTRA && klass != TDNA_PD_INTER) return fail(TDNA_E_ARG, "bad class");
+    tdna_analysis io = {};
+    io.want = klass == TDNA_PD_INTRA ? TDNA_WANT_INTRA : TDNA_WANT_INTER;
+    if (klass == TDNA_PD_INTRA) { io.intra = out; io.intra_cap = cap; } else { io.inter = out; io.inter_cap = cap; }
+    TRY(tdna_analyze(a, &io));
+    *n_out = klass == TDNA_PD_INTRA ? io.n_intra : io.n_inter;
+    return TDNA_OK;
+}
+
+int32_t tdna_edges_below(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out) {
+    if (!a || !n_out) return fail(TDNA_E_ARG, "null argument");
+    if (!a->has_labels) return edges_dense(a, t, ii, jj, d, cap, n_out);  // the streaming state needs the labels
+    tdna_analysis io = {};
+    io.want = TDNA_WANT_EDGES;
+    io.edge_threshold = t;
+    io.edge_i = ii; io.edge_j = jj; io.edge_d = d; io.edge_cap = cap;
+    TRY(tdna_analyze(a, &io));
+    *n_out = io.n_edges;
+    return TDNA_OK;
+}
+
+int32_t tdna_best_match_compute(tdna_aln *a, const tdna_row_result **out_dev) {
+    if (!a) return fail(TDNA_E_ARG, "null alignment");
+    tdna_analysis io = {};
+    io.want = TDNA_WANT_BEST_MATCH;
+    TRY(tdna_analyze(a, &io));
     if (out_dev) *out_dev = a->d_res;
     return TDNA_OK;
 }
@@ -914,7 +1082,7 @@ int32_t tdna_best_match(tdna_aln *a, tdna_row_result *out) {
     return TDNA_OK;
 }
 
-int32_t tdna_class_distances(tdna_aln *a, int32_t klass, float *out, int64_t cap, int64_t *n_out) {
+static int class_distances_dense(tdna_aln *a, int32_t klass, float *out, int64_t cap, int64_t *n_out) {
     if (!a || !n_out) return fail(TDNA_E_ARG, "null argument");
     if (klass != TDNA_PD_INTRA && klass != TDNA_PD_INTER) return fail(TDNA_E_ARG, "bad class");
     tdna_ctx *c = a->ctx;
@@ -956,7 +1124,7 @@ int32_t tdna_class_distances(tdna_aln *a, int32_t klass, float *out, int64_t cap
     return rc;
 }
 
-int32_t tdna_edges_below(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out) {
+static int edges_dense(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out) {
     if (!a || !n_out) return fail(TDNA_E_ARG, "null argument");
     tdna_ctx *c = a->ctx;
     CU(cudaSetDevice(c->device));

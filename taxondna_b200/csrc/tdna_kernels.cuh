@@ -131,6 +131,19 @@ struct StreamParams {
     long long cap;               // capacity of cq/cj/cd
     int *overflow;               // set when a record did not fit
     const int32_t *species;
+    // what this pass produces (TDNA_WANT_*): Best-Match candidates, PairwiseDistribution classes, Cluster edges
+    int want;
+    const int32_t *genus, *epi, *full;
+    const int4 *panel_range;     // per 64-row panel: (min, max) named species id, (min, max) genus id
+    float *cls[2];               // TDNA_PD_INTRA / TDNA_PD_INTER distances as (float)d, unordered (may be null: count only)
+    long long cls_cap[2];
+    unsigned long long *ncls;    // [2] pushes so far
+    uint32_t edge_tfix;          // 16.16 fixed point of the edge threshold, rounded up
+    double edge_t;
+    int32_t *ei, *ej;            // edge records (may be null: count only)
+    double *ed;
+    long long edge_cap;
+    unsigned long long *nedge;
 };
 __constant__ StreamParams c_sp;
 
@@ -240,6 +253,7 @@ __device__ __forceinline__ void matrix_epilogue(const TileParams &p, uint32_t (&
 
 __device__ __forceinline__ void stream_emit_side(int q, int o, double d, uint32_t lhs, uint32_t den) {
     const StreamParams &sp = c_sp;
+    if (!(sp.want & TDNA_WANT_BEST_MATCH)) return;
     const uint32_t fresh = *reinterpret_cast<volatile uint32_t *>(sp.thr + q);  // other CTAs tighten it all the time
     if (lhs > fresh * den) return;
     const unsigned long long pos = atomicAdd(sp.ncand, 1ull);
@@ -266,6 +280,10 @@ __device__ __forceinline__ void stream_emit_side(int q, int o, double d, uint32_
 template <int KM> __device__ __noinline__ void stream_emit(int i, int j, uint32_t a0, uint32_t a1, uint32_t lhs, uint32_t den, int min_overlap) {
     Counts cn = unpack_counts<KM>(a0, a1);
     const double d = distance_from_counts<KM>(cn, min_overlap);
+    if ((c_sp.want & TDNA_WANT_EDGES) && d >= 0 && d <= c_sp.edge_t) {  // Cluster.java:797-804 (NaN fails both tests)
+        const unsigned long long pos = atomicAdd(c_sp.nedge, 1ull);
+        if (c_sp.ei && (long long)pos < c_sp.edge_cap) { c_sp.ei[pos] = i; c_sp.ej[pos] = j; c_sp.ed[pos] = d; }
+    }
     if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) {  // NaN / +Inf: the host resolves these rows from tdna_row_distances
         atomicOr(c_sp.flags + i, TDNA_ROW_NONFINITE);
         atomicOr(c_sp.flags + j, TDNA_ROW_NONFINITE);
@@ -273,6 +291,28 @@ template <int KM> __device__ __noinline__ void stream_emit(int i, int j, uint32_
     }
     stream_emit_side(i, j, d, lhs, den);
     stream_emit_side(j, i, d, lhs, den);
+}
+
+// PairwiseDistribution classes of one valid pair i < j (PairwiseDistribution.java:161-203): pushes (float)d
+template <int KM> __device__ __noinline__ void class_emit(int i, int j, uint32_t a0, uint32_t a1, int min_overlap) {
+    const StreamParams &sp = c_sp;
+    int times[2] = {0, 0};
+    if (sp.want & TDNA_WANT_INTRA) {  // _addIntra: conspecific, both named; once per pair, twice when the full names are equal (:172)
+        const int si = sp.species[i];
+        if (si >= 0 && si == sp.species[j]) times[0] = 1 + (sp.full[i] == sp.full[j] ? 1 : 0);
+    }
+    if (sp.want & TDNA_WANT_INTER) {  // _addInter: same genus, epithets differ; exactly one direction has epi[q] < epi[j] (:191-198)
+        if (sp.genus[i] == sp.genus[j] && sp.epi[i] != sp.epi[j]) times[1] = 1;
+    }
+    if (!(times[0] | times[1])) return;
+    Counts cn = unpack_counts<KM>(a0, a1);
+    const float f = (float)distance_from_counts<KM>(cn, min_overlap);  // the pair is valid: never -1
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+        for (int t = 0; t < times[k]; t++) {
+            const unsigned long long pos = atomicAdd(sp.ncls + k, 1ull);
+            if (sp.cls[k] && (long long)pos < sp.cls_cap[k]) sp.cls[k][pos] = f;
+        }
 }
 
 template <int KM, int CN>
@@ -288,6 +328,13 @@ __device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&
     for (int e = 0; e < CN; e++) {
         const int j = j0 + (e >> 2) * PR + 4 * tx + (e & 3);
         tfj[e] = (j < n) ? __ldcg(sp.thr + j) : 0u;
+    }
+    const uint32_t edge_tf = (sp.want & TDNA_WANT_EDGES) ? sp.edge_tfix : 0u;  // 0: only mism == 0 pairs pass, re-checked in the slow path
+    if (!(sp.want & TDNA_WANT_BEST_MATCH)) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) tfi[r] = 0u;
+#pragma unroll
+        for (int e = 0; e < CN; e++) tfj[e] = 0u;
     }
     uint32_t bad_r = 0, bad_c = 0;  // invalid pairs per row / column of this thread, one nibble each (<= 8)
 #pragma unroll
@@ -323,7 +370,37 @@ __device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&
                 den = s;
             }
             const uint32_t lhs = mism << 16;
-            if (lhs <= tfi[r] * den || lhs <= tfj[e] * den || force) stream_emit<KM>(i, j, a0, a1, lhs, den, p.min_overlap);
+            if (lhs <= tfi[r] * den || lhs <= tfj[e] * den || lhs <= edge_tf * den || force) stream_emit<KM>(i, j, a0, a1, lhs, den, p.min_overlap);
+        }
+    }
+    if (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER)) {
+        // class pairs only live in tiles whose row and column panels share a species or a genus id range
+        // (a handful of near-diagonal tiles when the list is sorted by name)
+        bool may = false;
+        for (int a = 0; a < TM / PR; a++)
+            for (int b = 0; b < TN / PR; b++) {
+                const int pi = ti * (TM / PR) + a, pj = tj * (TN / PR) + b;
+                if ((int64_t)pi * PR >= n || (int64_t)pj * PR >= n) continue;
+                const int4 ri = sp.panel_range[pi], rj = sp.panel_range[pj];
+                may |= (ri.x <= rj.y && rj.x <= ri.y) || (ri.z <= rj.w && rj.z <= ri.w);
+            }
+        if (may) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int i = i0 + r;
+#pragma unroll
+                for (int e = 0; e < CN; e++) {
+                    const int j = j0 + (e >> 2) * PR + 4 * tx + (e & 3);
+                    const uint32_t a0 = acc[0][r][e];
+                    if (j <= i || j >= n || (int)(a0 >> 16) < p.min_overlap) continue;
+                    const bool hit = ((sp.want & TDNA_WANT_INTRA) && sp.species[i] == sp.species[j]) ||
+                                     ((sp.want & TDNA_WANT_INTER) && sp.genus[i] == sp.genus[j]);
+                    if (!hit) continue;
+                    uint32_t a1 = 0;
+                    if constexpr (NACC == 2) a1 = acc[1][r][e];
+                    class_emit<KM>(i, j, a0, a1, p.min_overlap);
+                }
+            }
         }
     }
     if (__any_sync(0xffffffffu, (bad_r | bad_c) != 0)) {  // rare on clean data
@@ -814,7 +891,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) row_summary_kernel(const double
 // needc[q] != 0: q is named and another row of its species exists (labels only; set by the host side)
 __global__ void __launch_bounds__(256) stream_init_kernel(StreamParams sp, int64_t n, const uint8_t *__restrict__ needc) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q == 0) { *sp.ncand = 0ull; *sp.overflow = 0; }
+    if (q == 0) { *sp.ncand = 0ull; *sp.overflow = 0; sp.ncls[0] = 0ull; sp.ncls[1] = 0ull; *sp.nedge = 0ull; }
     if (q >= n) return;
     sp.thr[q] = TDNA_THR_ALL;
     sp.mC[q] = needc[q] ? TDNA_INF_BITS : 0ull;

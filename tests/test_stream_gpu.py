@@ -230,3 +230,37 @@ def test_overflow_falls_back_to_dense(ctx):
     finally:
         ctx.set_memory_budget(64 << 30)
         ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+
+
+@pytest.mark.parametrize("mode,shuffle,ragged", [(0, False, False), (0, True, True), (1, True, False), (2, False, True)])
+def test_one_pass_analysis_equals_the_dense_functions(ctx, mode, shuffle, ragged):
+    """tdna_analyze: Best Match + both PairwiseDistribution classes + Cluster edges from ONE streaming pass."""
+    import taxondna_b200 as t
+    rng = np.random.default_rng(40 + mode)
+    sym, lens, sp, gen, epi, full = make(rng, 24, 7, 520, unnamed=4, dup=8, gap=0.05, ragged=ragged, shuffle=shuffle, singletons=3)
+    n = sym.shape[0]
+    full = rng.permutation(n).astype(np.int32)
+    full[5] = full[9]  # equal full names: the pair is pushed twice if conspecific (PairwiseDistribution.java:172)
+    sp[9] = sp[5]
+    gen[9] = gen[5]
+    epi = sp.copy()
+    aln = t.Alignment(ctx, sym, lens)
+    aln.set_labels(sp, gen, epi, full)
+    aln.set_config(mode, 260, True)
+    thr = 0.03
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_DENSE)
+    d_rows = aln.best_match()
+    d_intra, d_inter = np.sort(aln.class_distances(t.PD_INTRA)), np.sort(aln.class_distances(t.PD_INTER))
+    d_edges = sorted(zip(*[x.tolist() for x in aln.edges_below(thr)]))
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_STREAM)
+    out = aln.analyze(best_match=True, intra=True, inter=True, edges=thr)
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+    assert len(d_intra) > 0 and len(d_inter) > 0 and len(d_edges) > 0
+    assert first_difference(out["rows"], d_rows) is None, first_difference(out["rows"], d_rows)
+    assert np.array_equal(np.sort(out["intra"]).view(np.uint32), d_intra.view(np.uint32))
+    assert np.array_equal(np.sort(out["inter"]).view(np.uint32), d_inter.view(np.uint32))
+    assert sorted(zip(out["edge_i"].tolist(), out["edge_j"].tolist(), out["edge_d"].tolist())) == d_edges
+    # the single-purpose entry points ride the same pass
+    assert np.array_equal(np.sort(aln.class_distances(t.PD_INTRA)).view(np.uint32), d_intra.view(np.uint32))
+    assert sorted(zip(*[x.tolist() for x in aln.edges_below(thr)])) == d_edges
+    aln.close()
