@@ -317,7 +317,8 @@ template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts,
         p.tile_prefix = a->d_sprefix[ph];
         int64_t total = a->sprefix_tiles[ph];
         p.num_tiles = total > part ? (total - part + nparts - 1) / nparts : 0;
-        TRY((launch_kernel<KM, CN, EPI_STREAM>(c, p)));
+        if (a->sp.want == TDNA_WANT_BEST_MATCH) TRY((launch_kernel<KM, CN, EPI_STREAM>(c, p)));
+        else TRY((launch_kernel<KM, CN, EPI_STREAM_X>(c, p)));
     }
     if (phases & 2) {
         CU(cudaEventRecord(c->ev_k1, c->stream));

@@ -148,7 +148,7 @@ struct StreamParams {
 __constant__ StreamParams c_sp;
 
 enum { SCHED_RECT = 0, SCHED_SYMMETRIC = 1, SCHED_STREAM = 2 };
-enum { EPI_MATRIX = 0, EPI_MATRIX_COUNTS = 1, EPI_STREAM = 2 };
+enum { EPI_MATRIX = 0, EPI_MATRIX_COUNTS = 1, EPI_STREAM = 2 /* Best-Match candidates only */, EPI_STREAM_X = 3 /* + classes / edges */ };
 
 struct TileParams {
     const uint32_t *planes;
@@ -315,7 +315,7 @@ template <int KM> __device__ __noinline__ void class_emit(int i, int j, uint32_t
         }
 }
 
-template <int KM, int CN>
+template <int KM, int CN, bool EXTRAS>
 __device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&acc)[ModeTraits<KM>::NACC][8][CN], int ti, int tj, int tx, int ty) {
     constexpr int NACC = ModeTraits<KM>::NACC, TN = 16 * CN;
     const StreamParams &sp = c_sp;
@@ -329,8 +329,8 @@ __device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&
         const int j = j0 + (e >> 2) * PR + 4 * tx + (e & 3);
         tfj[e] = (j < n) ? __ldcg(sp.thr + j) : 0u;
     }
-    const uint32_t edge_tf = (sp.want & TDNA_WANT_EDGES) ? sp.edge_tfix : 0u;  // 0: only mism == 0 pairs pass, re-checked in the slow path
-    if (!(sp.want & TDNA_WANT_BEST_MATCH)) {
+    const uint32_t edge_tf = (EXTRAS && (sp.want & TDNA_WANT_EDGES)) ? sp.edge_tfix : 0u;  // 0: only mism == 0 pairs pass, re-checked in the slow path
+    if (EXTRAS && !(sp.want & TDNA_WANT_BEST_MATCH)) {
 #pragma unroll
         for (int r = 0; r < 8; r++) tfi[r] = 0u;
 #pragma unroll
@@ -370,10 +370,12 @@ __device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&
                 den = s;
             }
             const uint32_t lhs = mism << 16;
-            if (lhs <= tfi[r] * den || lhs <= tfj[e] * den || lhs <= edge_tf * den || force) stream_emit<KM>(i, j, a0, a1, lhs, den, p.min_overlap);
+            bool pass = lhs <= tfi[r] * den || lhs <= tfj[e] * den || force;
+            if constexpr (EXTRAS) pass |= lhs <= edge_tf * den;
+            if (pass) stream_emit<KM>(i, j, a0, a1, lhs, den, p.min_overlap);
         }
     }
-    if (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER)) {
+    if (EXTRAS && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER))) {
         // class pairs only live in tiles whose row and column panels share a species or a genus id range
         // (a handful of near-diagonal tiles when the list is sorted by name)
         bool may = false;
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TileCfg<KM, CN>::MIN_CTAS) count
             const int64_t t = blockIdx.x + (it / nchunks) * gridDim.x;
             int ti, tj;
             tile_coords<TN>(p, prefix, t, ti, tj);
-            if constexpr (EPI == EPI_STREAM) stream_epilogue<KM, CN>(p, acc, ti, tj, tx, ty);
+            if constexpr (EPI == EPI_STREAM || EPI == EPI_STREAM_X) stream_epilogue<KM, CN, EPI == EPI_STREAM_X>(p, acc, ti, tj, tx, ty);
             else matrix_epilogue<KM, CN, EPI == EPI_MATRIX_COUNTS>(p, acc, ti, tj, tx, ty);
         }
     }
