@@ -207,7 +207,12 @@ int32_t tdna_analyze(tdna_aln *aln, tdna_analysis *io);
 
 /* ---- options ------------------------------------------------------------------------------------ */
 enum { TDNA_OPT_BEST_MATCH_PATH = 1, /* TDNA_PATH_*: how tdna_best_match computes a whole-range request */
-       TDNA_OPT_TILE_COLUMNS = 2     /* 0 = automatic, 64 or 128: column width of a count tile */ };
+       TDNA_OPT_TILE_COLUMNS = 2,    /* 0 = automatic, 64 or 128: column width of a popc count tile */
+       TDNA_OPT_COUNT_KERNEL = 3     /* TDNA_KERNEL_*: which count kernel the streaming pass uses */ };
+enum { TDNA_KERNEL_AUTO = 0,   /* the faster eligible one (A/B on ncu evidence) */
+       TDNA_KERNEL_POPC = 1,   /* (a) bit-planes + LOP3/POPC, any alphabet, any mode */
+       TDNA_KERNEL_TENSOR = 2  /* (b) one-hot int8 contraction on tcgen05/TMEM: uncorrected p, ambiguity allowed, alignments
+                                  without IUPAC ambiguity letters, L < 4096; TDNA_E_STATE if the alignment is not eligible */ };
 enum { TDNA_PATH_AUTO = 0,   /* streaming; falls back to the dense path if the candidate buffer overflows */
        TDNA_PATH_DENSE = 1,  /* materialise row bands of the fp64 matrix, sweep them */
        TDNA_PATH_STREAM = 2  /* streaming only (TDNA_E_TOO_LARGE on overflow) */ };
@@ -245,6 +250,9 @@ int32_t tdna_time_matrix_kernel(tdna_aln *aln, int32_t reps, float *ms_per_launc
 /* Device time (CUDA events on the context's stream) of the most recent count-tile pass -- the tile
  * kernel launch(es) of the last matrix band or streaming pass; waits for it to finish. */
 int32_t tdna_last_tile_pass_ms(tdna_ctx *ctx, float *ms);
+/* Verification of count kernel (b): (shared, ident) of every pair straight from the tcgen05 kernel, n x n
+ * records row-major (host or device); TDNA_E_STATE if the alignment is not eligible for it. */
+int32_t tdna_tensor_counts(tdna_aln *aln, tdna_counts *out);
 /* Integer-pipe micro-benchmarks: results/s of dependent-free POPC and LOP3 streams over all SMs. */
 int32_t tdna_measure_int_peaks(tdna_ctx *ctx, double *popc_per_s, double *lop3_per_s);
 

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "tdna_kernels.cuh"
+#include "tdna_tc.cuh"
 
 using namespace tdna;
 
@@ -57,6 +58,7 @@ struct tdna_ctx {
     bool ev_valid = false;
     int opt_best_match_path = TDNA_PATH_AUTO;
     int opt_tile_cn = 0;  // 0 = automatic
+    int opt_count_kernel = TDNA_KERNEL_AUTO;
 };
 
 struct tdna_aln {
@@ -96,6 +98,12 @@ struct tdna_aln {
     double *d_ld = nullptr;
     long long list_cap = 0;
     long long last_ncand = 0, last_ncls[2] = {0, 0}, last_nedge = 0;
+    // count kernel (b): one-hot int8 operands (tdna_tc.cuh)
+    uint8_t *d_tcA = nullptr, *d_tcB = nullptr;
+    int tc_state = 0;  // 0 = not built, 1 = ready, -1 = not eligible
+    int tc_nchunks = 0, tc_wbits = 0;
+    int64_t *d_tcprefix[2] = {nullptr, nullptr};
+    int64_t tcprefix_tiles[2] = {0, 0};
 };
 
 namespace {
@@ -169,6 +177,9 @@ int pack(tdna_aln *a) {
     a->mat_valid = false;
     return TDNA_OK;
 }
+
+int ensure_tc(tdna_aln *a);
+template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts);
 
 template <int KM, int CN, int EPI> int launch_kernel(tdna_ctx *c, const TileParams &p) {
     using Cfg = TileCfg<KM, CN>;
@@ -339,12 +350,112 @@ template <int KM> int launch_stream_km(tdna_aln *a, int part, int nparts, int ph
 
 // phases: bit 0 = diagonal blocks, bit 1 = the rest of the triangle
 int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
+    tdna_ctx *c = a->ctx;
+    if (c->opt_count_kernel == TDNA_KERNEL_TENSOR) {  // AUTO stays on the popc kernel until the A/B says otherwise
+        if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p with ambiguity allowed, no IUPAC ambiguity letters, L < 4096");
+        CU(cudaMemcpyToSymbolAsync(c_sp, &a->sp, sizeof(StreamParams), 0, cudaMemcpyHostToDevice, c->stream));
+        if (phases & 1) CU(cudaEventRecord(c->ev_k0, c->stream));
+        for (int ph = 0; ph < 2; ph++)
+            if (phases & (1 << ph)) TRY(launch_tc<false>(a, ph, part, nparts, nullptr));
+        if (phases & 2) {
+            CU(cudaEventRecord(c->ev_k1, c->stream));
+            c->ev_valid = true;
+        }
+        return TDNA_OK;
+    }
     switch (a->kmode) {
         case KM_P_AMBIG: return launch_stream_km<KM_P_AMBIG>(a, part, nparts, phases);
         case KM_P_NOAMBIG: return launch_stream_km<KM_P_NOAMBIG>(a, part, nparts, phases);
         case KM_K2P: return launch_stream_km<KM_K2P>(a, part, nparts, phases);
         default: return launch_stream_km<KM_TRANS>(a, part, nparts, phases);
     }
+}
+
+// ---- count kernel (b): operands, launches ----------------------------------------------------------
+// 1 = ready, -1 = this alignment / configuration is not eligible
+int ensure_tc(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
+    if (a->kmode != KM_P_AMBIG || a->L >= 4096) return -1;
+    if (a->tc_state != 0) return a->tc_state;
+    int k = 8;
+    while ((1 << k) <= a->L) k++;
+    static const int8_t tab[5][4] = {{15, 17, 16, 16}, {7, 73, 16, 32}, {33, 31, 32, 32}, {23, 89, 32, 64}, {65, 63, 64, 64}};  // ca cb wa wb
+    tc::EncodeValues v = {tab[k - 8][0], tab[k - 8][1], tab[k - 8][2], tab[k - 8][3]};
+    int nchunks = (a->L * tc::DIMS + tc::KB - 1) / tc::KB;
+    int64_t npa = round_up(a->n, tc::M), npb = round_up(a->n, tc::N);
+    if (cudaSuccess != DMALLOC(&a->d_tcA, (size_t)npa * nchunks * tc::KB) || cudaSuccess != DMALLOC(&a->d_tcB, (size_t)npb * nchunks * tc::KB)) {
+        cudaGetLastError();
+        a->tc_state = -1;
+        return -1;
+    }
+    int *d_flag = reinterpret_cast<int *>(c->d_counter);
+    cudaMemsetAsync(d_flag, 0, 8, c->stream);
+    int64_t ua = npa * nchunks * (tc::KB / 16), ub = npb * nchunks * (tc::KB / 16);
+    tc::encode_kernel<false><<<(unsigned)((ua + 255) / 256), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, npa, a->sym_stride, a->L, nchunks, v, a->d_tcA, d_flag);
+    tc::encode_kernel<true><<<(unsigned)((ub + 255) / 256), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, npb, a->sym_stride, a->L, nchunks, v, a->d_tcB, d_flag);
+    c->launches += 2;
+    int flag = 0;
+    cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) flag = 1;
+    // tile lists of the two phases: row tile ti (128 rows) x column tiles >= ti / 2 (256 columns)
+    int nrt = (int)(npa / tc::M);
+    int64_t nct = npb / tc::N;
+    for (int ph = 0; ph < 2 && !flag; ph++) {
+        std::vector<int64_t> pre(nrt + 1);
+        pre[0] = 0;
+        for (int t = 0; t < nrt; t++) {
+            int64_t first = t >> 1;
+            int64_t cnt = ph == 0 ? (first < nct ? 1 : 0) : (nct - first - 1 > 0 ? nct - first - 1 : 0);
+            pre[t + 1] = pre[t] + cnt;
+        }
+        if (cudaSuccess != DMALLOC(&a->d_tcprefix[ph], (size_t)(nrt + 1) * 8)) { flag = 1; break; }
+        cudaMemcpyAsync(a->d_tcprefix[ph], pre.data(), (size_t)(nrt + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+        cudaStreamSynchronize(c->stream);
+        a->tcprefix_tiles[ph] = pre[nrt];
+    }
+    if (flag) {  // an IUPAC ambiguity letter (or an allocation failure): the popc kernel handles this alignment
+        DFREE(a->d_tcA);
+        DFREE(a->d_tcB);
+        a->d_tcA = a->d_tcB = nullptr;
+        a->tc_state = -1;
+        return -1;
+    }
+    a->tc_nchunks = nchunks;
+    a->tc_wbits = k;
+    a->tc_state = 1;
+    return 1;
+}
+
+template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts) {
+    tdna_ctx *c = a->ctx;
+    auto kern = tc::tile_kernel<COUNTS_MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
+        attr_set = true;
+    }
+    tc::Params p = {};
+    p.A = a->d_tcA;
+    p.B = a->d_tcB;
+    p.nchunks = a->tc_nchunks;
+    p.n = (int)a->n;
+    p.min_overlap = a->min_overlap;
+    p.wbits = a->tc_wbits;
+    p.nrt = (int)(round_up(a->n, tc::M) / tc::M);
+    p.prefix = a->d_tcprefix[phase];
+    p.first_col_extra = phase;
+    p.t_offset = part;
+    p.t_stride = nparts;
+    int64_t total = a->tcprefix_tiles[phase];
+    p.num_tiles = total > part ? (total - part + nparts - 1) / nparts : 0;
+    p.counts = counts;
+    p.extras = a->sp.want != TDNA_WANT_BEST_MATCH;
+    int64_t grid = p.num_tiles < c->sm_count ? p.num_tiles : c->sm_count;
+    if (grid < 1) return TDNA_OK;
+    kern<<<(unsigned)grid, tc::THREADS, tc::SMEM, c->stream>>>(p);
+    c->launches++;
+    CU(cudaGetLastError());
+    return TDNA_OK;
 }
 
 int ensure_packed(tdna_aln *a) {
@@ -545,7 +656,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     cudaSetDevice(c->device);
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
-                    a->d_needc, a->d_panel_range, a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
+                    a->d_needc, a->d_panel_range, a->d_tcA, a->d_tcB, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_cursor, a->d_lj, a->d_ld};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
@@ -608,6 +719,7 @@ int32_t tdna_set_config(tdna_aln *a, int32_t mode, int32_t min_overlap, int32_t 
     a->ambig = ambiguous_allowed ? 1 : 0;
     a->mat_valid = false;
     if (repack) TRY(pack(a));
+    if (a->tc_state == -1) a->tc_state = 0;  // eligibility depends on the mode: ask again
     return TDNA_OK;
 }
 
@@ -1224,12 +1336,39 @@ int32_t tdna_set_option(tdna_ctx *c, int32_t key, int64_t value) {
             if (value < TDNA_PATH_AUTO || value > TDNA_PATH_STREAM) return fail(TDNA_E_ARG, "bad path");
             c->opt_best_match_path = (int)value;
             return TDNA_OK;
+        case TDNA_OPT_COUNT_KERNEL:
+            if (value < TDNA_KERNEL_AUTO || value > TDNA_KERNEL_TENSOR) return fail(TDNA_E_ARG, "bad kernel");
+            c->opt_count_kernel = (int)value;
+            return TDNA_OK;
         case TDNA_OPT_TILE_COLUMNS:
             if (value != 0 && value != 64 && value != 128) return fail(TDNA_E_ARG, "tile columns must be 0, 64 or 128");
             c->opt_tile_cn = (int)(value / 16);
             return TDNA_OK;
     }
     return fail(TDNA_E_ARG, "unknown option");
+}
+
+int32_t tdna_tensor_counts(tdna_aln *a, tdna_counts *out) {
+    if (!a || !out) return fail(TDNA_E_ARG, "null argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(ensure_packed(a));
+    if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p with ambiguity allowed, no IUPAC ambiguity letters, L < 4096");
+    tdna_counts *dc = out;
+    bool own = !is_device_ptr(out);
+    size_t bytes = (size_t)a->n * a->n * sizeof(tdna_counts);
+    if (own) CU(DMALLOC(&dc, bytes));
+    CU(cudaMemsetAsync(dc, 0xff, bytes, c->stream));  // pairs the triangle does not cover stay -1
+    int rc = launch_tc<true>(a, 0, 0, 1, dc);
+    if (rc == TDNA_OK) rc = launch_tc<true>(a, 1, 0, 1, dc);
+    if (rc == TDNA_OK) {
+        cudaError_t e = cudaSuccess;
+        if (own) e = cudaMemcpyAsync(out, dc, bytes, cudaMemcpyDefault, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
+    }
+    if (own) DFREE(dc);
+    return rc;
 }
 
 int32_t tdna_last_tile_pass_ms(tdna_ctx *c, float *ms) {

@@ -1,0 +1,299 @@
+// Count kernel (b): the per-pair counts as a dense int8 contraction of one-hot matrices on the 5th-gen
+// tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).  p-distance with ambiguity codes
+// allowed, for alignments whose symbols are all in {A C G T - _ ?} ("clean": the alignment carries no
+// IUPAC ambiguity letter; anything else runs on the popc kernel).
+//
+// One int32 accumulator per pair carries BOTH counts.  Per site, six K-dimensions:
+//     a-side  (row x):  ca*[x==A] ca*[x==C] ca*[x==G] ca*[x==T] ca*[x=='-']  wa*V(x)
+//     b-side  (col y): -cb*[y==A] ...                           -cb*[y=='-']  wb*V(y)
+// with V = symbol is a base or '-' (Sequence.getSharedLength, Sequence.java:1429-1455), wa*wb = W = 2^k > L
+// and ca*cb = W-1, so that
+//     D(x,y) = W*shared - (W-1)*ident = ident + W*(shared - ident),   ident = D & (W-1), mism = D >> k.
+// ident = sites where both are the same base or both '-' (Sequence.identical, :1262-1302, restricted to
+// the clean alphabet); all |values| <= 127 (int8), D < 2^31 for L < 4096.
+//
+// Operand memory: per 128-row (a) / 256-row (b) panel and per K-chunk of 128 bytes, one contiguous
+// block already in the shared-memory image tcgen05 wants (K-major, no swizzle: 8-row x 16-byte core
+// matrices, [k16][row group][row][16 B]); a block is ONE cp.async.bulk.  CTA = 1 TMA producer warp,
+// 1 MMA issuer warp (one elected lane), 4 epilogue warps (TMEM -> registers -> the same integer
+// candidate filter as the popc kernel's stream epilogue).  Two accumulator stages of 256 columns.
+#pragma once
+#include "tdna_kernels.cuh"
+
+namespace tdna {
+namespace tc {
+
+constexpr int M = 128, N = 256, KB = 128;          // tile rows, tile columns, K bytes per row per stage
+constexpr int NSTAGE = 4;
+constexpr int A_STAGE = M * KB, B_STAGE = N * KB;  // 16 KB + 32 KB
+constexpr int STAGE = A_STAGE + B_STAGE;
+constexpr int THREADS = 192;                       // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+constexpr int DIMS = 6;                            // K-dimensions per site
+constexpr size_t SMEM = (size_t)NSTAGE * STAGE + 256 /*barriers*/ + 2 * N * 4 /*column thresholds*/ + 1024 /*alignment*/;
+
+struct Params {
+    const uint8_t *A;   // [a-panel][chunk][16 KB]
+    const uint8_t *B;   // [b-panel][chunk][32 KB]
+    int nchunks;        // K-chunks per row
+    int n;
+    int min_overlap;
+    int wbits;          // k: W = 2^k
+    int nrt;            // 128-row tiles
+    const int64_t *prefix;  // [nrt + 1] tiles before row tile ti (this phase)
+    int first_col_extra;    // 0: diagonal phase (column tile ti/2 only), 1: the rest
+    int64_t num_tiles, t_offset, t_stride;
+    tdna_counts *counts;    // verification mode: n x n counts (row-major), else null
+    int extras;             // stream mode: classes / edges wanted (c_sp.want beyond Best Match)
+};
+
+__device__ __forceinline__ void tile_coords(const Params &p, const int64_t *prefix, int64_t t, int &ti, int &tj) {
+    t = p.t_offset + t * p.t_stride;
+    int lo = 0, hi = p.nrt;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= t) lo = mid; else hi = mid;
+    }
+    ti = lo;
+    tj = (int)(t - prefix[lo]) + (ti >> 1) + p.first_col_extra;
+}
+
+// ---- operand encoding -------------------------------------------------------------------------
+struct EncodeValues {
+    int8_t ca, cb, wa, wb;
+};
+// one thread = one 16-byte unit of one row; unit index order (panel, chunk, k16, row group, row) = memory order
+template <bool BSIDE>
+__global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len, int64_t n, int64_t npad,
+                                                     int64_t sym_stride, int L, int nchunks, EncodeValues v, uint8_t *__restrict__ out,
+                                                     int *__restrict__ not_clean) {
+    constexpr int ROWS = BSIDE ? N : M;
+    const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t units = npad * nchunks * (KB / 16);
+    if (unit >= units) return;
+    const int r = (int)(unit % 8);
+    const int rg = (int)((unit / 8) % (ROWS / 8));
+    const int k16 = (int)((unit / (8 * (ROWS / 8))) % (KB / 16));
+    const int64_t pc = unit / (8 * (ROWS / 8) * (KB / 16));
+    const int c = (int)(pc % nchunks);
+    const int64_t panel = pc / nchunks;
+    const int64_t row = panel * ROWS + rg * 8 + r;
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (row < n) {
+        const int l = len[row];
+        const uint8_t *src = sym + row * sym_stride;
+        const int kk0 = c * KB + k16 * 16;
+        bool bad = false;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const int kk = kk0 + b, site = kk / DIMS, dim = kk % DIMS;
+            int val = 0;
+            if (site < L && site < l) {
+                const uint8_t ch = __ldg(src + site);
+                int code;  // 0..4 = A C G T '-', 5 = '_' / '?', 6 = anything else
+                switch (ch) {
+                    case 'A': code = 0; break;
+                    case 'C': code = 1; break;
+                    case 'G': code = 2; break;
+                    case 'T': code = 3; break;
+                    case '-': code = 4; break;
+                    case '_': case '?': code = 5; break;
+                    default: code = 6; break;
+                }
+                bad |= code == 6;
+                if (code < 5) {
+                    if (dim == 5) val = BSIDE ? v.wb : v.wa;
+                    else if (dim == code) val = BSIDE ? -(int)v.cb : (int)v.ca;
+                }
+            }
+            w[b >> 2] |= (uint32_t)(val & 0xff) << (8 * (b & 3));
+        }
+        if (bad) atomicOr(not_clean, 1);
+    }
+    reinterpret_cast<uint4 *>(out)[unit] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---- tcgen05 / TMEM primitives ---------------------------------------------------------------
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // K-major, SWIZZLE_NONE: start >> 4 in [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46), version 1 in [46,48)
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// kind::i8: D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {  // arrives on bar when every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) { mbar_wait_backoff(bar, parity); }
+
+// ---- the tile kernel ---------------------------------------------------------------------------
+template <bool COUNTS_MODE>
+__global__ void __launch_bounds__(THREADS, 1) tile_kernel(Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)NSTAGE * STAGE);
+    uint64_t *empty = full + NSTAGE;
+    uint64_t *tfull = empty + NSTAGE;   // [2] accumulator stage ready for the epilogue
+    uint64_t *tempty = tfull + 2;       // [2] accumulator stage drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint32_t *col_thr = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * STAGE + 256);  // [2][N]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t my_tiles = (p.num_tiles > blockIdx.x) ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulator stages)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int64_t it = 0;
+            for (int64_t k = 0; k < my_tiles; k++) {
+                int ti, tj;
+                tile_coords(p, p.prefix, blockIdx.x + k * gridDim.x, ti, tj);
+                const uint8_t *ga = p.A + (size_t)ti * p.nchunks * A_STAGE;
+                const uint8_t *gb = p.B + (size_t)tj * p.nchunks * B_STAGE;
+                for (int c = 0; c < p.nchunks; c++, it++) {
+                    const int slot = (int)(it % NSTAGE);
+                    if (it >= NSTAGE) mbar_wait_sleep(&empty[slot], (uint32_t)(((it / NSTAGE) - 1) & 1));
+                    uint8_t *sa = smem + (size_t)slot * STAGE, *sb = sa + A_STAGE;
+                    mbar_expect_tx(&full[slot], STAGE);
+                    bulk_g2s(sa, ga + (size_t)c * A_STAGE, A_STAGE, &full[slot]);
+                    bulk_g2s(sb, gb + (size_t)c * B_STAGE, B_STAGE, &full[slot]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int64_t it = 0;
+            for (int64_t k = 0; k < my_tiles; k++) {
+                const int as = (int)(k & 1);
+                if (k >= 2) mbar_wait_sleep(&tempty[as], (uint32_t)(((k >> 1) - 1) & 1));
+                fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * N);
+                for (int c = 0; c < p.nchunks; c++, it++) {
+                    const int slot = (int)(it % NSTAGE);
+                    mbar_wait(&full[slot], (uint32_t)((it / NSTAGE) & 1));
+                    fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)slot * STAGE), sb = sa + A_STAGE;
+#pragma unroll
+                    for (int s = 0; s < KB / 32; s++) {  // one MMA = 32 K-bytes = two 16-byte K-halves
+                        const uint64_t ad = smem_desc(sa + s * 2 * (M * 16), M * 16, 128);
+                        const uint64_t bd = smem_desc(sb + s * 2 * (N * 16), N * 16, 128);
+                        mma_i8(d_tmem, ad, bd, (c | s) != 0 ? 1u : 0u);
+                    }
+                    mma_commit(&empty[slot]);  // the stage may be refilled once these MMAs have read it
+                }
+                mma_commit(&tfull[as]);        // accumulator complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int et = (warp - 2) * 32 + lane;  // 0..127 among the epilogue threads
+        const StreamParams &sp = c_sp;
+        const uint32_t wmask = (1u << p.wbits) - 1u;
+        for (int64_t k = 0; k < my_tiles; k++) {
+            const int as = (int)(k & 1);
+            int ti, tj;
+            tile_coords(p, p.prefix, blockIdx.x + k * gridDim.x, ti, tj);
+            const int i = ti * M + q * 32 + lane, j0 = tj * N;
+            uint32_t tfi = 0;
+            if constexpr (!COUNTS_MODE) {
+                // column thresholds of this tile -> shared memory (read back as warp broadcasts)
+                for (int x = et; x < N; x += 128) col_thr[as * N + x] = (j0 + x < p.n && (sp.want & TDNA_WANT_BEST_MATCH)) ? __ldcg(sp.thr + j0 + x) : 0u;
+                tfi = (i < p.n && (sp.want & TDNA_WANT_BEST_MATCH)) ? __ldcg(sp.thr + i) : 0u;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            mbar_wait(&tfull[as], (uint32_t)((k >> 1) & 1));
+            fence_after();
+            const uint32_t edge_tf = (!COUNTS_MODE && p.extras && (sp.want & TDNA_WANT_EDGES)) ? sp.edge_tfix : 0u;
+            int bad_row = 0;
+            for (int cb = 0; cb < N / 32; cb++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + cb * 32), v);
+                if (cb == N / 32 - 1) {  // every column of this stage is in registers: hand the stage back
+                    fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                }
+#pragma unroll
+                for (int e = 0; e < 32; e++) {
+                    const int j = j0 + cb * 32 + e;
+                    const uint32_t ident = v[e] & wmask, mism = v[e] >> p.wbits, s = ident + mism;
+                    if constexpr (COUNTS_MODE) {
+                        if (i < p.n && j < p.n) {
+                            tdna_counts o = {(int)s, (int)ident, 0, 0};
+                            p.counts[(size_t)i * p.n + j] = o;
+                        }
+                    } else {
+                        if (j <= i || j >= p.n) {
+                            if (j == i && i < p.n && (int)s >= p.min_overlap) atomicOr(sp.flags + i, TDNA_ROW_SELF_VALID);
+                            continue;
+                        }
+                        if ((int)s < p.min_overlap) {
+                            bad_row++;
+                            atomicAdd(sp.inval + j, 1);
+                            continue;
+                        }
+                        const uint32_t lhs = mism << 16;
+                        const uint32_t a0 = ident | (s << 16);
+                        if (lhs <= tfi * s || lhs <= col_thr[as * N + cb * 32 + e] * s || lhs <= edge_tf * s)
+                            stream_emit<KM_P_AMBIG>(i, j, a0, 0u, lhs, s, p.min_overlap);
+                        if (p.extras && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER))) {
+                            const bool hit = ((sp.want & TDNA_WANT_INTRA) && sp.species[i] == sp.species[j]) ||
+                                             ((sp.want & TDNA_WANT_INTER) && sp.genus[i] == sp.genus[j]);
+                            if (hit) class_emit<KM_P_AMBIG>(i, j, a0, 0u, p.min_overlap);
+                        }
+                    }
+                }
+            }
+            if constexpr (!COUNTS_MODE) {
+                if (bad_row) atomicAdd(sp.inval + i, bad_row);
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // col_thr[as] is rewritten two tiles later, but keep the warps together
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+}  // namespace tc
+}  // namespace tdna

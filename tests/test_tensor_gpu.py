@@ -1,0 +1,108 @@
+"""Count kernel (b): the tcgen05 / TMEM one-hot int8 contraction must reproduce the oracle's integer
+counts bit for bit, and the streaming Best Match built on it must equal the popc kernel's."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+CLEAN = b"ACGT-?"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import taxondna_b200 as t
+    c = t.Context(0)
+    yield c
+    c.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
+    c.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+    c.close()
+
+
+def clean_alignment(rng, n, L, p_special=0.08, ragged=False):
+    base = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=L)
+    sym = np.tile(base, (n, 1))
+    mut = rng.random((n, L)) < 0.12
+    sym[mut] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(mut.sum()))
+    sp = rng.random((n, L)) < p_special
+    sym[sp] = rng.choice(np.frombuffer(CLEAN, dtype=np.uint8), size=int(sp.sum()))
+    for r in range(0, n, 7):  # leading / trailing external gaps ('_' after Sequence.changeSequence)
+        k = int(rng.integers(0, L // 4))
+        sym[r, :k] = ord("_")
+    lens = None
+    if ragged:
+        lens = rng.integers(max(1, L // 2), L + 1, size=n).astype(np.int32)
+        lens[0] = L
+    return sym, lens
+
+
+@pytest.mark.parametrize("n,L,ragged", [(2, 40, False), (130, 200, False), (300, 658, True), (257, 1539, False), (140, 2664, True), (520, 330, False)])
+def test_tensor_counts_equal_the_oracle(ctx, n, L, ragged):
+    import taxondna_b200 as t
+    rng = np.random.default_rng(n * 31 + L)
+    sym, lens = clean_alignment(rng, n, L, ragged=ragged)
+    aln = t.Alignment(ctx, sym, lens)
+    aln.set_config(t.PDM_UNCORRECTED, max(1, L // 3), True)
+    got = aln.tensor_counts()
+    ref = oracle.all_pairs(sym, lens if lens is not None else np.full(n, L, np.int32), 0, max(1, L // 3), True, threads=8)
+    iu = np.triu_indices(n, 0)  # the triangle incl. the diagonal is always covered
+    assert np.array_equal(got["shared"][iu], ref["shared"][iu]), "shared"
+    assert np.array_equal(got["c1"][iu], ref["c1"][iu]), "ident"
+    aln.close()
+
+
+def test_not_eligible_is_reported(ctx):
+    import taxondna_b200 as t
+    rng = np.random.default_rng(1)
+    sym, _ = clean_alignment(rng, 50, 100)
+    sym[3, 5] = ord("N")
+    aln = t.Alignment(ctx, sym)
+    with pytest.raises(t.TdnaError) as ei:
+        aln.tensor_counts()
+    assert ei.value.code == 4
+    aln.close()
+    sym, _ = clean_alignment(rng, 50, 100)
+    aln = t.Alignment(ctx, sym)
+    aln.set_config(t.PDM_K2P, 10, True)
+    with pytest.raises(t.TdnaError):
+        aln.tensor_counts()
+    aln.close()
+
+
+@pytest.mark.parametrize("shuffle,ragged,L", [(False, False, 658), (True, True, 500), (False, True, 2664)])
+def test_streaming_best_match_on_the_tensor_kernel(ctx, shuffle, ragged, L):
+    import taxondna_b200 as t
+    from test_stream_gpu import first_difference
+    from test_gpu_parity import labelled_alignment
+    rng = np.random.default_rng(17 + L)
+    sym, sp, gen, epi, full = labelled_alignment(rng, 36, 9, L, unnamed=4, dup=10, gappy=False)
+    n = sym.shape[0]
+    m = rng.random(sym.shape) < 0.04
+    sym[m] = rng.choice(np.frombuffer(CLEAN, dtype=np.uint8), size=int(m.sum()))
+    lens = rng.integers(L // 2, L + 1, size=n).astype(np.int32) if ragged else None
+    if shuffle:
+        perm = rng.permutation(n)
+        sym, sp, gen, epi = sym[perm], sp[perm], gen[perm], epi[perm]
+        if lens is not None:
+            lens = lens[perm]
+    aln = t.Alignment(ctx, sym, lens)
+    aln.set_labels(sp, gen, epi, full)
+    aln.set_config(t.PDM_UNCORRECTED, L // 2, True)
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_STREAM)
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_POPC)
+    a = aln.analyze(best_match=True, intra=True, inter=True, edges=0.03)
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_TENSOR)
+    b = aln.analyze(best_match=True, intra=True, inter=True, edges=0.03)
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+    assert first_difference(a["rows"], b["rows"]) is None, first_difference(a["rows"], b["rows"])
+    assert np.array_equal(np.sort(a["intra"]).view(np.uint32), np.sort(b["intra"]).view(np.uint32))
+    assert np.array_equal(np.sort(a["inter"]).view(np.uint32), np.sort(b["inter"]).view(np.uint32))
+    assert sorted(zip(a["edge_i"].tolist(), a["edge_j"].tolist(), a["edge_d"].tolist())) == \
+        sorted(zip(b["edge_i"].tolist(), b["edge_j"].tolist(), b["edge_d"].tolist()))
+    aln.close()
