@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "tensor"], help="count kernel of the streaming pass")
     return ap.parse_args()
 
 
@@ -230,6 +231,7 @@ def main():
     W32 = (L + 31) // 32
 
     ctx = t.Context(local)
+    ctx.set_option(t.OPT_COUNT_KERNEL, {"auto": t.KERNEL_AUTO, "popc": t.KERNEL_POPC, "tensor": t.KERNEL_TENSOR}[args.kernel])
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
     sym_pinned = torch.from_numpy(sym).pin_memory()
     labels = [data[k] for k in ("species_id", "genus_id", "epithet_rank", "fullname_rank")]

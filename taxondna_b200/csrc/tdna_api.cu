@@ -101,7 +101,10 @@ struct tdna_aln {
     // count kernel (b): one-hot int8 operands (tdna_tc.cuh)
     uint8_t *d_tcA = nullptr, *d_tcB = nullptr;
     int tc_state = 0;  // 0 = not built, 1 = ready, -1 = not eligible
-    int tc_nchunks = 0, tc_wbits = 0;
+    int tc_nchunks = 0;
+    uint32_t tc_W = 0;
+    CUtensorMap tc_mapA, tc_mapB;  // [.., 256 x uint32] views of d_tcA / d_tcB, boxes of one operand block
+    bool tc_maps = false;
     int64_t *d_tcprefix[2] = {nullptr, nullptr};
     int64_t tcprefix_tiles[2] = {0, 0};
 };
@@ -178,6 +181,13 @@ int pack(tdna_aln *a) {
     return TDNA_OK;
 }
 
+// c_sp for the next launch: the seed pass (diagonal blocks) only tightens thresholds and wants Best Match only
+int set_stream_symbol(tdna_aln *a, bool seed) {
+    StreamParams sp = a->sp;
+    if (seed) sp.want = TDNA_WANT_BEST_MATCH | TDNA_WANT_SEED;
+    CU(cudaMemcpyToSymbolAsync(c_sp, &sp, sizeof(StreamParams), 0, cudaMemcpyHostToDevice, a->ctx->stream));
+    return TDNA_OK;
+}
 int ensure_tc(tdna_aln *a);
 template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts);
 
@@ -290,7 +300,7 @@ template <int CN> int stream_prefixes(tdna_aln *a) {
             if (diag < 0) diag = 0;
             int64_t rest = nct - first - R;
             if (rest < 0) rest = 0;
-            pre[ph][t + 1] = pre[ph][t] + (ph == 0 ? diag : rest);
+            pre[ph][t + 1] = pre[ph][t] + (ph == 0 ? diag : diag + rest);  // seed pass: diagonal blocks; bulk pass: the whole triangle
         }
         if (a->d_sprefix[ph]) CU(DFREE(a->d_sprefix[ph]));
         a->d_sprefix[ph] = nullptr;
@@ -307,10 +317,10 @@ template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts,
     using Cfg = TileCfg<KM, CN>;
     tdna_ctx *c = a->ctx;
     TRY(stream_prefixes<CN>(a));
-    CU(cudaMemcpyToSymbolAsync(c_sp, &a->sp, sizeof(StreamParams), 0, cudaMemcpyHostToDevice, c->stream));
     if (phases & 1) CU(cudaEventRecord(c->ev_k0, c->stream));
     for (int ph = 0; ph < 2; ph++) {
         if (!(phases & (1 << ph))) continue;
+        TRY(set_stream_symbol(a, ph == 0));
         TileParams p = {};
         p.planes = a->d_planes;
         p.W = a->W;
@@ -320,7 +330,7 @@ template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts,
         p.row_end = a->n;
         p.symmetric = 0;
         p.sched = SCHED_STREAM;
-        p.first_col_extra = ph ? TM / Cfg::TN : 0;
+        p.first_col_extra = 0;
         p.t_offset = part;
         p.t_stride = nparts;
         p.nct = (int)((a->n + Cfg::TN - 1) / Cfg::TN);
@@ -328,7 +338,7 @@ template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts,
         p.tile_prefix = a->d_sprefix[ph];
         int64_t total = a->sprefix_tiles[ph];
         p.num_tiles = total > part ? (total - part + nparts - 1) / nparts : 0;
-        if (a->sp.want == TDNA_WANT_BEST_MATCH) TRY((launch_kernel<KM, CN, EPI_STREAM>(c, p)));
+        if (ph == 0 || a->sp.want == TDNA_WANT_BEST_MATCH) TRY((launch_kernel<KM, CN, EPI_STREAM>(c, p)));
         else TRY((launch_kernel<KM, CN, EPI_STREAM_X>(c, p)));
     }
     if (phases & 2) {
@@ -353,10 +363,12 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
     tdna_ctx *c = a->ctx;
     if (c->opt_count_kernel == TDNA_KERNEL_TENSOR) {  // AUTO stays on the popc kernel until the A/B says otherwise
         if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p with ambiguity allowed, no IUPAC ambiguity letters, L < 4096");
-        CU(cudaMemcpyToSymbolAsync(c_sp, &a->sp, sizeof(StreamParams), 0, cudaMemcpyHostToDevice, c->stream));
         if (phases & 1) CU(cudaEventRecord(c->ev_k0, c->stream));
         for (int ph = 0; ph < 2; ph++)
-            if (phases & (1 << ph)) TRY(launch_tc<false>(a, ph, part, nparts, nullptr));
+            if (phases & (1 << ph)) {
+                TRY(set_stream_symbol(a, ph == 0));
+                TRY(launch_tc<false>(a, ph, part, nparts, nullptr));
+            }
         if (phases & 2) {
             CU(cudaEventRecord(c->ev_k1, c->stream));
             c->ev_valid = true;
@@ -372,15 +384,42 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
 }
 
 // ---- count kernel (b): operands, launches ----------------------------------------------------------
+static int tc_band() {  // row tiles per band of the bulk phase (TDNA_TC_BAND overrides, for experiments)
+    const char *e = getenv("TDNA_TC_BAND");
+    int v = e ? atoi(e) : 16;
+    return v < 1 ? 1 : v;
+}
+#define TC_BAND tc_band()
+
+// Integers for the five-dimensional symbol code of tdna_tc.cuh: u = b*1 + a*e_x, v = d*1 + c*e_y with
+// a*c = -(W-1), a*d + b*c + 5*b*d = W, every entry (b, a+b, d, c+d) within int8, smallest W > L.
+bool find_code(int L, tc::EncodeValues &out, uint32_t &Wout) {
+    for (int W = L + 1; W < L + 4096; W++)
+        for (int aa = -127; aa <= 127; aa++) {
+            if (aa == 0 || (W - 1) % (aa < 0 ? -aa : aa) != 0) continue;
+            int cc = -(W - 1) / aa;
+            if (cc < -127 || cc > 127) continue;
+            for (int bb = -127; bb <= 127; bb++) {
+                if (aa + bb < -127 || aa + bb > 127) continue;
+                int den = aa + 5 * bb, num = W - bb * cc;
+                if (den == 0 || num % den != 0) continue;
+                int dd = num / den;
+                if (dd < -127 || dd > 127 || cc + dd < -127 || cc + dd > 127) continue;
+                out.a = aa; out.b = bb; out.c = cc; out.d = dd;
+                Wout = (uint32_t)W;
+                return true;
+            }
+        }
+    return false;
+}
 // 1 = ready, -1 = this alignment / configuration is not eligible
 int ensure_tc(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
     if (a->kmode != KM_P_AMBIG || a->L >= 4096) return -1;
     if (a->tc_state != 0) return a->tc_state;
-    int k = 8;
-    while ((1 << k) <= a->L) k++;
-    static const int8_t tab[5][4] = {{15, 17, 16, 16}, {7, 73, 16, 32}, {33, 31, 32, 32}, {23, 89, 32, 64}, {65, 63, 64, 64}};  // ca cb wa wb
-    tc::EncodeValues v = {tab[k - 8][0], tab[k - 8][1], tab[k - 8][2], tab[k - 8][3]};
+    tc::EncodeValues v;
+    uint32_t W = 0;
+    if (!find_code(a->L, v, W)) { a->tc_state = -1; return -1; }
     int nchunks = (a->L * tc::DIMS + tc::KB - 1) / tc::KB;
     int64_t npa = round_up(a->n, tc::M), npb = round_up(a->n, tc::N);
     if (cudaSuccess != DMALLOC(&a->d_tcA, (size_t)npa * nchunks * tc::KB) || cudaSuccess != DMALLOC(&a->d_tcB, (size_t)npb * nchunks * tc::KB)) {
@@ -397,21 +436,25 @@ int ensure_tc(tdna_aln *a) {
     int flag = 0;
     cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) flag = 1;
-    // tile lists of the two phases: row tile ti (128 rows) x column tiles >= ti / 2 (256 columns)
+    // bulk phase: bands of TC_BAND row tiles, column tile outer / row tile inner (tdna_tc.cuh: tile_coords)
     int nrt = (int)(npa / tc::M);
     int64_t nct = npb / tc::N;
-    for (int ph = 0; ph < 2 && !flag; ph++) {
-        std::vector<int64_t> pre(nrt + 1);
+    int nbands = (nrt + TC_BAND - 1) / TC_BAND;
+    if (!flag) {
+        std::vector<int64_t> pre(nbands + 1);
         pre[0] = 0;
-        for (int t = 0; t < nrt; t++) {
-            int64_t first = t >> 1;
-            int64_t cnt = ph == 0 ? (first < nct ? 1 : 0) : (nct - first - 1 > 0 ? nct - first - 1 : 0);
-            pre[t + 1] = pre[t] + cnt;
+        for (int b = 0; b < nbands; b++) {
+            int64_t tjmin = ((int64_t)b * TC_BAND >> 1);
+            int64_t cols = nct - tjmin > 0 ? nct - tjmin : 0;
+            pre[b + 1] = pre[b] + cols * TC_BAND;
         }
-        if (cudaSuccess != DMALLOC(&a->d_tcprefix[ph], (size_t)(nrt + 1) * 8)) { flag = 1; break; }
-        cudaMemcpyAsync(a->d_tcprefix[ph], pre.data(), (size_t)(nrt + 1) * 8, cudaMemcpyHostToDevice, c->stream);
-        cudaStreamSynchronize(c->stream);
-        a->tcprefix_tiles[ph] = pre[nrt];
+        if (cudaSuccess != DMALLOC(&a->d_tcprefix[1], (size_t)(nbands + 1) * 8)) flag = 1;
+        else {
+            cudaMemcpyAsync(a->d_tcprefix[1], pre.data(), (size_t)(nbands + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+            cudaStreamSynchronize(c->stream);
+            a->tcprefix_tiles[0] = nrt;
+            a->tcprefix_tiles[1] = pre[nbands];
+        }
     }
     if (flag) {  // an IUPAC ambiguity letter (or an allocation failure): the popc kernel handles this alignment
         DFREE(a->d_tcA);
@@ -421,7 +464,26 @@ int ensure_tc(tdna_aln *a) {
         return -1;
     }
     a->tc_nchunks = nchunks;
-    a->tc_wbits = k;
+    a->tc_W = W;
+    {   // tensor maps for the tiled TMA loads (driver entry point through the runtime: no -lcuda)
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        a->tc_maps = false;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr) == cudaSuccess && fp && qr == cudaDriverEntryPointSuccess) {
+            encode_fn enc = reinterpret_cast<encode_fn>(fp);
+            cuuint64_t dimsA[2] = {256, (cuuint64_t)((size_t)npa * nchunks * tc::KB / 1024)}, dimsB[2] = {256, (cuuint64_t)((size_t)npb * nchunks * tc::KB / 1024)};
+            cuuint64_t strides[1] = {1024};
+            cuuint32_t boxA[2] = {256, tc::A_STAGE / 1024}, boxB[2] = {256, tc::B_STAGE / 1024}, es[2] = {1, 1};
+            CUresult r1 = enc(&a->tc_mapA, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, a->d_tcA, dimsA, strides, boxA, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            CUresult r2 = enc(&a->tc_mapB, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, a->d_tcB, dimsB, strides, boxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            a->tc_maps = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS);
+        }
+        cudaGetLastError();
+    }
     a->tc_state = 1;
     return 1;
 }
@@ -440,19 +502,28 @@ template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int 
     p.nchunks = a->tc_nchunks;
     p.n = (int)a->n;
     p.min_overlap = a->min_overlap;
-    p.wbits = a->tc_wbits;
+    p.W = a->tc_W;
+    p.Winv = ((1ull << 40) + a->tc_W - 1) / a->tc_W;
     p.nrt = (int)(round_up(a->n, tc::M) / tc::M);
-    p.prefix = a->d_tcprefix[phase];
-    p.first_col_extra = phase;
+    p.nct = (int)(round_up(a->n, tc::N) / tc::N);
+    p.band = phase ? TC_BAND : 0;
+    p.nbands = (p.nrt + TC_BAND - 1) / TC_BAND;
+    p.prefix = a->d_tcprefix[1];
     p.t_offset = part;
     p.t_stride = nparts;
     int64_t total = a->tcprefix_tiles[phase];
     p.num_tiles = total > part ? (total - part + nparts - 1) / nparts : 0;
     p.counts = counts;
     p.extras = a->sp.want != TDNA_WANT_BEST_MATCH;
+    {
+        const char *e = getenv("TDNA_TC_PIECE");
+        int v = e ? atoi(e) : (a->tc_maps ? 0 : 16384);  // default: tiled TMA when the tensor maps exist
+        p.piece = (v >= 1024 && 16384 % v == 0) ? v : (a->tc_maps ? 0 : 16384);
+    }
     int64_t grid = p.num_tiles < c->sm_count ? p.num_tiles : c->sm_count;
+    if (const char *e = getenv("TDNA_TC_GRID")) { int v = atoi(e); if (v >= 1 && v < grid) grid = v; }
     if (grid < 1) return TDNA_OK;
-    kern<<<(unsigned)grid, tc::THREADS, tc::SMEM, c->stream>>>(p);
+    kern<<<(unsigned)grid, tc::THREADS, tc::SMEM, c->stream>>>(a->tc_mapA, a->tc_mapB, p);
     c->launches++;
     CU(cudaGetLastError());
     return TDNA_OK;
@@ -1359,8 +1430,7 @@ int32_t tdna_tensor_counts(tdna_aln *a, tdna_counts *out) {
     size_t bytes = (size_t)a->n * a->n * sizeof(tdna_counts);
     if (own) CU(DMALLOC(&dc, bytes));
     CU(cudaMemsetAsync(dc, 0xff, bytes, c->stream));  // pairs the triangle does not cover stay -1
-    int rc = launch_tc<true>(a, 0, 0, 1, dc);
-    if (rc == TDNA_OK) rc = launch_tc<true>(a, 1, 0, 1, dc);
+    int rc = launch_tc<true>(a, 1, 0, 1, dc);  // the bulk enumeration covers the whole triangle
     if (rc == TDNA_OK) {
         cudaError_t e = cudaSuccess;
         if (own) e = cudaMemcpyAsync(out, dc, bytes, cudaMemcpyDefault, c->stream);

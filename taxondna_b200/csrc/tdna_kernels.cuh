@@ -249,6 +249,7 @@ __device__ __forceinline__ void matrix_epilogue(const TileParams &p, uint32_t (&
 // row summary on the list alone.  The per-pair test is integer only (mism << 16 <= thr * den, a
 // conservative statement of d <= thr: for K2P, d >= (ts+tv)/n); fp64 happens on candidates only.
 #define TDNA_THR_ALL 65536u
+#define TDNA_WANT_SEED 0x100  // internal: the diagonal-block pass only tightens the per-row minima / thresholds, it emits nothing
 #define TDNA_INF_BITS 0x7ff0000000000000ull
 
 __device__ __forceinline__ void stream_emit_side(int q, int o, double d, uint32_t lhs, uint32_t den) {
@@ -256,12 +257,14 @@ __device__ __forceinline__ void stream_emit_side(int q, int o, double d, uint32_
     if (!(sp.want & TDNA_WANT_BEST_MATCH)) return;
     const uint32_t fresh = *reinterpret_cast<volatile uint32_t *>(sp.thr + q);  // other CTAs tighten it all the time
     if (lhs > fresh * den) return;
-    const unsigned long long pos = atomicAdd(sp.ncand, 1ull);
-    if ((long long)pos >= sp.cap) { *sp.overflow = 1; return; }
-    sp.cq[pos] = q;
-    sp.cj[pos] = o;
-    sp.cd[pos] = d;
-    atomicAdd(sp.cnt + q, 1);
+    if (!(sp.want & TDNA_WANT_SEED)) {
+        const unsigned long long pos = atomicAdd(sp.ncand, 1ull);
+        if ((long long)pos >= sp.cap) { *sp.overflow = 1; return; }
+        sp.cq[pos] = q;
+        sp.cj[pos] = o;
+        sp.cd[pos] = d;
+        atomicAdd(sp.cnt + q, 1);
+    }
     const int spo = sp.species[o];
     if (spo < 0) return;  // unnamed columns bound nothing
     const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
@@ -285,6 +288,7 @@ template <int KM> __device__ __noinline__ void stream_emit(int i, int j, uint32_
         if (c_sp.ei && (long long)pos < c_sp.edge_cap) { c_sp.ei[pos] = i; c_sp.ej[pos] = j; c_sp.ed[pos] = d; }
     }
     if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) {  // NaN / +Inf: the host resolves these rows from tdna_row_distances
+        if (c_sp.want & TDNA_WANT_SEED) return;
         atomicOr(c_sp.flags + i, TDNA_ROW_NONFINITE);
         atomicOr(c_sp.flags + j, TDNA_ROW_NONFINITE);
         return;
@@ -336,6 +340,7 @@ __device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&
 #pragma unroll
         for (int e = 0; e < CN; e++) tfj[e] = 0u;
     }
+    const bool seed = (sp.want & TDNA_WANT_SEED) != 0;  // diagonal-block pre-pass: thresholds only
     uint32_t bad_r = 0, bad_c = 0;  // invalid pairs per row / column of this thread, one nibble each (<= 8)
 #pragma unroll
     for (int r = 0; r < 8; r++) {
@@ -346,12 +351,14 @@ __device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&
             const uint32_t a0 = acc[0][r][e];
             const uint32_t s = a0 >> 16, c1 = a0 & 0xffffu;
             if (j <= i || j >= n) {
-                if (j == i && i < n && (int)s >= p.min_overlap) atomicOr(sp.flags + i, TDNA_ROW_SELF_VALID);
+                if (j == i && i < n && (int)s >= p.min_overlap && !seed) atomicOr(sp.flags + i, TDNA_ROW_SELF_VALID);
                 continue;
             }
             if ((int)s < p.min_overlap) {  // -1.0 in the reference: not a candidate of anything
-                bad_r += 1u << (4 * r);
-                bad_c += 1u << (4 * e);
+                if (!seed) {
+                    bad_r += 1u << (4 * r);
+                    bad_c += 1u << (4 * e);
+                }
                 continue;
             }
             uint32_t a1 = 0, mism, den;

@@ -3,14 +3,14 @@
 // allowed, for alignments whose symbols are all in {A C G T - _ ?} ("clean": the alignment carries no
 // IUPAC ambiguity letter; anything else runs on the popc kernel).
 //
-// One int32 accumulator per pair carries BOTH counts.  Per site, six K-dimensions:
-//     a-side  (row x):  ca*[x==A] ca*[x==C] ca*[x==G] ca*[x==T] ca*[x=='-']  wa*V(x)
-//     b-side  (col y): -cb*[y==A] ...                           -cb*[y=='-']  wb*V(y)
-// with V = symbol is a base or '-' (Sequence.getSharedLength, Sequence.java:1429-1455), wa*wb = W = 2^k > L
-// and ca*cb = W-1, so that
-//     D(x,y) = W*shared - (W-1)*ident = ident + W*(shared - ident),   ident = D & (W-1), mism = D >> k.
-// ident = sites where both are the same base or both '-' (Sequence.identical, :1262-1302, restricted to
-// the clean alphabet); all |values| <= 127 (int8), D < 2^31 for L < 4096.
+// One int32 accumulator per pair carries BOTH counts, from FIVE K-dimensions per site (one per valid symbol
+// A C G T '-'):   a-side (row x):  u = b*1 + a*e_x     b-side (column y):  v = d*1 + c*e_y     ('_', '?': zero vector)
+// with integers |entries| <= 127 chosen such that  a*c = -(W-1)  and  a*d + b*c + 5*b*d = W  for a W > L, so that
+//     u . v = W - (W-1)*[x == y]   for valid x, y, 0 otherwise, and summed over the sites
+//     D(x,y) = W*shared - (W-1)*ident = ident + W*(shared - ident),   ident = D mod W, mism = D / W.
+// shared = sites where both are a base or '-' (Sequence.getSharedLength, Sequence.java:1429-1455); ident = sites
+// where both are the same base or both '-' (Sequence.identical, :1262-1302, restricted to the clean alphabet).
+// D < 2^31 for L < 4096.  (The search for a, b, c, d is find_code() in tdna_api.cu.)
 //
 // Operand memory: per 128-row (a) / 256-row (b) panel and per K-chunk of 128 bytes, one contiguous
 // block already in the shared-memory image tcgen05 wants (K-major, no swizzle: 8-row x 16-byte core
@@ -18,6 +18,8 @@
 // 1 MMA issuer warp (one elected lane), 4 epilogue warps (TMEM -> registers -> the same integer
 // candidate filter as the popc kernel's stream epilogue).  Two accumulator stages of 256 columns.
 #pragma once
+#include <cuda.h>
+
 #include "tdna_kernels.cuh"
 
 namespace tdna {
@@ -27,8 +29,10 @@ constexpr int M = 128, N = 256, KB = 128;          // tile rows, tile columns, K
 constexpr int NSTAGE = 4;
 constexpr int A_STAGE = M * KB, B_STAGE = N * KB;  // 16 KB + 32 KB
 constexpr int STAGE = A_STAGE + B_STAGE;
-constexpr int THREADS = 192;                       // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
-constexpr int DIMS = 6;                            // K-dimensions per site
+constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter
+constexpr int EPI_COLS = N / (EPI_WARPS / 4);      // columns per epilogue warp
+constexpr int THREADS = 64 + EPI_WARPS * 32;       // warp 0 producer, warp 1 MMA issuer, warps 2.. epilogue
+constexpr int DIMS = 5;                            // K-dimensions per site
 constexpr size_t SMEM = (size_t)NSTAGE * STAGE + 256 /*barriers*/ + 2 * N * 4 /*column thresholds*/ + 1024 /*alignment*/;
 
 struct Params {
@@ -37,29 +41,44 @@ struct Params {
     int nchunks;        // K-chunks per row
     int n;
     int min_overlap;
-    int wbits;          // k: W = 2^k
+    uint32_t W;         // the accumulator's radix
+    uint64_t Winv;      // ceil(2^40 / W): D / W == (D * Winv) >> 40 for every D this kernel can produce
     int nrt;            // 128-row tiles
-    const int64_t *prefix;  // [nrt + 1] tiles before row tile ti (this phase)
-    int first_col_extra;    // 0: diagonal phase (column tile ti/2 only), 1: the rest
+    int nct;            // 256-column tiles
+    int band;           // 0: seed pass, tile t = (row tile t, column tile t / 2); else row tiles per band of the whole triangle
+    int nbands;
+    const int64_t *prefix;  // bulk phase: [nbands + 1] tile slots before band b
     int64_t num_tiles, t_offset, t_stride;
     tdna_counts *counts;    // verification mode: n x n counts (row-major), else null
     int extras;             // stream mode: classes / edges wanted (c_sp.want beyond Best Match)
+    int piece;              // bytes per 1-D bulk copy (divides 16 KB); 0 = tensor-map (2-D tiled TMA) loads
 };
 
-__device__ __forceinline__ void tile_coords(const Params &p, const int64_t *prefix, int64_t t, int &ti, int &tj) {
+// Tile slot -> (row tile, column tile); false = an empty slot.  The bulk phase walks BANDS of `band` row tiles,
+// column tile outer / row tile inner, so that the ~148 tiles in flight at any time share ~16 a-panels and ~9
+// b-panels: every operand block is fetched from HBM about once per band and otherwise hits L2.
+__device__ __forceinline__ bool tile_coords(const Params &p, const int64_t *prefix, int64_t t, int &ti, int &tj) {
     t = p.t_offset + t * p.t_stride;
-    int lo = 0, hi = p.nrt;
+    if (p.band == 0) {
+        ti = (int)t;
+        tj = ti >> 1;
+        return ti < p.nrt && tj < p.nct;
+    }
+    int lo = 0, hi = p.nbands;
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (prefix[mid] <= t) lo = mid; else hi = mid;
     }
-    ti = lo;
-    tj = (int)(t - prefix[lo]) + (ti >> 1) + p.first_col_extra;
+    const int64_t r = t - prefix[lo];
+    const int ti0 = lo * p.band;
+    ti = ti0 + (int)(r % p.band);
+    tj = (ti0 >> 1) + (int)(r / p.band);
+    return ti < p.nrt && tj < p.nct && tj >= (ti >> 1);
 }
 
 // ---- operand encoding -------------------------------------------------------------------------
 struct EncodeValues {
-    int8_t ca, cb, wa, wb;
+    int a, b, c, d;
 };
 // one thread = one 16-byte unit of one row; unit index order (panel, chunk, k16, row group, row) = memory order
 template <bool BSIDE>
@@ -100,10 +119,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
                     default: code = 6; break;
                 }
                 bad |= code == 6;
-                if (code < 5) {
-                    if (dim == 5) val = BSIDE ? v.wb : v.wa;
-                    else if (dim == code) val = BSIDE ? -(int)v.cb : (int)v.ca;
-                }
+                if (code < 5) val = BSIDE ? v.d + (dim == code ? v.c : 0) : v.b + (dim == code ? v.a : 0);
             }
             w[b >> 2] |= (uint32_t)(val & 0xff) << (8 * (b & 3));
         }
@@ -146,11 +162,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 2-D tiled TMA load (UTMALDG): box (256 uint32, rows) of the [.., 1 KB] view of an operand array
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) { mbar_wait_backoff(bar, parity); }
 
 // ---- the tile kernel ---------------------------------------------------------------------------
 template <bool COUNTS_MODE>
-__global__ void __launch_bounds__(THREADS, 1) tile_kernel(Params p) {
+__global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)NSTAGE * STAGE);
@@ -165,7 +188,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(Params p) {
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulator stages)
@@ -183,16 +206,21 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(Params p) {
             int64_t it = 0;
             for (int64_t k = 0; k < my_tiles; k++) {
                 int ti, tj;
-                tile_coords(p, p.prefix, blockIdx.x + k * gridDim.x, ti, tj);
+                if (!tile_coords(p, p.prefix, blockIdx.x + k * gridDim.x, ti, tj)) continue;
                 const uint8_t *ga = p.A + (size_t)ti * p.nchunks * A_STAGE;
                 const uint8_t *gb = p.B + (size_t)tj * p.nchunks * B_STAGE;
                 for (int c = 0; c < p.nchunks; c++, it++) {
                     const int slot = (int)(it % NSTAGE);
-                    if (it >= NSTAGE) mbar_wait_sleep(&empty[slot], (uint32_t)(((it / NSTAGE) - 1) & 1));
+                    if (it >= NSTAGE) mbar_wait(&empty[slot], (uint32_t)(((it / NSTAGE) - 1) & 1));  // the ring IS the bottleneck here: no back-off
                     uint8_t *sa = smem + (size_t)slot * STAGE, *sb = sa + A_STAGE;
                     mbar_expect_tx(&full[slot], STAGE);
-                    bulk_g2s(sa, ga + (size_t)c * A_STAGE, A_STAGE, &full[slot]);
-                    bulk_g2s(sb, gb + (size_t)c * B_STAGE, B_STAGE, &full[slot]);
+                    if (p.piece == 0) {  // one block = 16 (a) / 32 (b) rows of 1 KB
+                        tma_load_2d(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * (A_STAGE / 1024)), &full[slot]);
+                        tma_load_2d(sb, &mapB, 0, (int)(((int64_t)tj * p.nchunks + c) * (B_STAGE / 1024)), &full[slot]);
+                        continue;
+                    }
+                    for (int o = 0; o < A_STAGE; o += p.piece) bulk_g2s(sa + o, ga + (size_t)c * A_STAGE + o, p.piece, &full[slot]);
+                    for (int o = 0; o < B_STAGE; o += p.piece) bulk_g2s(sb + o, gb + (size_t)c * B_STAGE + o, p.piece, &full[slot]);
                 }
             }
         }
@@ -200,8 +228,10 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(Params p) {
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            int64_t it = 0;
-            for (int64_t k = 0; k < my_tiles; k++) {
+            int64_t it = 0, k = 0;  // k counts the non-empty tiles of this CTA
+            for (int64_t kk = 0; kk < my_tiles; kk++) {
+                int ti_, tj_;
+                if (!tile_coords(p, p.prefix, blockIdx.x + kk * gridDim.x, ti_, tj_)) continue;
                 const int as = (int)(k & 1);
                 if (k >= 2) mbar_wait_sleep(&tempty[as], (uint32_t)(((k >> 1) - 1) & 1));
                 fence_after();
@@ -220,73 +250,107 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(Params p) {
                     mma_commit(&empty[slot]);  // the stage may be refilled once these MMAs have read it
                 }
                 mma_commit(&tfull[as]);        // accumulator complete
+                k++;
             }
         }
         __syncwarp();
     } else {
-        // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
-        const int q = warp & 3;
-        const int et = (warp - 2) * 32 + lane;  // 0..127 among the epilogue threads
+        // ===== epilogue warps: TMEM lane quarter = warp % 4, column group = (warp - 2) / 4 =====
+        // Sixteen warps (four per scheduler): the per-pair test is a dependent integer chain, so latency is hidden by
+        // warps, and the flags of 32 pairs are computed branch-free before the (rare) slow path is entered.
+        const int q = warp & 3, g = (warp - 2) >> 2;
+        const int et = tid - 64;  // 0..511 among the epilogue threads
         const StreamParams &sp = c_sp;
-        const uint32_t wmask = (1u << p.wbits) - 1u;
-        for (int64_t k = 0; k < my_tiles; k++) {
-            const int as = (int)(k & 1);
+        int64_t k = 0;
+        for (int64_t kk = 0; kk < my_tiles; kk++, k++) {
             int ti, tj;
-            tile_coords(p, p.prefix, blockIdx.x + k * gridDim.x, ti, tj);
+            if (!tile_coords(p, p.prefix, blockIdx.x + kk * gridDim.x, ti, tj)) { k--; continue; }
+            const int as = (int)(k & 1);
             const int i = ti * M + q * 32 + lane, j0 = tj * N;
             uint32_t tfi = 0;
             if constexpr (!COUNTS_MODE) {
                 // column thresholds of this tile -> shared memory (read back as warp broadcasts)
-                for (int x = et; x < N; x += 128) col_thr[as * N + x] = (j0 + x < p.n && (sp.want & TDNA_WANT_BEST_MATCH)) ? __ldcg(sp.thr + j0 + x) : 0u;
+                if (et < N) col_thr[as * N + et] = (j0 + et < p.n && (sp.want & TDNA_WANT_BEST_MATCH)) ? __ldcg(sp.thr + j0 + et) : 0u;
                 tfi = (i < p.n && (sp.want & TDNA_WANT_BEST_MATCH)) ? __ldcg(sp.thr + i) : 0u;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 512;" ::: "memory");
             }
             mbar_wait(&tfull[as], (uint32_t)((k >> 1) & 1));
             fence_after();
             const uint32_t edge_tf = (!COUNTS_MODE && p.extras && (sp.want & TDNA_WANT_EDGES)) ? sp.edge_tfix : 0u;
+            const bool seed = (sp.want & TDNA_WANT_SEED) != 0;  // diagonal-block pre-pass: thresholds only
+            const bool classes = !COUNTS_MODE && !seed && p.extras && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER));
             int bad_row = 0;
-            for (int cb = 0; cb < N / 32; cb++) {
+#pragma unroll
+            for (int cbi = 0; cbi < EPI_COLS / 32; cbi++) {
+                const int cb = g * (EPI_COLS / 32) + cbi;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + cb * 32), v);
-                if (cb == N / 32 - 1) {  // every column of this stage is in registers: hand the stage back
+                if (cbi == EPI_COLS / 32 - 1) {  // this warp's columns of the stage are in registers: hand them back
                     fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[as]);
                 }
+                const int jb = j0 + cb * 32;
+                if constexpr (COUNTS_MODE) {
 #pragma unroll
-                for (int e = 0; e < 32; e++) {
-                    const int j = j0 + cb * 32 + e;
-                    const uint32_t ident = v[e] & wmask, mism = v[e] >> p.wbits, s = ident + mism;
-                    if constexpr (COUNTS_MODE) {
-                        if (i < p.n && j < p.n) {
-                            tdna_counts o = {(int)s, (int)ident, 0, 0};
-                            p.counts[(size_t)i * p.n + j] = o;
+                    for (int e = 0; e < 32; e++) {
+                        const uint32_t mism = (uint32_t)(((uint64_t)v[e] * p.Winv) >> 40), ident = v[e] - mism * p.W;
+                        if (i < p.n && jb + e < p.n) {
+                            tdna_counts o = {(int)(ident + mism), (int)ident, 0, 0};
+                            p.counts[(size_t)i * p.n + jb + e] = o;
                         }
-                    } else {
-                        if (j <= i || j >= p.n) {
-                            if (j == i && i < p.n && (int)s >= p.min_overlap) atomicOr(sp.flags + i, TDNA_ROW_SELF_VALID);
-                            continue;
+                    }
+                } else {
+                    uint32_t pmask = 0, bmask = 0, smask = 0;  // slow path wanted / pair below minOverlap / valid self pair
+                    const uint4 *ct4 = reinterpret_cast<const uint4 *>(col_thr + as * N + cb * 32);
+#pragma unroll
+                    for (int e4 = 0; e4 < 8; e4++) {
+                        const uint4 ct = ct4[e4];
+                        const uint32_t cts[4] = {ct.x, ct.y, ct.z, ct.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int e = e4 * 4 + u, j = jb + e;
+                            const uint32_t mism = (uint32_t)(((uint64_t)v[e] * p.Winv) >> 40), s = v[e] - mism * (p.W - 1u);  // ident + mism
+                            const bool inr = (j > i) & (j < p.n);
+                            const bool ok = (int)s >= p.min_overlap;
+                            const uint32_t lhs = mism << 16;
+                            const bool pass = (lhs <= tfi * s) | (lhs <= cts[u] * s) | (lhs <= edge_tf * s);
+                            pmask |= (uint32_t)(inr & ok & pass) << e;
+                            bmask |= (uint32_t)(inr & !ok) << e;
+                            smask |= (uint32_t)((j == i) & (i < p.n) & ok) << e;
                         }
-                        if ((int)s < p.min_overlap) {
-                            bad_row++;
-                            atomicAdd(sp.inval + j, 1);
-                            continue;
-                        }
-                        const uint32_t lhs = mism << 16;
-                        const uint32_t a0 = ident | (s << 16);
-                        if (lhs <= tfi * s || lhs <= col_thr[as * N + cb * 32 + e] * s || lhs <= edge_tf * s)
-                            stream_emit<KM_P_AMBIG>(i, j, a0, 0u, lhs, s, p.min_overlap);
-                        if (p.extras && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER))) {
+                    }
+                    if (smask && !seed) atomicOr(sp.flags + i, TDNA_ROW_SELF_VALID);
+                    if (bmask && !seed) {
+                        bad_row += __popc(bmask);
+#pragma unroll
+                        for (int e = 0; e < 32; e++)
+                            if (bmask & (1u << e)) atomicAdd(sp.inval + jb + e, 1);
+                    }
+                    if (pmask) {
+#pragma unroll
+                        for (int e = 0; e < 32; e++)
+                            if (pmask & (1u << e)) {
+                                const uint32_t mism = (uint32_t)(((uint64_t)v[e] * p.Winv) >> 40), ident = v[e] - mism * p.W, s = ident + mism;
+                                stream_emit<KM_P_AMBIG>(i, jb + e, ident | (s << 16), 0u, mism << 16, s, p.min_overlap);
+                            }
+                    }
+                    if (classes) {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) {
+                            const int j = jb + e;
+                            const uint32_t mism = (uint32_t)(((uint64_t)v[e] * p.Winv) >> 40), ident = v[e] - mism * p.W, s = ident + mism;
+                            if (j <= i || j >= p.n || (int)s < p.min_overlap) continue;
                             const bool hit = ((sp.want & TDNA_WANT_INTRA) && sp.species[i] == sp.species[j]) ||
                                              ((sp.want & TDNA_WANT_INTER) && sp.genus[i] == sp.genus[j]);
-                            if (hit) class_emit<KM_P_AMBIG>(i, j, a0, 0u, p.min_overlap);
+                            if (hit) class_emit<KM_P_AMBIG>(i, j, ident | (s << 16), 0u, p.min_overlap);
                         }
                     }
                 }
             }
             if constexpr (!COUNTS_MODE) {
                 if (bad_row) atomicAdd(sp.inval + i, bad_row);
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // col_thr[as] is rewritten two tiles later, but keep the warps together
+                asm volatile("bar.sync 1, 512;" ::: "memory");  // col_thr[as] is rewritten two tiles later: keep the warps within one tile of each other
             }
         }
     }
