@@ -352,28 +352,64 @@ def main():
     else:
         kern_ms = aln.time_matrix_kernel(max(3, min(20, args.steps)))
         kern_pairs = pairs if world == 1 else rows_mine * n  # symmetric triangle vs rectangular band
-    popc_alg = kern_pairs * POPC_PER_PAIR_WORD[mode] * W32
-    popc_peak, lop3_peak = ctx.measure_int_peaks()
-    achieved = popc_alg / (kern_ms * 1e-3)
     peaks, peak_src = measured_peaks()
     prof = {}
     pj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(pj):
-        prof = json.load(open(pj)).get(args.workload, {})
-    P_planes = {0: 6, 1: 5, 2: 4}[mode]
-    plane_bytes = n * P_planes * W32 * 4
-    roofline = {
-        "bound": "int-issue: POPC on the XU pipe (16 lanes/clk/SM); neither HBM nor tensor bound -- see DESIGN.md",
-        "kernel": "count_tile_kernel" + ("<EPI_STREAM>" if streaming else "<EPI_MATRIX>"),
-        "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": achieved / popc_peak,
-        "peak_source": "measured live by tdna_measure_int_peaks: dependent-free POPC stream on all SMs (MEASURED_PEAKS.json has no integer-pipe figure); LOP3 stream %.2f T/s (two LOP3 per result)" % (lop3_peak / 1e12),
-        "kernel_ms": kern_ms, "kernel_gpairs_per_s": kern_pairs / (kern_ms * 1e-3) / 1e9,
-        "algorithmic_popc32_per_pair": POPC_PER_PAIR_WORD[mode] * W32,
-        "traffic": prof.get("dram_bytes_per_launch"),
-        "hbm": {"algorithmic_bytes_per_launch": int(plane_bytes if streaming else plane_bytes + rows_mine * n * 8),
-                "achieved_gbs": (plane_bytes if streaming else plane_bytes + rows_mine * n * 8) / (kern_ms * 1e-3) / 1e9,
-                "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},
-    }
+        prof = json.load(open(pj))
+    used_tensor = streaming and aln.last_count_kernel() == t.KERNEL_TENSOR
+    if used_tensor:
+        # kernel (b): int8 one-hot contraction on tcgen05.  Algorithmic work = 2 * K * L int8 ops per pair with the K = 5
+        # symbol dimensions per site this kernel uses; peak = a cuBLASLt int8 GEMM (torch._int_mm, 8192^3)
+        # measured here, else twice MEASURED_PEAKS.json's bf16 burst figure.
+        ops = kern_pairs * 2 * 5 * L
+        int8_peak, int8_src = None, None
+        try:
+            a8 = torch.randint(-3, 3, (8192, 8192), dtype=torch.int8, device=dev)
+            b8 = torch.randint(-3, 3, (8192, 8192), dtype=torch.int8, device=dev)
+            for _ in range(3):
+                torch._int_mm(a8, b8)
+            best = 1e9
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch._int_mm(a8, b8)
+                e1.record()
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            int8_peak, int8_src = 2 * 8192 ** 3 / (best * 1e-3), "measured live: torch._int_mm int8 8192^3, best of 10 (cuBLASLt; MEASURED_PEAKS.json has no int8 figure)"
+            del a8, b8
+        except Exception as ex:  # noqa: BLE001
+            int8_peak, int8_src = 2 * peaks.get("bf16_tflops", 1590.0) * 1e12, "2 x MEASURED_PEAKS.json bf16_tflops (%s; torch._int_mm unavailable: %s)" % (peak_src, type(ex).__name__)
+        achieved = ops / (kern_ms * 1e-3)
+        P_bytes = 2 * n * 5 * L  # a-side + b-side one-hot operands
+        roofline = {
+            "bound": "tensor", "kernel": "tc::tile_kernel (tcgen05.mma kind::i8, TMEM accumulators)",
+            "achieved": achieved / 1e12, "peak": int8_peak / 1e12, "unit": "TOP/s (int8)", "frac": achieved / int8_peak,
+            "peak_source": int8_src, "kernel_ms": kern_ms, "kernel_gpairs_per_s": kern_pairs / (kern_ms * 1e-3) / 1e9,
+            "algorithmic_int8_ops_per_pair": 2 * 5 * L,
+            "traffic": prof.get(args.workload + "_tensor", {}).get("dram_bytes_per_launch"),
+            "hbm": {"algorithmic_bytes_per_launch": int(P_bytes), "achieved_gbs": P_bytes / (kern_ms * 1e-3) / 1e9,
+                    "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},
+        }
+    else:
+        popc_alg = kern_pairs * POPC_PER_PAIR_WORD[mode] * W32
+        popc_peak, lop3_peak = ctx.measure_int_peaks()
+        achieved = popc_alg / (kern_ms * 1e-3)
+        P_planes = {0: 6, 1: 5, 2: 4}[mode]
+        plane_bytes = n * P_planes * W32 * 4
+        roofline = {
+            "bound": "int-issue: POPC on the XU pipe (16 lanes/clk/SM); neither HBM nor tensor bound -- see DESIGN.md",
+            "kernel": "count_tile_kernel" + ("<EPI_STREAM>" if streaming else "<EPI_MATRIX>"),
+            "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": achieved / popc_peak,
+            "peak_source": "measured live by tdna_measure_int_peaks: dependent-free POPC stream on all SMs (MEASURED_PEAKS.json has no integer-pipe figure); LOP3 stream %.2f T/s (two LOP3 per result)" % (lop3_peak / 1e12),
+            "kernel_ms": kern_ms, "kernel_gpairs_per_s": kern_pairs / (kern_ms * 1e-3) / 1e9,
+            "algorithmic_popc32_per_pair": POPC_PER_PAIR_WORD[mode] * W32,
+            "traffic": prof.get(args.workload, {}).get("dram_bytes_per_launch"),
+            "hbm": {"algorithmic_bytes_per_launch": int(plane_bytes if streaming else plane_bytes + rows_mine * n * 8),
+                    "achieved_gbs": (plane_bytes if streaming else plane_bytes + rows_mine * n * 8) / (kern_ms * 1e-3) / 1e9,
+                    "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},
+        }
 
     # ---- e2e: the same step through the C ABI with HOST buffers ---------------------------------
     e2e_steps = max(1, min(args.steps, 5))
@@ -441,8 +477,8 @@ def main():
             "metric": "pairwise distances/s", "value": value, "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
-            "dtype": "u32 bit-planes -> int32 counts -> f64 distance", "data": "synthetic",
-            "config": {"workload": wl["desc"], "n": n, "L": L, "mode": ["uncorrected", "K2P", "trans-only"][mode], "min_overlap": 300,
+            "dtype": ("int8 one-hot -> int32 counts (tcgen05) -> f64 distance" if used_tensor else "u32 bit-planes -> int32 counts -> f64 distance"), "data": "synthetic",
+            "config": {"workload": wl["desc"], "n": n, "L": L, "count_kernel": ("tensor" if used_tensor else "popc"), "mode": ["uncorrected", "K2P", "trans-only"][mode], "min_overlap": 300,
                        "pairs": pairs, "step": kind, "l2": "flushed between timed steps (256 MiB write)", "parallelism": par},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "region_wall_s": t_region,

@@ -247,6 +247,8 @@ int32_t tdna_cancel(tdna_ctx *ctx);
  * `reps` times and returns the mean device time per launch in milliseconds (CUDA events on the
  * context's stream). */
 int32_t tdna_time_matrix_kernel(tdna_aln *aln, int32_t reps, float *ms_per_launch);
+/* TDNA_KERNEL_POPC / TDNA_KERNEL_TENSOR: which count kernel the alignment's most recent streaming pass ran on (0: none yet). */
+int32_t tdna_last_count_kernel(tdna_aln *aln);
 /* Device time (CUDA events on the context's stream) of the most recent count-tile pass -- the tile
  * kernel launch(es) of the last matrix band or streaming pass; waits for it to finish. */
 int32_t tdna_last_tile_pass_ms(tdna_ctx *ctx, float *ms);

@@ -66,7 +66,7 @@ EXPORTS = [
     "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_row_distances", "tdna_matrix", "tdna_matrix_compute",
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
-    "tdna_analyze", "tdna_tensor_counts", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_set_option", "tdna_last_tile_pass_ms",
+    "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_set_option", "tdna_last_tile_pass_ms",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -112,6 +112,7 @@ def load():
     L.tdna_time_matrix_kernel.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
     L.tdna_measure_int_peaks.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     L.tdna_tensor_counts.argtypes = [vp, vp]
+    L.tdna_last_count_kernel.argtypes = [vp]
     L.tdna_analyze.argtypes = [vp, ctypes.POINTER(Analysis)]
     L.tdna_best_match_seed.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
     L.tdna_best_match_part.argtypes = [vp, i32, i32, i32, ctypes.POINTER(StreamPart)]
@@ -278,6 +279,9 @@ class Alignment:
         if edges is not None:
             out["edge_i"], out["edge_j"], out["edge_d"] = out["edge_i"][:ne], out["edge_j"][:ne], out["edge_d"][:ne]
         return out
+
+    def last_count_kernel(self):
+        return int(self.L.tdna_last_count_kernel(self.h))
 
     def tensor_counts(self):
         """(shared, ident) of every pair from count kernel (b); pairs outside the triangle's tiles are -1."""

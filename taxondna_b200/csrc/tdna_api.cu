@@ -98,6 +98,7 @@ struct tdna_aln {
     double *d_ld = nullptr;
     long long list_cap = 0;
     long long last_ncand = 0, last_ncls[2] = {0, 0}, last_nedge = 0;
+    int last_kernel = 0;  // TDNA_KERNEL_* of the most recent streaming pass
     // count kernel (b): one-hot int8 operands (tdna_tc.cuh)
     uint8_t *d_tcA = nullptr, *d_tcB = nullptr;
     int tc_state = 0;  // 0 = not built, 1 = ready, -1 = not eligible
@@ -361,7 +362,10 @@ template <int KM> int launch_stream_km(tdna_aln *a, int part, int nparts, int ph
 // phases: bit 0 = diagonal blocks, bit 1 = the rest of the triangle
 int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
     tdna_ctx *c = a->ctx;
-    if (c->opt_count_kernel == TDNA_KERNEL_TENSOR) {  // AUTO stays on the popc kernel until the A/B says otherwise
+    // AUTO: kernel (b) wherever it is eligible -- it is ~3x faster than kernel (a) there (profiles/)
+    bool tensor = c->opt_count_kernel == TDNA_KERNEL_TENSOR || (c->opt_count_kernel == TDNA_KERNEL_AUTO && ensure_tc(a) == 1);
+    a->last_kernel = tensor ? TDNA_KERNEL_TENSOR : TDNA_KERNEL_POPC;
+    if (tensor) {
         if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p with ambiguity allowed, no IUPAC ambiguity letters, L < 4096");
         if (phases & 1) CU(cudaEventRecord(c->ev_k0, c->stream));
         for (int ph = 0; ph < 2; ph++)
@@ -394,8 +398,8 @@ static int tc_band() {  // row tiles per band of the bulk phase (TDNA_TC_BAND ov
 // Integers for the five-dimensional symbol code of tdna_tc.cuh: u = b*1 + a*e_x, v = d*1 + c*e_y with
 // a*c = -(W-1), a*d + b*c + 5*b*d = W, every entry (b, a+b, d, c+d) within int8, smallest W > L.
 bool find_code(int L, tc::EncodeValues &out, uint32_t &Wout) {
-    for (int W = L + 1; W < L + 4096; W++)
-        for (int aa = -127; aa <= 127; aa++) {
+    for (int W = 256; W <= 4096; W *= 2)  // a power of two: the epilogue decodes with a shift and a mask
+        for (int aa = -127; aa <= 127 && W > L; aa++) {
             if (aa == 0 || (W - 1) % (aa < 0 ? -aa : aa) != 0) continue;
             int cc = -(W - 1) / aa;
             if (cc < -127 || cc > 127) continue;
@@ -503,7 +507,8 @@ template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int 
     p.n = (int)a->n;
     p.min_overlap = a->min_overlap;
     p.W = a->tc_W;
-    p.Winv = ((1ull << 40) + a->tc_W - 1) / a->tc_W;
+    p.wshift = 0;
+    while ((1u << p.wshift) < a->tc_W) p.wshift++;
     p.nrt = (int)(round_up(a->n, tc::M) / tc::M);
     p.nct = (int)(round_up(a->n, tc::N) / tc::N);
     p.band = phase ? TC_BAND : 0;
@@ -1216,7 +1221,9 @@ int32_t tdna_analyze(tdna_aln *a, tdna_analysis *io) {
     CU(cudaSetDevice(c->device));
     if (io->want & (TDNA_WANT_BEST_MATCH | TDNA_WANT_INTRA | TDNA_WANT_INTER)) TRY(need_labels(a));
     bool whole = a->row_begin == 0 && a->row_end == a->n;
-    if (whole && c->opt_best_match_path != TDNA_PATH_DENSE && a->has_labels) {
+    // a materialised matrix of this very configuration is already resident (tdna_matrix_compute): sweeping it is cheaper than a pass
+    bool have_matrix = a->mat_valid && c->mat_owner == a && !(io->want & TDNA_WANT_BEST_MATCH) && c->opt_best_match_path != TDNA_PATH_STREAM;
+    if (whole && c->opt_best_match_path != TDNA_PATH_DENSE && a->has_labels && !have_matrix) {
         int rc = analyze_stream(a, io);
         if (rc != TDNA_E_TOO_LARGE || c->opt_best_match_path == TDNA_PATH_STREAM) return rc;
     }
@@ -1439,6 +1446,11 @@ int32_t tdna_tensor_counts(tdna_aln *a, tdna_counts *out) {
     }
     if (own) DFREE(dc);
     return rc;
+}
+
+int32_t tdna_last_count_kernel(tdna_aln *a) {
+    if (!a) return 0;
+    return a->last_kernel;
 }
 
 int32_t tdna_last_tile_pass_ms(tdna_ctx *c, float *ms) {

@@ -5,9 +5,10 @@
 //
 // One int32 accumulator per pair carries BOTH counts, from FIVE K-dimensions per site (one per valid symbol
 // A C G T '-'):   a-side (row x):  u = b*1 + a*e_x     b-side (column y):  v = d*1 + c*e_y     ('_', '?': zero vector)
-// with integers |entries| <= 127 chosen such that  a*c = -(W-1)  and  a*d + b*c + 5*b*d = W  for a W > L, so that
+// with integers |entries| <= 127 chosen such that  a*c = -(W-1)  and  a*d + b*c + 5*b*d = W  for a power of two W > L
+// (256, 1024 and 4096 have solutions), so that
 //     u . v = W - (W-1)*[x == y]   for valid x, y, 0 otherwise, and summed over the sites
-//     D(x,y) = W*shared - (W-1)*ident = ident + W*(shared - ident),   ident = D mod W, mism = D / W.
+//     D(x,y) = W*shared - (W-1)*ident = ident + W*(shared - ident),   ident = D & (W-1), mism = D >> log2 W.
 // shared = sites where both are a base or '-' (Sequence.getSharedLength, Sequence.java:1429-1455); ident = sites
 // where both are the same base or both '-' (Sequence.identical, :1262-1302, restricted to the clean alphabet).
 // D < 2^31 for L < 4096.  (The search for a, b, c, d is find_code() in tdna_api.cu.)
@@ -33,7 +34,7 @@ constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter
 constexpr int EPI_COLS = N / (EPI_WARPS / 4);      // columns per epilogue warp
 constexpr int THREADS = 64 + EPI_WARPS * 32;       // warp 0 producer, warp 1 MMA issuer, warps 2.. epilogue
 constexpr int DIMS = 5;                            // K-dimensions per site
-constexpr size_t SMEM = (size_t)NSTAGE * STAGE + 256 /*barriers*/ + 2 * N * 4 /*column thresholds*/ + 1024 /*alignment*/;
+constexpr size_t SMEM = (size_t)NSTAGE * STAGE + 256 /*barriers*/ + 16 * 64 * 4 /*column thresholds, per epilogue warp*/ + 1024 /*alignment*/;
 
 struct Params {
     const uint8_t *A;   // [a-panel][chunk][16 KB]
@@ -41,8 +42,8 @@ struct Params {
     int nchunks;        // K-chunks per row
     int n;
     int min_overlap;
-    uint32_t W;         // the accumulator's radix
-    uint64_t Winv;      // ceil(2^40 / W): D / W == (D * Winv) >> 40 for every D this kernel can produce
+    uint32_t W;         // the accumulator's radix, a power of two
+    int wshift;         // log2(W)
     int nrt;            // 128-row tiles
     int nct;            // 256-column tiles
     int band;           // 0: seed pass, tile t = (row tile t, column tile t / 2); else row tiles per band of the whole triangle
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
     uint64_t *tfull = empty + NSTAGE;   // [2] accumulator stage ready for the epilogue
     uint64_t *tempty = tfull + 2;       // [2] accumulator stage drained
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
-    uint32_t *col_thr = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * STAGE + 256);  // [2][N]
+    uint32_t *col_thr = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * STAGE + 256);  // [EPI_WARPS][EPI_COLS]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t my_tiles = (p.num_tiles > blockIdx.x) ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -256,29 +257,37 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
         __syncwarp();
     } else {
         // ===== epilogue warps: TMEM lane quarter = warp % 4, column group = (warp - 2) / 4 =====
-        // Sixteen warps (four per scheduler): the per-pair test is a dependent integer chain, so latency is hidden by
-        // warps, and the flags of 32 pairs are computed branch-free before the (rare) slow path is entered.
+        // Sixteen warps (four per scheduler): the per-pair test is a short dependent integer chain, so latency is hidden
+        // by warps; the flags of 32 pairs are computed branch-free (~9 instructions per pair) before the rare slow path.
         const int q = warp & 3, g = (warp - 2) >> 2;
-        const int et = tid - 64;  // 0..511 among the epilogue threads
+        uint32_t *my_thr = col_thr + (warp - 2) * EPI_COLS;  // this warp's column thresholds (warp-private: no CTA barrier)
         const StreamParams &sp = c_sp;
+        const uint32_t wm1 = p.W - 1u;
         int64_t k = 0;
         for (int64_t kk = 0; kk < my_tiles; kk++, k++) {
             int ti, tj;
             if (!tile_coords(p, p.prefix, blockIdx.x + kk * gridDim.x, ti, tj)) { k--; continue; }
             const int as = (int)(k & 1);
             const int i = ti * M + q * 32 + lane, j0 = tj * N;
-            uint32_t tfi = 0;
+            const bool seed = !COUNTS_MODE && (sp.want & TDNA_WANT_SEED) != 0;  // diagonal-block pre-pass: thresholds only
+            const bool want_bm = !COUNTS_MODE && (sp.want & TDNA_WANT_BEST_MATCH);
+            const uint32_t edge_tf = (!COUNTS_MODE && p.extras && (sp.want & TDNA_WANT_EDGES)) ? sp.edge_tfix : 0u;
+            const bool classes = !COUNTS_MODE && !seed && p.extras && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER));
+            uint32_t tf_row = edge_tf;
             if constexpr (!COUNTS_MODE) {
-                // column thresholds of this tile -> shared memory (read back as warp broadcasts)
-                if (et < N) col_thr[as * N + et] = (j0 + et < p.n && (sp.want & TDNA_WANT_BEST_MATCH)) ? __ldcg(sp.thr + j0 + et) : 0u;
-                tfi = (i < p.n && (sp.want & TDNA_WANT_BEST_MATCH)) ? __ldcg(sp.thr + i) : 0u;
-                asm volatile("bar.sync 1, 512;" ::: "memory");
+                __syncwarp();  // the previous tile's reads of my_thr are done
+#pragma unroll
+                for (int x = 0; x < EPI_COLS / 32; x++) {
+                    const int j = j0 + g * EPI_COLS + x * 32 + lane;
+                    my_thr[x * 32 + lane] = (want_bm && j < p.n) ? __ldcg(sp.thr + j) : 0u;
+                }
+                if (want_bm && i < p.n) tf_row = max(tf_row, __ldcg(sp.thr + i));
+                __syncwarp();
             }
+            // every pair of the tile is a real pair i < j < n: no range tests in the inner loop
+            const bool interior = (int64_t)tj * N > (int64_t)ti * M + M - 1 && (int64_t)tj * N + N <= p.n;
             mbar_wait(&tfull[as], (uint32_t)((k >> 1) & 1));
             fence_after();
-            const uint32_t edge_tf = (!COUNTS_MODE && p.extras && (sp.want & TDNA_WANT_EDGES)) ? sp.edge_tfix : 0u;
-            const bool seed = (sp.want & TDNA_WANT_SEED) != 0;  // diagonal-block pre-pass: thresholds only
-            const bool classes = !COUNTS_MODE && !seed && p.extras && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER));
             int bad_row = 0;
 #pragma unroll
             for (int cbi = 0; cbi < EPI_COLS / 32; cbi++) {
@@ -294,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                 if constexpr (COUNTS_MODE) {
 #pragma unroll
                     for (int e = 0; e < 32; e++) {
-                        const uint32_t mism = (uint32_t)(((uint64_t)v[e] * p.Winv) >> 40), ident = v[e] - mism * p.W;
+                        const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1;
                         if (i < p.n && jb + e < p.n) {
                             tdna_counts o = {(int)(ident + mism), (int)ident, 0, 0};
                             p.counts[(size_t)i * p.n + jb + e] = o;
@@ -302,22 +311,38 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     }
                 } else {
                     uint32_t pmask = 0, bmask = 0, smask = 0;  // slow path wanted / pair below minOverlap / valid self pair
-                    const uint4 *ct4 = reinterpret_cast<const uint4 *>(col_thr + as * N + cb * 32);
+                    const uint4 *ct4 = reinterpret_cast<const uint4 *>(my_thr + cbi * 32);
+                    if (interior) {
 #pragma unroll
-                    for (int e4 = 0; e4 < 8; e4++) {
-                        const uint4 ct = ct4[e4];
-                        const uint32_t cts[4] = {ct.x, ct.y, ct.z, ct.w};
+                        for (int e4 = 0; e4 < 8; e4++) {
+                            const uint4 ct = ct4[e4];
+                            const uint32_t cts[4] = {ct.x, ct.y, ct.z, ct.w};
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int e = e4 * 4 + u, j = jb + e;
-                            const uint32_t mism = (uint32_t)(((uint64_t)v[e] * p.Winv) >> 40), s = v[e] - mism * (p.W - 1u);  // ident + mism
-                            const bool inr = (j > i) & (j < p.n);
-                            const bool ok = (int)s >= p.min_overlap;
-                            const uint32_t lhs = mism << 16;
-                            const bool pass = (lhs <= tfi * s) | (lhs <= cts[u] * s) | (lhs <= edge_tf * s);
-                            pmask |= (uint32_t)(inr & ok & pass) << e;
-                            bmask |= (uint32_t)(inr & !ok) << e;
-                            smask |= (uint32_t)((j == i) & (i < p.n) & ok) << e;
+                            for (int u = 0; u < 4; u++) {
+                                const int e = e4 * 4 + u;
+                                const uint32_t mism = v[e] >> p.wshift, s = v[e] - mism * wm1;  // s = ident + mism
+                                const bool ok = (int)s >= p.min_overlap;
+                                const bool pass = (mism << 16) <= max(tf_row, cts[u]) * s;
+                                if (ok && pass) pmask |= 1u << e;
+                                if (!ok) bmask |= 1u << e;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int e4 = 0; e4 < 8; e4++) {
+                            const uint4 ct = ct4[e4];
+                            const uint32_t cts[4] = {ct.x, ct.y, ct.z, ct.w};
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int e = e4 * 4 + u, j = jb + e;
+                                const uint32_t mism = v[e] >> p.wshift, s = v[e] - mism * wm1;
+                                const bool inr = (j > i) & (j < p.n);
+                                const bool ok = (int)s >= p.min_overlap;
+                                const bool pass = (mism << 16) <= max(tf_row, cts[u]) * s;
+                                if (inr && ok && pass) pmask |= 1u << e;
+                                if (inr && !ok) bmask |= 1u << e;
+                                if (j == i && i < p.n && ok) smask |= 1u << e;
+                            }
                         }
                     }
                     if (smask && !seed) atomicOr(sp.flags + i, TDNA_ROW_SELF_VALID);
@@ -331,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
 #pragma unroll
                         for (int e = 0; e < 32; e++)
                             if (pmask & (1u << e)) {
-                                const uint32_t mism = (uint32_t)(((uint64_t)v[e] * p.Winv) >> 40), ident = v[e] - mism * p.W, s = ident + mism;
+                                const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1, s = ident + mism;
                                 stream_emit<KM_P_AMBIG>(i, jb + e, ident | (s << 16), 0u, mism << 16, s, p.min_overlap);
                             }
                     }
@@ -339,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
 #pragma unroll
                         for (int e = 0; e < 32; e++) {
                             const int j = jb + e;
-                            const uint32_t mism = (uint32_t)(((uint64_t)v[e] * p.Winv) >> 40), ident = v[e] - mism * p.W, s = ident + mism;
+                            const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1, s = ident + mism;
                             if (j <= i || j >= p.n || (int)s < p.min_overlap) continue;
                             const bool hit = ((sp.want & TDNA_WANT_INTRA) && sp.species[i] == sp.species[j]) ||
                                              ((sp.want & TDNA_WANT_INTER) && sp.genus[i] == sp.genus[j]);
@@ -350,7 +375,6 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             }
             if constexpr (!COUNTS_MODE) {
                 if (bad_row) atomicAdd(sp.inval + i, bad_row);
-                asm volatile("bar.sync 1, 512;" ::: "memory");  // col_thr[as] is rewritten two tiles later: keep the warps within one tile of each other
             }
         }
     }
