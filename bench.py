@@ -36,6 +36,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_OUT = sys.stdout
+
 WORKLOADS = {
     "C2": dict(config="C2", mode=0, kind="matrix+summary", desc="2,185 x 2,664 bp synthetic multi-gene alignment, uncorrected p: full pairwise matrix + Pairwise Summary classes"),
     "C3": dict(config="C3", mode=1, kind="bestmatch+intra", desc="8,000 x 658 bp synthetic COI, K2P: Best Close Match + intraspecific distances for the 95th-percentile threshold"),
@@ -164,7 +166,7 @@ def run_reference(args):
                          "sample": "first %d query rows x all later columns per step (%d pairs/step), C restatement of Sequence.getPairwiseNoBuffer (no JVM in image), %d pthreads" % (rows, pairs // max(1, args.steps), threads)},
         "e2e": {"value": v, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 class _DevBuf:
@@ -194,6 +196,11 @@ def exchange_parts(torch, dist, dev, part, n, world):
 
 def main():
     args = parse()
+    # the contract is ONE JSON line on stdout: keep the real stdout for it and send everything else
+    # (NCCL's version banner, library chatter) to stderr
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -485,7 +492,7 @@ def main():
         }
         if cand_counts:
             line["config"]["candidates_per_rank_per_step"] = int(np.mean(cand_counts))
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     aln.close()
     ctx.close()
     if world > 1:

@@ -525,6 +525,7 @@ template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int 
         int v = e ? atoi(e) : (a->tc_maps ? 0 : 16384);  // default: tiled TMA when the tensor maps exist
         p.piece = (v >= 1024 && 16384 % v == 0) ? v : (a->tc_maps ? 0 : 16384);
     }
+    if (const char *e = getenv("TDNA_TC_HINTS")) p.hints = atoi(e);
     int64_t grid = p.num_tiles < c->sm_count ? p.num_tiles : c->sm_count;
     if (const char *e = getenv("TDNA_TC_GRID")) { int v = atoi(e); if (v >= 1 && v < grid) grid = v; }
     if (grid < 1) return TDNA_OK;

@@ -52,6 +52,7 @@ struct Params {
     int64_t num_tiles, t_offset, t_stride;
     tdna_counts *counts;    // verification mode: n x n counts (row-major), else null
     int extras;             // stream mode: classes / edges wanted (c_sp.want beyond Best Match)
+    int hints;              // L2 cache-policy hints on the operand loads (experiments: TDNA_TC_HINTS)
     int piece;              // bytes per 1-D bulk copy (divides 16 KB); 0 = tensor-map (2-D tiled TMA) loads
 };
 
@@ -170,6 +171,14 @@ __device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *m
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                  : "memory");
 }
+// same with an L2 cache-policy hint (the a-panels of a band are re-read for every column tile: keep them)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) { mbar_wait_backoff(bar, parity); }
 
 // ---- the tile kernel ---------------------------------------------------------------------------
@@ -216,8 +225,13 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     uint8_t *sa = smem + (size_t)slot * STAGE, *sb = sa + A_STAGE;
                     mbar_expect_tx(&full[slot], STAGE);
                     if (p.piece == 0) {  // one block = 16 (a) / 32 (b) rows of 1 KB
-                        tma_load_2d(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * (A_STAGE / 1024)), &full[slot]);
-                        tma_load_2d(sb, &mapB, 0, (int)(((int64_t)tj * p.nchunks + c) * (B_STAGE / 1024)), &full[slot]);
+                        if (p.hints) {
+                            tma_load_2d_hint(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * (A_STAGE / 1024)), &full[slot], p.hints == 2 ? L2_EVICT_NORMAL : L2_EVICT_LAST);
+                            tma_load_2d_hint(sb, &mapB, 0, (int)(((int64_t)tj * p.nchunks + c) * (B_STAGE / 1024)), &full[slot], p.hints == 3 ? L2_EVICT_FIRST : (p.hints == 2 ? L2_EVICT_LAST : L2_EVICT_NORMAL));
+                        } else {
+                            tma_load_2d(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * (A_STAGE / 1024)), &full[slot]);
+                            tma_load_2d(sb, &mapB, 0, (int)(((int64_t)tj * p.nchunks + c) * (B_STAGE / 1024)), &full[slot]);
+                        }
                         continue;
                     }
                     for (int o = 0; o < A_STAGE; o += p.piece) bulk_g2s(sa + o, ga + (size_t)c * A_STAGE + o, p.piece, &full[slot]);
