@@ -104,8 +104,9 @@ struct tdna_aln {
     int tc_state = 0;  // 0 = not built, 1 = ready, -1 = not eligible
     int tc_nchunks = 0;
     uint32_t tc_W = 0;
-    CUtensorMap tc_mapA, tc_mapB;  // [.., 256 x uint32] views of d_tcA / d_tcB, boxes of one operand block
+    CUtensorMap tc_mapA, tc_mapB, tc_mapBh;  // [.., 256 x uint32] views of d_tcA / d_tcB, boxes of one operand block (Bh: half a b-block)
     bool tc_maps = false;
+    int tc_inner = 256;
     int64_t *d_tcprefix[2] = {nullptr, nullptr};
     int64_t tcprefix_tiles[2] = {0, 0};
 };
@@ -376,6 +377,19 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
         if (phases & 2) {
             CU(cudaEventRecord(c->ev_k1, c->stream));
             c->ev_valid = true;
+            // the queued pairs -> minima -> final thresholds -> candidate records
+            TRY(set_stream_symbol(a, false));
+            int wshift = 0;
+            while ((1u << wshift) < a->tc_W) wshift++;
+            unsigned grid = (unsigned)c->sm_count * 8;
+            if (a->sp.want & TDNA_WANT_BEST_MATCH) {
+                tc::resolve_min_kernel<<<grid, 256, 0, c->stream>>>(a->sp, wshift, a->tc_W - 1u, a->min_overlap);
+                stream_thr_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n);
+                c->launches += 2;
+            }
+            tc::resolve_emit_kernel<<<grid, 256, 0, c->stream>>>(a->sp, wshift, a->tc_W - 1u, a->min_overlap);
+            c->launches++;
+            CU(cudaGetLastError());
         }
         return TDNA_OK;
     }
@@ -477,14 +491,20 @@ int ensure_tc(tdna_aln *a) {
         a->tc_maps = false;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr) == cudaSuccess && fp && qr == cudaDriverEntryPointSuccess) {
             encode_fn enc = reinterpret_cast<encode_fn>(fp);
-            cuuint64_t dimsA[2] = {256, (cuuint64_t)((size_t)npa * nchunks * tc::KB / 1024)}, dimsB[2] = {256, (cuuint64_t)((size_t)npb * nchunks * tc::KB / 1024)};
-            cuuint64_t strides[1] = {1024};
-            cuuint32_t boxA[2] = {256, tc::A_STAGE / 1024}, boxB[2] = {256, tc::B_STAGE / 1024}, es[2] = {1, 1};
+            int inner = 256;  // uint32 elements per view row (TDNA_TC_INNER: experiments)
+            if (const char *e = getenv("TDNA_TC_INNER")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) inner = v; }
+            a->tc_inner = inner;
+            cuuint64_t rowb = (cuuint64_t)inner * 4;
+            cuuint64_t dimsA[2] = {(cuuint64_t)inner, (cuuint64_t)((size_t)npa * nchunks * tc::KB / rowb)}, dimsB[2] = {(cuuint64_t)inner, (cuuint64_t)((size_t)npb * nchunks * tc::KB / rowb)};
+            cuuint64_t strides[1] = {rowb};
+            cuuint32_t boxA[2] = {(cuuint32_t)inner, (cuuint32_t)(tc::A_STAGE / rowb)}, boxB[2] = {(cuuint32_t)inner, (cuuint32_t)(tc::B_STAGE / rowb)}, es[2] = {1, 1};
             CUresult r1 = enc(&a->tc_mapA, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, a->d_tcA, dimsA, strides, boxA, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             CUresult r2 = enc(&a->tc_mapB, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, a->d_tcB, dimsB, strides, boxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            a->tc_maps = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS);
+            CUresult r3 = enc(&a->tc_mapBh, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, a->d_tcB, dimsB, strides, boxA, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            a->tc_maps = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS && r3 == CUDA_SUCCESS);
         }
         cudaGetLastError();
     }
@@ -492,9 +512,9 @@ int ensure_tc(tdna_aln *a) {
     return 1;
 }
 
-template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts) {
+template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts) {
     tdna_ctx *c = a->ctx;
-    auto kern = tc::tile_kernel<COUNTS_MODE>;
+    auto kern = tc::tile_kernel<COUNTS_MODE, CL>;
     static bool attr_set = false;
     if (!attr_set) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
@@ -516,7 +536,8 @@ template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int 
     p.prefix = a->d_tcprefix[1];
     p.t_offset = part;
     p.t_stride = nparts;
-    int64_t total = a->tcprefix_tiles[phase];
+    int64_t total = a->tcprefix_tiles[phase];   // slots
+    if (CL == 2) total = (total + 1) / 2;         // pairs of slots
     p.num_tiles = total > part ? (total - part + nparts - 1) / nparts : 0;
     p.counts = counts;
     p.extras = a->sp.want != TDNA_WANT_BEST_MATCH;
@@ -526,13 +547,37 @@ template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int 
         p.piece = (v >= 1024 && 16384 % v == 0) ? v : (a->tc_maps ? 0 : 16384);
     }
     if (const char *e = getenv("TDNA_TC_HINTS")) p.hints = atoi(e);
-    int64_t grid = p.num_tiles < c->sm_count ? p.num_tiles : c->sm_count;
-    if (const char *e = getenv("TDNA_TC_GRID")) { int v = atoi(e); if (v >= 1 && v < grid) grid = v; }
+    p.a_rows = tc::A_STAGE / (a->tc_inner * 4);
+    p.b_rows = tc::B_STAGE / (a->tc_inner * 4);
+    int64_t units = CL == 2 ? c->sm_count / 2 : c->sm_count;
+    if (const char *e = getenv("TDNA_TC_GRID")) { int v = atoi(e); if (v >= 1 && v < units) units = v; }
+    int64_t grid = (p.num_tiles < units ? p.num_tiles : units) * CL;
     if (grid < 1) return TDNA_OK;
-    kern<<<(unsigned)grid, tc::THREADS, tc::SMEM, c->stream>>>(a->tc_mapA, a->tc_mapB, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = tc::SMEM;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, kern, a->tc_mapA, a->tc_mapB, a->tc_mapBh, p));
     c->launches++;
     CU(cudaGetLastError());
     return TDNA_OK;
+}
+
+// pairs of CTAs sharing the b-panel by TMA multicast need the tensor maps; TDNA_TC_CLUSTER=1 switches them off (experiments)
+template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts) {
+    const char *e = getenv("TDNA_TC_CLUSTER");
+    int cl = e ? atoi(e) : 2;
+    if (!a->tc_maps || (TC_BAND & 1)) cl = 1;
+    if (cl == 2) return launch_tc_cl<COUNTS_MODE, 2>(a, phase, part, nparts, counts);
+    return launch_tc_cl<COUNTS_MODE, 1>(a, phase, part, nparts, counts);
 }
 
 int ensure_packed(tdna_aln *a) {
@@ -733,7 +778,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     cudaSetDevice(c->device);
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
-                    a->d_needc, a->d_panel_range, a->d_tcA, a->d_tcB, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
+                    a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_cursor, a->d_lj, a->d_ld};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
@@ -960,11 +1005,16 @@ static int ensure_stream_state(tdna_aln *a) {
     CU(DMALLOC(&sp.cq, (size_t)cap * 4));
     CU(DMALLOC(&sp.cj, (size_t)cap * 4));
     CU(DMALLOC(&sp.cd, (size_t)cap * 8));
-    CU(DMALLOC(&a->d_stream_u64, 64));  // ncand, overflow, ncls[2], nedge
+    CU(DMALLOC(&sp.qi, (size_t)cap * 4));
+    CU(DMALLOC(&sp.qj, (size_t)cap * 4));
+    CU(DMALLOC(&sp.qv, (size_t)cap * 4));
+    sp.qcap = cap;
+    CU(DMALLOC(&a->d_stream_u64, 64));  // ncand, overflow, ncls[2], nedge, qn
     sp.ncand = reinterpret_cast<unsigned long long *>(a->d_stream_u64);
     sp.overflow = reinterpret_cast<int *>(reinterpret_cast<char *>(a->d_stream_u64) + 8);
     sp.ncls = sp.ncand + 2;
     sp.nedge = sp.ncand + 4;
+    sp.qn = sp.ncand + 5;
     sp.want = TDNA_WANT_BEST_MATCH;
     sp.cap = cap;
     sp.species = a->d_species;

@@ -144,6 +144,12 @@ struct StreamParams {
     double *ed;
     long long edge_cap;
     unsigned long long *nedge;
+    // count kernel (b) defers its slow path: the epilogue only queues (row, column, raw accumulator) of the pairs that pass
+    // the seeded thresholds; tc::resolve_*_kernel turn the queue into candidate records after the pass
+    int32_t *qi, *qj;
+    uint32_t *qv;
+    unsigned long long *qn;
+    long long qcap;
 };
 __constant__ StreamParams c_sp;
 
@@ -295,6 +301,81 @@ template <int KM> __device__ __noinline__ void stream_emit(int i, int j, uint32_
     }
     stream_emit_side(i, j, d, lhs, den);
     stream_emit_side(j, i, d, lhs, den);
+}
+
+// The same slow path for callers that enter it CONVERGED (every lane of the warp brings one pair, `active` lanes
+// have one): both sides of the pair are handled together and independent memory operations are issued back to back,
+// so a warp pays ~3 memory latencies per batch of up to 32 candidates instead of ~6 per candidate.
+template <int KM> __device__ __forceinline__ void stream_emit_converged(bool active, int i, int j, uint32_t a0, uint32_t a1, uint32_t lhs, uint32_t den,
+                                                                      int min_overlap) {
+    const StreamParams &sp = c_sp;
+    const bool seed = (sp.want & TDNA_WANT_SEED) != 0, want_bm = (sp.want & TDNA_WANT_BEST_MATCH) != 0;
+    double d = 0.0;
+    uint32_t fri = 0, frj = 0;
+    int spi = -1, spj = -1;
+    if (active) {  // loads first, the fp64 division overlaps them
+        if (want_bm) {
+            fri = *reinterpret_cast<volatile uint32_t *>(sp.thr + i);
+            frj = *reinterpret_cast<volatile uint32_t *>(sp.thr + j);
+            spi = __ldg(sp.species + i);
+            spj = __ldg(sp.species + j);
+        }
+        Counts cn = unpack_counts<KM>(a0, a1);
+        d = distance_from_counts<KM>(cn, min_overlap);
+        if ((sp.want & TDNA_WANT_EDGES) && d >= 0 && d <= sp.edge_t) {
+            const unsigned long long pos = atomicAdd(sp.nedge, 1ull);
+            if (sp.ei && (long long)pos < sp.edge_cap) { sp.ei[pos] = i; sp.ej[pos] = j; sp.ed[pos] = d; }
+        }
+        if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) {
+            if (!seed) { atomicOr(sp.flags + i, TDNA_ROW_NONFINITE); atomicOr(sp.flags + j, TDNA_ROW_NONFINITE); }
+            active = false;
+        }
+    }
+    const bool ei = active && want_bm && lhs <= fri * den, ej = active && want_bm && lhs <= frj * den;
+    if (!(ei || ej)) return;
+    if (!seed) {
+        const unsigned long long pos = atomicAdd(sp.ncand, (unsigned long long)(ei + ej));
+        if ((long long)(pos + ei + ej) > sp.cap) { *sp.overflow = 1; }
+        else {
+            unsigned long long w = pos;
+            if (ei) { sp.cq[w] = i; sp.cj[w] = j; sp.cd[w] = d; atomicAdd(sp.cnt + i, 1); w++; }
+            if (ej) { sp.cq[w] = j; sp.cj[w] = i; sp.cd[w] = d; atomicAdd(sp.cnt + j, 1); }
+        }
+    }
+    // minima (no return value: RED) and the thresholds derived from them
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+    const bool ui = ei && spj >= 0, uj = ej && spi >= 0;  // unnamed columns bound nothing
+    if (ui) { if (spj == spi) atomicMin(sp.mC + i, bits); atomicMin(sp.mPar + 2 * (int64_t)i + (spj & 1), bits); }
+    if (uj) { if (spi == spj) atomicMin(sp.mC + j, bits); atomicMin(sp.mPar + 2 * (int64_t)j + (spi & 1), bits); }
+    unsigned long long m_i[3] = {0, 0, 0}, m_j[3] = {0, 0, 0};
+    if (ui) {
+        m_i[0] = *reinterpret_cast<volatile unsigned long long *>(sp.mC + i);
+        m_i[1] = *reinterpret_cast<volatile unsigned long long *>(sp.mPar + 2 * (int64_t)i);
+        m_i[2] = *reinterpret_cast<volatile unsigned long long *>(sp.mPar + 2 * (int64_t)i + 1);
+    }
+    if (uj) {
+        m_j[0] = *reinterpret_cast<volatile unsigned long long *>(sp.mC + j);
+        m_j[1] = *reinterpret_cast<volatile unsigned long long *>(sp.mPar + 2 * (int64_t)j);
+        m_j[2] = *reinterpret_cast<volatile unsigned long long *>(sp.mPar + 2 * (int64_t)j + 1);
+    }
+    if (ui) {  // fold the own value in: the RED above need not be visible to the loads yet
+        if (spj == spi) m_i[0] = min(m_i[0], bits);
+        m_i[1 + (spj & 1)] = min(m_i[1 + (spj & 1)], bits);
+        const unsigned long long m = max(m_i[0], max(m_i[1], m_i[2]));
+        if (m < TDNA_INF_BITS) {
+            const double T = __longlong_as_double((long long)m) + 2e-5;
+            if (T < 1.0) atomicMin(sp.thr + i, (uint32_t)(T * 65536.0) + 2u);
+        }
+    }
+    if (uj) {
+        if (spi == spj) m_j[0] = min(m_j[0], bits);
+        m_j[1 + (spi & 1)] = min(m_j[1 + (spi & 1)], bits);
+        const unsigned long long m = max(m_j[0], max(m_j[1], m_j[2]));
+        if (m < TDNA_INF_BITS) {
+            const double T = __longlong_as_double((long long)m) + 2e-5;
+            if (T < 1.0) atomicMin(sp.thr + j, (uint32_t)(T * 65536.0) + 2u);
+        }
+    }
 }
 
 // PairwiseDistribution classes of one valid pair i < j (PairwiseDistribution.java:161-203): pushes (float)d
@@ -900,7 +981,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) row_summary_kernel(const double
 // needc[q] != 0: q is named and another row of its species exists (labels only; set by the host side)
 __global__ void __launch_bounds__(256) stream_init_kernel(StreamParams sp, int64_t n, const uint8_t *__restrict__ needc) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q == 0) { *sp.ncand = 0ull; *sp.overflow = 0; sp.ncls[0] = 0ull; sp.ncls[1] = 0ull; *sp.nedge = 0ull; }
+    if (q == 0) { *sp.ncand = 0ull; *sp.overflow = 0; sp.ncls[0] = 0ull; sp.ncls[1] = 0ull; *sp.nedge = 0ull; *sp.qn = 0ull; }
     if (q >= n) return;
     sp.thr[q] = TDNA_THR_ALL;
     sp.mC[q] = needc[q] ? TDNA_INF_BITS : 0ull;

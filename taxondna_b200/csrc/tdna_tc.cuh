@@ -27,7 +27,7 @@ namespace tdna {
 namespace tc {
 
 constexpr int M = 128, N = 256, KB = 128;          // tile rows, tile columns, K bytes per row per stage
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 4;                          // 4 x 48 KB (9 x 24 KB measured slower: small TMA boxes)
 constexpr int A_STAGE = M * KB, B_STAGE = N * KB;  // 16 KB + 32 KB
 constexpr int STAGE = A_STAGE + B_STAGE;
 constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter
@@ -52,6 +52,7 @@ struct Params {
     int64_t num_tiles, t_offset, t_stride;
     tdna_counts *counts;    // verification mode: n x n counts (row-major), else null
     int extras;             // stream mode: classes / edges wanted (c_sp.want beyond Best Match)
+    int a_rows, b_rows;     // rows of the tensor-map view per a / b stage block (view row = inner box width)
     int hints;              // L2 cache-policy hints on the operand loads (experiments: TDNA_TC_HINTS)
     int piece;              // bytes per 1-D bulk copy (divides 16 KB); 0 = tensor-map (2-D tiled TMA) loads
 };
@@ -59,8 +60,7 @@ struct Params {
 // Tile slot -> (row tile, column tile); false = an empty slot.  The bulk phase walks BANDS of `band` row tiles,
 // column tile outer / row tile inner, so that the ~148 tiles in flight at any time share ~16 a-panels and ~9
 // b-panels: every operand block is fetched from HBM about once per band and otherwise hits L2.
-__device__ __forceinline__ bool tile_coords(const Params &p, const int64_t *prefix, int64_t t, int &ti, int &tj) {
-    t = p.t_offset + t * p.t_stride;
+__device__ __forceinline__ bool slot_coords(const Params &p, const int64_t *prefix, int64_t t, int &ti, int &tj) {
     if (p.band == 0) {
         ti = (int)t;
         tj = ti >> 1;
@@ -76,6 +76,20 @@ __device__ __forceinline__ bool tile_coords(const Params &p, const int64_t *pref
     ti = ti0 + (int)(r % p.band);
     tj = (ti0 >> 1) + (int)(r / p.band);
     return ti < p.nrt && tj < p.nct && tj >= (ti >> 1);
+}
+
+// k-th work item of this CTA.  CL = 1: slot t_offset + (blockIdx.x + k * gridDim.x) * t_stride.  CL = 2: the cluster takes the PAIR
+// of slots (2u, 2u + 1), u = t_offset + (cluster id + k * clusters) * t_stride -- same column tile, adjacent row tiles -- and this
+// CTA the one of its cluster rank; the pair is as valid as its even slot (an odd row tile past the end reads zero-filled operands).
+template <int CL> __device__ __forceinline__ bool my_tile(const Params &p, int64_t k, uint32_t rank, int &ti, int &tj) {
+    if constexpr (CL == 1) {
+        return slot_coords(p, p.prefix, p.t_offset + ((int64_t)blockIdx.x + k * gridDim.x) * p.t_stride, ti, tj);
+    } else {
+        const int64_t u = p.t_offset + ((int64_t)(blockIdx.x >> 1) + k * (gridDim.x >> 1)) * p.t_stride;
+        const bool ok = slot_coords(p, p.prefix, 2 * u, ti, tj);
+        ti += (int)rank;
+        return ok;
+    }
 }
 
 // ---- operand encoding -------------------------------------------------------------------------
@@ -182,8 +196,24 @@ __device__ __forceinline__ void tma_load_2d_hint(void *dst_smem, const CUtensorM
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) { mbar_wait_backoff(bar, parity); }
 
 // ---- the tile kernel ---------------------------------------------------------------------------
-template <bool COUNTS_MODE>
-__global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p) {
+__device__ __forceinline__ void tma_load_2d_mc(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t *bar, uint16_t cta_mask) {  // arrive on the same barrier of every CTA in the mask
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// CL = 2: clusters of two CTAs on the same column tile; each loads one half of the b-panel stage and multicasts it to both,
+// so the pair reads 2 x 16 KB (a) + 32 KB (b) per K-chunk from L2 instead of 2 x 48 KB.
+template <bool COUNTS_MODE, int CL>
+__global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                          const __grid_constant__ CUtensorMap mapBh, Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)NSTAGE * STAGE);
@@ -194,10 +224,13 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
     uint32_t *col_thr = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * STAGE + 256);  // [EPI_WARPS][EPI_COLS]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t my_tiles = (p.num_tiles > blockIdx.x) ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    uint32_t rank = 0;
+    if constexpr (CL == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int64_t units = CL == 1 ? gridDim.x : (gridDim.x >> 1), first = CL == 1 ? blockIdx.x : (blockIdx.x >> 1);
+    const int64_t my_tiles = (p.num_tiles > first) ? (p.num_tiles - first + units - 1) / units : 0;  // tiles (CL = 1) or tile pairs (CL = 2)
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -208,6 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
     fence_before();
     __syncthreads();
     fence_after();
+    if constexpr (CL == 2) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
 
     if (warp == 0) {
@@ -216,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             int64_t it = 0;
             for (int64_t k = 0; k < my_tiles; k++) {
                 int ti, tj;
-                if (!tile_coords(p, p.prefix, blockIdx.x + k * gridDim.x, ti, tj)) continue;
+                if (!my_tile<CL>(p, k, rank, ti, tj)) continue;
                 const uint8_t *ga = p.A + (size_t)ti * p.nchunks * A_STAGE;
                 const uint8_t *gb = p.B + (size_t)tj * p.nchunks * B_STAGE;
                 for (int c = 0; c < p.nchunks; c++, it++) {
@@ -224,13 +258,19 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     if (it >= NSTAGE) mbar_wait(&empty[slot], (uint32_t)(((it / NSTAGE) - 1) & 1));  // the ring IS the bottleneck here: no back-off
                     uint8_t *sa = smem + (size_t)slot * STAGE, *sb = sa + A_STAGE;
                     mbar_expect_tx(&full[slot], STAGE);
+                    if constexpr (CL == 2) {  // own a-panel; own half of the b-panel stage to both CTAs (same offsets, same barrier)
+                        tma_load_2d(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * p.a_rows), &full[slot]);
+                        tma_load_2d_mc(sb + rank * (B_STAGE / 2), &mapBh, 0, (int)(((int64_t)tj * p.nchunks + c) * p.b_rows + rank * (p.b_rows / 2)),
+                                       &full[slot], (uint16_t)3);
+                        continue;
+                    }
                     if (p.piece == 0) {  // one block = 16 (a) / 32 (b) rows of 1 KB
                         if (p.hints) {
-                            tma_load_2d_hint(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * (A_STAGE / 1024)), &full[slot], p.hints == 2 ? L2_EVICT_NORMAL : L2_EVICT_LAST);
-                            tma_load_2d_hint(sb, &mapB, 0, (int)(((int64_t)tj * p.nchunks + c) * (B_STAGE / 1024)), &full[slot], p.hints == 3 ? L2_EVICT_FIRST : (p.hints == 2 ? L2_EVICT_LAST : L2_EVICT_NORMAL));
+                            tma_load_2d_hint(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * p.a_rows), &full[slot], p.hints == 2 ? L2_EVICT_NORMAL : L2_EVICT_LAST);
+                            tma_load_2d_hint(sb, &mapB, 0, (int)(((int64_t)tj * p.nchunks + c) * p.b_rows), &full[slot], p.hints == 3 ? L2_EVICT_FIRST : (p.hints == 2 ? L2_EVICT_LAST : L2_EVICT_NORMAL));
                         } else {
-                            tma_load_2d(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * (A_STAGE / 1024)), &full[slot]);
-                            tma_load_2d(sb, &mapB, 0, (int)(((int64_t)tj * p.nchunks + c) * (B_STAGE / 1024)), &full[slot]);
+                            tma_load_2d(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * p.a_rows), &full[slot]);
+                            tma_load_2d(sb, &mapB, 0, (int)(((int64_t)tj * p.nchunks + c) * p.b_rows), &full[slot]);
                         }
                         continue;
                     }
@@ -246,7 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             int64_t it = 0, k = 0;  // k counts the non-empty tiles of this CTA
             for (int64_t kk = 0; kk < my_tiles; kk++) {
                 int ti_, tj_;
-                if (!tile_coords(p, p.prefix, blockIdx.x + kk * gridDim.x, ti_, tj_)) continue;
+                if (!my_tile<CL>(p, kk, rank, ti_, tj_)) continue;
                 const int as = (int)(k & 1);
                 if (k >= 2) mbar_wait_sleep(&tempty[as], (uint32_t)(((k >> 1) - 1) & 1));
                 fence_after();
@@ -262,7 +302,8 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         const uint64_t bd = smem_desc(sb + s * 2 * (N * 16), N * 16, 128);
                         mma_i8(d_tmem, ad, bd, (c | s) != 0 ? 1u : 0u);
                     }
-                    mma_commit(&empty[slot]);  // the stage may be refilled once these MMAs have read it
+                    if constexpr (CL == 2) mma_commit_mc(&empty[slot], (uint16_t)3);  // both CTAs write into this stage: tell both
+                    else mma_commit(&empty[slot]);  // the stage may be refilled once these MMAs have read it
                 }
                 mma_commit(&tfull[as]);        // accumulator complete
                 k++;
@@ -280,7 +321,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
         int64_t k = 0;
         for (int64_t kk = 0; kk < my_tiles; kk++, k++) {
             int ti, tj;
-            if (!tile_coords(p, p.prefix, blockIdx.x + kk * gridDim.x, ti, tj)) { k--; continue; }
+            if (!my_tile<CL>(p, kk, rank, ti, tj)) { k--; continue; }
             const int as = (int)(k & 1);
             const int i = ti * M + q * 32 + lane, j0 = tj * N;
             const bool seed = !COUNTS_MODE && (sp.want & TDNA_WANT_SEED) != 0;  // diagonal-block pre-pass: thresholds only
@@ -366,13 +407,38 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         for (int e = 0; e < 32; e++)
                             if (bmask & (1u << e)) atomicAdd(sp.inval + jb + e, 1);
                     }
-                    if (pmask) {
+                    if (!seed) {
+                        // bulk pass: no fp64, no threshold traffic here -- the pairs that pass the seeded thresholds are queued
+                        // (one warp-aggregated atomic) and resolved after the pass (resolve_*_kernel)
+                        if (__any_sync(0xffffffffu, pmask != 0)) {
+                            const int cnt = __popc(pmask);
+                            int incl = cnt;
 #pragma unroll
-                        for (int e = 0; e < 32; e++)
-                            if (pmask & (1u << e)) {
-                                const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1, s = ident + mism;
-                                stream_emit<KM_P_AMBIG>(i, jb + e, ident | (s << 16), 0u, mism << 16, s, p.min_overlap);
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                                if (lane >= o) incl += t;
                             }
+                            const int total = __shfl_sync(0xffffffffu, incl, 31);
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(sp.qn, (unsigned long long)total);
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            unsigned long long w = base + (unsigned long long)(incl - cnt);
+                            if ((long long)(base + total) <= sp.qcap) {
+#pragma unroll
+                                for (int e = 0; e < 32; e++)
+                                    if (pmask & (1u << e)) { sp.qi[w] = i; sp.qj[w] = jb + e; sp.qv[w] = v[e]; w++; }
+                            } else if (lane == 0) *sp.overflow = 1;
+                        }
+                        pmask = 0;
+                    }
+                    while (__any_sync(0xffffffffu, pmask != 0)) {  // seed pass, converged: every lane brings its next candidate
+                        const int e = pmask ? __ffs((int)pmask) - 1 : -1;
+                        pmask &= pmask - 1u;
+                        uint32_t val = 0;
+#pragma unroll
+                        for (int x = 0; x < 32; x++) val = (x == e) ? v[x] : val;
+                        const uint32_t mism = val >> p.wshift, ident = val & wm1, s = ident + mism;
+                        stream_emit_converged<KM_P_AMBIG>(e >= 0, i, jb + e, ident | (s << 16), 0u, mism << 16, s, p.min_overlap);
                     }
                     if (classes) {
 #pragma unroll
@@ -394,7 +460,59 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
     }
     fence_before();
     __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still write into it
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// ---- after the bulk pass: the queue -> minima -> final thresholds -> candidate records --------------------------
+// every queued pair is a valid pair i < j; value = raw accumulator
+__device__ __forceinline__ double queued_distance(uint32_t val, int wshift, uint32_t wm1, int min_overlap, uint32_t &lhs, uint32_t &den) {
+    const uint32_t mism = val >> wshift, ident = val & wm1, s = ident + mism;
+    lhs = mism << 16;
+    den = s;
+    Counts cn = {(int)s, (int)ident, 0, 0};
+    return distance_from_counts<KM_P_AMBIG>(cn, min_overlap);
+}
+__global__ void __launch_bounds__(256) resolve_min_kernel(StreamParams sp, int wshift, uint32_t wm1, int min_overlap) {
+    if (*sp.overflow) return;  // the queue has holes when a push did not fit: the caller falls back to the dense path
+    const long long nq = min((long long)*sp.qn, sp.qcap);
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
+        const int i = sp.qi[r], j = sp.qj[r];
+        uint32_t lhs, den;
+        const double d = queued_distance(sp.qv[r], wshift, wm1, min_overlap, lhs, den);
+        if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) continue;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+        const int spi = sp.species[i], spj = sp.species[j];
+        if (spj >= 0 && lhs <= sp.thr[i] * den) { if (spj == spi) atomicMin(sp.mC + i, bits); atomicMin(sp.mPar + 2 * (int64_t)i + (spj & 1), bits); }
+        if (spi >= 0 && lhs <= sp.thr[j] * den) { if (spi == spj) atomicMin(sp.mC + j, bits); atomicMin(sp.mPar + 2 * (int64_t)j + (spi & 1), bits); }
+    }
+}
+__global__ void __launch_bounds__(256) resolve_emit_kernel(StreamParams sp, int wshift, uint32_t wm1, int min_overlap) {
+    if (*sp.overflow) return;
+    const long long nq = min((long long)*sp.qn, sp.qcap);
+    const bool want_bm = (sp.want & TDNA_WANT_BEST_MATCH) != 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
+        const int i = sp.qi[r], j = sp.qj[r];
+        uint32_t lhs, den;
+        const double d = queued_distance(sp.qv[r], wshift, wm1, min_overlap, lhs, den);
+        if ((sp.want & TDNA_WANT_EDGES) && d >= 0 && d <= sp.edge_t) {
+            const unsigned long long pos = atomicAdd(sp.nedge, 1ull);
+            if (sp.ei && (long long)pos < sp.edge_cap) { sp.ei[pos] = i; sp.ej[pos] = j; sp.ed[pos] = d; }
+        }
+        if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) {
+            atomicOr(sp.flags + i, TDNA_ROW_NONFINITE);
+            atomicOr(sp.flags + j, TDNA_ROW_NONFINITE);
+            continue;
+        }
+        if (!want_bm) continue;
+        const bool ei = lhs <= sp.thr[i] * den, ej = lhs <= sp.thr[j] * den;
+        if (!(ei || ej)) continue;
+        const unsigned long long pos = atomicAdd(sp.ncand, (unsigned long long)(ei + ej));
+        if ((long long)(pos + ei + ej) > sp.cap) { *sp.overflow = 1; continue; }
+        unsigned long long w = pos;
+        if (ei) { sp.cq[w] = i; sp.cj[w] = j; sp.cd[w] = d; atomicAdd(sp.cnt + i, 1); w++; }
+        if (ej) { sp.cq[w] = j; sp.cj[w] = i; sp.cd[w] = d; atomicAdd(sp.cnt + j, 1); }
+    }
 }
 
 }  // namespace tc
