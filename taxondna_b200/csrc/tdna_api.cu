@@ -447,9 +447,8 @@ int ensure_tc(tdna_aln *a) {
     }
     int *d_flag = reinterpret_cast<int *>(c->d_counter);
     cudaMemsetAsync(d_flag, 0, 8, c->stream);
-    int64_t ua = npa * nchunks * (tc::KB / 16), ub = npb * nchunks * (tc::KB / 16);
-    tc::encode_kernel<false><<<(unsigned)((ua + 255) / 256), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, npa, a->sym_stride, a->L, nchunks, v, a->d_tcA, d_flag);
-    tc::encode_kernel<true><<<(unsigned)((ub + 255) / 256), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, npb, a->sym_stride, a->L, nchunks, v, a->d_tcB, d_flag);
+    tc::encode_kernel<false><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, v, a->d_tcA, d_flag);
+    tc::encode_kernel<true><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::N)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, v, a->d_tcB, d_flag);
     c->launches += 2;
     int flag = 0;
     cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream);
@@ -798,35 +797,27 @@ int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const 
         if (!*dst[i]) CU(DMALLOC(dst[i], bytes));
         CU(cudaMemcpyAsync(*dst[i], src[i], bytes, cudaMemcpyDefault, c->stream));
     }
-    CU(cudaStreamSynchronize(c->stream));
-    // needc[q]: q is named and its species has another member (the streaming thresholds wait for a
-    // conspecific only where one can exist)
-    std::vector<int32_t> hs((size_t)a->n);
-    CU(cudaMemcpy(hs.data(), a->d_species, bytes, cudaMemcpyDeviceToHost));
-    std::unordered_map<int32_t, int> members;
-    for (int32_t v : hs)
-        if (v >= 0) members[v]++;
-    std::vector<uint8_t> need((size_t)a->n);
-    for (int64_t i = 0; i < a->n; i++) need[i] = (hs[i] >= 0 && members[hs[i]] > 1) ? 1 : 0;
+    // needc[q] (q is named and its species has another member: the streaming thresholds wait for a conspecific only where
+    // one can exist) and the per-panel label ranges (tile-level test for class pairs), all on the device
+    uint32_t hcap = 1024;
+    while (hcap < 2 * (uint64_t)a->n) hcap <<= 1;
+    int32_t *d_keys, *d_cnts;
+    CU(DMALLOC(&d_keys, (size_t)hcap * 4));
+    CU(DMALLOC(&d_cnts, (size_t)hcap * 4));
+    CU(cudaMemsetAsync(d_keys, 0xff, (size_t)hcap * 4, c->stream));
+    CU(cudaMemsetAsync(d_cnts, 0, (size_t)hcap * 4, c->stream));
     if (!a->d_needc) CU(DMALLOC(&a->d_needc, (size_t)a->n));
-    CU(cudaMemcpyAsync(a->d_needc, need.data(), (size_t)a->n, cudaMemcpyHostToDevice, c->stream));
-    // per 64-row panel: range of named species ids and of genus ids (tile-level test for class pairs)
-    std::vector<int32_t> hg((size_t)a->n);
-    CU(cudaMemcpy(hg.data(), a->d_genus, bytes, cudaMemcpyDeviceToHost));
     size_t panels = (size_t)(a->npad / PR);
-    std::vector<int4> pr(panels);
-    for (size_t pnl = 0; pnl < panels; pnl++) {
-        int4 r = make_int4(0x7fffffff, -1, 0x7fffffff, (int)0x80000000);
-        for (int64_t i = (int64_t)pnl * PR; i < (int64_t)(pnl + 1) * PR && i < a->n; i++) {
-            if (hs[i] >= 0) { r.x = hs[i] < r.x ? hs[i] : r.x; r.y = hs[i] > r.y ? hs[i] : r.y; }
-            r.z = hg[i] < r.z ? hg[i] : r.z;
-            r.w = hg[i] > r.w ? hg[i] : r.w;
-        }
-        pr[pnl] = r;
-    }
     if (!a->d_panel_range) CU(DMALLOC(&a->d_panel_range, panels * sizeof(int4)));
-    CU(cudaMemcpyAsync(a->d_panel_range, pr.data(), panels * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    unsigned gq = (unsigned)((a->n + 255) / 256);
+    species_count_kernel<<<gq, 256, 0, c->stream>>>(a->d_species, a->n, d_keys, d_cnts, hcap - 1);
+    needc_kernel<<<gq, 256, 0, c->stream>>>(a->d_species, a->n, d_keys, d_cnts, hcap - 1, a->d_needc);
+    panel_range_kernel<<<(unsigned)panels, 32, 0, c->stream>>>(a->d_species, a->d_genus, a->n, a->d_panel_range);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    CU(DFREE(d_keys));
+    CU(DFREE(d_cnts));
+    CU(cudaStreamSynchronize(c->stream));  // the caller's label arrays may be pageable: do not return before the copies have read them
     a->has_labels = true;
     return TDNA_OK;
 }

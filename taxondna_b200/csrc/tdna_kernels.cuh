@@ -976,6 +976,63 @@ __global__ void __launch_bounds__(RS_THREADS, 1) row_summary_kernel(const double
 }
 
 // ------------------------------------------------------------------------------------------
+// label-derived tables (tdna_alignment_set_labels), built on the device: no host round trip
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t label_hash(int32_t v) {
+    uint32_t x = (uint32_t)v * 0x9e3779b1u;
+    return x ^ (x >> 15);
+}
+// open-addressing table of the named species ids with their member counts; keys start at -1 (0xff fill), counts at 0
+__global__ void __launch_bounds__(256) species_count_kernel(const int32_t *__restrict__ species, int64_t n, int32_t *__restrict__ keys,
+                                                            int32_t *__restrict__ counts, uint32_t mask) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int32_t v = species[q];
+    if (v < 0) return;
+    for (uint32_t h = label_hash(v) & mask;; h = (h + 1) & mask) {
+        const int32_t old = atomicCAS(keys + h, -1, v);
+        if (old == -1 || old == v) { atomicAdd(counts + h, 1); return; }
+    }
+}
+// needc[q] != 0: q is named and another row carries the same species id
+__global__ void __launch_bounds__(256) needc_kernel(const int32_t *__restrict__ species, int64_t n, const int32_t *__restrict__ keys,
+                                                    const int32_t *__restrict__ counts, uint32_t mask, uint8_t *__restrict__ needc) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int32_t v = species[q];
+    uint8_t r = 0;
+    if (v >= 0)
+        for (uint32_t h = label_hash(v) & mask;; h = (h + 1) & mask) {
+            const int32_t k = keys[h];
+            if (k == v) { r = counts[h] > 1; break; }
+            if (k == -1) break;
+        }
+    needc[q] = r;
+}
+// per 64-row panel: (min, max) named species id, (min, max) genus id; one warp per panel
+__global__ void __launch_bounds__(32) panel_range_kernel(const int32_t *__restrict__ species, const int32_t *__restrict__ genus, int64_t n,
+                                                         int4 *__restrict__ out) {
+    const int64_t pnl = blockIdx.x;
+    int4 r = make_int4(0x7fffffff, -1, 0x7fffffff, (int)0x80000000);
+    for (int x = threadIdx.x; x < PR; x += 32) {
+        const int64_t i = pnl * PR + x;
+        if (i >= n) continue;
+        const int sv = species[i], gv = genus[i];
+        if (sv >= 0) { r.x = min(r.x, sv); r.y = max(r.y, sv); }
+        r.z = min(r.z, gv);
+        r.w = max(r.w, gv);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        r.x = min(r.x, __shfl_xor_sync(0xffffffffu, r.x, m));
+        r.y = max(r.y, __shfl_xor_sync(0xffffffffu, r.y, m));
+        r.z = min(r.z, __shfl_xor_sync(0xffffffffu, r.z, m));
+        r.w = max(r.w, __shfl_xor_sync(0xffffffffu, r.w, m));
+    }
+    if (threadIdx.x == 0) out[pnl] = r;
+}
+
+// ------------------------------------------------------------------------------------------
 // streaming Best Match, after the tile pass: state init, candidate CSR, exact per-row summaries
 // ------------------------------------------------------------------------------------------
 // needc[q] != 0: q is named and another row of its species exists (labels only; set by the host side)

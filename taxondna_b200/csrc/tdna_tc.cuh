@@ -96,52 +96,52 @@ template <int CL> __device__ __forceinline__ bool my_tile(const Params &p, int64
 struct EncodeValues {
     int a, b, c, d;
 };
-// one thread = one 16-byte unit of one row; unit index order (panel, chunk, k16, row group, row) = memory order
+// one CTA = one operand block (panel x K-chunk): the ~27 sites the chunk covers are staged as symbol codes in shared
+// memory (coalesced 27-byte runs per row), then every thread emits 16-byte units in memory order (coalesced uint4 stores)
+constexpr int ENC_SITES = KB / DIMS + 3;
 template <bool BSIDE>
-__global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len, int64_t n, int64_t npad,
-                                                     int64_t sym_stride, int L, int nchunks, EncodeValues v, uint8_t *__restrict__ out,
-                                                     int *__restrict__ not_clean) {
+__global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len, int64_t n, int64_t sym_stride,
+                                                     int L, int nchunks, EncodeValues v, uint8_t *__restrict__ out, int *__restrict__ not_clean) {
     constexpr int ROWS = BSIDE ? N : M;
-    const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t units = npad * nchunks * (KB / 16);
-    if (unit >= units) return;
-    const int r = (int)(unit % 8);
-    const int rg = (int)((unit / 8) % (ROWS / 8));
-    const int k16 = (int)((unit / (8 * (ROWS / 8))) % (KB / 16));
-    const int64_t pc = unit / (8 * (ROWS / 8) * (KB / 16));
-    const int c = (int)(pc % nchunks);
-    const int64_t panel = pc / nchunks;
-    const int64_t row = panel * ROWS + rg * 8 + r;
-    uint32_t w[4] = {0, 0, 0, 0};
-    if (row < n) {
-        const int l = len[row];
-        const uint8_t *src = sym + row * sym_stride;
-        const int kk0 = c * KB + k16 * 16;
-        bool bad = false;
+    __shared__ uint8_t codes[ROWS][ENC_SITES + 1];  // 0..4 = A C G T '-', 5 = no contribution ('_', '?', beyond the row)
+    const int c = blockIdx.x;
+    const int64_t panel = blockIdx.y;
+    const int s0 = (c * KB) / DIMS;
+    bool bad = false;
+    for (int idx = threadIdx.x; idx < ROWS * ENC_SITES; idx += 256) {
+        const int row_l = idx / ENC_SITES, s = idx % ENC_SITES;
+        const int64_t row = panel * ROWS + row_l;
+        const int site = s0 + s;
+        uint8_t code = 5;
+        if (row < n && site < L && site < len[row]) {
+            switch (__ldg(sym + row * sym_stride + site)) {
+                case 'A': code = 0; break;
+                case 'C': code = 1; break;
+                case 'G': code = 2; break;
+                case 'T': code = 3; break;
+                case '-': code = 4; break;
+                case '_': case '?': code = 5; break;
+                default: code = 5; bad = true; break;
+            }
+        }
+        codes[row_l][s] = code;
+    }
+    if (bad) atomicOr(not_clean, 1);
+    __syncthreads();
+    uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)panel * nchunks + c) * (size_t)(ROWS * KB));
+    const int va = BSIDE ? v.c : v.a, vb = BSIDE ? v.d : v.b;
+    for (int u = threadIdx.x; u < ROWS * (KB / 16); u += 256) {
+        const int row_l = u % ROWS, k16 = u / ROWS;  // u = (k16 * (ROWS / 8) + rg) * 8 + r, row = rg * 8 + r
+        uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int b = 0; b < 16; b++) {
-            const int kk = kk0 + b, site = kk / DIMS, dim = kk % DIMS;
-            int val = 0;
-            if (site < L && site < l) {
-                const uint8_t ch = __ldg(src + site);
-                int code;  // 0..4 = A C G T '-', 5 = '_' / '?', 6 = anything else
-                switch (ch) {
-                    case 'A': code = 0; break;
-                    case 'C': code = 1; break;
-                    case 'G': code = 2; break;
-                    case 'T': code = 3; break;
-                    case '-': code = 4; break;
-                    case '_': case '?': code = 5; break;
-                    default: code = 6; break;
-                }
-                bad |= code == 6;
-                if (code < 5) val = BSIDE ? v.d + (dim == code ? v.c : 0) : v.b + (dim == code ? v.a : 0);
-            }
+            const int kk = c * KB + k16 * 16 + b, site = kk / DIMS - s0, dim = kk % DIMS;
+            const int code = codes[row_l][site];
+            const int val = code < 5 ? vb + (dim == code ? va : 0) : 0;
             w[b >> 2] |= (uint32_t)(val & 0xff) << (8 * (b & 3));
         }
-        if (bad) atomicOr(not_clean, 1);
+        dst[u] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    reinterpret_cast<uint4 *>(out)[unit] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // ---- tcgen05 / TMEM primitives ---------------------------------------------------------------
@@ -327,7 +327,18 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             const bool seed = !COUNTS_MODE && (sp.want & TDNA_WANT_SEED) != 0;  // diagonal-block pre-pass: thresholds only
             const bool want_bm = !COUNTS_MODE && (sp.want & TDNA_WANT_BEST_MATCH);
             const uint32_t edge_tf = (!COUNTS_MODE && p.extras && (sp.want & TDNA_WANT_EDGES)) ? sp.edge_tfix : 0u;
-            const bool classes = !COUNTS_MODE && !seed && p.extras && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER));
+            bool classes = !COUNTS_MODE && !seed && p.extras && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER));
+            if (classes) {  // class pairs only live in tiles whose row and column panels share a species or a genus id range
+                bool may = false;
+                for (int a = 0; a < M / PR; a++)
+                    for (int b = 0; b < N / PR; b++) {
+                        const int pi = ti * (M / PR) + a, pj = tj * (N / PR) + b;
+                        if ((int64_t)pi * PR >= p.n || (int64_t)pj * PR >= p.n) continue;
+                        const int4 ri = sp.panel_range[pi], rj = sp.panel_range[pj];
+                        may |= (ri.x <= rj.y && rj.x <= ri.y) || (ri.z <= rj.w && rj.z <= ri.w);
+                    }
+                classes = may;
+            }
             uint32_t tf_row = edge_tf;
             if constexpr (!COUNTS_MODE) {
                 __syncwarp();  // the previous tile's reads of my_thr are done
@@ -507,8 +518,16 @@ __global__ void __launch_bounds__(256) resolve_emit_kernel(StreamParams sp, int 
         if (!want_bm) continue;
         const bool ei = lhs <= sp.thr[i] * den, ej = lhs <= sp.thr[j] * den;
         if (!(ei || ej)) continue;
-        const unsigned long long pos = atomicAdd(sp.ncand, (unsigned long long)(ei + ej));
-        if ((long long)(pos + ei + ej) > sp.cap) { *sp.overflow = 1; continue; }
+        // one atomic per warp: positions from ballots over the lanes that got here together
+        const unsigned amask = __activemask();
+        const int lane = threadIdx.x & 31, mine = ei + ej;
+        const unsigned bi = __ballot_sync(amask, ei), bj = __ballot_sync(amask, ej), lt = (1u << lane) - 1u;
+        const int total = __popc(bi) + __popc(bj), below = __popc(bi & lt) + __popc(bj & lt);
+        const int leader = __ffs((int)amask) - 1;
+        unsigned long long pos = 0;
+        if (lane == leader) pos = atomicAdd(sp.ncand, (unsigned long long)total);
+        pos = __shfl_sync(amask, pos, leader) + (unsigned long long)below;
+        if ((long long)(pos + mine) > sp.cap) { *sp.overflow = 1; continue; }
         unsigned long long w = pos;
         if (ei) { sp.cq[w] = i; sp.cj[w] = j; sp.cd[w] = d; atomicAdd(sp.cnt + i, 1); w++; }
         if (ej) { sp.cq[w] = j; sp.cj[w] = i; sp.cd[w] = d; atomicAdd(sp.cnt + j, 1); }
