@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
 #pragma unroll
                 for (int x = 0; x < EPI_COLS / 32; x++) {
                     const int j = j0 + g * EPI_COLS + x * 32 + lane;
-                    my_thr[x * 32 + lane] = (want_bm && j < p.n) ? __ldcg(sp.thr + j) : 0u;
+                    if (seed) my_thr[x * 32 + lane] = (uint32_t)(j < p.n ? __ldg(sp.species + j) : -1);  // seed pass: the columns' species ids
+                    else my_thr[x * 32 + lane] = (want_bm && j < p.n) ? __ldcg(sp.thr + j) : 0u;
                 }
                 if (want_bm && i < p.n) tf_row = max(tf_row, __ldcg(sp.thr + i));
                 __syncwarp();
@@ -355,6 +356,9 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             mbar_wait(&tfull[as], (uint32_t)((k >> 1) & 1));
             fence_after();
             int bad_row = 0;
+            // seed pass: exact minima of this row over the columns of its diagonal block (both sides of the diagonal), by category
+            unsigned long long seed_c = TDNA_INF_BITS, seed_p0 = TDNA_INF_BITS, seed_p1 = TDNA_INF_BITS;
+            const int spi = (seed && i < p.n) ? __ldg(sp.species + i) : -1;
 #pragma unroll
             for (int cbi = 0; cbi < EPI_COLS / 32; cbi++) {
                 const int cb = g * (EPI_COLS / 32) + cbi;
@@ -366,6 +370,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     if (lane == 0) mbar_arrive(&tempty[as]);
                 }
                 const int jb = j0 + cb * 32;
+                if (p.hints == 8) continue;  // experiment: no epilogue work at all (results are wrong)
                 if constexpr (COUNTS_MODE) {
 #pragma unroll
                     for (int e = 0; e < 32; e++) {
@@ -374,6 +379,19 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                             tdna_counts o = {(int)(ident + mism), (int)ident, 0, 0};
                             p.counts[(size_t)i * p.n + jb + e] = o;
                         }
+                    }
+                } else if (seed) {
+#pragma unroll
+                    for (int e = 0; e < 32; e++) {  // fully unrolled: v[] must stay in registers
+                        const int j = jb + e, spj = (int)my_thr[cbi * 32 + e];
+                        const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1, s = ident + mism;
+                        if (j == i || j >= p.n || i >= p.n || spj < 0 || (int)s < p.min_overlap) continue;
+                        Counts cn = {(int)s, (int)ident, 0, 0};
+                        const double d = distance_from_counts<KM_P_AMBIG>(cn, p.min_overlap);
+                        if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) continue;
+                        const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+                        if (spj == spi) seed_c = min(seed_c, bits);
+                        if (spj & 1) seed_p1 = min(seed_p1, bits); else seed_p0 = min(seed_p0, bits);
                     }
                 } else {
                     uint32_t pmask = 0, bmask = 0, smask = 0;  // slow path wanted / pair below minOverlap / valid self pair
@@ -442,15 +460,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         }
                         pmask = 0;
                     }
-                    while (__any_sync(0xffffffffu, pmask != 0)) {  // seed pass, converged: every lane brings its next candidate
-                        const int e = pmask ? __ffs((int)pmask) - 1 : -1;
-                        pmask &= pmask - 1u;
-                        uint32_t val = 0;
-#pragma unroll
-                        for (int x = 0; x < 32; x++) val = (x == e) ? v[x] : val;
-                        const uint32_t mism = val >> p.wshift, ident = val & wm1, s = ident + mism;
-                        stream_emit_converged<KM_P_AMBIG>(e >= 0, i, jb + e, ident | (s << 16), 0u, mism << 16, s, p.min_overlap);
-                    }
+
                     if (classes) {
 #pragma unroll
                         for (int e = 0; e < 32; e++) {
@@ -466,6 +476,11 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             }
             if constexpr (!COUNTS_MODE) {
                 if (bad_row) atomicAdd(sp.inval + i, bad_row);
+                if (seed && i < p.n) {
+                    if (seed_c < TDNA_INF_BITS) atomicMin(sp.mC + i, seed_c);
+                    if (seed_p0 < TDNA_INF_BITS) atomicMin(sp.mPar + 2 * (int64_t)i, seed_p0);
+                    if (seed_p1 < TDNA_INF_BITS) atomicMin(sp.mPar + 2 * (int64_t)i + 1, seed_p1);
+                }
             }
         }
     }
