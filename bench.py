@@ -366,10 +366,11 @@ def main():
         prof = json.load(open(pj))
     used_tensor = streaming and aln.last_count_kernel() == t.KERNEL_TENSOR
     if used_tensor:
-        # kernel (b): int8 one-hot contraction on tcgen05.  Algorithmic work = 2 * K * L int8 ops per pair with the K = 5
-        # symbol dimensions per site this kernel uses; peak = a cuBLASLt int8 GEMM (torch._int_mm, 8192^3)
+        # kernel (b): int8 one-hot contraction on tcgen05.  Algorithmic work = 2 * K * L int8 ops per pair with the K = 5 (p) or
+        # 4 (K2P) symbol dimensions per site this kernel uses; peak = a cuBLASLt int8 GEMM (torch._int_mm, 8192^3)
         # measured here, else twice MEASURED_PEAKS.json's bf16 burst figure.
-        ops = kern_pairs * 2 * 5 * L
+        dims = 4 if mode == 1 else 5  # K2P ignores gap sites: four symbol dimensions
+        ops = kern_pairs * 2 * dims * L
         int8_peak, int8_src = None, None
         try:
             a8 = torch.randint(-3, 3, (8192, 8192), dtype=torch.int8, device=dev)
@@ -389,12 +390,12 @@ def main():
         except Exception as ex:  # noqa: BLE001
             int8_peak, int8_src = 2 * peaks.get("bf16_tflops", 1590.0) * 1e12, "2 x MEASURED_PEAKS.json bf16_tflops (%s; torch._int_mm unavailable: %s)" % (peak_src, type(ex).__name__)
         achieved = ops / (kern_ms * 1e-3)
-        P_bytes = 2 * n * 5 * L  # a-side + b-side one-hot operands
+        P_bytes = 2 * n * dims * L  # a-side + b-side one-hot operands
         roofline = {
             "bound": "tensor", "kernel": "tc::tile_kernel (tcgen05.mma kind::i8, TMEM accumulators)",
             "achieved": achieved / 1e12, "peak": int8_peak / 1e12, "unit": "TOP/s (int8)", "frac": achieved / int8_peak,
             "peak_source": int8_src, "kernel_ms": kern_ms, "kernel_gpairs_per_s": kern_pairs / (kern_ms * 1e-3) / 1e9,
-            "algorithmic_int8_ops_per_pair": 2 * 5 * L,
+            "algorithmic_int8_ops_per_pair": 2 * dims * L,
             "traffic": prof.get(args.workload + "_tensor", {}).get("dram_bytes_per_launch"),
             "hbm": {"algorithmic_bytes_per_launch": int(P_bytes), "achieved_gbs": P_bytes / (kern_ms * 1e-3) / 1e9,
                     "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},

@@ -102,7 +102,7 @@ struct tdna_aln {
     // count kernel (b): one-hot int8 operands (tdna_tc.cuh)
     uint8_t *d_tcA = nullptr, *d_tcB = nullptr;
     int tc_state = 0;  // 0 = not built, 1 = ready, -1 = not eligible
-    int tc_nchunks = 0;
+    int tc_nchunks = 0, tc_kmode = -1, tc_dims = 5;
     uint32_t tc_W = 0;
     CUtensorMap tc_mapA, tc_mapB, tc_mapBh;  // [.., 256 x uint32] views of d_tcA / d_tcB, boxes of one operand block (Bh: half a b-block)
     bool tc_maps = false;
@@ -367,7 +367,7 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
     bool tensor = c->opt_count_kernel == TDNA_KERNEL_TENSOR || (c->opt_count_kernel == TDNA_KERNEL_AUTO && ensure_tc(a) == 1);
     a->last_kernel = tensor ? TDNA_KERNEL_TENSOR : TDNA_KERNEL_POPC;
     if (tensor) {
-        if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p with ambiguity allowed, no IUPAC ambiguity letters, L < 4096");
+        if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p (ambiguity allowed) or K2P, an alignment without IUPAC ambiguity letters, L < 4096");
         if (phases & 1) CU(cudaEventRecord(c->ev_k0, c->stream));
         for (int ph = 0; ph < 2; ph++)
             if (phases & (1 << ph)) {
@@ -382,12 +382,13 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
             int wshift = 0;
             while ((1u << wshift) < a->tc_W) wshift++;
             unsigned grid = (unsigned)c->sm_count * 8;
+            tc::ResolveArgs ra = {wshift, a->tc_W - 1u, a->min_overlap, a->kmode == KM_K2P ? a->d_planes : nullptr, a->W};
             if (a->sp.want & TDNA_WANT_BEST_MATCH) {
-                tc::resolve_min_kernel<<<grid, 256, 0, c->stream>>>(a->sp, wshift, a->tc_W - 1u, a->min_overlap);
+                tc::resolve_min_kernel<<<grid, 256, 0, c->stream>>>(a->sp, ra);
                 stream_thr_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n);
                 c->launches += 2;
             }
-            tc::resolve_emit_kernel<<<grid, 256, 0, c->stream>>>(a->sp, wshift, a->tc_W - 1u, a->min_overlap);
+            tc::resolve_emit_kernel<<<grid, 256, 0, c->stream>>>(a->sp, ra);
             c->launches++;
             CU(cudaGetLastError());
         }
@@ -409,9 +410,9 @@ static int tc_band() {  // row tiles per band of the bulk phase (TDNA_TC_BAND ov
 }
 #define TC_BAND tc_band()
 
-// Integers for the five-dimensional symbol code of tdna_tc.cuh: u = b*1 + a*e_x, v = d*1 + c*e_y with
-// a*c = -(W-1), a*d + b*c + 5*b*d = W, every entry (b, a+b, d, c+d) within int8, smallest W > L.
-bool find_code(int L, tc::EncodeValues &out, uint32_t &Wout) {
+// Integers for the `dims`-dimensional symbol code of tdna_tc.cuh: u = b*1 + a*e_x, v = d*1 + c*e_y with
+// a*c = -(W-1), a*d + b*c + dims*b*d = W, every entry (b, a+b, d, c+d) within int8, smallest W > L.
+bool find_code(int L, int dims, tc::EncodeValues &out, uint32_t &Wout) {
     for (int W = 256; W <= 4096; W *= 2)  // a power of two: the epilogue decodes with a shift and a mask
         for (int aa = -127; aa <= 127 && W > L; aa++) {
             if (aa == 0 || (W - 1) % (aa < 0 ? -aa : aa) != 0) continue;
@@ -419,7 +420,7 @@ bool find_code(int L, tc::EncodeValues &out, uint32_t &Wout) {
             if (cc < -127 || cc > 127) continue;
             for (int bb = -127; bb <= 127; bb++) {
                 if (aa + bb < -127 || aa + bb > 127) continue;
-                int den = aa + 5 * bb, num = W - bb * cc;
+                int den = aa + dims * bb, num = W - bb * cc;
                 if (den == 0 || num % den != 0) continue;
                 int dd = num / den;
                 if (dd < -127 || dd > 127 || cc + dd < -127 || cc + dd > 127) continue;
@@ -433,12 +434,21 @@ bool find_code(int L, tc::EncodeValues &out, uint32_t &Wout) {
 // 1 = ready, -1 = this alignment / configuration is not eligible
 int ensure_tc(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
-    if (a->kmode != KM_P_AMBIG || a->L >= 4096) return -1;
+    if ((a->kmode != KM_P_AMBIG && a->kmode != KM_K2P) || a->L >= 4096) return -1;
+    if (a->tc_state == 1 && a->tc_kmode != a->kmode) {  // the operands encode the mode's valid-symbol set: rebuild
+        DFREE(a->d_tcA);
+        DFREE(a->d_tcB);
+        if (a->d_tcprefix[1]) DFREE(a->d_tcprefix[1]);
+        a->d_tcA = a->d_tcB = nullptr;
+        a->d_tcprefix[1] = nullptr;
+        a->tc_state = 0;
+    }
     if (a->tc_state != 0) return a->tc_state;
+    const int dims = a->kmode == KM_K2P ? 4 : 5;  // K2P ignores gap sites: four symbols
     tc::EncodeValues v;
     uint32_t W = 0;
-    if (!find_code(a->L, v, W)) { a->tc_state = -1; return -1; }
-    int nchunks = (a->L * tc::DIMS + tc::KB - 1) / tc::KB;
+    if (!find_code(a->L, dims, v, W)) { a->tc_state = -1; return -1; }
+    int nchunks = (a->L * dims + tc::KB - 1) / tc::KB;
     int64_t npa = round_up(a->n, tc::M), npb = round_up(a->n, tc::N);
     if (cudaSuccess != DMALLOC(&a->d_tcA, (size_t)npa * nchunks * tc::KB) || cudaSuccess != DMALLOC(&a->d_tcB, (size_t)npb * nchunks * tc::KB)) {
         cudaGetLastError();
@@ -447,8 +457,8 @@ int ensure_tc(tdna_aln *a) {
     }
     int *d_flag = reinterpret_cast<int *>(c->d_counter);
     cudaMemsetAsync(d_flag, 0, 8, c->stream);
-    tc::encode_kernel<false><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, v, a->d_tcA, d_flag);
-    tc::encode_kernel<true><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::N)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, v, a->d_tcB, d_flag);
+    tc::encode_kernel<false><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcA, d_flag);
+    tc::encode_kernel<true><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::N)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcB, d_flag);
     c->launches += 2;
     int flag = 0;
     cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream);
@@ -482,6 +492,8 @@ int ensure_tc(tdna_aln *a) {
     }
     a->tc_nchunks = nchunks;
     a->tc_W = W;
+    a->tc_kmode = a->kmode;
+    a->tc_dims = dims;
     {   // tensor maps for the tiled TMA loads (driver entry point through the runtime: no -lcuda)
         typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -540,6 +552,9 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.num_tiles = total > part ? (total - part + nparts - 1) / nparts : 0;
     p.counts = counts;
     p.extras = a->sp.want != TDNA_WANT_BEST_MATCH;
+    p.k2p = a->kmode == KM_K2P ? 1 : 0;
+    p.planes = a->d_planes;
+    p.W32 = a->W;
     {
         const char *e = getenv("TDNA_TC_PIECE");
         int v = e ? atoi(e) : (a->tc_maps ? 0 : 16384);  // default: tiled TMA when the tensor maps exist
@@ -1473,7 +1488,8 @@ int32_t tdna_tensor_counts(tdna_aln *a, tdna_counts *out) {
     tdna_ctx *c = a->ctx;
     CU(cudaSetDevice(c->device));
     TRY(ensure_packed(a));
-    if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p with ambiguity allowed, no IUPAC ambiguity letters, L < 4096");
+    if (a->kmode != KM_P_AMBIG) return fail(TDNA_E_STATE, "tdna_tensor_counts: uncorrected p only (for K2P the accumulator carries n and ts + tv)");
+    if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p (ambiguity allowed) or K2P, an alignment without IUPAC ambiguity letters, L < 4096");
     tdna_counts *dc = out;
     bool own = !is_device_ptr(out);
     size_t bytes = (size_t)a->n * a->n * sizeof(tdna_counts);

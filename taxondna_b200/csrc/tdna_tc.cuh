@@ -33,7 +33,7 @@ constexpr int STAGE = A_STAGE + B_STAGE;
 constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter
 constexpr int EPI_COLS = N / (EPI_WARPS / 4);      // columns per epilogue warp
 constexpr int THREADS = 64 + EPI_WARPS * 32;       // warp 0 producer, warp 1 MMA issuer, warps 2.. epilogue
-constexpr int DIMS = 5;                            // K-dimensions per site
+constexpr int MAX_DIMS = 5;                        // K-dimensions per site: 5 (p: A C G T -) or 4 (K2P: A C G T)
 constexpr size_t SMEM = (size_t)NSTAGE * STAGE + 256 /*barriers*/ + 16 * 64 * 4 /*column thresholds, per epilogue warp*/ + 1024 /*alignment*/;
 
 struct Params {
@@ -52,6 +52,9 @@ struct Params {
     int64_t num_tiles, t_offset, t_stride;
     tdna_counts *counts;    // verification mode: n x n counts (row-major), else null
     int extras;             // stream mode: classes / edges wanted (c_sp.want beyond Best Match)
+    int k2p;                // the accumulator carries (n, ts + tv) of the K2P model; exact counts come from the bit-planes
+    const uint32_t *planes; // K2P: the popc kernel's planes, for the exact counts of queued / class pairs
+    int W32;
     int a_rows, b_rows;     // rows of the tensor-map view per a / b stage block (view row = inner box width)
     int hints;              // L2 cache-policy hints on the operand loads (experiments: TDNA_TC_HINTS)
     int piece;              // bytes per 1-D bulk copy (divides 16 KB); 0 = tensor-map (2-D tiled TMA) loads
@@ -98,12 +101,12 @@ struct EncodeValues {
 };
 // one CTA = one operand block (panel x K-chunk): the ~27 sites the chunk covers are staged as symbol codes in shared
 // memory (coalesced 27-byte runs per row), then every thread emits 16-byte units in memory order (coalesced uint4 stores)
-constexpr int ENC_SITES = KB / DIMS + 3;
+constexpr int ENC_SITES = KB / 4 + 3;
 template <bool BSIDE>
 __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len, int64_t n, int64_t sym_stride,
-                                                     int L, int nchunks, EncodeValues v, uint8_t *__restrict__ out, int *__restrict__ not_clean) {
+                                                     int L, int nchunks, int DIMS, EncodeValues v, uint8_t *__restrict__ out, int *__restrict__ not_clean) {
     constexpr int ROWS = BSIDE ? N : M;
-    __shared__ uint8_t codes[ROWS][ENC_SITES + 1];  // 0..4 = A C G T '-', 5 = no contribution ('_', '?', beyond the row)
+    __shared__ uint8_t codes[ROWS][ENC_SITES + 1];  // 0..4 = A C G T '-', 5 = no contribution ('_', '?', beyond the row; '-' when DIMS == 4)
     const int c = blockIdx.x;
     const int64_t panel = blockIdx.y;
     const int s0 = (c * KB) / DIMS;
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
                 case 'C': code = 1; break;
                 case 'G': code = 2; break;
                 case 'T': code = 3; break;
-                case '-': code = 4; break;
+                case '-': code = DIMS == 5 ? 4 : 5; break;  // K2P ignores gap sites (Sequence.java:1446-1471)
                 case '_': case '?': code = 5; break;
                 default: code = 5; bad = true; break;
             }
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
         for (int b = 0; b < 16; b++) {
             const int kk = c * KB + k16 * 16 + b, site = kk / DIMS - s0, dim = kk % DIMS;
             const int code = codes[row_l][site];
-            const int val = code < 5 ? vb + (dim == code ? va : 0) : 0;
+            const int val = code < DIMS ? vb + (dim == code ? va : 0) : 0;
             w[b >> 2] |= (uint32_t)(val & 0xff) << (8 * (b & 3));
         }
         dst[u] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -194,6 +197,12 @@ __device__ __forceinline__ void tma_load_2d_hint(void *dst_smem, const CUtensorM
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) { mbar_wait_backoff(bar, parity); }
+
+// K2P: exact counts of one pair from the bit-planes (the accumulator only carries n and ts + tv)
+__device__ __noinline__ void class_emit_k2p(const uint32_t *planes, int W32, int i, int j, int min_overlap) {
+    const Counts c = pair_counts_global<KM_K2P>(planes, i, j, W32);
+    class_emit<KM_K2P>(i, j, (uint32_t)c.c1 | ((uint32_t)c.shared << 16), (uint32_t)c.c2 | ((uint32_t)c.c3 << 16), min_overlap);
+}
 
 // ---- the tile kernel ---------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d_mc(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint16_t cta_mask) {
@@ -327,6 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             const bool seed = !COUNTS_MODE && (sp.want & TDNA_WANT_SEED) != 0;  // diagonal-block pre-pass: thresholds only
             const bool want_bm = !COUNTS_MODE && (sp.want & TDNA_WANT_BEST_MATCH);
             const uint32_t edge_tf = (!COUNTS_MODE && p.extras && (sp.want & TDNA_WANT_EDGES)) ? sp.edge_tfix : 0u;
+            const bool k2p_force = p.k2p != 0;  // K2P: 2(ts + tv) >= n may mean w1 <= 0 or w2 <= 0 -> NaN / +Inf must reach the exact path
             bool classes = !COUNTS_MODE && !seed && p.extras && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER));
             if (classes) {  // class pairs only live in tiles whose row and column panels share a species or a genus id range
                 bool may = false;
@@ -386,27 +396,44 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         const int j = jb + e, spj = (int)my_thr[cbi * 32 + e];
                         const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1, s = ident + mism;
                         if (j == i || j >= p.n || i >= p.n || spj < 0 || (int)s < p.min_overlap) continue;
-                        Counts cn = {(int)s, (int)ident, 0, 0};
-                        const double d = distance_from_counts<KM_P_AMBIG>(cn, p.min_overlap);
-                        if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) continue;
+                        double d;
+                        if (p.k2p) {
+                            // only n and ts + tv are known here: d_K2P <= -ln(1 - 2(P+Q)) / 2 (all differences transitions) bounds the
+                            // minima from above, which is all a threshold needs; the exact minima come from the queue afterwards
+                            if (mism == 0) d = 0.0;
+                            else {
+                                const double w = dsub(1.0, ddiv(dmul(2.0, (double)mism), (double)s));
+                                if (!(w > 0.0)) continue;
+                                d = dmul(-0.5, strict_log_call(w));
+                            }
+                        } else {
+                            Counts cn = {(int)s, (int)ident, 0, 0};
+                            d = distance_from_counts<KM_P_AMBIG>(cn, p.min_overlap);
+                        }
+                        if (!(d < __longlong_as_double((long long)TDNA_INF_BITS)) || d < 0.0) continue;
                         const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
                         if (spj == spi) seed_c = min(seed_c, bits);
                         if (spj & 1) seed_p1 = min(seed_p1, bits); else seed_p0 = min(seed_p0, bits);
                     }
                 } else {
                     uint32_t pmask = 0, bmask = 0, smask = 0;  // slow path wanted / pair below minOverlap / valid self pair
-                    const uint4 *ct4 = reinterpret_cast<const uint4 *>(my_thr + cbi * 32);
+                    const uint32_t ct_addr = smem_u32(my_thr + cbi * 32);  // explicit ld.shared (a generic LD otherwise)
+                    auto lds4 = [](uint32_t addr) {
+                        uint4 r;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+                        return r;
+                    };
                     if (interior) {
 #pragma unroll
                         for (int e4 = 0; e4 < 8; e4++) {
-                            const uint4 ct = ct4[e4];
+                            const uint4 ct = lds4(ct_addr + e4 * 16);
                             const uint32_t cts[4] = {ct.x, ct.y, ct.z, ct.w};
 #pragma unroll
                             for (int u = 0; u < 4; u++) {
                                 const int e = e4 * 4 + u;
                                 const uint32_t mism = v[e] >> p.wshift, s = v[e] - mism * wm1;  // s = ident + mism
                                 const bool ok = (int)s >= p.min_overlap;
-                                const bool pass = (mism << 16) <= max(tf_row, cts[u]) * s;
+                                const bool pass = ((mism << 16) <= max(tf_row, cts[u]) * s) | (k2p_force & (2u * mism >= s));
                                 if (ok && pass) pmask |= 1u << e;
                                 if (!ok) bmask |= 1u << e;
                             }
@@ -414,7 +441,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     } else {
 #pragma unroll
                         for (int e4 = 0; e4 < 8; e4++) {
-                            const uint4 ct = ct4[e4];
+                            const uint4 ct = lds4(ct_addr + e4 * 16);
                             const uint32_t cts[4] = {ct.x, ct.y, ct.z, ct.w};
 #pragma unroll
                             for (int u = 0; u < 4; u++) {
@@ -422,7 +449,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                                 const uint32_t mism = v[e] >> p.wshift, s = v[e] - mism * wm1;
                                 const bool inr = (j > i) & (j < p.n);
                                 const bool ok = (int)s >= p.min_overlap;
-                                const bool pass = (mism << 16) <= max(tf_row, cts[u]) * s;
+                                const bool pass = ((mism << 16) <= max(tf_row, cts[u]) * s) | (k2p_force & (2u * mism >= s));
                                 if (inr && ok && pass) pmask |= 1u << e;
                                 if (inr && !ok) bmask |= 1u << e;
                                 if (j == i && i < p.n && ok) smask |= 1u << e;
@@ -469,7 +496,10 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                             if (j <= i || j >= p.n || (int)s < p.min_overlap) continue;
                             const bool hit = ((sp.want & TDNA_WANT_INTRA) && sp.species[i] == sp.species[j]) ||
                                              ((sp.want & TDNA_WANT_INTER) && sp.genus[i] == sp.genus[j]);
-                            if (hit) class_emit<KM_P_AMBIG>(i, j, ident | (s << 16), 0u, p.min_overlap);
+                            if (hit) {
+                                if (p.k2p) class_emit_k2p(p.planes, p.W32, i, j, p.min_overlap);
+                                else class_emit<KM_P_AMBIG>(i, j, ident | (s << 16), 0u, p.min_overlap);
+                            }
                         }
                     }
                 }
@@ -492,20 +522,33 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
 
 // ---- after the bulk pass: the queue -> minima -> final thresholds -> candidate records --------------------------
 // every queued pair is a valid pair i < j; value = raw accumulator
-__device__ __forceinline__ double queued_distance(uint32_t val, int wshift, uint32_t wm1, int min_overlap, uint32_t &lhs, uint32_t &den) {
-    const uint32_t mism = val >> wshift, ident = val & wm1, s = ident + mism;
+struct ResolveArgs {
+    int wshift;
+    uint32_t wm1;
+    int min_overlap;
+    const uint32_t *planes;  // non-null: K2P -- exact (n, ts, tv) of the pair from the bit-planes
+    int W32;
+};
+__device__ __forceinline__ double queued_distance(const ResolveArgs &ra, int i, int j, uint32_t val, uint32_t &lhs, uint32_t &den) {
+    if (ra.planes) {
+        const Counts c = pair_counts_global<KM_K2P>(ra.planes, i, j, ra.W32);
+        lhs = (uint32_t)(c.c2 + c.c3) << 16;
+        den = (uint32_t)c.c1;
+        return distance_from_counts<KM_K2P>(c, ra.min_overlap);
+    }
+    const uint32_t mism = val >> ra.wshift, ident = val & ra.wm1, s = ident + mism;
     lhs = mism << 16;
     den = s;
     Counts cn = {(int)s, (int)ident, 0, 0};
-    return distance_from_counts<KM_P_AMBIG>(cn, min_overlap);
+    return distance_from_counts<KM_P_AMBIG>(cn, ra.min_overlap);
 }
-__global__ void __launch_bounds__(256) resolve_min_kernel(StreamParams sp, int wshift, uint32_t wm1, int min_overlap) {
+__global__ void __launch_bounds__(256) resolve_min_kernel(StreamParams sp, ResolveArgs ra) {
     if (*sp.overflow) return;  // the queue has holes when a push did not fit: the caller falls back to the dense path
     const long long nq = min((long long)*sp.qn, sp.qcap);
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
         const int i = sp.qi[r], j = sp.qj[r];
         uint32_t lhs, den;
-        const double d = queued_distance(sp.qv[r], wshift, wm1, min_overlap, lhs, den);
+        const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den);
         if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) continue;
         const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
         const int spi = sp.species[i], spj = sp.species[j];
@@ -513,14 +556,14 @@ __global__ void __launch_bounds__(256) resolve_min_kernel(StreamParams sp, int w
         if (spi >= 0 && lhs <= sp.thr[j] * den) { if (spi == spj) atomicMin(sp.mC + j, bits); atomicMin(sp.mPar + 2 * (int64_t)j + (spi & 1), bits); }
     }
 }
-__global__ void __launch_bounds__(256) resolve_emit_kernel(StreamParams sp, int wshift, uint32_t wm1, int min_overlap) {
+__global__ void __launch_bounds__(256) resolve_emit_kernel(StreamParams sp, ResolveArgs ra) {
     if (*sp.overflow) return;
     const long long nq = min((long long)*sp.qn, sp.qcap);
     const bool want_bm = (sp.want & TDNA_WANT_BEST_MATCH) != 0;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
         const int i = sp.qi[r], j = sp.qj[r];
         uint32_t lhs, den;
-        const double d = queued_distance(sp.qv[r], wshift, wm1, min_overlap, lhs, den);
+        const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den);
         if ((sp.want & TDNA_WANT_EDGES) && d >= 0 && d <= sp.edge_t) {
             const unsigned long long pos = atomicAdd(sp.nedge, 1ull);
             if (sp.ei && (long long)pos < sp.edge_cap) { sp.ei[pos] = i; sp.ej[pos] = j; sp.ed[pos] = d; }

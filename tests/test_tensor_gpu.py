@@ -106,3 +106,56 @@ def test_streaming_best_match_on_the_tensor_kernel(ctx, shuffle, ragged, L):
     assert sorted(zip(a["edge_i"].tolist(), a["edge_j"].tolist(), a["edge_d"].tolist())) == \
         sorted(zip(b["edge_i"].tolist(), b["edge_j"].tolist(), b["edge_d"].tolist()))
     aln.close()
+
+
+@pytest.mark.parametrize("shuffle,ragged,L,saturated", [(False, False, 658, 0), (True, True, 700, 0), (False, False, 400, 25)])
+def test_k2p_streaming_on_the_tensor_kernel(ctx, shuffle, ragged, L, saturated):
+    """K2P: the accumulator carries (n, ts + tv) -- enough for the conservative filter -- and the exact (n, ts, tv) of the
+    queued pairs come from the bit-planes; records, classes and edges must equal the popc kernel's."""
+    import taxondna_b200 as t
+    from test_stream_gpu import first_difference
+    from test_gpu_parity import labelled_alignment
+    rng = np.random.default_rng(99 + L)
+    sym, sp, gen, epi, full = labelled_alignment(rng, 30, 8, L, unnamed=3, dup=8, gappy=False)
+    m = rng.random(sym.shape) < 0.05
+    sym[m] = rng.choice(np.frombuffer(CLEAN, dtype=np.uint8), size=int(m.sum()))
+    if saturated:  # unrelated rows: P + Q ~ 0.75 -> NaN / +Inf / huge distances must be flagged exactly as by the popc kernel
+        rnd = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(saturated, L))
+        sym = np.concatenate([sym, rnd])
+        extra = rng.integers(0, 30, size=saturated).astype(np.int32)
+        sp, gen, epi = np.concatenate([sp, extra]), np.concatenate([gen, extra // 3]), np.concatenate([epi, extra])
+    n = sym.shape[0]
+    full = np.arange(n, dtype=np.int32)
+    lens = rng.integers(L // 2, L + 1, size=n).astype(np.int32) if ragged else None
+    if shuffle:
+        perm = rng.permutation(n)
+        sym, sp, gen, epi = sym[perm], sp[perm], gen[perm], epi[perm]
+        if lens is not None:
+            lens = lens[perm]
+    aln = t.Alignment(ctx, sym, lens)
+    aln.set_labels(sp, gen, epi, full)
+    aln.set_config(t.PDM_K2P, L // 3, True)
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_STREAM)
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_POPC)
+    a = aln.analyze(best_match=True, intra=True, inter=True, edges=0.03)
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_TENSOR)
+    b = aln.analyze(best_match=True, intra=True, inter=True, edges=0.03)
+    assert aln.last_count_kernel() == t.KERNEL_TENSOR
+    # and back to uncorrected p on the same alignment: the operands are re-encoded for the other symbol set
+    aln.set_config(t.PDM_UNCORRECTED, L // 3, True)
+    bp = aln.best_match()
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_POPC)
+    ap = aln.best_match()
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+    if saturated:
+        assert (a["rows"]["flags"] & t.ROW_NONFINITE).any()
+    assert np.array_equal(a["rows"]["flags"], b["rows"]["flags"]) and np.array_equal(a["rows"]["n_valid"], b["rows"]["n_valid"])
+    ok = (a["rows"]["flags"] & t.ROW_NONFINITE) == 0
+    assert first_difference(a["rows"][ok], b["rows"][ok]) is None, first_difference(a["rows"][ok], b["rows"][ok])
+    assert np.array_equal(np.sort(a["intra"]).view(np.uint32), np.sort(b["intra"]).view(np.uint32))
+    assert np.array_equal(np.sort(a["inter"]).view(np.uint32), np.sort(b["inter"]).view(np.uint32))
+    assert sorted(zip(a["edge_i"].tolist(), a["edge_j"].tolist(), a["edge_d"].tolist())) == \
+        sorted(zip(b["edge_i"].tolist(), b["edge_j"].tolist(), b["edge_d"].tolist()))
+    assert first_difference(ap, bp) is None, first_difference(ap, bp)
+    aln.close()
