@@ -319,6 +319,16 @@ DistanceEngine::DistanceEngine(const SequenceList &list) {
         ptrs[i]->home_gen_ = gen_;
     }
     ck(tdna_alignment_set_labels(aln_, species_id_.data(), genus.data(), epi.data(), full.data()));
+    // upper bounds of the two PairwiseDistribution classes from the labels alone (ordered conspecific pairs cover the
+    // double push of equal full names; all congeneric pairs cover the inter class): one pass then needs no sizing call
+    std::map<int, int64_t> perSpecies, perGenus;
+    for (int64_t i = 0; i < n_; i++) {
+        if (species_id_[i] >= 0) perSpecies[species_id_[i]]++;
+        perGenus[genus[i]]++;
+    }
+    class_cap_[0] = class_cap_[1] = 0;
+    for (auto &kv : perSpecies) class_cap_[0] += kv.second * (kv.second - 1);
+    for (auto &kv : perGenus) class_cap_[1] += kv.second * (kv.second - 1) / 2;
 }
 DistanceEngine::~DistanceEngine() {
     if (aln_) tdna_alignment_destroy(aln_);
@@ -330,6 +340,7 @@ void DistanceEngine::syncConfig() const {
         cfg_mode_ = m;
         cfg_overlap_ = o;
         cfg_ambig_ = a;
+        class_cached_ = false;
     }
 }
 tdna_counts DistanceEngine::pair(int64_t i, int64_t j, double *d) const {
@@ -356,15 +367,26 @@ std::vector<tdna_row_result> DistanceEngine::bestMatch() const {
     ck(tdna_best_match(aln_, r.data()));
     return r;
 }
+// PairwiseSummary builds PD_INTRA and then PD_INTER (PairwiseSummary.java:131-151): both come from ONE pass over the
+// pair space (tdna_analyze), sized from the labels, and the second request is served from the first one's result.
 std::vector<float> DistanceEngine::classDistances(int klass) const {
     syncConfig();
-    int64_t cnt = 0;
-    ck(tdna_class_distances(aln_, klass, nullptr, 0, &cnt));
-    std::vector<float> out((size_t)std::max<int64_t>(cnt, 1));
-    int64_t got = 0;
-    ck(tdna_class_distances(aln_, klass, out.data(), cnt, &got));
-    out.resize((size_t)cnt);
-    return out;
+    if (!class_cached_) {
+        tdna_analysis io = {};
+        io.want = TDNA_WANT_INTRA | TDNA_WANT_INTER;
+        class_cache_[0].assign((size_t)std::max<int64_t>(class_cap_[0], 1), 0.f);
+        class_cache_[1].assign((size_t)std::max<int64_t>(class_cap_[1], 1), 0.f);
+        io.intra = class_cache_[0].data();
+        io.intra_cap = class_cap_[0];
+        io.inter = class_cache_[1].data();
+        io.inter_cap = class_cap_[1];
+        ck(tdna_analyze(aln_, &io));
+        if (io.n_intra > class_cap_[0] || io.n_inter > class_cap_[1]) throw EngineError("class distances exceed their label-derived bound");
+        class_cache_[0].resize((size_t)io.n_intra);
+        class_cache_[1].resize((size_t)io.n_inter);
+        class_cached_ = true;
+    }
+    return class_cache_[klass == TDNA_PD_INTRA ? 0 : 1];
 }
 void DistanceEngine::edgesBelow(double t, std::vector<int32_t> &ii, std::vector<int32_t> &jj, std::vector<double> &d) const {
     syncConfig();

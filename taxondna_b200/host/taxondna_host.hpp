@@ -177,6 +177,9 @@ class DistanceEngine {
     uint64_t gen_ = 0;
     std::vector<int32_t> species_id_;
     mutable int cfg_mode_ = -1, cfg_overlap_ = -1, cfg_ambig_ = -1;
+    int64_t class_cap_[2] = {0, 0};              // label-derived upper bounds of |PD_INTRA|, |PD_INTER|
+    mutable std::vector<float> class_cache_[2];  // both classes of the current configuration (one pass serves both)
+    mutable bool class_cached_ = false;
 };
 
 // Common/DNA/SortedSequenceList.java:60-162 (+ SortedSequenceComparator :197-261)
