@@ -131,6 +131,10 @@ int32_t tdna_set_row_range(tdna_aln *aln, int64_t row_begin, int64_t row_end);
 /* Sequence.getPairwiseNoBuffer / getSharedLength / countIdentical / countTransversions /
  * getK2PDistance (Sequence.java:1322-1717): one pair, a one-warp launch. counts or d may be NULL. */
 int32_t tdna_pair(tdna_aln *aln, int64_t i, int64_t j, tdna_counts *counts, double *d);
+/* A batch of arbitrary pairs in one launch: (counts[k], d[k]) = pair (ii[k], jj[k]).  What PairwiseDistances
+ * (Common/DNA/PairwiseDistances.java:128-185) and PairwiseExplorer need: the distances of an explicit pair list with
+ * the pair identities kept.  ii / jj / counts / d may be host or device pointers; counts or d may be NULL. */
+int32_t tdna_pairs(tdna_aln *aln, const int32_t *ii, const int32_t *jj, int64_t m, tdna_counts *counts, double *d);
 /* d[j] = query.getPairwise(seq_j) for all j (what SortedSequenceList.sortAgainst evaluates,
  * SortedSequenceList.java:104-118); shared may be NULL. */
 int32_t tdna_row_distances(tdna_aln *aln, int64_t q, double *d, int32_t *shared);

@@ -1048,6 +1048,50 @@ def _pad(x, y=None):
     return x + buff + "\t" + str(y) + "\n"
 
 
+def pairwise_distances(D, kind):
+    """PairwiseDistances (Common/DNA/PairwiseDistances.java:49-185) + PairwiseDistance.compareTo
+    (Common/DNA/PairwiseDistance.java:58-63).  `D.seqs` in SORT_BYNAME order (the constructor re-sorts for
+    PD_INTRA, :82-83).  Returns (triples (name A, name B, d) in Collections.sort order, {full name: mean})."""
+    seqs = D.seqs
+    n = len(seqs)
+    pairs, averages = [], {}
+    first_idx = {}
+    for i, s in enumerate(seqs):  # conspecificIterator: first occurrence, contiguous run (SequenceList.java:614-658)
+        nm = s.species_name()
+        if nm is not None and nm not in first_idx:
+            first_idx[nm] = i
+    for q in range(n):
+        a = seqs[q]
+        total, count = 0.0, 0
+        if kind == PD_INTRA:
+            nm = a.species_name()
+            if nm is None:  # :133: no pushes, no average entry
+                continue
+            x = first_idx[nm]
+            run = []
+            while x < n and seqs[x].species_name() is not None and seqs[x].species_name() == nm:
+                run.append(x)
+                x += 1
+            others = [x for x in run if x != q]
+        else:  # :160-181: same genus, different epithet, BOTH directions (the half-table test is commented out)
+            others = [j for j in range(n) if j != q and a.genus == seqs[j].genus and a.species != seqs[j].species]
+        for j in others:
+            d = D.pairwise(q, j)
+            if not (d < 0):  # distances_push (:64-68): NaN is kept
+                pairs.append((q, j, d))
+            if d > -1:
+                total += d
+                count += 1
+        averages[a.name] = (total / count) if count else float("nan")  # 0.0 / 0 in Java
+
+    def cmp(p1, p2):  # (int) Settings.makeLongFromDouble(d1 - d2)
+        return _java_long_to_int(make_long(p1[2] - p2[2]))
+
+    if pairs:
+        java_sort(pairs, cmp)
+    return [(seqs[q].name, seqs[j].name, d) for q, j, d in pairs], averages
+
+
 def pairwise_summary(D):
     """PairwiseSummary.run (SpeciesIdentifier/PairwiseSummary.java:109-485).
 

@@ -63,7 +63,7 @@ assert ROW_RESULT_DTYPE.itemsize == 120, ROW_RESULT_DTYPE.itemsize
 EXPORTS = [
     "tdna_abi_version", "tdna_init", "tdna_shutdown", "tdna_last_error", "tdna_stream", "tdna_set_memory_budget",
     "tdna_launch_count", "tdna_alignment_create", "tdna_alignment_destroy", "tdna_alignment_set_labels",
-    "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_row_distances", "tdna_matrix", "tdna_matrix_compute",
+    "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_pairs", "tdna_row_distances", "tdna_matrix", "tdna_matrix_compute",
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
     "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_set_option", "tdna_last_tile_pass_ms",
@@ -99,6 +99,7 @@ def load():
     L.tdna_set_config.argtypes = [vp, i32, i32, i32]
     L.tdna_set_row_range.argtypes = [vp, i64, i64]
     L.tdna_pair.argtypes = [vp, i64, i64, ctypes.POINTER(Counts), ctypes.POINTER(dbl)]
+    L.tdna_pairs.argtypes = [vp, vp, vp, i64, vp, vp]
     L.tdna_row_distances.argtypes = [vp, i64, vp, vp]
     L.tdna_matrix.argtypes = [vp, vp, vp]
     L.tdna_matrix_compute.argtypes = [vp, ctypes.POINTER(vp)]
@@ -210,6 +211,16 @@ class Alignment:
         c, d = Counts(), ctypes.c_double()
         check(self.L.tdna_pair(self.h, i, j, ctypes.byref(c), ctypes.byref(d)))
         return (c.shared, c.c1, c.c2, c.c3), d.value
+
+    def pairs(self, ii, jj, want_counts=False):
+        """A batch of pairs in one launch: returns d (and the counts)."""
+        ii = np.ascontiguousarray(ii, dtype=np.int32)
+        jj = np.ascontiguousarray(jj, dtype=np.int32)
+        assert ii.shape == jj.shape and ii.ndim == 1
+        d = np.empty(len(ii), dtype=np.float64)
+        c = np.empty(len(ii), dtype=COUNTS_DTYPE) if want_counts else None
+        check(self.L.tdna_pairs(self.h, ii.ctypes.data, jj.ctypes.data, len(ii), c.ctypes.data if want_counts else None, d.ctypes.data))
+        return (d, c) if want_counts else d
 
     def row_distances(self, q, want_shared=True):
         d = np.empty(self.n, dtype=np.float64)

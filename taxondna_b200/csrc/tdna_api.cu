@@ -896,6 +896,49 @@ int32_t tdna_pair(tdna_aln *a, int64_t i, int64_t j, tdna_counts *counts, double
     return rc;
 }
 
+int32_t tdna_pairs(tdna_aln *a, const int32_t *ii, const int32_t *jj, int64_t m, tdna_counts *counts, double *d) {
+    TRY(ensure_packed(a));
+    if (m < 0 || (m > 0 && (!ii || !jj))) return fail(TDNA_E_ARG, "bad argument");
+    if (m == 0) return TDNA_OK;
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    const bool di = is_device_ptr(ii), dj = is_device_ptr(jj), dd = d && is_device_ptr(d), dc = counts && is_device_ptr(counts);
+    int32_t *gi = const_cast<int32_t *>(ii), *gj = const_cast<int32_t *>(jj);
+    double *gd = d;
+    tdna_counts *gc = counts;
+    int rc = TDNA_OK;
+    cudaError_t e = cudaSuccess;
+    if (!di) { e = DMALLOC(&gi, (size_t)m * 4); if (e == cudaSuccess) e = cudaMemcpyAsync(gi, ii, (size_t)m * 4, cudaMemcpyDefault, c->stream); }
+    if (e == cudaSuccess && !dj) { e = DMALLOC(&gj, (size_t)m * 4); if (e == cudaSuccess) e = cudaMemcpyAsync(gj, jj, (size_t)m * 4, cudaMemcpyDefault, c->stream); }
+    if (e == cudaSuccess && d && !dd) e = DMALLOC(&gd, (size_t)m * 8);
+    if (e == cudaSuccess && counts && !dc) e = DMALLOC(&gc, (size_t)m * sizeof(tdna_counts));
+    if (e == cudaSuccess) {
+        // indices are checked on the host when they are host memory; device index arrays are the caller's responsibility
+        if (!di) for (int64_t k = 0; k < m; k++) if (ii[k] < 0 || ii[k] >= a->n) { rc = fail(TDNA_E_ARG, "pair index out of range"); break; }
+        if (rc == TDNA_OK && !dj) for (int64_t k = 0; k < m; k++) if (jj[k] < 0 || jj[k] >= a->n) { rc = fail(TDNA_E_ARG, "pair index out of range"); break; }
+    }
+    if (e == cudaSuccess && rc == TDNA_OK) {
+        unsigned grid = (unsigned)((m + 255) / 256);
+        switch (a->kmode) {
+            case KM_P_AMBIG: pairs_from_planes_kernel<KM_P_AMBIG><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, gi, gj, m, a->min_overlap, gd, gc); break;
+            case KM_P_NOAMBIG: pairs_from_planes_kernel<KM_P_NOAMBIG><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, gi, gj, m, a->min_overlap, gd, gc); break;
+            case KM_K2P: pairs_from_planes_kernel<KM_K2P><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, gi, gj, m, a->min_overlap, gd, gc); break;
+            default: pairs_from_planes_kernel<KM_TRANS><<<grid, 256, 0, c->stream>>>(a->d_planes, a->W, gi, gj, m, a->min_overlap, gd, gc); break;
+        }
+        c->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess && d && !dd) e = cudaMemcpyAsync(d, gd, (size_t)m * 8, cudaMemcpyDefault, c->stream);
+        if (e == cudaSuccess && counts && !dc) e = cudaMemcpyAsync(counts, gc, (size_t)m * sizeof(tdna_counts), cudaMemcpyDefault, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    }
+    if (!di && gi) DFREE(gi);
+    if (!dj && gj) DFREE(gj);
+    if (d && !dd && gd) DFREE(gd);
+    if (counts && !dc && gc) DFREE(gc);
+    if (e != cudaSuccess) return fail(TDNA_E_CUDA, cudaGetErrorString(e));
+    return rc;
+}
+
 int32_t tdna_row_distances(tdna_aln *a, int64_t q, double *d, int32_t *shared) {
     TRY(ensure_packed(a));
     if (q < 0 || q >= a->n || !d) return fail(TDNA_E_ARG, "bad argument");

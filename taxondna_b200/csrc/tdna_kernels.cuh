@@ -642,6 +642,21 @@ __global__ void __launch_bounds__(256) row_from_planes_kernel(const uint32_t *__
     }
 }
 
+// an explicit list of pairs straight from the planes (tdna_pairs): thread <-> pair
+template <int KM>
+__global__ void __launch_bounds__(256) pairs_from_planes_kernel(const uint32_t *__restrict__ planes, int W, const int32_t *__restrict__ ii,
+                                                                const int32_t *__restrict__ jj, int64_t m, int min_overlap,
+                                                                double *__restrict__ d_out, tdna_counts *__restrict__ counts_out) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    Counts c = pair_counts_global<KM>(planes, ii[k], jj[k], W);
+    if (d_out) d_out[k] = distance_from_counts<KM>(c, min_overlap);
+    if (counts_out) {
+        tdna_counts o = {c.shared, c.c1, c.c2, c.c3};
+        counts_out[k] = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // per-query summary over one band of the distance matrix (HBM/L2-bound: three sweeps of the
 // query's row, the 2nd and 3rd from L2).  One CTA per query row.

@@ -114,6 +114,26 @@ PYBIND11_MODULE(_host, m) {
         .def("getMinimumDistance", &PairwiseDistribution::getMinimumDistance)
         .def("getDistancesBetween", &PairwiseDistribution::getDistancesBetween);
 
+    py::class_<PairwiseDistances, std::shared_ptr<PairwiseDistances>>(m, "PairwiseDistances")
+        .def(py::init([](const SequenceList &l, int type) { return std::make_shared<PairwiseDistances>(l, type, nullptr); }))
+        .def_readonly_static("PD_INTRA", &PairwiseDistances::PD_INTRA)
+        .def_readonly_static("PD_INTER", &PairwiseDistances::PD_INTER)
+        .def("countSequences", &PairwiseDistances::countSequences)
+        .def("countValidComparisons", &PairwiseDistances::countValidComparisons)
+        .def("getZero", &PairwiseDistances::getZero)
+        .def("getOne", &PairwiseDistances::getOne)
+        .def("getBetween", &PairwiseDistances::getBetween)
+        .def("getBetweenIncl", &PairwiseDistances::getBetweenIncl)
+        .def("getMaximumDistance", &PairwiseDistances::getMaximumDistance)
+        .def("getMinimumDistance", &PairwiseDistances::getMinimumDistance)
+        .def("getAverageDistance", &PairwiseDistances::getAverageDistance)
+        .def("getAveragedSequences", &PairwiseDistances::getAveragedSequences)
+        .def("triples", [](const PairwiseDistances &p) {  // (full name A, full name B, distance) in sorted order
+            std::vector<std::tuple<std::string, std::string, double>> out;
+            for (auto &x : p.all()) out.emplace_back(x.seqA->getFullName(), x.seqB->getFullName(), x.distance);
+            return out;
+        });
+
     py::class_<BestMatch>(m, "BestMatch")
         .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
         .def("setThreshold", &BestMatch::setThreshold)

@@ -10,6 +10,7 @@
 #include <fstream>
 #include <functional>
 #include <map>
+#include <set>
 #include <regex>
 #include <sstream>
 #include <unordered_map>
@@ -387,6 +388,12 @@ std::vector<float> DistanceEngine::classDistances(int klass) const {
         class_cached_ = true;
     }
     return class_cache_[klass == TDNA_PD_INTRA ? 0 : 1];
+}
+std::vector<double> DistanceEngine::pairs(const std::vector<int32_t> &ii, const std::vector<int32_t> &jj) const {
+    syncConfig();
+    std::vector<double> d(ii.size());
+    if (!ii.empty()) ck(tdna_pairs(aln_, ii.data(), jj.data(), (int64_t)ii.size(), nullptr, d.data()));
+    return d;
 }
 void DistanceEngine::edgesBelow(double t, std::vector<int32_t> &ii, std::vector<int32_t> &jj, std::vector<double> &d) const {
     syncConfig();
@@ -853,6 +860,108 @@ PairwiseDistribution::PairwiseDistribution(const SequenceList &list, int type, D
     }
     if (delay) delay->end();
 }
+// ------------------------------------------------------------------------------------------------
+// PairwiseDistances (PairwiseDistances.java:49-377) / PairwiseDistance (PairwiseDistance.java:30-75)
+// ------------------------------------------------------------------------------------------------
+bool PairwiseDistance::isMentioned(const Sequence &s) const { return s.getId() == seqA->getId() || s.getId() == seqB->getId(); }
+
+PairwiseDistances::PairwiseDistances(const SequenceList &list, int type, DelayCallback *delay) {
+    if (type != PD_INTRA && type != PD_INTER) throw std::runtime_error("Programmer Error in PairwiseDistances: Please inform the programmer!");
+    if (delay) delay->begin();
+    const int n = list.count();
+    const auto &seqs = list.sequences();
+    // the pushes in the reference's order: (query, seq) for every query in list order
+    std::vector<int32_t> qi, qj;
+    std::vector<int> first_of_query(n + 1, 0);
+    std::vector<bool> has_entry(n, false);
+    if (n > 0) {
+        const auto &sp = list.engine().speciesId();
+        if (type == PD_INTRA) {  // conspecificIterator = the first contiguous run of the species (SequenceList.java:614-658): see PairwiseDistribution
+            std::unordered_map<int, int> last, first;
+            for (int i = 0; i < n; i++) {
+                if (sp[i] < 0) continue;
+                auto it = last.find(sp[i]);
+                if (it != last.end() && it->second != i - 1)
+                    throw EngineError("conspecific sequences are not contiguous in list order (resort(SORT_BYNAME) first)");
+                if (it == last.end()) first[sp[i]] = i;
+                last[sp[i]] = i;
+            }
+            for (int q = 0; q < n; q++) {
+                first_of_query[q] = (int)qi.size();
+                if (sp[q] < 0) continue;  // :133 no species name: no pushes and NO average entry
+                has_entry[q] = true;
+                for (int x = first[sp[q]]; x <= last[sp[q]]; x++)
+                    if (x != q) { qi.push_back(q); qj.push_back(x); }
+            }
+        } else {
+            std::vector<const std::string *> genus(n), epi(n);
+            for (int i = 0; i < n; i++) { genus[i] = &seqs[i]->getGenusName(); epi[i] = &seqs[i]->getSpeciesNameOnly(); }
+            // group by genus string so that the O(N^2) string compares of :165-181 become per-genus loops (same pushes, same order)
+            std::map<std::string, std::vector<int>> byGenus;
+            for (int i = 0; i < n; i++) byGenus[*genus[i]].push_back(i);
+            for (int q = 0; q < n; q++) {
+                first_of_query[q] = (int)qi.size();
+                has_entry[q] = true;
+                for (int x : byGenus[*genus[q]])  // ascending list positions == list order
+                    if (x != q && *epi[x] != *epi[q]) { qi.push_back(q); qj.push_back(x); }
+            }
+        }
+        first_of_query[n] = (int)qi.size();
+        std::vector<double> d = list.engine().pairs(qi, qj);  // ONE launch instead of one getPairwise per pair
+        std::vector<int> kept;
+        for (int q = 0; q < n; q++) {
+            if (delay) delay->delay(count_sequences_, n);
+            count_sequences_++;
+            if (!has_entry[q]) continue;
+            double total = 0.0;
+            int count = 0;
+            for (int k = first_of_query[q]; k < first_of_query[q + 1]; k++) {
+                if (!(d[k] < 0)) kept.push_back(k);          // distances_push (:64-68): NaN is kept
+                if (d[k] > -1) { total += d[k]; count++; }   // :146-149 / :177-180
+            }
+            averages_.emplace_back(seqs[q]->getFullName(), total / count);  // 0.0 / 0 = NaN, as in Java
+        }
+        // Collections.sort(distances) with PairwiseDistance.compareTo = (int) makeLongFromDouble(d1 - d2) (:58-63)
+        if (!kept.empty())
+            javaSort(kept, [&](int a, int b) -> int { return (int)(int32_t)(uint32_t)(uint64_t)Settings::makeLongFromDouble(d[a] - d[b]); });
+        d_.reserve(kept.size());
+        for (int k : kept) d_.push_back(PairwiseDistance{seqs[qi[k]], seqs[qj[k]], d[k]});
+    }
+    if (delay) delay->end();
+}
+int PairwiseDistances::getZero() const {
+    int c = 0;
+    for (auto &p : d_) { if (Settings::identical(p.distance, 0.0)) c++; else break; }
+    return c;
+}
+int PairwiseDistances::getOne() const {
+    int c = 0;
+    for (int x = (int)d_.size() - 1; x >= 0; x--) { if (Settings::identical(d_[x].distance, 1.0)) c++; else break; }
+    return c;
+}
+std::vector<PairwiseDistance> PairwiseDistances::getDistancesBetween(double from, double to) const {
+    std::vector<PairwiseDistance> v;
+    bool count = false;
+    for (auto &p : d_) {
+        if (p.distance >= from) count = true;
+        if (p.distance > to) break;
+        if (count) v.push_back(p);
+    }
+    return v;
+}
+double PairwiseDistances::getAverageDistance(const std::string &seqName) const {
+    for (auto it = averages_.rbegin(); it != averages_.rend(); ++it)
+        if (it->first == seqName) return it->second;
+    return -1.0;
+}
+std::vector<std::string> PairwiseDistances::getAveragedSequences() const {
+    std::vector<std::string> out;
+    std::set<std::string> seen;
+    for (auto &kv : averages_)
+        if (seen.insert(kv.first).second) out.push_back(kv.first);
+    return out;
+}
+
 static bool pdIdentical(float x, float y) { return (y - x) < 0.0000001; }  // :393-396 (one-sided, float vs double literal)
 int PairwiseDistribution::getZero() const {
     int c = 0;

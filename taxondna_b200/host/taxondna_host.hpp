@@ -164,6 +164,7 @@ class DistanceEngine {
     std::vector<double> matrix() const;  // n x n, row-major
     std::vector<tdna_row_result> bestMatch() const;
     std::vector<float> classDistances(int klass) const;
+    std::vector<double> pairs(const std::vector<int32_t> &ii, const std::vector<int32_t> &jj) const;  // one launch for a pair list
     void edgesBelow(double t, std::vector<int32_t> &ii, std::vector<int32_t> &jj, std::vector<double> &d) const;
     std::vector<uint8_t> validConspecifics() const;
     const std::vector<int32_t> &speciesId() const { return species_id_; }
@@ -223,6 +224,41 @@ class PairwiseDistribution {
 
   private:
     std::vector<float> d_;  // sorted as Arrays.sort(float[]) sorts (NaN last)
+    int count_sequences_ = 0;
+};
+
+// Common/DNA/PairwiseDistance.java:30-75 -- one kept pair
+struct PairwiseDistance {
+    SequencePtr seqA, seqB;
+    double distance;
+    const SequencePtr &getSequenceA() const { return seqA; }
+    const SequencePtr &getSequenceB() const { return seqB; }
+    double getDistance() const { return distance; }
+    bool isMentioned(const Sequence &s) const;
+};
+
+// Common/DNA/PairwiseDistances.java:49-377: like PairwiseDistribution, but the pairs keep their identities, BOTH
+// directions of a pair are pushed (the half-table test is commented out at :171) and a per-sequence mean is kept.
+class PairwiseDistances {
+  public:
+    static constexpr int PD_INTRA = 0, PD_INTER = 1;
+    PairwiseDistances(const SequenceList &list, int type, DelayCallback *delay);
+    int countSequences() const { return count_sequences_; }
+    int countValidComparisons() const { return (int)d_.size(); }
+    int getZero() const;
+    int getOne() const;
+    int getBetween(double from, double to) const { return (int)getDistancesBetween(from, to - 0.000001).size(); }
+    int getBetweenIncl(double from, double to) const { return (int)getDistancesBetween(from, to).size(); }
+    double getMaximumDistance() const { return d_.empty() ? 0.0 : d_.back().distance; }
+    double getMinimumDistance() const { return d_.empty() ? 0.0 : d_.front().distance; }
+    std::vector<PairwiseDistance> getDistancesBetween(double from, double to) const;
+    double getAverageDistance(const std::string &seqName) const;  // -1.0 when the name has no entry
+    std::vector<std::string> getAveragedSequences() const;
+    const std::vector<PairwiseDistance> &all() const { return d_; }
+
+  private:
+    std::vector<PairwiseDistance> d_;  // sorted by PairwiseDistance.compareTo through Collections.sort (TimSort)
+    std::vector<std::pair<std::string, double>> averages_;  // Hashtable.put order; later puts of a name win
     int count_sequences_ = 0;
 };
 

@@ -263,3 +263,23 @@ def test_class_distances_edges_and_valid_conspecifics(ctx):
         expv = [int(sp[i] >= 0 and any(j != i and sp[j] == sp[i] and D[i, j] != -1.0 for j in range(n))) for i in range(n)]
         assert v.tolist() == expv
     aln.close()
+
+
+def test_pairs_batch(ctx):
+    """tdna_pairs: an explicit pair list in one launch (PairwiseDistances / PairwiseExplorer) == the oracle's entries."""
+    import taxondna_b200 as t
+    rng = np.random.default_rng(21)
+    sym, lens = random_alignment(rng, 180, 500, ragged=True)
+    aln = t.Alignment(ctx, sym, lens)
+    ii = rng.integers(0, 180, size=1000).astype(np.int32)
+    jj = rng.integers(0, 180, size=1000).astype(np.int32)
+    for mode in (0, 1, 2):
+        aln.set_config(mode, 120, True)
+        ref = oracle.all_pairs(sym, lens, mode, 120, True, threads=8)
+        d, c = aln.pairs(ii, jj, want_counts=True)
+        assert np.array_equal(u64(d), u64(ref["dist"][ii, jj]))
+        for k in ("shared", "c1", "c2", "c3"):
+            assert np.array_equal(c[k], ref[k][ii, jj]), (mode, k)
+    with pytest.raises(t.TdnaError):
+        aln.pairs(np.array([0, 180], np.int32), np.array([1, 2], np.int32))
+    aln.close()

@@ -119,6 +119,22 @@ def run_all_consumers(H, text, mode, overlap, threshold=3.0, expect_host_rows=No
     ps = H.PairwiseSummary(lst)
     assert ps.run() == stext
     assert np.float32(ps.getFivePercentCutoff()) == five
+    for kind in (H.PairwiseDistances.PD_INTRA, H.PairwiseDistances.PD_INTER):  # PairwiseDistances keeps the pair identities
+        try:
+            exp_pairs, exp_avg = C.pairwise_distances(D, kind)
+        except C.ComparisonContractError:
+            exp_pairs = None
+        if exp_pairs is not None:
+            pd = H.PairwiseDistances(lst, kind)
+            got = pd.triples()
+            assert len(got) == len(exp_pairs) == pd.countValidComparisons()
+            assert [(a, b) for a, b, _ in got] == [(a, b) for a, b, _ in exp_pairs]
+            assert np.array_equal(np.array([d for _, _, d in got]).view(np.uint64), np.array([d for _, _, d in exp_pairs]).view(np.uint64))
+            assert set(pd.getAveragedSequences()) == set(exp_avg)
+            for nm, v in exp_avg.items():
+                g = pd.getAverageDistance(nm)
+                assert (g != g and v != v) or g == v, (nm, g, v)
+            assert pd.getAverageDistance("no such sequence") == -1.0
     oc, ostats = C.cluster(D, threshold / 100)
     cl = H.Cluster(lst)
     cl.setThreshold(threshold)
