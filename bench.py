@@ -15,7 +15,7 @@ between steps.  `e2e`: the same work through the C ABI with HOST buffers (symbol
 host<->device copies inside the timed region.
 
 N > 1 (torchrun, one rank per GPU): every rank holds the whole packed alignment.  Best-Match steps
-share the triangle of tiles cyclically (rank r takes tiles r, r+N, ...: tdna_best_match_part) and
+share the triangle's tile list in N contiguous slices (tdna_best_match_seed / _part_packed) and
 exchange their candidate records / per-row counts once per step over NCCL, then merge; matrix steps
 split the query rows into bands (no collective).  Weak scaling: the alignment grows as sqrt(N) so
 pairs per GPU stay fixed.
@@ -274,6 +274,13 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     tile_ms = []
     cand_counts = []
+    # exchange buffers of the multi-GPU streaming path: one segment of `seg` packed records per rank
+    seg = max(1 << 16, (32 * n) // max(world, 1))
+    xb = None
+    if world > 1 and streaming:
+        xb = {"rec": torch.empty((seg, 2), dtype=torch.int64, device=dev), "count": torch.zeros(1, dtype=torch.int64, device=dev),
+              "counts": torch.zeros(world, dtype=torch.int64, device=dev), "state": torch.empty(n, dtype=torch.int64, device=dev),
+              "allrec": torch.empty((world, seg, 2), dtype=torch.int64, device=dev)}
 
     def best_match_step(a, out_ptr=None):
         """Per-query Best Match summaries for ALL rows, left on the device (or copied to out_ptr)."""
@@ -283,18 +290,19 @@ def main():
             else:
                 a.best_match_into(out_ptr)
             return
-        mins = a.best_match_seed(rank, world)  # diagonal blocks -> per-row minima
+        mins = a.best_match_seed(rank, world)  # this rank's diagonal blocks -> per-row minima
         with torch.cuda.stream(stream):
             mt = torch.as_tensor(_DevBuf(mins, 3 * n, "<i8"), device=dev)
             dist.all_reduce(mt, op=dist.ReduceOp.MIN)  # thresholds from ALL list neighbours on every rank
             stream.synchronize()
-        part = a.best_match_part(rank, world, seeded=True)
-        cand_counts.append(int(part.n_cand))
+        # the part writes packed records / count / per-row state straight into these buffers; NCCL takes them as they are
+        a.best_match_part_packed(rank, world, True, xb["rec"].data_ptr(), seg, xb["count"].data_ptr(), xb["state"].data_ptr())
         with torch.cuda.stream(stream):
-            rows, cols, d, inval, flags = exchange_parts(torch, dist, dev, part, n, world)
+            dist.all_gather_into_tensor(xb["counts"], xb["count"])
+            dist.all_gather_into_tensor(xb["allrec"].view(-1), xb["rec"].view(-1))
+            dist.all_reduce(xb["state"], op=dist.ReduceOp.SUM)
             stream.synchronize()
-        t.check(L_.tdna_best_match_merge(a.h, rows.data_ptr(), cols.data_ptr(), d.data_ptr(), rows.numel(), inval.data_ptr(),
-                                         flags.data_ptr(), out_ptr))
+        a.best_match_merge_gathered(xb["allrec"].data_ptr(), world, seg, xb["counts"].data_ptr(), xb["state"].data_ptr(), out_ptr)
 
     def step_device():
         aln.set_config(mode, 300, True)  # invalidates every cached result: each step recomputes everything
@@ -341,6 +349,8 @@ def main():
         if streaming:
             tile_ms.append(ctx.last_tile_pass_ms())  # the count-tile pass of THIS step (CUDA events on the library's stream)
     barrier()
+    if xb is not None:
+        cand_counts.append(int(xb["count"].item()))
     t_region = time.perf_counter() - t_region0
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -478,7 +488,7 @@ def main():
 
     if rank == 0:
         if streaming:
-            par = ("every %d-th tile of the triangle per rank, one NCCL exchange of candidate records + per-row counts, merge on every rank" % world) if world > 1 else "single GPU, whole triangle"
+            par = ("one of %d contiguous slices of the triangle's tile list per rank; NCCL: all_reduce(min) of the seeded minima, all_gather of the candidate records, all_reduce(sum) of the per-row state; merge on every rank" % world) if world > 1 else "single GPU, whole triangle"
         else:
             par = "row bands, %d rank(s), rows [%d,%d) on rank 0" % (world, b0, b1)
         line = {

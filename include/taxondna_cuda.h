@@ -159,7 +159,7 @@ int32_t tdna_best_match_compute(tdna_aln *aln, const tdna_row_result **out_dev);
  * per-row bound that provably covers every distance tdna_row_result refers to (+ the near-tie
  * window), and the exact two-sweep summary then runs on those short lists (DESIGN.md "streaming
  * Best Match").  The two halves are exposed so that several GPUs can share one pass:
- *   part k of m takes every m-th tile of the triangle; its candidates / per-row invalid-pair counts /
+ *   part k of m takes the k-th of m equal, contiguous slices of the triangle's tile list; its candidates / per-row invalid-pair counts /
  *   per-row flags stay on the device (pointers in *out, valid until the next call on the alignment);
  *   the caller concatenates the candidate records of all parts (NCCL all_gather), sums the invalid
  *   counts and ORs the flags (NCCL all_reduce), and hands the union to tdna_best_match_merge. */
@@ -183,6 +183,18 @@ int32_t tdna_best_match_part(tdna_aln *aln, int32_t part, int32_t nparts, int32_
 /* Inputs are DEVICE pointers (the part's own, or gathered); out: n records, host or device. */
 int32_t tdna_best_match_merge(tdna_aln *aln, const int32_t *cand_row, const int32_t *cand_col, const double *cand_d,
                               int64_t n_cand, const int32_t *invalid_count, const int32_t *flags, tdna_row_result *out);
+
+/* The same exchange without any host-side glue: the part writes PACKED outputs straight into caller-provided DEVICE
+ * buffers that can be handed to NCCL as they are --
+ *   rec   : capacity seg_stride records of two int64: (row << 32 | column), fp64 bits of d(row, column)
+ *   count : one int64, the number of records written (TDNA_E_TOO_LARGE if it would exceed seg_stride)
+ *   state : n int64, invalid_count | (self-valid count << 32) | (non-finite count << 48): SUM-reducible
+ * and tdna_best_match_merge_gathered consumes the all_gathered records (nseg segments of seg_stride records, their
+ * counts on the device) and the all_reduced state.  out: n records, host or device, or NULL (results stay on the device). */
+int32_t tdna_best_match_part_packed(tdna_aln *aln, int32_t part, int32_t nparts, int32_t seeded, int64_t *rec, int64_t seg_stride,
+                                    int64_t *count, int64_t *state);
+int32_t tdna_best_match_merge_gathered(tdna_aln *aln, const int64_t *rec, int32_t nseg, int64_t seg_stride, const int64_t *seg_count,
+                                       const int64_t *state, tdna_row_result *out);
 
 /* ---- one pass, several analyses ------------------------------------------------------------------ */
 /* SpeciesIdentifier runs Pairwise Summary, the threshold percentile, Best (Close) Match and Cluster on the

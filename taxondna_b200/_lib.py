@@ -66,7 +66,7 @@ EXPORTS = [
     "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_pairs", "tdna_row_distances", "tdna_matrix", "tdna_matrix_compute",
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
-    "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_set_option", "tdna_last_tile_pass_ms",
+    "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_set_option", "tdna_last_tile_pass_ms",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -118,6 +118,8 @@ def load():
     L.tdna_best_match_seed.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
     L.tdna_best_match_part.argtypes = [vp, i32, i32, i32, ctypes.POINTER(StreamPart)]
     L.tdna_best_match_merge.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
+    L.tdna_best_match_part_packed.argtypes = [vp, i32, i32, i32, vp, i64, vp, vp]
+    L.tdna_best_match_merge_gathered.argtypes = [vp, vp, i32, i64, vp, vp, vp]
     L.tdna_set_option.argtypes = [vp, i32, i64]
     L.tdna_last_tile_pass_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     _lib = L
@@ -311,6 +313,13 @@ class Alignment:
         sp = StreamPart()
         check(self.L.tdna_best_match_part(self.h, int(part), int(nparts), 1 if seeded else 0, ctypes.byref(sp)))
         return sp
+
+    def best_match_part_packed(self, part, nparts, seeded, rec_ptr, seg_stride, count_ptr, state_ptr):
+        """The part's outputs packed into caller-provided DEVICE buffers (addresses), ready for NCCL."""
+        check(self.L.tdna_best_match_part_packed(self.h, int(part), int(nparts), 1 if seeded else 0, rec_ptr, int(seg_stride), count_ptr, state_ptr))
+
+    def best_match_merge_gathered(self, rec_ptr, nseg, seg_stride, seg_count_ptr, state_ptr, out_ptr=None):
+        check(self.L.tdna_best_match_merge_gathered(self.h, rec_ptr, int(nseg), int(seg_stride), seg_count_ptr, state_ptr, out_ptr))
 
     def best_match_merge(self, cand_row, cand_col, cand_d, n_cand, invalid_count, flags, out=None):
         """All inputs are device addresses (ints); returns the n row records (host)."""

@@ -333,13 +333,15 @@ template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts,
         p.symmetric = 0;
         p.sched = SCHED_STREAM;
         p.first_col_extra = 0;
-        p.t_offset = part;
-        p.t_stride = nparts;
         p.nct = (int)((a->n + Cfg::TN - 1) / Cfg::TN);
         p.nrt = (int)((a->n + TM - 1) / TM);
         p.tile_prefix = a->d_sprefix[ph];
+        // part k of m: a CONTIGUOUS 1/m of the tile list (all tiles cost the same; neighbours in the list share panels in L2)
         int64_t total = a->sprefix_tiles[ph];
-        p.num_tiles = total > part ? (total - part + nparts - 1) / nparts : 0;
+        int64_t t0 = total * part / nparts, t1 = total * (part + 1) / nparts;
+        p.t_offset = t0;
+        p.t_stride = 1;
+        p.num_tiles = t1 - t0;
         if (ph == 0 || a->sp.want == TDNA_WANT_BEST_MATCH) TRY((launch_kernel<KM, CN, EPI_STREAM>(c, p)));
         else TRY((launch_kernel<KM, CN, EPI_STREAM_X>(c, p)));
     }
@@ -545,11 +547,13 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.band = phase ? TC_BAND : 0;
     p.nbands = (p.nrt + TC_BAND - 1) / TC_BAND;
     p.prefix = a->d_tcprefix[1];
-    p.t_offset = part;
-    p.t_stride = nparts;
     int64_t total = a->tcprefix_tiles[phase];   // slots
     if (CL == 2) total = (total + 1) / 2;         // pairs of slots
-    p.num_tiles = total > part ? (total - part + nparts - 1) / nparts : 0;
+    // part k of m: a CONTIGUOUS 1/m of the slot list (all slots cost the same; neighbours in the list share panels in L2)
+    int64_t t0 = total * part / nparts, t1 = total * (part + 1) / nparts;
+    p.t_offset = t0;
+    p.t_stride = 1;
+    p.num_tiles = t1 - t0;
     p.counts = counts;
     p.extras = a->sp.want != TDNA_WANT_BEST_MATCH;
     p.k2p = a->kmode == KM_K2P ? 1 : 0;
@@ -1179,6 +1183,68 @@ int32_t tdna_best_match_part(tdna_aln *a, int32_t part, int32_t nparts, int32_t 
     out->n_cand = ncand;
     out->invalid_count = a->sp.inval;
     out->flags = a->sp.flags;
+    return TDNA_OK;
+}
+
+int32_t tdna_best_match_part_packed(tdna_aln *a, int32_t part, int32_t nparts, int32_t seeded, int64_t *rec, int64_t seg_stride, int64_t *count,
+                                    int64_t *state) {
+    if (!a || !rec || !count || !state || seg_stride < 1 || nparts < 1 || part < 0 || part >= nparts) return fail(TDNA_E_ARG, "bad argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(need_labels(a));
+    if (seeded && !a->stream_alloc) return fail(TDNA_E_STATE, "tdna_best_match_seed has not run");
+    long long ncand = 0;
+    if (seeded) TRY(stream_bulk(a, part, nparts, &ncand));
+    else TRY(stream_part(a, part, nparts, &ncand));
+    if (ncand > seg_stride) return fail(TDNA_E_TOO_LARGE, "the part's candidates do not fit the exchange segment");
+    unsigned gr = (unsigned)((ncand + 255) / 256);
+    if (gr < 1) gr = 1;
+    if (gr > 65535u * 4) gr = 65535u * 4;
+    pack_records_kernel<<<gr, 256, 0, c->stream>>>(a->sp.cq, a->sp.cj, a->sp.cd, ncand, reinterpret_cast<long long *>(rec));
+    pack_state_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp.inval, a->sp.flags, a->n, ncand, reinterpret_cast<long long *>(state),
+                                                                            reinterpret_cast<long long *>(count));
+    c->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));  // the caller hands the buffers to NCCL on another stream
+    return TDNA_OK;
+}
+
+int32_t tdna_best_match_merge_gathered(tdna_aln *a, const int64_t *rec, int32_t nseg, int64_t seg_stride, const int64_t *seg_count, const int64_t *state,
+                                       tdna_row_result *out) {
+    if (!a || !rec || !seg_count || !state || nseg < 1 || seg_stride < 1) return fail(TDNA_E_ARG, "bad argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(need_labels(a));
+    TRY(ensure_packed(a));
+    TRY(ensure_stream_state(a));
+    if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+    size_t n = (size_t)a->n;
+    const long long total = (long long)nseg * seg_stride;  // upper bound of the records: sizes the lists without a host round trip
+    if (total > a->list_cap) {
+        if (a->d_lj) CU(DFREE(a->d_lj));
+        if (a->d_ld) CU(DFREE(a->d_ld));
+        a->d_lj = nullptr;
+        a->d_ld = nullptr;
+        CU(DMALLOC(&a->d_lj, (size_t)total * 4));
+        CU(DMALLOC(&a->d_ld, (size_t)total * 8));
+        a->list_cap = total;
+    }
+    unsigned gr = (unsigned)((total + 255) / 256);
+    if (gr > 65535u * 4) gr = 65535u * 4;
+    const long long *lrec = reinterpret_cast<const long long *>(rec), *lcnt = reinterpret_cast<const long long *>(seg_count);
+    unpack_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const long long *>(state), a->n, a->sp.inval, a->sp.flags);
+    CU(cudaMemsetAsync(a->sp.cnt, 0, n * 4, c->stream));
+    CU(cudaMemsetAsync(a->d_cursor, 0, n * 4, c->stream));
+    count_rows_seg_kernel<<<gr, 256, 0, c->stream>>>(lrec, nseg, seg_stride, lcnt, a->sp.cnt);
+    exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(a->sp.cnt, a->n, a->d_ptr);
+    scatter_seg_kernel<<<gr, 256, 0, c->stream>>>(lrec, nseg, seg_stride, lcnt, a->d_ptr, a->d_cursor, a->d_lj, a->d_ld);
+    stream_finalize_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, a->sp.inval, a->sp.flags, a->d_species, a->n,
+                                                                                    a->d_res);
+    c->launches += 5;
+    CU(cudaGetLastError());
+    TRY(fill_shared(a, 0, a->n));
+    if (out) CU(cudaMemcpyAsync(out, a->d_res, n * sizeof(tdna_row_result), cudaMemcpyDefault, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return TDNA_OK;
 }
 

@@ -1114,6 +1114,52 @@ __global__ void __launch_bounds__(256) count_rows_kernel(const int32_t *__restri
         atomicAdd(cnt + cq[r], 1);
 }
 
+// ---- packed exchange format (tdna_best_match_part_packed / _merge_gathered) ----------------------------------
+__global__ void __launch_bounds__(256) pack_records_kernel(const int32_t *__restrict__ cq, const int32_t *__restrict__ cj, const double *__restrict__ cd,
+                                                           long long ncand, long long *__restrict__ rec) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < ncand; r += (long long)gridDim.x * blockDim.x) {
+        rec[2 * r] = ((long long)cq[r] << 32) | (long long)(uint32_t)cj[r];
+        rec[2 * r + 1] = __double_as_longlong(cd[r]);
+    }
+}
+__global__ void __launch_bounds__(256) pack_state_kernel(const int *__restrict__ inval, const int *__restrict__ flags, int64_t n, long long ncand,
+                                                         long long *__restrict__ state, long long *__restrict__ count) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) *count = ncand;
+    if (q >= n) return;
+    const int f = flags[q];
+    state[q] = (long long)(uint32_t)inval[q] | ((long long)(f & TDNA_ROW_SELF_VALID ? 1 : 0) << 32) | ((long long)(f & TDNA_ROW_NONFINITE ? 1 : 0) << 48);
+}
+__global__ void __launch_bounds__(256) unpack_state_kernel(const long long *__restrict__ state, int64_t n, int *__restrict__ inval, int *__restrict__ flags) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const long long s = state[q];
+    inval[q] = (int)(s & 0xffffffffll);
+    flags[q] = (((s >> 32) & 0xffff) ? TDNA_ROW_SELF_VALID : 0) | (((s >> 48) & 0xffff) ? TDNA_ROW_NONFINITE : 0);
+}
+// gathered segments: segment g holds seg_count[g] records at rec + 2 * g * seg_stride
+__global__ void __launch_bounds__(256) count_rows_seg_kernel(const long long *__restrict__ rec, int nseg, long long seg_stride,
+                                                             const long long *__restrict__ seg_count, int *__restrict__ cnt) {
+    const long long total = (long long)nseg * seg_stride;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
+        if (r % seg_stride >= seg_count[r / seg_stride]) continue;
+        atomicAdd(cnt + (int)(rec[2 * r] >> 32), 1);
+    }
+}
+__global__ void __launch_bounds__(256) scatter_seg_kernel(const long long *__restrict__ rec, int nseg, long long seg_stride,
+                                                          const long long *__restrict__ seg_count, const long long *__restrict__ ptr,
+                                                          int *__restrict__ cursor, int32_t *__restrict__ lj, double *__restrict__ ld) {
+    const long long total = (long long)nseg * seg_stride;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
+        if (r % seg_stride >= seg_count[r / seg_stride]) continue;
+        const long long key = rec[2 * r];
+        const int q = (int)(key >> 32);
+        const long long slot = ptr[q] + atomicAdd(cursor + q, 1);
+        lj[slot] = (int32_t)(key & 0xffffffffll);
+        ld[slot] = __longlong_as_double(rec[2 * r + 1]);
+    }
+}
+
 // one warp per query row: the two sweeps over the row's candidate list (complete below its threshold)
 __global__ void __launch_bounds__(256) stream_finalize_kernel(const long long *__restrict__ ptr, const int32_t *__restrict__ lj,
                                                               const double *__restrict__ ld, const int *__restrict__ inval,

@@ -264,3 +264,50 @@ def test_one_pass_analysis_equals_the_dense_functions(ctx, mode, shuffle, ragged
     assert np.array_equal(np.sort(aln.class_distances(t.PD_INTRA)).view(np.uint32), d_intra.view(np.uint32))
     assert sorted(zip(*[x.tolist() for x in aln.edges_below(thr)])) == d_edges
     aln.close()
+
+
+def test_packed_parts_exchange_on_one_device(ctx):
+    """The glue-free multi-GPU data flow (tdna_best_match_part_packed -> NCCL -> tdna_best_match_merge_gathered), three ranks
+    played by one device: seeds MIN-reduced, packed segments placed side by side, states summed."""
+    import torch
+    import taxondna_b200 as t
+    rng = np.random.default_rng(123)
+    sym, lens, sp, gen, epi, full = make(rng, 36, 8, 500, unnamed=4, dup=8, gap=0.05, ragged=True, shuffle=False, singletons=4)
+    n = sym.shape[0]
+    aln = t.Alignment(ctx, sym, lens)
+    aln.set_labels(sp, gen, epi, full)
+
+    class Dev:
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+    for mode, kern in ((0, t.KERNEL_POPC), (1, t.KERNEL_POPC), (0, t.KERNEL_AUTO)):
+        aln.set_config(mode, 260, True)
+        ctx.set_option(t.OPT_COUNT_KERNEL, kern)
+        ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_STREAM)
+        whole = aln.best_match()
+        world, seg = 3, 32 * n
+        allmin = None
+        for part in range(world):
+            m = torch.as_tensor(Dev(aln.best_match_seed(part, world), (3 * n,), "<i8"), device="cuda").clone()
+            allmin = m if allmin is None else torch.minimum(allmin, m)
+        allrec = torch.zeros((world, seg, 2), dtype=torch.int64, device="cuda")
+        counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+        state = torch.zeros(n, dtype=torch.int64, device="cuda")
+        for part in range(world):
+            mp = aln.best_match_seed(part, world)
+            torch.as_tensor(Dev(mp, (3 * n,), "<i8"), device="cuda").copy_(allmin)
+            st = torch.zeros(n, dtype=torch.int64, device="cuda")
+            torch.cuda.synchronize()
+            aln.best_match_part_packed(part, world, True, allrec[part].data_ptr(), seg, counts[part:].data_ptr(), st.data_ptr())
+            state += st
+        torch.cuda.synchronize()
+        out = np.zeros(n, dtype=t.ROW_RESULT_DTYPE)
+        aln.best_match_merge_gathered(allrec.data_ptr(), world, seg, counts.data_ptr(), state.data_ptr(), out.ctypes.data)
+        assert first_difference(out, whole) is None, (mode, kern, first_difference(out, whole))
+        with pytest.raises(t.TdnaError) as ei:  # a segment that is too small is reported, not overrun
+            aln.best_match_part_packed(0, 1, False, allrec.data_ptr(), 8, counts.data_ptr(), state.data_ptr())
+        assert ei.value.code == 5
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+    aln.close()
