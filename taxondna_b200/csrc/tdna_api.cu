@@ -549,11 +549,15 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.prefix = a->d_tcprefix[1];
     int64_t total = a->tcprefix_tiles[phase];   // slots
     if (CL == 2) total = (total + 1) / 2;         // pairs of slots
-    // part k of m: a CONTIGUOUS 1/m of the slot list (all slots cost the same; neighbours in the list share panels in L2)
-    int64_t t0 = total * part / nparts, t1 = total * (part + 1) / nparts;
-    p.t_offset = t0;
-    p.t_stride = 1;
-    p.num_tiles = t1 - t0;
+    // part k of m takes every m-th UNIT of 128 consecutive slots (16 row tiles x 8 column tiles of one band: the panels a
+    // unit shares stay in this GPU's L2); units are dealt cyclically so that work AND candidates (which cluster near the
+    // diagonal) are balanced across the parts
+    p.unit = CL == 2 ? 64 : 128;
+    int64_t units_total = (total + p.unit - 1) / p.unit;
+    int64_t my_units = units_total > part ? (units_total - part + nparts - 1) / nparts : 0;
+    p.t_offset = part;
+    p.t_stride = nparts;
+    p.num_tiles = my_units * p.unit;  // items past the end of the list are skipped by the kernel
     p.counts = counts;
     p.extras = a->sp.want != TDNA_WANT_BEST_MATCH;
     p.k2p = a->kmode == KM_K2P ? 1 : 0;

@@ -49,7 +49,8 @@ struct Params {
     int band;           // 0: seed pass, tile t = (row tile t, column tile t / 2); else row tiles per band of the whole triangle
     int nbands;
     const int64_t *prefix;  // bulk phase: [nbands + 1] tile slots before band b
-    int64_t num_tiles, t_offset, t_stride;
+    int64_t num_tiles, t_offset, t_stride;  // this launch's k-th work item is global item ((k / unit) * t_stride + t_offset) * unit + k % unit
+    int unit;               // work items per scheduling unit (parts take units cyclically: balanced in work AND in candidates)
     tdna_counts *counts;    // verification mode: n x n counts (row-major), else null
     int extras;             // stream mode: classes / edges wanted (c_sp.want beyond Best Match)
     int k2p;                // the accumulator carries (n, ts + tv) of the K2P model; exact counts come from the bit-planes
@@ -81,14 +82,16 @@ __device__ __forceinline__ bool slot_coords(const Params &p, const int64_t *pref
     return ti < p.nrt && tj < p.nct && tj >= (ti >> 1);
 }
 
-// k-th work item of this CTA.  CL = 1: slot t_offset + (blockIdx.x + k * gridDim.x) * t_stride.  CL = 2: the cluster takes the PAIR
-// of slots (2u, 2u + 1), u = t_offset + (cluster id + k * clusters) * t_stride -- same column tile, adjacent row tiles -- and this
+// k-th work item of this CTA (items = slots for CL = 1, PAIRS of slots (2u, 2u + 1) -- same column tile, adjacent row tiles -- for
+// CL = 2); a part takes every t_stride-th UNIT of `unit` consecutive items.  Items past the end of the list are empty.  CL = 2: this
 // CTA the one of its cluster rank; the pair is as valid as its even slot (an odd row tile past the end reads zero-filled operands).
 template <int CL> __device__ __forceinline__ bool my_tile(const Params &p, int64_t k, uint32_t rank, int &ti, int &tj) {
     if constexpr (CL == 1) {
-        return slot_coords(p, p.prefix, p.t_offset + ((int64_t)blockIdx.x + k * gridDim.x) * p.t_stride, ti, tj);
+        const int64_t l = (int64_t)blockIdx.x + k * gridDim.x;
+        return slot_coords(p, p.prefix, ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit, ti, tj);
     } else {
-        const int64_t u = p.t_offset + ((int64_t)(blockIdx.x >> 1) + k * (gridDim.x >> 1)) * p.t_stride;
+        const int64_t l = (int64_t)(blockIdx.x >> 1) + k * (gridDim.x >> 1);
+        const int64_t u = ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit;
         const bool ok = slot_coords(p, p.prefix, 2 * u, ti, tj);
         ti += (int)rank;
         return ok;
