@@ -1062,10 +1062,15 @@ static int ensure_stream_state(tdna_aln *a) {
     CU(DMALLOC(&sp.cq, (size_t)cap * 4));
     CU(DMALLOC(&sp.cj, (size_t)cap * 4));
     CU(DMALLOC(&sp.cd, (size_t)cap * 8));
-    CU(DMALLOC(&sp.qi, (size_t)cap * 4));
-    CU(DMALLOC(&sp.qj, (size_t)cap * 4));
-    CU(DMALLOC(&sp.qv, (size_t)cap * 4));
-    sp.qcap = cap;
+    // kernel (b)'s queue holds every pair that passes the SEEDED threshold of either of its rows (about four times the final
+    // candidates): 256 per row, 12 bytes each
+    long long qcap = (long long)n * 256;
+    if (qcap < (1ll << 22)) qcap = 1ll << 22;
+    if (qcap * 12 > c->budget / 2) qcap = c->budget / 24;
+    CU(DMALLOC(&sp.qi, (size_t)qcap * 4));
+    CU(DMALLOC(&sp.qj, (size_t)qcap * 4));
+    CU(DMALLOC(&sp.qv, (size_t)qcap * 4));
+    sp.qcap = qcap;
     CU(DMALLOC(&a->d_stream_u64, 64));  // ncand, overflow, ncls[2], nedge, qn
     sp.ncand = reinterpret_cast<unsigned long long *>(a->d_stream_u64);
     sp.overflow = reinterpret_cast<int *>(reinterpret_cast<char *>(a->d_stream_u64) + 8);
