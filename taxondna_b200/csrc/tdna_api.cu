@@ -99,6 +99,7 @@ struct tdna_aln {
     long long list_cap = 0;
     long long last_ncand = 0, last_ncls[2] = {0, 0}, last_nedge = 0;
     int last_kernel = 0;  // TDNA_KERNEL_* of the most recent streaming pass
+    bool avoid_tensor = false;  // AUTO: kernel (b)'s queue overflowed on this alignment (static thresholds too loose): use kernel (a)
     // count kernel (b): one-hot int8 operands (tdna_tc.cuh)
     uint8_t *d_tcA = nullptr, *d_tcB = nullptr;
     int tc_state = 0;  // 0 = not built, 1 = ready, -1 = not eligible
@@ -366,7 +367,7 @@ template <int KM> int launch_stream_km(tdna_aln *a, int part, int nparts, int ph
 int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
     tdna_ctx *c = a->ctx;
     // AUTO: kernel (b) wherever it is eligible -- it is ~3x faster than kernel (a) there (profiles/)
-    bool tensor = c->opt_count_kernel == TDNA_KERNEL_TENSOR || (c->opt_count_kernel == TDNA_KERNEL_AUTO && ensure_tc(a) == 1);
+    bool tensor = c->opt_count_kernel == TDNA_KERNEL_TENSOR || (c->opt_count_kernel == TDNA_KERNEL_AUTO && !a->avoid_tensor && ensure_tc(a) == 1);
     a->last_kernel = tensor ? TDNA_KERNEL_TENSOR : TDNA_KERNEL_POPC;
     if (tensor) {
         if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p (ambiguity allowed) or K2P, an alignment without IUPAC ambiguity letters, L < 4096");
@@ -1400,6 +1401,11 @@ int32_t tdna_analyze(tdna_aln *a, tdna_analysis *io) {
     bool have_matrix = a->mat_valid && c->mat_owner == a && !(io->want & TDNA_WANT_BEST_MATCH) && c->opt_best_match_path != TDNA_PATH_STREAM;
     if (whole && c->opt_best_match_path != TDNA_PATH_DENSE && a->has_labels && !have_matrix) {
         int rc = analyze_stream(a, io);
+        if (rc == TDNA_E_TOO_LARGE && c->opt_count_kernel == TDNA_KERNEL_AUTO && a->last_kernel == TDNA_KERNEL_TENSOR) {
+            // kernel (b) filters with the seeded thresholds only; kernel (a) tightens them while it runs: try it before the matrix
+            a->avoid_tensor = true;
+            rc = analyze_stream(a, io);
+        }
         if (rc != TDNA_E_TOO_LARGE || c->opt_best_match_path == TDNA_PATH_STREAM) return rc;
     }
     return analyze_dense(a, io);

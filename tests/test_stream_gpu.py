@@ -311,3 +311,34 @@ def test_packed_parts_exchange_on_one_device(ctx):
     ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
     ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
     aln.close()
+
+
+def test_auto_falls_back_from_kernel_b_to_kernel_a_on_a_shuffled_list(ctx):
+    """A list in random order: the diagonal blocks hold unrelated rows, so kernel (b)'s static thresholds are loose and its queue
+    overflows (small budget here); AUTO retries on kernel (a), whose thresholds tighten while it runs, and the records still
+    equal the dense path's."""
+    import taxondna_b200 as t
+    from taxondna_b200 import synth
+    data = synth.generate("C3", names=False, genera=40, species=10, reps=10)
+    rng = np.random.default_rng(8)
+    perm = rng.permutation(data["symbols"].shape[0])
+    sym = data["symbols"][perm]
+    lab = [data[k][perm] for k in ("species_id", "genus_id", "epithet_rank", "fullname_rank")]
+    ctx.set_memory_budget(24 << 20)  # queue capacity = budget / 24 records (~ 1 M), candidates budget / 32
+    try:
+        aln = t.Alignment(ctx, sym)
+        aln.set_labels(*lab)
+        aln.set_config(0, 300, True)
+        ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+        ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
+        auto = aln.best_match()
+        used = aln.last_count_kernel()
+        ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_DENSE)
+        ctx.set_memory_budget(64 << 30)
+        dense = aln.best_match()
+        assert first_difference(auto, dense) is None, first_difference(auto, dense)
+        print("shuffled list, AUTO ended on count kernel", used)
+        aln.close()
+    finally:
+        ctx.set_memory_budget(64 << 30)
+        ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
