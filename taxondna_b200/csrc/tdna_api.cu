@@ -101,12 +101,12 @@ struct tdna_aln {
     int last_kernel = 0;  // TDNA_KERNEL_* of the most recent streaming pass
     bool avoid_tensor = false;  // AUTO: kernel (b)'s queue overflowed on this alignment (static thresholds too loose): use kernel (a)
     // count kernel (b): one-hot int8 operands (tdna_tc.cuh)
-    uint8_t *d_tcA = nullptr, *d_tcB = nullptr;
+    uint8_t *d_tcA = nullptr, *d_tcB = nullptr, *d_tcfull = nullptr;
     int tc_state = 0;  // 0 = not built, 1 = ready, -1 = not eligible
     int tc_nchunks = 0, tc_kmode = -1, tc_dims = 5;
     uint32_t tc_W = 0;
     CUtensorMap tc_mapA, tc_mapB, tc_mapBh;  // [.., 256 x uint32] views of d_tcA / d_tcB, boxes of one operand block (Bh: half a b-block)
-    bool tc_maps = false;
+    bool tc_maps = false, tc_pair = false;
     int tc_inner = 256;
     int64_t *d_tcprefix[2] = {nullptr, nullptr};
     int64_t tcprefix_tiles[2] = {0, 0};
@@ -406,6 +406,10 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
 }
 
 // ---- count kernel (b): operands, launches ----------------------------------------------------------
+static bool tc_pair_mode() {  // TDNA_TC_CLUSTER: 1 = single CTAs, 2 = pairs sharing the b-panel by multicast, 3 = cta_group::2 MMAs
+    const char *e = getenv("TDNA_TC_CLUSTER");  // default 2: measured 2.79 ms against 2.86 ms for cta_group::2 on the 50,000 x 658 pass
+    return (e ? atoi(e) : 2) == 3;
+}
 static int tc_band() {  // row tiles per band of the bulk phase (TDNA_TC_BAND overrides, for experiments)
     const char *e = getenv("TDNA_TC_BAND");
     int v = e ? atoi(e) : 16;
@@ -441,6 +445,8 @@ int ensure_tc(tdna_aln *a) {
     if (a->tc_state == 1 && a->tc_kmode != a->kmode) {  // the operands encode the mode's valid-symbol set: rebuild
         DFREE(a->d_tcA);
         DFREE(a->d_tcB);
+        if (a->d_tcfull) DFREE(a->d_tcfull);
+        a->d_tcfull = nullptr;
         if (a->d_tcprefix[1]) DFREE(a->d_tcprefix[1]);
         a->d_tcA = a->d_tcB = nullptr;
         a->d_tcprefix[1] = nullptr;
@@ -460,8 +466,20 @@ int ensure_tc(tdna_aln *a) {
     }
     int *d_flag = reinterpret_cast<int *>(c->d_counter);
     cudaMemsetAsync(d_flag, 0, 8, c->stream);
-    tc::encode_kernel<false><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcA, d_flag);
-    tc::encode_kernel<true><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::N)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcB, d_flag);
+    // per 128-row panel: does any of its rows have a site that contributes nothing ('_', '?', beyond the row; '-' for K2P)?
+    size_t npan = (size_t)(npb / tc::M);
+    if (a->d_tcfull) DFREE(a->d_tcfull);
+    a->d_tcfull = nullptr;
+    if (cudaSuccess != DMALLOC(&a->d_tcfull, npan)) { cudaGetLastError(); a->tc_state = -1; return -1; }
+    cudaMemsetAsync(a->d_tcfull, 0, npan, c->stream);
+    tc::encode_kernel<false, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcA, d_flag, a->d_tcfull);
+    if (tc_pair_mode())  // cta_group::2: the b-side in 128-row panels as well (each CTA of a pair stages half of the tile's columns)
+        tc::encode_kernel<true, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcB, d_flag, nullptr);
+    else
+        tc::encode_kernel<true, tc::N><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::N)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcB, d_flag, nullptr);
+    a->tc_pair = tc_pair_mode();
+    tc::flip_flags_kernel<<<(unsigned)((npan + 255) / 256), 256, 0, c->stream>>>(a->d_tcfull, (int64_t)npan, (int64_t)((a->n + tc::M - 1) / tc::M));  // gappy -> full
+    c->launches++;
     c->launches += 2;
     int flag = 0;
     cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream);
@@ -549,11 +567,11 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.nbands = (p.nrt + TC_BAND - 1) / TC_BAND;
     p.prefix = a->d_tcprefix[1];
     int64_t total = a->tcprefix_tiles[phase];   // slots
-    if (CL == 2) total = (total + 1) / 2;         // pairs of slots
+    if (CL >= 2) total = (total + 1) / 2;         // pairs of slots
     // part k of m takes every m-th UNIT of 128 consecutive slots (16 row tiles x 8 column tiles of one band: the panels a
     // unit shares stay in this GPU's L2); units are dealt cyclically so that work AND candidates (which cluster near the
     // diagonal) are balanced across the parts
-    p.unit = CL == 2 ? 64 : 128;
+    p.unit = CL >= 2 ? 64 : 128;
     int64_t units_total = (total + p.unit - 1) / p.unit;
     int64_t my_units = units_total > part ? (units_total - part + nparts - 1) / nparts : 0;
     p.t_offset = part;
@@ -562,6 +580,8 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.counts = counts;
     p.extras = a->sp.want != TDNA_WANT_BEST_MATCH;
     p.k2p = a->kmode == KM_K2P ? 1 : 0;
+    p.panel_full = a->d_tcfull;
+    p.L = a->L;
     p.planes = a->d_planes;
     p.W32 = a->W;
     {
@@ -572,9 +592,9 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     if (const char *e = getenv("TDNA_TC_HINTS")) p.hints = atoi(e);
     p.a_rows = tc::A_STAGE / (a->tc_inner * 4);
     p.b_rows = tc::B_STAGE / (a->tc_inner * 4);
-    int64_t units = CL == 2 ? c->sm_count / 2 : c->sm_count;
+    int64_t units = CL >= 2 ? c->sm_count / 2 : c->sm_count;
     if (const char *e = getenv("TDNA_TC_GRID")) { int v = atoi(e); if (v >= 1 && v < units) units = v; }
-    int64_t grid = (p.num_tiles < units ? p.num_tiles : units) * CL;
+    int64_t grid = (p.num_tiles < units ? p.num_tiles : units) * (CL >= 2 ? 2 : 1);
     if (grid < 1) return TDNA_OK;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -583,7 +603,7 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.x = CL >= 2 ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -598,7 +618,10 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
 template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts) {
     const char *e = getenv("TDNA_TC_CLUSTER");
     int cl = e ? atoi(e) : 2;
-    if (!a->tc_maps || (TC_BAND & 1)) cl = 1;
+    if (a->tc_pair) cl = 3;          // the b-side operands were encoded for cta_group::2
+    else if (cl == 3) cl = 2;
+    if (!a->tc_maps || (TC_BAND & 1)) { if (a->tc_pair) return fail(TDNA_E_STATE, "cta_group::2 needs the tensor maps"); cl = 1; }
+    if (cl == 3) return launch_tc_cl<COUNTS_MODE, 3>(a, phase, part, nparts, counts);
     if (cl == 2) return launch_tc_cl<COUNTS_MODE, 2>(a, phase, part, nparts, counts);
     return launch_tc_cl<COUNTS_MODE, 1>(a, phase, part, nparts, counts);
 }
@@ -801,7 +824,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     cudaSetDevice(c->device);
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
-                    a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
+                    a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_cursor, a->d_lj, a->d_ld};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream

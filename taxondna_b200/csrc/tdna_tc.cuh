@@ -53,6 +53,8 @@ struct Params {
     int unit;               // work items per scheduling unit (parts take units cyclically: balanced in work AND in candidates)
     tdna_counts *counts;    // verification mode: n x n counts (row-major), else null
     int extras;             // stream mode: classes / edges wanted (c_sp.want beyond Best Match)
+    const uint8_t *panel_full;  // [128-row panel] 1 = every row of the panel is valid at every site: pairs of two such panels share L sites
+    int L;
     int k2p;                // the accumulator carries (n, ts + tv) of the K2P model; exact counts come from the bit-planes
     const uint32_t *planes; // K2P: the popc kernel's planes, for the exact counts of queued / class pairs
     int W32;
@@ -105,10 +107,10 @@ struct EncodeValues {
 // one CTA = one operand block (panel x K-chunk): the ~27 sites the chunk covers are staged as symbol codes in shared
 // memory (coalesced 27-byte runs per row), then every thread emits 16-byte units in memory order (coalesced uint4 stores)
 constexpr int ENC_SITES = KB / 4 + 3;
-template <bool BSIDE>
+template <bool BSIDE, int ROWS>
 __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len, int64_t n, int64_t sym_stride,
-                                                     int L, int nchunks, int DIMS, EncodeValues v, uint8_t *__restrict__ out, int *__restrict__ not_clean) {
-    constexpr int ROWS = BSIDE ? N : M;
+                                                     int L, int nchunks, int DIMS, EncodeValues v, uint8_t *__restrict__ out, int *__restrict__ not_clean,
+                                                     uint8_t *__restrict__ panel_gappy) {
     __shared__ uint8_t codes[ROWS][ENC_SITES + 1];  // 0..4 = A C G T '-', 5 = no contribution ('_', '?', beyond the row; '-' when DIMS == 4)
     const int c = blockIdx.x;
     const int64_t panel = blockIdx.y;
@@ -131,6 +133,8 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
             }
         }
         codes[row_l][s] = code;
+        // a site of the alignment (site < L) of an existing row that contributes nothing: the panel is not "full"
+        if (panel_gappy && row < n && site < L && s < (KB + DIMS - 1) / DIMS + 1 && code >= DIMS) panel_gappy[panel] = 1;
     }
     if (bad) atomicOr(not_clean, 1);
     __syncthreads();
@@ -148,6 +152,12 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
         }
         dst[u] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+
+// panel_gappy -> panel_full; panels beyond the last row are not full (their pairs are out of range anyway)
+__global__ void __launch_bounds__(256) flip_flags_kernel(uint8_t *flags, int64_t npan, int64_t real_panels) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < npan) flags[k] = (k < real_panels && flags[k] == 0) ? 1 : 0;
 }
 
 // ---- tcgen05 / TMEM primitives ---------------------------------------------------------------
@@ -217,6 +227,34 @@ __device__ __forceinline__ void tma_load_2d_mc(void *dst_smem, const CUtensorMap
 __device__ __forceinline__ void mma_commit_mc(uint64_t *bar, uint16_t cta_mask) {  // arrive on the same barrier of every CTA in the mask
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
+// cta_group::2: both CTAs of the pair load into their own shared memory, the bytes are credited to the LEADER's barrier
+// (the barrier address with the peer bit cleared addresses CTA 0 of the pair)
+__device__ __forceinline__ void tma_load_2d_pair(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(L2_EVICT_NORMAL)
+                 : "memory");
+}
+constexpr uint32_t IDESC_PAIR = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * M) >> 4) << 24);
+__device__ __forceinline__ void mma_i8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {  // M = 256 across the CTA pair
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC_PAIR), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair(uint64_t *bar) {  // arrives on the same barrier of BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar, uint32_t cta) {  // arrive on `bar` of CTA `cta` of the cluster
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -226,34 +264,43 @@ __device__ __forceinline__ void cluster_sync_all() {
 template <bool COUNTS_MODE, int CL>
 __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                           const __grid_constant__ CUtensorMap mapBh, Params p) {
+    // CL = 3: the pair runs ONE M = 256 MMA (cta_group::2): each CTA stages its own a-panel and its 128-row HALF of the
+    // b-panel, i.e. 32 KB per stage instead of 48 KB -> a six-deep ring, and half the b-operand shared-memory reads
+    constexpr bool PAIR = CL == 3;
+    constexpr int B_ST = PAIR ? B_STAGE / 2 : B_STAGE, STG = A_STAGE + B_ST, NST = PAIR ? 6 : NSTAGE;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)NSTAGE * STAGE);
-    uint64_t *empty = full + NSTAGE;
-    uint64_t *tfull = empty + NSTAGE;   // [2] accumulator stage ready for the epilogue
+    uint64_t *empty = full + 8;
+    uint64_t *tfull = empty + 8;        // [2] accumulator stage ready for the epilogue
     uint64_t *tempty = tfull + 2;       // [2] accumulator stage drained
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     uint32_t *col_thr = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * STAGE + 256);  // [EPI_WARPS][EPI_COLS]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t rank = 0;
-    if constexpr (CL == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if constexpr (CL >= 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int64_t units = CL == 1 ? gridDim.x : (gridDim.x >> 1), first = CL == 1 ? blockIdx.x : (blockIdx.x >> 1);
     const int64_t my_tiles = (p.num_tiles > first) ? (p.num_tiles - first + units - 1) / units : 0;  // tiles (CL = 1) or tile pairs (CL = 2)
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-        for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
+        for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL == 2 ? 2 : 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulator stages)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     fence_before();
     __syncthreads();
     fence_after();
-    if constexpr (CL == 2) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
+    if constexpr (CL >= 2) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
 
     if (warp == 0) {
@@ -266,10 +313,16 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                 const uint8_t *ga = p.A + (size_t)ti * p.nchunks * A_STAGE;
                 const uint8_t *gb = p.B + (size_t)tj * p.nchunks * B_STAGE;
                 for (int c = 0; c < p.nchunks; c++, it++) {
-                    const int slot = (int)(it % NSTAGE);
-                    if (it >= NSTAGE) mbar_wait(&empty[slot], (uint32_t)(((it / NSTAGE) - 1) & 1));  // the ring IS the bottleneck here: no back-off
-                    uint8_t *sa = smem + (size_t)slot * STAGE, *sb = sa + A_STAGE;
-                    mbar_expect_tx(&full[slot], STAGE);
+                    const int slot = (int)(it % NST);
+                    if (it >= NST) mbar_wait(&empty[slot], (uint32_t)(((it / NST) - 1) & 1));  // the ring IS the bottleneck here: no back-off
+                    uint8_t *sa = smem + (size_t)slot * STG, *sb = sa + A_STAGE;
+                    if constexpr (PAIR) {  // both CTAs load (own a-panel, own half of the b-panel); the leader's barrier counts all 64 KB
+                        if (rank == 0) mbar_expect_tx(&full[slot], 2 * STG);
+                        tma_load_2d_pair(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * p.a_rows), &full[slot]);
+                        tma_load_2d_pair(sb, &mapBh, 0, (int)(((int64_t)(2 * tj + (int)rank) * p.nchunks + c) * p.a_rows), &full[slot]);
+                        continue;
+                    }
+                    mbar_expect_tx(&full[slot], STG);
                     if constexpr (CL == 2) {  // own a-panel; own half of the b-panel stage to both CTAs (same offsets, same barrier)
                         tma_load_2d(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * p.a_rows), &full[slot]);
                         tma_load_2d_mc(sb + rank * (B_STAGE / 2), &mapBh, 0, (int)(((int64_t)tj * p.nchunks + c) * p.b_rows + rank * (p.b_rows / 2)),
@@ -293,8 +346,8 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (CL = 3: the leader CTA issues for the pair) =====
+        if (lane == 0 && !(PAIR && rank != 0)) {
             int64_t it = 0, k = 0;  // k counts the non-empty tiles of this CTA
             for (int64_t kk = 0; kk < my_tiles; kk++) {
                 int ti_, tj_;
@@ -304,20 +357,27 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                 fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * N);
                 for (int c = 0; c < p.nchunks; c++, it++) {
-                    const int slot = (int)(it % NSTAGE);
-                    mbar_wait(&full[slot], (uint32_t)((it / NSTAGE) & 1));
+                    const int slot = (int)(it % NST);
+                    mbar_wait(&full[slot], (uint32_t)((it / NST) & 1));
                     fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)slot * STAGE), sb = sa + A_STAGE;
+                    const uint32_t sa = smem_u32(smem + (size_t)slot * STG), sb = sa + A_STAGE;
 #pragma unroll
                     for (int s = 0; s < KB / 32; s++) {  // one MMA = 32 K-bytes = two 16-byte K-halves
                         const uint64_t ad = smem_desc(sa + s * 2 * (M * 16), M * 16, 128);
-                        const uint64_t bd = smem_desc(sb + s * 2 * (N * 16), N * 16, 128);
-                        mma_i8(d_tmem, ad, bd, (c | s) != 0 ? 1u : 0u);
+                        if constexpr (PAIR) {  // each CTA holds 128 of the tile's 256 b-rows, laid out like an a-panel
+                            const uint64_t bd = smem_desc(sb + s * 2 * (M * 16), M * 16, 128);
+                            mma_i8_pair(d_tmem, ad, bd, (c | s) != 0 ? 1u : 0u);
+                        } else {
+                            const uint64_t bd = smem_desc(sb + s * 2 * (N * 16), N * 16, 128);
+                            mma_i8(d_tmem, ad, bd, (c | s) != 0 ? 1u : 0u);
+                        }
                     }
-                    if constexpr (CL == 2) mma_commit_mc(&empty[slot], (uint16_t)3);  // both CTAs write into this stage: tell both
+                    if constexpr (PAIR) mma_commit_pair(&empty[slot]);                     // the stage of BOTH CTAs may be refilled
+                    else if constexpr (CL == 2) mma_commit_mc(&empty[slot], (uint16_t)3);  // both CTAs write into this stage: tell both
                     else mma_commit(&empty[slot]);  // the stage may be refilled once these MMAs have read it
                 }
-                mma_commit(&tfull[as]);        // accumulator complete
+                if constexpr (PAIR) mma_commit_pair(&tfull[as]);  // accumulator complete, in both CTAs' tensor memory
+                else mma_commit(&tfull[as]);
                 k++;
             }
         }
@@ -352,6 +412,12 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     }
                 classes = may;
             }
+            // every pair of the tile is a real pair i < j < n: no range tests in the inner loop
+            const bool interior = (int64_t)tj * N > (int64_t)ti * M + M - 1 && (int64_t)tj * N + N <= p.n;
+            // ... and every row / column is valid at all L sites: shared == L for every pair, so the test (mism << 16 <= thr * shared)
+            // is mism <= (thr * L) >> 16, with the right-hand side staged per column and kept per row
+            const bool full = !COUNTS_MODE && interior && !seed && p.L >= p.min_overlap && p.panel_full[ti] && p.panel_full[2 * tj] &&
+                              p.panel_full[2 * tj + 1] && (int64_t)ti * M + M <= p.n;
             uint32_t tf_row = edge_tf;
             if constexpr (!COUNTS_MODE) {
                 __syncwarp();  // the previous tile's reads of my_thr are done
@@ -359,13 +425,16 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                 for (int x = 0; x < EPI_COLS / 32; x++) {
                     const int j = j0 + g * EPI_COLS + x * 32 + lane;
                     if (seed) my_thr[x * 32 + lane] = (uint32_t)(j < p.n ? __ldg(sp.species + j) : -1);  // seed pass: the columns' species ids
-                    else my_thr[x * 32 + lane] = (want_bm && j < p.n) ? __ldcg(sp.thr + j) : 0u;
+                    else {
+                        const uint32_t t = (want_bm && j < p.n) ? __ldcg(sp.thr + j) : 0u;
+                        my_thr[x * 32 + lane] = full ? (uint32_t)(((unsigned long long)t * (uint32_t)p.L) >> 16) : t;
+                    }
                 }
                 if (want_bm && i < p.n) tf_row = max(tf_row, __ldcg(sp.thr + i));
                 __syncwarp();
             }
-            // every pair of the tile is a real pair i < j < n: no range tests in the inner loop
-            const bool interior = (int64_t)tj * N > (int64_t)ti * M + M - 1 && (int64_t)tj * N + N <= p.n;
+            const uint32_t brow = (uint32_t)(((unsigned long long)tf_row * (uint32_t)p.L) >> 16);
+            const uint32_t half_l = k2p_force ? ((uint32_t)p.L + 1u) >> 1 : 0xffffffffu;  // 2 * mism >= L
             mbar_wait(&tfull[as], (uint32_t)((k >> 1) & 1));
             fence_after();
             int bad_row = 0;
@@ -380,7 +449,10 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                 if (cbi == EPI_COLS / 32 - 1) {  // this warp's columns of the stage are in registers: hand them back
                     fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[as]);
+                    if (lane == 0) {
+                        if constexpr (PAIR) mbar_arrive_cta(&tempty[as], 0);  // the leader's MMA issuer waits for both CTAs' epilogues
+                        else mbar_arrive(&tempty[as]);
+                    }
                 }
                 const int jb = j0 + cb * 32;
                 if (p.hints == 8) continue;  // experiment: no epilogue work at all (results are wrong)
@@ -426,7 +498,19 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
                         return r;
                     };
-                    if (interior) {
+                    if (full) {
+#pragma unroll
+                        for (int e4 = 0; e4 < 8; e4++) {
+                            const uint4 ct = lds4(ct_addr + e4 * 16);
+                            const uint32_t cts[4] = {ct.x, ct.y, ct.z, ct.w};
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int e = e4 * 4 + u;
+                                const uint32_t mism = v[e] >> p.wshift;
+                                if ((mism <= max(brow, cts[u])) | (mism >= half_l)) pmask |= 1u << e;
+                            }
+                        }
+                    } else if (interior) {
 #pragma unroll
                         for (int e4 = 0; e4 < 8; e4++) {
                             const uint4 ct = lds4(ct_addr + e4 * 16);
@@ -519,8 +603,11 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
     }
     fence_before();
     __syncthreads();
-    if constexpr (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still write into it
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if constexpr (CL >= 2) cluster_sync_all();  // no CTA leaves while its peer may still write into it
+    if (warp == 1) {
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
 }
 
 // ---- after the bulk pass: the queue -> minima -> final thresholds -> candidate records --------------------------
