@@ -582,6 +582,10 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.k2p = a->kmode == KM_K2P ? 1 : 0;
     p.panel_full = a->d_tcfull;
     p.L = a->L;
+    if (!COUNTS_MODE && a->d_panel_range && (a->sp.want & ~(TDNA_WANT_INTRA | TDNA_WANT_INTER)) == 0 && !getenv("TDNA_TC_NOSKIP")) {
+        p.class_only = ((a->sp.want & TDNA_WANT_INTRA) ? 1 : 0) | ((a->sp.want & TDNA_WANT_INTER) ? 2 : 0);
+        p.panel_range = a->d_panel_range;
+    }
     p.planes = a->d_planes;
     p.W32 = a->W;
     {

@@ -61,6 +61,8 @@ struct Params {
     int a_rows, b_rows;     // rows of the tensor-map view per a / b stage block (view row = inner box width)
     int hints;              // L2 cache-policy hints on the operand loads (experiments: TDNA_TC_HINTS)
     int piece;              // bytes per 1-D bulk copy (divides 16 KB); 0 = tensor-map (2-D tiled TMA) loads
+    int class_only;         // the pass wants class distances and nothing per row: bit 0 = intra, bit 1 = inter.  Tiles whose row and
+    const int4 *panel_range;  // column panels share no species / genus id range hold no such pair and are skipped by every role
 };
 
 // Tile slot -> (row tile, column tile); false = an empty slot.  The bulk phase walks BANDS of `band` row tiles,
@@ -87,14 +89,30 @@ __device__ __forceinline__ bool slot_coords(const Params &p, const int64_t *pref
 // k-th work item of this CTA (items = slots for CL = 1, PAIRS of slots (2u, 2u + 1) -- same column tile, adjacent row tiles -- for
 // CL = 2); a part takes every t_stride-th UNIT of `unit` consecutive items.  Items past the end of the list are empty.  CL = 2: this
 // CTA the one of its cluster rank; the pair is as valid as its even slot (an odd row tile past the end reads zero-filled operands).
+// rows [r0, r0 + rows) as a union of the 64-row panels' (min, max) species / genus ids
+__device__ __forceinline__ int4 range_union(const Params &p, int64_t r0, int rows) {
+    int4 r = make_int4(0x7fffffff, -1, 0x7fffffff, (int)0x80000000);
+    for (int64_t pn = r0 / PR; pn * PR < r0 + rows && pn * PR < p.n; pn++) {
+        const int4 x = __ldg(p.panel_range + pn);
+        r.x = min(r.x, x.x); r.y = max(r.y, x.y); r.z = min(r.z, x.z); r.w = max(r.w, x.w);
+    }
+    return r;
+}
+// a pass that only collects class distances: can the item (ROWS rows from row tile ti, column tile tj) hold an intra / inter pair?
+__device__ __forceinline__ bool may_hold_class_pairs(const Params &p, int ti, int tj, int rows) {
+    const int4 a = range_union(p, (int64_t)ti * M, rows), b = range_union(p, (int64_t)tj * N, N);
+    return ((p.class_only & 1) && a.x <= b.y && b.x <= a.y) || ((p.class_only & 2) && a.z <= b.w && b.z <= a.w);
+}
 template <int CL> __device__ __forceinline__ bool my_tile(const Params &p, int64_t k, uint32_t rank, int &ti, int &tj) {
     if constexpr (CL == 1) {
         const int64_t l = (int64_t)blockIdx.x + k * gridDim.x;
-        return slot_coords(p, p.prefix, ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit, ti, tj);
+        if (!slot_coords(p, p.prefix, ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit, ti, tj)) return false;
+        return !p.class_only || may_hold_class_pairs(p, ti, tj, M);
     } else {
         const int64_t l = (int64_t)(blockIdx.x >> 1) + k * (gridDim.x >> 1);
         const int64_t u = ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit;
-        const bool ok = slot_coords(p, p.prefix, 2 * u, ti, tj);
+        bool ok = slot_coords(p, p.prefix, 2 * u, ti, tj);
+        if (ok && p.class_only) ok = may_hold_class_pairs(p, ti, tj, 2 * M);  // the same answer in both CTAs of the pair
         ti += (int)rank;
         return ok;
     }
