@@ -139,6 +139,13 @@ int32_t tdna_pairs(tdna_aln *aln, const int32_t *ii, const int32_t *jj, int64_t 
  * SortedSequenceList.java:104-118); shared may be NULL. */
 int32_t tdna_row_distances(tdna_aln *aln, int64_t q, double *d, int32_t *shared);
 
+/* A sequence that is NOT a row of the alignment against every row: d[n] (and optionally shared[n], counts[n]).
+ * `symbols` holds `len` bytes of the normalised alphabet (host or device memory); sites past the alignment's width are ignored
+ * (every comparison stops at the shorter sequence, Sequence.java:1417-1419).  Replaces the N getPairwise calls of
+ * SortedSequenceList.sortAgainst (SortedSequenceList.java:78-128) for a foreign query, as issued by
+ * QuerySequence.query (QuerySequence.java:113-145). */
+int32_t tdna_query_distances(tdna_aln *aln, const uint8_t *symbols, int32_t len, double *d, int32_t *shared, tdna_counts *counts);
+
 /* ---- full matrix (config C2; Cluster.java:605-626 prints one per cluster) ---------------- */
 /* d: (row_end-row_begin) x n doubles, row-major, ld = n.  counts (optional): same shape. */
 int32_t tdna_matrix(tdna_aln *aln, double *d, tdna_counts *counts);

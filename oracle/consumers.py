@@ -1272,3 +1272,165 @@ def cluster(D, max_pairwise):
         stats.append(dict(size=len(b), largest=largest, valid=valid, over=over,
                           pct=(percentage(over, valid) if valid != 0 else 0.0)))
     return clusters, stats
+
+
+# --------------------------------------------------------------------------
+# ExtremePairwise.run (SpeciesIdentifier/ExtremePairwise.java:72-210)
+# --------------------------------------------------------------------------
+def extreme_pairwise(D):
+    """Per query: the LAST valid conspecific and the FIRST valid congeneric, allospecific entry of sortAgainst(query).
+    Returns (text, records); a record is (largest-intra list position or None, smallest-inter list position or None)."""
+    seqs = D.seqs
+    out = ["Sequence name\tLargest conspecific match\tDistance\tOverlap\tClosest congeneric, interspecific match\tDistance\tOverlap\n"]
+    records = []
+    for q, seq in enumerate(seqs):
+        if seq.species_name() is None:  # :109-112
+            out.append(seq.name + "\tUnable to identify species name\n")
+            records.append(None)
+            continue
+        ss = sort_against(D, q)
+        largest_intra = smallest_inter = None
+        for x in ss:  # :121-146
+            s2 = seqs[x]
+            if s2.species_name() is None:
+                continue
+            if seq.genus and s2.genus and seq.genus == s2.genus and seq.species_name() != s2.species_name():
+                if D.pairwise(x, q) != -1:
+                    smallest_inter = x
+                    break
+        for k in range(len(ss) - 1, 0, -1):  # :149-163: never entry 0
+            x = ss[k]
+            s2 = seqs[x]
+            if s2.species_name() is None:
+                continue
+            if seq.species_name() == s2.species_name():
+                if D.pairwise(x, q) != -1:
+                    largest_intra = x
+                    break
+        out.append(seq.display_name() + "\t")
+        if largest_intra is None:
+            out.append("No matching conspecific sequence\tN/A\tN/A\t")
+        else:
+            out.append(seqs[largest_intra].display_name() + "\t" + java_double_str(percentage(D.pairwise(largest_intra, q), 1)) + "\t" +
+                       str(D.shared_length(largest_intra, q)) + "\t")
+        if smallest_inter is None:
+            out.append("No matching congeneric, interspecific sequence\tN/A\tN/A\t")
+        else:
+            out.append(seqs[smallest_inter].display_name() + "\t" + java_double_str(percentage(D.pairwise(smallest_inter, q), 1)) + "\t" +
+                       str(D.shared_length(smallest_inter, q)) + "\t")
+        out.append("\n")
+        records.append((largest_intra, smallest_inter))
+    return "".join(out), records
+
+
+# --------------------------------------------------------------------------
+# QuerySequence.query (SpeciesIdentifier/QuerySequence.java:113-180)
+# --------------------------------------------------------------------------
+def query_sequence(seqs, cfg, raw_query, threads=1):
+    """A pasted sequence against the list: the entries of list_result, in order.  Returns (lines, list positions)."""
+    q = OSeq("Query", "".join(ch for ch in raw_query if not ch.isspace()))  # :127-133
+    rows, lens = pack_rows([s.seq for s in seqs] + [q.seq])
+    r = all_pairs(rows, lens, cfg.mode, cfg.min_overlap, cfg.ambig, threads=threads)
+    n = len(seqs)
+    D = Dist(seqs + [q], cfg, dist=r["dist"], shared=r["shared"])
+    ss = sort_against(D, n, order=range(n))  # the query is not in the list: no entry is "the query" for the comparator
+    lines, positions = [], []
+    for x in ss:
+        d = D.pairwise(n, x)
+        if d < 0:
+            continue
+        lines.append("(%.4f%%) %s" % (d * 100, seqs[x].display_name()))  # MessageFormat "({0,number,##0.0000}%) {1}"
+        positions.append(x)
+    return lines, positions
+
+
+# --------------------------------------------------------------------------
+# PairwiseExplorer.run (SpeciesIdentifier/PairwiseExplorer.java:109-190)
+# --------------------------------------------------------------------------
+def pairwise_explorer(D, kind):
+    """The distance categories of list_distances: [(key, [(name A, name B, d), ...])] in 0.5 % steps, then "Averages"."""
+    triples, _ = pairwise_distances(D, kind)
+    cats = []
+    for x in range(-5, 1000, 5):
+        lo, hi = x / 1000 + 0.000001, (x + 5) / 1000
+        members, count = [], False  # PairwiseDistances.getDistancesBetween (:266-285): one scan of the sorted vector
+        for t in triples:
+            if t[2] >= lo:
+                count = True
+            if t[2] > hi:
+                break
+            if count:
+                members.append(t)
+        if members:
+            key = java_float_str(np.float32(x) / np.float32(10)) + "% to " + java_float_str((np.float32(x) + np.float32(5)) / np.float32(10)) + \
+                "% (" + str(len(members)) + " matches)"
+            if x + 5 == 0:
+                key = "Before 0% (" + str(len(members)) + " matches)"
+            cats.append((key, members))
+    cats.append(("Averages", []))
+    return cats
+
+
+# --------------------------------------------------------------------------
+# DistanceAnalysis.run (SpeciesIdentifier/DistanceAnalysis.java:161-320)
+# --------------------------------------------------------------------------
+def distance_analysis(D):
+    """Per genus: the mean over species of (mean over sequences of the smallest / of the mean congeneric, allospecific
+    distance).  The reference iterates Hashtables keyed by Sequence objects (identity hash: the order differs from run to
+    run) and by species name; sums here are taken in list order / order of first appearance, which only moves the last
+    ulp of a sum that is then rounded to two decimals of a percentage (Settings.percentage)."""
+    seqs = D.seqs
+    if any(s.species_name() is None for s in seqs):
+        raise JavaNPE("DistanceAnalysis.java:196 Hashtable.put(null, ...) / :205 getSpeciesName().equals on null")
+
+    def average(v):
+        tot, cnt = 0.0, 0
+        for val in v:
+            if val > -1:
+                tot += val
+                cnt += 1
+        return tot / cnt if cnt else float("nan")
+
+    species_order, per_seq = [], []
+    for q, query in enumerate(seqs):
+        if query.species_name() not in species_order:
+            species_order.append(query.species_name())
+        closest, inters = -1.0, []
+        for x in sort_against(D, q):
+            cmpseq = seqs[x]
+            if cmpseq.species_name() == query.species_name():
+                continue
+            if cmpseq.genus == query.genus:
+                dist = D.pairwise(x, q)
+                if closest < 0:
+                    closest = dist
+                inters.append(dist)
+        if closest != -1:
+            per_seq.append((q, average(inters), closest))
+    genera_all, genera_smallest = {}, {}
+    for sp in species_order:
+        genus = None
+        d_all, d_small = [], []
+        for q, avg, closest in per_seq:
+            if seqs[q].species_name() == sp:
+                genus = seqs[q].genus
+                d_all.append(avg)
+                d_small.append(closest)
+        if genus is None:
+            genus = sp[:sp.index(" ")]
+        if d_all:
+            genera_all.setdefault(genus, []).append(average(d_all))
+            genera_smallest.setdefault(genus, []).append(average(d_small))
+        else:
+            genera_all.setdefault(genus, []).append(-1.0)
+            genera_smallest.setdefault(genus, []).append(-1.0)
+    out = ["Genus\t\t\tAvg. Avg. Smallest Inter\t\tAvg. Avg. Avg. Inter\n"]
+    rows = {}
+    for genus in sorted(genera_all, key=lambda g: g.encode("utf-16-be")):  # Collections.sort of Strings
+        avg_inter, avg_smallest = average(genera_all[genus]), average(genera_smallest[genus])
+        rows[genus] = (avg_smallest, avg_inter)
+        if avg_inter < 0:
+            out.append(genus + "\t\t\tNo comparisions\t\tNo comparisions\n")
+        else:
+            out.append(genus + "\t\t\t" + java_double_str(percentage(avg_smallest, 1)) + "\t\t" + java_double_str(percentage(avg_inter, 1)) + "\n")
+    return "".join(out), rows

@@ -63,7 +63,7 @@ assert ROW_RESULT_DTYPE.itemsize == 120, ROW_RESULT_DTYPE.itemsize
 EXPORTS = [
     "tdna_abi_version", "tdna_init", "tdna_shutdown", "tdna_last_error", "tdna_stream", "tdna_set_memory_budget",
     "tdna_launch_count", "tdna_alignment_create", "tdna_alignment_destroy", "tdna_alignment_set_labels",
-    "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_pairs", "tdna_row_distances", "tdna_matrix", "tdna_matrix_compute",
+    "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_pairs", "tdna_row_distances", "tdna_query_distances", "tdna_matrix", "tdna_matrix_compute",
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
     "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_set_option", "tdna_last_tile_pass_ms",
@@ -101,6 +101,7 @@ def load():
     L.tdna_pair.argtypes = [vp, i64, i64, ctypes.POINTER(Counts), ctypes.POINTER(dbl)]
     L.tdna_pairs.argtypes = [vp, vp, vp, i64, vp, vp]
     L.tdna_row_distances.argtypes = [vp, i64, vp, vp]
+    L.tdna_query_distances.argtypes = [vp, vp, i32, vp, vp, vp]
     L.tdna_matrix.argtypes = [vp, vp, vp]
     L.tdna_matrix_compute.argtypes = [vp, ctypes.POINTER(vp)]
     L.tdna_best_match.argtypes = [vp, vp]
@@ -229,6 +230,15 @@ class Alignment:
         sh = np.empty(self.n, dtype=np.int32) if want_shared else None
         check(self.L.tdna_row_distances(self.h, q, d.ctypes.data, sh.ctypes.data if want_shared else None))
         return d, sh
+
+    def query_distances(self, symbols, want_counts=False):
+        """A normalised sequence that is not a row of the alignment against every row (QuerySequence.java:113-145)."""
+        q = np.ascontiguousarray(np.frombuffer(symbols, dtype=np.uint8) if isinstance(symbols, (bytes, bytearray)) else symbols, dtype=np.uint8)
+        d = np.empty(self.n, dtype=np.float64)
+        sh = np.empty(self.n, dtype=np.int32)
+        c = np.empty(self.n, dtype=COUNTS_DTYPE) if want_counts else None
+        check(self.L.tdna_query_distances(self.h, q.ctypes.data, int(q.size), d.ctypes.data, sh.ctypes.data, c.ctypes.data if want_counts else None))
+        return (d, sh, c) if want_counts else (d, sh)
 
     def matrix(self, counts=False, out=None):
         rows = self.row_end - self.row_begin

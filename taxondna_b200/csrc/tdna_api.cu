@@ -996,6 +996,67 @@ int32_t tdna_row_distances(tdna_aln *a, int64_t q, double *d, int32_t *shared) {
     return rc;
 }
 
+int32_t tdna_query_distances(tdna_aln *a, const uint8_t *symbols, int32_t len, double *d, int32_t *shared, tdna_counts *counts) {
+    TRY(ensure_packed(a));
+    if (!symbols || len < 0 || !d) return fail(TDNA_E_ARG, "bad argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    // sites past the alignment's width meet no row (every comparison stops at the shorter sequence, Sequence.java:1417-1419)
+    const int32_t ql = len < a->L ? len : a->L;
+    const size_t sym_bytes = (size_t)a->W * 32, plane_words = (size_t)PR * a->P * a->W;
+    uint8_t *q_sym = nullptr;
+    int32_t *q_len = nullptr;
+    uint32_t *q_planes = nullptr;
+    double *dd = nullptr;
+    int32_t *ds = nullptr;
+    tdna_counts *dc = nullptr;
+    int rc = TDNA_OK;
+    auto cleanup = [&]() {
+        for (void *p : {(void *)q_sym, (void *)q_len, (void *)q_planes, (void *)dd, (void *)ds, (void *)dc})
+            if (p) DFREE(p);
+    };
+#define QCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(TDNA_E_CUDA, cudaGetErrorString(e_)); } } while (0)
+    QCU(DMALLOC(&q_sym, sym_bytes));
+    QCU(DMALLOC(&q_len, 4));
+    QCU(DMALLOC(&q_planes, plane_words * 4));
+    QCU(DMALLOC(&dd, (size_t)a->n * 8));
+    if (shared) QCU(DMALLOC(&ds, (size_t)a->n * 4));
+    if (counts) QCU(DMALLOC(&dc, (size_t)a->n * sizeof(tdna_counts)));
+    QCU(cudaMemsetAsync(q_sym, '?', sym_bytes, c->stream));
+    if (ql > 0) QCU(cudaMemcpyAsync(q_sym, symbols, (size_t)ql, cudaMemcpyDefault, c->stream));
+    QCU(cudaMemcpyAsync(q_len, &ql, 4, cudaMemcpyHostToDevice, c->stream));
+    int *d_err = reinterpret_cast<int *>(c->d_counter);
+    QCU(cudaMemsetAsync(d_err, 0, 8, c->stream));
+    PlaneBits pb;
+    switch (a->kmode) {
+        case KM_P_AMBIG: pb = plane_bits<KM_P_AMBIG>(); break;
+        case KM_P_NOAMBIG: pb = plane_bits<KM_P_NOAMBIG>(); break;
+        case KM_K2P: pb = plane_bits<KM_K2P>(); break;
+        default: pb = plane_bits<KM_TRANS>(); break;
+    }
+    const int64_t total = (int64_t)PR * a->W;
+    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(q_sym, q_len, 1, PR, (int64_t)sym_bytes, a->W, a->P, pb, q_planes, d_err);
+    const unsigned grid = (unsigned)((a->n + 255) / 256);
+    switch (a->kmode) {
+        case KM_P_AMBIG: query_from_planes_kernel<KM_P_AMBIG><<<grid, 256, 0, c->stream>>>(q_planes, a->d_planes, a->W, a->n, a->min_overlap, dd, ds, dc); break;
+        case KM_P_NOAMBIG: query_from_planes_kernel<KM_P_NOAMBIG><<<grid, 256, 0, c->stream>>>(q_planes, a->d_planes, a->W, a->n, a->min_overlap, dd, ds, dc); break;
+        case KM_K2P: query_from_planes_kernel<KM_K2P><<<grid, 256, 0, c->stream>>>(q_planes, a->d_planes, a->W, a->n, a->min_overlap, dd, ds, dc); break;
+        default: query_from_planes_kernel<KM_TRANS><<<grid, 256, 0, c->stream>>>(q_planes, a->d_planes, a->W, a->n, a->min_overlap, dd, ds, dc); break;
+    }
+    c->launches += 2;
+    QCU(cudaGetLastError());
+    int err = 0;
+    QCU(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
+    QCU(cudaMemcpyAsync(d, dd, (size_t)a->n * 8, cudaMemcpyDefault, c->stream));
+    if (shared) QCU(cudaMemcpyAsync(shared, ds, (size_t)a->n * 4, cudaMemcpyDefault, c->stream));
+    if (counts) QCU(cudaMemcpyAsync(counts, dc, (size_t)a->n * sizeof(tdna_counts), cudaMemcpyDefault, c->stream));
+    QCU(cudaStreamSynchronize(c->stream));
+#undef QCU
+    cleanup();
+    if (err) return fail(TDNA_E_SYMBOL, "a symbol outside the normalised alphabet ACGT RYKMSWBDHVN - _ ?");
+    return rc;
+}
+
 int32_t tdna_matrix(tdna_aln *a, double *d, tdna_counts *counts) {
     if (!a || !d) return fail(TDNA_E_ARG, "null argument");
     tdna_ctx *c = a->ctx;

@@ -642,6 +642,34 @@ __global__ void __launch_bounds__(256) row_from_planes_kernel(const uint32_t *__
     }
 }
 
+// a sequence that is not a row of the alignment against every row (QuerySequence.java:125-145 -> SortedSequenceList.sortAgainst with
+// a foreign query): the query's planes are packed like a one-row alignment (row 0 of qplanes); thread <-> column j
+template <int KM>
+__global__ void __launch_bounds__(256) query_from_planes_kernel(const uint32_t *__restrict__ qplanes, const uint32_t *__restrict__ planes, int W,
+                                                                int64_t n, int min_overlap, double *__restrict__ d_out,
+                                                                int32_t *__restrict__ shared_out, tdna_counts *__restrict__ counts_out) {
+    constexpr int P = ModeTraits<KM>::P;
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t a0 = 0, a1 = 0;
+    for (int k = 0; k < W; k++) {
+        uint32_t x[P], y[P];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            x[p] = __ldg(qplanes + plane_index(0, p, k, P, W));  // the same word in every lane: a broadcast load
+            y[p] = planes[plane_index(j, p, k, P, W)];
+        }
+        accumulate_word<KM>(x, y, a0, a1);
+    }
+    Counts c = unpack_counts<KM>(a0, a1);
+    if (d_out) d_out[j] = distance_from_counts<KM>(c, min_overlap);
+    if (shared_out) shared_out[j] = c.shared;
+    if (counts_out) {
+        tdna_counts o = {c.shared, c.c1, c.c2, c.c3};
+        counts_out[j] = o;
+    }
+}
+
 // an explicit list of pairs straight from the planes (tdna_pairs): thread <-> pair
 template <int KM>
 __global__ void __launch_bounds__(256) pairs_from_planes_kernel(const uint32_t *__restrict__ planes, int W, const int32_t *__restrict__ ii,

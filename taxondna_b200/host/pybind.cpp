@@ -97,6 +97,7 @@ PYBIND11_MODULE(_host, m) {
         .def("get", &SortedSequenceList::get)
         .def("getQuery", &SortedSequenceList::getQuery)
         .def("getDistance", &SortedSequenceList::getDistance)
+        .def("getOverlap", &SortedSequenceList::getOverlap)
         .def("position", &SortedSequenceList::position);
 
     py::class_<PairwiseDistribution, std::shared_ptr<PairwiseDistribution>>(m, "PairwiseDistribution")
@@ -175,4 +176,35 @@ PYBIND11_MODULE(_host, m) {
         .def("run", [](Cluster &c) { c.run(nullptr); })
         .def("clusters", &Cluster::clusters)
         .def("stats", &Cluster::stats);
+
+    py::class_<ExtremePairwise>(m, "ExtremePairwise")
+        .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
+        .def("run", [](ExtremePairwise &e) { return e.run(nullptr); })
+        .def("rows", [](const ExtremePairwise &e) {
+            std::vector<std::pair<int, int>> out;
+            for (auto &r : e.rows()) out.emplace_back(r.largest_intra, r.smallest_inter);
+            return out;
+        });
+
+    py::class_<QuerySequence>(m, "QuerySequence")
+        .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
+        .def("query", [](QuerySequence &q, const std::string &s) { return q.query(s, nullptr); })
+        .def("positions", &QuerySequence::positions)
+        .def("distances", &QuerySequence::distances);
+
+    py::class_<PairwiseExplorer>(m, "PairwiseExplorer")
+        .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
+        .def("run", [](PairwiseExplorer &p, int type) {  // [(key, [(full name A, full name B, distance)])]
+            std::vector<std::pair<std::string, std::vector<std::tuple<std::string, std::string, double>>>> out;
+            for (auto &c : p.run(type, nullptr)) {
+                std::vector<std::tuple<std::string, std::string, double>> v;
+                for (auto &x : c.distances) v.emplace_back(x.seqA->getFullName(), x.seqB->getFullName(), x.distance);
+                out.emplace_back(c.key, std::move(v));
+            }
+            return out;
+        });
+
+    py::class_<DistanceAnalysis>(m, "DistanceAnalysis")
+        .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
+        .def("run", [](DistanceAnalysis &d) { return d.run(nullptr); });
 }

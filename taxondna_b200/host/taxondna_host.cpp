@@ -356,6 +356,13 @@ void DistanceEngine::rowDistances(int64_t q, std::vector<double> &d, std::vector
     if (shared) shared->resize(n_);
     ck(tdna_row_distances(aln_, q, d.data(), shared ? shared->data() : nullptr));
 }
+void DistanceEngine::queryDistances(const Sequence &query, std::vector<double> &d, std::vector<int32_t> *shared) const {
+    syncConfig();
+    d.resize(n_);
+    if (shared) shared->resize(n_);
+    const std::string &raw = query.getSequenceRaw();
+    ck(tdna_query_distances(aln_, reinterpret_cast<const uint8_t *>(raw.data()), (int32_t)raw.size(), d.data(), shared ? shared->data() : nullptr, nullptr));
+}
 std::vector<double> DistanceEngine::matrix() const {
     syncConfig();
     std::vector<double> d((size_t)n_ * n_);
@@ -782,12 +789,9 @@ void SortedSequenceList::sortAgainst(const SequencePtr &query, DelayCallback *de
     for (int i = 0; i < n; i++)
         if (seqs[i]->getId() == query->getId()) { q = i; break; }
     if (delay) delay->begin();
-    if (q >= 0) {
-        original_->engine().rowDistances(q, dist_, nullptr);  // one launch: the row the reference builds with N getPairwise calls
-    } else {  // a query that is not in the list (QuerySequence): N single-pair calls against a transient pair
-        dist_.resize(n);
-        for (int i = 0; i < n; i++) dist_[i] = seqs[i]->getPairwise(*query);
-    }
+    if (n == 0) { dist_.clear(); shared_.clear(); }
+    else if (q >= 0) original_->engine().rowDistances(q, dist_, &shared_);  // one launch: the row the reference builds with N getPairwise calls
+    else original_->engine().queryDistances(*query, dist_, &shared_);      // a query that is not in the list (QuerySequence): one launch too
     sorted_.clear();
     for (int i = 0; i < n; i++) {
         if (delay) delay->delay(i + 1, n);
@@ -1516,6 +1520,177 @@ void Cluster::run(DelayCallback *delay) {
         stats_.push_back(st);
     }
     if (delay) delay->end();
+}
+
+// ------------------------------------------------------------------------------------------------
+// ExtremePairwise.run (ExtremePairwise.java:72-210)
+// ------------------------------------------------------------------------------------------------
+std::string ExtremePairwise::run(DelayCallback *delay) {
+    const SequenceList &list = *list_;
+    rows_.clear();
+    std::string results = "Sequence name\tLargest conspecific match\tDistance\tOverlap\tClosest congeneric, interspecific match\tDistance\tOverlap\n";
+    if (delay) delay->begin();
+    SortedSequenceList sorted(list);
+    const int total_sequences = list.count();
+    auto entry = [&](int x) {  // display name, distance as a percentage, overlap
+        return sorted.get(x)->getDisplayName() + "\t" + javaDouble(Settings::percentage(sorted.getDistance(x), 1)) + "\t" +
+               std::to_string(sorted.getOverlap(x)) + "\t";
+    };
+    for (int count = 0; count < total_sequences; count++) {
+        if (delay) delay->delay(count, total_sequences);
+        const SequencePtr &seq = list.get(count);
+        auto name = seq->getSpeciesName();
+        if (!name) {  // :109-112
+            results += seq->getFullName() + "\tUnable to identify species name\n";
+            rows_.push_back(Row{-2, -2});
+            continue;
+        }
+        sorted.sortAgainst(seq, nullptr);
+        int largest = -1, smallest = -1;  // entries of the sorted list
+        const std::string &genus1 = seq->getGenusName();
+        for (int x = 0; x < sorted.count(); x++) {  // :121-146
+            SequencePtr seq2 = sorted.get(x);
+            auto name2 = seq2->getSpeciesName();
+            if (!name2) continue;
+            const std::string &genus2 = seq2->getGenusName();
+            if (!genus1.empty() && !genus2.empty() && genus1 == genus2 && *name != *name2) {
+                if (sorted.getDistance(x) != -1) { smallest = x; break; }
+            }
+        }
+        for (int x = sorted.count() - 1; x >= 1; x--) {  // :149-163: entry 0 is taken to be the query
+            SequencePtr seq2 = sorted.get(x);
+            auto name2 = seq2->getSpeciesName();
+            if (!name2) continue;
+            if (*name == *name2 && sorted.getDistance(x) != -1) { largest = x; break; }
+        }
+        results += seq->getDisplayName() + "\t";
+        results += largest < 0 ? std::string("No matching conspecific sequence\tN/A\tN/A\t") : entry(largest);
+        results += smallest < 0 ? std::string("No matching congeneric, interspecific sequence\tN/A\tN/A\t") : entry(smallest);
+        results += '\n';
+        rows_.push_back(Row{largest < 0 ? -1 : sorted.position(largest), smallest < 0 ? -1 : sorted.position(smallest)});
+    }
+    if (delay) delay->end();
+    return results;
+}
+
+// ------------------------------------------------------------------------------------------------
+// QuerySequence.query (QuerySequence.java:113-180)
+// ------------------------------------------------------------------------------------------------
+std::vector<std::string> QuerySequence::query(const std::string &string_sequence, DelayCallback *delay) {
+    positions_.clear();
+    distances_.clear();
+    std::string buff;
+    for (char ch : string_sequence)
+        if (!std::isspace((unsigned char)ch)) buff += ch;  // :127-133
+    auto q = std::make_shared<Sequence>("Query", buff);     // throws SequenceException
+    SortedSequenceList sset(*list_);
+    sset.sortAgainst(q, delay);
+    std::vector<std::string> out;
+    for (int x = 0; x < sset.count(); x++) {
+        double distance = sset.getDistance(x);
+        if (distance < 0) continue;
+        char num[64];
+        std::snprintf(num, sizeof num, "%.4f", distance * 100);  // MessageFormat "({0,number,##0.0000}%) {1}"
+        out.push_back(std::string("(") + num + "%) " + sset.get(x)->getDisplayName());
+        positions_.push_back(sset.position(x));
+        distances_.push_back(distance);
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PairwiseExplorer.run (PairwiseExplorer.java:109-190)
+// ------------------------------------------------------------------------------------------------
+std::vector<PairwiseExplorer::Category> PairwiseExplorer::run(int type, DelayCallback *delay) {
+    std::shared_ptr<PairwiseDistances> &current = type == PairwiseDistances::PD_INTRA ? intra_ : inter_;
+    if (!current) current = std::make_shared<PairwiseDistances>(*list_, type, delay);
+    std::vector<Category> cats;
+    for (int x = -5; x < 1000; x += 5) {
+        double from = (double)x / 1000 + 0.000001;
+        double to = (double)(x + 5) / 1000;
+        auto distances = current->getDistancesBetween(from, to);
+        if (!distances.empty()) {
+            std::string key = javaFloat((float)x / 10) + "% to " + javaFloat(((float)x + 5) / 10) + "% (" + std::to_string(distances.size()) + " matches)";
+            if (x + 5 == 0) key = "Before 0% (" + std::to_string(distances.size()) + " matches)";
+            cats.push_back(Category{key, std::move(distances)});
+        }
+    }
+    cats.push_back(Category{"Averages", {}});
+    return cats;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DistanceAnalysis.run (DistanceAnalysis.java:161-320)
+// The reference walks Hashtables keyed by Sequence objects (identity hash: an order that differs from run to run) and by
+// species name; the sums here are taken in list order / order of first appearance.  Only the last ulp of a mean depends on
+// that order, and the means are printed through Settings.percentage (two decimals of a percentage).
+// ------------------------------------------------------------------------------------------------
+std::string DistanceAnalysis::run(DelayCallback *delay) {
+    const SequenceList &list = *list_;
+    const int n = list.count();
+    for (int i = 0; i < n; i++)
+        if (!list.get(i)->getSpeciesName()) throw NullPointerException("DistanceAnalysis.java:196/205: a sequence without a species name");
+    auto average = [](const std::vector<double> &v) {  // :139-151
+        double sum = 0.0;
+        int count = 0;
+        for (double val : v)
+            if (val > -1) { sum += val; count++; }
+        return sum / count;
+    };
+    if (delay) delay->begin();
+    SortedSequenceList ssl(list);
+    std::vector<std::string> species_order;
+    std::set<std::string> species_seen;
+    struct PerSeq { int q; double avg, closest; };
+    std::vector<PerSeq> per_seq;
+    for (int current_seq = 0; current_seq < n; current_seq++) {
+        if (delay) delay->delay(current_seq, n);
+        const SequencePtr &query = list.get(current_seq);
+        const std::string qname = *query->getSpeciesName();
+        if (species_seen.insert(qname).second) species_order.push_back(qname);
+        ssl.sortAgainst(query, nullptr);
+        double closest = -1;
+        std::vector<double> inters;
+        for (int x = 0; x < ssl.count(); x++) {
+            SequencePtr compare = ssl.get(x);
+            if (*compare->getSpeciesName() == qname) continue;
+            if (compare->getGenusName() == query->getGenusName()) {
+                double dist = ssl.getDistance(x);
+                if (closest < 0) closest = dist;
+                inters.push_back(dist);
+            }
+        }
+        if (closest != -1) per_seq.push_back(PerSeq{current_seq, average(inters), closest});
+    }
+    std::map<std::string, std::vector<double>> genera_all, genera_smallest;  // std::string order == String.compareTo for the names the parser accepts
+    for (const std::string &sp : species_order) {
+        std::optional<std::string> genus;
+        std::vector<double> d_all, d_small;
+        for (const PerSeq &e : per_seq) {
+            const SequencePtr &seq = list.get(e.q);
+            if (*seq->getSpeciesName() == sp) {
+                genus = seq->getGenusName();
+                d_all.push_back(e.avg);
+                d_small.push_back(e.closest);
+            }
+        }
+        if (!genus) genus = sp.substr(0, sp.find(' '));
+        if (!d_all.empty()) {
+            genera_all[*genus].push_back(average(d_all));
+            genera_smallest[*genus].push_back(average(d_small));
+        } else {
+            genera_all[*genus].push_back(-1);
+            genera_smallest[*genus].push_back(-1);
+        }
+    }
+    std::string buff = "Genus\t\t\tAvg. Avg. Smallest Inter\t\tAvg. Avg. Avg. Inter\n";
+    for (auto &kv : genera_all) {
+        double avg_inter = average(kv.second), avg_smallest = average(genera_smallest[kv.first]);
+        if (avg_inter < 0) buff += kv.first + "\t\t\tNo comparisions\t\tNo comparisions\n";
+        else buff += kv.first + "\t\t\t" + javaDouble(Settings::percentage(avg_smallest, 1)) + "\t\t" + javaDouble(Settings::percentage(avg_inter, 1)) + "\n";
+    }
+    if (delay) delay->end();
+    return buff;
 }
 
 }  // namespace taxondna

@@ -161,6 +161,8 @@ class DistanceEngine {
     void syncConfig() const;  // pushes the Sequence statics if they changed
     tdna_counts pair(int64_t i, int64_t j, double *d) const;
     void rowDistances(int64_t q, std::vector<double> &d, std::vector<int32_t> *shared) const;
+    // a sequence that is not in the list against every row: one launch (tdna_query_distances)
+    void queryDistances(const Sequence &query, std::vector<double> &d, std::vector<int32_t> *shared) const;
     std::vector<double> matrix() const;  // n x n, row-major
     std::vector<tdna_row_result> bestMatch() const;
     std::vector<float> classDistances(int klass) const;
@@ -193,12 +195,16 @@ class SortedSequenceList {
     SequencePtr getQuery() const { return query_; }
     double getDistance(int x) const;
     int position(int x) const { return sorted_.at(x); }  // list position of entry x (not in the Java API)
+    // getSharedLength(query, entry x): the row kernel produces it with the distances (not in the Java API, which asks
+    // Sequence.getOverlap pair by pair)
+    int getOverlap(int x) const { return shared_.at(sorted_.at(x)); }
 
   private:
     const SequenceList *original_;
     SequencePtr query_;
     std::vector<int> sorted_;
     std::vector<double> dist_;
+    std::vector<int32_t> shared_;
 };
 
 // java.util.TimSort restated (Arrays.sort(Object[], Comparator)); cmp(a, b) as Comparator.compare.
@@ -331,6 +337,62 @@ class Cluster {
     double max_pairwise_ = 0.03;
     std::vector<std::vector<int>> clusters_;
     std::vector<Stat> stats_;
+};
+
+// SpeciesIdentifier/ExtremePairwise.java:72-210: per sequence, the largest conspecific and the smallest congeneric,
+// allospecific distance.  run() returns text_matches' content.
+class ExtremePairwise {
+  public:
+    struct Row {
+        int largest_intra = -1, smallest_inter = -1;  // list positions; -1 = none; both -2 = no species name
+    };
+    explicit ExtremePairwise(const SequenceList &list) : list_(&list) {}
+    std::string run(DelayCallback *delay = nullptr);
+    const std::vector<Row> &rows() const { return rows_; }
+
+  private:
+    const SequenceList *list_;
+    std::vector<Row> rows_;
+};
+
+// SpeciesIdentifier/QuerySequence.java:113-180: a pasted sequence against the list
+class QuerySequence {
+  public:
+    explicit QuerySequence(const SequenceList &list) : list_(&list) {}
+    // the entries of list_result, in order; throws SequenceException for a bad sequence (:150-155 reports it)
+    std::vector<std::string> query(const std::string &string_sequence, DelayCallback *delay = nullptr);
+    const std::vector<int> &positions() const { return positions_; }  // list position of every entry (map_index)
+    const std::vector<double> &distances() const { return distances_; }
+
+  private:
+    const SequenceList *list_;
+    std::vector<int> positions_;
+    std::vector<double> distances_;
+};
+
+// SpeciesIdentifier/PairwiseExplorer.java:109-190: the pairs of a class in 0.5 % categories
+class PairwiseExplorer {
+  public:
+    struct Category {
+        std::string key;
+        std::vector<PairwiseDistance> distances;
+    };
+    explicit PairwiseExplorer(const SequenceList &list) : list_(&list) {}
+    std::vector<Category> run(int type, DelayCallback *delay = nullptr);  // PairwiseDistances::PD_INTRA / PD_INTER
+
+  private:
+    const SequenceList *list_;
+    std::shared_ptr<PairwiseDistances> intra_, inter_;  // kept between runs like the reference's fields (:125-152)
+};
+
+// SpeciesIdentifier/DistanceAnalysis.java:161-320: per-genus means of the smallest / mean congeneric, allospecific distance
+class DistanceAnalysis {
+  public:
+    explicit DistanceAnalysis(const SequenceList &list) : list_(&list) {}
+    std::string run(DelayCallback *delay = nullptr);
+
+  private:
+    const SequenceList *list_;
 };
 
 // Common/DNA/SpeciesDetails.java / SpeciesDetail.java:78-95

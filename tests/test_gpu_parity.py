@@ -283,3 +283,31 @@ def test_pairs_batch(ctx):
     with pytest.raises(t.TdnaError):
         aln.pairs(np.array([0, 180], np.int32), np.array([1, 2], np.int32))
     aln.close()
+
+
+def test_query_distances(ctx):
+    """tdna_query_distances: a sequence that is not in the list against every row (QuerySequence.java:113-145) == the
+    oracle's row for that sequence appended to the list; queries shorter than, as long as and longer than the alignment."""
+    import taxondna_b200 as t
+    rng = np.random.default_rng(33)
+    n, L = 300, 200
+    sym, lens = random_alignment(rng, n, L, ragged=True)
+    aln = t.Alignment(ctx, sym, lens)
+    for qlen in (0, 1, 150, 200, 260):
+        q = np.frombuffer(SYMS, dtype=np.uint8)[rng.integers(0, len(SYMS), size=qlen)].copy()
+        width = max(L, qlen)
+        rows2 = np.full((n + 1, width), ord("?"), dtype=np.uint8)
+        rows2[:n, :L] = sym
+        rows2[n, :qlen] = q
+        lens2 = np.concatenate([lens, [qlen]]).astype(np.int32)
+        for mode, ambig in MODES:
+            aln.set_config(mode, 40, ambig)
+            ref = oracle.all_pairs(rows2, lens2, mode, 40, ambig, threads=8)
+            d, sh, c = aln.query_distances(q, want_counts=True)
+            assert np.array_equal(u64(d), u64(ref["dist"][n, :n])), (qlen, mode, ambig)
+            assert np.array_equal(sh, ref["shared"][n, :n]), (qlen, mode, ambig)
+            for k in ("shared", "c1", "c2", "c3"):
+                assert np.array_equal(c[k], ref[k][n, :n]), (qlen, mode, ambig, k)
+    with pytest.raises(t.TdnaError):
+        aln.query_distances(b"ACGTU")  # U is outside the normalised alphabet (Sequence.java:1727-1763 rejects it)
+    aln.close()

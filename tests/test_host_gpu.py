@@ -135,6 +135,41 @@ def run_all_consumers(H, text, mode, overlap, threshold=3.0, expect_host_rows=No
                 g = pd.getAverageDistance(nm)
                 assert (g != g and v != v) or g == v, (nm, g, v)
             assert pd.getAverageDistance("no such sequence") == -1.0
+    # the remaining getPairwise consumers
+    etext, erecs = C.extreme_pairwise(D)
+    ep = H.ExtremePairwise(lst)
+    assert ep.run() == etext
+    assert ep.rows() == [(-2, -2) if r is None else (-1 if r[0] is None else r[0], -1 if r[1] is None else r[1]) for r in erecs]
+    for kind in (H.PairwiseDistances.PD_INTRA, H.PairwiseDistances.PD_INTER):
+        try:
+            ecats = C.pairwise_explorer(D, kind)
+        except C.ComparisonContractError:
+            continue
+        got = H.PairwiseExplorer(lst).run(kind)
+        assert [k for k, _ in got] == [k for k, _ in ecats]
+        for (_, g), (_, e) in zip(got, ecats):
+            assert [(a, b) for a, b, _ in g] == [(a, b) for a, b, _ in e]
+            assert np.array_equal(np.array([d for _, _, d in g]).view(np.uint64), np.array([d for _, _, d in e]).view(np.uint64))
+    try:
+        dtext, _ = C.distance_analysis(D)
+    except C.JavaNPE:
+        with pytest.raises(Exception):
+            H.DistanceAnalysis(lst).run()
+    else:
+        assert H.DistanceAnalysis(lst).run() == dtext
+    # QuerySequence: a pasted sequence that is not in the list -- a mutated copy of a list member, a short fragment, and whitespace
+    rng = np.random.default_rng(5)
+    for which, cut in ((0, None), (len(oseqs) // 2, 350)):
+        member = oseqs[which].seq
+        raw = list((member.decode() if isinstance(member, bytes) else member).replace("_", "-"))
+        for pos in rng.integers(0, len(raw), size=12):
+            raw[pos] = "ACGT"[int(rng.integers(0, 4))]
+        raw = "".join(raw)[:cut]
+        pasted = "\n".join(raw[i:i + 60] for i in range(0, len(raw), 60)) + " \n"
+        qlines, qpos = C.query_sequence(oseqs, C.Config(mode, overlap, True), pasted, threads=8)
+        qs = H.QuerySequence(lst)
+        assert qs.query(pasted) == qlines
+        assert qs.positions() == qpos
     oc, ostats = C.cluster(D, threshold / 100)
     cl = H.Cluster(lst)
     cl.setThreshold(threshold)
