@@ -473,17 +473,20 @@ int ensure_tc(tdna_aln *a) {
     if (cudaSuccess != DMALLOC(&a->d_tcfull, npan)) { cudaGetLastError(); a->tc_state = -1; return -1; }
     cudaMemsetAsync(a->d_tcfull, 0, npan, c->stream);
     tc::encode_kernel<false, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcA, d_flag, a->d_tcfull);
+    if (getenv("TDNA_TC_DEBUG")) fprintf(stderr, "[tc] a-side encode: %s\n", cudaGetErrorString(cudaStreamSynchronize(c->stream)));
     if (tc_pair_mode())  // cta_group::2: the b-side in 128-row panels as well (each CTA of a pair stages half of the tile's columns)
         tc::encode_kernel<true, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcB, d_flag, nullptr);
     else
         tc::encode_kernel<true, tc::N><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::N)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcB, d_flag, nullptr);
     a->tc_pair = tc_pair_mode();
+    if (getenv("TDNA_TC_DEBUG")) fprintf(stderr, "[tc] b-side encode: %s\n", cudaGetErrorString(cudaStreamSynchronize(c->stream)));
     tc::flip_flags_kernel<<<(unsigned)((npan + 255) / 256), 256, 0, c->stream>>>(a->d_tcfull, (int64_t)npan, (int64_t)((a->n + tc::M - 1) / tc::M));  // gappy -> full
     c->launches++;
     c->launches += 2;
     int flag = 0;
     cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) flag = 1;
+    if (getenv("TDNA_TC_DEBUG")) fprintf(stderr, "[tc] flag = 0x%x\n", flag);
     // bulk phase: bands of TC_BAND row tiles, column tile outer / row tile inner (tdna_tc.cuh: tile_coords)
     int nrt = (int)(npa / tc::M);
     int64_t nct = npb / tc::N;

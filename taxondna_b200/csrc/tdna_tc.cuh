@@ -133,40 +133,45 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
     const int c = blockIdx.x;
     const int64_t panel = blockIdx.y;
     const int s0 = (c * KB) / DIMS;
-    bool bad = false;
-    for (int idx = threadIdx.x; idx < ROWS * ENC_SITES; idx += 256) {
-        const int row_l = idx / ENC_SITES, s = idx % ENC_SITES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    bool bad = false, gappy = false;
+    for (int row_l = warp; row_l < ROWS; row_l += 8) {  // one warp per row: a run of ENC_SITES consecutive bytes
         const int64_t row = panel * ROWS + row_l;
-        const int site = s0 + s;
-        uint8_t code = 5;
-        if (row < n && site < L && site < len[row]) {
-            switch (__ldg(sym + row * sym_stride + site)) {
-                case 'A': code = 0; break;
-                case 'C': code = 1; break;
-                case 'G': code = 2; break;
-                case 'T': code = 3; break;
-                case '-': code = DIMS == 5 ? 4 : 5; break;  // K2P ignores gap sites (Sequence.java:1446-1471)
-                case '_': case '?': code = 5; break;
-                default: code = 5; bad = true; break;
+        const int row_len = row < n ? min(len[row], L) : 0;
+        for (int s = lane; s < ENC_SITES; s += 32) {
+            const int site = s0 + s;
+            uint32_t code = 5;
+            if (site < row_len) {
+                const uint32_t cls = c_symlut[sym[row * sym_stride + site]];  // the pack kernel's table: IUPAC mask in bits 0..3 (A C G T)
+                const uint32_t bases = cls & 15u;
+                if (cls & SB_LET) {
+                    if (__popc(bases) == 1) code = (uint32_t)__ffs((int)bases) - 1u;
+                    else bad = true;            // an ambiguity letter: this alignment is for the popc kernel
+                } else if (cls & SB_D) code = DIMS == 5 ? 4u : 5u;  // K2P ignores gap sites (Sequence.java:1446-1471)
+                else if (cls & 0x8000u) bad = true;
             }
+            codes[row_l][s] = (uint8_t)code;
+            // a site of the alignment of an existing row that contributes nothing: the panel is not "full"
+            if (row < n && site < L && code >= (uint32_t)DIMS) gappy = true;
         }
-        codes[row_l][s] = code;
-        // a site of the alignment (site < L) of an existing row that contributes nothing: the panel is not "full"
-        if (panel_gappy && row < n && site < L && s < (KB + DIMS - 1) / DIMS + 1 && code >= DIMS) panel_gappy[panel] = 1;
     }
     if (bad) atomicOr(not_clean, 1);
+    if constexpr (!BSIDE) {  // only the a-side launch tracks this (its panels are the 128-row panels the tile kernel asks about)
+        if (gappy) panel_gappy[panel] = 1;
+    }
     __syncthreads();
     uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)panel * nchunks + c) * (size_t)(ROWS * KB));
     const int va = BSIDE ? v.c : v.a, vb = BSIDE ? v.d : v.b;
     for (int u = threadIdx.x; u < ROWS * (KB / 16); u += 256) {
         const int row_l = u % ROWS, k16 = u / ROWS;  // u = (k16 * (ROWS / 8) + rg) * 8 + r, row = rg * 8 + r
         uint32_t w[4] = {0, 0, 0, 0};
+        int kk = c * KB + k16 * 16, site = kk / DIMS - s0, dim = kk % DIMS;  // one division per 16 bytes, then a running (site, dim)
 #pragma unroll
         for (int b = 0; b < 16; b++) {
-            const int kk = c * KB + k16 * 16 + b, site = kk / DIMS - s0, dim = kk % DIMS;
             const int code = codes[row_l][site];
             const int val = code < DIMS ? vb + (dim == code ? va : 0) : 0;
             w[b >> 2] |= (uint32_t)(val & 0xff) << (8 * (b & 3));
+            if (++dim == DIMS) { dim = 0; site++; }
         }
         dst[u] = make_uint4(w[0], w[1], w[2], w[3]);
     }

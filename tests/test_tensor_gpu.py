@@ -159,3 +159,33 @@ def test_k2p_streaming_on_the_tensor_kernel(ctx, shuffle, ragged, L, saturated):
         sorted(zip(b["edge_i"].tolist(), b["edge_j"].tolist(), b["edge_d"].tolist()))
     assert first_difference(ap, bp) is None, first_difference(ap, bp)
     aln.close()
+
+
+@pytest.mark.parametrize("n,L", [(1024, 2664), (700, 1300)])
+def test_ambiguity_codes_at_scale_fall_back_cleanly(ctx, n, L):
+    """An alignment full of IUPAC ambiguity letters ('?', gaps and external gaps too) is not for kernel (b): the operand
+    encoder must say so and leave the device usable -- AUTO then serves every consumer from the popc kernel.
+    (Regression: the C4 shape, 5,000 x 2,664 with 4 % ambiguity letters, once took the context down here.)"""
+    import taxondna_b200 as t
+    from taxondna_b200 import synth
+    d = synth.generate("C4", names=False, genera=8, species=8, reps=max(1, n // 64), L=L)
+    sym = np.ascontiguousarray(d["symbols"][:n])
+    n = sym.shape[0]
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+    aln = t.Alignment(ctx, sym)
+    aln.set_labels(*(d[k][:n] for k in ("species_id", "genus_id", "epithet_rank", "fullname_rank")))
+    aln.set_config(t.PDM_UNCORRECTED, 300, True)
+    with pytest.raises(t.TdnaError) as ei:
+        aln.tensor_counts()
+    assert ei.value.code == 4
+    (shared, ident, _, _), dist = aln.pair(0, 1)  # the context is alive
+    ref = oracle.all_pairs(sym[:2], np.full(2, L, np.int32), 0, 300, True)
+    assert shared == ref["shared"][0, 1] and ident == ref["c1"][0, 1]
+    intra = aln.class_distances(t.PD_INTRA)
+    assert aln.last_count_kernel() == t.KERNEL_POPC
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_DENSE)
+    dense = aln.class_distances(t.PD_INTRA)
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+    assert np.array_equal(np.sort(intra), np.sort(dense))
+    aln.close()
