@@ -65,9 +65,9 @@ struct Params {
     const int4 *panel_range;  // column panels share no species / genus id range hold no such pair and are skipped by every role
 };
 
-// Tile slot -> (row tile, column tile); false = an empty slot.  The bulk phase walks BANDS of `band` row tiles,
-// column tile outer / row tile inner, so that the ~148 tiles in flight at any time share ~16 a-panels and ~9
-// b-panels: every operand block is fetched from HBM about once per band and otherwise hits L2.
+// Tile slot -> (row tile, column tile); false = an empty slot.  The bulk phase walks BANDS of `band` row tiles (64 by
+// default), column tile outer / row tile inner, so that the ~148 tiles in flight at any time share the band's a-panels
+// (L2-resident for the whole band) and two or three b-panels: every b-panel is fetched from HBM once per band.
 __device__ __forceinline__ bool slot_coords(const Params &p, const int64_t *prefix, int64_t t, int &ti, int &tj) {
     if (p.band == 0) {
         ti = (int)t;
