@@ -93,6 +93,7 @@ struct tdna_aln {
     int64_t sprefix_tiles[2] = {0, 0};
     int sprefix_cn = 0;
     long long *d_ptr = nullptr;  // CSR row pointers [n + 1]
+    long long *d_scan = nullptr; // block sums of the row-pointer scan
     int *d_cursor = nullptr;
     int32_t *d_lj = nullptr;
     double *d_ld = nullptr;
@@ -834,7 +835,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
                     a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
-                    a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_cursor, a->d_lj, a->d_ld};
+                    a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_cursor, a->d_lj, a->d_ld};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
     delete a;
@@ -1222,7 +1223,19 @@ static int stream_part(tdna_aln *a, int part, int nparts, long long *ncand_out) 
     return stream_bulk(a, part, nparts, ncand_out);
 }
 
-// candidate records (device) -> per-row lists -> exact summaries into a->d_res
+// CSR row pointers d_ptr[0..n] from the per-row record counts: three launches (tdna_kernels.cuh: scan_*_kernel)
+static int row_pointers(tdna_aln *a, const int *cnt) {
+    tdna_ctx *c = a->ctx;
+    const int64_t nb = (a->n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (!a->d_scan) CU(DMALLOC(&a->d_scan, (size_t)nb * 8));
+    scan_block_sums_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(cnt, a->n, a->d_scan);
+    scan_block_offsets_kernel<<<1, 1024, 0, c->stream>>>(a->d_scan, nb, a->d_ptr + a->n);
+    scan_apply_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(cnt, a->n, a->d_scan, a->d_ptr);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    return TDNA_OK;
+}
+
 static int stream_merge(tdna_aln *a, const int32_t *cq, const int32_t *cj, const double *cd, long long ncand, const int32_t *inval,
                         const int32_t *flags, bool counts_ready) {
     tdna_ctx *c = a->ctx;
@@ -1238,8 +1251,7 @@ static int stream_merge(tdna_aln *a, const int32_t *cq, const int32_t *cj, const
         count_rows_kernel<<<gr, 256, 0, c->stream>>>(cq, ncand, cnt);
         c->launches++;
     }
-    exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(cnt, a->n, a->d_ptr);
-    c->launches++;
+    TRY(row_pointers(a, cnt));
     if (ncand > a->list_cap) {
         if (a->d_lj) CU(DFREE(a->d_lj));
         if (a->d_ld) CU(DFREE(a->d_ld));
@@ -1339,11 +1351,11 @@ int32_t tdna_best_match_merge_gathered(tdna_aln *a, const int64_t *rec, int32_t 
     CU(cudaMemsetAsync(a->sp.cnt, 0, n * 4, c->stream));
     CU(cudaMemsetAsync(a->d_cursor, 0, n * 4, c->stream));
     count_rows_seg_kernel<<<gr, 256, 0, c->stream>>>(lrec, nseg, seg_stride, lcnt, a->sp.cnt);
-    exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(a->sp.cnt, a->n, a->d_ptr);
+    TRY(row_pointers(a, a->sp.cnt));
     scatter_seg_kernel<<<gr, 256, 0, c->stream>>>(lrec, nseg, seg_stride, lcnt, a->d_ptr, a->d_cursor, a->d_lj, a->d_ld);
     stream_finalize_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, a->sp.inval, a->sp.flags, a->d_species, a->n,
                                                                                     a->d_res);
-    c->launches += 5;
+    c->launches += 4;
     CU(cudaGetLastError());
     TRY(fill_shared(a, 0, a->n));
     if (out) CU(cudaMemcpyAsync(out, a->d_res, n * sizeof(tdna_row_result), cudaMemcpyDefault, c->stream));

@@ -1105,13 +1105,35 @@ __global__ void __launch_bounds__(256) stream_thr_kernel(StreamParams sp, int64_
     sp.thr[q] = min(sp.thr[q], tf);
 }
 
-// exclusive prefix sum of cnt[0..n) into ptr[0..n] (one CTA; n <= a few million)
-__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int *__restrict__ cnt, int64_t n, long long *__restrict__ ptr) {
+// exclusive prefix sum of cnt[0..n) into ptr[0..n], three launches: per-block sums (SCAN_BLOCK items per CTA), a one-CTA scan of
+// the block sums, per-block scan + offset.  (One CTA over all n took 48 us at n = 50,000 and a millisecond at 10^6 rows.)
+constexpr int SCAN_BLOCK = 4096, SCAN_PER_THREAD = SCAN_BLOCK / 256;
+__global__ void __launch_bounds__(256) scan_block_sums_kernel(const int *__restrict__ cnt, int64_t n, long long *__restrict__ bsum) {
+    __shared__ long long s_w[8];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK;
+    long long sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {  // coalesced: consecutive threads, consecutive items
+        const int64_t i = base + k * 256 + threadIdx.x;
+        if (i < n) sum += cnt[i];
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < 8; w++) t += s_w[w];
+        bsum[blockIdx.x] = t;
+    }
+}
+// one CTA: exclusive scan of the nb block sums in place; total -> ptr_n[0]
+__global__ void __launch_bounds__(1024) scan_block_offsets_kernel(long long *__restrict__ bsum, int64_t nb, long long *__restrict__ ptr_n) {
     __shared__ long long s_part[1024];
     const int t = threadIdx.x;
-    const int64_t per = (n + 1023) / 1024, b = t * per, e = min(n, b + per);
+    const int64_t per = (nb + 1023) / 1024, b = t * per, e = min(nb, b + per);
     long long sum = 0;
-    for (int64_t i = b; i < e; i++) sum += cnt[i];
+    for (int64_t i = b; i < e; i++) sum += bsum[i];
     s_part[t] = sum;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele over the 1024 partials
@@ -1121,8 +1143,45 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int *__restr
         __syncthreads();
     }
     long long run = s_part[t] - sum;
-    for (int64_t i = b; i < e; i++) { ptr[i] = run; run += cnt[i]; }
-    if (t == 1023) ptr[n] = s_part[1023];
+    for (int64_t i = b; i < e; i++) { const long long v = bsum[i]; bsum[i] = run; run += v; }
+    if (t == 1023) *ptr_n = s_part[1023];
+}
+// thread t of a block owns items [t * 16, t * 16 + 16) of the block's 4096
+__global__ void __launch_bounds__(256) scan_apply_kernel(const int *__restrict__ cnt, int64_t n, const long long *__restrict__ boff,
+                                                         long long *__restrict__ ptr) {
+    __shared__ long long s_w[8];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+    int v[SCAN_PER_THREAD];
+    long long sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD / 4; k++) {  // 16-byte loads; cnt is 16-byte aligned and base a multiple of 16 items
+        int4 q = make_int4(0, 0, 0, 0);
+        const int64_t i = base + 4 * k;
+        if (i + 3 < n) q = *reinterpret_cast<const int4 *>(cnt + i);
+        else {
+            if (i < n) q.x = cnt[i];
+            if (i + 1 < n) q.y = cnt[i + 1];
+            if (i + 2 < n) q.z = cnt[i + 2];
+        }
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+        sum += (long long)q.x + q.y + q.z + q.w;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    long long run = boff[blockIdx.x] + incl - sum;
+    for (int k = 0; k < w; k++) run += s_w[k];
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        if (base + k < n) ptr[base + k] = run;
+        run += v[k];
+    }
 }
 
 // scatter the unordered records into per-row lists; cursor[] starts at zero
