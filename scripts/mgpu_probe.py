@@ -1,4 +1,4 @@
-"""Development probe (torchrun): where a multi-GPU streaming Best-Match step spends its time."""
+"""Development probe (torchrun): where a multi-GPU streaming Best-Match step (the packed exchange bench.py uses) spends its time."""
 import os
 import sys
 import time
@@ -9,7 +9,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, ".")
 import taxondna_b200 as t
-from taxondna_b200 import shard, synth
+from taxondna_b200 import synth
 
 world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -25,6 +25,10 @@ aln = t.Alignment(ctx, sym)
 aln.set_labels(data["species_id"], data["genus_id"], data["epithet_rank"], data["fullname_rank"])
 aln.set_config(0, 300, True)
 stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
+seg = max(1 << 16, (32 * n) // world)
+xb = {"rec": torch.empty((seg, 2), dtype=torch.int64, device=dev), "count": torch.zeros(1, dtype=torch.int64, device=dev),
+      "counts": torch.zeros(world, dtype=torch.int64, device=dev), "state": torch.empty(n, dtype=torch.int64, device=dev),
+      "allrec": torch.empty((world, seg, 2), dtype=torch.int64, device=dev)}
 
 
 class Dev:
@@ -38,6 +42,7 @@ def sync():
 
 
 for rep in range(6):
+    aln.set_config(0, 300, True)
     dist.barrier()
     ts = [sync()]
     mins = aln.best_match_seed(rank, world); ts.append(sync())
@@ -45,18 +50,16 @@ for rep in range(6):
         mt = torch.as_tensor(Dev(mins, 3 * n, "<i8"), device=dev)
         dist.all_reduce(mt, op=dist.ReduceOp.MIN)
     ts.append(sync())
-    part = aln.best_match_part(rank, world, seeded=True); ts.append(sync())
-    k = int(part.n_cand)
+    aln.best_match_part_packed(rank, world, True, xb["rec"].data_ptr(), seg, xb["count"].data_ptr(), xb["state"].data_ptr()); ts.append(sync())
+    tile_ms = ctx.last_tile_pass_ms()
     with torch.cuda.stream(stream):
-        rows = torch.as_tensor(Dev(part.cand_row, k, "<i4"), device=dev)
-        cols = torch.as_tensor(Dev(part.cand_col, k, "<i4"), device=dev)
-        d = torch.as_tensor(Dev(part.cand_d, k, "<f8"), device=dev)
-        inval = torch.as_tensor(Dev(part.invalid_count, n, "<i4"), device=dev)
-        flags = torch.as_tensor(Dev(part.flags, n, "<i4"), device=dev)
-        ur, uc, ud, ui, uf = shard.exchange_candidates(rows, cols, d, inval, flags)
+        dist.all_gather_into_tensor(xb["counts"], xb["count"])
+        dist.all_gather_into_tensor(xb["allrec"].view(-1), xb["rec"].view(-1))
+        dist.all_reduce(xb["state"], op=dist.ReduceOp.SUM)
     ts.append(sync())
-    res = aln.best_match_merge(ur.data_ptr(), uc.data_ptr(), ud.data_ptr(), ur.numel(), ui.data_ptr(), uf.data_ptr()); ts.append(sync())
+    aln.best_match_merge_gathered(xb["allrec"].data_ptr(), world, seg, xb["counts"].data_ptr(), xb["state"].data_ptr(), None); ts.append(sync())
     if rank == 0:
-        names = ["seed", "allreduce_min", "bulk", "exchange", "merge+d2h"]
-        print("rep", rep, " ".join("%s=%.3f" % (nm, (b - a) * 1e3) for nm, a, b in zip(names, ts, ts[1:])), "total=%.3f ms, cand/rank %d" % ((ts[-1] - ts[0]) * 1e3, k), flush=True)
+        names = ["seed", "allreduce_min", "part_packed", "exchange", "merge"]
+        print("rep", rep, "n", n, " ".join("%s=%.3f" % (nm, (b - a) * 1e3) for nm, a, b in zip(names, ts, ts[1:])),
+              "total=%.3f ms (tile pass %.3f), records/rank %d, seg %d" % ((ts[-1] - ts[0]) * 1e3, tile_ms, int(xb["count"].item()), seg), flush=True)
 dist.destroy_process_group()
