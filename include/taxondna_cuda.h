@@ -234,8 +234,10 @@ enum { TDNA_OPT_BEST_MATCH_PATH = 1, /* TDNA_PATH_*: how tdna_best_match compute
        TDNA_OPT_COUNT_KERNEL = 3     /* TDNA_KERNEL_*: which count kernel the streaming pass uses */ };
 enum { TDNA_KERNEL_AUTO = 0,   /* the faster eligible one (A/B on ncu evidence) */
        TDNA_KERNEL_POPC = 1,   /* (a) bit-planes + LOP3/POPC, any alphabet, any mode */
-       TDNA_KERNEL_TENSOR = 2  /* (b) one-hot int8 contraction on tcgen05/TMEM: uncorrected p, ambiguity allowed, alignments
-                                  without IUPAC ambiguity letters, L < 4096; TDNA_E_STATE if the alignment is not eligible */ };
+       TDNA_KERNEL_TENSOR = 2  /* (b) one-hot int8 contraction on tcgen05/TMEM: uncorrected p with ambiguity allowed, or K2P;
+                                  L < 4096.  Pairs that involve IUPAC ambiguity letters are only BOUNDED by it (enough for the
+                                  candidate filter); their exact counts come from the bit-planes.  TDNA_E_STATE if the
+                                  configuration is not eligible */ };
 enum { TDNA_PATH_AUTO = 0,   /* streaming; falls back to the dense path if the candidate buffer overflows */
        TDNA_PATH_DENSE = 1,  /* materialise row bands of the fp64 matrix, sweep them */
        TDNA_PATH_STREAM = 2  /* streaming only (TDNA_E_TOO_LARGE on overflow) */ };

@@ -102,7 +102,9 @@ struct tdna_aln {
     int last_kernel = 0;  // TDNA_KERNEL_* of the most recent streaming pass
     bool avoid_tensor = false;  // AUTO: kernel (b)'s queue overflowed on this alignment (static thresholds too loose): use kernel (a)
     // count kernel (b): one-hot int8 operands (tdna_tc.cuh)
-    uint8_t *d_tcA = nullptr, *d_tcB = nullptr, *d_tcfull = nullptr;
+    uint8_t *d_tcA = nullptr, *d_tcB = nullptr, *d_tcfull = nullptr, *d_tcpanel_amb = nullptr;
+    int32_t *d_tcamb = nullptr;  // per row: sites holding a letter the operands cannot express (nullptr state: see tc_has_amb)
+    bool tc_has_amb = false;
     int tc_state = 0;  // 0 = not built, 1 = ready, -1 = not eligible
     int tc_nchunks = 0, tc_kmode = -1, tc_dims = 5;
     uint32_t tc_W = 0;
@@ -386,7 +388,8 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
             int wshift = 0;
             while ((1u << wshift) < a->tc_W) wshift++;
             unsigned grid = (unsigned)c->sm_count * 8;
-            tc::ResolveArgs ra = {wshift, a->tc_W - 1u, a->min_overlap, a->kmode == KM_K2P ? a->d_planes : nullptr, a->W};
+            tc::ResolveArgs ra = {wshift, a->tc_W - 1u, a->min_overlap, (a->kmode == KM_K2P || a->tc_has_amb) ? a->d_planes : nullptr, a->W,
+                                  a->kmode == KM_K2P ? 1 : 0};
             if (a->sp.want & TDNA_WANT_BEST_MATCH) {
                 tc::resolve_min_kernel<<<grid, 256, 0, c->stream>>>(a->sp, ra);
                 stream_thr_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n);
@@ -450,6 +453,10 @@ int ensure_tc(tdna_aln *a) {
         DFREE(a->d_tcB);
         if (a->d_tcfull) DFREE(a->d_tcfull);
         a->d_tcfull = nullptr;
+        if (a->d_tcamb) DFREE(a->d_tcamb);
+        if (a->d_tcpanel_amb) DFREE(a->d_tcpanel_amb);
+        a->d_tcamb = nullptr;
+        a->d_tcpanel_amb = nullptr;
         if (a->d_tcprefix[1]) DFREE(a->d_tcprefix[1]);
         a->d_tcA = a->d_tcB = nullptr;
         a->d_tcprefix[1] = nullptr;
@@ -475,6 +482,16 @@ int ensure_tc(tdna_aln *a) {
     a->d_tcfull = nullptr;
     if (cudaSuccess != DMALLOC(&a->d_tcfull, npan)) { cudaGetLastError(); a->tc_state = -1; return -1; }
     cudaMemsetAsync(a->d_tcfull, 0, npan, c->stream);
+    // ambiguity letters: per-row counts and per-panel flags (d_flag[1] = any at all)
+    if (a->d_tcamb) DFREE(a->d_tcamb);
+    if (a->d_tcpanel_amb) DFREE(a->d_tcpanel_amb);
+    a->d_tcamb = nullptr;
+    a->d_tcpanel_amb = nullptr;
+    if (cudaSuccess != DMALLOC(&a->d_tcamb, (size_t)a->n * 4) || cudaSuccess != DMALLOC(&a->d_tcpanel_amb, npan)) { cudaGetLastError(); a->tc_state = -1; return -1; }
+    cudaMemsetAsync(a->d_tcpanel_amb, 0, npan, c->stream);
+    tc::amb_count_kernel<<<(unsigned)((a->n + 7) / 8), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, a->kmode == KM_K2P ? 1 : 0, a->d_tcamb,
+                                                                            a->d_tcpanel_amb, d_flag + 1);
+    c->launches++;
     tc::encode_kernel<false, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcA, d_flag, a->d_tcfull);
     if (getenv("TDNA_TC_DEBUG")) fprintf(stderr, "[tc] a-side encode: %s\n", cudaGetErrorString(cudaStreamSynchronize(c->stream)));
     if (tc_pair_mode())  // cta_group::2: the b-side in 128-row panels as well (each CTA of a pair stages half of the tile's columns)
@@ -486,9 +503,11 @@ int ensure_tc(tdna_aln *a) {
     tc::flip_flags_kernel<<<(unsigned)((npan + 255) / 256), 256, 0, c->stream>>>(a->d_tcfull, (int64_t)npan, (int64_t)((a->n + tc::M - 1) / tc::M));  // gappy -> full
     c->launches++;
     c->launches += 2;
-    int flag = 0;
-    cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream);
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) flag = 1;
+    int flags2[2] = {0, 0};
+    cudaMemcpyAsync(flags2, d_flag, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) flags2[0] = 1;
+    int flag = flags2[0];
+    a->tc_has_amb = flags2[1] != 0;
     if (getenv("TDNA_TC_DEBUG")) fprintf(stderr, "[tc] flag = 0x%x\n", flag);
     // bulk phase: bands of TC_BAND row tiles, column tile outer / row tile inner (tdna_tc.cuh: tile_coords)
     int nrt = (int)(npa / tc::M);
@@ -510,7 +529,7 @@ int ensure_tc(tdna_aln *a) {
             a->tcprefix_tiles[1] = pre[nbands];
         }
     }
-    if (flag) {  // an IUPAC ambiguity letter (or an allocation failure): the popc kernel handles this alignment
+    if (flag) {  // a symbol outside the alphabet (the pack kernel rejects those first) or an allocation failure: the popc kernel handles it
         DFREE(a->d_tcA);
         DFREE(a->d_tcB);
         a->d_tcA = a->d_tcB = nullptr;
@@ -588,6 +607,8 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.k2p = a->kmode == KM_K2P ? 1 : 0;
     p.panel_full = a->d_tcfull;
     p.L = a->L;
+    p.amb = a->tc_has_amb ? a->d_tcamb : nullptr;
+    p.panel_amb = a->d_tcpanel_amb;
     if (!COUNTS_MODE && a->d_panel_range && (a->sp.want & ~(TDNA_WANT_INTRA | TDNA_WANT_INTER)) == 0 && !getenv("TDNA_TC_NOSKIP")) {
         p.class_only = ((a->sp.want & TDNA_WANT_INTRA) ? 1 : 0) | ((a->sp.want & TDNA_WANT_INTER) ? 2 : 0);
         p.panel_range = a->d_panel_range;
@@ -834,7 +855,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     cudaSetDevice(c->device);
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
-                    a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
+                    a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_cursor, a->d_lj, a->d_ld};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
@@ -1718,7 +1739,8 @@ int32_t tdna_tensor_counts(tdna_aln *a, tdna_counts *out) {
     CU(cudaSetDevice(c->device));
     TRY(ensure_packed(a));
     if (a->kmode != KM_P_AMBIG) return fail(TDNA_E_STATE, "tdna_tensor_counts: uncorrected p only (for K2P the accumulator carries n and ts + tv)");
-    if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p (ambiguity allowed) or K2P, an alignment without IUPAC ambiguity letters, L < 4096");
+    if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p (ambiguity allowed) or K2P, and L < 4096");
+    if (a->tc_has_amb) return fail(TDNA_E_STATE, "tdna_tensor_counts: the alignment has IUPAC ambiguity letters -- kernel (b) only bounds such pairs (exact counts come from the bit-planes)");
     tdna_counts *dc = out;
     bool own = !is_device_ptr(out);
     size_t bytes = (size_t)a->n * a->n * sizeof(tdna_counts);

@@ -61,6 +61,11 @@ struct Params {
     int a_rows, b_rows;     // rows of the tensor-map view per a / b stage block (view row = inner box width)
     int hints;              // L2 cache-policy hints on the operand loads (experiments: TDNA_TC_HINTS)
     int piece;              // bytes per 1-D bulk copy (divides 16 KB); 0 = tensor-map (2-D tiled TMA) loads
+    // IUPAC ambiguity letters are encoded as "no contribution"; amb[i] = how many of them row i
+    // has.  The accumulator then bounds the pair from both sides -- mism >= mism', shared' <= shared <= shared' + amb[i] + amb[j] --
+    // which is all the candidate filter needs; exact counts of the queued pairs come from the bit-planes (like K2P's).
+    const int32_t *amb;        // nullptr: the alignment has no such letter
+    const uint8_t *panel_amb;  // [128-row panel] 1 = some row of the panel has one
     int class_only;         // the pass wants class distances and nothing per row: bit 0 = intra, bit 1 = inter.  Tiles whose row and
     const int4 *panel_range;  // column panels share no species / genus id range hold no such pair and are skipped by every role
 };
@@ -144,9 +149,8 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
             if (site < row_len) {
                 const uint32_t cls = c_symlut[sym[row * sym_stride + site]];  // the pack kernel's table: IUPAC mask in bits 0..3 (A C G T)
                 const uint32_t bases = cls & 15u;
-                if (cls & SB_LET) {
+                if (cls & SB_LET) {  // an ambiguity letter contributes nothing here: amb_count_kernel counts it, the filter allows for it
                     if (__popc(bases) == 1) code = (uint32_t)__ffs((int)bases) - 1u;
-                    else bad = true;            // an ambiguity letter: this alignment is for the popc kernel
                 } else if (cls & SB_D) code = DIMS == 5 ? 4u : 5u;  // K2P ignores gap sites (Sequence.java:1446-1471)
                 else if (cls & 0x8000u) bad = true;
             }
@@ -181,6 +185,27 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
 __global__ void __launch_bounds__(256) flip_flags_kernel(uint8_t *flags, int64_t npan, int64_t real_panels) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < npan) flags[k] = (k < real_panels && flags[k] == 0) ? 1 : 0;
+}
+
+// per row: the number of sites (< min(len, L)) holding a letter the operands cannot express, i.e. any IUPAC ambiguity letter.
+// (K2P: only R and Y are inside the model, Sequence.java:1498-1557, but every letter counts towards the K2P-mode shared length
+// that the minOverlap gate tests, :1446-1471 -- one count bounds both.)
+__global__ void __launch_bounds__(256) amb_count_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len, int64_t n, int64_t sym_stride,
+                                                        int L, int k2p, int32_t *__restrict__ amb, uint8_t *__restrict__ panel_amb, int *__restrict__ any) {
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = threadIdx.x & 31, row_len = min(len[row], L);
+    int cnt = 0;
+    for (int site = lane; site < row_len; site += 32) {
+        const uint32_t cls = c_symlut[sym[row * sym_stride + site]];
+        if ((cls & SB_LET) && __popc(cls & 15u) != 1) cnt++;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, m);
+    if (lane == 0) {
+        amb[row] = cnt;
+        if (cnt) { panel_amb[row / M] = 1; *any = 1; }
+    }
 }
 
 // ---- tcgen05 / TMEM primitives ---------------------------------------------------------------
@@ -234,10 +259,13 @@ __device__ __forceinline__ void tma_load_2d_hint(void *dst_smem, const CUtensorM
 }
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) { mbar_wait_backoff(bar, parity); }
 
-// K2P: exact counts of one pair from the bit-planes (the accumulator only carries n and ts + tv)
-__device__ __noinline__ void class_emit_k2p(const uint32_t *planes, int W32, int i, int j, int min_overlap) {
-    const Counts c = pair_counts_global<KM_K2P>(planes, i, j, W32);
-    class_emit<KM_K2P>(i, j, (uint32_t)c.c1 | ((uint32_t)c.shared << 16), (uint32_t)c.c2 | ((uint32_t)c.c3 << 16), min_overlap);
+// exact counts of one pair from the bit-planes: K2P (the accumulator only carries n and ts + tv) and alignments with ambiguity
+// letters (the accumulator only bounds the counts).  The caller may not know whether the pair has enough overlap: checked here.
+template <int KM> __device__ __noinline__ void class_emit_planes(const uint32_t *planes, int W32, int i, int j, int min_overlap) {
+    const Counts c = pair_counts_global<KM>(planes, i, j, W32);
+    if (c.shared < min_overlap) return;
+    if constexpr (KM == KM_K2P) class_emit<KM_K2P>(i, j, (uint32_t)c.c1 | ((uint32_t)c.shared << 16), (uint32_t)c.c2 | ((uint32_t)c.c3 << 16), min_overlap);
+    else class_emit<KM>(i, j, (uint32_t)c.c1 | ((uint32_t)c.shared << 16), 0u, min_overlap);
 }
 
 // ---- the tile kernel ---------------------------------------------------------------------------
@@ -441,6 +469,9 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             // is mism <= (thr * L) >> 16, with the right-hand side staged per column and kept per row
             const bool full = !COUNTS_MODE && interior && !seed && p.L >= p.min_overlap && p.panel_full[ti] && p.panel_full[2 * tj] &&
                               p.panel_full[2 * tj + 1] && (int64_t)ti * M + M <= p.n;
+            // some row or column of the tile has ambiguity letters: the accumulators bound the counts (see Params::amb)
+            const bool tile_amb = !COUNTS_MODE && p.amb != nullptr && (p.panel_amb[ti] || p.panel_amb[2 * tj] || p.panel_amb[2 * tj + 1]);
+            const uint32_t amb_i = (!COUNTS_MODE && p.amb != nullptr && i < p.n) ? (uint32_t)__ldg(p.amb + i) : 0u;
             uint32_t tf_row = edge_tf;
             if constexpr (!COUNTS_MODE) {
                 __syncwarp();  // the previous tile's reads of my_thr are done
@@ -449,8 +480,9 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     const int j = j0 + g * EPI_COLS + x * 32 + lane;
                     if (seed) my_thr[x * 32 + lane] = (uint32_t)(j < p.n ? __ldg(sp.species + j) : -1);  // seed pass: the columns' species ids
                     else {
-                        const uint32_t t = (want_bm && j < p.n) ? __ldcg(sp.thr + j) : 0u;
-                        my_thr[x * 32 + lane] = full ? (uint32_t)(((unsigned long long)t * (uint32_t)p.L) >> 16) : t;
+                        const uint32_t t = (want_bm && j < p.n) ? __ldcg(sp.thr + j) : 0u;  // <= 2^16
+                        if (tile_amb) my_thr[x * 32 + lane] = t | ((j < p.n ? (uint32_t)__ldg(p.amb + j) : 0u) << 20);  // amb[j] < 4096
+                        else my_thr[x * 32 + lane] = full ? (uint32_t)(((unsigned long long)t * (uint32_t)p.L) >> 16) : t;
                     }
                 }
                 if (want_bm && i < p.n) tf_row = max(tf_row, __ldcg(sp.thr + i));
@@ -494,18 +526,20 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         const int j = jb + e, spj = (int)my_thr[cbi * 32 + e];
                         const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1, s = ident + mism;
                         if (j == i || j >= p.n || i >= p.n || spj < 0 || (int)s < p.min_overlap) continue;
+                        // ambiguity letters: an UPPER bound of the distance is all a threshold needs (0 extra sites: the exact value)
+                        const uint32_t aij = p.amb != nullptr ? amb_i + (uint32_t)__ldg(p.amb + j) : 0u;
                         double d;
                         if (p.k2p) {
                             // only n and ts + tv are known here: d_K2P <= -ln(1 - 2(P+Q)) / 2 (all differences transitions) bounds the
                             // minima from above, which is all a threshold needs; the exact minima come from the queue afterwards
-                            if (mism == 0) d = 0.0;
+                            if (mism + aij == 0) d = 0.0;
                             else {
-                                const double w = dsub(1.0, ddiv(dmul(2.0, (double)mism), (double)s));
+                                const double w = dsub(1.0, ddiv(dmul(2.0, (double)(mism + aij)), (double)s));
                                 if (!(w > 0.0)) continue;
                                 d = dmul(-0.5, strict_log_call(w));
                             }
                         } else {
-                            Counts cn = {(int)s, (int)ident, 0, 0};
+                            Counts cn = {(int)(s + aij), (int)ident, 0, 0};  // 1 - ident' / (shared' + amb) >= the pair's distance
                             d = distance_from_counts<KM_P_AMBIG>(cn, p.min_overlap);
                         }
                         if (!(d < __longlong_as_double((long long)TDNA_INF_BITS)) || d < 0.0) continue;
@@ -521,7 +555,25 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
                         return r;
                     };
-                    if (full) {
+                    if (tile_amb) {
+#pragma unroll
+                        for (int e4 = 0; e4 < 8; e4++) {
+                            const uint4 ct = lds4(ct_addr + e4 * 16);
+                            const uint32_t cts[4] = {ct.x, ct.y, ct.z, ct.w};
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int e = e4 * 4 + u, j = jb + e;
+                                const uint32_t thr_j = cts[u] & 0xfffffu, extra = amb_i + (cts[u] >> 20);
+                                const uint32_t mism = v[e] >> p.wshift, s = v[e] - mism * wm1, sb = s + extra;  // shared' <= shared <= sb
+                                const bool inr = (j > i) & (j < p.n);
+                                const bool sure = (int)s >= p.min_overlap, maybe = (int)sb >= p.min_overlap;
+                                const bool pass = ((mism << 16) <= max(tf_row, thr_j) * sb) | (k2p_force & (2u * (mism + extra) >= s));
+                                if (inr && maybe && (pass || !sure)) pmask |= 1u << e;  // an uncertain overlap is settled by the exact counts
+                                if (inr && !maybe) bmask |= 1u << e;
+                                if (j == i && i < p.n && (int)(s + amb_i) >= p.min_overlap) smask |= 1u << e;  // a row shares all its letters with itself
+                            }
+                        }
+                    } else if (full) {
 #pragma unroll
                         for (int e4 = 0; e4 < 8; e4++) {
                             const uint4 ct = lds4(ct_addr + e4 * 16);
@@ -603,11 +655,13 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         for (int e = 0; e < 32; e++) {
                             const int j = jb + e;
                             const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1, s = ident + mism;
-                            if (j <= i || j >= p.n || (int)s < p.min_overlap) continue;
+                            if (j <= i || j >= p.n) continue;
+                            if ((int)(s + (tile_amb ? amb_i + (uint32_t)__ldg(p.amb + j) : 0u)) < p.min_overlap) continue;
                             const bool hit = ((sp.want & TDNA_WANT_INTRA) && sp.species[i] == sp.species[j]) ||
                                              ((sp.want & TDNA_WANT_INTER) && sp.genus[i] == sp.genus[j]);
                             if (hit) {
-                                if (p.k2p) class_emit_k2p(p.planes, p.W32, i, j, p.min_overlap);
+                                if (p.k2p) class_emit_planes<KM_K2P>(p.planes, p.W32, i, j, p.min_overlap);
+                                else if (tile_amb) class_emit_planes<KM_P_AMBIG>(p.planes, p.W32, i, j, p.min_overlap);
                                 else class_emit<KM_P_AMBIG>(i, j, ident | (s << 16), 0u, p.min_overlap);
                             }
                         }
@@ -634,20 +688,27 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
 }
 
 // ---- after the bulk pass: the queue -> minima -> final thresholds -> candidate records --------------------------
-// every queued pair is a valid pair i < j; value = raw accumulator
+// every queued pair is a pair i < j that is valid or (ambiguity letters) may be; value = raw accumulator
 struct ResolveArgs {
     int wshift;
     uint32_t wm1;
     int min_overlap;
-    const uint32_t *planes;  // non-null: K2P -- exact (n, ts, tv) of the pair from the bit-planes
+    const uint32_t *planes;  // non-null: exact counts of the pair from the bit-planes (K2P; alignments with ambiguity letters)
     int W32;
+    int k2p;
 };
 __device__ __forceinline__ double queued_distance(const ResolveArgs &ra, int i, int j, uint32_t val, uint32_t &lhs, uint32_t &den) {
     if (ra.planes) {
-        const Counts c = pair_counts_global<KM_K2P>(ra.planes, i, j, ra.W32);
-        lhs = (uint32_t)(c.c2 + c.c3) << 16;
-        den = (uint32_t)c.c1;
-        return distance_from_counts<KM_K2P>(c, ra.min_overlap);
+        if (ra.k2p) {
+            const Counts c = pair_counts_global<KM_K2P>(ra.planes, i, j, ra.W32);
+            lhs = (uint32_t)(c.c2 + c.c3) << 16;
+            den = (uint32_t)c.c1;
+            return distance_from_counts<KM_K2P>(c, ra.min_overlap);
+        }
+        const Counts c = pair_counts_global<KM_P_AMBIG>(ra.planes, i, j, ra.W32);
+        lhs = (uint32_t)(c.shared - c.c1) << 16;
+        den = (uint32_t)c.shared;
+        return distance_from_counts<KM_P_AMBIG>(c, ra.min_overlap);  // -1.0: the queued overlap was uncertain and is too short
     }
     const uint32_t mism = val >> ra.wshift, ident = val & ra.wm1, s = ident + mism;
     lhs = mism << 16;
@@ -662,7 +723,7 @@ __global__ void __launch_bounds__(256) resolve_min_kernel(StreamParams sp, Resol
         const int i = sp.qi[r], j = sp.qj[r];
         uint32_t lhs, den;
         const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den);
-        if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) continue;
+        if (!(d < __longlong_as_double((long long)TDNA_INF_BITS)) || d < 0.0) continue;
         const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
         const int spi = sp.species[i], spj = sp.species[j];
         if (spj >= 0 && lhs <= sp.thr[i] * den) { if (spj == spi) atomicMin(sp.mC + i, bits); atomicMin(sp.mPar + 2 * (int64_t)i + (spj & 1), bits); }
@@ -677,6 +738,11 @@ __global__ void __launch_bounds__(256) resolve_emit_kernel(StreamParams sp, Reso
         const int i = sp.qi[r], j = sp.qj[r];
         uint32_t lhs, den;
         const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den);
+        if (d < 0.0) {  // queued with an uncertain overlap (ambiguity letters), and the exact overlap is below minOverlap: an invalid pair
+            atomicAdd(sp.inval + i, 1);
+            atomicAdd(sp.inval + j, 1);
+            continue;
+        }
         if ((sp.want & TDNA_WANT_EDGES) && d >= 0 && d <= sp.edge_t) {
             const unsigned long long pos = atomicAdd(sp.nedge, 1ull);
             if (sp.ei && (long long)pos < sp.edge_cap) { sp.ei[pos] = i; sp.ej[pos] = j; sp.ed[pos] = d; }

@@ -74,8 +74,22 @@ def test_not_eligible_is_reported(ctx):
     aln.close()
 
 
-@pytest.mark.parametrize("shuffle,ragged,L", [(False, False, 658), (True, True, 500), (False, True, 2664)])
-def test_streaming_best_match_on_the_tensor_kernel(ctx, shuffle, ragged, L):
+AMBIG = b"RYKMSWBDHVN"
+
+
+def sprinkle_ambiguity(rng, sym, rate):
+    """IUPAC ambiguity letters everywhere at `rate`; every ninth row is mostly ambiguity letters and '?' so that its overlaps
+    straddle minOverlap (kernel (b) only bounds such pairs: the exact counts must settle them)."""
+    m = rng.random(sym.shape) < rate
+    sym[m] = rng.choice(np.frombuffer(AMBIG, dtype=np.uint8), size=int(m.sum()))
+    for r in range(4, sym.shape[0], 9):
+        m = rng.random(sym.shape[1]) < 0.55
+        sym[r, m] = rng.choice(np.frombuffer(AMBIG + b"????", dtype=np.uint8), size=int(m.sum()))
+
+
+@pytest.mark.parametrize("shuffle,ragged,L,ambig", [(False, False, 658, 0), (True, True, 500, 0), (False, True, 2664, 0),
+                                                    (False, False, 658, 0.03), (True, True, 500, 0.05), (False, True, 2664, 0.04)])
+def test_streaming_best_match_on_the_tensor_kernel(ctx, shuffle, ragged, L, ambig):
     import taxondna_b200 as t
     from test_stream_gpu import first_difference
     from test_gpu_parity import labelled_alignment
@@ -84,6 +98,8 @@ def test_streaming_best_match_on_the_tensor_kernel(ctx, shuffle, ragged, L):
     n = sym.shape[0]
     m = rng.random(sym.shape) < 0.04
     sym[m] = rng.choice(np.frombuffer(CLEAN, dtype=np.uint8), size=int(m.sum()))
+    if ambig:
+        sprinkle_ambiguity(rng, sym, ambig)
     lens = rng.integers(L // 2, L + 1, size=n).astype(np.int32) if ragged else None
     if shuffle:
         perm = rng.permutation(n)
@@ -98,6 +114,7 @@ def test_streaming_best_match_on_the_tensor_kernel(ctx, shuffle, ragged, L):
     a = aln.analyze(best_match=True, intra=True, inter=True, edges=0.03)
     ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_TENSOR)
     b = aln.analyze(best_match=True, intra=True, inter=True, edges=0.03)
+    assert aln.last_count_kernel() == t.KERNEL_TENSOR
     ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
     ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
     assert first_difference(a["rows"], b["rows"]) is None, first_difference(a["rows"], b["rows"])
@@ -108,8 +125,9 @@ def test_streaming_best_match_on_the_tensor_kernel(ctx, shuffle, ragged, L):
     aln.close()
 
 
-@pytest.mark.parametrize("shuffle,ragged,L,saturated", [(False, False, 658, 0), (True, True, 700, 0), (False, False, 400, 25)])
-def test_k2p_streaming_on_the_tensor_kernel(ctx, shuffle, ragged, L, saturated):
+@pytest.mark.parametrize("shuffle,ragged,L,saturated,ambig", [(False, False, 658, 0, 0), (True, True, 700, 0, 0), (False, False, 400, 25, 0),
+                                                              (False, False, 658, 0, 0.04), (True, True, 700, 10, 0.05)])
+def test_k2p_streaming_on_the_tensor_kernel(ctx, shuffle, ragged, L, saturated, ambig):
     """K2P: the accumulator carries (n, ts + tv) -- enough for the conservative filter -- and the exact (n, ts, tv) of the
     queued pairs come from the bit-planes; records, classes and edges must equal the popc kernel's."""
     import taxondna_b200 as t
@@ -119,6 +137,8 @@ def test_k2p_streaming_on_the_tensor_kernel(ctx, shuffle, ragged, L, saturated):
     sym, sp, gen, epi, full = labelled_alignment(rng, 30, 8, L, unnamed=3, dup=8, gappy=False)
     m = rng.random(sym.shape) < 0.05
     sym[m] = rng.choice(np.frombuffer(CLEAN, dtype=np.uint8), size=int(m.sum()))
+    if ambig:  # R and Y are inside the K2P model (purine / pyrimidine), the other ambiguity letters outside it
+        sprinkle_ambiguity(rng, sym, ambig)
     if saturated:  # unrelated rows: P + Q ~ 0.75 -> NaN / +Inf / huge distances must be flagged exactly as by the popc kernel
         rnd = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(saturated, L))
         sym = np.concatenate([sym, rnd])
@@ -163,9 +183,10 @@ def test_k2p_streaming_on_the_tensor_kernel(ctx, shuffle, ragged, L, saturated):
 
 @pytest.mark.parametrize("n,L", [(1024, 2664), (700, 1300)])
 def test_ambiguity_codes_at_scale_fall_back_cleanly(ctx, n, L):
-    """An alignment full of IUPAC ambiguity letters ('?', gaps and external gaps too) is not for kernel (b): the operand
-    encoder must say so and leave the device usable -- AUTO then serves every consumer from the popc kernel.
-    (Regression: the C4 shape, 5,000 x 2,664 with 4 % ambiguity letters, once took the context down here.)"""
+    """An alignment full of IUPAC ambiguity letters ('?', gaps and external gaps too): kernel (b) cannot give exact counts
+    (tdna_tensor_counts says so and leaves the device usable) but serves the streaming consumers as a filter, with the
+    exact counts of the queued pairs from the bit-planes -- identical to kernel (a) and to the dense path.
+    (Regression: the C4 shape, 5,000 x 2,664 with 4 % ambiguity letters, once took the context down in the encoder.)"""
     import taxondna_b200 as t
     from taxondna_b200 import synth
     d = synth.generate("C4", names=False, genera=8, species=8, reps=max(1, n // 64), L=L)
@@ -182,10 +203,17 @@ def test_ambiguity_codes_at_scale_fall_back_cleanly(ctx, n, L):
     (shared, ident, _, _), dist = aln.pair(0, 1)  # the context is alive
     ref = oracle.all_pairs(sym[:2], np.full(2, L, np.int32), 0, 300, True)
     assert shared == ref["shared"][0, 1] and ident == ref["c1"][0, 1]
-    intra = aln.class_distances(t.PD_INTRA)
+    intra = aln.class_distances(t.PD_INTRA)  # AUTO: kernel (b) bounds the pairs with ambiguity letters, the planes settle them
+    assert aln.last_count_kernel() == t.KERNEL_TENSOR
+    rows_b = aln.best_match()
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_POPC)
+    rows_a = aln.best_match()
+    intra_a = aln.class_distances(t.PD_INTRA)
     assert aln.last_count_kernel() == t.KERNEL_POPC
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
     ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_DENSE)
     dense = aln.class_distances(t.PD_INTRA)
     ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
-    assert np.array_equal(np.sort(intra), np.sort(dense))
+    assert np.array_equal(np.sort(intra), np.sort(dense)) and np.array_equal(np.sort(intra_a), np.sort(dense))
+    assert rows_a.tobytes() == rows_b.tobytes()
     aln.close()
