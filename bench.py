@@ -24,6 +24,7 @@ pairs per GPU stay fixed.
 the reference is Java and no JVM exists in this image) on the host cores, bounded sample.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -275,15 +276,28 @@ def main():
     tile_ms = []
     cand_counts = []
     # exchange buffers of the multi-GPU streaming path: one segment of `seg` packed records per rank
-    seg = max(1 << 16, (32 * n) // max(world, 1))
+    # Exchange of the candidate records at N > 1 (TDNA_BENCH_EXCHANGE overrides the choice):
+    #  "gathered": one segment per rank, all_gather, every rank merges all n rows            (least latency: 2 GPUs)
+    #  "routed":   one segment per (source, destination), all_to_all to the rank that owns the row, every rank finalises its own
+    #              rows_per_part rows, all_gather of the row records                          (least volume and merge work: 4+ GPUs)
+    exchange = os.environ.get("TDNA_BENCH_EXCHANGE", "gathered" if world <= 2 else "routed")
+    routed = exchange == "routed"
+    seg = max(1 << 14, (48 * n) // max(world * world, 1)) if routed else max(1 << 16, (32 * n) // max(world, 1))
     xb = None
-    if world > 1 and streaming:
+    if world > 1 and streaming and routed:
+        rpp = aln.rows_per_part(world)
+        xb = {"rec": torch.empty((world, seg, 2), dtype=torch.int64, device=dev), "counts": torch.zeros(world, dtype=torch.int64, device=dev),
+              "recv": torch.empty((world, seg, 2), dtype=torch.int64, device=dev), "recv_counts": torch.zeros(world, dtype=torch.int64, device=dev),
+              "state": torch.empty(n, dtype=torch.int64, device=dev),
+              "slice": torch.empty(rpp * RS, dtype=torch.uint8, device=dev), "rows": torch.empty(world * rpp * RS, dtype=torch.uint8, device=dev)}
+    elif world > 1 and streaming:
         xb = {"rec": torch.empty((seg, 2), dtype=torch.int64, device=dev), "count": torch.zeros(1, dtype=torch.int64, device=dev),
               "counts": torch.zeros(world, dtype=torch.int64, device=dev), "state": torch.empty(n, dtype=torch.int64, device=dev),
               "allrec": torch.empty((world, seg, 2), dtype=torch.int64, device=dev)}
 
-    def best_match_step(a, out_ptr=None):
-        """Per-query Best Match summaries for ALL rows, left on the device (or copied to out_ptr)."""
+    def best_match_step(a, out=None):
+        """Per-query Best Match summaries for ALL rows, left on the device (or copied to the pinned host tensor `out`)."""
+        out_ptr = out.data_ptr() if out is not None else None
         if world == 1:
             if out_ptr is None:
                 a.best_match_compute()
@@ -295,14 +309,28 @@ def main():
             mt = torch.as_tensor(_DevBuf(mins, 3 * n, "<i8"), device=dev)
             dist.all_reduce(mt, op=dist.ReduceOp.MIN)  # thresholds from ALL list neighbours on every rank
             stream.synchronize()
-        # the part writes packed records / count / per-row state straight into these buffers; NCCL takes them as they are
-        a.best_match_part_packed(rank, world, True, xb["rec"].data_ptr(), seg, xb["count"].data_ptr(), xb["state"].data_ptr())
+        if not routed:
+            # the part writes packed records / count / per-row state straight into these buffers; NCCL takes them as they are
+            a.best_match_part_packed(rank, world, True, xb["rec"].data_ptr(), seg, xb["count"].data_ptr(), xb["state"].data_ptr())
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(xb["counts"], xb["count"])
+                dist.all_gather_into_tensor(xb["allrec"].view(-1), xb["rec"].view(-1))
+                dist.all_reduce(xb["state"], op=dist.ReduceOp.SUM)
+                stream.synchronize()
+            a.best_match_merge_gathered(xb["allrec"].data_ptr(), world, seg, xb["counts"].data_ptr(), xb["state"].data_ptr(), out_ptr)
+            return
+        a.best_match_part_routed(rank, world, True, xb["rec"].data_ptr(), seg, xb["counts"].data_ptr(), xb["state"].data_ptr())
         with torch.cuda.stream(stream):
-            dist.all_gather_into_tensor(xb["counts"], xb["count"])
-            dist.all_gather_into_tensor(xb["allrec"].view(-1), xb["rec"].view(-1))
+            dist.all_to_all_single(xb["recv_counts"], xb["counts"])
+            dist.all_to_all_single(xb["recv"].view(-1), xb["rec"].view(-1))
             dist.all_reduce(xb["state"], op=dist.ReduceOp.SUM)
             stream.synchronize()
-        a.best_match_merge_gathered(xb["allrec"].data_ptr(), world, seg, xb["counts"].data_ptr(), xb["state"].data_ptr(), out_ptr)
+        a.best_match_merge_routed(rank, world, xb["recv"].data_ptr(), seg, xb["recv_counts"].data_ptr(), xb["state"].data_ptr(), xb["slice"].data_ptr())
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(xb["rows"], xb["slice"])  # every rank holds all n row records (120 B each)
+            if out is not None:
+                out.view(torch.uint8).view(-1)[: n * RS].copy_(xb["rows"][: n * RS], non_blocking=True)
+            stream.synchronize()
 
     def step_device():
         aln.set_config(mode, 300, True)  # invalidates every cached result: each step recomputes everything
@@ -350,7 +378,7 @@ def main():
             tile_ms.append(ctx.last_tile_pass_ms())  # the count-tile pass of THIS step (CUDA events on the library's stream)
     barrier()
     if xb is not None:
-        cand_counts.append(int(xb["count"].item()))
+        cand_counts.append(int(xb["counts"].sum().item()) if routed else int(xb["count"].item()))
     t_region = time.perf_counter() - t_region0
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -458,7 +486,7 @@ def main():
             io.intra, io.intra_cap = h_intra.data_ptr(), n_intra
             t.check(L_.tdna_analyze(a2.h, ctypes.byref(io)))
         else:
-            best_match_step(a2, out_host.data_ptr())
+            best_match_step(a2, out_host)
             if "intra" in kind:
                 t.check(L_.tdna_class_distances(a2.h, t.PD_INTRA, h_intra.data_ptr(), n_intra, ctypes.byref(c64)))
         a2.close()
@@ -488,7 +516,11 @@ def main():
 
     if rank == 0:
         if streaming:
-            par = ("one of %d contiguous slices of the triangle's tile list per rank; NCCL: all_reduce(min) of the seeded minima, all_gather of the candidate records, all_reduce(sum) of the per-row state; merge on every rank" % world) if world > 1 else "single GPU, whole triangle"
+            par = "single GPU, whole triangle"
+            if world > 1 and routed:
+                par = "every %d-th unit of 128 tile slots of the triangle per rank; NCCL: all_reduce(min) of the seeded minima, all_to_all of the candidate records (to the rank that owns the row), all_reduce(sum) of the per-row state, all_gather of the row records each rank finalised" % world
+            elif world > 1:
+                par = "every %d-th unit of 128 tile slots of the triangle per rank; NCCL: all_reduce(min) of the seeded minima, all_gather of the candidate records, all_reduce(sum) of the per-row state; merge on every rank" % world
         else:
             par = "row bands, %d rank(s), rows [%d,%d) on rank 0" % (world, b0, b1)
         line = {
@@ -504,6 +536,11 @@ def main():
         if cand_counts:
             line["config"]["candidates_per_rank_per_step"] = int(np.mean(cand_counts))
         print(json.dumps(line), file=_OUT, flush=True)
+    # torch releases pinned blocks that were used on the library's stream by recording an event on that stream: let them go
+    # while the stream still exists
+    out_host = h_intra = h_inter = xb = None  # noqa: F841
+    gc.collect()
+    torch.cuda.synchronize()
     aln.close()
     ctx.close()
     if world > 1:

@@ -203,6 +203,19 @@ int32_t tdna_best_match_part_packed(tdna_aln *aln, int32_t part, int32_t nparts,
 int32_t tdna_best_match_merge_gathered(tdna_aln *aln, const int64_t *rec, int32_t nseg, int64_t seg_stride, const int64_t *seg_count,
                                        const int64_t *state, tdna_row_result *out);
 
+/* Routed variant of the same exchange (row-sharded merge, what bench.py runs at N > 1): the records are bucketed by the part that
+ * OWNS their row, owner(row) = row / tdna_rows_per_part(n, nparts).  `rec` holds nparts segments of seg_stride records (16 B each),
+ * segment g at rec + 2 * g * seg_stride with counts[g] records; TDNA_E_TOO_LARGE if a segment is too small.  The caller exchanges
+ * the segments and counts with an all-to-all (equal splits) and SUM-reduces `state` ... */
+int64_t tdna_rows_per_part(int64_t n, int32_t nparts);
+int32_t tdna_best_match_part_routed(tdna_aln *aln, int32_t part, int32_t nparts, int32_t seeded, int64_t *rec, int64_t seg_stride, int64_t *counts,
+                                    int64_t *state);
+/* ... then every part finalises ONLY the rows it owns from the segments it received (same layout: segment g = the records part g
+ * sent) and writes tdna_rows_per_part() records (zero padded past the end of the list) to out_slice (host or device); an all-gather
+ * of the slices is the whole result, bit-identical to one GPU's. */
+int32_t tdna_best_match_merge_routed(tdna_aln *aln, int32_t part, int32_t nparts, const int64_t *rec, int64_t seg_stride, const int64_t *seg_count,
+                                     const int64_t *state, tdna_row_result *out_slice);
+
 /* ---- one pass, several analyses ------------------------------------------------------------------ */
 /* SpeciesIdentifier runs Pairwise Summary, the threshold percentile, Best (Close) Match and Cluster on the
  * SAME list one after the other (PairwiseSummary.java:131-151 -> BestMatch.java:107-120 "Compute from

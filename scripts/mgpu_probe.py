@@ -25,10 +25,13 @@ aln = t.Alignment(ctx, sym)
 aln.set_labels(data["species_id"], data["genus_id"], data["epithet_rank"], data["fullname_rank"])
 aln.set_config(0, 300, True)
 stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
-seg = max(1 << 16, (32 * n) // world)
-xb = {"rec": torch.empty((seg, 2), dtype=torch.int64, device=dev), "count": torch.zeros(1, dtype=torch.int64, device=dev),
-      "counts": torch.zeros(world, dtype=torch.int64, device=dev), "state": torch.empty(n, dtype=torch.int64, device=dev),
-      "allrec": torch.empty((world, seg, 2), dtype=torch.int64, device=dev)}
+seg = max(1 << 14, (48 * n) // (world * world))
+rpp = aln.rows_per_part(world)
+RS = t.ROW_RESULT_DTYPE.itemsize
+xb = {"rec": torch.empty((world, seg, 2), dtype=torch.int64, device=dev), "counts": torch.zeros(world, dtype=torch.int64, device=dev),
+      "recv": torch.empty((world, seg, 2), dtype=torch.int64, device=dev), "recv_counts": torch.zeros(world, dtype=torch.int64, device=dev),
+      "state": torch.empty(n, dtype=torch.int64, device=dev),
+      "slice": torch.empty(rpp * RS, dtype=torch.uint8, device=dev), "rows": torch.empty(world * rpp * RS, dtype=torch.uint8, device=dev)}
 
 
 class Dev:
@@ -50,16 +53,19 @@ for rep in range(6):
         mt = torch.as_tensor(Dev(mins, 3 * n, "<i8"), device=dev)
         dist.all_reduce(mt, op=dist.ReduceOp.MIN)
     ts.append(sync())
-    aln.best_match_part_packed(rank, world, True, xb["rec"].data_ptr(), seg, xb["count"].data_ptr(), xb["state"].data_ptr()); ts.append(sync())
+    aln.best_match_part_routed(rank, world, True, xb["rec"].data_ptr(), seg, xb["counts"].data_ptr(), xb["state"].data_ptr()); ts.append(sync())
     tile_ms = ctx.last_tile_pass_ms()
     with torch.cuda.stream(stream):
-        dist.all_gather_into_tensor(xb["counts"], xb["count"])
-        dist.all_gather_into_tensor(xb["allrec"].view(-1), xb["rec"].view(-1))
+        dist.all_to_all_single(xb["recv_counts"], xb["counts"])
+        dist.all_to_all_single(xb["recv"].view(-1), xb["rec"].view(-1))
         dist.all_reduce(xb["state"], op=dist.ReduceOp.SUM)
     ts.append(sync())
-    aln.best_match_merge_gathered(xb["allrec"].data_ptr(), world, seg, xb["counts"].data_ptr(), xb["state"].data_ptr(), None); ts.append(sync())
+    aln.best_match_merge_routed(rank, world, xb["recv"].data_ptr(), seg, xb["recv_counts"].data_ptr(), xb["state"].data_ptr(), xb["slice"].data_ptr()); ts.append(sync())
+    with torch.cuda.stream(stream):
+        dist.all_gather_into_tensor(xb["rows"], xb["slice"])
+    ts.append(sync())
     if rank == 0:
-        names = ["seed", "allreduce_min", "part_packed", "exchange", "merge"]
+        names = ["seed", "allreduce_min", "part_routed", "all_to_all", "merge_own_rows", "all_gather_rows"]
         print("rep", rep, "n", n, " ".join("%s=%.3f" % (nm, (b - a) * 1e3) for nm, a, b in zip(names, ts, ts[1:])),
-              "total=%.3f ms (tile pass %.3f), records/rank %d, seg %d" % ((ts[-1] - ts[0]) * 1e3, tile_ms, int(xb["count"].item()), seg), flush=True)
+              "total=%.3f ms (tile pass %.3f), records/rank %d, seg %d" % ((ts[-1] - ts[0]) * 1e3, tile_ms, int(xb["counts"].sum().item()), seg), flush=True)
 dist.destroy_process_group()

@@ -66,7 +66,7 @@ EXPORTS = [
     "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_pairs", "tdna_row_distances", "tdna_query_distances", "tdna_matrix", "tdna_matrix_compute",
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
-    "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_set_option", "tdna_last_tile_pass_ms",
+    "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_rows_per_part", "tdna_best_match_part_routed", "tdna_best_match_merge_routed", "tdna_set_option", "tdna_last_tile_pass_ms",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -100,6 +100,10 @@ def load():
     L.tdna_set_row_range.argtypes = [vp, i64, i64]
     L.tdna_pair.argtypes = [vp, i64, i64, ctypes.POINTER(Counts), ctypes.POINTER(dbl)]
     L.tdna_pairs.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.tdna_rows_per_part.argtypes = [i64, i32]
+    L.tdna_rows_per_part.restype = i64
+    L.tdna_best_match_part_routed.argtypes = [vp, i32, i32, i32, vp, i64, vp, vp]
+    L.tdna_best_match_merge_routed.argtypes = [vp, i32, i32, vp, i64, vp, vp, vp]
     L.tdna_row_distances.argtypes = [vp, i64, vp, vp]
     L.tdna_query_distances.argtypes = [vp, vp, i32, vp, vp, vp]
     L.tdna_matrix.argtypes = [vp, vp, vp]
@@ -327,6 +331,15 @@ class Alignment:
     def best_match_part_packed(self, part, nparts, seeded, rec_ptr, seg_stride, count_ptr, state_ptr):
         """The part's outputs packed into caller-provided DEVICE buffers (addresses), ready for NCCL."""
         check(self.L.tdna_best_match_part_packed(self.h, int(part), int(nparts), 1 if seeded else 0, rec_ptr, int(seg_stride), count_ptr, state_ptr))
+
+    def rows_per_part(self, nparts):
+        return int(self.L.tdna_rows_per_part(self.n, int(nparts)))
+
+    def best_match_part_routed(self, part, nparts, seeded, rec_ptr, seg_stride, counts_ptr, state_ptr):
+        check(self.L.tdna_best_match_part_routed(self.h, int(part), int(nparts), 1 if seeded else 0, rec_ptr, int(seg_stride), counts_ptr, state_ptr))
+
+    def best_match_merge_routed(self, part, nparts, rec_ptr, seg_stride, seg_count_ptr, state_ptr, out_slice_ptr=None):
+        check(self.L.tdna_best_match_merge_routed(self.h, int(part), int(nparts), rec_ptr, int(seg_stride), seg_count_ptr, state_ptr, out_slice_ptr))
 
     def best_match_merge_gathered(self, rec_ptr, nseg, seg_stride, seg_count_ptr, state_ptr, out_ptr=None):
         check(self.L.tdna_best_match_merge_gathered(self.h, rec_ptr, int(nseg), int(seg_stride), seg_count_ptr, state_ptr, out_ptr))

@@ -1289,7 +1289,7 @@ static int stream_merge(tdna_aln *a, const int32_t *cq, const int32_t *cj, const
         c->launches++;
     }
     stream_finalize_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, inval, flags, a->d_species, a->n,
-                                                                                    a->d_res);
+                                                                                    a->d_res, 0, a->n);
     c->launches++;
     CU(cudaGetLastError());
     return fill_shared(a, 0, a->n);
@@ -1375,11 +1375,95 @@ int32_t tdna_best_match_merge_gathered(tdna_aln *a, const int64_t *rec, int32_t 
     TRY(row_pointers(a, a->sp.cnt));
     scatter_seg_kernel<<<gr, 256, 0, c->stream>>>(lrec, nseg, seg_stride, lcnt, a->d_ptr, a->d_cursor, a->d_lj, a->d_ld);
     stream_finalize_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, a->sp.inval, a->sp.flags, a->d_species, a->n,
-                                                                                    a->d_res);
+                                                                                    a->d_res, 0, a->n);
     c->launches += 4;
     CU(cudaGetLastError());
     TRY(fill_shared(a, 0, a->n));
     if (out) CU(cudaMemcpyAsync(out, a->d_res, n * sizeof(tdna_row_result), cudaMemcpyDefault, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TDNA_OK;
+}
+
+// ---- routed exchange: records travel to the part that owns their row; every part finalises its own rows only ----------------
+int64_t tdna_rows_per_part(int64_t n, int32_t nparts) {
+    if (n < 1 || nparts < 1) return 0;
+    return round_up((n + nparts - 1) / nparts, 128);
+}
+
+int32_t tdna_best_match_part_routed(tdna_aln *a, int32_t part, int32_t nparts, int32_t seeded, int64_t *rec, int64_t seg_stride, int64_t *counts,
+                                    int64_t *state) {
+    if (!a || !rec || !counts || !state || seg_stride < 1 || nparts < 1 || nparts > ROUTE_MAX_PARTS || part < 0 || part >= nparts)
+        return fail(TDNA_E_ARG, "bad argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(need_labels(a));
+    if (seeded && !a->stream_alloc) return fail(TDNA_E_STATE, "tdna_best_match_seed has not run");
+    long long ncand = 0;
+    if (seeded) TRY(stream_bulk(a, part, nparts, &ncand));
+    else TRY(stream_part(a, part, nparts, &ncand));
+    int *d_over = reinterpret_cast<int *>(c->d_counter) + 4;
+    CU(cudaMemsetAsync(d_over, 0, 4, c->stream));
+    CU(cudaMemsetAsync(counts, 0, (size_t)nparts * 8, c->stream));
+    unsigned gr = (unsigned)((ncand + 255) / 256);
+    if (gr < 1) gr = 1;
+    if (gr > (unsigned)c->sm_count * 16) gr = (unsigned)c->sm_count * 16;
+    route_records_kernel<<<gr, 256, 0, c->stream>>>(a->sp.cq, a->sp.cj, a->sp.cd, ncand, tdna_rows_per_part(a->n, nparts), nparts, seg_stride,
+                                                    reinterpret_cast<long long *>(rec), reinterpret_cast<unsigned long long *>(counts), d_over);
+    pack_state_only_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp.inval, a->sp.flags, a->n, reinterpret_cast<long long *>(state));
+    c->launches += 2;
+    CU(cudaGetLastError());
+    int over = 0;
+    CU(cudaMemcpyAsync(&over, d_over, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // the caller hands the buffers to NCCL on another stream
+    if (over) return fail(TDNA_E_TOO_LARGE, "a destination's candidates do not fit its exchange segment");
+    return TDNA_OK;
+}
+
+int32_t tdna_best_match_merge_routed(tdna_aln *a, int32_t part, int32_t nparts, const int64_t *rec, int64_t seg_stride, const int64_t *seg_count,
+                                     const int64_t *state, tdna_row_result *out_slice) {
+    if (!a || !rec || !seg_count || !state || seg_stride < 1 || nparts < 1 || nparts > ROUTE_MAX_PARTS || part < 0 || part >= nparts)
+        return fail(TDNA_E_ARG, "bad argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(need_labels(a));
+    TRY(ensure_packed(a));
+    TRY(ensure_stream_state(a));
+    if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+    const size_t n = (size_t)a->n;
+    const int64_t rpp = tdna_rows_per_part(a->n, nparts);
+    const int64_t q0 = std::min<int64_t>(a->n, (int64_t)part * rpp), q1 = std::min<int64_t>(a->n, q0 + rpp);
+    const long long total = (long long)nparts * seg_stride;  // upper bound of the records received
+    if (total > a->list_cap) {
+        if (a->d_lj) CU(DFREE(a->d_lj));
+        if (a->d_ld) CU(DFREE(a->d_ld));
+        a->d_lj = nullptr;
+        a->d_ld = nullptr;
+        CU(DMALLOC(&a->d_lj, (size_t)total * 4));
+        CU(DMALLOC(&a->d_ld, (size_t)total * 8));
+        a->list_cap = total;
+    }
+    unsigned gr = (unsigned)((total + 255) / 256);
+    if (gr > 65535u * 4) gr = 65535u * 4;
+    const long long *lrec = reinterpret_cast<const long long *>(rec), *lcnt = reinterpret_cast<const long long *>(seg_count);
+    unpack_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const long long *>(state), a->n, a->sp.inval, a->sp.flags);
+    CU(cudaMemsetAsync(a->sp.cnt, 0, n * 4, c->stream));
+    CU(cudaMemsetAsync(a->d_cursor, 0, n * 4, c->stream));
+    count_rows_seg_kernel<<<gr, 256, 0, c->stream>>>(lrec, nparts, seg_stride, lcnt, a->sp.cnt);  // every record received is one of this part's rows
+    TRY(row_pointers(a, a->sp.cnt));
+    scatter_seg_kernel<<<gr, 256, 0, c->stream>>>(lrec, nparts, seg_stride, lcnt, a->d_ptr, a->d_cursor, a->d_lj, a->d_ld);
+    if (q1 > q0)
+        stream_finalize_kernel<<<(unsigned)(((q1 - q0) * 32 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, a->sp.inval, a->sp.flags, a->d_species,
+                                                                                                a->n, a->d_res, q0, q1);
+    c->launches += 4;
+    CU(cudaGetLastError());
+    TRY(fill_shared(a, q0, q1));
+    if (out_slice) {  // rows_per_part records: this part's rows, zero padded past the last row of the list
+        if (q1 > q0) CU(cudaMemcpyAsync(out_slice, a->d_res + q0, (size_t)(q1 - q0) * sizeof(tdna_row_result), cudaMemcpyDefault, c->stream));
+        if (q1 - q0 < rpp) {
+            if (is_device_ptr(out_slice)) CU(cudaMemsetAsync(out_slice + (q1 - q0), 0, (size_t)(rpp - (q1 - q0)) * sizeof(tdna_row_result), c->stream));
+            else { CU(cudaStreamSynchronize(c->stream)); memset(out_slice + (q1 - q0), 0, (size_t)(rpp - (q1 - q0)) * sizeof(tdna_row_result)); }
+        }
+    }
     CU(cudaStreamSynchronize(c->stream));
     return TDNA_OK;
 }

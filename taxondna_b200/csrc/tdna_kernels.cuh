@@ -1224,6 +1224,46 @@ __global__ void __launch_bounds__(256) unpack_state_kernel(const long long *__re
     inval[q] = (int)(s & 0xffffffffll);
     flags[q] = (((s >> 32) & 0xffff) ? TDNA_ROW_SELF_VALID : 0) | (((s >> 48) & 0xffff) ? TDNA_ROW_NONFINITE : 0);
 }
+// routed exchange: the records bucketed by the part that OWNS their row (row / rows_per_part); segment g at rec + 2 * g * seg_stride.
+// Positions come from shared-memory counters per block and ONE global atomic per (block, destination).
+constexpr int ROUTE_MAX_PARTS = 64;
+__global__ void __launch_bounds__(256) route_records_kernel(const int32_t *__restrict__ cq, const int32_t *__restrict__ cj, const double *__restrict__ cd,
+                                                            long long ncand, int64_t rows_per_part, int nparts, long long seg_stride,
+                                                            long long *__restrict__ rec, unsigned long long *__restrict__ counts, int *__restrict__ overflow) {
+    __shared__ int s_cnt[ROUTE_MAX_PARTS];
+    __shared__ long long s_base[ROUTE_MAX_PARTS];
+    const long long chunks = (ncand + 255) / 256;
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        if (threadIdx.x < nparts) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const long long r = ch * 256 + threadIdx.x;
+        int dest = -1, local = 0, q = 0;
+        if (r < ncand) {
+            q = cq[r];
+            dest = (int)(q / rows_per_part);
+            local = atomicAdd(&s_cnt[dest], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < nparts && s_cnt[threadIdx.x] > 0)
+            s_base[threadIdx.x] = (long long)atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+        __syncthreads();
+        if (dest >= 0) {
+            const long long pos = s_base[dest] + local;
+            if (pos < seg_stride) {
+                long long *o = rec + 2 * ((long long)dest * seg_stride + pos);
+                o[0] = ((long long)q << 32) | (long long)(uint32_t)cj[r];
+                o[1] = __double_as_longlong(cd[r]);
+            } else *overflow = 1;
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) pack_state_only_kernel(const int *__restrict__ inval, const int *__restrict__ flags, int64_t n, long long *__restrict__ state) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int f = flags[q];
+    state[q] = (long long)(uint32_t)inval[q] | ((long long)(f & TDNA_ROW_SELF_VALID ? 1 : 0) << 32) | ((long long)(f & TDNA_ROW_NONFINITE ? 1 : 0) << 48);
+}
 // gathered segments: segment g holds seg_count[g] records at rec + 2 * g * seg_stride
 __global__ void __launch_bounds__(256) count_rows_seg_kernel(const long long *__restrict__ rec, int nseg, long long seg_stride,
                                                              const long long *__restrict__ seg_count, int *__restrict__ cnt) {
@@ -1251,10 +1291,10 @@ __global__ void __launch_bounds__(256) scatter_seg_kernel(const long long *__res
 __global__ void __launch_bounds__(256) stream_finalize_kernel(const long long *__restrict__ ptr, const int32_t *__restrict__ lj,
                                                               const double *__restrict__ ld, const int *__restrict__ inval,
                                                               const int *__restrict__ flags, const int32_t *__restrict__ species,
-                                                              int64_t n, tdna_row_result *__restrict__ out) {
+                                                              int64_t n, tdna_row_result *__restrict__ out, int64_t q_begin, int64_t q_end) {
     const int lane = threadIdx.x & 31;
-    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (q >= n) return;
+    const int64_t q = q_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);  // rows [q_begin, q_end): a part's own rows, or all
+    if (q >= q_end) return;
     const int spq = species[q];
     const bool qnamed = spq >= 0;
     const long long b = ptr[q], e = ptr[q + 1];

@@ -342,3 +342,60 @@ def test_auto_falls_back_from_kernel_b_to_kernel_a_on_a_shuffled_list(ctx):
     finally:
         ctx.set_memory_budget(64 << 30)
         ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_routed_parts_exchange_on_one_device(ctx, world):
+    """The row-sharded multi-GPU data flow (tdna_best_match_part_routed -> all-to-all -> tdna_best_match_merge_routed -> all-gather
+    of the row slices), the ranks played by one device: every part finalises only the rows it owns; the slices side by side
+    are the one-GPU result byte for byte."""
+    import torch
+    import taxondna_b200 as t
+    rng = np.random.default_rng(321 + world)
+    sym, lens, sp, gen, epi, full = make(rng, 40, 9, 500, unnamed=4, dup=8, gap=0.05, ragged=True, shuffle=False, singletons=4)
+    n = sym.shape[0]
+    aln = t.Alignment(ctx, sym, lens)
+    aln.set_labels(sp, gen, epi, full)
+    rpp = aln.rows_per_part(world)
+    assert rpp % 128 == 0 and rpp * world >= n and rpp == t.load().tdna_rows_per_part(n, world)
+
+    class Dev:
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+    for mode, kern in ((0, t.KERNEL_POPC), (1, t.KERNEL_AUTO), (0, t.KERNEL_AUTO)):
+        aln.set_config(mode, 260, True)
+        ctx.set_option(t.OPT_COUNT_KERNEL, kern)
+        ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_STREAM)
+        whole = aln.best_match()
+        seg = 32 * n
+        allmin = None
+        for part in range(world):
+            m = torch.as_tensor(Dev(aln.best_match_seed(part, world), (3 * n,), "<i8"), device="cuda").clone()
+            allmin = m if allmin is None else torch.minimum(allmin, m)
+        sent = torch.zeros((world, world, seg, 2), dtype=torch.int64, device="cuda")     # [source][destination]
+        sent_counts = torch.zeros((world, world), dtype=torch.int64, device="cuda")
+        state = torch.zeros(n, dtype=torch.int64, device="cuda")
+        for part in range(world):
+            mp = aln.best_match_seed(part, world)
+            torch.as_tensor(Dev(mp, (3 * n,), "<i8"), device="cuda").copy_(allmin)
+            st = torch.zeros(n, dtype=torch.int64, device="cuda")
+            torch.cuda.synchronize()
+            aln.best_match_part_routed(part, world, True, sent[part].data_ptr(), seg, sent_counts[part].data_ptr(), st.data_ptr())
+            state += st
+        recv = sent.transpose(0, 1).contiguous()            # the all-to-all: [destination][source]
+        recv_counts = sent_counts.t().contiguous()
+        torch.cuda.synchronize()
+        out = np.zeros(world * rpp, dtype=t.ROW_RESULT_DTYPE)
+        for part in range(world):
+            sl = out[part * rpp:(part + 1) * rpp]
+            aln.best_match_merge_routed(part, world, recv[part].data_ptr(), seg, recv_counts[part].data_ptr(), state.data_ptr(), sl.ctypes.data)
+        assert first_difference(out[:n], whole) is None, (mode, kern, first_difference(out[:n], whole))
+        assert not out[n:].tobytes().strip(b"\0")  # the padding past the end of the list is zero
+        with pytest.raises(t.TdnaError) as ei:  # a segment that is too small is reported, not overrun
+            aln.best_match_part_routed(0, world, False, sent.data_ptr(), 8, sent_counts.data_ptr(), state.data_ptr())
+        assert ei.value.code == 5
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+    aln.close()
+
