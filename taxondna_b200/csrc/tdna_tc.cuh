@@ -259,15 +259,6 @@ __device__ __forceinline__ void tma_load_2d_hint(void *dst_smem, const CUtensorM
 }
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) { mbar_wait_backoff(bar, parity); }
 
-// exact counts of one pair from the bit-planes: K2P (the accumulator only carries n and ts + tv) and alignments with ambiguity
-// letters (the accumulator only bounds the counts).  The caller may not know whether the pair has enough overlap: checked here.
-template <int KM> __device__ __noinline__ void class_emit_planes(const uint32_t *planes, int W32, int i, int j, int min_overlap) {
-    const Counts c = pair_counts_global<KM>(planes, i, j, W32);
-    if (c.shared < min_overlap) return;
-    if constexpr (KM == KM_K2P) class_emit<KM_K2P>(i, j, (uint32_t)c.c1 | ((uint32_t)c.shared << 16), (uint32_t)c.c2 | ((uint32_t)c.c3 << 16), min_overlap);
-    else class_emit<KM>(i, j, (uint32_t)c.c1 | ((uint32_t)c.shared << 16), 0u, min_overlap);
-}
-
 // ---- the tile kernel ---------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d_mc(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint16_t cta_mask) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
@@ -625,6 +616,24 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         for (int e = 0; e < 32; e++)
                             if (bmask & (1u << e)) atomicAdd(sp.inval + jb + e, 1);
                     }
+                    // class pairs whose exact counts must come from the bit-planes (K2P; tiles with ambiguity letters) are not computed
+                    // here -- a 200-load chain per pair, one lane at a time, stalled the whole tile -- but queued with bit 31 of the
+                    // row index set; resolve_emit_kernel emits them, one thread per entry
+                    uint32_t cmask = 0;
+                    const bool classes_deferred = classes && (p.k2p || tile_amb);
+                    if (classes_deferred && i < p.n) {
+                        const int spi_ = sp.species[i], gi_ = sp.genus[i];
+#pragma unroll
+                        for (int e = 0; e < 32; e++) {
+                            const int j = jb + e;
+                            if (j <= i || j >= p.n) continue;
+                            const bool hit = ((sp.want & TDNA_WANT_INTRA) && spi_ == sp.species[j]) || ((sp.want & TDNA_WANT_INTER) && gi_ == sp.genus[j]);
+                            if (!hit) continue;
+                            const uint32_t mism = v[e] >> p.wshift, s = v[e] - mism * wm1;
+                            if ((int)(s + (tile_amb ? amb_i + (uint32_t)__ldg(p.amb + j) : 0u)) >= p.min_overlap) cmask |= 1u << e;
+                        }
+                    }
+                    pmask |= cmask;
                     if (!seed) {
                         // bulk pass: no fp64, no threshold traffic here -- the pairs that pass the seeded thresholds are queued
                         // (one warp-aggregated atomic) and resolved after the pass (resolve_*_kernel)
@@ -644,26 +653,21 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                             if ((long long)(base + total) <= sp.qcap) {
 #pragma unroll
                                 for (int e = 0; e < 32; e++)
-                                    if (pmask & (1u << e)) { sp.qi[w] = i; sp.qj[w] = jb + e; sp.qv[w] = v[e]; w++; }
+                                    if (pmask & (1u << e)) { sp.qi[w] = i | (int)((cmask >> e) << 31); sp.qj[w] = jb + e; sp.qv[w] = v[e]; w++; }
                             } else if (lane == 0) *sp.overflow = 1;
                         }
                         pmask = 0;
                     }
 
-                    if (classes) {
+                    if (classes && !classes_deferred) {  // exact accumulators: one fp64 division per class pair, right here
 #pragma unroll
                         for (int e = 0; e < 32; e++) {
                             const int j = jb + e;
                             const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1, s = ident + mism;
-                            if (j <= i || j >= p.n) continue;
-                            if ((int)(s + (tile_amb ? amb_i + (uint32_t)__ldg(p.amb + j) : 0u)) < p.min_overlap) continue;
+                            if (j <= i || j >= p.n || (int)s < p.min_overlap) continue;
                             const bool hit = ((sp.want & TDNA_WANT_INTRA) && sp.species[i] == sp.species[j]) ||
                                              ((sp.want & TDNA_WANT_INTER) && sp.genus[i] == sp.genus[j]);
-                            if (hit) {
-                                if (p.k2p) class_emit_planes<KM_K2P>(p.planes, p.W32, i, j, p.min_overlap);
-                                else if (tile_amb) class_emit_planes<KM_P_AMBIG>(p.planes, p.W32, i, j, p.min_overlap);
-                                else class_emit<KM_P_AMBIG>(i, j, ident | (s << 16), 0u, p.min_overlap);
-                            }
+                            if (hit) class_emit<KM_P_AMBIG>(i, j, ident | (s << 16), 0u, p.min_overlap);
                         }
                     }
                 }
@@ -716,11 +720,29 @@ __device__ __forceinline__ double queued_distance(const ResolveArgs &ra, int i, 
     Counts cn = {(int)s, (int)ident, 0, 0};
     return distance_from_counts<KM_P_AMBIG>(cn, ra.min_overlap);
 }
+// a queued class pair (bit 31 of the row index): PairwiseDistribution's pushes for it, with the exact distance d >= 0 (or NaN / +Inf)
+__device__ __forceinline__ void class_emit_value(const StreamParams &sp, int i, int j, double d) {
+    int times[2] = {0, 0};
+    if (sp.want & TDNA_WANT_INTRA) {
+        const int si = sp.species[i];
+        if (si >= 0 && si == sp.species[j]) times[0] = 1 + (sp.full[i] == sp.full[j] ? 1 : 0);
+    }
+    if (sp.want & TDNA_WANT_INTER) {
+        if (sp.genus[i] == sp.genus[j] && sp.epi[i] != sp.epi[j]) times[1] = 1;
+    }
+    const float f = (float)d;
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+        for (int t = 0; t < times[k]; t++) {
+            const unsigned long long pos = atomicAdd(sp.ncls + k, 1ull);
+            if (sp.cls[k] && (long long)pos < sp.cls_cap[k]) sp.cls[k][pos] = f;
+        }
+}
 __global__ void __launch_bounds__(256) resolve_min_kernel(StreamParams sp, ResolveArgs ra) {
     if (*sp.overflow) return;  // the queue has holes when a push did not fit: the caller falls back to the dense path
     const long long nq = min((long long)*sp.qn, sp.qcap);
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
-        const int i = sp.qi[r], j = sp.qj[r];
+        const int i = sp.qi[r] & 0x7fffffff, j = sp.qj[r];
         uint32_t lhs, den;
         const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den);
         if (!(d < __longlong_as_double((long long)TDNA_INF_BITS)) || d < 0.0) continue;
@@ -735,9 +757,10 @@ __global__ void __launch_bounds__(256) resolve_emit_kernel(StreamParams sp, Reso
     const long long nq = min((long long)*sp.qn, sp.qcap);
     const bool want_bm = (sp.want & TDNA_WANT_BEST_MATCH) != 0;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
-        const int i = sp.qi[r], j = sp.qj[r];
+        const int qi_raw = sp.qi[r], i = qi_raw & 0x7fffffff, j = sp.qj[r];
         uint32_t lhs, den;
         const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den);
+        if (qi_raw < 0 && !(d < 0.0)) class_emit_value(sp, i, j, d);  // a deferred class pair (valid: NaN / +Inf are kept, -1 is dropped)
         if (d < 0.0) {  // queued with an uncertain overlap (ambiguity letters), and the exact overlap is below minOverlap: an invalid pair
             atomicAdd(sp.inval + i, 1);
             atomicAdd(sp.inval + j, 1);
