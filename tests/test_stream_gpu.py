@@ -399,3 +399,33 @@ def test_routed_parts_exchange_on_one_device(ctx, world):
     ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
     aln.close()
 
+
+
+@pytest.mark.parametrize("n,L", [(1, 1), (1, 40), (2, 1), (2, 33), (3, 129), (129, 5)])
+def test_tiny_alignments_through_every_path(ctx, n, L):
+    """The smallest lists (one sequence, one column, one row past a tile) through the streaming pass on both count kernels, the
+    dense path, the one-pass analysis and the foreign-query entry point: same bytes everywhere, nothing out of range."""
+    import taxondna_b200 as t
+    rng = np.random.default_rng(n * 100 + L)
+    sym = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n, L))].copy()
+    sp = (np.arange(n) // 2).astype(np.int32)
+    aln = t.Alignment(ctx, sym)
+    aln.set_labels(sp, (sp // 2).astype(np.int32), sp, np.arange(n, dtype=np.int32))
+    for mode in (0, 1):
+        aln.set_config(mode, 1, True)
+        got = {}
+        for name, path, kern in (("dense", t.PATH_DENSE, t.KERNEL_AUTO), ("popc", t.PATH_STREAM, t.KERNEL_POPC), ("tensor", t.PATH_STREAM, t.KERNEL_TENSOR)):
+            ctx.set_option(t.OPT_BEST_MATCH_PATH, path)
+            ctx.set_option(t.OPT_COUNT_KERNEL, kern)
+            got[name] = aln.analyze(best_match=True, intra=True, inter=True, edges=0.5)
+        ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+        ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
+        for name in ("popc", "tensor"):
+            assert first_difference(got[name]["rows"], got["dense"]["rows"]) is None, (mode, name)
+            for k in ("intra", "inter"):
+                assert np.array_equal(np.sort(got[name][k]).view(np.uint32), np.sort(got["dense"][k]).view(np.uint32)), (mode, name, k)
+            assert sorted(zip(got[name]["edge_i"].tolist(), got[name]["edge_j"].tolist())) == sorted(zip(got["dense"]["edge_i"].tolist(), got["dense"]["edge_j"].tolist()))
+        ref = oracle.all_pairs(sym, np.full(n, L, np.int32), mode, 1, True)
+        d, sh = aln.query_distances(sym[0])
+        assert np.array_equal(d.view(np.uint64), ref["dist"][0].view(np.uint64)) and np.array_equal(sh, ref["shared"][0])
+    aln.close()
