@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtaxondna_cuda.so")
+LIB_PATH = os.environ.get("TDNA_LIB") or os.path.join(_HERE, "libtaxondna_cuda.so")  # TDNA_LIB: A/B of library builds
 
 PDM_UNCORRECTED, PDM_K2P, PDM_TRANS_ONLY = 0, 1, 2
 PD_INTRA, PD_INTER = 0, 1
@@ -100,10 +100,11 @@ def load():
     L.tdna_set_row_range.argtypes = [vp, i64, i64]
     L.tdna_pair.argtypes = [vp, i64, i64, ctypes.POINTER(Counts), ctypes.POINTER(dbl)]
     L.tdna_pairs.argtypes = [vp, vp, vp, i64, vp, vp]
-    L.tdna_rows_per_part.argtypes = [i64, i32]
-    L.tdna_rows_per_part.restype = i64
-    L.tdna_best_match_part_routed.argtypes = [vp, i32, i32, i32, vp, i64, vp, vp]
-    L.tdna_best_match_merge_routed.argtypes = [vp, i32, i32, vp, i64, vp, vp, vp]
+    if hasattr(L, "tdna_rows_per_part"):  # absent from older builds loaded through TDNA_LIB for an A/B
+        L.tdna_rows_per_part.argtypes = [i64, i32]
+        L.tdna_rows_per_part.restype = i64
+        L.tdna_best_match_part_routed.argtypes = [vp, i32, i32, i32, vp, i64, vp, vp]
+        L.tdna_best_match_merge_routed.argtypes = [vp, i32, i32, vp, i64, vp, vp, vp]
     L.tdna_row_distances.argtypes = [vp, i64, vp, vp]
     L.tdna_query_distances.argtypes = [vp, vp, i32, vp, vp, vp]
     L.tdna_matrix.argtypes = [vp, vp, vp]

@@ -366,6 +366,15 @@ template <int KM> int launch_stream_km(tdna_aln *a, int part, int nparts, int ph
     }
 }
 
+static int launch_stream_popc(tdna_aln *a, int part, int nparts, int phases) {
+    switch (a->kmode) {
+        case KM_P_AMBIG: return launch_stream_km<KM_P_AMBIG>(a, part, nparts, phases);
+        case KM_P_NOAMBIG: return launch_stream_km<KM_P_NOAMBIG>(a, part, nparts, phases);
+        case KM_K2P: return launch_stream_km<KM_K2P>(a, part, nparts, phases);
+        default: return launch_stream_km<KM_TRANS>(a, part, nparts, phases);
+    }
+}
+
 // phases: bit 0 = diagonal blocks, bit 1 = the rest of the triangle
 int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
     tdna_ctx *c = a->ctx;
@@ -373,7 +382,7 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
     bool tensor = c->opt_count_kernel == TDNA_KERNEL_TENSOR || (c->opt_count_kernel == TDNA_KERNEL_AUTO && !a->avoid_tensor && ensure_tc(a) == 1);
     a->last_kernel = tensor ? TDNA_KERNEL_TENSOR : TDNA_KERNEL_POPC;
     if (tensor) {
-        if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p (ambiguity allowed) or K2P, an alignment without IUPAC ambiguity letters, L < 4096");
+        if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p (ambiguity allowed) or K2P, and L < 4096");
         if (phases & 1) CU(cudaEventRecord(c->ev_k0, c->stream));
         for (int ph = 0; ph < 2; ph++)
             if (phases & (1 << ph)) {
@@ -401,12 +410,7 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
         }
         return TDNA_OK;
     }
-    switch (a->kmode) {
-        case KM_P_AMBIG: return launch_stream_km<KM_P_AMBIG>(a, part, nparts, phases);
-        case KM_P_NOAMBIG: return launch_stream_km<KM_P_NOAMBIG>(a, part, nparts, phases);
-        case KM_K2P: return launch_stream_km<KM_K2P>(a, part, nparts, phases);
-        default: return launch_stream_km<KM_TRANS>(a, part, nparts, phases);
-    }
+    return launch_stream_popc(a, part, nparts, phases);
 }
 
 // ---- count kernel (b): operands, launches ----------------------------------------------------------
@@ -463,10 +467,16 @@ int ensure_tc(tdna_aln *a) {
         a->tc_state = 0;
     }
     if (a->tc_state != 0) return a->tc_state;
-    const int dims = a->kmode == KM_K2P ? 4 : 5;  // K2P ignores gap sites: four symbols
-    tc::EncodeValues v;
+    // K2P ignores gap sites: four symbol dimensions -- where a four-dimension code exists (W = 1024 only, i.e. L < 1024); longer K2P
+    // alignments use the five-dimension code with the gap dimension left empty (25 % more K-bytes per site)
+    int dims = a->kmode == KM_K2P ? 4 : 5;
+    tc::EncodeValues v = {};
     uint32_t W = 0;
-    if (!find_code(a->L, dims, v, W)) { a->tc_state = -1; return -1; }
+    if (!find_code(a->L, dims, v, W)) {
+        dims = 5;
+        if (!find_code(a->L, dims, v, W)) { a->tc_state = -1; return -1; }
+    }
+    v.gap_is_symbol = a->kmode == KM_K2P ? 0 : 1;
     int nchunks = (a->L * dims + tc::KB - 1) / tc::KB;
     int64_t npa = round_up(a->n, tc::M), npb = round_up(a->n, tc::N);
     if (cudaSuccess != DMALLOC(&a->d_tcA, (size_t)npa * nchunks * tc::KB) || cudaSuccess != DMALLOC(&a->d_tcB, (size_t)npb * nchunks * tc::KB)) {
@@ -571,10 +581,16 @@ int ensure_tc(tdna_aln *a) {
 
 template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts) {
     tdna_ctx *c = a->ctx;
-    auto kern = tc::tile_kernel<COUNTS_MODE, CL>;
+    // the plain instantiation serves uncorrected p on alignments without ambiguity letters (exact accumulators everywhere)
+    const bool general = !COUNTS_MODE && (a->kmode == KM_K2P || a->tc_has_amb);
+    auto kern = tc::tile_kernel<COUNTS_MODE, CL, false>;
+    if constexpr (!COUNTS_MODE) {
+        if (general) kern = tc::tile_kernel<COUNTS_MODE, CL, true>;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
+        CU(cudaFuncSetAttribute(tc::tile_kernel<COUNTS_MODE, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
+        if constexpr (!COUNTS_MODE) CU(cudaFuncSetAttribute(tc::tile_kernel<COUNTS_MODE, CL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
         attr_set = true;
     }
     tc::Params p = {};

@@ -126,6 +126,7 @@ template <int CL> __device__ __forceinline__ bool my_tile(const Params &p, int64
 // ---- operand encoding -------------------------------------------------------------------------
 struct EncodeValues {
     int a, b, c, d;
+    int gap_is_symbol;  // uncorrected p: '-' is the fifth symbol; K2P ignores gap sites (Sequence.java:1446-1471): no contribution
 };
 // one CTA = one operand block (panel x K-chunk): the ~27 sites the chunk covers are staged as symbol codes in shared
 // memory (coalesced 27-byte runs per row), then every thread emits 16-byte units in memory order (coalesced uint4 stores)
@@ -151,12 +152,12 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
                 const uint32_t bases = cls & 15u;
                 if (cls & SB_LET) {  // an ambiguity letter contributes nothing here: amb_count_kernel counts it, the filter allows for it
                     if (__popc(bases) == 1) code = (uint32_t)__ffs((int)bases) - 1u;
-                } else if (cls & SB_D) code = DIMS == 5 ? 4u : 5u;  // K2P ignores gap sites (Sequence.java:1446-1471)
+                } else if (cls & SB_D) code = v.gap_is_symbol ? 4u : 5u;
                 else if (cls & 0x8000u) bad = true;
             }
             codes[row_l][s] = (uint8_t)code;
             // a site of the alignment of an existing row that contributes nothing: the panel is not "full"
-            if (row < n && site < L && code >= (uint32_t)DIMS) gappy = true;
+            if (row < n && site < L && code >= 5u) gappy = true;
         }
     }
     if (bad) atomicOr(not_clean, 1);
@@ -259,6 +260,16 @@ __device__ __forceinline__ void tma_load_2d_hint(void *dst_smem, const CUtensorM
 }
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) { mbar_wait_backoff(bar, parity); }
 
+// seed pass, tiles with ambiguity letters: the exact distance of one pair from the bit-planes, as ordered bits (+Inf bits: no use)
+__device__ __noinline__ unsigned long long exact_seed_bits(const Params &p, int i, int j) {
+    if (j < 0) return TDNA_INF_BITS;
+    double d;
+    if (p.k2p) d = distance_from_counts<KM_K2P>(pair_counts_global<KM_K2P>(p.planes, i, j, p.W32), p.min_overlap);
+    else d = distance_from_counts<KM_P_AMBIG>(pair_counts_global<KM_P_AMBIG>(p.planes, i, j, p.W32), p.min_overlap);
+    if (!(d < __longlong_as_double((long long)TDNA_INF_BITS)) || d < 0.0) return TDNA_INF_BITS;
+    return (unsigned long long)__double_as_longlong(d);
+}
+
 // ---- the tile kernel ---------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d_mc(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint16_t cta_mask) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
@@ -303,7 +314,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 // CL = 2: clusters of two CTAs on the same column tile; each loads one half of the b-panel stage and multicasts it to both,
 // so the pair reads 2 x 16 KB (a) + 32 KB (b) per K-chunk from L2 instead of 2 x 48 KB.
-template <bool COUNTS_MODE, int CL>
+// GENERAL = false: uncorrected p on an alignment without ambiguity letters -- every accumulator is exact and none of the K2P /
+// ambiguity-letter machinery is compiled in (it cost the hot loop 4 % through register pressure alone).
+template <bool COUNTS_MODE, int CL, bool GENERAL>
 __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                           const __grid_constant__ CUtensorMap mapBh, Params p) {
     // CL = 3: the pair runs ONE M = 256 MMA (cta_group::2): each CTA stages its own a-panel and its 128-row HALF of the
@@ -441,7 +454,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             const bool seed = !COUNTS_MODE && (sp.want & TDNA_WANT_SEED) != 0;  // diagonal-block pre-pass: thresholds only
             const bool want_bm = !COUNTS_MODE && (sp.want & TDNA_WANT_BEST_MATCH);
             const uint32_t edge_tf = (!COUNTS_MODE && p.extras && (sp.want & TDNA_WANT_EDGES)) ? sp.edge_tfix : 0u;
-            const bool k2p_force = p.k2p != 0;  // K2P: 2(ts + tv) >= n may mean w1 <= 0 or w2 <= 0 -> NaN / +Inf must reach the exact path
+            const bool k2p_force = GENERAL && p.k2p != 0;  // K2P: 2(ts + tv) >= n may mean w1 <= 0 or w2 <= 0 -> NaN / +Inf must reach the exact path
             bool classes = !COUNTS_MODE && !seed && p.extras && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER));
             if (classes) {  // class pairs only live in tiles whose row and column panels share a species or a genus id range
                 bool may = false;
@@ -461,8 +474,8 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             const bool full = !COUNTS_MODE && interior && !seed && p.L >= p.min_overlap && p.panel_full[ti] && p.panel_full[2 * tj] &&
                               p.panel_full[2 * tj + 1] && (int64_t)ti * M + M <= p.n;
             // some row or column of the tile has ambiguity letters: the accumulators bound the counts (see Params::amb)
-            const bool tile_amb = !COUNTS_MODE && p.amb != nullptr && (p.panel_amb[ti] || p.panel_amb[2 * tj] || p.panel_amb[2 * tj + 1]);
-            const uint32_t amb_i = (!COUNTS_MODE && p.amb != nullptr && i < p.n) ? (uint32_t)__ldg(p.amb + i) : 0u;
+            const bool tile_amb = GENERAL && !COUNTS_MODE && p.amb != nullptr && (p.panel_amb[ti] || p.panel_amb[2 * tj] || p.panel_amb[2 * tj + 1]);
+            const uint32_t amb_i = (GENERAL && !COUNTS_MODE && p.amb != nullptr && i < p.n) ? (uint32_t)__ldg(p.amb + i) : 0u;
             uint32_t tf_row = edge_tf;
             if constexpr (!COUNTS_MODE) {
                 __syncwarp();  // the previous tile's reads of my_thr are done
@@ -486,6 +499,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             int bad_row = 0;
             // seed pass: exact minima of this row over the columns of its diagonal block (both sides of the diagonal), by category
             unsigned long long seed_c = TDNA_INF_BITS, seed_p0 = TDNA_INF_BITS, seed_p1 = TDNA_INF_BITS;
+            int seed_jc = -1, seed_j0 = -1, seed_j1 = -1;  // the columns those minima came from
             const int spi = (seed && i < p.n) ? __ldg(sp.species + i) : -1;
 #pragma unroll
             for (int cbi = 0; cbi < EPI_COLS / 32; cbi++) {
@@ -518,9 +532,9 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1, s = ident + mism;
                         if (j == i || j >= p.n || i >= p.n || spj < 0 || (int)s < p.min_overlap) continue;
                         // ambiguity letters: an UPPER bound of the distance is all a threshold needs (0 extra sites: the exact value)
-                        const uint32_t aij = p.amb != nullptr ? amb_i + (uint32_t)__ldg(p.amb + j) : 0u;
+                        const uint32_t aij = (GENERAL && p.amb != nullptr) ? amb_i + (uint32_t)__ldg(p.amb + j) : 0u;
                         double d;
-                        if (p.k2p) {
+                        if (GENERAL && p.k2p) {
                             // only n and ts + tv are known here: d_K2P <= -ln(1 - 2(P+Q)) / 2 (all differences transitions) bounds the
                             // minima from above, which is all a threshold needs; the exact minima come from the queue afterwards
                             if (mism + aij == 0) d = 0.0;
@@ -535,8 +549,14 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         }
                         if (!(d < __longlong_as_double((long long)TDNA_INF_BITS)) || d < 0.0) continue;
                         const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
-                        if (spj == spi) seed_c = min(seed_c, bits);
-                        if (spj & 1) seed_p1 = min(seed_p1, bits); else seed_p0 = min(seed_p0, bits);
+                        if constexpr (GENERAL) {  // remember where each minimum came from (refined below in tiles with ambiguity letters)
+                            if (spj == spi && bits < seed_c) { seed_c = bits; seed_jc = j; }
+                            if (spj & 1) { if (bits < seed_p1) { seed_p1 = bits; seed_j1 = j; } }
+                            else if (bits < seed_p0) { seed_p0 = bits; seed_j0 = j; }
+                        } else {
+                            if (spj == spi) seed_c = min(seed_c, bits);
+                            if (spj & 1) seed_p1 = min(seed_p1, bits); else seed_p0 = min(seed_p0, bits);
+                        }
                     }
                 } else {
                     uint32_t pmask = 0, bmask = 0, smask = 0;  // slow path wanted / pair below minOverlap / valid self pair
@@ -620,7 +640,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     // here -- a 200-load chain per pair, one lane at a time, stalled the whole tile -- but queued with bit 31 of the
                     // row index set; resolve_emit_kernel emits them, one thread per entry
                     uint32_t cmask = 0;
-                    const bool classes_deferred = classes && (p.k2p || tile_amb);
+                    const bool classes_deferred = GENERAL && classes && (p.k2p || tile_amb);
                     if (classes_deferred && i < p.n) {
                         const int spi_ = sp.species[i], gi_ = sp.genus[i];
 #pragma unroll
@@ -674,6 +694,14 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             }
             if constexpr (!COUNTS_MODE) {
                 if (bad_row) atomicAdd(sp.inval + i, bad_row);
+                if (GENERAL && seed && i < p.n && tile_amb) {
+                    // ambiguity letters: the minima above are upper BOUNDS, loose by (amb[i] + amb[j]) / shared -- 0.1 at 4 % ambiguity letters,
+                    // and the bulk would queue every congener.  The exact distance of the pair each bound came from (three pairs per row,
+                    // from the bit-planes) is a valid and tight upper bound of the category's minimum.
+                    seed_c = exact_seed_bits(p, i, seed_jc);
+                    seed_p0 = exact_seed_bits(p, i, seed_j0);
+                    seed_p1 = exact_seed_bits(p, i, seed_j1);
+                }
                 if (seed && i < p.n) {
                     if (seed_c < TDNA_INF_BITS) atomicMin(sp.mC + i, seed_c);
                     if (seed_p0 < TDNA_INF_BITS) atomicMin(sp.mPar + 2 * (int64_t)i, seed_p0);

@@ -126,7 +126,8 @@ def test_streaming_best_match_on_the_tensor_kernel(ctx, shuffle, ragged, L, ambi
 
 
 @pytest.mark.parametrize("shuffle,ragged,L,saturated,ambig", [(False, False, 658, 0, 0), (True, True, 700, 0, 0), (False, False, 400, 25, 0),
-                                                              (False, False, 658, 0, 0.04), (True, True, 700, 10, 0.05)])
+                                                              (False, False, 658, 0, 0.04), (True, True, 700, 10, 0.05),
+                                                              (False, True, 1500, 0, 0.03), (False, False, 200, 0, 0)])  # L >= 1024: the five-dimension code
 def test_k2p_streaming_on_the_tensor_kernel(ctx, shuffle, ragged, L, saturated, ambig):
     """K2P: the accumulator carries (n, ts + tv) -- enough for the conservative filter -- and the exact (n, ts, tv) of the
     queued pairs come from the bit-planes; records, classes and edges must equal the popc kernel's."""
