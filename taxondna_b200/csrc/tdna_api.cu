@@ -502,16 +502,17 @@ int ensure_tc(tdna_aln *a) {
     tc::amb_count_kernel<<<(unsigned)((a->n + 7) / 8), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, a->kmode == KM_K2P ? 1 : 0, a->d_tcamb,
                                                                             a->d_tcpanel_amb, d_flag + 1);
     c->launches++;
-    tc::encode_kernel<false, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcA, d_flag, a->d_tcfull);
-    if (getenv("TDNA_TC_DEBUG")) fprintf(stderr, "[tc] a-side encode: %s\n", cudaGetErrorString(cudaStreamSynchronize(c->stream)));
-    if (tc_pair_mode())  // cta_group::2: the b-side in 128-row panels as well (each CTA of a pair stages half of the tile's columns)
+    if (tc_pair_mode()) {  // cta_group::2: the b-side in 128-row panels as well (each CTA of a pair stages half of the tile's columns)
+        tc::encode_kernel<false, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcA, d_flag, a->d_tcfull);
         tc::encode_kernel<true, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcB, d_flag, nullptr);
-    else
-        tc::encode_kernel<true, tc::N><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::N)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcB, d_flag, nullptr);
+        c->launches++;
+    } else {
+        tc::encode_both_kernel<<<dim3((unsigned)nchunks, (unsigned)(npb / tc::N)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcA,
+                                                                                                        a->d_tcB, npa / tc::M, d_flag, a->d_tcfull);
+    }
     a->tc_pair = tc_pair_mode();
     if (getenv("TDNA_TC_DEBUG")) fprintf(stderr, "[tc] b-side encode: %s\n", cudaGetErrorString(cudaStreamSynchronize(c->stream)));
     tc::flip_flags_kernel<<<(unsigned)((npan + 255) / 256), 256, 0, c->stream>>>(a->d_tcfull, (int64_t)npan, (int64_t)((a->n + tc::M - 1) / tc::M));  // gappy -> full
-    c->launches++;
     c->launches += 2;
     int flags2[2] = {0, 0};
     cudaMemcpyAsync(flags2, d_flag, 8, cudaMemcpyDeviceToHost, c->stream);

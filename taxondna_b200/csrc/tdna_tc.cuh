@@ -182,6 +182,68 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
     }
 }
 
+// Both operand images from ONE read of the symbols (the default, multicast-pair layout): one CTA = one K-chunk of one 256-row b-panel
+// = the same chunk of two 128-row a-panels.  The symbol -> code table sits in shared memory (a divergent constant-memory index
+// serialises), one warp stages a row's ~27 symbols, then every thread emits 16-byte units of the b-image and of the a-images.
+__global__ void __launch_bounds__(256) encode_both_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len, int64_t n, int64_t sym_stride,
+                                                          int L, int nchunks, int DIMS, EncodeValues v, uint8_t *__restrict__ outA, uint8_t *__restrict__ outB,
+                                                          int64_t a_panels, int *__restrict__ not_clean, uint8_t *__restrict__ panel_gappy) {
+    __shared__ uint8_t codes[N][ENC_SITES + 1];
+    __shared__ uint8_t s_code[256];  // 0..3 A C G T, 4 '-' (when it is a symbol), 5 no contribution, 0x85 outside the alphabet
+    {
+        const uint32_t cls = c_symlut[threadIdx.x], bases = cls & 15u;
+        uint32_t code = 5;
+        if (cls & SB_LET) { if (__popc(bases) == 1) code = (uint32_t)__ffs((int)bases) - 1u; }
+        else if (cls & SB_D) code = v.gap_is_symbol ? 4u : 5u;
+        else if (cls & 0x8000u) code = 0x85u;
+        s_code[threadIdx.x] = (uint8_t)code;
+    }
+    __syncthreads();
+    const int c = blockIdx.x;
+    const int64_t panel = blockIdx.y;  // 256-row panel
+    const int s0 = (c * KB) / DIMS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    bool bad = false;
+    uint32_t gappy = 0;  // bit h: half h (a-panel 2 * panel + h) has a row with a site that contributes nothing
+    for (int row_l = warp; row_l < N; row_l += 8) {
+        const int64_t row = panel * N + row_l;
+        const int row_len = row < n ? min(__ldg(len + row), L) : 0;
+        const uint8_t *src = sym + row * sym_stride + s0;
+#pragma unroll
+        for (int s = lane; s < ENC_SITES; s += 32) {
+            uint32_t code = 5;
+            if (s0 + s < row_len) code = s_code[__ldg(src + s)];
+            if (code & 0x80u) { bad = true; code = 5; }
+            codes[row_l][s] = (uint8_t)code;
+            if (row < n && s0 + s < L && code >= 5u) gappy |= 1u << (row_l >> 7);
+        }
+    }
+    if (bad) atomicOr(not_clean, 1);
+    if (gappy & 1u) panel_gappy[2 * panel] = 1;
+    if (gappy & 2u) panel_gappy[2 * panel + 1] = 1;
+    __syncthreads();
+    auto unit = [&](int row_l, int k16, int va, int vb) {
+        uint32_t w[4] = {0, 0, 0, 0};
+        int kk = c * KB + k16 * 16, site = kk / DIMS - s0, dim = kk % DIMS;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const int code = codes[row_l][site];
+            const int val = code < DIMS ? vb + (dim == code ? va : 0) : 0;
+            w[b >> 2] |= (uint32_t)(val & 0xff) << (8 * (b & 3));
+            if (++dim == DIMS) { dim = 0; site++; }
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    };
+    uint4 *dstB = reinterpret_cast<uint4 *>(outB + ((size_t)panel * nchunks + c) * (size_t)(N * KB));
+    for (int u = threadIdx.x; u < N * (KB / 16); u += 256) dstB[u] = unit(u % N, u / N, v.c, v.d);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        if (2 * panel + h >= a_panels) break;
+        uint4 *dstA = reinterpret_cast<uint4 *>(outA + ((size_t)(2 * panel + h) * nchunks + c) * (size_t)(M * KB));
+        for (int u = threadIdx.x; u < M * (KB / 16); u += 256) dstA[u] = unit(h * M + u % M, u / M, v.a, v.b);
+    }
+}
+
 // panel_gappy -> panel_full; panels beyond the last row are not full (their pairs are out of range anyway)
 __global__ void __launch_bounds__(256) flip_flags_kernel(uint8_t *flags, int64_t npan, int64_t real_panels) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
