@@ -562,6 +562,9 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             // seed pass: exact minima of this row over the columns of its diagonal block (both sides of the diagonal), by category
             unsigned long long seed_c = TDNA_INF_BITS, seed_p0 = TDNA_INF_BITS, seed_p1 = TDNA_INF_BITS;
             int seed_jc = -1, seed_j0 = -1, seed_j1 = -1;  // the columns those minima came from
+            // plain instantiation: 1 - ident / shared is smallest where ident / shared is largest -- fractions compare exactly by integer
+            // cross-multiplication (both below 2^12), so the fp64 division happens three times per row instead of once per pair
+            uint32_t fc_i = 0, fc_s = 0, f0_i = 0, f0_s = 0, f1_i = 0, f1_s = 0;
             const int spi = (seed && i < p.n) ? __ldg(sp.species + i) : -1;
 #pragma unroll
             for (int cbi = 0; cbi < EPI_COLS / 32; cbi++) {
@@ -593,6 +596,12 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         const int j = jb + e, spj = (int)my_thr[cbi * 32 + e];
                         const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1, s = ident + mism;
                         if (j == i || j >= p.n || i >= p.n || spj < 0 || (int)s < p.min_overlap) continue;
+                        if constexpr (!GENERAL) {
+                            if (spj == spi && (fc_s == 0 || ident * fc_s > fc_i * s)) { fc_i = ident; fc_s = s; }
+                            if (spj & 1) { if (f1_s == 0 || ident * f1_s > f1_i * s) { f1_i = ident; f1_s = s; } }
+                            else if (f0_s == 0 || ident * f0_s > f0_i * s) { f0_i = ident; f0_s = s; }
+                            continue;
+                        }
                         // ambiguity letters: an UPPER bound of the distance is all a threshold needs (0 extra sites: the exact value)
                         const uint32_t aij = (GENERAL && p.amb != nullptr) ? amb_i + (uint32_t)__ldg(p.amb + j) : 0u;
                         double d;
@@ -756,6 +765,16 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             }
             if constexpr (!COUNTS_MODE) {
                 if (bad_row) atomicAdd(sp.inval + i, bad_row);
+                if (!GENERAL && seed && i < p.n) {
+                    auto frac_bits = [&](uint32_t ident, uint32_t sh) -> unsigned long long {
+                        if (sh == 0) return TDNA_INF_BITS;
+                        Counts cn = {(int)sh, (int)ident, 0, 0};
+                        return (unsigned long long)__double_as_longlong(distance_from_counts<KM_P_AMBIG>(cn, p.min_overlap));
+                    };
+                    seed_c = frac_bits(fc_i, fc_s);
+                    seed_p0 = frac_bits(f0_i, f0_s);
+                    seed_p1 = frac_bits(f1_i, f1_s);
+                }
                 if (GENERAL && seed && i < p.n && tile_amb) {
                     // ambiguity letters: the minima above are upper BOUNDS, loose by (amb[i] + amb[j]) / shared -- 0.1 at 4 % ambiguity letters,
                     // and the bulk would queue every congener.  The exact distance of the pair each bound came from (three pairs per row,
