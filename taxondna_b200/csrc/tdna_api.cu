@@ -94,6 +94,12 @@ struct tdna_aln {
     int sprefix_cn = 0;
     long long *d_ptr = nullptr;  // CSR row pointers [n + 1]
     long long *d_scan = nullptr; // block sums of the row-pointer scan
+    std::vector<int32_t> h_species;            // host copy of the species ids (seed list of count kernel (b))
+    int2 *d_seedlist = nullptr;
+    int seed_pairs = 0;
+    bool seedlist_valid = false;
+    long long need_cand = 0, need_queue = 0;  // demand of the last pass that overflowed
+    bool stream_broken = false;               // a buffer could not be regrown: the streaming state is unusable
     int *d_cursor = nullptr;
     int32_t *d_lj = nullptr;
     double *d_ld = nullptr;
@@ -580,6 +586,63 @@ int ensure_tc(tdna_aln *a) {
     return 1;
 }
 
+// Seed pass of kernel (b): which 256-column blocks each pair of row tiles (= one 256-row block) visits.  Always its own diagonal
+// block; plus, from the labels, the block holding the nearest row of a species whose id has the parity the diagonal block lacks
+// (thresholds are max(min conspecific, min even-id species, min odd-id species): a block inside one large species would leave
+// one of them unbounded and the bulk pass would queue every pair of its rows), and the neighbouring block when a row at the
+// block's edge has its only conspecific neighbours across the edge.
+static int build_seed_list(tdna_aln *a) {
+    if (a->seedlist_valid) return TDNA_OK;
+    tdna_ctx *c = a->ctx;
+    const int64_t n = a->n;
+    const std::vector<int32_t> &sp = a->h_species;
+    if ((int64_t)sp.size() != n) return fail(TDNA_E_STATE, "labels are not set");
+    const int64_t nblk = (n + tc::N - 1) / tc::N;
+    // nearest named row of each id parity at or before / at or after every row
+    std::vector<int32_t> prev[2], next[2];
+    for (int m = 0; m < 2; m++) {
+        prev[m].assign((size_t)n, -1);
+        next[m].assign((size_t)n, -1);
+        int32_t last = -1;
+        for (int64_t i = 0; i < n; i++) { if (sp[i] >= 0 && (sp[i] & 1) == m) last = (int32_t)i; prev[m][i] = last; }
+        last = -1;
+        for (int64_t i = n - 1; i >= 0; i--) { if (sp[i] >= 0 && (sp[i] & 1) == m) last = (int32_t)i; next[m][i] = last; }
+    }
+    std::vector<int2> list;
+    list.reserve((size_t)nblk * 2);
+    for (int64_t u = 0; u < nblk; u++) {
+        const int64_t c0 = u * tc::N, c1 = std::min<int64_t>(n, c0 + tc::N);
+        int64_t extra[4];
+        int ne = 0;
+        auto add = [&](int64_t row) {
+            if (row < 0 || row >= n) return;
+            const int64_t b = row / tc::N;
+            if (b == u) return;
+            for (int k = 0; k < ne; k++)
+                if (extra[k] == b) return;
+            if (ne < 4) extra[ne++] = b;
+        };
+        for (int m = 0; m < 2; m++) {
+            if (next[m][c0] >= 0 && next[m][c0] < c1) continue;  // the block has a species of this parity
+            const int64_t l = c0 > 0 ? prev[m][c0 - 1] : -1, r = c1 < n ? next[m][c1] : -1;
+            if (l >= 0 && (r < 0 || c0 - l <= r - (c1 - 1))) add(l); else if (r >= 0) add(r);
+        }
+        // rows at the block's edges whose conspecific neighbours are all across the edge (lists sorted by name: adjacent rows)
+        if (c0 > 0 && sp[c0] >= 0 && sp[c0 - 1] == sp[c0] && !(c0 + 1 < c1 && sp[c0 + 1] == sp[c0])) add(c0 - 1);
+        if (c1 < n && sp[c1 - 1] >= 0 && sp[c1] == sp[c1 - 1] && !(c1 - 2 >= c0 && sp[c1 - 2] == sp[c1 - 1])) add(c1);
+        list.push_back(make_int2((int)(2 * u), (int)u));
+        for (int k = 0; k < ne; k++) list.push_back(make_int2((int)(2 * u), (int)extra[k]));
+    }
+    if (a->d_seedlist) CU(DFREE(a->d_seedlist));
+    a->d_seedlist = nullptr;
+    CU(DMALLOC(&a->d_seedlist, list.size() * sizeof(int2)));
+    CU(cudaMemcpyAsync(a->d_seedlist, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    a->seed_pairs = (int)list.size();
+    a->seedlist_valid = true;
+    return TDNA_OK;
+}
+
 template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts) {
     tdna_ctx *c = a->ctx;
     // the plain instantiation serves uncorrected p on alignments without ambiguity letters (exact accumulators everywhere)
@@ -608,7 +671,12 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.band = phase ? TC_BAND : 0;
     p.nbands = (p.nrt + TC_BAND - 1) / TC_BAND;
     p.prefix = a->d_tcprefix[1];
-    int64_t total = a->tcprefix_tiles[phase];   // slots
+    if (!COUNTS_MODE && phase == 0 && a->has_labels) {
+        TRY(build_seed_list(a));
+        p.seed_list = a->d_seedlist;
+        p.seed_pairs = a->seed_pairs;
+    }
+    int64_t total = p.seed_list ? 2 * (int64_t)a->seed_pairs : a->tcprefix_tiles[phase];   // slots
     if (CL >= 2) total = (total + 1) / 2;         // pairs of slots
     // part k of m takes every m-th UNIT of 128 consecutive slots (64 row tiles x 2 column tiles of one band: the panels a
     // unit shares stay in this GPU's L2); units are dealt cyclically so that work AND candidates (which cluster near the
@@ -873,7 +941,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
                     a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
-                    a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_cursor, a->d_lj, a->d_ld};
+                    a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_seedlist, a->d_cursor, a->d_lj, a->d_ld};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
     delete a;
@@ -912,8 +980,11 @@ int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const 
     CU(cudaGetLastError());
     CU(DFREE(d_keys));
     CU(DFREE(d_cnts));
+    a->h_species.resize((size_t)a->n);
+    CU(cudaMemcpyAsync(a->h_species.data(), a->d_species, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));  // the caller's label arrays may be pageable: do not return before the copies have read them
     a->has_labels = true;
+    a->seedlist_valid = false;
     return TDNA_OK;
 }
 
@@ -1179,6 +1250,7 @@ static int best_match_dense(tdna_aln *a) {
 }
 
 static int ensure_stream_state(tdna_aln *a) {
+    if (a->stream_broken) return fail(TDNA_E_TOO_LARGE, "the streaming buffers could not be regrown");  // the caller takes the dense path
     if (a->stream_alloc) return TDNA_OK;
     tdna_ctx *c = a->ctx;
     size_t n = (size_t)a->n;
@@ -1219,6 +1291,41 @@ static int ensure_stream_state(tdna_aln *a) {
     return TDNA_OK;
 }
 
+// After an overflow: buffers sized to what the failed pass asked for (+25 %), within a quarter of the memory budget.  Lists with
+// hundreds of conspecifics per species need it -- every conspecific closer than the nearest other species is a candidate.
+// false: nothing to grow, or no room (the caller falls back to the next path).
+static bool grow_stream_buffers(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
+    StreamParams &sp = a->sp;
+    long long cap = sp.cap, qcap = sp.qcap;
+    if (a->need_cand > cap) cap = a->need_cand + a->need_cand / 4;
+    if (a->need_queue > qcap) qcap = a->need_queue + a->need_queue / 4;
+    a->need_cand = a->need_queue = 0;
+    if (cap == sp.cap && qcap == sp.qcap) return false;
+    if (cap * 16 + qcap * 12 > c->budget / 4) return false;
+    if (cap != sp.cap) {
+        DFREE(sp.cq); DFREE(sp.cj); DFREE(sp.cd);
+        sp.cq = sp.cj = nullptr; sp.cd = nullptr;
+        if (cudaSuccess != DMALLOC(&sp.cq, (size_t)cap * 4) || cudaSuccess != DMALLOC(&sp.cj, (size_t)cap * 4) || cudaSuccess != DMALLOC(&sp.cd, (size_t)cap * 8)) {
+            cudaGetLastError();
+            a->stream_broken = true;
+            return false;
+        }
+        sp.cap = cap;
+    }
+    if (qcap != sp.qcap) {
+        DFREE(sp.qi); DFREE(sp.qj); DFREE(sp.qv);
+        sp.qi = sp.qj = nullptr; sp.qv = nullptr;
+        if (cudaSuccess != DMALLOC(&sp.qi, (size_t)qcap * 4) || cudaSuccess != DMALLOC(&sp.qj, (size_t)qcap * 4) || cudaSuccess != DMALLOC(&sp.qv, (size_t)qcap * 4)) {
+            cudaGetLastError();
+            a->stream_broken = true;
+            return false;
+        }
+        sp.qcap = qcap;
+    }
+    return true;
+}
+
 // seed: state init + the diagonal blocks of this part (thresholds from list neighbours)
 static int stream_seed(tdna_aln *a, int part, int nparts) {
     tdna_ctx *c = a->ctx;
@@ -1244,10 +1351,14 @@ static int stream_bulk(tdna_aln *a, int part, int nparts, long long *ncand_out) 
     c->launches++;
     CU(cudaGetLastError());
     TRY(launch_stream(a, part, nparts, 2));
-    struct { unsigned long long ncand; int overflow; int pad; unsigned long long ncls[2]; unsigned long long nedge; } h;
+    struct { unsigned long long ncand; int overflow; int pad; unsigned long long ncls[2]; unsigned long long nedge; unsigned long long qn; } h;
     CU(cudaMemcpyAsync(&h, a->d_stream_u64, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (h.overflow) return fail(TDNA_E_TOO_LARGE, "streaming Best Match: candidate buffer overflow");
+    if (h.overflow) {  // both counters kept counting past their buffers: they are the demand (grow_stream_buffers)
+        a->need_cand = (long long)h.ncand;
+        a->need_queue = (long long)h.qn;
+        return fail(TDNA_E_TOO_LARGE, "streaming Best Match: candidate buffer overflow");
+    }
     a->last_ncand = (long long)h.ncand;
     a->last_ncls[0] = (long long)h.ncls[0];
     a->last_ncls[1] = (long long)h.ncls[1];
@@ -1563,6 +1674,7 @@ static int analyze_stream(tdna_aln *a, tdna_analysis *io) {
     }
     long long ncand = 0;
     rc = stream_part(a, 0, 1, &ncand);
+    for (int attempt = 0; rc == TDNA_E_TOO_LARGE && attempt < 3 && grow_stream_buffers(a); attempt++) rc = stream_part(a, 0, 1, &ncand);
     if (rc == TDNA_OK && (io->want & TDNA_WANT_BEST_MATCH)) {
         if (!a->d_res) {
             cudaError_t e = DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result));

@@ -66,6 +66,10 @@ struct Params {
     // which is all the candidate filter needs; exact counts of the queued pairs come from the bit-planes (like K2P's).
     const int32_t *amb;        // nullptr: the alignment has no such letter
     const uint8_t *panel_amb;  // [128-row panel] 1 = some row of the panel has one
+    // seed pass: the PAIRS of row tiles to visit, (even row tile, column tile) each -- the diagonal block of every pair plus, where the
+    // labels say a row would otherwise see no conspecific or no species of the other id parity, the neighbouring block that has one
+    const int2 *seed_list;
+    int seed_pairs;
     int class_only;         // the pass wants class distances and nothing per row: bit 0 = intra, bit 1 = inter.  Tiles whose row and
     const int4 *panel_range;  // column panels share no species / genus id range hold no such pair and are skipped by every role
 };
@@ -75,6 +79,13 @@ struct Params {
 // (L2-resident for the whole band) and two or three b-panels: every b-panel is fetched from HBM once per band.
 __device__ __forceinline__ bool slot_coords(const Params &p, const int64_t *prefix, int64_t t, int &ti, int &tj) {
     if (p.band == 0) {
+        if (p.seed_list) {
+            if ((t >> 1) >= p.seed_pairs) return false;
+            const int2 e = __ldg(p.seed_list + (t >> 1));
+            ti = e.x + (int)(t & 1);
+            tj = e.y;
+            return ti < p.nrt && tj < p.nct;
+        }
         ti = (int)t;
         tj = ti >> 1;
         return ti < p.nrt && tj < p.nct;

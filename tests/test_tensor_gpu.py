@@ -218,3 +218,31 @@ def test_ambiguity_codes_at_scale_fall_back_cleanly(ctx, n, L):
     assert np.array_equal(np.sort(intra), np.sort(dense)) and np.array_equal(np.sort(intra_a), np.sort(dense))
     assert rows_a.tobytes() == rows_b.tobytes()
     aln.close()
+
+
+@pytest.mark.parametrize("reps,L", [(600, 300), (300, 658)])
+def test_species_blocks_wider_than_the_seed_window(ctx, reps, L):
+    """Hundreds of conspecifics in a row: a 256-row diagonal block lies inside ONE species, so the seed pass must also visit the
+    block with the nearest species of the other id parity (else one of the three minima stays unbounded and every pair of
+    the row is queued), and every conspecific closer than the nearest other species is a candidate (the record buffers grow
+    on demand).  Kernel (b) == kernel (a) == the dense path."""
+    import taxondna_b200 as t
+    from taxondna_b200 import synth
+    d = synth.generate("H", names=False, genera=2, species=3, reps=reps, L=L)
+    sym = d["symbols"]
+    n = sym.shape[0]
+    aln = t.Alignment(ctx, sym)
+    aln.set_labels(d["species_id"], d["genus_id"], d["epithet_rank"], d["fullname_rank"])
+    aln.set_config(t.PDM_UNCORRECTED, L // 2, True)
+    got = {}
+    for name, path, k in (("dense", t.PATH_DENSE, t.KERNEL_AUTO), ("popc", t.PATH_STREAM, t.KERNEL_POPC), ("tensor", t.PATH_STREAM, t.KERNEL_TENSOR)):
+        ctx.set_option(t.OPT_BEST_MATCH_PATH, path)
+        ctx.set_option(t.OPT_COUNT_KERNEL, k)
+        got[name] = aln.best_match()
+        if name != "dense":
+            assert aln.last_count_kernel() == k
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
+    assert got["tensor"].tobytes() == got["dense"].tobytes() and got["popc"].tobytes() == got["dense"].tobytes()
+    assert (got["dense"]["n_valid"] == n - 1).all()
+    aln.close()
