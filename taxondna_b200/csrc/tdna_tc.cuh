@@ -591,7 +591,9 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     }
                 }
                 const int jb = j0 + cb * 32;
-                if (p.hints == 8) continue;  // experiment: no epilogue work at all (results are wrong)
+#ifdef TDNA_TC_EXPERIMENTS
+                if (p.hints == 8) continue;  // -DTDNA_TC_EXPERIMENTS, TDNA_TC_HINTS=8: no epilogue work at all (results are wrong) -- the MMA floor
+#endif
                 if constexpr (COUNTS_MODE) {
 #pragma unroll
                     for (int e = 0; e < 32; e++) {
