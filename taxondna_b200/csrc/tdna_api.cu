@@ -1385,6 +1385,17 @@ static int row_pointers(tdna_aln *a, const int *cnt) {
     return TDNA_OK;
 }
 
+// G lanes per row from the mean list length (tdna_kernels.cuh: stream_finalize_kernel)
+static void launch_finalize(tdna_aln *a, const int *inval, const int *flags, int64_t q0, int64_t q1, long long records) {
+    tdna_ctx *c = a->ctx;
+    const int64_t rows = q1 - q0;
+    if (rows <= 0) return;
+    const long long mean = records / rows;
+    if (mean < 24) stream_finalize_kernel<8><<<(unsigned)((rows * 8 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, inval, flags, a->d_species, a->n, a->d_res, q0, q1);
+    else if (mean < 64) stream_finalize_kernel<16><<<(unsigned)((rows * 16 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, inval, flags, a->d_species, a->n, a->d_res, q0, q1);
+    else stream_finalize_kernel<32><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, inval, flags, a->d_species, a->n, a->d_res, q0, q1);
+}
+
 static int stream_merge(tdna_aln *a, const int32_t *cq, const int32_t *cj, const double *cd, long long ncand, const int32_t *inval,
                         const int32_t *flags, bool counts_ready) {
     tdna_ctx *c = a->ctx;
@@ -1416,8 +1427,7 @@ static int stream_merge(tdna_aln *a, const int32_t *cq, const int32_t *cj, const
         stream_scatter_kernel<<<gr, 256, 0, c->stream>>>(cq, cj, cd, ncand, a->d_ptr, a->d_cursor, a->d_lj, a->d_ld);
         c->launches++;
     }
-    stream_finalize_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, inval, flags, a->d_species, a->n,
-                                                                                    a->d_res, 0, a->n);
+    launch_finalize(a, inval, flags, 0, a->n, ncand);
     c->launches++;
     CU(cudaGetLastError());
     return fill_shared(a, 0, a->n);
@@ -1502,8 +1512,7 @@ int32_t tdna_best_match_merge_gathered(tdna_aln *a, const int64_t *rec, int32_t 
     count_rows_seg_kernel<<<gr, 256, 0, c->stream>>>(lrec, nseg, seg_stride, lcnt, a->sp.cnt);
     TRY(row_pointers(a, a->sp.cnt));
     scatter_seg_kernel<<<gr, 256, 0, c->stream>>>(lrec, nseg, seg_stride, lcnt, a->d_ptr, a->d_cursor, a->d_lj, a->d_ld);
-    stream_finalize_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, a->sp.inval, a->sp.flags, a->d_species, a->n,
-                                                                                    a->d_res, 0, a->n);
+    launch_finalize(a, a->sp.inval, a->sp.flags, 0, a->n, total / 2);  // the segments are sized with about 2x headroom
     c->launches += 4;
     CU(cudaGetLastError());
     TRY(fill_shared(a, 0, a->n));
@@ -1579,9 +1588,7 @@ int32_t tdna_best_match_merge_routed(tdna_aln *a, int32_t part, int32_t nparts, 
     count_rows_seg_kernel<<<gr, 256, 0, c->stream>>>(lrec, nparts, seg_stride, lcnt, a->sp.cnt);  // every record received is one of this part's rows
     TRY(row_pointers(a, a->sp.cnt));
     scatter_seg_kernel<<<gr, 256, 0, c->stream>>>(lrec, nparts, seg_stride, lcnt, a->d_ptr, a->d_cursor, a->d_lj, a->d_ld);
-    if (q1 > q0)
-        stream_finalize_kernel<<<(unsigned)(((q1 - q0) * 32 + 255) / 256), 256, 0, c->stream>>>(a->d_ptr, a->d_lj, a->d_ld, a->sp.inval, a->sp.flags, a->d_species,
-                                                                                                a->n, a->d_res, q0, q1);
+    launch_finalize(a, a->sp.inval, a->sp.flags, q0, q1, total / 3);  // the segments are sized with about 3x headroom
     c->launches += 4;
     CU(cudaGetLastError());
     TRY(fill_shared(a, q0, q1));

@@ -879,9 +879,9 @@ __device__ __forceinline__ void sweep2_elem(Sweep2 &s, const RowRefs &f, int spq
         if (!f.has_o || key_less(k, f.ko)) s.v[9]++;
     }
 }
-__device__ __forceinline__ void sweep2_warp_reduce(Sweep2 &s) {
+__device__ __forceinline__ void sweep2_warp_reduce(Sweep2 &s, int first = 16) {  // first = half the lanes that hold one row
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
+    for (int m = first; m >= 1; m >>= 1) {
 #pragma unroll
         for (int i = 0; i < 10; i++) s.v[i] += __shfl_xor_sync(0xffffffffu, s.v[i], m);
         s.smin = min(s.smin, __shfl_xor_sync(0xffffffffu, s.smin, m));
@@ -1287,35 +1287,39 @@ __global__ void __launch_bounds__(256) scatter_seg_kernel(const long long *__res
     }
 }
 
-// one warp per query row: the two sweeps over the row's candidate list (complete below its threshold)
+// G lanes per query row (32 / G rows per warp): the two sweeps over the row's candidate list (complete below its threshold).
+// Lists average ~15 entries on barcode data, so eight lanes per row keep the lanes busy and the butterflies short; rows of large
+// species carry hundreds of entries and get a whole warp (the host picks G from the mean list length).
+template <int G>
 __global__ void __launch_bounds__(256) stream_finalize_kernel(const long long *__restrict__ ptr, const int32_t *__restrict__ lj,
                                                               const double *__restrict__ ld, const int *__restrict__ inval,
                                                               const int *__restrict__ flags, const int32_t *__restrict__ species,
                                                               int64_t n, tdna_row_result *__restrict__ out, int64_t q_begin, int64_t q_end) {
-    const int lane = threadIdx.x & 31;
-    const int64_t q = q_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);  // rows [q_begin, q_end): a part's own rows, or all
-    if (q >= q_end) return;
-    const int spq = species[q];
+    const int gl = threadIdx.x & (G - 1);
+    const int64_t q = q_begin + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;  // rows [q_begin, q_end): a part's own rows, or all
+    const bool live = q < q_end;  // dead groups run along with empty lists: the shuffles below are warp-wide
+    const int64_t qq = live ? q : q_begin;
+    const int spq = species[qq];
     const bool qnamed = spq >= 0;
-    const long long b = ptr[q], e = ptr[q + 1];
+    const long long b = live ? ptr[qq] : 0, e = live ? ptr[qq + 1] : 0;
     RowAgg g = agg_identity();
-    for (long long k = b + lane; k < e; k += 32) {
+    for (long long k = b + gl; k < e; k += G) {
         const int j = lj[k];
         sweep1_elem(g, spq, qnamed, j, ld[k], species[j]);
     }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) { RowAgg o = agg_shfl_xor(g, m); agg_merge(g, o); }
+    for (int m = G / 2; m >= 1; m >>= 1) { RowAgg o = agg_shfl_xor(g, m); agg_merge(g, o); }
     const RowRefs f = make_refs(g, species);
     Sweep2 s2 = sweep2_identity();
     if (f.has_b) {
-        for (long long k = b + lane; k < e; k += 32) {
+        for (long long k = b + gl; k < e; k += G) {
             const int j = lj[k];
             sweep2_elem(s2, f, spq, qnamed, j, ld[k], species[j]);
         }
-        sweep2_warp_reduce(s2);
     }
+    sweep2_warp_reduce(s2, G / 2);
     // every valid column is counted through inval[] (the list holds only the near ones)
-    if (lane == 0) out[q] = make_row_result(f, s2, (int)(n - 1) - inval[q], flags[q]);
+    if (live && gl == 0) out[q] = make_row_result(f, s2, (int)(n - 1) - inval[q], flags[q]);
 }
 
 // getSharedLength(query, first_con / first_allo) for the listing (BestMatch.java:372,386)
