@@ -146,6 +146,26 @@ int32_t tdna_row_distances(tdna_aln *aln, int64_t q, double *d, int32_t *shared)
  * QuerySequence.query (QuerySequence.java:113-145). */
 int32_t tdna_query_distances(tdna_aln *aln, const uint8_t *symbols, int32_t len, double *d, int32_t *shared, tdna_counts *counts);
 
+/* ---- FASTA on the device (the format on the input side of the path) -------------------------------------
+ * FastaFile.appendFromFile / makeSequence (Common/DNA/formats/FastaFile.java:144-289) and the alphabet part of
+ * Sequence.changeSequence (Common/DNA/Sequence.java:751-840) as byte-parallel kernels: `text` (host or device, nbytes) ->
+ * records.  Per record: where its header line (after '>') sits in `text` (names are parsed by the host layer as before), its
+ * sequence length, flags; and the n x width symbol matrix in the normalised alphabet ('?' padded), resident on the device. */
+typedef struct tdna_fasta tdna_fasta;
+enum { TDNA_FASTA_URACIL = 1,      /* U converted to T (FastaFile.java:273-285 warns) */
+       TDNA_FASTA_INVALID = 2,     /* a symbol isValid rejects (Sequence.java:927-965), or a '_' where a gap stroke meets it (:812-838) */
+       TDNA_FASTA_NEEDS_HOST = 4   /* "[AG]" / "(AG)" group syntax (:758-796): normalise this record on the host */ };
+int32_t tdna_fasta_parse(tdna_ctx *ctx, const uint8_t *text, int64_t nbytes, tdna_fasta **out);
+int32_t tdna_fasta_destroy(tdna_fasta *f);
+int64_t tdna_fasta_count(const tdna_fasta *f);
+int32_t tdna_fasta_width(const tdna_fasta *f);
+/* any of the four outputs may be NULL; n entries each */
+int32_t tdna_fasta_records(tdna_fasta *f, int64_t *header_offset, int32_t *header_length, int32_t *seq_length, int32_t *flags);
+int32_t tdna_fasta_symbols(tdna_fasta *f, uint8_t *out, int64_t row_stride);
+/* an alignment straight from the parsed records: the symbols never visit the host.  TDNA_E_SYMBOL if a record is flagged
+ * INVALID or NEEDS_HOST. */
+int32_t tdna_alignment_create_from_fasta(tdna_ctx *ctx, tdna_fasta *f, tdna_aln **out);
+
 /* ---- full matrix (config C2; Cluster.java:605-626 prints one per cluster) ---------------- */
 /* d: (row_end-row_begin) x n doubles, row-major, ld = n.  counts (optional): same shape. */
 int32_t tdna_matrix(tdna_aln *aln, double *d, tdna_counts *counts);

@@ -66,7 +66,7 @@ EXPORTS = [
     "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_pairs", "tdna_row_distances", "tdna_query_distances", "tdna_matrix", "tdna_matrix_compute",
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
-    "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_rows_per_part", "tdna_best_match_part_routed", "tdna_best_match_merge_routed", "tdna_set_option", "tdna_last_tile_pass_ms",
+    "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_rows_per_part", "tdna_fasta_parse", "tdna_fasta_destroy", "tdna_fasta_count", "tdna_fasta_width", "tdna_fasta_records", "tdna_fasta_symbols", "tdna_alignment_create_from_fasta", "tdna_best_match_part_routed", "tdna_best_match_merge_routed", "tdna_set_option", "tdna_last_tile_pass_ms",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -100,6 +100,15 @@ def load():
     L.tdna_set_row_range.argtypes = [vp, i64, i64]
     L.tdna_pair.argtypes = [vp, i64, i64, ctypes.POINTER(Counts), ctypes.POINTER(dbl)]
     L.tdna_pairs.argtypes = [vp, vp, vp, i64, vp, vp]
+    if hasattr(L, "tdna_fasta_parse"):
+        L.tdna_fasta_parse.argtypes = [vp, vp, i64, ctypes.POINTER(vp)]
+        L.tdna_fasta_destroy.argtypes = [vp]
+        L.tdna_fasta_count.argtypes = [vp]
+        L.tdna_fasta_count.restype = i64
+        L.tdna_fasta_width.argtypes = [vp]
+        L.tdna_fasta_records.argtypes = [vp, vp, vp, vp, vp]
+        L.tdna_fasta_symbols.argtypes = [vp, vp, i64]
+        L.tdna_alignment_create_from_fasta.argtypes = [vp, vp, ctypes.POINTER(vp)]
     if hasattr(L, "tdna_rows_per_part"):  # absent from older builds loaded through TDNA_LIB for an A/B
         L.tdna_rows_per_part.argtypes = [i64, i32]
         L.tdna_rows_per_part.restype = i64
@@ -378,3 +387,54 @@ class Alignment:
         ms = ctypes.c_float()
         check(self.L.tdna_time_matrix_kernel(self.h, reps, ctypes.byref(ms)))
         return ms.value
+
+
+FASTA_URACIL, FASTA_INVALID, FASTA_NEEDS_HOST = 1, 2, 4
+
+
+class Fasta:
+    """FASTA text parsed on the device (tdna_fasta_parse): record table + the normalised symbol matrix, device resident."""
+
+    def __init__(self, ctx, text):
+        self.L, self.ctx = ctx.L, ctx
+        data = np.frombuffer(text if isinstance(text, (bytes, bytearray)) else text.encode("latin-1"), dtype=np.uint8)
+        self.text = data
+        h = ctypes.c_void_p()
+        check(self.L.tdna_fasta_parse(ctx.h, data.ctypes.data if data.size else b"", int(data.size), ctypes.byref(h)))
+        self.h = h
+        self.n = int(self.L.tdna_fasta_count(self.h))
+        self.width = int(self.L.tdna_fasta_width(self.h))
+
+    def records(self):
+        off = np.zeros(self.n, dtype=np.int64)
+        hl = np.zeros(self.n, dtype=np.int32)
+        sl = np.zeros(self.n, dtype=np.int32)
+        fl = np.zeros(self.n, dtype=np.int32)
+        check(self.L.tdna_fasta_records(self.h, off.ctypes.data, hl.ctypes.data, sl.ctypes.data, fl.ctypes.data))
+        return off, hl, sl, fl
+
+    def headers(self):
+        off, hl, _, _ = self.records()
+        raw = self.text.tobytes()
+        return [raw[o:o + k].decode("latin-1") for o, k in zip(off.tolist(), hl.tolist())]
+
+    def symbols(self):
+        out = np.full((self.n, max(self.width, 1)), ord("?"), dtype=np.uint8)
+        if self.n and self.width:
+            check(self.L.tdna_fasta_symbols(self.h, out.ctypes.data, out.shape[1]))
+        return out
+
+    def alignment(self):
+        """An Alignment straight from the device-resident records (no host round trip of the symbols)."""
+        h = ctypes.c_void_p()
+        check(self.L.tdna_alignment_create_from_fasta(self.ctx.h, self.h, ctypes.byref(h)))
+        a = Alignment.__new__(Alignment)
+        a.L, a.ctx, a.h, a.n, a.ncols = self.L, self.ctx, h, self.n, self.width
+        a.row_begin, a.row_end = 0, self.n
+        return a
+
+    def close(self):
+        if self.h:
+            self.L.tdna_fasta_destroy(self.h)
+            self.h = None
+

@@ -9,6 +9,7 @@
 
 #include "tdna_kernels.cuh"
 #include "tdna_tc.cuh"
+#include "tdna_fasta.cuh"
 
 using namespace tdna;
 
@@ -1975,6 +1976,161 @@ int32_t tdna_tensor_counts(tdna_aln *a, tdna_counts *out) {
     }
     if (own) DFREE(dc);
     return rc;
+}
+
+// ---- FASTA on the device (tdna_fasta.cuh) ---------------------------------------------------------------------------------
+struct tdna_fasta {
+    tdna_ctx *ctx = nullptr;
+    int64_t n = 0;
+    int32_t width = 0;
+    int64_t stride = 0;
+    uint8_t *d_rows = nullptr;
+    int *d_seq_length = nullptr, *d_flags = nullptr, *d_header_length = nullptr;
+    long long *d_header_offset = nullptr;
+};
+
+// exclusive prefix sum of n ints into ptr[0..n] with the row-pointer kernels; scratch holds ceil(n / SCAN_BLOCK) sums
+static int scan_ints(tdna_ctx *c, const int *cnt, int64_t n, long long *ptr, long long *scratch) {
+    const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    scan_block_sums_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(cnt, n, scratch);
+    scan_block_offsets_kernel<<<1, 1024, 0, c->stream>>>(scratch, nb, ptr + n);
+    scan_apply_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(cnt, n, scratch, ptr);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    return TDNA_OK;
+}
+
+int32_t tdna_fasta_destroy(tdna_fasta *f) {
+    if (!f) return TDNA_OK;
+    tdna_ctx *c = f->ctx;
+    cudaSetDevice(c->device);
+    void *ptrs[] = {f->d_rows, f->d_seq_length, f->d_flags, f->d_header_length, f->d_header_offset};
+    for (void *p : ptrs)
+        if (p) DFREE(p);
+    delete f;
+    return TDNA_OK;
+}
+
+int32_t tdna_fasta_parse(tdna_ctx *c, const uint8_t *text, int64_t nbytes, tdna_fasta **out) {
+    if (!c || !text || !out || nbytes < 0) return fail(TDNA_E_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    tdna_fasta *f = new tdna_fasta();
+    f->ctx = c;
+    *out = nullptr;
+    if (nbytes == 0) { *out = f; return TDNA_OK; }
+    // device scratch, all freed before returning
+    uint8_t *d_text = nullptr;
+    int *d_block_lines = nullptr, *d_kind = nullptr, *d_symbols = nullptr, *d_isname = nullptr, *d_max = nullptr;
+    long long *d_block_first = nullptr, *d_scratch = nullptr, *d_line_start = nullptr, *d_rec_of_line = nullptr, *d_sym_before = nullptr, *d_rec_line = nullptr;
+    int rc = TDNA_OK;
+    auto cleanup = [&]() {
+        void *ptrs[] = {d_block_lines, d_kind, d_symbols, d_isname, d_max, d_block_first, d_scratch, d_line_start, d_rec_of_line, d_sym_before, d_rec_line};
+        for (void *p : ptrs)
+            if (p) DFREE(p);
+        if (d_text && d_text != text) DFREE(d_text);
+    };
+#define FCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); tdna_fasta_destroy(f); return fail(TDNA_E_CUDA, cudaGetErrorString(e_)); } } while (0)
+    if (is_device_ptr(text)) d_text = const_cast<uint8_t *>(text);
+    else {
+        FCU(DMALLOC(&d_text, (size_t)nbytes));
+        FCU(cudaMemcpyAsync(d_text, text, (size_t)nbytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    const int64_t nblocks = (nbytes + fasta::BLOCK_BYTES - 1) / fasta::BLOCK_BYTES;
+    FCU(DMALLOC(&d_block_lines, (size_t)nblocks * 4));
+    FCU(DMALLOC(&d_block_first, (size_t)(nblocks + 1) * 8));
+    FCU(DMALLOC(&d_scratch, (size_t)((std::max<int64_t>(nblocks, nbytes / 2 + 2) + SCAN_BLOCK - 1) / SCAN_BLOCK + 1) * 8));
+    fasta::count_lines_kernel<<<(unsigned)nblocks, 256, 0, c->stream>>>(d_text, nbytes, d_block_lines);
+    c->launches++;
+    if ((rc = scan_ints(c, d_block_lines, nblocks, d_block_first, d_scratch)) != TDNA_OK) { cleanup(); tdna_fasta_destroy(f); return rc; }
+    long long nlines = 0;
+    FCU(cudaMemcpyAsync(&nlines, d_block_first + nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
+    FCU(cudaStreamSynchronize(c->stream));
+    FCU(DMALLOC(&d_line_start, (size_t)nlines * 8));
+    FCU(DMALLOC(&d_kind, (size_t)nlines * 4));
+    FCU(DMALLOC(&d_symbols, (size_t)nlines * 4));
+    FCU(DMALLOC(&d_isname, (size_t)nlines * 4));
+    FCU(DMALLOC(&d_rec_of_line, (size_t)(nlines + 1) * 8));
+    FCU(DMALLOC(&d_sym_before, (size_t)(nlines + 1) * 8));
+    fasta::list_lines_kernel<<<(unsigned)nblocks, 32, 0, c->stream>>>(d_text, nbytes, d_block_first, d_line_start);
+    fasta::classify_lines_kernel<<<(unsigned)((nlines + 255) / 256), 256, 0, c->stream>>>(d_text, nbytes, d_line_start, nlines, d_kind, d_symbols, d_isname);
+    c->launches += 2;
+    if ((rc = scan_ints(c, d_isname, nlines, d_rec_of_line, d_scratch)) != TDNA_OK || (rc = scan_ints(c, d_symbols, nlines, d_sym_before, d_scratch)) != TDNA_OK) {
+        cleanup(); tdna_fasta_destroy(f); return rc;
+    }
+    long long nrec = 0;
+    FCU(cudaMemcpyAsync(&nrec, d_rec_of_line + nlines, 8, cudaMemcpyDeviceToHost, c->stream));
+    FCU(cudaStreamSynchronize(c->stream));
+    f->n = nrec;
+    if (nrec > 0) {
+        FCU(DMALLOC(&d_rec_line, (size_t)nrec * 8));
+        FCU(DMALLOC(&f->d_header_offset, (size_t)nrec * 8));
+        FCU(DMALLOC(&f->d_header_length, (size_t)nrec * 4));
+        FCU(DMALLOC(&f->d_seq_length, (size_t)nrec * 4));
+        FCU(DMALLOC(&f->d_flags, (size_t)nrec * 4));
+        FCU(DMALLOC(&d_max, 4));
+        FCU(cudaMemsetAsync(d_max, 0, 4, c->stream));
+        FCU(cudaMemsetAsync(f->d_flags, 0, (size_t)nrec * 4, c->stream));
+        fasta::records_kernel<<<(unsigned)((nlines + 255) / 256), 256, 0, c->stream>>>(d_text, nbytes, d_line_start, nlines, d_kind, d_rec_of_line, d_sym_before, d_rec_line,
+                                                                                    f->d_header_offset, f->d_header_length);
+        fasta::record_lengths_kernel<<<(unsigned)((nrec + 255) / 256), 256, 0, c->stream>>>(d_rec_line, nrec, nlines, d_sym_before, f->d_seq_length, d_max);
+        c->launches += 2;
+        int width = 0;
+        FCU(cudaMemcpyAsync(&width, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
+        FCU(cudaStreamSynchronize(c->stream));
+        f->width = width;
+        f->stride = round_up(std::max(width, 1), 32);
+        FCU(DMALLOC(&f->d_rows, (size_t)nrec * f->stride));
+        FCU(cudaMemsetAsync(f->d_rows, '?', (size_t)nrec * f->stride, c->stream));
+        fasta::scatter_symbols_kernel<<<(unsigned)((nlines * 32 + 255) / 256), 256, 0, c->stream>>>(d_text, nbytes, d_line_start, nlines, d_kind, d_rec_of_line, d_sym_before,
+                                                                                                 d_rec_line, f->d_rows, f->stride, f->d_flags);
+        fasta::external_gaps_kernel<<<(unsigned)((nrec * 32 + 255) / 256), 256, 0, c->stream>>>(f->d_rows, f->stride, (int)f->stride, f->d_seq_length, nrec, f->d_flags);
+        c->launches += 2;
+        FCU(cudaGetLastError());
+    }
+    FCU(cudaStreamSynchronize(c->stream));
+#undef FCU
+    cleanup();
+    *out = f;
+    return TDNA_OK;
+}
+
+int64_t tdna_fasta_count(const tdna_fasta *f) { return f ? f->n : 0; }
+int32_t tdna_fasta_width(const tdna_fasta *f) { return f ? f->width : 0; }
+
+int32_t tdna_fasta_records(tdna_fasta *f, int64_t *header_offset, int32_t *header_length, int32_t *seq_length, int32_t *flags) {
+    if (!f) return fail(TDNA_E_ARG, "null argument");
+    tdna_ctx *c = f->ctx;
+    CU(cudaSetDevice(c->device));
+    if (f->n == 0) return TDNA_OK;
+    if (header_offset) CU(cudaMemcpyAsync(header_offset, f->d_header_offset, (size_t)f->n * 8, cudaMemcpyDefault, c->stream));
+    if (header_length) CU(cudaMemcpyAsync(header_length, f->d_header_length, (size_t)f->n * 4, cudaMemcpyDefault, c->stream));
+    if (seq_length) CU(cudaMemcpyAsync(seq_length, f->d_seq_length, (size_t)f->n * 4, cudaMemcpyDefault, c->stream));
+    if (flags) CU(cudaMemcpyAsync(flags, f->d_flags, (size_t)f->n * 4, cudaMemcpyDefault, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TDNA_OK;
+}
+
+int32_t tdna_fasta_symbols(tdna_fasta *f, uint8_t *out, int64_t row_stride) {
+    if (!f || !out || row_stride < f->width) return fail(TDNA_E_ARG, "bad argument");
+    tdna_ctx *c = f->ctx;
+    CU(cudaSetDevice(c->device));
+    if (f->n == 0 || f->width == 0) return TDNA_OK;
+    CU(cudaMemcpy2DAsync(out, (size_t)row_stride, f->d_rows, (size_t)f->stride, (size_t)f->width, (size_t)f->n, cudaMemcpyDefault, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TDNA_OK;
+}
+
+int32_t tdna_alignment_create_from_fasta(tdna_ctx *c, tdna_fasta *f, tdna_aln **out) {
+    if (!c || !f || !out) return fail(TDNA_E_ARG, "null argument");
+    if (f->ctx != c) return fail(TDNA_E_ARG, "the records were parsed on another context");
+    if (f->n < 1 || f->width < 1) return fail(TDNA_E_ARG, "no sequences");
+    std::vector<int32_t> flags((size_t)f->n);
+    TRY(tdna_fasta_records(f, nullptr, nullptr, nullptr, flags.data()));
+    for (int64_t r = 0; r < f->n; r++)
+        if (flags[r] & (fasta::FLAG_INVALID | fasta::FLAG_NEEDS_HOST))
+            return fail(TDNA_E_SYMBOL, "record " + std::to_string(r) + ((flags[r] & fasta::FLAG_INVALID) ? ": a symbol outside the alphabet" : ": '[..]' / '(..)' groups need the host normaliser"));
+    // device-to-device: the symbols never visit the host (rows keep the parser's stride; lengths are the records' own)
+    return tdna_alignment_create(c, f->d_rows, f->n, f->width, f->stride, f->d_seq_length, out);
 }
 
 int32_t tdna_last_count_kernel(tdna_aln *a) {
