@@ -166,6 +166,14 @@ int32_t tdna_fasta_symbols(tdna_fasta *f, uint8_t *out, int64_t row_stride);
  * INVALID or NEEDS_HOST. */
 int32_t tdna_alignment_create_from_fasta(tdna_ctx *ctx, tdna_fasta *f, tdna_aln **out);
 
+/* ---- consensus of bins (the step after Cluster: Cluster.makeConsensusOfBin, SpeciesIdentifier/Cluster.java:123-138) -------------
+ * The left fold of Sequence.getConsensus (Common/DNA/Sequence.java:1374-1398; consensus() :1008-1050) over each bin's members, as
+ * the reference computes it with a re-normalisation after every step.  Bin k = rows members[offsets[k] .. offsets[k + 1]) (host
+ * arrays, offsets[0] = 0).  out: nclusters rows of row_stride >= L bytes in the normalised alphabet ('?' padded), out_len[k] = the
+ * longest member's length (host or device). */
+int32_t tdna_consensus(tdna_aln *aln, const int32_t *members, const int64_t *offsets, int64_t nclusters, uint8_t *out, int64_t row_stride,
+                       int32_t *out_len);
+
 /* ---- full matrix (config C2; Cluster.java:605-626 prints one per cluster) ---------------- */
 /* d: (row_end-row_begin) x n doubles, row-major, ld = n.  counts (optional): same shape. */
 int32_t tdna_matrix(tdna_aln *aln, double *d, tdna_counts *counts);

@@ -1434,3 +1434,70 @@ def distance_analysis(D):
         else:
             out.append(genus + "\t\t\t" + java_double_str(percentage(avg_smallest, 1)) + "\t\t" + java_double_str(percentage(avg_inter, 1)) + "\n")
     return "".join(out), rows
+
+
+# --------------------------------------------------------------------------
+# Cluster.makeConsensusOfBin (SpeciesIdentifier/Cluster.java:123-138): the left fold of Sequence.getConsensus
+# (Common/DNA/Sequence.java:1374-1398) with consensus() (:1008-1050), getint (:1125-1143) and getcode (:1149-1196)
+# --------------------------------------------------------------------------
+def _getint(ch):
+    v = 0
+    if ch in "ARMNDHVW":
+        v |= 1
+    if ch in "CYMSNBHV":
+        v |= 2
+    if ch in "TYKNBDHW":
+        v |= 4
+    if ch in "GRKSNBDV":
+        v |= 8
+    return v
+
+
+def _getcode(v):
+    a, c, t, g = bool(v & 1), bool(v & 2), bool(v & 4), bool(v & 8)
+    if a:
+        if c:
+            if t:
+                return "N" if g else "H"
+            return "V" if g else "M"
+        if t:
+            return "D" if g else "W"
+        return "R" if g else "A"
+    if c:
+        if t:
+            return "B" if g else "Y"
+        return "S" if g else "C"
+    if t:
+        return "K" if g else "T"
+    return "G" if g else "-"
+
+
+def _consensus_char(ch1, ch2):
+    if ch1 == "?" or ch2 == "?":
+        return "?"
+    if ch1 == "_":
+        return "_" if ch2 == "_" else ("-" if ch2 == "-" else ch2)
+    if ch2 == "_":
+        return "-" if ch1 == "-" else ch1
+    if ch1 in "-_":
+        return ch2
+    if ch2 in "-_":
+        return ch1
+    return _getcode(_getint(ch1) | _getint(ch2))
+
+
+def get_consensus(seq1, seq2):
+    """Sequence.getConsensus on two normalised sequences (bytes) -> the normalised consensus (the Sequence constructor re-normalises)."""
+    a, b = seq1.decode("latin-1"), seq2.decode("latin-1")
+    out = []
+    for x in range(max(len(a), len(b))):
+        out.append(_consensus_char(a[x] if x < len(a) else "?", b[x] if x < len(b) else "?"))
+    return normalise("".join(out).replace("_", "-"))
+
+
+def consensus_of_bin(seqs):
+    cons = None
+    for s in seqs:
+        cons = s if cons is None else get_consensus(cons, s)
+    return cons
+

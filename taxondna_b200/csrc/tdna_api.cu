@@ -2133,6 +2133,49 @@ int32_t tdna_alignment_create_from_fasta(tdna_ctx *c, tdna_fasta *f, tdna_aln **
     return tdna_alignment_create(c, f->d_rows, f->n, f->width, f->stride, f->d_seq_length, out);
 }
 
+int32_t tdna_consensus(tdna_aln *a, const int32_t *members, const int64_t *offsets, int64_t nclusters, uint8_t *out, int64_t row_stride, int32_t *out_len) {
+    if (!a || !members || !offsets || !out || !out_len || nclusters < 0 || row_stride < a->L) return fail(TDNA_E_ARG, "bad argument");
+    if (nclusters == 0) return TDNA_OK;
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    const int64_t total = offsets[nclusters];
+    if (offsets[0] != 0 || total < 0) return fail(TDNA_E_ARG, "offsets must start at 0 and be host memory");
+    for (int64_t k = 0; k < nclusters; k++)
+        if (offsets[k + 1] <= offsets[k]) return fail(TDNA_E_ARG, "a bin has no member");
+    int32_t *d_members = nullptr;
+    long long *d_offsets = nullptr;
+    uint8_t *d_out = nullptr;
+    int *d_len = nullptr, *d_flags = nullptr;
+    auto cleanup = [&]() {
+        for (void *p : {(void *)d_members, (void *)d_offsets, (void *)d_out, (void *)d_len, (void *)d_flags})
+            if (p) DFREE(p);
+    };
+#define KCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(TDNA_E_CUDA, cudaGetErrorString(e_)); } } while (0)
+    const int64_t stride = round_up(a->L, 32);
+    KCU(DMALLOC(&d_members, (size_t)total * 4));
+    KCU(DMALLOC(&d_offsets, (size_t)(nclusters + 1) * 8));
+    KCU(DMALLOC(&d_out, (size_t)nclusters * stride));
+    KCU(DMALLOC(&d_len, (size_t)nclusters * 4));
+    KCU(DMALLOC(&d_flags, (size_t)nclusters * 4));
+    std::vector<int32_t> hm(members, members + total);
+    for (int32_t m : hm)
+        if (m < 0 || m >= a->n) { cleanup(); return fail(TDNA_E_ARG, "member index out of range"); }
+    KCU(cudaMemcpyAsync(d_members, hm.data(), (size_t)total * 4, cudaMemcpyHostToDevice, c->stream));
+    KCU(cudaMemcpyAsync(d_offsets, offsets, (size_t)(nclusters + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    KCU(cudaMemsetAsync(d_out, '?', (size_t)nclusters * stride, c->stream));
+    KCU(cudaMemsetAsync(d_flags, 0, (size_t)nclusters * 4, c->stream));
+    fasta::consensus_kernel<<<(unsigned)nclusters, 256, 0, c->stream>>>(a->d_sym, a->d_len, a->sym_stride, a->L, d_members, d_offsets, d_out, stride, d_len);
+    fasta::external_gaps_kernel<<<(unsigned)((nclusters * 32 + 255) / 256), 256, 0, c->stream>>>(d_out, stride, (int)stride, d_len, nclusters, d_flags);
+    c->launches += 2;
+    KCU(cudaGetLastError());
+    KCU(cudaMemcpy2DAsync(out, (size_t)row_stride, d_out, (size_t)stride, (size_t)a->L, (size_t)nclusters, cudaMemcpyDefault, c->stream));
+    KCU(cudaMemcpyAsync(out_len, d_len, (size_t)nclusters * 4, cudaMemcpyDefault, c->stream));
+    KCU(cudaStreamSynchronize(c->stream));
+#undef KCU
+    cleanup();
+    return TDNA_OK;
+}
+
 int32_t tdna_last_count_kernel(tdna_aln *a) {
     if (!a) return 0;
     return a->last_kernel;

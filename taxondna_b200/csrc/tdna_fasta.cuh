@@ -169,5 +169,35 @@ __global__ void __launch_bounds__(256) external_gaps_kernel(uint8_t *__restrict_
     }
 }
 
+// ---- consensus of a bin (Cluster.makeConsensusOfBin, SpeciesIdentifier/Cluster.java:123-138) --------------------------------
+// The reference folds Sequence.getConsensus (Common/DNA/Sequence.java:1374-1398; per column consensus(), :1008-1050) over the
+// members, re-normalising after every step.  Column by column the fold has a closed form: '?' is absorbing (a member that has
+// ended counts as '?'), letters combine as the union of their IUPAC sets, gaps of either kind give way to letters -- so the result
+// is '?' if any member has '?' there, else the code of the union if any member has a letter, else a gap; which gap ('-' or
+// '_') is decided by the final normalisation alone (external_gaps_kernel).  One CTA per bin, threads over columns.
+__global__ void __launch_bounds__(256) consensus_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len, int64_t sym_stride, int L,
+                                                        const int32_t *__restrict__ members, const long long *__restrict__ offsets,
+                                                        uint8_t *__restrict__ out, int64_t out_stride, int *__restrict__ out_len) {
+    // IUPAC code of a set of bases, bits A C G T as in the pack kernel's table (getcode, Sequence.java:1149-1196, with its A C T G bits)
+    const char code[16] = {'-', 'A', 'C', 'M', 'G', 'R', 'S', 'V', 'T', 'W', 'Y', 'H', 'K', 'D', 'B', 'N'};
+    const long long b = offsets[blockIdx.x], e = offsets[blockIdx.x + 1];
+    int maxlen = 0;
+    for (long long k = b; k < e; k++) maxlen = max(maxlen, min(len[members[k]], L));
+    if (threadIdx.x == 0) out_len[blockIdx.x] = maxlen;
+    uint8_t *dst = out + (int64_t)blockIdx.x * out_stride;
+    for (int col = threadIdx.x; col < maxlen; col += 256) {
+        bool missing = false;
+        uint32_t bases = 0;
+        for (long long k = b; k < e; k++) {
+            const int row = members[k];
+            if (col >= len[row]) { missing = true; break; }
+            const uint8_t ch = sym[(int64_t)row * sym_stride + col];
+            if (ch == '?') { missing = true; break; }
+            bases |= c_symlut[ch] & 15u;
+        }
+        dst[col] = missing ? (uint8_t)'?' : (uint8_t)code[bases];
+    }
+}
+
 }  // namespace fasta
 }  // namespace tdna

@@ -175,6 +175,11 @@ PYBIND11_MODULE(_host, m) {
         .def("setThreshold", &Cluster::setThreshold)
         .def("run", [](Cluster &c) { c.run(nullptr); })
         .def("clusters", &Cluster::clusters)
+        .def("consensusSequences", [](const Cluster &c) {
+            std::vector<py::bytes> out;
+            for (auto &s : c.consensusSequences()) out.emplace_back(s);
+            return out;
+        })
         .def("stats", &Cluster::stats);
 
     py::class_<ExtremePairwise>(m, "ExtremePairwise")

@@ -292,6 +292,7 @@ DistanceEngine::DistanceEngine(const SequenceList &list) {
     int L;
     packSymbols(ptrs, sym, len, L);
     ck(tdna_alignment_create(context(), sym.data(), n_, L, L, len.data(), &aln_));
+    width_ = L;
     // labels: ids of species / genus strings, ranks of epithets and full names under String.compareTo
     std::map<std::string, int> spIds, genIds;
     std::vector<int32_t> genus(n_), epi(n_), full(n_);
@@ -362,6 +363,21 @@ void DistanceEngine::queryDistances(const Sequence &query, std::vector<double> &
     if (shared) shared->resize(n_);
     const std::string &raw = query.getSequenceRaw();
     ck(tdna_query_distances(aln_, reinterpret_cast<const uint8_t *>(raw.data()), (int32_t)raw.size(), d.data(), shared ? shared->data() : nullptr, nullptr));
+}
+std::vector<std::string> DistanceEngine::consensus(const std::vector<std::vector<int>> &bins) const {
+    std::vector<std::string> out;
+    if (bins.empty()) return out;
+    std::vector<int32_t> members;
+    std::vector<int64_t> offsets(1, 0);
+    for (auto &b : bins) {
+        for (int m : b) members.push_back(m);
+        offsets.push_back((int64_t)members.size());
+    }
+    std::vector<uint8_t> buf((size_t)bins.size() * width_);
+    std::vector<int32_t> lens(bins.size());
+    ck(tdna_consensus(aln_, members.data(), offsets.data(), (int64_t)bins.size(), buf.data(), width_, lens.data()));
+    for (size_t k = 0; k < bins.size(); k++) out.emplace_back(reinterpret_cast<const char *>(buf.data() + k * width_), (size_t)lens[k]);
+    return out;
 }
 std::vector<double> DistanceEngine::matrix() const {
     syncConfig();
@@ -1691,6 +1707,10 @@ std::string DistanceAnalysis::run(DelayCallback *delay) {
     }
     if (delay) delay->end();
     return buff;
+}
+
+std::vector<std::string> Cluster::consensusSequences() const {
+    return list_->engine().consensus(clusters_);
 }
 
 }  // namespace taxondna

@@ -169,6 +169,8 @@ class DistanceEngine {
     std::vector<double> pairs(const std::vector<int32_t> &ii, const std::vector<int32_t> &jj) const;  // one launch for a pair list
     void edgesBelow(double t, std::vector<int32_t> &ii, std::vector<int32_t> &jj, std::vector<double> &d) const;
     std::vector<uint8_t> validConspecifics() const;
+    // consensus sequence (normalised alphabet) of every bin of list positions: one launch (tdna_consensus)
+    std::vector<std::string> consensus(const std::vector<std::vector<int>> &bins) const;
     const std::vector<int32_t> &speciesId() const { return species_id_; }
     static tdna_ctx *context();  // process-wide, device from $TDNA_DEVICE (default 0)
     static int64_t launchCount();
@@ -177,6 +179,7 @@ class DistanceEngine {
   private:
     tdna_aln *aln_ = nullptr;
     int64_t n_ = 0;
+    int64_t width_ = 0;  // columns of the alignment (the longest sequence)
     uint64_t gen_ = 0;
     std::vector<int32_t> species_id_;
     mutable int cfg_mode_ = -1, cfg_overlap_ = -1, cfg_ambig_ = -1;
@@ -330,6 +333,8 @@ class Cluster {
     void setThreshold(double percent) { max_pairwise_ = percent / 100.0; }
     void run(DelayCallback *delay = nullptr);
     const std::vector<std::vector<int>> &clusters() const { return clusters_; }  // list positions, reference order
+    // Cluster.makeConsensusOfBin (:123-138) for every cluster: the raw (normalised-alphabet) consensus sequences
+    std::vector<std::string> consensusSequences() const;
     const std::vector<Stat> &stats() const { return stats_; }
 
   private:

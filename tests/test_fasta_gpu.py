@@ -181,3 +181,46 @@ def test_large_synthetic_file(ctx):
     a.close()
     b.close()
     f.close()
+
+
+def test_consensus_of_bins_equals_the_reference_fold(ctx):
+    """tdna_consensus (a column-wise closed form) against the reference's own procedure: the left fold of Sequence.getConsensus with
+    a re-normalisation after every step (Cluster.java:123-138), on rows with gaps, external gaps, '?', ambiguity letters and
+    unequal lengths; bins of one to forty members."""
+    import taxondna_b200 as t
+    from oracle import consumers as C
+    rng = np.random.default_rng(77)
+    n, L = 160, 240
+    alphabet = np.frombuffer(b"ACGTACGTACGTACGTRYKMSWBDHVN---??", dtype=np.uint8)
+    base = alphabet[rng.integers(0, 16, size=L)]
+    raws = []
+    for i in range(n):
+        row = base.copy()
+        m = rng.random(L) < 0.15
+        row[m] = alphabet[rng.integers(0, len(alphabet), size=int(m.sum()))]
+        k0, k1 = int(rng.integers(0, 30)), int(rng.integers(0, 30))
+        if i % 3 == 0:
+            row[:k0] = ord("-")
+        if i % 4 == 0:
+            row[L - k1:] = ord("-")
+        if i % 5 == 0:
+            row[:k0 // 2] = ord("?")
+        ln = L if i % 7 else int(rng.integers(L // 2, L))
+        raws.append(row[:ln].tobytes().decode())
+    seqs = [oracle.normalise(r) for r in raws]
+    rows, lens = oracle.pack_rows(seqs)
+    aln = t.Alignment(ctx, rows, lens)
+    bins = [[int(i)] for i in (0, 5, 21)]
+    for size in (2, 3, 7, 40):
+        for _ in range(6):
+            bins.append([int(x) for x in rng.choice(n, size=size, replace=False)])
+    bins.append(list(range(n)))
+    out, out_len = aln.consensus(bins)
+    for k, b in enumerate(bins):
+        ref = C.consensus_of_bin([seqs[i] for i in b])
+        assert out_len[k] == len(ref), (k, b)
+        assert out[k, :len(ref)].tobytes() == ref, (k, b, out[k, :len(ref)].tobytes()[:60], ref[:60])
+        assert (out[k, len(ref):] == ord("?")).all()
+    with pytest.raises(t.TdnaError):
+        aln.consensus([[0, n]])
+    aln.close()

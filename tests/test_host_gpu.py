@@ -175,6 +175,7 @@ def run_all_consumers(H, text, mode, overlap, threshold=3.0, expect_host_rows=No
     cl.setThreshold(threshold)
     cl.run()
     assert cl.clusters() == oc
+    assert cl.consensusSequences() == [C.consensus_of_bin([oseqs[i].seq for i in b]) for b in oc]  # Cluster.makeConsensusOfBin
     for s, e in zip(cl.stats(), ostats):
         assert (s.size, s.valid_comparisons, s.valid_comparisons_over) == (e["size"], e["valid"], e["over"])
         assert s.largest_pairwise == e["largest"] and s.percentage == e["pct"]
