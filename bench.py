@@ -63,8 +63,9 @@ def parse():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons while the timed region runs (B200_PROFILING.md recipe): NVML polled every 2 ms from a thread
-    (the region is tens of milliseconds; nvidia-smi -lms 100 would see it twice), nvidia-smi when NVML is unavailable."""
+    """SM clock + throttle reasons while the timed region runs (B200_PROFILING.md recipe): NVML polled every 10 ms from a thread
+    (the region is tens of milliseconds; nvidia-smi -lms 100 would see it twice -- and a 2 ms period cost the multi-rank step 6 %
+    through the interpreter lock), nvidia-smi when NVML is unavailable."""
 
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
@@ -110,7 +111,7 @@ class ClockSampler:
                     self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            time.sleep(0.010)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -122,7 +123,7 @@ class ClockSampler:
             self.thread.join(timeout=1)
             reasons = sorted(name for bit, name in self.REASONS if self.bits & bit)
             return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                    "samples": len(self.samples), "source": "nvml, 2 ms period"}
+                    "samples": len(self.samples), "source": "nvml, 10 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -405,6 +406,11 @@ def main():
     for _ in range(args.steps):
         flush.fill_(1)  # L2 flush between timed iterations (on torch's stream; joined below)
         torch.cuda.synchronize()
+        if world > 1:
+            # the untimed flush ends at different moments on different ranks; without this the ranks that finish it first would time
+            # their wait for the others inside the step's first collective
+            dist.barrier()
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
