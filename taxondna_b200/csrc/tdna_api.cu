@@ -599,15 +599,28 @@ static int build_seed_list(tdna_aln *a) {
     const std::vector<int32_t> &sp = a->h_species;
     if ((int64_t)sp.size() != n) return fail(TDNA_E_STATE, "labels are not set");
     const int64_t nblk = (n + tc::N - 1) / tc::N;
-    // nearest named row of each id parity at or before / at or after every row
-    std::vector<int32_t> prev[2], next[2];
-    for (int m = 0; m < 2; m++) {
-        prev[m].assign((size_t)n, -1);
-        next[m].assign((size_t)n, -1);
-        int32_t last = -1;
-        for (int64_t i = 0; i < n; i++) { if (sp[i] >= 0 && (sp[i] & 1) == m) last = (int32_t)i; prev[m][i] = last; }
-        last = -1;
-        for (int64_t i = n - 1; i >= 0; i--) { if (sp[i] >= 0 && (sp[i] & 1) == m) last = (int32_t)i; next[m][i] = last; }
+    // per block and id parity: does the block hold a named row of that parity; the nearest such row before / after the block
+    // (two passes over the labels, O(blocks) memory: this runs once per alignment and is part of the host-buffer path)
+    std::vector<int32_t> before[2], after[2];
+    std::vector<uint8_t> has[2];
+    for (int m = 0; m < 2; m++) { before[m].assign((size_t)nblk, -1); after[m].assign((size_t)nblk, -1); has[m].assign((size_t)nblk, 0); }
+    {
+        int32_t last[2] = {-1, -1};
+        for (int64_t u = 0; u < nblk; u++) {
+            before[0][u] = last[0];
+            before[1][u] = last[1];
+            const int64_t c0 = u * tc::N, c1 = std::min<int64_t>(n, c0 + tc::N);
+            for (int64_t i = c0; i < c1; i++)
+                if (sp[i] >= 0) { last[sp[i] & 1] = (int32_t)i; has[sp[i] & 1][u] = 1; }
+        }
+        int32_t nxt[2] = {-1, -1};
+        for (int64_t u = nblk - 1; u >= 0; u--) {
+            after[0][u] = nxt[0];
+            after[1][u] = nxt[1];
+            const int64_t c0 = u * tc::N, c1 = std::min<int64_t>(n, c0 + tc::N);
+            for (int64_t i = c1 - 1; i >= c0; i--)
+                if (sp[i] >= 0) nxt[sp[i] & 1] = (int32_t)i;
+        }
     }
     std::vector<int2> list;
     list.reserve((size_t)nblk * 2);
@@ -624,8 +637,8 @@ static int build_seed_list(tdna_aln *a) {
             if (ne < 4) extra[ne++] = b;
         };
         for (int m = 0; m < 2; m++) {
-            if (next[m][c0] >= 0 && next[m][c0] < c1) continue;  // the block has a species of this parity
-            const int64_t l = c0 > 0 ? prev[m][c0 - 1] : -1, r = c1 < n ? next[m][c1] : -1;
+            if (has[m][u]) continue;  // the block has a species of this parity
+            const int64_t l = before[m][u], r = after[m][u];
             if (l >= 0 && (r < 0 || c0 - l <= r - (c1 - 1))) add(l); else if (r >= 0) add(r);
         }
         // rows at the block's edges whose conspecific neighbours are all across the edge (lists sorted by name: adjacent rows)
