@@ -314,6 +314,10 @@ int32_t tdna_cancel(tdna_ctx *ctx);
  * context's stream). */
 int32_t tdna_time_matrix_kernel(tdna_aln *aln, int32_t reps, float *ms_per_launch);
 /* TDNA_KERNEL_POPC / TDNA_KERNEL_TENSOR: which count kernel the alignment's most recent streaming pass ran on (0: none yet). */
+/* The integer code count kernel (b) uses for L columns and `dims` symbol dimensions: code[0..3] = a, b, c, d with
+ * a*c = -(W-1), a*d + b*c + dims*b*d = W, all operand entries within int8, W the smallest usable power of two above L -- so that a
+ * row symbol x and a column symbol y contribute W - (W-1)[x == y] to the int32 accumulator.  Host arithmetic only (no device). */
+int32_t tdna_tensor_code(int32_t L, int32_t dims, int32_t *code, uint32_t *W);
 int32_t tdna_last_count_kernel(tdna_aln *aln);
 /* Device time (CUDA events on the context's stream) of the most recent count-tile pass -- the tile
  * kernel launch(es) of the last matrix band or streaming pass; waits for it to finish. */

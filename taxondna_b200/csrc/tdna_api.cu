@@ -2189,6 +2189,18 @@ int32_t tdna_consensus(tdna_aln *a, const int32_t *members, const int64_t *offse
     return TDNA_OK;
 }
 
+// The integer code of count kernel (b) for an alignment of L columns and `dims` symbol dimensions: code[0..3] = a, b, c, d and the
+// power of two W.  Pure host arithmetic (no device needed): the CPU tests check its algebra.
+int32_t tdna_tensor_code(int32_t L, int32_t dims, int32_t *code, uint32_t *W) {
+    if (L < 1 || dims < 1 || !code || !W) return fail(TDNA_E_ARG, "bad argument");
+    tc::EncodeValues v = {};
+    uint32_t w = 0;
+    if (!find_code(L, dims, v, w)) return fail(TDNA_E_STATE, "no code with int8 entries for this width and dimension count");
+    code[0] = v.a; code[1] = v.b; code[2] = v.c; code[3] = v.d;
+    *W = w;
+    return TDNA_OK;
+}
+
 int32_t tdna_last_count_kernel(tdna_aln *a) {
     if (!a) return 0;
     return a->last_kernel;
