@@ -55,3 +55,14 @@ def test_host_layer_loads_and_refuses_to_compute_without_a_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(H.EngineError):
             a.getPairwise(b)
+
+
+def test_rows_per_part_is_pure_host_arithmetic():
+    """Owner-of-row arithmetic of the routed multi-GPU merge: slices are multiples of 128 rows and cover the list."""
+    import taxondna_b200 as t
+    lib = t.load()
+    for n in (1, 127, 128, 129, 2185, 50000, 141500, 1000000):
+        for parts in (1, 2, 3, 4, 8, 64):
+            rpp = lib.tdna_rows_per_part(n, parts)
+            assert rpp % 128 == 0 and rpp * parts >= n and (rpp - 128) * parts < n + 128 * parts
+    assert lib.tdna_rows_per_part(0, 4) == 0
