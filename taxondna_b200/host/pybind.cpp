@@ -71,6 +71,12 @@ PYBIND11_MODULE(_host, m) {
         .def(py::init<const std::vector<SequencePtr> &>())
         .def_static("readFasta", &SequenceList::readFasta)
         .def_static("fromFastaText", &SequenceList::fromFastaText)
+        .def_static("fromFastaTextOnDevice", &SequenceList::fromFastaTextOnDevice)
+        .def("rawSequences", [](const SequenceList &l) {
+            std::vector<py::bytes> v;
+            for (auto &s : l.sequences()) v.emplace_back(s->getSequenceRaw());
+            return v;
+        })
         .def_readonly_static("SORT_BYNAME", &SequenceList::SORT_BYNAME)
         .def("add", &SequenceList::add)
         .def("count", &SequenceList::count)

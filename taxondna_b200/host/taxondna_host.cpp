@@ -128,6 +128,12 @@ Sequence::Sequence(const std::string &name, const std::string &seq) {
     changeSequence(trim(up));
 }
 
+Sequence::Sequence(const std::string &name, const std::string &seq, Normalised) {
+    changeName(name);
+    seq_ = seq;
+    id_ = g_nextId++;
+}
+
 void Sequence::changeName(const std::string &nameIn) {
     static const std::regex p3("([A-Z][a-z]+) ([a-z]+) ([a-z]+)\\b"), p2("([A-Z][a-z]+) ([a-z]+)\\b"),
         psp("([A-Z][a-z]+) ([a-z]+)\\.\\b"), pgi("gi\\|([0-9]+)[\\|:]"), pfam("\\(family:\\s*([A-Za-z]+)\\s*\\)");
@@ -537,6 +543,32 @@ SequenceList SequenceList::fromFastaText(const std::string &text) {
         } else seq += trim(line);
     }
     flush();
+    out.modified();
+    return out;
+}
+SequenceList SequenceList::fromFastaTextOnDevice(const std::string &text) {
+    tdna_fasta *f = nullptr;
+    ck(tdna_fasta_parse(DistanceEngine::context(), reinterpret_cast<const uint8_t *>(text.data()), (int64_t)text.size(), &f));
+    struct Guard { tdna_fasta *f; ~Guard() { tdna_fasta_destroy(f); } } guard{f};
+    const int64_t n = tdna_fasta_count(f);
+    const int32_t width = tdna_fasta_width(f);
+    std::vector<int64_t> off((size_t)n);
+    std::vector<int32_t> hlen((size_t)n), slen((size_t)n), flags((size_t)n);
+    ck(tdna_fasta_records(f, off.data(), hlen.data(), slen.data(), flags.data()));
+    for (int32_t fl : flags)
+        if (fl & (TDNA_FASTA_INVALID | TDNA_FASTA_NEEDS_HOST)) return fromFastaText(text);  // the host path words the errors / expands the groups
+    std::vector<uint8_t> sym((size_t)n * std::max(width, 1));
+    if (n > 0 && width > 0) ck(tdna_fasta_symbols(f, sym.data(), width));
+    SequenceList out;
+    for (int64_t r = 0; r < n; r++) {
+        std::string nm = text.substr((size_t)off[r], (size_t)hlen[r]);  // after '>' up to the line end: "^>\\s*(.+)\\s*$" keeps trailing blanks
+        size_t a = nm.find_first_not_of(" \t\f\v\r\n");
+        nm = a == std::string::npos ? "" : nm.substr(a);
+        if (nm.empty()) nm = "No name specified in file";
+        std::replace(nm.begin(), nm.end(), '_', ' ');  // makeSequence (FastaFile.java:268-270)
+        out.seqs_.push_back(std::make_shared<Sequence>(nm, std::string(reinterpret_cast<const char *>(sym.data() + (size_t)r * width), (size_t)slen[r]),
+                                                       Sequence::Normalised{}));
+    }
     out.modified();
     return out;
 }

@@ -76,6 +76,8 @@ class Sequence {
     static void clearPairwiseCache();  // :1606-1611 (no cache exists here; kept for the API)
 
     Sequence(const std::string &name, const std::string &seq);  // :163-166; throws SequenceException
+    struct Normalised {};                                        // tag: `seq` is already in the normalised alphabet (device parser)
+    Sequence(const std::string &name, const std::string &seq, Normalised);
     void changeName(const std::string &name);                   // :668-742
     void changeSequence(const std::string &seq);                // :751-853
 
@@ -134,6 +136,10 @@ class SequenceList {
     explicit SequenceList(const std::vector<SequencePtr> &v) : seqs_(v) { modified(); }
     static SequenceList readFasta(const std::string &path);   // formats/FastaFile.java:144-289
     static SequenceList fromFastaText(const std::string &text);
+    // the same list through the device parser (tdna_fasta_parse: record structure and alphabet normalisation as byte-parallel
+    // kernels; names are parsed here from the header spans).  Files with "[AG]" groups or invalid symbols take the host path, which
+    // reports them the reference's way.
+    static SequenceList fromFastaTextOnDevice(const std::string &text);
     void add(const SequencePtr &s) { seqs_.push_back(s); modified(); }
     int count() const { return (int)seqs_.size(); }
     const SequencePtr &get(int i) const { return seqs_.at(i); }

@@ -232,3 +232,15 @@ def test_generation_order_is_byname_order(H):
     lst.resort(H.SequenceList.SORT_BYNAME)
     assert lst.names() == before
     assert lst.speciesIds() == d["species_id"].tolist()
+
+
+def test_fasta_through_the_device_parser_gives_the_same_list(H, golden_dir):
+    """SequenceList.fromFastaTextOnDevice == fromFastaText: names, normalised sequences, and a file with a "[AG]" group (host path)."""
+    for text in (gzip.open(os.path.join(golden_dir, "diptera_coi.fasta.gz"), "rt", encoding="latin-1").read(),
+                 synth_fasta("C3", genera=4, species=3, reps=5)[0],
+                 ">Aus bus gi|1|\nAC[AG]TAC-T\n>Aus_cus gi|2|\r\n--acgu acgt??\r\n"):
+        a = H.SequenceList.fromFastaText(text)
+        b = H.SequenceList.fromFastaTextOnDevice(text)
+        assert a.count() == b.count() and a.names() == b.names()
+        assert a.rawSequences() == b.rawSequences()
+
