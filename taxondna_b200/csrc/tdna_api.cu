@@ -207,10 +207,10 @@ template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int 
 template <int KM, int CN, int EPI> int launch_kernel(tdna_ctx *c, const TileParams &p) {
     using Cfg = TileCfg<KM, CN>;
     auto kern = count_tile_kernel<KM, CN, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // per device: function attributes live in the device's context (one process may drive several)
+    if (!attr_set[c->device & 63]) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
+        attr_set[c->device & 63] = true;
     }
     int64_t slots = (int64_t)c->sm_count * Cfg::MIN_CTAS;
     int64_t grid = p.num_tiles < slots ? p.num_tiles : slots;
@@ -665,11 +665,11 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     if constexpr (!COUNTS_MODE) {
         if (general) kern = tc::tile_kernel<COUNTS_MODE, CL, true>;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // per device (see launch_kernel)
+    if (!attr_set[c->device & 63]) {
         CU(cudaFuncSetAttribute(tc::tile_kernel<COUNTS_MODE, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
         if constexpr (!COUNTS_MODE) CU(cudaFuncSetAttribute(tc::tile_kernel<COUNTS_MODE, CL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM));
-        attr_set = true;
+        attr_set[c->device & 63] = true;
     }
     tc::Params p = {};
     p.A = a->d_tcA;
