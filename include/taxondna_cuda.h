@@ -93,7 +93,10 @@ enum { TDNA_PD_INTRA = 0, TDNA_PD_INTER = 1 };
 
 /* ---- lifetime ------------------------------------------------------------------------- */
 int32_t tdna_abi_version(void);
-/* Creates the context for CUDA device `device` (one per process in the torchrun layout). */
+/* Creates the context for CUDA device `device` (one per process in the torchrun layout).
+ * Threading (the reference runs one analysis at a time under SequenceList's static lock, SequenceList.java:403-440): calls may come
+ * from any thread; calls on ONE context are serialised by the caller; contexts on DIFFERENT devices are independent.  Use one
+ * context per device and process: the streaming passes keep their parameters in per-device constant memory. */
 int32_t tdna_init(int32_t device, tdna_ctx **out);
 int32_t tdna_shutdown(tdna_ctx *ctx);
 const char *tdna_last_error(void);
