@@ -98,3 +98,59 @@ def test_small_end_to_end_consumers_run():
         assert intra.count_valid() == 6 * 6 and inter.count_valid() == 2 * 3 * 16
         clusters, stats = C.cluster(D, 0.03)
         assert sorted(x for c in clusters for x in c) == list(range(24))
+
+
+HAND = (">gi|1| Aus bus\nAAAAAAAAAA\n>gi|2| Aus bus\nAAAAAAAAAC\n>gi|3| Aus cus\nAAAAAACCCC\n>gi|4| Bus dus\nCCCCCCCCCC\n")
+
+
+def hand_list():
+    seqs = C.sort_by_name(C.read_fasta_text(HAND))
+    assert [s.species_name() for s in seqs] == ["Aus bus", "Aus bus", "Aus cus", "Bus dus"]
+    return seqs, C.Dist(seqs, C.Config(PDM_UNCORRECTED, 5, True))
+
+
+def test_extreme_pairwise_by_hand():
+    # d(A1,A2) = 0.1, d(A1,B1) = 0.4, d(A2,B1) = 0.3, everything to C1 = 0.6 .. 1.0 (another genus: never "congeneric")
+    seqs, D = hand_list()
+    assert [D.pairwise(0, 1), D.pairwise(0, 2), D.pairwise(1, 2)] == [1.0 - 9 / 10, 1.0 - 6 / 10, 1.0 - 7 / 10]
+    text, recs = C.extreme_pairwise(D)
+    assert recs == [(1, 2), (0, 2), (None, 1), (None, None)]
+    lines = text.split("\n")
+    assert lines[0].startswith("Sequence name\tLargest conspecific match\tDistance\tOverlap\t")
+    # 1.0 - 9/10 is 0.09999999999999998 and Settings.percentage truncates (Settings.java:69-87): 9.99, not 10.0
+    assert lines[1] == "Aus bus (gi:1)\tAus bus (gi:2)\t9.99\t10\tAus cus (gi:3)\t40.0\t10\t"
+    assert lines[3] == "Aus cus (gi:3)\tNo matching conspecific sequence\tN/A\tN/A\tAus bus (gi:2)\t30.0\t10\t"
+    assert lines[4] == "Bus dus (gi:4)\tNo matching conspecific sequence\tN/A\tN/A\tNo matching congeneric, interspecific sequence\tN/A\tN/A\t"
+
+
+def test_distance_analysis_by_hand():
+    # per sequence (smallest, mean) congeneric allospecific: A1 (.4, .4), A2 (.3, .3), B1 (.3, .35); species means: bus (.35, .35),
+    # cus (.3, .35); genus Aus: smallest (.35 + .3) / 2, mean .35; genus Bus has no comparison: the mean of nothing is NaN, NaN < 0 is
+    # false, and Settings.percentage turns NaN into 0.0 ((long) NaN == 0)
+    _, D = hand_list()
+    text, rows = C.distance_analysis(D)
+    assert abs(rows["Aus"][0] - 0.325) < 1e-12 and abs(rows["Aus"][1] - 0.35) < 1e-12
+    assert text == "Genus\t\t\tAvg. Avg. Smallest Inter\t\tAvg. Avg. Avg. Inter\nAus\t\t\t32.5\t\t35.0\nBus\t\t\t0.0\t\t0.0\n"
+
+
+def test_pairwise_explorer_and_query_by_hand():
+    seqs, D = hand_list()
+    cats = C.pairwise_explorer(D, C.PD_INTRA)  # the one conspecific pair, pushed from both sides, d = 0.1 = "9.5% to 10.0%"
+    assert [k for k, _ in cats] == ["9.5% to 10.0% (2 matches)", "Averages"]
+    # Aus bus x Aus cus: 0.4 and 0.30000000000000004, both directions -- and the latter falls BETWEEN two categories, whose bounds
+    # are (x/1000 + 0.000001, (x+5)/1000] (PairwiseExplorer.java:163-165): the reference lists it nowhere
+    cats = C.pairwise_explorer(D, C.PD_INTER)
+    assert [k for k, _ in cats] == ["39.5% to 40.0% (2 matches)", "Averages"]
+    lines, pos = C.query_sequence(seqs, C.Config(PDM_UNCORRECTED, 5, True), "aaaaa aaaac\n")
+    assert pos == [1, 0, 2, 3]
+    assert lines[0] == "(0.0000%) Aus bus (gi:2)" and lines[1] == "(10.0000%) Aus bus (gi:1)" and lines[2].startswith("(30.0000%) Aus cus")
+
+
+def test_consensus_by_hand():
+    n = C.normalise
+    assert C.get_consensus(n("ACGT"), n("ACGA")) == b"ACGW"          # T | A = W
+    assert C.get_consensus(n("AC-T"), n("ACGT")) == b"ACGT"          # a gap gives way to a letter
+    assert C.get_consensus(n("A?GT"), n("ACGT")) == b"A?GT"          # missing data is absorbing
+    assert C.get_consensus(n("--GT"), n("-CGT")) == b"_CGT"          # external gaps: '_' only where both are gaps
+    assert C.get_consensus(n("ACGT"), n("AC")) == b"AC??"            # the shorter sequence has ended: '?'
+    assert C.consensus_of_bin([n("AAAA"), n("CAAA"), n("GAAA"), n("TAA-")]) == b"NAAA"
