@@ -237,6 +237,11 @@ def exchange_parts(torch, dist, dev, part, n, world):
 
 def main():
     args = parse()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl != "reference":
+        # asked for N GPUs outside torchrun: become the launch the driver uses (one rank per GPU over NCCL, rendezvous on 127.0.0.1)
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 500),
+                                   os.path.abspath(__file__)] + sys.argv[1:])
     # the contract is ONE JSON line on stdout: keep the real stdout for it and send everything else
     # (NCCL's version banner, library chatter) to stderr
     global _OUT
