@@ -244,3 +244,32 @@ def test_fasta_through_the_device_parser_gives_the_same_list(H, golden_dir):
         assert a.count() == b.count() and a.names() == b.names()
         assert a.rawSequences() == b.rawSequences()
 
+
+@pytest.mark.parametrize("mode,key", [(0, "p"), (1, "k2p")])
+def test_reports_hash_to_the_committed_digests(H, golden_dir, mode, key):
+    """No oracle in the loop: the host layer's report text on the reference's small Diptera fixture against
+    tests/golden/consumer_digests.json (generated by tests/golden/make_consumer_digests.py)."""
+    import hashlib
+    import json
+    want = json.load(open(os.path.join(golden_dir, "consumer_digests.json")))["diptera_small_nogaps"][key]
+    text = gzip.open(os.path.join(golden_dir, "diptera_small_nogaps.fasta.gz"), "rt", encoding="latin-1").read()
+    configure(H, mode, 300)
+    lst = H.SequenceList.fromFastaText(text)
+    lst.resort(H.SequenceList.SORT_BYNAME)
+    assert lst.count() == want["n"]
+    sha = lambda s: hashlib.sha256(s.encode("utf-8")).hexdigest()  # noqa: E731
+    bm = H.BestMatch(lst)
+    bm.setThreshold(3.0)
+    assert sha(bm.run()) == want["best_match"]
+    ba = H.BlockAnalysis(lst)
+    ba.setThreshold(3.0)
+    assert sha(ba.run()) == want["block_analysis"]
+    assert sha(H.PairwiseSummary(lst).run()) == want["pairwise_summary"]
+    assert sha(H.ExtremePairwise(lst).run()) == want["extreme_pairwise"]
+    if want["distance_analysis"] != "NullPointerException":
+        assert sha(H.DistanceAnalysis(lst).run()) == want["distance_analysis"]
+    cl = H.Cluster(lst)
+    cl.setThreshold(3.0)
+    cl.run()
+    assert sha(json.dumps(cl.clusters())) == want["cluster"]
+

@@ -154,3 +154,18 @@ def test_consensus_by_hand():
     assert C.get_consensus(n("--GT"), n("-CGT")) == b"_CGT"          # external gaps: '_' only where both are gaps
     assert C.get_consensus(n("ACGT"), n("AC")) == b"AC??"            # the shorter sequence has ended: '?'
     assert C.consensus_of_bin([n("AAAA"), n("CAAA"), n("GAAA"), n("TAA-")]) == b"NAAA"
+
+
+def test_consumer_digests_of_the_reference_fixture(golden_dir):
+    """The report text of every restated module on the reference's small Diptera fixture hashes to the committed digests
+    (tests/golden/make_consumer_digests.py): the oracle does not drift, and the GPU host layer is held to the same bytes."""
+    import gzip
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_consumer_digests", os.path.join(golden_dir, "make_consumer_digests.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(golden_dir, "consumer_digests.json")))["diptera_small_nogaps"]
+    text = gzip.open(os.path.join(golden_dir, "diptera_small_nogaps.fasta.gz"), "rt", encoding="latin-1").read()
+    assert mod.digests(text, PDM_UNCORRECTED) == want["p"]
+    assert mod.digests(text, PDM_K2P) == want["k2p"]
