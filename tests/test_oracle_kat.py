@@ -154,3 +154,28 @@ def test_k2p_formula_and_edges():
     assert lib.tdo_shared_length(b"NNAA", 4, b"NNAA", 4, PDM_K2P) == 4
     lib.tdo_k2p(b"NNAA", 4, b"NNAA", 4, n, ts, tv)
     assert n.value == 2
+
+
+def test_oracle_reproduces_the_committed_fixture_checksums(golden_dir):
+    """tests/golden/checksums.json (make_golden.py; the figures SURVEY.md Appendix B got from an independent numpy restatement):
+    the C oracle still produces them on the reference's small Diptera fixture, in all three modes."""
+    import hashlib
+    import json
+    import os
+
+    import numpy as np
+
+    from oracle import consumers as C
+    want = json.load(open(os.path.join(golden_dir, "checksums.json")))["diptera_small_nogaps"]
+    seqs = C.read_fasta(os.path.join(golden_dir, "diptera_small_nogaps.fasta.gz"))
+    rows, lens = oracle.pack_rows([s.seq for s in seqs])
+    assert (len(seqs), int(rows.shape[1])) == (want["n"], want["L"])
+    iu = np.triu_indices(len(seqs), 1)
+    for mode, nm in ((0, "p"), (1, "k2p"), (2, "trans")):
+        r = oracle.all_pairs(rows, lens, mode, 300, True, threads=8)
+        d = r["dist"][iu]
+        got = {"sum_shared": int(r["shared"][iu].sum()), "sum_c1": int(r["c1"][iu].sum()), "sum_c2": int(r["c2"][iu].sum()),
+               "sum_c3": int(r["c3"][iu].sum()), "valid_pairs": int((~(d < 0)).sum()), "exact_zero": int((d == 0).sum()),
+               "nan": int(np.isnan(d).sum()), "sha256_dist_upper": hashlib.sha256(np.ascontiguousarray(d).tobytes()).hexdigest()}
+        for k, v in got.items():
+            assert want[nm][k] == v, (nm, k)
