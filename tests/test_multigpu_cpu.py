@@ -80,3 +80,64 @@ def test_three_rank_exchange_with_an_empty_rank(tmp_path):
     np.save(os.path.join(tmp_path, "full.npy"), rng.integers(0, 256, size=(n, 120), dtype=np.uint8))
     port = 31500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+
+
+def _routed_worker(rank, world, port, n, seg):
+    """The torch.distributed calls of bench.py's routed exchange, on gloo, with numpy standing in for the library: records are
+    bucketed by the rank that owns their row (owner = row // rows_per_part), one equal segment per destination travels through
+    all_to_all_single, the per-row state is SUM-reduced, every rank finalises its own rows and the slices are all-gathered."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rpp = -(-(-(-n // world)) // 128) * 128  # tdna_rows_per_part: ceil(n / world) rounded up to 128
+    assert rpp * world >= n
+    # every rank's records (row, col, d): what its share of the tiles would have emitted
+    per_rank = []
+    for r in range(world):
+        g = np.random.default_rng(500 + r)
+        k = 40 + 17 * r
+        per_rank.append((g.integers(0, n, size=k), g.integers(0, n, size=k), g.random(k), g.integers(0, 3, size=n)))
+    rows, cols, d, st = per_rank[rank]
+    rec = torch.zeros((world, seg, 2), dtype=torch.int64)
+    counts = torch.zeros(world, dtype=torch.int64)
+    for q, j, dd in zip(rows, cols, d):  # tdna_best_match_part_routed: segment = owner of the row
+        dest = int(q) // rpp
+        pos = int(counts[dest])
+        rec[dest, pos, 0] = (int(q) << 32) | int(j)
+        rec[dest, pos, 1] = int(np.float64(dd).view(np.int64))
+        counts[dest] += 1
+    state = torch.from_numpy(st.astype(np.int64))
+    recv = torch.zeros_like(rec)
+    recv_counts = torch.zeros_like(counts)
+    dist.all_to_all_single(recv_counts, counts)
+    dist.all_to_all_single(recv.view(-1), rec.view(-1))
+    dist.all_reduce(state, op=dist.ReduceOp.SUM)
+    # what arrived: segment s = the records rank s had for MY rows, in rank s's order
+    q0, q1 = min(n, rank * rpp), min(n, rank * rpp + rpp)
+    got = []
+    for s in range(world):
+        for p in range(int(recv_counts[s])):
+            key, bits = int(recv[s, p, 0]), int(recv[s, p, 1])
+            got.append((key >> 32, key & 0xffffffff, bits))
+    exp = []
+    for s in range(world):
+        r_, c_, d_, _ = per_rank[s]
+        exp += [(int(q), int(j), int(np.float64(dd).view(np.int64))) for q, j, dd in zip(r_, c_, d_) if q0 <= q < q1]
+    assert got == exp
+    assert np.array_equal(state.numpy(), sum(p[3] for p in per_rank))
+    # tdna_best_match_merge_routed stand-in: one 8-byte "record" per own row = how many candidates it received
+    own = torch.zeros(rpp, dtype=torch.int64)
+    for q, _, _ in got:
+        own[q - q0] += 1
+    allrows = torch.zeros(world * rpp, dtype=torch.int64)
+    dist.all_gather_into_tensor(allrows, own)
+    want = np.zeros(n, dtype=np.int64)
+    for r_, _, _, _ in per_rank:
+        np.add.at(want, r_, 1)
+    assert np.array_equal(allrows.numpy()[:n], want) and not allrows.numpy()[n:].any()
+    dist.destroy_process_group()
+
+
+def test_routed_exchange_choreography_on_three_ranks():
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_routed_worker, args=(3, port, 700, 256), nprocs=3, join=True)
