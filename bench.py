@@ -14,16 +14,19 @@ in HBM, results left in HBM, each step timed with CUDA events on the library's s
 between steps.  `e2e`: the same work through the C ABI with HOST buffers (symbols in, results out),
 host<->device copies inside the timed region.
 
-N > 1 (torchrun, one rank per GPU): every rank holds the whole packed alignment.  Best-Match steps
-share the triangle's tile list in N contiguous slices (tdna_best_match_seed / _part_packed) and
-exchange their candidate records / per-row counts once per step over NCCL, then merge; matrix steps
-split the query rows into bands (no collective).  Weak scaling: the alignment grows as sqrt(N) so
-pairs per GPU stay fixed.
+N > 1 (torchrun, one rank per GPU): every rank holds the whole packed alignment (each uploads 1/N of the rows, the library
+all-gathers them over NVLink).  Best-Match steps are ONE library call per rank: inside it (tdna_comm_init, NCCL on the library's
+stream) the ranks take units of 128 tile slots of the triangle cyclically, all-reduce the seeded per-row minima, route the candidate
+records to the rank that owns the row, and all-gather the row records; matrix steps split the query rows into bands (no
+collective).  --scaling strong (default): the named shape itself on N GPUs; the other mode (weak: the alignment grows as sqrt(N)
+so that pairs per GPU stay fixed) is measured too and reported under an extra key.  After the timed region rank 0 recomputes the
+result on ONE GPU and compares it byte for byte with the all-gathered N-GPU result: "parity_vs_1gpu".
 
 --impl reference: the reference's CPU algorithm (oracle/ C restatement of Sequence.getPairwise --
 the reference is Java and no JVM exists in this image) on the host cores, bounded sample.
 """
 import argparse
+import ctypes
 import gc
 import json
 import os
@@ -40,10 +43,13 @@ sys.path.insert(0, ROOT)
 _OUT = sys.stdout
 
 WORKLOADS = {
-    "C2": dict(config="C2", mode=0, kind="matrix+summary", desc="2,185 x 2,664 bp synthetic multi-gene alignment, uncorrected p: full pairwise matrix + Pairwise Summary classes"),
-    "C3": dict(config="C3", mode=1, kind="bestmatch+intra", desc="8,000 x 658 bp synthetic COI, K2P: Best Close Match + intraspecific distances for the 95th-percentile threshold"),
-    "C4": dict(config="C4", mode=0, kind="matrix+summary", desc="5,000 x 2,664 bp gappy/ambiguous alignment (20% ?/-/IUPAC), uncorrected p: matrix + Pairwise Summary classes"),
-    "H": dict(config="H", mode=0, kind="bestmatch", desc="50,000 x 658 bp synthetic COI, uncorrected p: streaming per-query Best Match summaries"),
+    "C2": dict(config="C2", mode=0, kind="matrix+summary", desc="synthetic multi-gene alignment, uncorrected p: full pairwise matrix + Pairwise Summary classes"),
+    "C3": dict(config="C3", mode=1, kind="bestmatch+intra", desc="synthetic COI, K2P: Best Close Match + intraspecific distances for the 95th-percentile threshold"),
+    "C4": dict(config="C4", mode=0, kind="matrix+summary", desc="gappy/ambiguous alignment (20% ?/-/IUPAC), uncorrected p: matrix + Pairwise Summary classes"),
+    "H": dict(config="H", mode=0, kind="bestmatch", desc="synthetic COI, uncorrected p: streaming per-query Best Match summaries"),
+    # H's shape with C4's noise (8 % '?', 8 % '-', 4 % IUPAC letters): no tile is free of gaps / ambiguity letters (the GENERAL instantiation)
+    "Hg": dict(config="Hg", mode=0, kind="bestmatch", desc="synthetic COI with 20% ?/-/IUPAC noise, uncorrected p: streaming per-query Best Match summaries"),
+    "HgK": dict(config="Hg", mode=1, kind="bestmatch", desc="synthetic COI with 20% ?/-/IUPAC noise, K2P: streaming per-query Best Match summaries"),
 }
 POPC_PER_PAIR_WORD = {0: 2, 1: 4, 2: 2}  # C = 2 (p), 4 (K2P), 2 (trans-only)
 
@@ -55,7 +61,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="H", choices=sorted(WORKLOADS))
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong = the named shape itself on N GPUs (the north star's own shapes); weak = n grows as sqrt(N)")
+    ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the run of the other scaling mode (extra key)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "tensor"], help="count kernel of the streaming pass")
@@ -202,7 +210,7 @@ def run_reference(args):
         "impl": "reference", "metric": "pairwise distances/s", "value": v, "unit": "Gpairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / max(1, args.steps) * 1e3, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "int32 counts + f64 distance", "data": "synthetic",
-        "config": {"workload": wl["desc"], "n": n, "L": L, "mode": wl["mode"]},
+        "config": {"workload": "%s x %s bp: %s" % (format(n, ","), format(L, ","), wl["desc"]), "n": n, "L": L, "mode": wl["mode"]},
         "cpu_baseline": {"value": v, "unit": "Gpairs/s", "cores": threads, "kind": "port",
                          "sample": "first %d query rows x all later columns per step (%d pairs/step), C restatement of Sequence.getPairwiseNoBuffer (no JVM in image), %d pthreads" % (rows, pairs // max(1, args.steps), threads)},
         "e2e": {"value": v, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -217,22 +225,319 @@ class _DevBuf:
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
-def exchange_parts(torch, dist, dev, part, n, world):
-    """The multi-GPU exchange step of the streaming path (taxondna_b200.shard.exchange_candidates) on
-    zero-copy views of the library's device buffers."""
-    from taxondna_b200 import shard
-    k = int(part.n_cand)
-    if k:
-        rows = torch.as_tensor(_DevBuf(part.cand_row, k, "<i4"), device=dev)
-        cols = torch.as_tensor(_DevBuf(part.cand_col, k, "<i4"), device=dev)
-        d = torch.as_tensor(_DevBuf(part.cand_d, k, "<f8"), device=dev)
-    else:
-        rows = torch.zeros(0, dtype=torch.int32, device=dev)
-        cols = torch.zeros(0, dtype=torch.int32, device=dev)
-        d = torch.zeros(0, dtype=torch.float64, device=dev)
-    inval = torch.as_tensor(_DevBuf(part.invalid_count, n, "<i4"), device=dev)
-    flags = torch.as_tensor(_DevBuf(part.flags, n, "<i4"), device=dev)
-    return shard.exchange_candidates(rows, cols, d, inval, flags)
+def int8_peak_live(torch, dev):
+    """A cuBLASLt int8 GEMM (torch._int_mm, 8192^3) timed here: the tensor-pipe denominator (MEASURED_PEAKS.json has no int8 line)."""
+    a8 = torch.randint(-3, 3, (8192, 8192), dtype=torch.int8, device=dev)
+    b8 = torch.randint(-3, 3, (8192, 8192), dtype=torch.int8, device=dev)
+    for _ in range(3):
+        torch._int_mm(a8, b8)
+    best = 1e9
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch._int_mm(a8, b8)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a8, b8
+    return 2 * 8192 ** 3 / (best * 1e-3)
+
+
+class Bench:
+    """One process per GPU.  Every data-plane step of the N > 1 path happens inside the C ABI (tdna_comm_init: NCCL on the library's
+    stream); torch.distributed is the control plane only (the unique-id broadcast, barriers, the max over ranks of the timings)."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        import taxondna_b200 as t
+        self.args, self.torch, self.dist, self.t = args, torch, dist, t
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.ctx = t.Context(self.local)
+        self.ctx.set_option(t.OPT_COUNT_KERNEL, {"auto": t.KERNEL_AUTO, "popc": t.KERNEL_POPC, "tensor": t.KERNEL_TENSOR}[args.kernel])
+        if self.world > 1:
+            self.ctx.comm_init_torch(dist, self.dev)  # from here on whole-range library calls are collective over the ranks
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream_ptr(), device=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.L_ = t.load()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        tm = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(tm, op=self.dist.ReduceOp.MAX)
+        return float(tm.item())
+
+    def close(self):
+        self.flush = None
+        gc.collect()
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.ctx.comm_destroy()
+        self.ctx.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+    def measure(self, workload, scale_n=None, steps=None, warmup=None, full=True):
+        """Times `steps` steps of the workload.  full: also the roofline's live peak, the e2e leg, the parity check against one GPU
+        and (N = 1) the CPU baseline; otherwise only `value` and `e2e`."""
+        from taxondna_b200 import synth
+        torch, dist, t, args = self.torch, self.dist, self.t, self.args
+        world, rank, dev, ctx, stream, L_ = self.world, self.rank, self.dev, self.ctx, self.stream, self.L_
+        steps = steps or args.steps
+        warmup = max(warmup if warmup is not None else args.warmup, 3)
+        wl = WORKLOADS[workload]
+        mode, kind = wl["mode"], wl["kind"]
+        streaming = kind.startswith("bestmatch")
+        data = synth.generate(wl["config"], names=False, scale_n=scale_n)
+        sym = data["symbols"]
+        n, L = sym.shape
+        pairs = n * (n - 1) // 2
+        W32 = (L + 31) // 32
+        c64 = ctypes.c_int64()
+        RS = t.ROW_RESULT_DTYPE.itemsize
+        sym_pinned = torch.from_numpy(sym).pin_memory()
+        labels = [data[k] for k in ("species_id", "genus_id", "epithet_rank", "fullname_rank")]
+        aln = t.Alignment(ctx, sym_pinned.numpy())
+        aln.set_labels(*labels)
+        aln.set_config(mode, 300, True)
+
+        # how the pair space is shared between the ranks
+        #  streaming kinds: inside the library (unit-cyclic tile parts, NCCL exchange, row-sharded merge, all-gathered records)
+        #  matrix kinds:    row bands (each rank owns rows [b0, b1) x all columns); no collective
+        if world > 1 and not streaming:
+            per = -(-n // world)
+            per = -(-per // 128) * 128
+            b0, b1 = min(n, rank * per), min(n, (rank + 1) * per)
+            aln.set_row_range(b0, b1)
+        else:
+            b0, b1 = 0, n
+        rows_mine = b1 - b0
+
+        n_intra = n_inter = 0
+        if "summary" in kind or "intra" in kind:
+            io = t.Analysis()
+            io.want = t.WANT_INTRA | (t.WANT_INTER if "summary" in kind else 0)
+            t.check(L_.tdna_analyze(aln.h, ctypes.byref(io)))  # sizes of this rank's lists (they depend on the labels only)
+            n_intra, n_inter = int(io.n_intra_local), int(io.n_inter_local)
+        d_intra = torch.empty(max(1, n_intra), dtype=torch.float32, device=dev)
+        d_inter = torch.empty(max(1, n_inter), dtype=torch.float32, device=dev)
+
+        def step_device():
+            aln.set_config(mode, 300, True)  # invalidates every cached result: each step recomputes everything
+            if kind.startswith("matrix"):
+                aln.matrix_compute()
+                t.check(L_.tdna_class_distances(aln.h, t.PD_INTRA, d_intra.data_ptr(), n_intra, ctypes.byref(c64)))
+                t.check(L_.tdna_class_distances(aln.h, t.PD_INTER, d_inter.data_ptr(), n_inter, ctypes.byref(c64)))
+            elif "intra" in kind:
+                # Best Close Match + the intraspecific distances for the percentile from ONE streaming pass (N > 1: the ranks share it)
+                io = t.Analysis()
+                io.want = t.WANT_BEST_MATCH | t.WANT_INTRA
+                io.intra, io.intra_cap = d_intra.data_ptr(), n_intra
+                t.check(L_.tdna_analyze(aln.h, ctypes.byref(io)))
+            else:
+                aln.best_match_compute()  # all n row records left in HBM (on every rank)
+
+        for _ in range(warmup):
+            step_device()
+        self.barrier()
+        sampler = ClockSampler(self.local)
+        if rank == 0 and full:
+            sampler.start()
+        launches0 = ctx.launch_count()
+        step_ms, tile_ms = [], []
+        t_region0 = time.perf_counter()
+        for _ in range(steps):
+            self.flush.fill_(1)  # L2 flush between timed iterations (on torch's stream; joined below)
+            torch.cuda.synchronize()
+            if world > 1:
+                # the untimed flush ends at different moments on different ranks; without this the ranks that finish it first would
+                # time their wait for the others inside the step's first collective
+                dist.barrier()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                step_device()
+                e1.record(stream)
+            e1.synchronize()
+            torch.cuda.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+            if streaming:
+                tile_ms.append(ctx.last_tile_pass_ms())  # the count-tile launches of THIS step (CUDA events on the library's stream)
+        self.barrier()
+        t_region = time.perf_counter() - t_region0
+        launches = ctx.launch_count() - launches0
+        clocks = sampler.stop() if (rank == 0 and full) else None
+        ms_per_step = self.max_over_ranks(float(sum(step_ms))) / steps
+        value = pairs / (ms_per_step * 1e-3) / 1e9
+        used_tensor = streaming and aln.last_count_kernel() == t.KERNEL_TENSOR
+        out = {"n": n, "L": L, "pairs": pairs, "mode": mode, "kind": kind, "desc": wl["desc"], "value": value, "ms_per_step": ms_per_step,
+               "steps": steps, "warmup": warmup, "launches": int(launches), "clocks": clocks, "region_wall_s": t_region,
+               "used_tensor": used_tensor, "rows_mine": rows_mine, "b0": b0, "b1": b1}
+
+        # ---- the result of the N-GPU pass against ONE GPU's, byte for byte ------------------------------------------
+        if world > 1 and streaming:
+            import hashlib
+            p = aln.best_match_compute()
+            multi = torch.as_tensor(_DevBuf(p, n * RS, "|u1"), device=dev).cpu().numpy().tobytes()
+            digest = hashlib.sha256(multi).hexdigest()
+            digests = [None] * world
+            dist.all_gather_object(digests, digest)
+            same = None
+            if rank == 0:
+                ctx.set_option(t.OPT_MULTI, 0)  # this rank alone, the whole triangle
+                aln.set_config(mode, 300, True)
+                one = aln.best_match().tobytes()
+                ctx.set_option(t.OPT_MULTI, 1)
+                same = bool(one == multi) and all(d == digest for d in digests)
+            flag = [same]
+            dist.broadcast_object_list(flag, 0)
+            out["parity_vs_1gpu"] = bool(flag[0])
+            out["result_sha256"] = digest
+            self.barrier()
+
+        # ---- the dominant kernel: the count-tile pass, timed live with CUDA events on the library's stream ----
+        if streaming:
+            kern_ms = float(np.mean(tile_ms))
+            kern_pairs = pairs / world  # this rank's share of the triangle's tiles
+        else:
+            kern_ms = aln.time_matrix_kernel(max(3, min(20, steps)))
+            kern_pairs = pairs if world == 1 else rows_mine * n  # symmetric triangle vs rectangular band
+        out["kernel_ms"] = kern_ms
+        if full:
+            peaks, peak_src = measured_peaks()
+            prof = {}
+            pj = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(pj):
+                prof = json.load(open(pj))
+            if used_tensor:
+                # kernel (b): int8 one-hot contraction on tcgen05.  Algorithmic work = 2 * K * L int8 ops per pair with the K symbol
+                # dimensions per site the kernel's code uses (DESIGN.md 4.5: 5 for p, 4 for K2P below 1,024 columns).  Peaks: a cuBLASLt
+                # int8 GEMM timed in this run, and twice MEASURED_PEAKS.json's bf16 burst figure beside it.
+                dims = aln.tensor_dims()
+                ops = kern_pairs * 2 * dims * L
+                twice_bf16 = 2 * peaks.get("bf16_tflops", 1590.0) * 1e12
+                try:
+                    int8_peak, int8_src = int8_peak_live(torch, dev), "measured live: torch._int_mm int8 8192^3, best of 10 (cuBLASLt; MEASURED_PEAKS.json has no int8 figure)"
+                except Exception as ex:  # noqa: BLE001
+                    int8_peak, int8_src = twice_bf16, "2 x MEASURED_PEAKS.json bf16_tflops (%s; torch._int_mm unavailable: %s)" % (peak_src, type(ex).__name__)
+                achieved = ops / (kern_ms * 1e-3)
+                P_bytes = 2 * n * dims * L  # a-side + b-side one-hot operands
+                out["roofline"] = {
+                    "bound": "tensor", "kernel": "tc::tile_kernel (tcgen05.mma kind::i8, TMEM accumulators)",
+                    "achieved": achieved / 1e12, "peak": int8_peak / 1e12, "unit": "TOP/s (int8)", "frac": achieved / int8_peak,
+                    "peak_source": int8_src, "peak_2x_bf16_burst": twice_bf16 / 1e12, "frac_of_2x_bf16_burst": achieved / twice_bf16,
+                    "kernel_ms": kern_ms, "kernel_gpairs_per_s": kern_pairs / (kern_ms * 1e-3) / 1e9,
+                    "algorithmic_int8_ops_per_pair": 2 * dims * L, "symbol_dimensions": dims,
+                    "traffic": prof.get(workload + "_tensor", {}).get("dram_bytes_per_launch"),
+                    "hbm": {"algorithmic_bytes_per_launch": int(P_bytes), "achieved_gbs": P_bytes / (kern_ms * 1e-3) / 1e9,
+                            "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},
+                }
+            else:
+                popc_alg = kern_pairs * POPC_PER_PAIR_WORD[mode] * W32
+                popc_peak, lop3_peak = ctx.measure_int_peaks()
+                achieved = popc_alg / (kern_ms * 1e-3)
+                P_planes = {0: 6, 1: 5, 2: 4}[mode]
+                plane_bytes = n * P_planes * W32 * 4
+                out["roofline"] = {
+                    "bound": "int-issue: POPC on the XU pipe (16 lanes/clk/SM); neither HBM nor tensor bound -- see DESIGN.md",
+                    "kernel": "count_tile_kernel" + ("<EPI_STREAM>" if streaming else "<EPI_MATRIX>"),
+                    "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": achieved / popc_peak,
+                    "peak_source": "measured live by tdna_measure_int_peaks: dependent-free POPC stream on all SMs (MEASURED_PEAKS.json has no integer-pipe figure); LOP3 stream %.2f T/s (two LOP3 per result)" % (lop3_peak / 1e12),
+                    "kernel_ms": kern_ms, "kernel_gpairs_per_s": kern_pairs / (kern_ms * 1e-3) / 1e9,
+                    "algorithmic_popc32_per_pair": POPC_PER_PAIR_WORD[mode] * W32,
+                    "traffic": prof.get(workload, {}).get("dram_bytes_per_launch"),
+                    "hbm": {"algorithmic_bytes_per_launch": int(plane_bytes if streaming else plane_bytes + rows_mine * n * 8),
+                            "achieved_gbs": (plane_bytes if streaming else plane_bytes + rows_mine * n * 8) / (kern_ms * 1e-3) / 1e9,
+                            "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},
+                }
+
+        # ---- e2e: the same step through the C ABI with HOST buffers ---------------------------------
+        e2e_steps = max(1, min(steps, 5))
+        if kind.startswith("matrix"):
+            out_host = torch.empty((rows_mine, n), dtype=torch.float64).pin_memory()
+            d2h_rank = out_host.numel() * 8 + 4 * (n_intra + n_inter)
+        else:
+            out_host = torch.empty((n, RS), dtype=torch.uint8).pin_memory()
+            d2h_rank = n * RS + 4 * n_intra
+        h_intra = torch.empty(max(1, n_intra), dtype=torch.float32).pin_memory()
+        h_inter = torch.empty(max(1, n_inter), dtype=torch.float32).pin_memory()
+        # N > 1: every rank uploads 1 / N of the symbol rows (the library all-gathers them over NVLink) and the whole label arrays,
+        # and reads back its own copy of the result
+        h2d = sym.nbytes + world * 4 * 4 * n
+        d2h = sum(self._gather_int(d2h_rank))
+
+        def step_e2e():
+            a2 = t.Alignment(ctx, sym_pinned.numpy())  # H2D of the symbols + pack
+            a2.set_labels(*labels)
+            a2.set_config(mode, 300, True)
+            if world > 1 and not streaming:
+                a2.set_row_range(b0, b1)
+            if kind.startswith("matrix"):
+                t.check(L_.tdna_matrix(a2.h, out_host.data_ptr(), None))
+                t.check(L_.tdna_class_distances(a2.h, t.PD_INTRA, h_intra.data_ptr(), n_intra, ctypes.byref(c64)))
+                t.check(L_.tdna_class_distances(a2.h, t.PD_INTER, h_inter.data_ptr(), n_inter, ctypes.byref(c64)))
+            elif "intra" in kind:
+                io = t.Analysis()
+                io.want = t.WANT_BEST_MATCH | t.WANT_INTRA
+                io.rows = out_host.data_ptr()
+                io.intra, io.intra_cap = h_intra.data_ptr(), n_intra
+                t.check(L_.tdna_analyze(a2.h, ctypes.byref(io)))
+            else:
+                a2.best_match_into(out_host.data_ptr())
+            a2.close()
+
+        step_e2e()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        self.barrier()
+        e2e_s = self.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        out["e2e"] = {"value": pairs / e2e_s / 1e9, "unit": "Gpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                      "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
+
+        out["cpu_baseline"] = None
+        if full and rank == 0 and world == 1 and not args.no_cpu_baseline:
+            import shutil
+            threads = os.cpu_count() or 1
+            v, cnt, dt, rows = cpu_reference_leg(data, mode, args.cpu_seconds, threads)
+            v1, cnt1, dt1, rows1 = cpu_reference_leg(data, mode, min(4.0, args.cpu_seconds), 1)
+            out["cpu_baseline"] = {
+                "value": v / 1e9, "unit": "Gpairs/s", "cores": threads, "kind": "port",
+                "sample": "first %d query rows x all later columns of the same alignment: %d pairs in %.1f s; C restatement of the reference's Sequence.getPairwiseNoBuffer (oracle/tdna_oracle.c)" % (rows, cnt, dt),
+                "single_thread_value": v1 / 1e9,
+                # the reference is Java; its sources cannot travel to this box (they may not be copied into the repo), so even a JVM
+                # found here could not run it -- recorded for the record (BASELINE.md 3(1))
+                "jvm": shutil.which("java") or "absent"}
+        # torch releases pinned blocks that were used on the library's stream by recording an event on that stream: let them go
+        # while the stream still exists
+        out_host = h_intra = h_inter = sym_pinned = None  # noqa: F841
+        gc.collect()
+        torch.cuda.synchronize()
+        aln.close()
+        return out
+
+    def _gather_int(self, v):
+        if self.world == 1:
+            return [v]
+        vals = [None] * self.world
+        self.dist.all_gather_object(vals, int(v))
+        return vals
 
 
 def main():
@@ -250,351 +555,55 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import ctypes
-
-    import torch
-    import torch.distributed as dist
-
-    import taxondna_b200 as t
     from taxondna_b200 import synth
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+    b = Bench(args)
+    world, rank = b.world, b.rank
     wl = WORKLOADS[args.workload]
-    mode = wl["mode"]
-    kind = wl["kind"]
-    streaming = kind.startswith("bestmatch")
+    streaming = wl["kind"].startswith("bestmatch")
     base = synth.CONFIGS[wl["config"]]
     n1 = base["genera"] * base["species"] * base["reps"]
-    scale_n = None
-    if world > 1 and args.scaling == "weak":
-        scale_n = n1 * (world ** 0.5)  # pairs per GPU stay fixed
-    data = synth.generate(wl["config"], names=False, scale_n=scale_n)
-    sym = data["symbols"]
-    n, L = sym.shape
-    pairs = n * (n - 1) // 2
-    W32 = (L + 31) // 32
-
-    ctx = t.Context(local)
-    ctx.set_option(t.OPT_COUNT_KERNEL, {"auto": t.KERNEL_AUTO, "popc": t.KERNEL_POPC, "tensor": t.KERNEL_TENSOR}[args.kernel])
-    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
-    sym_pinned = torch.from_numpy(sym).pin_memory()
-    labels = [data[k] for k in ("species_id", "genus_id", "epithet_rank", "fullname_rank")]
-    aln = t.Alignment(ctx, sym_pinned.numpy())
-    aln.set_labels(*labels)
-    aln.set_config(mode, 300, True)
-    L_ = t.load()
-    c64 = ctypes.c_int64()
-    RS = t.ROW_RESULT_DTYPE.itemsize
-
-    # ---- how the pair space is shared between ranks ------------------------------------------
-    #  streaming kinds: every rank takes every world-th tile of the triangle (tdna_best_match_part),
-    #                   then one NCCL exchange of the candidate records / per-row counts, then merge.
-    #  matrix kinds:    row bands (each rank owns rows [b0,b1) x all columns); no collective.
-    if world > 1 and not streaming:
-        per = -(-n // world)
-        per = -(-per // 128) * 128
-        b0, b1 = min(n, rank * per), min(n, (rank + 1) * per)
-        aln.set_row_range(b0, b1)
-    else:
-        b0, b1 = 0, n
-    rows_mine = b1 - b0
-
-    n_intra = n_inter = 0
-    if "summary" in kind or "intra" in kind:
-        L_.tdna_class_distances(aln.h, t.PD_INTRA, None, 0, ctypes.byref(c64))  # sizes depend on the labels only
-        n_intra = c64.value
-        if "summary" in kind:
-            L_.tdna_class_distances(aln.h, t.PD_INTER, None, 0, ctypes.byref(c64))
-            n_inter = c64.value
-    d_intra = torch.empty(max(1, n_intra), dtype=torch.float32, device=dev)
-    d_inter = torch.empty(max(1, n_inter), dtype=torch.float32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    tile_ms = []
-    cand_counts = []
-    # exchange buffers of the multi-GPU streaming path: one segment of `seg` packed records per rank
-    # Exchange of the candidate records at N > 1 (TDNA_BENCH_EXCHANGE overrides the choice):
-    #  "gathered": one segment per rank, all_gather, every rank merges all n rows            (least latency: 2 GPUs)
-    #  "routed":   one segment per (source, destination), all_to_all to the rank that owns the row, every rank finalises its own
-    #              rows_per_part rows, all_gather of the row records                          (least volume and merge work: 4+ GPUs)
-    exchange = os.environ.get("TDNA_BENCH_EXCHANGE", "gathered" if world <= 2 else "routed")
-    routed = exchange == "routed"
-    seg = max(1 << 14, (48 * n) // max(world * world, 1)) if routed else max(1 << 16, (32 * n) // max(world, 1))
-    xb = None
-    if world > 1 and streaming and routed:
-        rpp = aln.rows_per_part(world)
-        xb = {"rec": torch.empty((world, seg, 2), dtype=torch.int64, device=dev), "counts": torch.zeros(world, dtype=torch.int64, device=dev),
-              "recv": torch.empty((world, seg, 2), dtype=torch.int64, device=dev), "recv_counts": torch.zeros(world, dtype=torch.int64, device=dev),
-              "state": torch.empty(n, dtype=torch.int64, device=dev),
-              "slice": torch.empty(rpp * RS, dtype=torch.uint8, device=dev), "rows": torch.empty(world * rpp * RS, dtype=torch.uint8, device=dev)}
-    elif world > 1 and streaming:
-        xb = {"rec": torch.empty((seg, 2), dtype=torch.int64, device=dev), "count": torch.zeros(1, dtype=torch.int64, device=dev),
-              "counts": torch.zeros(world, dtype=torch.int64, device=dev), "state": torch.empty(n, dtype=torch.int64, device=dev),
-              "allrec": torch.empty((world, seg, 2), dtype=torch.int64, device=dev)}
-
-    def best_match_step(a, out=None):
-        """Per-query Best Match summaries for ALL rows, left on the device (or copied to the pinned host tensor `out`)."""
-        out_ptr = out.data_ptr() if out is not None else None
-        if world == 1:
-            if out_ptr is None:
-                a.best_match_compute()
-            else:
-                a.best_match_into(out_ptr)
-            return
-        mins = a.best_match_seed(rank, world)  # this rank's diagonal blocks -> per-row minima
-        with torch.cuda.stream(stream):
-            mt = torch.as_tensor(_DevBuf(mins, 3 * n, "<i8"), device=dev)
-            dist.all_reduce(mt, op=dist.ReduceOp.MIN)  # thresholds from ALL list neighbours on every rank
-            stream.synchronize()
-        if not routed:
-            # the part writes packed records / count / per-row state straight into these buffers; NCCL takes them as they are
-            a.best_match_part_packed(rank, world, True, xb["rec"].data_ptr(), seg, xb["count"].data_ptr(), xb["state"].data_ptr())
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(xb["counts"], xb["count"])
-                dist.all_gather_into_tensor(xb["allrec"].view(-1), xb["rec"].view(-1))
-                dist.all_reduce(xb["state"], op=dist.ReduceOp.SUM)
-                stream.synchronize()
-            a.best_match_merge_gathered(xb["allrec"].data_ptr(), world, seg, xb["counts"].data_ptr(), xb["state"].data_ptr(), out_ptr)
-            return
-        a.best_match_part_routed(rank, world, True, xb["rec"].data_ptr(), seg, xb["counts"].data_ptr(), xb["state"].data_ptr())
-        with torch.cuda.stream(stream):
-            dist.all_to_all_single(xb["recv_counts"], xb["counts"])
-            dist.all_to_all_single(xb["recv"].view(-1), xb["rec"].view(-1))
-            dist.all_reduce(xb["state"], op=dist.ReduceOp.SUM)
-            stream.synchronize()
-        a.best_match_merge_routed(rank, world, xb["recv"].data_ptr(), seg, xb["recv_counts"].data_ptr(), xb["state"].data_ptr(), xb["slice"].data_ptr())
-        with torch.cuda.stream(stream):
-            dist.all_gather_into_tensor(xb["rows"], xb["slice"])  # every rank holds all n row records (120 B each)
-            if out is not None:
-                out.view(torch.uint8).view(-1)[: n * RS].copy_(xb["rows"][: n * RS], non_blocking=True)
-            stream.synchronize()
-
-    def step_device():
-        aln.set_config(mode, 300, True)  # invalidates every cached result: each step recomputes everything
-        if kind.startswith("matrix"):
-            aln.matrix_compute()
-            t.check(L_.tdna_class_distances(aln.h, t.PD_INTRA, d_intra.data_ptr(), n_intra, ctypes.byref(c64)))
-            t.check(L_.tdna_class_distances(aln.h, t.PD_INTER, d_inter.data_ptr(), n_inter, ctypes.byref(c64)))
-        elif "intra" in kind and world == 1:
-            # Best Close Match + the intraspecific distances for the percentile from ONE streaming pass
-            io = t.Analysis()
-            io.want = t.WANT_BEST_MATCH | t.WANT_INTRA
-            io.intra, io.intra_cap = d_intra.data_ptr(), n_intra
-            t.check(L_.tdna_analyze(aln.h, ctypes.byref(io)))
-        else:
-            best_match_step(aln)
-            if "intra" in kind:
-                t.check(L_.tdna_class_distances(aln.h, t.PD_INTRA, d_intra.data_ptr(), n_intra, ctypes.byref(c64)))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = ctx.launch_count()
-    step_ms = []
-    t_region0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.fill_(1)  # L2 flush between timed iterations (on torch's stream; joined below)
-        torch.cuda.synchronize()
-        if world > 1:
-            # the untimed flush ends at different moments on different ranks; without this the ranks that finish it first would time
-            # their wait for the others inside the step's first collective
-            dist.barrier()
-            torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            step_device()
-            e1.record(stream)
-        e1.synchronize()
-        torch.cuda.synchronize()
-        step_ms.append(e0.elapsed_time(e1))
-        if streaming:
-            tile_ms.append(ctx.last_tile_pass_ms())  # the count-tile pass of THIS step (CUDA events on the library's stream)
-    barrier()
-    if xb is not None:
-        cand_counts.append(int(xb["counts"].sum().item()) if routed else int(xb["count"].item()))
-    t_region = time.perf_counter() - t_region0
-    launches = ctx.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = float(sum(step_ms))
-    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms = float(tm.item())
-    ms_per_step = total_ms / args.steps
-    value = pairs / (ms_per_step * 1e-3) / 1e9
-
-    # ---- the dominant kernel: the count-tile pass, timed live with CUDA events on the library's stream ----
-    if streaming:
-        kern_ms = float(np.mean(tile_ms))
-        kern_pairs = pairs / world  # every world-th tile of the triangle
-    else:
-        kern_ms = aln.time_matrix_kernel(max(3, min(20, args.steps)))
-        kern_pairs = pairs if world == 1 else rows_mine * n  # symmetric triangle vs rectangular band
-    peaks, peak_src = measured_peaks()
-    prof = {}
-    pj = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(pj):
-        prof = json.load(open(pj))
-    used_tensor = streaming and aln.last_count_kernel() == t.KERNEL_TENSOR
-    if used_tensor:
-        # kernel (b): int8 one-hot contraction on tcgen05.  Algorithmic work = 2 * K * L int8 ops per pair with the K = 5 (p) or
-        # 4 (K2P) symbol dimensions per site this kernel uses (DESIGN.md 4.5); peak = a cuBLASLt int8 GEMM (torch._int_mm, 8192^3)
-        # measured here, else twice MEASURED_PEAKS.json's bf16 burst figure.
-        dims = 4 if mode == 1 else 5  # K2P ignores gap sites: four symbol dimensions
-        ops = kern_pairs * 2 * dims * L
-        int8_peak, int8_src = None, None
-        try:
-            a8 = torch.randint(-3, 3, (8192, 8192), dtype=torch.int8, device=dev)
-            b8 = torch.randint(-3, 3, (8192, 8192), dtype=torch.int8, device=dev)
-            for _ in range(3):
-                torch._int_mm(a8, b8)
-            best = 1e9
-            for _ in range(10):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                torch._int_mm(a8, b8)
-                e1.record()
-                e1.synchronize()
-                best = min(best, e0.elapsed_time(e1))
-            int8_peak, int8_src = 2 * 8192 ** 3 / (best * 1e-3), "measured live: torch._int_mm int8 8192^3, best of 10 (cuBLASLt; MEASURED_PEAKS.json has no int8 figure)"
-            del a8, b8
-        except Exception as ex:  # noqa: BLE001
-            int8_peak, int8_src = 2 * peaks.get("bf16_tflops", 1590.0) * 1e12, "2 x MEASURED_PEAKS.json bf16_tflops (%s; torch._int_mm unavailable: %s)" % (peak_src, type(ex).__name__)
-        achieved = ops / (kern_ms * 1e-3)
-        P_bytes = 2 * n * dims * L  # a-side + b-side one-hot operands
-        roofline = {
-            "bound": "tensor", "kernel": "tc::tile_kernel (tcgen05.mma kind::i8, TMEM accumulators)",
-            "achieved": achieved / 1e12, "peak": int8_peak / 1e12, "unit": "TOP/s (int8)", "frac": achieved / int8_peak,
-            "peak_source": int8_src, "kernel_ms": kern_ms, "kernel_gpairs_per_s": kern_pairs / (kern_ms * 1e-3) / 1e9,
-            "algorithmic_int8_ops_per_pair": 2 * dims * L,
-            "traffic": prof.get(args.workload + "_tensor", {}).get("dram_bytes_per_launch"),
-            "hbm": {"algorithmic_bytes_per_launch": int(P_bytes), "achieved_gbs": P_bytes / (kern_ms * 1e-3) / 1e9,
-                    "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},
-        }
-    else:
-        popc_alg = kern_pairs * POPC_PER_PAIR_WORD[mode] * W32
-        popc_peak, lop3_peak = ctx.measure_int_peaks()
-        achieved = popc_alg / (kern_ms * 1e-3)
-        P_planes = {0: 6, 1: 5, 2: 4}[mode]
-        plane_bytes = n * P_planes * W32 * 4
-        roofline = {
-            "bound": "int-issue: POPC on the XU pipe (16 lanes/clk/SM); neither HBM nor tensor bound -- see DESIGN.md",
-            "kernel": "count_tile_kernel" + ("<EPI_STREAM>" if streaming else "<EPI_MATRIX>"),
-            "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": achieved / popc_peak,
-            "peak_source": "measured live by tdna_measure_int_peaks: dependent-free POPC stream on all SMs (MEASURED_PEAKS.json has no integer-pipe figure); LOP3 stream %.2f T/s (two LOP3 per result)" % (lop3_peak / 1e12),
-            "kernel_ms": kern_ms, "kernel_gpairs_per_s": kern_pairs / (kern_ms * 1e-3) / 1e9,
-            "algorithmic_popc32_per_pair": POPC_PER_PAIR_WORD[mode] * W32,
-            "traffic": prof.get(args.workload, {}).get("dram_bytes_per_launch"),
-            "hbm": {"algorithmic_bytes_per_launch": int(plane_bytes if streaming else plane_bytes + rows_mine * n * 8),
-                    "achieved_gbs": (plane_bytes if streaming else plane_bytes + rows_mine * n * 8) / (kern_ms * 1e-3) / 1e9,
-                    "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},
-        }
-
-    # ---- e2e: the same step through the C ABI with HOST buffers ---------------------------------
-    e2e_steps = max(1, min(args.steps, 5))
-    h2d = sym.nbytes + 4 * 4 * n
-    if kind.startswith("matrix"):
-        out_host = torch.empty((rows_mine, n), dtype=torch.float64).pin_memory()
-        d2h = out_host.numel() * 8 + 4 * (n_intra + n_inter)
-    else:
-        out_host = torch.empty((n, RS), dtype=torch.uint8).pin_memory()
-        d2h = n * RS + 4 * n_intra
-    h_intra = torch.empty(max(1, n_intra), dtype=torch.float32).pin_memory()
-    h_inter = torch.empty(max(1, n_inter), dtype=torch.float32).pin_memory()
-
-    def step_e2e():
-        a2 = t.Alignment(ctx, sym_pinned.numpy())  # H2D of the symbols + pack
-        a2.set_labels(*labels)
-        a2.set_config(mode, 300, True)
-        if world > 1 and not streaming:
-            a2.set_row_range(b0, b1)
-        if kind.startswith("matrix"):
-            t.check(L_.tdna_matrix(a2.h, out_host.data_ptr(), None))
-            t.check(L_.tdna_class_distances(a2.h, t.PD_INTRA, h_intra.data_ptr(), n_intra, ctypes.byref(c64)))
-            t.check(L_.tdna_class_distances(a2.h, t.PD_INTER, h_inter.data_ptr(), n_inter, ctypes.byref(c64)))
-        elif "intra" in kind and world == 1:
-            io = t.Analysis()
-            io.want = t.WANT_BEST_MATCH | t.WANT_INTRA
-            io.rows = out_host.data_ptr()
-            io.intra, io.intra_cap = h_intra.data_ptr(), n_intra
-            t.check(L_.tdna_analyze(a2.h, ctypes.byref(io)))
-        else:
-            best_match_step(a2, out_host)
-            if "intra" in kind:
-                t.check(L_.tdna_class_distances(a2.h, t.PD_INTRA, h_intra.data_ptr(), n_intra, ctypes.byref(c64)))
-        a2.close()
-
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    e2e = {"value": pairs / e2e_s / 1e9, "unit": "Gpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        v, cnt, dt, rows = cpu_reference_leg(data, mode, args.cpu_seconds, threads)
-        v1, cnt1, dt1, rows1 = cpu_reference_leg(data, mode, min(4.0, args.cpu_seconds), 1)
-        cpu = {"value": v / 1e9, "unit": "Gpairs/s", "cores": threads, "kind": "port",
-               "sample": "first %d query rows x all later columns of the same alignment: %d pairs in %.1f s; C restatement of the reference's Sequence.getPairwiseNoBuffer (oracle/tdna_oracle.c; the reference is Java and no JVM exists in the image)" % (rows, cnt, dt),
-               "single_thread_value": v1 / 1e9}
-
+    # the headline run.  --scaling strong (default): the named shape itself on N GPUs; weak: the alignment grows as sqrt(N) so that
+    # the pairs per GPU stay fixed
+    weak_n = n1 * (world ** 0.5) if world > 1 else None
+    r = b.measure(args.workload, scale_n=weak_n if (args.scaling == "weak" and world > 1) else None)
+    extras = {}
+    if world > 1 and streaming and not args.no_extras:
+        # the other scaling mode of the same workload as an extra key (value + e2e + parity only)
+        other = "weak" if args.scaling == "strong" else "strong"
+        ro = b.measure(args.workload, scale_n=weak_n if other == "weak" else None, steps=max(3, min(args.steps, 10)), warmup=3, full=False)
+        extras[other + "_scaling"] = {"n": ro["n"], "pairs": ro["pairs"], "value": ro["value"], "unit": "Gpairs/s", "ms_per_step": ro["ms_per_step"],
+                                      "kernel_ms": ro["kernel_ms"], "e2e": ro["e2e"], "parity_vs_1gpu": ro.get("parity_vs_1gpu"),
+                                      "note": "pairs per GPU fixed (n grows as sqrt(N))" if other == "weak" else "the named shape itself on N GPUs"}
     if rank == 0:
         if streaming:
             par = "single GPU, whole triangle"
-            if world > 1 and routed:
-                par = "every %d-th unit of 128 tile slots of the triangle per rank; NCCL: all_reduce(min) of the seeded minima, all_to_all of the candidate records (to the rank that owns the row), all_reduce(sum) of the per-row state, all_gather of the row records each rank finalised" % world
-            elif world > 1:
-                par = "every %d-th unit of 128 tile slots of the triangle per rank; NCCL: all_reduce(min) of the seeded minima, all_gather of the candidate records, all_reduce(sum) of the per-row state; merge on every rank" % world
+            if world > 1:
+                par = ("inside the C ABI (tdna_comm_init): every %d-th unit of 128 tile slots of the triangle per rank; NCCL on the library's stream: "
+                       "all_reduce(min) of the seeded per-row minima, grouped send/recv of the candidate records to the rank that owns the row, "
+                       "all_reduce(sum) of the per-row state + status, all_gather of the row records each rank finalised; one host sync per step" % world)
         else:
-            par = "row bands, %d rank(s), rows [%d,%d) on rank 0" % (world, b0, b1)
+            par = "row bands, %d rank(s), rows [%d,%d) on rank 0" % (world, r["b0"], r["b1"])
+        n, L, mode = r["n"], r["L"], r["mode"]
         line = {
-            "metric": "pairwise distances/s", "value": value, "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": "pairwise distances/s", "value": r["value"], "unit": "Gpairs/s", "n_gpus": world, "steps": r["steps"],
+            "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
-            "dtype": ("int8 one-hot -> int32 counts (tcgen05) -> f64 distance" if used_tensor else "u32 bit-planes -> int32 counts -> f64 distance"), "data": "synthetic",
-            "config": {"workload": wl["desc"], "n": n, "L": L, "count_kernel": ("tensor" if used_tensor else "popc"), "mode": ["uncorrected", "K2P", "trans-only"][mode], "min_overlap": 300,
-                       "pairs": pairs, "step": kind, "l2": "flushed between timed steps (256 MiB write)", "parallelism": par},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "region_wall_s": t_region,
+            "dtype": ("int8 one-hot -> int32 counts (tcgen05) -> f64 distance" if r["used_tensor"] else "u32 bit-planes -> int32 counts -> f64 distance"), "data": "synthetic",
+            "config": {"workload": "%s x %s bp: %s" % (format(n, ","), format(L, ","), r["desc"]), "n": n, "L": L,
+                       "count_kernel": ("tensor" if r["used_tensor"] else "popc"), "mode": ["uncorrected", "K2P", "trans-only"][mode], "min_overlap": 300,
+                       "pairs": r["pairs"], "step": r["kind"], "l2": "flushed between timed steps (256 MiB write)", "parallelism": par},
+            "roofline": r.get("roofline"), "cpu_baseline": r["cpu_baseline"], "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"],
+            "region_wall_s": r["region_wall_s"],
         }
-        if cand_counts:
-            line["config"]["candidates_per_rank_per_step"] = int(np.mean(cand_counts))
+        if "parity_vs_1gpu" in r:
+            line["parity_vs_1gpu"] = r["parity_vs_1gpu"]
+            line["result_sha256"] = r["result_sha256"]
+        line.update(extras)
         print(json.dumps(line), file=_OUT, flush=True)
-    # torch releases pinned blocks that were used on the library's stream by recording an event on that stream: let them go
-    # while the stream still exists
-    out_host = h_intra = h_inter = xb = None  # noqa: F841
-    gc.collect()
-    torch.cuda.synchronize()
-    aln.close()
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    bad = ("parity_vs_1gpu" in r and not r["parity_vs_1gpu"]) or any(v.get("parity_vs_1gpu") is False for v in extras.values())
+    b.close()
+    if bad:
+        raise SystemExit("the N-GPU result differs from one GPU's")
 
 
 if __name__ == "__main__":

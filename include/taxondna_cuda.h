@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TDNA_ABI_VERSION 1
+#define TDNA_ABI_VERSION 2
 
 enum {
     TDNA_OK = 0,
@@ -100,6 +100,26 @@ int32_t tdna_abi_version(void);
 int32_t tdna_init(int32_t device, tdna_ctx **out);
 int32_t tdna_shutdown(tdna_ctx *ctx);
 const char *tdna_last_error(void);
+/* ---- several GPUs of one box -----------------------------------------------------------------------------------
+ * The reference runs every analysis on one thread of one JVM (SpeciesIdentifier.java:668-681); here the O(N^2) pass of ONE analysis
+ * is shared by up to 8 GPUs.  One context per GPU; the contexts form a communicator (NCCL over NVLink / NVSwitch, bound with dlopen
+ * at the first tdna_comm_* call -- a single-GPU host never loads it).  From then on every whole-range tdna_analyze / tdna_best_match*
+ * / tdna_class_distances / tdna_edges_below / tdna_class_histogram on an alignment is a COLLECTIVE call: every rank makes it, on an
+ * alignment with the same content, labels and configuration, from its own thread (one JVM: one thread per GPU) or its own process
+ * (torchrun: one process per GPU).  Inside the call the ranks share the triangle's tiles, all-reduce the seeded per-row minima,
+ * route the candidate records to the rank that owns the row, and all-gather the row records -- all on the contexts' streams, with
+ * one host synchronisation at the end.  Per-row records and histograms come back complete and bit-identical to one GPU's on every
+ * rank; variable-length lists (class distances, edges) come back as this rank's share (n_*_local entries) with the totals in n_*.
+ *   tdna_comm_unique_id : rank 0 makes the 128-byte id; the host hands it to every rank (a Java array, an MPI / torch broadcast)
+ *   tdna_comm_init      : collective; the context joins as `rank` of `nranks`
+ *   tdna_init_multi     : ONE process, one thread: creates ndev contexts (out[k] on devices[k], rank k) with their communicator */
+#define TDNA_COMM_ID_BYTES 128
+int32_t tdna_comm_unique_id(uint8_t *id128);
+int32_t tdna_comm_init(tdna_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t nranks);
+int32_t tdna_comm_destroy(tdna_ctx *ctx);
+int32_t tdna_comm_info(tdna_ctx *ctx, int32_t *rank, int32_t *nranks);
+int32_t tdna_init_multi(const int32_t *devices, int32_t ndev, tdna_ctx **out);
+
 /* The context's CUDA stream (a cudaStream_t) so that a caller can order its own work/events on it. */
 void *tdna_stream(tdna_ctx *ctx);
 /* Bytes of HBM the library may use for device-resident N x N results (default 64 GiB). */
@@ -269,13 +289,17 @@ typedef struct {
     double *edge_d;
     int64_t edge_cap;
     int64_t n_intra, n_inter, n_edges; /* out: totals (may exceed the capacities: only the first cap are stored) */
+    int64_t n_intra_local, n_inter_local, n_edges_local; /* out: entries THIS rank produced (== the totals on one GPU); with a
+                                                            communicator the lists hold this rank's share and the host concatenates */
 } tdna_analysis;
 int32_t tdna_analyze(tdna_aln *aln, tdna_analysis *io);
 
 /* ---- options ------------------------------------------------------------------------------------ */
 enum { TDNA_OPT_BEST_MATCH_PATH = 1, /* TDNA_PATH_*: how tdna_best_match computes a whole-range request */
        TDNA_OPT_TILE_COLUMNS = 2,    /* 0 = automatic, 64 or 128: column width of a popc count tile */
-       TDNA_OPT_COUNT_KERNEL = 3     /* TDNA_KERNEL_*: which count kernel the streaming pass uses */ };
+       TDNA_OPT_COUNT_KERNEL = 3,    /* TDNA_KERNEL_*: which count kernel the streaming pass uses */
+       TDNA_OPT_MULTI = 4            /* 1 (default): whole-range calls are shared by the communicator's ranks; 0: this GPU alone;
+                                        2: the collective path even when the communicator has ONE rank (tests on a one-GPU box) */ };
 enum { TDNA_KERNEL_AUTO = 0,   /* the faster eligible one (A/B on ncu evidence) */
        TDNA_KERNEL_POPC = 1,   /* (a) bit-planes + LOP3/POPC, any alphabet, any mode */
        TDNA_KERNEL_TENSOR = 2  /* (b) one-hot int8 contraction on tcgen05/TMEM: uncorrected p with ambiguity allowed, or K2P;
@@ -322,6 +346,9 @@ int32_t tdna_time_matrix_kernel(tdna_aln *aln, int32_t reps, float *ms_per_launc
  * row symbol x and a column symbol y contribute W - (W-1)[x == y] to the int32 accumulator.  Host arithmetic only (no device). */
 int32_t tdna_tensor_code(int32_t L, int32_t dims, int32_t *code, uint32_t *W);
 int32_t tdna_last_count_kernel(tdna_aln *aln);
+/* Symbol dimensions per site of the one-hot operands count kernel (b) built for this alignment (5, or 4 when no row has an internal
+ * gap / in K2P mode); 0 if they have not been built.  The roofline's algorithmic work per pair is 2 * dims * L int8 operations. */
+int32_t tdna_tensor_dims(tdna_aln *aln);
 /* Device time (CUDA events on the context's stream) of the most recent count-tile pass -- the tile
  * kernel launch(es) of the last matrix band or streaming pass; waits for it to finish. */
 int32_t tdna_last_tile_pass_ms(tdna_ctx *ctx, float *ms);

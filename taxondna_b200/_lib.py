@@ -12,7 +12,8 @@ LIB_PATH = os.environ.get("TDNA_LIB") or os.path.join(_HERE, "libtaxondna_cuda.s
 PDM_UNCORRECTED, PDM_K2P, PDM_TRANS_ONLY = 0, 1, 2
 PD_INTRA, PD_INTER = 0, 1
 ROW_SELF_VALID, ROW_NONFINITE = 1, 2
-OPT_BEST_MATCH_PATH, OPT_TILE_COLUMNS, OPT_COUNT_KERNEL = 1, 2, 3
+OPT_BEST_MATCH_PATH, OPT_TILE_COLUMNS, OPT_COUNT_KERNEL, OPT_MULTI = 1, 2, 3, 4
+COMM_ID_BYTES = 128
 KERNEL_AUTO, KERNEL_POPC, KERNEL_TENSOR = 0, 1, 2
 PATH_AUTO, PATH_DENSE, PATH_STREAM = 0, 1, 2
 
@@ -36,7 +37,8 @@ class Analysis(ctypes.Structure):
                 ("intra", ctypes.c_void_p), ("intra_cap", ctypes.c_int64), ("inter", ctypes.c_void_p), ("inter_cap", ctypes.c_int64),
                 ("edge_threshold", ctypes.c_double), ("edge_i", ctypes.c_void_p), ("edge_j", ctypes.c_void_p),
                 ("edge_d", ctypes.c_void_p), ("edge_cap", ctypes.c_int64),
-                ("n_intra", ctypes.c_int64), ("n_inter", ctypes.c_int64), ("n_edges", ctypes.c_int64)]
+                ("n_intra", ctypes.c_int64), ("n_inter", ctypes.c_int64), ("n_edges", ctypes.c_int64),
+                ("n_intra_local", ctypes.c_int64), ("n_inter_local", ctypes.c_int64), ("n_edges_local", ctypes.c_int64)]
 
 
 class StreamPart(ctypes.Structure):
@@ -67,11 +69,33 @@ EXPORTS = [
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
     "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_rows_per_part", "tdna_tensor_code", "tdna_consensus", "tdna_fasta_parse", "tdna_fasta_destroy", "tdna_fasta_count", "tdna_fasta_width", "tdna_fasta_records", "tdna_fasta_symbols", "tdna_alignment_create_from_fasta", "tdna_best_match_part_routed", "tdna_best_match_merge_routed", "tdna_set_option", "tdna_last_tile_pass_ms",
+    "tdna_tensor_dims", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
 
 _lib = None
+_nccl = None
+
+
+def preload_nccl():
+    """Python hosts usually carry a pip-installed NCCL (nvidia-nccl-cu12, what torch links against).  The library binds NCCL with
+    dlopen("libnccl.so.2") at the first tdna_comm_* call and would take the SYSTEM copy if none is loaded yet -- after which a
+    later `import torch` would be bound to that (older) copy too and fail on its newer symbols.  So load the pip copy first."""
+    global _nccl
+    if _nccl is not None:
+        return
+    _nccl = False
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                _nccl = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+                return
+    except Exception:  # noqa: BLE001 -- no pip NCCL: the system copy is what there is
+        pass
 
 
 def load():
@@ -133,6 +157,7 @@ def load():
     L.tdna_measure_int_peaks.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     L.tdna_tensor_counts.argtypes = [vp, vp]
     L.tdna_last_count_kernel.argtypes = [vp]
+    L.tdna_tensor_dims.argtypes = [vp]
     L.tdna_analyze.argtypes = [vp, ctypes.POINTER(Analysis)]
     L.tdna_best_match_seed.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
     L.tdna_best_match_part.argtypes = [vp, i32, i32, i32, ctypes.POINTER(StreamPart)]
@@ -140,6 +165,11 @@ def load():
     L.tdna_best_match_part_packed.argtypes = [vp, i32, i32, i32, vp, i64, vp, vp]
     L.tdna_best_match_merge_gathered.argtypes = [vp, vp, i32, i64, vp, vp, vp]
     L.tdna_set_option.argtypes = [vp, i32, i64]
+    L.tdna_comm_unique_id.argtypes = [vp]
+    L.tdna_comm_init.argtypes = [vp, vp, i32, i32]
+    L.tdna_comm_destroy.argtypes = [vp]
+    L.tdna_comm_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.tdna_init_multi.argtypes = [vp, i32, vp]
     L.tdna_last_tile_pass_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     _lib = L
     return L
@@ -153,12 +183,57 @@ def check(rc):
 class Context:
     """tdna_ctx: one per GPU per process."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, handle=None):
         self.L = load()
         self.h = ctypes.c_void_p()
-        check(self.L.tdna_init(device, ctypes.byref(self.h)))
+        if handle is not None:
+            self.h = ctypes.c_void_p(handle)  # a context tdna_init_multi created
+        else:
+            check(self.L.tdna_init(device, ctypes.byref(self.h)))
         self.device = device
         self._cb = None
+
+    @staticmethod
+    def init_multi(devices):
+        """One process, several GPUs (the one-JVM layout): one context per device, joined in one communicator.  Collective
+        calls are then made from one thread per context."""
+        L = load()
+        preload_nccl()
+        devs = (ctypes.c_int32 * len(devices))(*devices)
+        out = (ctypes.c_void_p * len(devices))()
+        check(L.tdna_init_multi(devs, len(devices), out))
+        return [Context(d, handle=h) for d, h in zip(devices, out)]
+
+    @staticmethod
+    def comm_unique_id():
+        preload_nccl()
+        buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+        check(load().tdna_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, nranks):
+        """Collective over the nranks contexts (one per GPU): joins the NCCL communicator the library runs its multi-GPU passes on."""
+        assert len(unique_id) == COMM_ID_BYTES
+        preload_nccl()
+        check(self.L.tdna_comm_init(self.h, ctypes.c_char_p(unique_id), int(rank), int(nranks)))
+
+    def comm_init_torch(self, dist, device):
+        """comm_init with the id broadcast through an existing torch.distributed group (control plane only)."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        t = torch.zeros(COMM_ID_BYTES, dtype=torch.uint8, device=device)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        self.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    def comm_destroy(self):
+        check(self.L.tdna_comm_destroy(self.h))
+
+    def comm_info(self):
+        r, n = ctypes.c_int32(), ctypes.c_int32()
+        check(self.L.tdna_comm_info(self.h, ctypes.byref(r), ctypes.byref(n)))
+        return r.value, n.value
 
     def close(self):
         if self.h:
@@ -333,6 +408,9 @@ class Alignment:
 
     def last_count_kernel(self):
         return int(self.L.tdna_last_count_kernel(self.h))
+
+    def tensor_dims(self):
+        return int(self.L.tdna_tensor_dims(self.h))
 
     def tensor_counts(self):
         """(shared, ident) of every pair from count kernel (b); pairs outside the triangle's tiles are -1."""

@@ -10,6 +10,7 @@
 #include "tdna_kernels.cuh"
 #include "tdna_tc.cuh"
 #include "tdna_fasta.cuh"
+#include "tdna_comm.cuh"
 
 using namespace tdna;
 
@@ -55,8 +56,12 @@ struct tdna_ctx {
     double *d_mat = nullptr;
     int64_t mat_cap = 0;              // doubles
     const void *mat_owner = nullptr;  // alignment whose whole-range matrix currently sits in d_mat
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the most recent tile pass (tdna_last_tile_pass_ms)
-    bool ev_valid = false;
+    // the most recent tile pass (tdna_last_tile_pass_ms): seed launch = [k0, s1], bulk launch = [b0, k1]; what lies between them
+    // (the MIN all-reduce of the seeded minima when several GPUs share the pass) is not tile work
+    cudaEvent_t ev_k0 = nullptr, ev_s1 = nullptr, ev_b0 = nullptr, ev_k1 = nullptr;
+    bool ev_valid = false, ev_split = false;
+    Comm comm;                        // tdna_comm_init: NCCL communicator of this context (one rank per GPU)
+    int64_t *h_status = nullptr;      // pinned: the status words a multi-GPU pass reads back at its one and only host sync
     int opt_best_match_path = TDNA_PATH_AUTO;
     int opt_tile_cn = 0;  // 0 = automatic
     int opt_count_kernel = TDNA_KERNEL_AUTO;
@@ -120,6 +125,13 @@ struct tdna_aln {
     int tc_inner = 256;
     int64_t *d_tcprefix[2] = {nullptr, nullptr};
     int64_t tcprefix_tiles[2] = {0, 0};
+    // in-library multi-GPU pass (tdna_comm_init): exchange segments, reduced per-row state, the all-gathered row records
+    long long *x_send = nullptr, *x_recv = nullptr, *x_state = nullptr;
+    int64_t x_seg = 0;        // records per exchange segment (same on every rank: derived from n, the rank count and x_scale only)
+    int x_scale = 1;          // doubled on every rank alike when some segment overflowed (the status word is all-reduced)
+    int x_nranks = 0;
+    int64_t res_rows = 0;     // records d_res holds (n, or nranks * rows_per_part once a multi-GPU pass ran)
+    long long local_ncls[2] = {0, 0}, local_nedge = 0;  // this rank's share of the class distances / edges of the last pass
 };
 
 namespace {
@@ -267,6 +279,7 @@ template <int KM, int CN, bool WC> int launch_tiles_t(tdna_aln *a, int64_t b0, i
     TRY((launch_kernel<KM, CN, WC ? EPI_MATRIX_COUNTS : EPI_MATRIX>(c, p)));
     CU(cudaEventRecord(c->ev_k1, c->stream));
     c->ev_valid = true;
+    c->ev_split = false;
     return TDNA_OK;
 }
 
@@ -353,12 +366,15 @@ template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts,
         p.t_offset = t0;
         p.t_stride = 1;
         p.num_tiles = t1 - t0;
+        if (ph == 1) CU(cudaEventRecord(c->ev_b0, c->stream));
         if (ph == 0 || a->sp.want == TDNA_WANT_BEST_MATCH) TRY((launch_kernel<KM, CN, EPI_STREAM>(c, p)));
         else TRY((launch_kernel<KM, CN, EPI_STREAM_X>(c, p)));
+        if (ph == 0) CU(cudaEventRecord(c->ev_s1, c->stream));
     }
     if (phases & 2) {
         CU(cudaEventRecord(c->ev_k1, c->stream));
         c->ev_valid = true;
+        c->ev_split = true;
     }
     return TDNA_OK;
 }
@@ -394,11 +410,14 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
         for (int ph = 0; ph < 2; ph++)
             if (phases & (1 << ph)) {
                 TRY(set_stream_symbol(a, ph == 0));
+                if (ph == 1) CU(cudaEventRecord(c->ev_b0, c->stream));
                 TRY(launch_tc<false>(a, ph, part, nparts, nullptr));
+                if (ph == 0) CU(cudaEventRecord(c->ev_s1, c->stream));
             }
         if (phases & 2) {
             CU(cudaEventRecord(c->ev_k1, c->stream));
             c->ev_valid = true;
+            c->ev_split = true;
             // the queued pairs -> minima -> final thresholds -> candidate records
             TRY(set_stream_symbol(a, false));
             int wshift = 0;
@@ -838,6 +857,19 @@ int ensure_scratch(tdna_aln *a, size_t bytes) {
     return TDNA_OK;
 }
 
+// the per-row result records: n, or every rank's padded slice once a multi-GPU pass gathers them here
+int ensure_res(tdna_aln *a, int64_t rows) {
+    tdna_ctx *c = a->ctx;
+    if (rows < a->n) rows = a->n;
+    if (a->d_res && a->res_rows >= rows) return TDNA_OK;
+    if (a->d_res) CU(DFREE(a->d_res));
+    a->d_res = nullptr;
+    a->res_rows = 0;
+    CU(DMALLOC(&a->d_res, (size_t)rows * sizeof(tdna_row_result)));
+    a->res_rows = rows;
+    return TDNA_OK;
+}
+
 int need_labels(tdna_aln *a) {
     if (!a->has_labels) return fail(TDNA_E_STATE, "tdna_alignment_set_labels has not been called");
     return TDNA_OK;
@@ -867,6 +899,9 @@ int32_t tdna_init(int32_t device, tdna_ctx **out) {
     CU(cudaMalloc(&c->d_counter, 64));
     CU(cudaEventCreate(&c->ev_k0));
     CU(cudaEventCreate(&c->ev_k1));
+    CU(cudaEventCreate(&c->ev_s1));
+    CU(cudaEventCreate(&c->ev_b0));
+    CU(cudaMallocHost(&c->h_status, 64 * sizeof(int64_t)));
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     unsigned long long keep = ~0ull;
@@ -883,10 +918,99 @@ int32_t tdna_shutdown(tdna_ctx *c) {
     cudaSetDevice(c->device);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_mat) cudaFree(c->d_mat);
-    if (c->ev_k0) cudaEventDestroy(c->ev_k0);
-    if (c->ev_k1) cudaEventDestroy(c->ev_k1);
+    if (c->comm.comm && c->comm.api) c->comm.api->CommDestroy(c->comm.comm);
+    c->comm.comm = nullptr;
+    if (c->h_status) cudaFreeHost(c->h_status);
+    for (cudaEvent_t e : {c->ev_k0, c->ev_k1, c->ev_s1, c->ev_b0})
+        if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+    return TDNA_OK;
+}
+
+// ---- communicator ------------------------------------------------------------------------------------------------------------
+int32_t tdna_comm_unique_id(uint8_t *id) {
+    if (!id) return fail(TDNA_E_ARG, "null argument");
+    std::string why;
+    const NcclApi *nc = nccl_api(&why);
+    if (!nc) return fail(TDNA_E_STATE, why);
+    static_assert(sizeof(ncclUniqueId) == TDNA_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    ncclUniqueId u;
+    ncclResult_t r = nc->GetUniqueId(&u);
+    if (r != ncclSuccess) return fail(TDNA_E_CUDA, std::string("ncclGetUniqueId: ") + nc->GetErrorString(r));
+    memcpy(id, &u, sizeof(u));
+    return TDNA_OK;
+}
+
+int32_t tdna_comm_init(tdna_ctx *c, const uint8_t *id, int32_t rank, int32_t nranks) {
+    if (!c || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(TDNA_E_ARG, "bad argument");
+    if (nranks > ROUTE_MAX_PARTS) return fail(TDNA_E_ARG, "at most 64 ranks");
+    if (c->comm.comm) return fail(TDNA_E_STATE, "the context already has a communicator");
+    std::string why;
+    const NcclApi *nc = nccl_api(&why);
+    if (!nc) return fail(TDNA_E_STATE, why);
+    CU(cudaSetDevice(c->device));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = nc->CommInitRank(&comm, nranks, u, rank);
+    if (r != ncclSuccess) return fail(TDNA_E_CUDA, std::string("ncclCommInitRank: ") + nc->GetErrorString(r));
+    c->comm.api = nc;
+    c->comm.comm = comm;
+    c->comm.rank = rank;
+    c->comm.nranks = nranks;
+    c->comm.enabled = true;
+    return TDNA_OK;
+}
+
+int32_t tdna_comm_destroy(tdna_ctx *c) {
+    if (!c) return fail(TDNA_E_ARG, "null ctx");
+    if (c->comm.comm) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        c->comm.api->CommDestroy(c->comm.comm);
+    }
+    c->comm = Comm();
+    return TDNA_OK;
+}
+
+int32_t tdna_comm_info(tdna_ctx *c, int32_t *rank, int32_t *nranks) {
+    if (!c) return fail(TDNA_E_ARG, "null ctx");
+    if (rank) *rank = c->comm.comm ? c->comm.rank : 0;
+    if (nranks) *nranks = c->comm.comm ? c->comm.nranks : 1;
+    return TDNA_OK;
+}
+
+int32_t tdna_init_multi(const int32_t *devices, int32_t ndev, tdna_ctx **out) {
+    if (!devices || !out || ndev < 1 || ndev > ROUTE_MAX_PARTS) return fail(TDNA_E_ARG, "bad argument");
+    for (int k = 0; k < ndev; k++) out[k] = nullptr;
+    auto undo = [&]() { for (int k = 0; k < ndev; k++) { if (out[k]) tdna_shutdown(out[k]); out[k] = nullptr; } };
+    for (int k = 0; k < ndev; k++) {
+        int rc = tdna_init(devices[k], &out[k]);
+        if (rc != TDNA_OK) { undo(); return rc; }
+    }
+    if (ndev == 1) return TDNA_OK;
+    std::string why;
+    const NcclApi *nc = nccl_api(&why);
+    if (!nc) { undo(); return fail(TDNA_E_STATE, why); }
+    ncclUniqueId u;
+    ncclResult_t r = nc->GetUniqueId(&u);
+    if (r == ncclSuccess) r = nc->GroupStart();
+    std::vector<ncclComm_t> comms((size_t)ndev, nullptr);
+    for (int k = 0; k < ndev && r == ncclSuccess; k++) {  // one thread, several devices: the inits must sit in one NCCL group
+        if (cudaSetDevice(devices[k]) != cudaSuccess) { r = ncclUnhandledCudaError; break; }
+        r = nc->CommInitRank(&comms[k], ndev, u, k);
+    }
+    ncclResult_t r2 = nc->GroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess) { undo(); return fail(TDNA_E_CUDA, std::string("NCCL communicator setup: ") + nc->GetErrorString(r)); }
+    for (int k = 0; k < ndev; k++) {
+        out[k]->comm.api = nc;
+        out[k]->comm.comm = comms[k];
+        out[k]->comm.rank = k;
+        out[k]->comm.nranks = ndev;
+        out[k]->comm.enabled = true;
+    }
     return TDNA_OK;
 }
 
@@ -928,8 +1052,24 @@ int32_t tdna_alignment_create(tdna_ctx *c, const uint8_t *symbols, int64_t n, in
     a->row_begin = 0;
     a->row_end = n;
     size_t sym_bytes = (size_t)(n - 1) * row_stride + L;
-    CU(DMALLOC(&a->d_sym, sym_bytes));
-    CU(cudaMemcpyAsync(a->d_sym, symbols, sym_bytes, cudaMemcpyDefault, c->stream));
+    const int G = c->comm.active() ? c->comm.nranks : 1;
+    if (G > 1 && n >= 1024 * (int64_t)G && !is_device_ptr(symbols)) {
+        // several GPUs, host symbols (the same list on every rank -- one JVM: the same array): each rank uploads 1/G of the rows over
+        // its own PCIe link and the slices are all-gathered over NVLink, instead of G full uploads through the host at once
+        const NcclApi *nc = c->comm.api;
+        const int64_t rs = (n + G - 1) / G;
+        const size_t slice = (size_t)rs * row_stride;
+        CU(DMALLOC(&a->d_sym, slice * G));
+        const int64_t r0 = std::min<int64_t>(n, (int64_t)c->comm.rank * rs);
+        const size_t off = (size_t)r0 * row_stride;
+        const size_t mine = off < sym_bytes ? std::min(slice, sym_bytes - off) : 0;
+        if (mine) CU(cudaMemcpyAsync(a->d_sym + off, symbols + off, mine, cudaMemcpyHostToDevice, c->stream));
+        ncclResult_t r = nc->AllGather(a->d_sym + (size_t)c->comm.rank * slice, a->d_sym, slice, ncclInt8, c->comm.comm, c->stream);
+        if (r != ncclSuccess) { tdna_alignment_destroy(a); return fail(TDNA_E_CUDA, std::string("ncclAllGather: ") + nc->GetErrorString(r)); }
+    } else {
+        CU(DMALLOC(&a->d_sym, sym_bytes));
+        CU(cudaMemcpyAsync(a->d_sym, symbols, sym_bytes, cudaMemcpyDefault, c->stream));
+    }
     CU(DMALLOC(&a->d_len, (size_t)n * 4));
     if (lengths) {
         CU(cudaMemcpyAsync(a->d_len, lengths, (size_t)n * 4, cudaMemcpyDefault, c->stream));
@@ -955,7 +1095,8 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
                     a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
-                    a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_seedlist, a->d_cursor, a->d_lj, a->d_ld};
+                    a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_seedlist, a->d_cursor, a->d_lj, a->d_ld,
+                    a->x_send, a->x_recv, a->x_state};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
     delete a;
@@ -1359,13 +1500,18 @@ static int stream_seed(tdna_aln *a, int part, int nparts) {
 // bulk: thresholds from the minima (all-reduced by the caller when there are several parts), then the
 // rest of the triangle.  rc TDNA_E_TOO_LARGE: the candidate buffer overflowed (thresholds never
 // tightened: e.g. one species only, or a list order in which neighbours are unrelated)
-static int stream_bulk(tdna_aln *a, int part, int nparts, long long *ncand_out) {
+static int stream_bulk_launch(tdna_aln *a, int part, int nparts) {  // enqueue only: no host round trip
     tdna_ctx *c = a->ctx;
     stream_thr_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n);
     c->launches++;
     CU(cudaGetLastError());
-    TRY(launch_stream(a, part, nparts, 2));
-    struct { unsigned long long ncand; int overflow; int pad; unsigned long long ncls[2]; unsigned long long nedge; unsigned long long qn; } h;
+    return launch_stream(a, part, nparts, 2);
+}
+struct StreamCounters { unsigned long long ncand; int overflow; int pad; unsigned long long ncls[2]; unsigned long long nedge; unsigned long long qn; };
+static int stream_bulk(tdna_aln *a, int part, int nparts, long long *ncand_out) {
+    tdna_ctx *c = a->ctx;
+    TRY(stream_bulk_launch(a, part, nparts));
+    StreamCounters h;
     CU(cudaMemcpyAsync(&h, a->d_stream_u64, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (h.overflow) {  // both counters kept counting past their buffers: they are the demand (grow_stream_buffers)
@@ -1374,9 +1520,9 @@ static int stream_bulk(tdna_aln *a, int part, int nparts, long long *ncand_out) 
         return fail(TDNA_E_TOO_LARGE, "streaming Best Match: candidate buffer overflow");
     }
     a->last_ncand = (long long)h.ncand;
-    a->last_ncls[0] = (long long)h.ncls[0];
-    a->last_ncls[1] = (long long)h.ncls[1];
-    a->last_nedge = (long long)h.nedge;
+    a->last_ncls[0] = a->local_ncls[0] = (long long)h.ncls[0];
+    a->last_ncls[1] = a->local_ncls[1] = (long long)h.ncls[1];
+    a->last_nedge = a->local_nedge = (long long)h.nedge;
     if (ncand_out) *ncand_out = (long long)h.ncand;
     return TDNA_OK;
 }
@@ -1414,7 +1560,7 @@ static int stream_merge(tdna_aln *a, const int32_t *cq, const int32_t *cj, const
                         const int32_t *flags, bool counts_ready) {
     tdna_ctx *c = a->ctx;
     TRY(ensure_stream_state(a));
-    if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+    TRY(ensure_res(a, a->n));
     size_t n = (size_t)a->n;
     unsigned gr = (unsigned)((ncand + 255) / 256);
     if (gr > 65535u * 4) gr = 65535u * 4;
@@ -1445,6 +1591,163 @@ static int stream_merge(tdna_aln *a, const int32_t *cq, const int32_t *cj, const
     c->launches++;
     CU(cudaGetLastError());
     return fill_shared(a, 0, a->n);
+}
+
+
+// ---- the same pass shared by the GPUs of a communicator (tdna_comm_init) ------------------------------------------------------
+// Every rank: seed its share of the diagonal blocks -> ncclAllReduce(MIN) of the 3n per-row minima -> its share of the triangle ->
+// queue -> candidate records -> records routed to the rank that OWNS the row (grouped ncclSend / ncclRecv of fixed-size segments,
+// each carrying its own count) -> ncclAllReduce(SUM) of the per-row state and the status words -> exact two-sweep summaries of the
+// rank's own rows -> ncclAllGather of the row records.  Everything is enqueued on the context's stream; the host waits ONCE, at
+// the end, and reads a status block that is identical on every rank (it was all-reduced), so that retries with larger buffers and
+// the dense fallback are taken by all ranks together.  Results are bit-identical to one GPU's: min / sum / or are order-free and
+// every rank's record list is complete below the row's final threshold.
+#define NC(call)                                                                                                          \
+    do {                                                                                                                  \
+        ncclResult_t r_ = (call);                                                                                         \
+        if (r_ != ncclSuccess && r_ != ncclInProgress) return fail(TDNA_E_CUDA, std::string(#call) + ": " + nc->GetErrorString(r_)); \
+    } while (0)
+
+static int64_t multi_seg_records(const tdna_aln *a, int G) {
+    int64_t seg = (48 * a->n) / ((int64_t)G * G);
+    if (seg < (1 << 14)) seg = 1 << 14;
+    return seg * a->x_scale;
+}
+
+static int ensure_multi_buffers(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
+    const int G = c->comm.nranks;
+    const int64_t seg = multi_seg_records(a, G);
+    if (a->x_send && a->x_seg == seg && a->x_nranks == G) return TDNA_OK;
+    for (long long **p : {&a->x_send, &a->x_recv, &a->x_state})
+        if (*p) { CU(DFREE(*p)); *p = nullptr; }
+    const size_t bytes = (size_t)G * (size_t)(seg + 1) * 16;
+    CU(DMALLOC(&a->x_send, bytes));
+    CU(DMALLOC(&a->x_recv, bytes));
+    CU(DMALLOC(&a->x_state, (size_t)(a->n + MULTI_STATE_EXTRA) * 8));
+    a->x_seg = seg;
+    a->x_nranks = G;
+    return TDNA_OK;
+}
+
+// One attempt.  *status: [0] segment overflow, [1] candidate / queue overflow (summed over the ranks), [2..4] class pushes / edges.
+static int multi_attempt(tdna_aln *a, bool want_bm, int64_t *status) {
+    tdna_ctx *c = a->ctx;
+    const NcclApi *nc = c->comm.api;
+    const int G = c->comm.nranks, rank = c->comm.rank;
+    const int64_t n = a->n, rpp = tdna_rows_per_part(n, G);
+    const int64_t q0 = std::min<int64_t>(n, (int64_t)rank * rpp), q1 = std::min<int64_t>(n, q0 + rpp);
+    TRY(ensure_multi_buffers(a));
+    TRY(ensure_res(a, (int64_t)G * rpp));
+    const int64_t seg = a->x_seg;
+    const size_t seg_bytes = (size_t)(seg + 1) * 16;
+    TRY(stream_seed(a, rank, G));
+    NC(nc->AllReduce(a->sp.mC, a->sp.mC, (size_t)3 * n, ncclUint64, ncclMin, c->comm.comm, c->stream));
+    TRY(stream_bulk_launch(a, rank, G));
+    pack_state_multi_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a->sp, n, a->x_state);
+    c->launches++;
+    if (want_bm) {
+        zero_headers_kernel<<<1, 64, 0, c->stream>>>(a->x_send, G, seg);
+        route_records_dev_kernel<<<(unsigned)c->sm_count * 4, 256, 0, c->stream>>>(a->sp, rpp, G, seg, a->x_send, a->x_state + n);
+        c->launches += 2;
+        CU(cudaGetLastError());
+        NC(nc->GroupStart());
+        for (int g = 0; g < G; g++) {
+            NC(nc->Send(reinterpret_cast<char *>(a->x_send) + (size_t)g * seg_bytes, seg_bytes, ncclInt8, g, c->comm.comm, c->stream));
+            NC(nc->Recv(reinterpret_cast<char *>(a->x_recv) + (size_t)g * seg_bytes, seg_bytes, ncclInt8, g, c->comm.comm, c->stream));
+        }
+        NC(nc->GroupEnd());
+    }
+    NC(nc->AllReduce(a->x_state, a->x_state, (size_t)(n + MULTI_STATE_EXTRA), ncclInt64, ncclSum, c->comm.comm, c->stream));
+    if (want_bm) {
+        const long long total = (long long)G * seg;  // upper bound of the records received
+        if (total > a->list_cap) {
+            if (a->d_lj) CU(DFREE(a->d_lj));
+            if (a->d_ld) CU(DFREE(a->d_ld));
+            a->d_lj = nullptr;
+            a->d_ld = nullptr;
+            a->list_cap = 0;
+            CU(DMALLOC(&a->d_lj, (size_t)total * 4));
+            CU(DMALLOC(&a->d_ld, (size_t)total * 8));
+            a->list_cap = total;
+        }
+        unsigned gr = (unsigned)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16);
+        unpack_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a->x_state, n, a->sp.inval, a->sp.flags);
+        CU(cudaMemsetAsync(a->sp.cnt, 0, (size_t)n * 4, c->stream));
+        CU(cudaMemsetAsync(a->d_cursor, 0, (size_t)n * 4, c->stream));
+        count_rows_hseg_kernel<<<gr, 256, 0, c->stream>>>(a->x_recv, G, seg, a->sp.cnt);
+        TRY(row_pointers(a, a->sp.cnt));
+        scatter_hseg_kernel<<<gr, 256, 0, c->stream>>>(a->x_recv, G, seg, a->d_ptr, a->d_cursor, a->d_lj, a->d_ld);
+        const long long guess = a->last_ncand > 0 ? a->last_ncand / std::max<int64_t>(n, 1) * (q1 - q0) : 15 * (long long)(q1 - q0);
+        launch_finalize(a, a->sp.inval, a->sp.flags, q0, q1, guess);
+        c->launches += 4;
+        CU(cudaGetLastError());
+        TRY(fill_shared(a, q0, q1));
+        if (q1 - q0 < rpp) {
+            zero_rows_kernel<<<64, 256, 0, c->stream>>>(a->d_res, q0 + (q1 - q0), (int64_t)rank * rpp + rpp);
+            c->launches++;
+        }
+        // in place: this rank's slice already sits at its offset of the gathered buffer
+        NC(nc->AllGather(a->d_res + (int64_t)rank * rpp, a->d_res, (size_t)rpp * sizeof(tdna_row_result), ncclInt8, c->comm.comm, c->stream));
+    }
+    // the one host synchronisation of the step: the all-reduced status words and this rank's own counters
+    CU(cudaMemcpyAsync(c->h_status, a->x_state + n, MULTI_STATE_EXTRA * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_status + 16, a->d_stream_u64, sizeof(StreamCounters), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < MULTI_STATE_EXTRA; k++) status[k] = c->h_status[k];
+    StreamCounters h;
+    memcpy(&h, c->h_status + 16, sizeof(h));
+    if (h.overflow) { a->need_cand = (long long)h.ncand; a->need_queue = (long long)h.qn; }
+    a->local_ncls[0] = (long long)h.ncls[0];
+    a->local_ncls[1] = (long long)h.ncls[1];
+    a->local_nedge = (long long)h.nedge;
+    a->last_ncls[0] = status[2];
+    a->last_ncls[1] = status[3];
+    a->last_nedge = status[4];
+    a->last_ncand = status[5];
+    return TDNA_OK;
+}
+
+static int best_match_dense(tdna_aln *a);
+// TDNA_E_TOO_LARGE (on every rank alike): the streaming pass cannot serve this list; the caller runs the dense row-band fallback
+static int multi_pass(tdna_aln *a, bool want_bm) {
+    int64_t status[MULTI_STATE_EXTRA];
+    for (int attempt = 0; attempt < 4; attempt++) {
+        TRY(multi_attempt(a, want_bm, status));
+        if (status[0] == 0 && status[1] == 0) return TDNA_OK;
+        // some rank overflowed: every rank sees the same two words and retries together
+        if (status[0]) a->x_scale *= 2;                                      // identical on every rank
+        if (a->need_cand || a->need_queue) {                                   // this rank's own buffers
+            if (!grow_stream_buffers(a) && a->last_kernel == TDNA_KERNEL_TENSOR && a->ctx->opt_count_kernel == TDNA_KERNEL_AUTO) a->avoid_tensor = true;
+        }
+    }
+    return fail(TDNA_E_TOO_LARGE, "streaming Best Match: a candidate buffer or exchange segment overflowed on some rank");
+}
+
+// dense fallback on several GPUs: every rank sweeps its own band of query rows, the row records are all-gathered
+static int multi_dense_rows(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
+    const NcclApi *nc = c->comm.api;
+    const int G = c->comm.nranks, rank = c->comm.rank;
+    const int64_t n = a->n, rpp = tdna_rows_per_part(n, G);
+    const int64_t q0 = std::min<int64_t>(n, (int64_t)rank * rpp), q1 = std::min<int64_t>(n, q0 + rpp);
+    TRY(ensure_res(a, (int64_t)G * rpp));
+    const int64_t rb = a->row_begin, re = a->row_end;
+    a->row_begin = q0;
+    a->row_end = q1;
+    a->mat_valid = false;
+    int rc = q1 > q0 ? best_match_dense(a) : TDNA_OK;
+    a->row_begin = rb;
+    a->row_end = re;
+    a->mat_valid = false;
+    TRY(rc);
+    if (q1 - q0 < rpp) {
+        zero_rows_kernel<<<64, 256, 0, c->stream>>>(a->d_res, q1, (int64_t)rank * rpp + rpp);
+        c->launches++;
+    }
+    NC(nc->AllGather(a->d_res + (int64_t)rank * rpp, a->d_res, (size_t)rpp * sizeof(tdna_row_result), ncclInt8, c->comm.comm, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TDNA_OK;
 }
 
 int32_t tdna_best_match_seed(tdna_aln *a, int32_t part, int32_t nparts, uint64_t **minima_dev) {
@@ -1505,7 +1808,7 @@ int32_t tdna_best_match_merge_gathered(tdna_aln *a, const int64_t *rec, int32_t 
     TRY(need_labels(a));
     TRY(ensure_packed(a));
     TRY(ensure_stream_state(a));
-    if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+    TRY(ensure_res(a, a->n));
     size_t n = (size_t)a->n;
     const long long total = (long long)nseg * seg_stride;  // upper bound of the records: sizes the lists without a host round trip
     if (total > a->list_cap) {
@@ -1579,7 +1882,7 @@ int32_t tdna_best_match_merge_routed(tdna_aln *a, int32_t part, int32_t nparts, 
     TRY(need_labels(a));
     TRY(ensure_packed(a));
     TRY(ensure_stream_state(a));
-    if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+    TRY(ensure_res(a, a->n));
     const size_t n = (size_t)a->n;
     const int64_t rpp = tdna_rows_per_part(a->n, nparts);
     const int64_t q0 = std::min<int64_t>(a->n, (int64_t)part * rpp), q1 = std::min<int64_t>(a->n, q0 + rpp);
@@ -1694,14 +1997,17 @@ static int analyze_stream(tdna_aln *a, tdna_analysis *io) {
         }
     }
     long long ncand = 0;
-    rc = stream_part(a, 0, 1, &ncand);
-    for (int attempt = 0; rc == TDNA_E_TOO_LARGE && attempt < 3 && grow_stream_buffers(a); attempt++) rc = stream_part(a, 0, 1, &ncand);
+    const bool multi = c->comm.active();  // the GPUs of the communicator share the pass (every rank makes this same call)
+    if (multi) rc = multi_pass(a, (io->want & TDNA_WANT_BEST_MATCH) != 0);
+    else {
+        rc = stream_part(a, 0, 1, &ncand);
+        for (int attempt = 0; rc == TDNA_E_TOO_LARGE && attempt < 3 && grow_stream_buffers(a); attempt++) rc = stream_part(a, 0, 1, &ncand);
+    }
     if (rc == TDNA_OK && (io->want & TDNA_WANT_BEST_MATCH)) {
-        if (!a->d_res) {
-            cudaError_t e = DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result));
-            if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
+        if (!multi) {
+            rc = ensure_res(a, a->n);
+            if (rc == TDNA_OK) rc = stream_merge(a, sp.cq, sp.cj, sp.cd, ncand, sp.inval, sp.flags, true);
         }
-        if (rc == TDNA_OK) rc = stream_merge(a, sp.cq, sp.cj, sp.cd, ncand, sp.inval, sp.flags, true);
         if (rc == TDNA_OK && io->rows) {
             cudaError_t e = cudaMemcpyAsync(io->rows, a->d_res, (size_t)a->n * sizeof(tdna_row_result), cudaMemcpyDefault, c->stream);
             if (e != cudaSuccess) rc = fail(TDNA_E_CUDA, cudaGetErrorString(e));
@@ -1711,14 +2017,17 @@ static int analyze_stream(tdna_aln *a, tdna_analysis *io) {
         io->n_intra = (io->want & TDNA_WANT_INTRA) ? a->last_ncls[0] : 0;
         io->n_inter = (io->want & TDNA_WANT_INTER) ? a->last_ncls[1] : 0;
         io->n_edges = (io->want & TDNA_WANT_EDGES) ? a->last_nedge : 0;
+        io->n_intra_local = (io->want & TDNA_WANT_INTRA) ? a->local_ncls[0] : 0;
+        io->n_inter_local = (io->want & TDNA_WANT_INTER) ? a->local_ncls[1] : 0;
+        io->n_edges_local = (io->want & TDNA_WANT_EDGES) ? a->local_nedge : 0;
         cudaError_t e = cudaSuccess;
         for (int k = 0; k < 2 && e == cudaSuccess; k++)
             if (own_cls[k]) {
-                int64_t m = a->last_ncls[k] < ccap[k] ? a->last_ncls[k] : ccap[k];
+                int64_t m = a->local_ncls[k] < ccap[k] ? a->local_ncls[k] : ccap[k];
                 if (m > 0) e = cudaMemcpyAsync(hcls[k], dcls[k], (size_t)m * 4, cudaMemcpyDefault, c->stream);
             }
         if (e == cudaSuccess && own_edges) {
-            int64_t m = a->last_nedge < io->edge_cap ? a->last_nedge : io->edge_cap;
+            int64_t m = a->local_nedge < io->edge_cap ? a->local_nedge : io->edge_cap;
             if (m > 0) {
                 e = cudaMemcpyAsync(io->edge_i, dei, (size_t)m * 4, cudaMemcpyDefault, c->stream);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(io->edge_j, dej, (size_t)m * 4, cudaMemcpyDefault, c->stream);
@@ -1732,10 +2041,45 @@ static int analyze_stream(tdna_aln *a, tdna_analysis *io) {
     return rc;
 }
 
+// several GPUs, dense fallback: Best Match rows from every rank's own band of query rows (all-gathered); class distances and
+// edges of the rank's own band with the totals all-reduced.  Every rank takes this path together (multi_pass's status is shared).
+static int analyze_dense_multi(tdna_aln *a, tdna_analysis *io) {
+    tdna_ctx *c = a->ctx;
+    const NcclApi *nc = c->comm.api;
+    const int G = c->comm.nranks, rank = c->comm.rank;
+    if (io->want & TDNA_WANT_BEST_MATCH) {
+        TRY(multi_dense_rows(a));
+        if (io->rows) CU(cudaMemcpyAsync(io->rows, a->d_res, (size_t)a->n * sizeof(tdna_row_result), cudaMemcpyDefault, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    const int64_t rpp = tdna_rows_per_part(a->n, G);
+    const int64_t q0 = std::min<int64_t>(a->n, (int64_t)rank * rpp), q1 = std::min<int64_t>(a->n, q0 + rpp);
+    const int64_t rb = a->row_begin, re = a->row_end;
+    a->row_begin = q0; a->row_end = q1; a->mat_valid = false;
+    int64_t loc[3] = {0, 0, 0};
+    int rc = TDNA_OK;
+    if (q1 > q0) {
+        if (rc == TDNA_OK && (io->want & TDNA_WANT_INTRA)) rc = class_distances_dense(a, TDNA_PD_INTRA, io->intra, io->intra_cap, &loc[0]);
+        if (rc == TDNA_OK && (io->want & TDNA_WANT_INTER)) rc = class_distances_dense(a, TDNA_PD_INTER, io->inter, io->inter_cap, &loc[1]);
+        if (rc == TDNA_OK && (io->want & TDNA_WANT_EDGES)) rc = edges_dense(a, io->edge_threshold, io->edge_i, io->edge_j, io->edge_d, io->edge_cap, &loc[2]);
+    }
+    a->row_begin = rb; a->row_end = re; a->mat_valid = false;
+    TRY(rc);
+    io->n_intra_local = loc[0]; io->n_inter_local = loc[1]; io->n_edges_local = loc[2];
+    long long *d_tot = reinterpret_cast<long long *>(c->d_counter);
+    CU(cudaMemcpyAsync(d_tot, loc, 24, cudaMemcpyHostToDevice, c->stream));
+    NC(nc->AllReduce(d_tot, d_tot, 3, ncclInt64, ncclSum, c->comm.comm, c->stream));
+    int64_t tot[3];
+    CU(cudaMemcpyAsync(tot, d_tot, 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    io->n_intra = tot[0]; io->n_inter = tot[1]; io->n_edges = tot[2];
+    return TDNA_OK;
+}
+
 static int analyze_dense(tdna_aln *a, tdna_analysis *io) {
     tdna_ctx *c = a->ctx;
     if (io->want & TDNA_WANT_BEST_MATCH) {
-        if (!a->d_res) CU(DMALLOC(&a->d_res, (size_t)a->n * sizeof(tdna_row_result)));
+        TRY(ensure_res(a, a->n));
         TRY(best_match_dense(a));
         int64_t rows = a->row_end - a->row_begin;
         if (io->rows && rows > 0)
@@ -1746,6 +2090,7 @@ static int analyze_dense(tdna_aln *a, tdna_analysis *io) {
     if (io->want & TDNA_WANT_INTRA) TRY(class_distances_dense(a, TDNA_PD_INTRA, io->intra, io->intra_cap, &io->n_intra));
     if (io->want & TDNA_WANT_INTER) TRY(class_distances_dense(a, TDNA_PD_INTER, io->inter, io->inter_cap, &io->n_inter));
     if (io->want & TDNA_WANT_EDGES) TRY(edges_dense(a, io->edge_threshold, io->edge_i, io->edge_j, io->edge_d, io->edge_cap, &io->n_edges));
+    io->n_intra_local = io->n_intra; io->n_inter_local = io->n_inter; io->n_edges_local = io->n_edges;
     return TDNA_OK;
 }
 
@@ -1757,6 +2102,16 @@ int32_t tdna_analyze(tdna_aln *a, tdna_analysis *io) {
     CU(cudaSetDevice(c->device));
     if (io->want & (TDNA_WANT_BEST_MATCH | TDNA_WANT_INTRA | TDNA_WANT_INTER)) TRY(need_labels(a));
     bool whole = a->row_begin == 0 && a->row_end == a->n;
+    if (whole && c->comm.active()) {
+        // the communicator's GPUs share the request; every decision below is the same on every rank (labels are part of the contract,
+        // the streaming pass reports an all-reduced status)
+        if (!a->has_labels) return fail(TDNA_E_STATE, "a multi-GPU pass needs the labels (tdna_alignment_set_labels)");
+        if (c->opt_best_match_path != TDNA_PATH_DENSE) {
+            int rc = analyze_stream(a, io);
+            if (rc != TDNA_E_TOO_LARGE || c->opt_best_match_path == TDNA_PATH_STREAM) return rc;
+        }
+        return analyze_dense_multi(a, io);
+    }
     // a materialised matrix of this very configuration is already resident (tdna_matrix_compute): sweeping it is cheaper than a pass
     bool have_matrix = a->mat_valid && c->mat_owner == a && !(io->want & TDNA_WANT_BEST_MATCH) && c->opt_best_match_path != TDNA_PATH_STREAM;
     if (whole && c->opt_best_match_path != TDNA_PATH_DENSE && a->has_labels && !have_matrix) {
@@ -1962,6 +2317,11 @@ int32_t tdna_set_option(tdna_ctx *c, int32_t key, int64_t value) {
         case TDNA_OPT_TILE_COLUMNS:
             if (value != 0 && value != 64 && value != 128) return fail(TDNA_E_ARG, "tile columns must be 0, 64 or 128");
             c->opt_tile_cn = (int)(value / 16);
+            return TDNA_OK;
+        case TDNA_OPT_MULTI:
+            if (value < 0 || value > 2) return fail(TDNA_E_ARG, "TDNA_OPT_MULTI is 0, 1 or 2");
+            c->comm.enabled = value != 0;
+            c->comm.force = value == 2;
             return TDNA_OK;
     }
     return fail(TDNA_E_ARG, "unknown option");
@@ -2206,11 +2566,23 @@ int32_t tdna_last_count_kernel(tdna_aln *a) {
     return a->last_kernel;
 }
 
+int32_t tdna_tensor_dims(tdna_aln *a) {
+    if (!a || a->tc_state != 1) return 0;
+    return a->tc_dims;
+}
+
 int32_t tdna_last_tile_pass_ms(tdna_ctx *c, float *ms) {
     if (!c || !ms) return fail(TDNA_E_ARG, "null argument");
     if (!c->ev_valid) return fail(TDNA_E_STATE, "no tile pass has run yet");
     CU(cudaSetDevice(c->device));
     CU(cudaEventSynchronize(c->ev_k1));
+    if (c->ev_split) {  // seed launch + bulk launch; the thresholds (and, on several GPUs, the all-reduce) between them are not tile work
+        float seed_ms = 0, bulk_ms = 0;
+        CU(cudaEventElapsedTime(&seed_ms, c->ev_k0, c->ev_s1));
+        CU(cudaEventElapsedTime(&bulk_ms, c->ev_b0, c->ev_k1));
+        *ms = seed_ms + bulk_ms;
+        return TDNA_OK;
+    }
     CU(cudaEventElapsedTime(ms, c->ev_k0, c->ev_k1));
     return TDNA_OK;
 }

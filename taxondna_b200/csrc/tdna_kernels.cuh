@@ -1287,6 +1287,94 @@ __global__ void __launch_bounds__(256) scatter_seg_kernel(const long long *__res
     }
 }
 
+// ---- in-library multi-GPU exchange (tdna_comm_init): nothing here needs a host round trip ---------------------------------
+// Segment g of an exchange buffer = one 16-byte header (word 0: the record count, used as the atomic cursor while routing)
+// followed by seg_stride 16-byte records, i.e. it starts at rec + 2 * g * (seg_stride + 1).  The record count of the pass is read
+// from device memory, so the whole step (tile pass -> route -> NCCL -> merge) is enqueued without waiting for the GPU.
+constexpr int MULTI_STATE_EXTRA = 8;  // state[n + k]: 0 segment overflow, 1 candidate / queue overflow, 2..3 class pushes, 4 edges, 5 candidates
+__global__ void __launch_bounds__(256) pack_state_multi_kernel(StreamParams sp, int64_t n, long long *__restrict__ state) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) {
+        state[n + 0] = 0;
+        state[n + 1] = *sp.overflow ? 1 : 0;
+        state[n + 2] = (long long)sp.ncls[0];
+        state[n + 3] = (long long)sp.ncls[1];
+        state[n + 4] = (long long)*sp.nedge;
+        state[n + 5] = (long long)*sp.ncand;
+        state[n + 6] = 0;
+        state[n + 7] = 0;
+    }
+    if (q >= n) return;
+    const int f = sp.flags[q];
+    state[q] = (long long)(uint32_t)sp.inval[q] | ((long long)(f & TDNA_ROW_SELF_VALID ? 1 : 0) << 32) | ((long long)(f & TDNA_ROW_NONFINITE ? 1 : 0) << 48);
+}
+__global__ void __launch_bounds__(64) zero_headers_kernel(long long *__restrict__ rec, int nparts, long long seg_stride) {
+    if (threadIdx.x < nparts) { rec[2 * threadIdx.x * (seg_stride + 1)] = 0; rec[2 * threadIdx.x * (seg_stride + 1) + 1] = 0; }
+}
+__global__ void __launch_bounds__(256) route_records_dev_kernel(StreamParams sp, int64_t rows_per_part, int nparts, long long seg_stride,
+                                                                long long *__restrict__ rec, long long *__restrict__ seg_overflow) {
+    __shared__ int s_cnt[ROUTE_MAX_PARTS];
+    __shared__ long long s_base[ROUTE_MAX_PARTS];
+    if (*sp.overflow) return;  // the record list has holes: the status word tells every rank to retry
+    const long long ncand = min((long long)*sp.ncand, sp.cap);
+    const long long chunks = (ncand + 255) / 256;
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        if (threadIdx.x < nparts) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const long long r = ch * 256 + threadIdx.x;
+        int dest = -1, local = 0, q = 0;
+        if (r < ncand) {
+            q = sp.cq[r];
+            dest = (int)(q / rows_per_part);
+            local = atomicAdd(&s_cnt[dest], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < nparts && s_cnt[threadIdx.x] > 0)
+            s_base[threadIdx.x] = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(rec + 2 * threadIdx.x * (seg_stride + 1)),
+                                                       (unsigned long long)s_cnt[threadIdx.x]);
+        __syncthreads();
+        if (dest >= 0) {
+            const long long pos = s_base[dest] + local;
+            if (pos < seg_stride) {
+                long long *o = rec + 2 * ((long long)dest * (seg_stride + 1) + 1 + pos);
+                o[0] = ((long long)q << 32) | (long long)(uint32_t)sp.cj[r];
+                o[1] = __double_as_longlong(sp.cd[r]);
+            } else *seg_overflow = 1;
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) count_rows_hseg_kernel(const long long *__restrict__ rec, int nseg, long long seg_stride, int *__restrict__ cnt) {
+    const long long total = (long long)nseg * seg_stride;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
+        const long long g = r / seg_stride, k = r % seg_stride;
+        const long long *seg = rec + 2 * g * (seg_stride + 1);
+        if (k >= min(seg[0], seg_stride)) continue;
+        atomicAdd(cnt + (int)(seg[2 + 2 * k] >> 32), 1);
+    }
+}
+__global__ void __launch_bounds__(256) scatter_hseg_kernel(const long long *__restrict__ rec, int nseg, long long seg_stride,
+                                                           const long long *__restrict__ ptr, int *__restrict__ cursor, int32_t *__restrict__ lj,
+                                                           double *__restrict__ ld) {
+    const long long total = (long long)nseg * seg_stride;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
+        const long long g = r / seg_stride, k = r % seg_stride;
+        const long long *seg = rec + 2 * g * (seg_stride + 1);
+        if (k >= min(seg[0], seg_stride)) continue;
+        const long long key = seg[2 + 2 * k];
+        const int q = (int)(key >> 32);
+        const long long slot = ptr[q] + atomicAdd(cursor + q, 1);
+        lj[slot] = (int32_t)(key & 0xffffffffll);
+        ld[slot] = __longlong_as_double(seg[3 + 2 * k]);
+    }
+}
+// rows past the end of the list in the last rank's slice: zero records, so that the all-gathered buffer is deterministic
+__global__ void __launch_bounds__(256) zero_rows_kernel(tdna_row_result *__restrict__ res, int64_t q0, int64_t q1) {
+    const int64_t words = (q1 - q0) * (int64_t)(sizeof(tdna_row_result) / 8);
+    long long *p = reinterpret_cast<long long *>(res + q0);
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < words; k += (int64_t)gridDim.x * blockDim.x) p[k] = 0;
+}
+
 // G lanes per query row (32 / G rows per warp): the two sweeps over the row's candidate list (complete below its threshold).
 // Lists average ~15 entries on barcode data, so eight lanes per row keep the lanes busy and the butterflies short; rows of large
 // species carry hundreds of entries and get a whole warp (the host picks G from the mean list length).

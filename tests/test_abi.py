@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for nm in names:
         assert hasattr(L, nm), "libtaxondna_cuda.so does not export %s" % nm
     assert sorted(_lib.EXPORTS) == names
-    assert L.tdna_abi_version() == 1
+    assert L.tdna_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
