@@ -358,7 +358,7 @@ class Bench:
         if rank == 0 and full:
             sampler.start()
         launches0 = ctx.launch_count()
-        step_ms, tile_ms = [], []
+        step_ms, tile_ms, phase_ms = [], [], []
         t_region0 = time.perf_counter()
         for _ in range(steps):
             self.flush.fill_(1)  # L2 flush between timed iterations (on torch's stream; joined below)
@@ -378,6 +378,8 @@ class Bench:
             step_ms.append(e0.elapsed_time(e1))
             if streaming:
                 tile_ms.append(ctx.last_tile_pass_ms())  # the count-tile launches of THIS step (CUDA events on the library's stream)
+                if world > 1:
+                    phase_ms.append(ctx.multi_phase_ms())
         self.barrier()
         t_region = time.perf_counter() - t_region0
         launches = ctx.launch_count() - launches0
@@ -418,6 +420,8 @@ class Bench:
             kern_ms = aln.time_matrix_kernel(max(3, min(20, steps)))
             kern_pairs = pairs if world == 1 else rows_mine * n  # symmetric triangle vs rectangular band
         out["kernel_ms"] = kern_ms
+        if phase_ms:  # rank 0's device time per phase of the multi-GPU pass, mean over the timed steps
+            out["phases_ms"] = {k: float(np.mean([p[k] for p in phase_ms if k in p])) for k in phase_ms[0]}
         if full:
             peaks, peak_src = measured_peaks()
             prof = {}
@@ -481,12 +485,18 @@ class Bench:
         h2d = sym.nbytes + world * 4 * 4 * n
         d2h = sum(self._gather_int(d2h_rank))
 
+        e2e_marks = []
+
         def step_e2e():
-            a2 = t.Alignment(ctx, sym_pinned.numpy())  # H2D of the symbols + pack
+            m = [time.perf_counter()]
+            a2 = t.Alignment(ctx, sym_pinned.numpy())  # H2D of the symbols (N > 1: this rank's 1/N of the rows + all-gather) + pack
+            m.append(time.perf_counter())
             a2.set_labels(*labels)
+            m.append(time.perf_counter())
             a2.set_config(mode, 300, True)
             if world > 1 and not streaming:
                 a2.set_row_range(b0, b1)
+            m.append(time.perf_counter())
             if kind.startswith("matrix"):
                 t.check(L_.tdna_matrix(a2.h, out_host.data_ptr(), None))
                 t.check(L_.tdna_class_distances(a2.h, t.PD_INTRA, h_intra.data_ptr(), n_intra, ctypes.byref(c64)))
@@ -499,9 +509,13 @@ class Bench:
                 t.check(L_.tdna_analyze(a2.h, ctypes.byref(io)))
             else:
                 a2.best_match_into(out_host.data_ptr())
+            m.append(time.perf_counter())
             a2.close()
+            m.append(time.perf_counter())
+            e2e_marks.append([1e3 * (y - x) for x, y in zip(m, m[1:])])
 
         step_e2e()
+        e2e_marks.clear()
         self.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -509,7 +523,9 @@ class Bench:
         self.barrier()
         e2e_s = self.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         out["e2e"] = {"value": pairs / e2e_s / 1e9, "unit": "Gpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                      "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
+                      "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                      "host_phases_ms_this_rank": dict(zip(("create(h2d+pack)", "labels", "config", "analysis(+d2h)", "destroy"),
+                                                           [float(x) for x in np.mean(np.array(e2e_marks), axis=0)]))}
 
         out["cpu_baseline"] = None
         if full and rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -579,8 +595,8 @@ def main():
             par = "single GPU, whole triangle"
             if world > 1:
                 par = ("inside the C ABI (tdna_comm_init): every %d-th unit of 128 tile slots of the triangle per rank; NCCL on the library's stream: "
-                       "all_reduce(min) of the seeded per-row minima, grouped send/recv of the candidate records to the rank that owns the row, "
-                       "all_reduce(sum) of the per-row state + status, all_gather of the row records each rank finalised; one host sync per step" % world)
+                       "all_reduce(min) of the seeded per-row minima, ONE grouped send/recv that carries the candidate records, the per-row state and the status "
+                       "words to the rank that owns the row, all_gather of the row records each rank finalised; one host sync per step" % world)
         else:
             par = "row bands, %d rank(s), rows [%d,%d) on rank 0" % (world, r["b0"], r["b1"])
         n, L, mode = r["n"], r["L"], r["mode"]
@@ -595,6 +611,8 @@ def main():
             "roofline": r.get("roofline"), "cpu_baseline": r["cpu_baseline"], "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"],
             "region_wall_s": r["region_wall_s"],
         }
+        if "phases_ms" in r:
+            line["phases_ms_rank0"] = r["phases_ms"]
         if "parity_vs_1gpu" in r:
             line["parity_vs_1gpu"] = r["parity_vs_1gpu"]
             line["result_sha256"] = r["result_sha256"]

@@ -349,6 +349,10 @@ int32_t tdna_last_count_kernel(tdna_aln *aln);
 /* Symbol dimensions per site of the one-hot operands count kernel (b) built for this alignment (5, or 4 when no row has an internal
  * gap / in K2P mode); 0 if they have not been built.  The roofline's algorithmic work per pair is 2 * dims * L int8 operations. */
 int32_t tdna_tensor_dims(tdna_aln *aln);
+/* Device time between the phase marks of the context's most recent multi-GPU pass (CUDA events on its stream), in order: seed launch,
+ * MIN all-reduce of the per-row minima, thresholds + bulk launch + queue resolution, routing + exchange of records / state / status,
+ * merge of the own rows, all-gather of the row records.  *n_out phases are written (at most cap). */
+int32_t tdna_multi_phase_ms(tdna_ctx *ctx, float *ms, int32_t cap, int32_t *n_out);
 /* Device time (CUDA events on the context's stream) of the most recent count-tile pass -- the tile
  * kernel launch(es) of the last matrix band or streaming pass; waits for it to finish. */
 int32_t tdna_last_tile_pass_ms(tdna_ctx *ctx, float *ms);

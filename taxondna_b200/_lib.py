@@ -69,7 +69,7 @@ EXPORTS = [
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
     "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_rows_per_part", "tdna_tensor_code", "tdna_consensus", "tdna_fasta_parse", "tdna_fasta_destroy", "tdna_fasta_count", "tdna_fasta_width", "tdna_fasta_records", "tdna_fasta_symbols", "tdna_alignment_create_from_fasta", "tdna_best_match_part_routed", "tdna_best_match_merge_routed", "tdna_set_option", "tdna_last_tile_pass_ms",
-    "tdna_tensor_dims", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
+    "tdna_tensor_dims", "tdna_multi_phase_ms", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -158,6 +158,7 @@ def load():
     L.tdna_tensor_counts.argtypes = [vp, vp]
     L.tdna_last_count_kernel.argtypes = [vp]
     L.tdna_tensor_dims.argtypes = [vp]
+    L.tdna_multi_phase_ms.argtypes = [vp, vp, i32, ctypes.POINTER(i32)]
     L.tdna_analyze.argtypes = [vp, ctypes.POINTER(Analysis)]
     L.tdna_best_match_seed.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
     L.tdna_best_match_part.argtypes = [vp, i32, i32, i32, ctypes.POINTER(StreamPart)]
@@ -226,6 +227,15 @@ class Context:
             t.copy_(torch.frombuffer(bytearray(Context.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(t, 0)
         self.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    MULTI_PHASES = ("seed", "allreduce_min", "bulk+resolve", "route+exchange", "merge_own_rows", "allgather_rows")
+
+    def multi_phase_ms(self):
+        """Device time of the phases of the most recent multi-GPU pass: {name: ms}."""
+        ms = (ctypes.c_float * 12)()
+        k = ctypes.c_int32()
+        check(self.L.tdna_multi_phase_ms(self.h, ms, 12, ctypes.byref(k)))
+        return {nm: float(ms[i]) for i, nm in zip(range(k.value), self.MULTI_PHASES)}
 
     def comm_destroy(self):
         check(self.L.tdna_comm_destroy(self.h))
@@ -398,12 +408,15 @@ class Alignment:
         ni, nn, ne = io.n_intra, io.n_inter, io.n_edges
         check(self.L.tdna_analyze(self.h, ctypes.byref(io)))
         assert (not intra or io.n_intra == ni) and (not inter or io.n_inter == nn) and (edges is None or io.n_edges == ne)
+        # with a communicator the variable-length lists hold THIS rank's share (n_*_local entries); the totals are in n_*
         if intra:
-            out["intra"] = out["intra"][:ni]
+            out["intra"] = out["intra"][:io.n_intra_local]
         if inter:
-            out["inter"] = out["inter"][:nn]
+            out["inter"] = out["inter"][:io.n_inter_local]
         if edges is not None:
-            out["edge_i"], out["edge_j"], out["edge_d"] = out["edge_i"][:ne], out["edge_j"][:ne], out["edge_d"][:ne]
+            k = io.n_edges_local
+            out["edge_i"], out["edge_j"], out["edge_d"] = out["edge_i"][:k], out["edge_j"][:k], out["edge_d"][:k]
+        out["totals"] = (io.n_intra, io.n_inter, io.n_edges)
         return out
 
     def last_count_kernel(self):

@@ -60,6 +60,8 @@ struct tdna_ctx {
     // (the MIN all-reduce of the seeded minima when several GPUs share the pass) is not tile work
     cudaEvent_t ev_k0 = nullptr, ev_s1 = nullptr, ev_b0 = nullptr, ev_k1 = nullptr;
     bool ev_valid = false, ev_split = false;
+    cudaEvent_t ev_ph[12] = {};       // phase marks of the most recent multi-GPU pass (tdna_multi_phase_ms)
+    int n_ph = 0;
     Comm comm;                        // tdna_comm_init: NCCL communicator of this context (one rank per GPU)
     int64_t *h_status = nullptr;      // pinned: the status words a multi-GPU pass reads back at its one and only host sync
     int opt_best_match_path = TDNA_PATH_AUTO;
@@ -554,9 +556,12 @@ int ensure_tc(tdna_aln *a) {
         std::vector<int64_t> pre(nbands + 1);
         pre[0] = 0;
         for (int b = 0; b < nbands; b++) {
+            // only real tiles are numbered (tdna_tc.cuh: slot_coords): a staircase over the band's first TC_BAND / 2 columns, then
+            // TC_BAND slots per column
             int64_t tjmin = ((int64_t)b * TC_BAND >> 1);
             int64_t cols = nct - tjmin > 0 ? nct - tjmin : 0;
-            pre[b + 1] = pre[b] + cols * TC_BAND;
+            int64_t tri = std::min<int64_t>(cols, TC_BAND >> 1);
+            pre[b + 1] = pre[b] + tri * (tri + 1) + (cols - tri) * TC_BAND;
         }
         if (cudaSuccess != DMALLOC(&a->d_tcprefix[1], (size_t)(nbands + 1) * 8)) flag = 1;
         else {
@@ -715,6 +720,7 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     // unit shares stay in this GPU's L2); units are dealt cyclically so that work AND candidates (which cluster near the
     // diagonal) are balanced across the parts
     p.unit = CL >= 2 ? 64 : 128;
+    if (phase == 0) p.unit = 1;  // the seed pass has a few hundred items in all: deal them one by one, or most parts get none
     int64_t units_total = (total + p.unit - 1) / p.unit;
     int64_t my_units = units_total > part ? (units_total - part + nparts - 1) / nparts : 0;
     p.t_offset = part;
@@ -901,6 +907,7 @@ int32_t tdna_init(int32_t device, tdna_ctx **out) {
     CU(cudaEventCreate(&c->ev_k1));
     CU(cudaEventCreate(&c->ev_s1));
     CU(cudaEventCreate(&c->ev_b0));
+    for (cudaEvent_t &e : c->ev_ph) CU(cudaEventCreate(&e));
     CU(cudaMallocHost(&c->h_status, 64 * sizeof(int64_t)));
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -922,6 +929,8 @@ int32_t tdna_shutdown(tdna_ctx *c) {
     c->comm.comm = nullptr;
     if (c->h_status) cudaFreeHost(c->h_status);
     for (cudaEvent_t e : {c->ev_k0, c->ev_k1, c->ev_s1, c->ev_b0})
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_ph)
         if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1621,10 +1630,10 @@ static int ensure_multi_buffers(tdna_aln *a) {
     if (a->x_send && a->x_seg == seg && a->x_nranks == G) return TDNA_OK;
     for (long long **p : {&a->x_send, &a->x_recv, &a->x_state})
         if (*p) { CU(DFREE(*p)); *p = nullptr; }
-    const size_t bytes = (size_t)G * (size_t)(seg + 1) * 16;
+    const size_t bytes = (size_t)G * (size_t)multi_seg_words(seg, tdna_rows_per_part(a->n, G)) * 8;
     CU(DMALLOC(&a->x_send, bytes));
     CU(DMALLOC(&a->x_recv, bytes));
-    CU(DMALLOC(&a->x_state, (size_t)(a->n + MULTI_STATE_EXTRA) * 8));
+    CU(DMALLOC(&a->x_state, (size_t)MULTI_STATE_EXTRA * 8));
     a->x_seg = seg;
     a->x_nranks = G;
     return TDNA_OK;
@@ -1640,26 +1649,29 @@ static int multi_attempt(tdna_aln *a, bool want_bm, int64_t *status) {
     TRY(ensure_multi_buffers(a));
     TRY(ensure_res(a, (int64_t)G * rpp));
     const int64_t seg = a->x_seg;
-    const size_t seg_bytes = (size_t)(seg + 1) * 16;
+    const long long segw = multi_seg_words(seg, rpp);
+    c->n_ph = 0;
+#define MARK() do { if (c->n_ph < 12) cudaEventRecord(c->ev_ph[c->n_ph++], c->stream); } while (0)
+    MARK();  // 0: start
     TRY(stream_seed(a, rank, G));
+    MARK();  // 1: seeded
     NC(nc->AllReduce(a->sp.mC, a->sp.mC, (size_t)3 * n, ncclUint64, ncclMin, c->comm.comm, c->stream));
+    MARK();  // 2: minima reduced
     TRY(stream_bulk_launch(a, rank, G));
-    pack_state_multi_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a->sp, n, a->x_state);
-    c->launches++;
+    MARK();  // 3: bulk + queue resolved
     if (want_bm) {
-        zero_headers_kernel<<<1, 64, 0, c->stream>>>(a->x_send, G, seg);
-        route_records_dev_kernel<<<(unsigned)c->sm_count * 4, 256, 0, c->stream>>>(a->sp, rpp, G, seg, a->x_send, a->x_state + n);
-        c->launches += 2;
+        multi_zero_kernel<<<1, 64, 0, c->stream>>>(a->x_send, G, segw, a->x_state);
+        route_records_dev_kernel<<<(unsigned)c->sm_count * 4, 256, 0, c->stream>>>(a->sp, rpp, G, seg, segw, a->x_send, a->x_state);
+        multi_pack_kernel<<<(unsigned)(((int64_t)G * rpp + 255) / 256), 256, 0, c->stream>>>(a->sp, n, rpp, G, seg, segw, a->x_send, a->x_state);
+        c->launches += 3;
         CU(cudaGetLastError());
         NC(nc->GroupStart());
         for (int g = 0; g < G; g++) {
-            NC(nc->Send(reinterpret_cast<char *>(a->x_send) + (size_t)g * seg_bytes, seg_bytes, ncclInt8, g, c->comm.comm, c->stream));
-            NC(nc->Recv(reinterpret_cast<char *>(a->x_recv) + (size_t)g * seg_bytes, seg_bytes, ncclInt8, g, c->comm.comm, c->stream));
+            NC(nc->Send(a->x_send + (size_t)g * segw, (size_t)segw, ncclInt64, g, c->comm.comm, c->stream));
+            NC(nc->Recv(a->x_recv + (size_t)g * segw, (size_t)segw, ncclInt64, g, c->comm.comm, c->stream));
         }
         NC(nc->GroupEnd());
-    }
-    NC(nc->AllReduce(a->x_state, a->x_state, (size_t)(n + MULTI_STATE_EXTRA), ncclInt64, ncclSum, c->comm.comm, c->stream));
-    if (want_bm) {
+        MARK();  // 4: records, state and status exchanged
         const long long total = (long long)G * seg;  // upper bound of the records received
         if (total > a->list_cap) {
             if (a->d_lj) CU(DFREE(a->d_lj));
@@ -1671,27 +1683,45 @@ static int multi_attempt(tdna_aln *a, bool want_bm, int64_t *status) {
             CU(DMALLOC(&a->d_ld, (size_t)total * 8));
             a->list_cap = total;
         }
-        unsigned gr = (unsigned)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16);
-        unpack_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a->x_state, n, a->sp.inval, a->sp.flags);
-        CU(cudaMemsetAsync(a->sp.cnt, 0, (size_t)n * 4, c->stream));
-        CU(cudaMemsetAsync(a->d_cursor, 0, (size_t)n * 4, c->stream));
-        count_rows_hseg_kernel<<<gr, 256, 0, c->stream>>>(a->x_recv, G, seg, a->sp.cnt);
-        TRY(row_pointers(a, a->sp.cnt));
-        scatter_hseg_kernel<<<gr, 256, 0, c->stream>>>(a->x_recv, G, seg, a->d_ptr, a->d_cursor, a->d_lj, a->d_ld);
+        const unsigned gr = (unsigned)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16);
+        multi_prep_kernel<<<(unsigned)((std::max<int64_t>(q1 - q0, MULTI_STATE_EXTRA) + 255) / 256), 256, 0, c->stream>>>(
+            a->x_recv, G, seg, segw, rpp, q0, q1, a->sp.inval, a->sp.flags, a->sp.cnt, a->d_cursor, a->x_state);
+        count_rows_hseg_kernel<<<gr, 256, 0, c->stream>>>(a->x_recv, G, seg, segw, a->sp.cnt);
+        // row pointers of the own rows only: d_ptr[q0 .. q1]
+        if (q1 - q0 <= (1 << 17)) {
+            scan_small_kernel<<<1, 1024, 0, c->stream>>>(a->sp.cnt + q0, q1 - q0, a->d_ptr + q0);
+            c->launches++;
+        } else {
+            const int64_t m = q1 - q0, nb = (m + SCAN_BLOCK - 1) / SCAN_BLOCK;
+            if (!a->d_scan) CU(DMALLOC(&a->d_scan, (size_t)((a->n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1) * 8));
+            scan_block_sums_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(a->sp.cnt + q0, m, a->d_scan);
+            scan_block_offsets_kernel<<<1, 1024, 0, c->stream>>>(a->d_scan, nb, a->d_ptr + q0 + m);
+            scan_apply_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(a->sp.cnt + q0, m, a->d_scan, a->d_ptr + q0);
+            c->launches += 3;
+        }
+        scatter_hseg_kernel<<<gr, 256, 0, c->stream>>>(a->x_recv, G, seg, segw, a->d_ptr, a->d_cursor, a->d_lj, a->d_ld);
         const long long guess = a->last_ncand > 0 ? a->last_ncand / std::max<int64_t>(n, 1) * (q1 - q0) : 15 * (long long)(q1 - q0);
         launch_finalize(a, a->sp.inval, a->sp.flags, q0, q1, guess);
         c->launches += 4;
         CU(cudaGetLastError());
         TRY(fill_shared(a, q0, q1));
         if (q1 - q0 < rpp) {
-            zero_rows_kernel<<<64, 256, 0, c->stream>>>(a->d_res, q0 + (q1 - q0), (int64_t)rank * rpp + rpp);
+            zero_rows_kernel<<<64, 256, 0, c->stream>>>(a->d_res, q1, (int64_t)rank * rpp + rpp);
             c->launches++;
         }
+        MARK();  // 5: own rows finalised
         // in place: this rank's slice already sits at its offset of the gathered buffer
         NC(nc->AllGather(a->d_res + (int64_t)rank * rpp, a->d_res, (size_t)rpp * sizeof(tdna_row_result), ncclInt8, c->comm.comm, c->stream));
+        MARK();  // 6: rows gathered
+    } else {  // a pass without Best Match rows exchanges nothing but its status
+        multi_zero_kernel<<<1, 64, 0, c->stream>>>(a->x_send, 0, segw, a->x_state);
+        multi_pack_kernel<<<1, 256, 0, c->stream>>>(a->sp, n, rpp, G, seg, segw, nullptr, a->x_state);
+        c->launches += 2;
+        NC(nc->AllReduce(a->x_state, a->x_state, (size_t)MULTI_STATE_EXTRA, ncclInt64, ncclSum, c->comm.comm, c->stream));
     }
-    // the one host synchronisation of the step: the all-reduced status words and this rank's own counters
-    CU(cudaMemcpyAsync(c->h_status, a->x_state + n, MULTI_STATE_EXTRA * 8, cudaMemcpyDeviceToHost, c->stream));
+#undef MARK
+    // the one host synchronisation of the step: the status words summed over the ranks and this rank's own counters
+    CU(cudaMemcpyAsync(c->h_status, a->x_state, MULTI_STATE_EXTRA * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(c->h_status + 16, a->d_stream_u64, sizeof(StreamCounters), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < MULTI_STATE_EXTRA; k++) status[k] = c->h_status[k];
@@ -2564,6 +2594,16 @@ int32_t tdna_tensor_code(int32_t L, int32_t dims, int32_t *code, uint32_t *W) {
 int32_t tdna_last_count_kernel(tdna_aln *a) {
     if (!a) return 0;
     return a->last_kernel;
+}
+
+int32_t tdna_multi_phase_ms(tdna_ctx *c, float *ms, int32_t cap, int32_t *n_out) {
+    if (!c || !ms || !n_out || cap < 0) return fail(TDNA_E_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    int k = 0;
+    for (; k + 1 < c->n_ph && k < cap; k++) CU(cudaEventElapsedTime(&ms[k], c->ev_ph[k], c->ev_ph[k + 1]));
+    *n_out = k;
+    return TDNA_OK;
 }
 
 int32_t tdna_tensor_dims(tdna_aln *a) {

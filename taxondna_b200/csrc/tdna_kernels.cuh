@@ -1288,31 +1288,22 @@ __global__ void __launch_bounds__(256) scatter_seg_kernel(const long long *__res
 }
 
 // ---- in-library multi-GPU exchange (tdna_comm_init): nothing here needs a host round trip ---------------------------------
-// Segment g of an exchange buffer = one 16-byte header (word 0: the record count, used as the atomic cursor while routing)
-// followed by seg_stride 16-byte records, i.e. it starts at rec + 2 * g * (seg_stride + 1).  The record count of the pass is read
-// from device memory, so the whole step (tile pass -> route -> NCCL -> merge) is enqueued without waiting for the GPU.
-constexpr int MULTI_STATE_EXTRA = 8;  // state[n + k]: 0 segment overflow, 1 candidate / queue overflow, 2..3 class pushes, 4 edges, 5 candidates
-__global__ void __launch_bounds__(256) pack_state_multi_kernel(StreamParams sp, int64_t n, long long *__restrict__ state) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q == 0) {
-        state[n + 0] = 0;
-        state[n + 1] = *sp.overflow ? 1 : 0;
-        state[n + 2] = (long long)sp.ncls[0];
-        state[n + 3] = (long long)sp.ncls[1];
-        state[n + 4] = (long long)*sp.nedge;
-        state[n + 5] = (long long)*sp.ncand;
-        state[n + 6] = 0;
-        state[n + 7] = 0;
-    }
-    if (q >= n) return;
-    const int f = sp.flags[q];
-    state[q] = (long long)(uint32_t)sp.inval[q] | ((long long)(f & TDNA_ROW_SELF_VALID ? 1 : 0) << 32) | ((long long)(f & TDNA_ROW_NONFINITE ? 1 : 0) << 48);
+// What rank s sends to rank g is ONE segment of segw 64-bit words:
+//   [0]            the record count (the atomic cursor while routing), [1] unused
+//   [2 ..)         seg_stride 16-byte records (row << 32 | column, fp64 bits of the distance) of rows that g owns
+//   then           rpp words: s's per-row state (invalid-pair count | self-valid << 32 | non-finite << 48) of g's rows
+//   then           MULTI_STATE_EXTRA status words of s (the same in every segment s sends)
+// so one grouped send / recv moves the records, the state and the status; the receiver sums state and status over the segments.
+// The record count of the pass is read from device memory: the whole step is enqueued without waiting for the GPU.
+constexpr int MULTI_STATE_EXTRA = 8;  // status: 0 segment overflow, 1 candidate / queue overflow, 2..3 class pushes, 4 edges, 5 candidates
+__host__ __device__ inline long long multi_seg_words(long long seg_stride, long long rpp) { return 2 * (seg_stride + 1) + rpp + MULTI_STATE_EXTRA; }
+
+__global__ void __launch_bounds__(64) multi_zero_kernel(long long *__restrict__ send, int nparts, long long segw, long long *__restrict__ status) {
+    if (threadIdx.x < nparts) { send[threadIdx.x * segw] = 0; send[threadIdx.x * segw + 1] = 0; }
+    if (threadIdx.x == 0) status[0] = 0;
 }
-__global__ void __launch_bounds__(64) zero_headers_kernel(long long *__restrict__ rec, int nparts, long long seg_stride) {
-    if (threadIdx.x < nparts) { rec[2 * threadIdx.x * (seg_stride + 1)] = 0; rec[2 * threadIdx.x * (seg_stride + 1) + 1] = 0; }
-}
-__global__ void __launch_bounds__(256) route_records_dev_kernel(StreamParams sp, int64_t rows_per_part, int nparts, long long seg_stride,
-                                                                long long *__restrict__ rec, long long *__restrict__ seg_overflow) {
+__global__ void __launch_bounds__(256) route_records_dev_kernel(StreamParams sp, int64_t rows_per_part, int nparts, long long seg_stride, long long segw,
+                                                                long long *__restrict__ send, long long *__restrict__ seg_overflow) {
     __shared__ int s_cnt[ROUTE_MAX_PARTS];
     __shared__ long long s_base[ROUTE_MAX_PARTS];
     if (*sp.overflow) return;  // the record list has holes: the status word tells every rank to retry
@@ -1330,13 +1321,12 @@ __global__ void __launch_bounds__(256) route_records_dev_kernel(StreamParams sp,
         }
         __syncthreads();
         if (threadIdx.x < nparts && s_cnt[threadIdx.x] > 0)
-            s_base[threadIdx.x] = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(rec + 2 * threadIdx.x * (seg_stride + 1)),
-                                                       (unsigned long long)s_cnt[threadIdx.x]);
+            s_base[threadIdx.x] = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(send + threadIdx.x * segw), (unsigned long long)s_cnt[threadIdx.x]);
         __syncthreads();
         if (dest >= 0) {
             const long long pos = s_base[dest] + local;
             if (pos < seg_stride) {
-                long long *o = rec + 2 * ((long long)dest * (seg_stride + 1) + 1 + pos);
+                long long *o = send + dest * segw + 2 + 2 * pos;
                 o[0] = ((long long)q << 32) | (long long)(uint32_t)sp.cj[r];
                 o[1] = __double_as_longlong(sp.cd[r]);
             } else *seg_overflow = 1;
@@ -1344,22 +1334,57 @@ __global__ void __launch_bounds__(256) route_records_dev_kernel(StreamParams sp,
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(256) count_rows_hseg_kernel(const long long *__restrict__ rec, int nseg, long long seg_stride, int *__restrict__ cnt) {
+// the state slices and the status words of every segment; status[0] (segment overflow) was set by the routing kernel.  send == nullptr:
+// a pass without Best Match rows exchanges nothing -- only the status block (all-reduced by the caller) is written
+__global__ void __launch_bounds__(256) multi_pack_kernel(StreamParams sp, int64_t n, int64_t rpp, int nparts, long long seg_stride, long long segw,
+                                                         long long *__restrict__ send, long long *__restrict__ status) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    long long st[MULTI_STATE_EXTRA] = {status[0], *sp.overflow ? 1 : 0, (long long)sp.ncls[0], (long long)sp.ncls[1], (long long)*sp.nedge, (long long)*sp.ncand, 0, 0};
+    if (q < MULTI_STATE_EXTRA) status[q] = st[q];
+    if (!send) return;
+    if (q < (int64_t)nparts * MULTI_STATE_EXTRA) send[(q / MULTI_STATE_EXTRA) * segw + 2 * (seg_stride + 1) + rpp + q % MULTI_STATE_EXTRA] = st[q % MULTI_STATE_EXTRA];
+    if (q >= (int64_t)nparts * rpp) return;
+    long long v = 0;
+    if (q < n) {
+        const int f = sp.flags[q];
+        v = (long long)(uint32_t)sp.inval[q] | ((long long)(f & TDNA_ROW_SELF_VALID ? 1 : 0) << 32) | ((long long)(f & TDNA_ROW_NONFINITE ? 1 : 0) << 48);
+    }
+    send[(q / rpp) * segw + 2 * (seg_stride + 1) + q % rpp] = v;
+}
+// receiver: the own rows' state summed over the segments, list counters cleared, the status summed
+__global__ void __launch_bounds__(256) multi_prep_kernel(const long long *__restrict__ recv, int nparts, long long seg_stride, long long segw, int64_t rpp,
+                                                         int64_t q0, int64_t q1, int *__restrict__ inval, int *__restrict__ flags, int *__restrict__ cnt,
+                                                         int *__restrict__ cursor, long long *__restrict__ status) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < MULTI_STATE_EXTRA) {
+        long long t = 0;
+        for (int g = 0; g < nparts; g++) t += recv[g * segw + 2 * (seg_stride + 1) + rpp + r];
+        status[r] = t;
+    }
+    if (q0 + r >= q1) return;
+    long long sum = 0;
+    for (int g = 0; g < nparts; g++) sum += recv[g * segw + 2 * (seg_stride + 1) + r];
+    inval[q0 + r] = (int)(sum & 0xffffffffll);
+    flags[q0 + r] = (((sum >> 32) & 0xffff) ? TDNA_ROW_SELF_VALID : 0) | (((sum >> 48) & 0xffff) ? TDNA_ROW_NONFINITE : 0);
+    cnt[q0 + r] = 0;
+    cursor[q0 + r] = 0;
+}
+__global__ void __launch_bounds__(256) count_rows_hseg_kernel(const long long *__restrict__ recv, int nseg, long long seg_stride, long long segw, int *__restrict__ cnt) {
     const long long total = (long long)nseg * seg_stride;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
         const long long g = r / seg_stride, k = r % seg_stride;
-        const long long *seg = rec + 2 * g * (seg_stride + 1);
+        const long long *seg = recv + g * segw;
         if (k >= min(seg[0], seg_stride)) continue;
         atomicAdd(cnt + (int)(seg[2 + 2 * k] >> 32), 1);
     }
 }
-__global__ void __launch_bounds__(256) scatter_hseg_kernel(const long long *__restrict__ rec, int nseg, long long seg_stride,
+__global__ void __launch_bounds__(256) scatter_hseg_kernel(const long long *__restrict__ recv, int nseg, long long seg_stride, long long segw,
                                                            const long long *__restrict__ ptr, int *__restrict__ cursor, int32_t *__restrict__ lj,
                                                            double *__restrict__ ld) {
     const long long total = (long long)nseg * seg_stride;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
         const long long g = r / seg_stride, k = r % seg_stride;
-        const long long *seg = rec + 2 * g * (seg_stride + 1);
+        const long long *seg = recv + g * segw;
         if (k >= min(seg[0], seg_stride)) continue;
         const long long key = seg[2 + 2 * k];
         const int q = (int)(key >> 32);
@@ -1367,6 +1392,25 @@ __global__ void __launch_bounds__(256) scatter_hseg_kernel(const long long *__re
         lj[slot] = (int32_t)(key & 0xffffffffll);
         ld[slot] = __longlong_as_double(seg[3 + 2 * k]);
     }
+}
+// one CTA: exclusive scan of cnt[0..m) into ptr[0..m] (a rank's own rows: a few thousand)
+__global__ void __launch_bounds__(1024) scan_small_kernel(const int *__restrict__ cnt, int64_t m, long long *__restrict__ ptr) {
+    __shared__ long long s_part[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (m + 1023) / 1024, b = t * per, e = min(m, b + per);
+    long long sum = 0;
+    for (int64_t i = b; i < e; i++) sum += cnt[i];
+    s_part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        long long v = t >= off ? s_part[t - off] : 0;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    long long run = s_part[t] - sum;
+    for (int64_t i = b; i < e; i++) { ptr[i] = run; run += cnt[i]; }
+    if (t == 1023) ptr[m] = s_part[1023];
 }
 // rows past the end of the list in the last rank's slice: zero records, so that the all-gathered buffer is deterministic
 __global__ void __launch_bounds__(256) zero_rows_kernel(tdna_row_result *__restrict__ res, int64_t q0, int64_t q1) {

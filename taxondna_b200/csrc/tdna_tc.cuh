@@ -95,10 +95,26 @@ __device__ __forceinline__ bool slot_coords(const Params &p, const int64_t *pref
         int mid = (lo + hi) >> 1;
         if (prefix[mid] <= t) lo = mid; else hi = mid;
     }
+    // Slots of a band, column tile by column tile: column c of the band (tile tj = tjmin + c) meets the band's first min(band, 2c + 2)
+    // row tiles (the rest lie below the diagonal), so the first band / 2 columns form a staircase of c(c + 1) slots before column c
+    // and every later column holds `band` slots.  Only real tiles are numbered: parts that take units of consecutive slots
+    // cyclically get equal work (a rectangular numbering left the staircase's holes to some parts and not to others: 16 % imbalance
+    // at eight parts).  Counts are even, so the slot pairs (2u, 2u + 1) of the two-CTA clusters stay adjacent row tiles of one column.
     const int64_t r = t - prefix[lo];
-    const int ti0 = lo * p.band;
-    ti = ti0 + (int)(r % p.band);
-    tj = (ti0 >> 1) + (int)(r / p.band);
+    const int ti0 = lo * p.band, tjmin = ti0 >> 1;
+    const int cols = p.nct - tjmin, tri = min(cols, p.band >> 1);
+    const int64_t T = (int64_t)tri * (tri + 1);
+    if (r < T) {
+        int c = (int)((sqrtf(4.0f * (float)r + 1.0f) - 1.0f) * 0.5f);
+        while ((int64_t)c * (c + 1) > r) c--;
+        while ((int64_t)(c + 1) * (c + 2) <= r) c++;
+        ti = ti0 + (int)(r - (int64_t)c * (c + 1));
+        tj = tjmin + c;
+    } else {
+        const int64_t r2 = r - T;
+        ti = ti0 + (int)(r2 % p.band);
+        tj = tjmin + tri + (int)(r2 / p.band);
+    }
     return ti < p.nrt && tj < p.nct && tj >= (ti >> 1);
 }
 
