@@ -131,8 +131,11 @@ int64_t tdna_launch_count(tdna_ctx *ctx);
 /* symbols: n rows of `row_stride` bytes, alphabet after Sequence.changeSequence
  * (Common/DNA/Sequence.java:751-853): ACGT RYKMSWBDHVN - _ ? ; lengths[i] <= L is the row's own
  * length (shorter rows behave as '?'-padded: the reference loops to min(len1,len2),
- * Sequence.java:1326-1327); lengths may be NULL (all L).  The symbols are copied to the device
- * and packed there into bit-planes; nothing of the caller's memory is retained. */
+ * Sequence.java:1326-1327; TDNA_E_ARG if a host lengths[i] is outside [0, L]); lengths may be NULL (all L).  The symbols are copied
+ * to the device and packed there into bit-planes; nothing of the caller's memory is retained.  Host symbols of 8,192+ rows are
+ * uploaded in row chunks while the chunks that have arrived are packed and (for the default configuration: uncorrected p,
+ * ambiguity allowed) encoded into count kernel (b)'s operands, so the PCIe time hides that work; with a communicator each rank
+ * uploads 1/G of the rows and the slices are all-gathered over NVLink. */
 int32_t tdna_alignment_create(tdna_ctx *ctx, const uint8_t *symbols, int64_t n, int32_t L,
                               int64_t row_stride, const int32_t *lengths, tdna_aln **out);
 int32_t tdna_alignment_destroy(tdna_aln *aln);
@@ -293,6 +296,24 @@ typedef struct {
                                                             communicator the lists hold this rank's share and the host concatenates */
 } tdna_analysis;
 int32_t tdna_analyze(tdna_aln *aln, tdna_analysis *io);
+
+/* One analysis of a list that is not on the device yet, in ONE call: what a module does when its list has just been loaded or edited
+ * (SpeciesIdentifier's modules rebuild everything on dataChanged(), UIExtension.java:40).  Same results as tdna_alignment_create +
+ * tdna_alignment_set_labels + tdna_set_config + tdna_analyze, one downcall instead of four.  Nothing of the caller's memory is
+ * referenced after the call returns.  *aln_out (optional) receives the resident alignment for further calls; with aln_out == NULL it
+ * is destroyed. */
+typedef struct {
+    const uint8_t *symbols;   /* as tdna_alignment_create */
+    int64_t n;
+    int32_t L;
+    int32_t mode;             /* TDNA_PDM_* */
+    int64_t row_stride;
+    const int32_t *lengths;   /* may be NULL */
+    const int32_t *species_id, *genus_id, *epithet_rank, *fullname_rank; /* as tdna_alignment_set_labels; all NULL = no labels */
+    int32_t min_overlap;
+    int32_t ambiguous_allowed;
+} tdna_host_list;
+int32_t tdna_analyze_host(tdna_ctx *ctx, const tdna_host_list *in, tdna_analysis *io, tdna_aln **aln_out);
 
 /* ---- options ------------------------------------------------------------------------------------ */
 enum { TDNA_OPT_BEST_MATCH_PATH = 1, /* TDNA_PATH_*: how tdna_best_match computes a whole-range request */

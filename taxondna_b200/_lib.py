@@ -41,6 +41,14 @@ class Analysis(ctypes.Structure):
                 ("n_intra_local", ctypes.c_int64), ("n_inter_local", ctypes.c_int64), ("n_edges_local", ctypes.c_int64)]
 
 
+class HostList(ctypes.Structure):
+    """tdna_host_list: a list that is not on the device yet (tdna_analyze_host)."""
+    _fields_ = [("symbols", ctypes.c_void_p), ("n", ctypes.c_int64), ("L", ctypes.c_int32), ("mode", ctypes.c_int32),
+                ("row_stride", ctypes.c_int64), ("lengths", ctypes.c_void_p),
+                ("species_id", ctypes.c_void_p), ("genus_id", ctypes.c_void_p), ("epithet_rank", ctypes.c_void_p), ("fullname_rank", ctypes.c_void_p),
+                ("min_overlap", ctypes.c_int32), ("ambiguous_allowed", ctypes.c_int32)]
+
+
 class StreamPart(ctypes.Structure):
     """tdna_stream_part: device pointers to one part's streaming Best-Match output."""
     _fields_ = [("cand_row", ctypes.c_void_p), ("cand_col", ctypes.c_void_p), ("cand_d", ctypes.c_void_p),
@@ -69,7 +77,7 @@ EXPORTS = [
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
     "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_rows_per_part", "tdna_tensor_code", "tdna_consensus", "tdna_fasta_parse", "tdna_fasta_destroy", "tdna_fasta_count", "tdna_fasta_width", "tdna_fasta_records", "tdna_fasta_symbols", "tdna_alignment_create_from_fasta", "tdna_best_match_part_routed", "tdna_best_match_merge_routed", "tdna_set_option", "tdna_last_tile_pass_ms",
-    "tdna_tensor_dims", "tdna_multi_phase_ms", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
+    "tdna_tensor_dims", "tdna_multi_phase_ms", "tdna_analyze_host", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -160,6 +168,7 @@ def load():
     L.tdna_tensor_dims.argtypes = [vp]
     L.tdna_multi_phase_ms.argtypes = [vp, vp, i32, ctypes.POINTER(i32)]
     L.tdna_analyze.argtypes = [vp, ctypes.POINTER(Analysis)]
+    L.tdna_analyze_host.argtypes = [vp, ctypes.POINTER(HostList), ctypes.POINTER(Analysis), vp]
     L.tdna_best_match_seed.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
     L.tdna_best_match_part.argtypes = [vp, i32, i32, i32, ctypes.POINTER(StreamPart)]
     L.tdna_best_match_merge.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
@@ -278,6 +287,31 @@ class Context:
         a, b = ctypes.c_double(), ctypes.c_double()
         check(self.L.tdna_measure_int_peaks(self.h, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
+
+
+def host_list(symbols, labels, mode, min_overlap, ambiguous_allowed=True, lengths=None):
+    """HostList over numpy arrays (kept alive by the returned tuple: (HostList, keepalive))."""
+    symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+    labs = [np.ascontiguousarray(a, dtype=np.int32) for a in labels] if labels is not None else [None] * 4
+    lens = np.ascontiguousarray(lengths, dtype=np.int32) if lengths is not None else None
+    h = HostList()
+    h.symbols, h.n, h.L, h.mode, h.row_stride = symbols.ctypes.data, symbols.shape[0], symbols.shape[1], int(mode), symbols.strides[0]
+    h.lengths = lens.ctypes.data if lens is not None else None
+    if labels is not None:
+        h.species_id, h.genus_id, h.epithet_rank, h.fullname_rank = [a.ctypes.data for a in labs]
+    h.min_overlap, h.ambiguous_allowed = int(min_overlap), 1 if ambiguous_allowed else 0
+    return h, (symbols, labs, lens)
+
+
+def best_match_host(ctx, symbols, labels, mode, min_overlap, ambiguous_allowed=True, lengths=None, out=None):
+    """Best Match rows of a list that is not on the device yet, in one call (tdna_analyze_host: the upload is pipelined with the pass)."""
+    h, keep = host_list(symbols, labels, mode, min_overlap, ambiguous_allowed, lengths)
+    r = out if out is not None else np.zeros(h.n, dtype=ROW_RESULT_DTYPE)
+    io = Analysis()
+    io.want = WANT_BEST_MATCH
+    io.rows = r.ctypes.data
+    check(ctx.L.tdna_analyze_host(ctx.h, ctypes.byref(h), ctypes.byref(io), None))
+    return r
 
 
 class Alignment:

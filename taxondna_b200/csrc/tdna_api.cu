@@ -2,6 +2,8 @@
 // N x N pair space through HBM, kernel launches.  No CPU arithmetic path exists here by design.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -62,6 +64,8 @@ struct tdna_ctx {
     bool ev_valid = false, ev_split = false;
     cudaEvent_t ev_ph[12] = {};       // phase marks of the most recent multi-GPU pass (tdna_multi_phase_ms)
     int n_ph = 0;
+    cudaStream_t copy_stream = nullptr;  // chunked upload (tdna_alignment_create): the H2D copies; pack + encode follow on `stream`
+    cudaEvent_t ev_copy[16] = {};
     Comm comm;                        // tdna_comm_init: NCCL communicator of this context (one rank per GPU)
     int64_t *h_status = nullptr;      // pinned: the status words a multi-GPU pass reads back at its one and only host sync
     int opt_best_match_path = TDNA_PATH_AUTO;
@@ -117,6 +121,8 @@ struct tdna_aln {
     bool avoid_tensor = false;  // AUTO: kernel (b)'s queue overflowed on this alignment (static thresholds too loose): use kernel (a)
     // count kernel (b): one-hot int8 operands (tdna_tc.cuh)
     uint8_t *d_tcA = nullptr, *d_tcB = nullptr, *d_tcfull = nullptr, *d_tcpanel_amb = nullptr;
+    int *d_tcflag = nullptr;       // [0] a symbol outside the alphabet met while encoding, [1] some IUPAC ambiguity letter
+    tc::EncodeValues tc_values = {};
     int32_t *d_tcamb = nullptr;  // per row: sites holding a letter the operands cannot express (nullptr state: see tc_has_amb)
     bool tc_has_amb = false;
     int tc_state = 0;  // 0 = not built, 1 = ready, -1 = not eligible
@@ -169,7 +175,8 @@ template <int KM> PlaneBits plane_bits() {
     return pb;
 }
 
-int pack(tdna_aln *a) {
+// mode -> plane set; (re)allocates the planes.  The pack kernel itself runs in pack() (whole alignment) or chunk by chunk (aln_build)
+int pack_prepare(tdna_aln *a, PlaneBits *pb_out) {
     tdna_ctx *c = a->ctx;
     int km;
     if (a->mode == TDNA_PDM_K2P) km = KM_K2P;
@@ -190,10 +197,22 @@ int pack(tdna_aln *a) {
         CU(DMALLOC(&a->d_planes, words * 4));
         a->planes_words = words;
     }
+    a->kmode = km;
+    a->P = P;
+    a->mat_valid = false;
+    *pb_out = pb;
+    return TDNA_OK;
+}
+
+int pack(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
+    PlaneBits pb;
+    TRY(pack_prepare(a, &pb));
+    const int P = a->P;
     int *d_err = reinterpret_cast<int *>(c->d_counter);
     CU(cudaMemsetAsync(d_err, 0, 8, c->stream));
     int64_t total = a->npad * a->W;
-    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->npad, a->sym_stride, a->W, P, pb,
+    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, 0, a->npad, a->sym_stride, a->W, P, a->L, pb,
                                                                        a->d_planes, d_err);
     c->launches++;
     CU(cudaGetLastError());
@@ -201,10 +220,7 @@ int pack(tdna_aln *a) {
     CU(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (err) return fail(TDNA_E_SYMBOL, "a symbol outside the normalised alphabet ACGT RYKMSWBDHVN - _ ?");
-    a->kmode = km;
-    a->P = P;
     a->packed = true;
-    a->mat_valid = false;
     return TDNA_OK;
 }
 
@@ -400,6 +416,26 @@ static int launch_stream_popc(tdna_aln *a, int part, int nparts, int phases) {
     }
 }
 
+// kernel (b) after its bulk launch(es): the queued pairs -> minima -> final thresholds -> candidate records
+static int tc_resolve_queue(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
+    TRY(set_stream_symbol(a, false));
+    int wshift = 0;
+    while ((1u << wshift) < a->tc_W) wshift++;
+    unsigned grid = (unsigned)c->sm_count * 8;
+    tc::ResolveArgs ra = {wshift, a->tc_W - 1u, a->min_overlap, (a->kmode == KM_K2P || a->tc_has_amb) ? a->d_planes : nullptr, a->W,
+                          a->kmode == KM_K2P ? 1 : 0};
+    if (a->sp.want & TDNA_WANT_BEST_MATCH) {
+        tc::resolve_min_kernel<<<grid, 256, 0, c->stream>>>(a->sp, ra);
+        stream_thr_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n);
+        c->launches += 2;
+    }
+    tc::resolve_emit_kernel<<<grid, 256, 0, c->stream>>>(a->sp, ra);
+    c->launches++;
+    CU(cudaGetLastError());
+    return TDNA_OK;
+}
+
 // phases: bit 0 = diagonal blocks, bit 1 = the rest of the triangle
 int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
     tdna_ctx *c = a->ctx;
@@ -420,21 +456,7 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
             CU(cudaEventRecord(c->ev_k1, c->stream));
             c->ev_valid = true;
             c->ev_split = true;
-            // the queued pairs -> minima -> final thresholds -> candidate records
-            TRY(set_stream_symbol(a, false));
-            int wshift = 0;
-            while ((1u << wshift) < a->tc_W) wshift++;
-            unsigned grid = (unsigned)c->sm_count * 8;
-            tc::ResolveArgs ra = {wshift, a->tc_W - 1u, a->min_overlap, (a->kmode == KM_K2P || a->tc_has_amb) ? a->d_planes : nullptr, a->W,
-                                  a->kmode == KM_K2P ? 1 : 0};
-            if (a->sp.want & TDNA_WANT_BEST_MATCH) {
-                tc::resolve_min_kernel<<<grid, 256, 0, c->stream>>>(a->sp, ra);
-                stream_thr_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n);
-                c->launches += 2;
-            }
-            tc::resolve_emit_kernel<<<grid, 256, 0, c->stream>>>(a->sp, ra);
-            c->launches++;
-            CU(cudaGetLastError());
+            TRY(tc_resolve_queue(a));
         }
         return TDNA_OK;
     }
@@ -442,12 +464,22 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
 }
 
 // ---- count kernel (b): operands, launches ----------------------------------------------------------
-static bool tc_pair_mode() {  // TDNA_TC_CLUSTER: 1 = single CTAs, 2 = pairs sharing the b-panel by multicast, 3 = cta_group::2 MMAs
-    const char *e = getenv("TDNA_TC_CLUSTER");  // default 2: measured 2.79 ms against 2.86 ms for cta_group::2 on the 50,000 x 658 pass
+// Experiment switches (TDNA_TC_CLUSTER / BAND / INNER / PIECE / HINTS / GRID / NOSKIP) exist only in -DTDNA_TC_EXPERIMENTS builds; the
+// product reads no environment variable on its launch path.
+static const char *exp_env(const char *name) {
+#ifdef TDNA_TC_EXPERIMENTS
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
+static bool tc_pair_mode() {  // 1 = single CTAs, 2 = pairs sharing the b-panel by multicast (default), 3 = cta_group::2 MMAs
+    const char *e = exp_env("TDNA_TC_CLUSTER");  // 2: measured 2.79 ms against 2.86 ms for cta_group::2 on the 50,000 x 658 pass
     return (e ? atoi(e) : 2) == 3;
 }
-static int tc_band() {  // row tiles per band of the bulk phase (TDNA_TC_BAND overrides, for experiments)
-    const char *e = getenv("TDNA_TC_BAND");
+static int tc_band() {  // row tiles per band of the bulk phase
+    const char *e = exp_env("TDNA_TC_BAND");
     // 64 row tiles = 8,192 rows: the band's a-panels (27 MB at 658 columns) stay in L2 while the b-panels stream past once per band;
     // measured on 50,000 x 658: band 16 2.82 ms / 2.04 GB DRAM, 32 2.76 ms, 64 2.75 ms, 128 2.75 ms
     int v = e ? atoi(e) : 64;
@@ -476,25 +508,20 @@ bool find_code(int L, int dims, tc::EncodeValues &out, uint32_t &Wout) {
         }
     return false;
 }
-// 1 = ready, -1 = this alignment / configuration is not eligible
-int ensure_tc(tdna_aln *a) {
+
+static void tc_release(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
+    for (void **p : {(void **)&a->d_tcA, (void **)&a->d_tcB, (void **)&a->d_tcfull, (void **)&a->d_tcamb, (void **)&a->d_tcpanel_amb, (void **)&a->d_tcprefix[1],
+                     (void **)&a->d_tcflag})
+        if (*p) { DFREE(*p); *p = nullptr; }
+    a->tc_state = 0;
+}
+
+// Everything about the operands that does not depend on the symbols: eligibility, the integer code, the buffers, the tile-slot prefix,
+// the tensor maps.  1 = ready to be encoded into, -1 = this alignment / configuration is not eligible.
+static int tc_prepare(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
     if ((a->kmode != KM_P_AMBIG && a->kmode != KM_K2P) || a->L >= 4096) return -1;
-    if (a->tc_state == 1 && a->tc_kmode != a->kmode) {  // the operands encode the mode's valid-symbol set: rebuild
-        DFREE(a->d_tcA);
-        DFREE(a->d_tcB);
-        if (a->d_tcfull) DFREE(a->d_tcfull);
-        a->d_tcfull = nullptr;
-        if (a->d_tcamb) DFREE(a->d_tcamb);
-        if (a->d_tcpanel_amb) DFREE(a->d_tcpanel_amb);
-        a->d_tcamb = nullptr;
-        a->d_tcpanel_amb = nullptr;
-        if (a->d_tcprefix[1]) DFREE(a->d_tcprefix[1]);
-        a->d_tcA = a->d_tcB = nullptr;
-        a->d_tcprefix[1] = nullptr;
-        a->tc_state = 0;
-    }
-    if (a->tc_state != 0) return a->tc_state;
     // K2P ignores gap sites: four symbol dimensions -- where a four-dimension code exists (W = 1024 only, i.e. L < 1024); longer K2P
     // alignments use the five-dimension code with the gap dimension left empty (25 % more K-bytes per site)
     int dims = a->kmode == KM_K2P ? 4 : 5;
@@ -502,86 +529,49 @@ int ensure_tc(tdna_aln *a) {
     uint32_t W = 0;
     if (!find_code(a->L, dims, v, W)) {
         dims = 5;
-        if (!find_code(a->L, dims, v, W)) { a->tc_state = -1; return -1; }
+        if (!find_code(a->L, dims, v, W)) return -1;
     }
     v.gap_is_symbol = a->kmode == KM_K2P ? 0 : 1;
-    int nchunks = (a->L * dims + tc::KB - 1) / tc::KB;
-    int64_t npa = round_up(a->n, tc::M), npb = round_up(a->n, tc::N);
-    if (cudaSuccess != DMALLOC(&a->d_tcA, (size_t)npa * nchunks * tc::KB) || cudaSuccess != DMALLOC(&a->d_tcB, (size_t)npb * nchunks * tc::KB)) {
+    const int nchunks = (a->L * dims + tc::KB - 1) / tc::KB;
+    const int64_t npa = round_up(a->n, tc::M), npb = round_up(a->n, tc::N);
+    const size_t npan = (size_t)(npb / tc::M);
+    bool ok = cudaSuccess == DMALLOC(&a->d_tcA, (size_t)npa * nchunks * tc::KB) && cudaSuccess == DMALLOC(&a->d_tcB, (size_t)npb * nchunks * tc::KB) &&
+              cudaSuccess == DMALLOC(&a->d_tcfull, npan) && cudaSuccess == DMALLOC(&a->d_tcamb, (size_t)a->n * 4) &&
+              cudaSuccess == DMALLOC(&a->d_tcpanel_amb, npan) && cudaSuccess == DMALLOC(&a->d_tcflag, 8);
+    // bulk phase: bands of TC_BAND row tiles; only real tiles are numbered (tdna_tc.cuh: slot_coords): a staircase over the band's
+    // first TC_BAND / 2 columns, then TC_BAND slots per column
+    const int nrt = (int)(npa / tc::M);
+    const int64_t nct = npb / tc::N;
+    const int nbands = (nrt + TC_BAND - 1) / TC_BAND;
+    std::vector<int64_t> pre(nbands + 1);
+    pre[0] = 0;
+    for (int b = 0; b < nbands; b++) {
+        int64_t tjmin = ((int64_t)b * TC_BAND >> 1);
+        int64_t cols = nct - tjmin > 0 ? nct - tjmin : 0;
+        int64_t tri = std::min<int64_t>(cols, TC_BAND >> 1);
+        pre[b + 1] = pre[b] + tri * (tri + 1) + (cols - tri) * TC_BAND;
+    }
+    ok = ok && cudaSuccess == DMALLOC(&a->d_tcprefix[1], (size_t)(nbands + 1) * 8);
+    if (ok) {
+        cudaMemsetAsync(a->d_tcfull, 0, npan, c->stream);
+        cudaMemsetAsync(a->d_tcpanel_amb, 0, npan, c->stream);
+        cudaMemsetAsync(a->d_tcflag, 0, 8, c->stream);
+        cudaMemcpyAsync(a->d_tcprefix[1], pre.data(), (size_t)(nbands + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+        ok = cudaStreamSynchronize(c->stream) == cudaSuccess;  // pre is a stack-lifetime host buffer
+    }
+    if (!ok) {
         cudaGetLastError();
-        a->tc_state = -1;
+        tc_release(a);
         return -1;
     }
-    int *d_flag = reinterpret_cast<int *>(c->d_counter);
-    cudaMemsetAsync(d_flag, 0, 8, c->stream);
-    // per 128-row panel: does any of its rows have a site that contributes nothing ('_', '?', beyond the row; '-' for K2P)?
-    size_t npan = (size_t)(npb / tc::M);
-    if (a->d_tcfull) DFREE(a->d_tcfull);
-    a->d_tcfull = nullptr;
-    if (cudaSuccess != DMALLOC(&a->d_tcfull, npan)) { cudaGetLastError(); a->tc_state = -1; return -1; }
-    cudaMemsetAsync(a->d_tcfull, 0, npan, c->stream);
-    // ambiguity letters: per-row counts and per-panel flags (d_flag[1] = any at all)
-    if (a->d_tcamb) DFREE(a->d_tcamb);
-    if (a->d_tcpanel_amb) DFREE(a->d_tcpanel_amb);
-    a->d_tcamb = nullptr;
-    a->d_tcpanel_amb = nullptr;
-    if (cudaSuccess != DMALLOC(&a->d_tcamb, (size_t)a->n * 4) || cudaSuccess != DMALLOC(&a->d_tcpanel_amb, npan)) { cudaGetLastError(); a->tc_state = -1; return -1; }
-    cudaMemsetAsync(a->d_tcpanel_amb, 0, npan, c->stream);
-    tc::amb_count_kernel<<<(unsigned)((a->n + 7) / 8), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, a->kmode == KM_K2P ? 1 : 0, a->d_tcamb,
-                                                                            a->d_tcpanel_amb, d_flag + 1);
-    c->launches++;
-    if (tc_pair_mode()) {  // cta_group::2: the b-side in 128-row panels as well (each CTA of a pair stages half of the tile's columns)
-        tc::encode_kernel<false, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcA, d_flag, a->d_tcfull);
-        tc::encode_kernel<true, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::M)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcB, d_flag, nullptr);
-        c->launches++;
-    } else {
-        tc::encode_both_kernel<<<dim3((unsigned)nchunks, (unsigned)(npb / tc::N)), 256, 0, c->stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, v, a->d_tcA,
-                                                                                                        a->d_tcB, npa / tc::M, d_flag, a->d_tcfull);
-    }
-    a->tc_pair = tc_pair_mode();
-    if (getenv("TDNA_TC_DEBUG")) fprintf(stderr, "[tc] b-side encode: %s\n", cudaGetErrorString(cudaStreamSynchronize(c->stream)));
-    tc::flip_flags_kernel<<<(unsigned)((npan + 255) / 256), 256, 0, c->stream>>>(a->d_tcfull, (int64_t)npan, (int64_t)((a->n + tc::M - 1) / tc::M));  // gappy -> full
-    c->launches += 2;
-    int flags2[2] = {0, 0};
-    cudaMemcpyAsync(flags2, d_flag, 8, cudaMemcpyDeviceToHost, c->stream);
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) flags2[0] = 1;
-    int flag = flags2[0];
-    a->tc_has_amb = flags2[1] != 0;
-    if (getenv("TDNA_TC_DEBUG")) fprintf(stderr, "[tc] flag = 0x%x\n", flag);
-    // bulk phase: bands of TC_BAND row tiles, column tile outer / row tile inner (tdna_tc.cuh: tile_coords)
-    int nrt = (int)(npa / tc::M);
-    int64_t nct = npb / tc::N;
-    int nbands = (nrt + TC_BAND - 1) / TC_BAND;
-    if (!flag) {
-        std::vector<int64_t> pre(nbands + 1);
-        pre[0] = 0;
-        for (int b = 0; b < nbands; b++) {
-            // only real tiles are numbered (tdna_tc.cuh: slot_coords): a staircase over the band's first TC_BAND / 2 columns, then
-            // TC_BAND slots per column
-            int64_t tjmin = ((int64_t)b * TC_BAND >> 1);
-            int64_t cols = nct - tjmin > 0 ? nct - tjmin : 0;
-            int64_t tri = std::min<int64_t>(cols, TC_BAND >> 1);
-            pre[b + 1] = pre[b] + tri * (tri + 1) + (cols - tri) * TC_BAND;
-        }
-        if (cudaSuccess != DMALLOC(&a->d_tcprefix[1], (size_t)(nbands + 1) * 8)) flag = 1;
-        else {
-            cudaMemcpyAsync(a->d_tcprefix[1], pre.data(), (size_t)(nbands + 1) * 8, cudaMemcpyHostToDevice, c->stream);
-            cudaStreamSynchronize(c->stream);
-            a->tcprefix_tiles[0] = nrt;
-            a->tcprefix_tiles[1] = pre[nbands];
-        }
-    }
-    if (flag) {  // a symbol outside the alphabet (the pack kernel rejects those first) or an allocation failure: the popc kernel handles it
-        DFREE(a->d_tcA);
-        DFREE(a->d_tcB);
-        a->d_tcA = a->d_tcB = nullptr;
-        a->tc_state = -1;
-        return -1;
-    }
+    a->tcprefix_tiles[0] = nrt;
+    a->tcprefix_tiles[1] = pre[nbands];
     a->tc_nchunks = nchunks;
     a->tc_W = W;
     a->tc_kmode = a->kmode;
     a->tc_dims = dims;
+    a->tc_values = v;
+    a->tc_pair = tc_pair_mode();
     {   // tensor maps for the tiled TMA loads (driver entry point through the runtime: no -lcuda)
         typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -590,8 +580,8 @@ int ensure_tc(tdna_aln *a) {
         a->tc_maps = false;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr) == cudaSuccess && fp && qr == cudaDriverEntryPointSuccess) {
             encode_fn enc = reinterpret_cast<encode_fn>(fp);
-            int inner = 256;  // uint32 elements per view row (TDNA_TC_INNER: experiments)
-            if (const char *e = getenv("TDNA_TC_INNER")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) inner = v; }
+            int inner = 256;  // uint32 elements per view row
+            if (const char *e = exp_env("TDNA_TC_INNER")) { int x = atoi(e); if (x == 32 || x == 64 || x == 128 || x == 256) inner = x; }
             a->tc_inner = inner;
             cuuint64_t rowb = (cuuint64_t)inner * 4;
             cuuint64_t dimsA[2] = {(cuuint64_t)inner, (cuuint64_t)((size_t)npa * nchunks * tc::KB / rowb)}, dimsB[2] = {(cuuint64_t)inner, (cuuint64_t)((size_t)npb * nchunks * tc::KB / rowb)};
@@ -607,6 +597,51 @@ int ensure_tc(tdna_aln *a) {
         }
         cudaGetLastError();
     }
+    return 1;
+}
+
+// Encodes the 256-row panels [panel0, panel0 + panels) on `stream` (the whole alignment, or one chunk of a chunked upload): both
+// operand images, the per-panel "full" flags, the per-row counts of ambiguity letters.  d_tcflag[0]: a symbol outside the alphabet,
+// d_tcflag[1]: some ambiguity letter.
+static void tc_encode_range(tdna_aln *a, cudaStream_t stream, int64_t panel0, int64_t panels) {
+    tdna_ctx *c = a->ctx;
+    if (panels <= 0) return;
+    const int nchunks = a->tc_nchunks, dims = a->tc_dims;
+    const int64_t npa = round_up(a->n, tc::M), npb = round_up(a->n, tc::N);
+    const int64_t row0 = panel0 * tc::N, rows = std::min<int64_t>(a->n, (panel0 + panels) * tc::N) - row0;
+    if (rows > 0)
+        tc::amb_count_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, a->kmode == KM_K2P ? 1 : 0, a->d_tcamb,
+                                                                            a->d_tcpanel_amb, a->d_tcflag + 1, row0);
+    if (a->tc_pair) {  // cta_group::2 (experiments): the b-side in 128-row panels as well; whole alignment only
+        tc::encode_kernel<false, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, a->tc_values, a->d_tcA, a->d_tcflag, a->d_tcfull);
+        tc::encode_kernel<true, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::M)), 256, 0, stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, a->tc_values, a->d_tcB, a->d_tcflag, nullptr);
+        c->launches++;
+    } else {
+        tc::encode_both_kernel<<<dim3((unsigned)nchunks, (unsigned)panels), 256, 0, stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, a->tc_values, a->d_tcA,
+                                                                                            a->d_tcB, npa / tc::M, a->d_tcflag, a->d_tcfull, panel0);
+    }
+    const int64_t k0 = 2 * panel0, k1 = std::min<int64_t>(npb / tc::M, 2 * (panel0 + panels));
+    tc::flip_flags_kernel<<<(unsigned)((k1 - k0 + 255) / 256), 256, 0, stream>>>(a->d_tcfull, k0, k1, (int64_t)((a->n + tc::M - 1) / tc::M));  // gappy -> full
+    c->launches += 3;
+}
+
+// 1 = ready, -1 = this alignment / configuration is not eligible
+int ensure_tc(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
+    if ((a->kmode != KM_P_AMBIG && a->kmode != KM_K2P) || a->L >= 4096) return -1;
+    if (a->tc_state == 1 && a->tc_kmode != a->kmode) tc_release(a);  // the operands encode the mode's valid-symbol set: rebuild
+    if (a->tc_state != 0) return a->tc_state;
+    if (tc_prepare(a) != 1) { a->tc_state = -1; return -1; }
+    tc_encode_range(a, c->stream, 0, round_up(a->n, tc::N) / tc::N);
+    int flags2[2] = {0, 0};
+    cudaMemcpyAsync(flags2, a->d_tcflag, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) flags2[0] = 1;
+    if (flags2[0]) {  // a symbol outside the alphabet (the pack kernel rejects those first) or a launch failure: the popc kernel handles it
+        tc_release(a);
+        a->tc_state = -1;
+        return -1;
+    }
+    a->tc_has_amb = flags2[1] != 0;
     a->tc_state = 1;
     return 1;
 }
@@ -714,7 +749,7 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
         p.seed_list = a->d_seedlist;
         p.seed_pairs = a->seed_pairs;
     }
-    int64_t total = p.seed_list ? 2 * (int64_t)a->seed_pairs : a->tcprefix_tiles[phase];   // slots
+    int64_t total = p.seed_list ? 2 * (int64_t)p.seed_pairs : a->tcprefix_tiles[phase];   // slots
     if (CL >= 2) total = (total + 1) / 2;         // pairs of slots
     // part k of m takes every m-th UNIT of 128 consecutive slots (64 row tiles x 2 column tiles of one band: the panels a
     // unit shares stay in this GPU's L2); units are dealt cyclically so that work AND candidates (which cluster near the
@@ -733,22 +768,22 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.L = a->L;
     p.amb = a->tc_has_amb ? a->d_tcamb : nullptr;
     p.panel_amb = a->d_tcpanel_amb;
-    if (!COUNTS_MODE && a->d_panel_range && (a->sp.want & ~(TDNA_WANT_INTRA | TDNA_WANT_INTER)) == 0 && !getenv("TDNA_TC_NOSKIP")) {
+    if (!COUNTS_MODE && a->d_panel_range && (a->sp.want & ~(TDNA_WANT_INTRA | TDNA_WANT_INTER)) == 0 && !exp_env("TDNA_TC_NOSKIP")) {
         p.class_only = ((a->sp.want & TDNA_WANT_INTRA) ? 1 : 0) | ((a->sp.want & TDNA_WANT_INTER) ? 2 : 0);
         p.panel_range = a->d_panel_range;
     }
     p.planes = a->d_planes;
     p.W32 = a->W;
     {
-        const char *e = getenv("TDNA_TC_PIECE");
+        const char *e = exp_env("TDNA_TC_PIECE");
         int v = e ? atoi(e) : (a->tc_maps ? 0 : 16384);  // default: tiled TMA when the tensor maps exist
         p.piece = (v >= 1024 && 16384 % v == 0) ? v : (a->tc_maps ? 0 : 16384);
     }
-    if (const char *e = getenv("TDNA_TC_HINTS")) p.hints = atoi(e);
+    if (const char *e = exp_env("TDNA_TC_HINTS")) p.hints = atoi(e);
     p.a_rows = tc::A_STAGE / (a->tc_inner * 4);
     p.b_rows = tc::B_STAGE / (a->tc_inner * 4);
     int64_t units = CL >= 2 ? c->sm_count / 2 : c->sm_count;
-    if (const char *e = getenv("TDNA_TC_GRID")) { int v = atoi(e); if (v >= 1 && v < units) units = v; }
+    if (const char *e = exp_env("TDNA_TC_GRID")) { int v = atoi(e); if (v >= 1 && v < units) units = v; }
     int64_t grid = (p.num_tiles < units ? p.num_tiles : units) * (CL >= 2 ? 2 : 1);
     if (grid < 1) return TDNA_OK;
     cudaLaunchConfig_t cfg = {};
@@ -771,7 +806,7 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
 
 // pairs of CTAs sharing the b-panel by TMA multicast need the tensor maps; TDNA_TC_CLUSTER=1 switches them off (experiments)
 template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts) {
-    const char *e = getenv("TDNA_TC_CLUSTER");
+    const char *e = exp_env("TDNA_TC_CLUSTER");
     int cl = e ? atoi(e) : 2;
     if (a->tc_pair) cl = 3;          // the b-side operands were encoded for cta_group::2
     else if (cl == 3) cl = 2;
@@ -909,6 +944,8 @@ int32_t tdna_init(int32_t device, tdna_ctx **out) {
     CU(cudaEventCreate(&c->ev_b0));
     for (cudaEvent_t &e : c->ev_ph) CU(cudaEventCreate(&e));
     CU(cudaMallocHost(&c->h_status, 64 * sizeof(int64_t)));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : c->ev_copy) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     unsigned long long keep = ~0ull;
@@ -928,6 +965,8 @@ int32_t tdna_shutdown(tdna_ctx *c) {
     if (c->comm.comm && c->comm.api) c->comm.api->CommDestroy(c->comm.comm);
     c->comm.comm = nullptr;
     if (c->h_status) cudaFreeHost(c->h_status);
+    for (cudaEvent_t e : c->ev_copy) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (cudaEvent_t e : {c->ev_k0, c->ev_k1, c->ev_s1, c->ev_b0})
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_ph)
@@ -1043,12 +1082,96 @@ int32_t tdna_cancel(tdna_ctx *c) {
     return TDNA_OK;
 }
 
-int32_t tdna_alignment_create(tdna_ctx *c, const uint8_t *symbols, int64_t n, int32_t L, int64_t row_stride, const int32_t *lengths,
-                              tdna_aln **out) {
+// Device buffers of a new alignment, the symbols, the bit-planes of the default configuration.  Any failure leaves `a` to the
+// caller, who destroys it (nothing leaks: destroy frees whatever was allocated so far).
+//  - several GPUs, host symbols (the same list on every rank -- one JVM: the same array): each rank uploads 1/G of the rows over
+//    its own PCIe link and the slices are all-gathered over NVLink, instead of G full uploads through the host at once;
+//  - one GPU, host symbols, 8,192+ rows: the upload runs in row chunks on a copy stream while the context's stream packs each
+//    chunk that has arrived into bit-planes AND encodes count kernel (b)'s operand panels for the default configuration (the GPU
+//    would idle through the PCIe time otherwise): both are ready when the last chunk lands.
+static int aln_build(tdna_ctx *c, tdna_aln *a, const uint8_t *symbols, const int32_t *lengths) {
+    const int64_t n = a->n, row_stride = a->sym_stride;
+    const int32_t L = a->L;
+    const size_t sym_bytes = (size_t)(n - 1) * row_stride + L;
+    const int G = c->comm.active() ? c->comm.nranks : 1;
+    const bool host_sym = !is_device_ptr(symbols);
+    const bool chunked = G == 1 && host_sym && n >= 8192;
+    if (G > 1 && n >= 1024 * (int64_t)G && host_sym) {
+        const NcclApi *nc = c->comm.api;
+        const int64_t rs = (n + G - 1) / G;
+        const size_t slice = (size_t)rs * row_stride;
+        CU(DMALLOC(&a->d_sym, slice * G));
+        const int64_t r0 = std::min<int64_t>(n, (int64_t)c->comm.rank * rs);
+        const size_t off = (size_t)r0 * row_stride;
+        const size_t mine = off < sym_bytes ? std::min(slice, sym_bytes - off) : 0;
+        if (mine) CU(cudaMemcpyAsync(a->d_sym + off, symbols + off, mine, cudaMemcpyHostToDevice, c->stream));
+        ncclResult_t r = nc->AllGather(a->d_sym + (size_t)c->comm.rank * slice, a->d_sym, slice, ncclInt8, c->comm.comm, c->stream);
+        if (r != ncclSuccess) return fail(TDNA_E_CUDA, std::string("ncclAllGather: ") + nc->GetErrorString(r));
+    } else {
+        CU(DMALLOC(&a->d_sym, sym_bytes));
+        if (!chunked) CU(cudaMemcpyAsync(a->d_sym, symbols, sym_bytes, cudaMemcpyDefault, c->stream));
+    }
+    CU(DMALLOC(&a->d_len, (size_t)n * 4));
+    if (lengths) CU(cudaMemcpyAsync(a->d_len, lengths, (size_t)n * 4, cudaMemcpyDefault, c->stream));
+    else {
+        fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a->d_len, n, L);
+        c->launches++;
+    }
+    if (!chunked) {
+        CU(cudaStreamSynchronize(c->stream));  // the caller's buffers have been read
+        return pack(a);
+    }
+    PlaneBits pb;
+    TRY(pack_prepare(a, &pb));
+    const bool tc_ok = c->opt_count_kernel != TDNA_KERNEL_POPC && tc_prepare(a) == 1;  // (synchronises the stream: buffers exist, lengths are in)
+    if (!tc_ok) CU(cudaStreamSynchronize(c->stream));
+    int *d_err = reinterpret_cast<int *>(c->d_counter);
+    CU(cudaMemsetAsync(d_err, 0, 8, c->stream));
+    const int C = 8;
+    const int64_t R = round_up((n + C - 1) / C, tc::N);
+    const int64_t panels_all = round_up(n, tc::N) / tc::N;
+    cudaError_t e = cudaSuccess;
+    for (int ch = 0; ch < C && e == cudaSuccess; ch++) {
+        const int64_t r0 = ch * R, r1 = std::min<int64_t>(n, r0 + R);
+        if (r0 >= n) break;
+        const size_t off = (size_t)r0 * row_stride;
+        const size_t bytes = r1 == n ? (size_t)(r1 - r0 - 1) * row_stride + L : (size_t)(r1 - r0) * row_stride;
+        e = cudaMemcpyAsync(a->d_sym + off, symbols + off, bytes, cudaMemcpyHostToDevice, c->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev_copy[ch], c->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->ev_copy[ch], 0);
+        if (e != cudaSuccess) break;
+        const int64_t prows = std::min<int64_t>(a->npad, r0 + R) - r0;  // whole 64-row panels (the last chunk runs to npad)
+        const int64_t total = prows * a->W;
+        pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(a->d_sym, a->d_len, n, r0, prows, row_stride, a->W, a->P, L, pb, a->d_planes, d_err);
+        c->launches++;
+        if (tc_ok) tc_encode_range(a, c->stream, r0 / tc::N, std::min<int64_t>(panels_all, (r0 + R) / tc::N) - r0 / tc::N);
+    }
+    int flags[4] = {0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(flags, d_err, 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && tc_ok) e = cudaMemcpyAsync(flags + 2, a->d_tcflag, 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e2 = cudaStreamSynchronize(c->copy_stream);  // whatever happened: no copy outlives the call
+    cudaError_t e3 = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : e3;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(TDNA_E_CUDA, cudaGetErrorString(e));
+    if (flags[0] || flags[2]) return fail(TDNA_E_SYMBOL, "a symbol outside the normalised alphabet ACGT RYKMSWBDHVN - _ ?");
+    a->packed = true;
+    if (tc_ok) {
+        a->tc_has_amb = flags[3] != 0;
+        a->tc_state = 1;
+    }
+    return TDNA_OK;
+}
+
+static int aln_new(tdna_ctx *c, const uint8_t *symbols, int64_t n, int32_t L, int64_t row_stride, const int32_t *lengths, tdna_aln **out) {
     if (!c || !symbols || !out) return fail(TDNA_E_ARG, "null argument");
     if (n < 1 || n > 0x7fffffff) return fail(TDNA_E_ARG, "n out of range");
     if (L < 1 || L > 65535) return fail(TDNA_E_ARG, "L must be in [1, 65535] (two 16-bit counts share an accumulator)");
     if (row_stride < L) return fail(TDNA_E_ARG, "row_stride < L");
+    if (lengths && !is_device_ptr(lengths)) {  // the header promises lengths[i] <= L; hold the caller to it where the host can see them
+        for (int64_t i = 0; i < n; i++)
+            if (lengths[i] < 0 || lengths[i] > L) return fail(TDNA_E_ARG, "lengths[i] must be in [0, L]");
+    }
     CU(cudaSetDevice(c->device));
     tdna_aln *a = new tdna_aln();
     a->ctx = c;
@@ -1060,40 +1183,42 @@ int32_t tdna_alignment_create(tdna_ctx *c, const uint8_t *symbols, int64_t n, in
     a->ld = round_up(n, 16);
     a->row_begin = 0;
     a->row_end = n;
-    size_t sym_bytes = (size_t)(n - 1) * row_stride + L;
-    const int G = c->comm.active() ? c->comm.nranks : 1;
-    if (G > 1 && n >= 1024 * (int64_t)G && !is_device_ptr(symbols)) {
-        // several GPUs, host symbols (the same list on every rank -- one JVM: the same array): each rank uploads 1/G of the rows over
-        // its own PCIe link and the slices are all-gathered over NVLink, instead of G full uploads through the host at once
-        const NcclApi *nc = c->comm.api;
-        const int64_t rs = (n + G - 1) / G;
-        const size_t slice = (size_t)rs * row_stride;
-        CU(DMALLOC(&a->d_sym, slice * G));
-        const int64_t r0 = std::min<int64_t>(n, (int64_t)c->comm.rank * rs);
-        const size_t off = (size_t)r0 * row_stride;
-        const size_t mine = off < sym_bytes ? std::min(slice, sym_bytes - off) : 0;
-        if (mine) CU(cudaMemcpyAsync(a->d_sym + off, symbols + off, mine, cudaMemcpyHostToDevice, c->stream));
-        ncclResult_t r = nc->AllGather(a->d_sym + (size_t)c->comm.rank * slice, a->d_sym, slice, ncclInt8, c->comm.comm, c->stream);
-        if (r != ncclSuccess) { tdna_alignment_destroy(a); return fail(TDNA_E_CUDA, std::string("ncclAllGather: ") + nc->GetErrorString(r)); }
-    } else {
-        CU(DMALLOC(&a->d_sym, sym_bytes));
-        CU(cudaMemcpyAsync(a->d_sym, symbols, sym_bytes, cudaMemcpyDefault, c->stream));
-    }
-    CU(DMALLOC(&a->d_len, (size_t)n * 4));
-    if (lengths) {
-        CU(cudaMemcpyAsync(a->d_len, lengths, (size_t)n * 4, cudaMemcpyDefault, c->stream));
-    } else {
-        std::vector<int32_t> l((size_t)n, L);
-        CU(cudaMemcpyAsync(a->d_len, l.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-    }
-    CU(cudaStreamSynchronize(c->stream));
-    int rc = pack(a);
+    int rc = aln_build(c, a, symbols, lengths);
     if (rc != TDNA_OK) {
+        std::string keep = g_err;
         tdna_alignment_destroy(a);
+        g_err = keep;
         return rc;
     }
     *out = a;
+    return TDNA_OK;
+}
+
+int32_t tdna_alignment_create(tdna_ctx *c, const uint8_t *symbols, int64_t n, int32_t L, int64_t row_stride, const int32_t *lengths,
+                              tdna_aln **out) {
+    return aln_new(c, symbols, n, L, row_stride, lengths, out);
+}
+
+// Create + labels + configuration + analysis in ONE call from host buffers: one downcall for a host that has just loaded or edited
+// its list (the upload itself is chunked and overlapped with packing / operand encoding inside tdna_alignment_create's path).
+int32_t tdna_analyze_host(tdna_ctx *c, const tdna_host_list *in, tdna_analysis *io, tdna_aln **aln_out) {
+    if (!c || !in || !io) return fail(TDNA_E_ARG, "null argument");
+    if (aln_out) *aln_out = nullptr;
+    if (in->mode < 0 || in->mode > 2) return fail(TDNA_E_ARG, "mode must be 0, 1 or 2");
+    const bool labels = in->species_id && in->genus_id && in->epithet_rank && in->fullname_rank;
+    tdna_aln *a = nullptr;
+    TRY(aln_new(c, in->symbols, in->n, in->L, in->row_stride, in->lengths, &a));
+    int rc = TDNA_OK;
+    if (labels) rc = tdna_alignment_set_labels(a, in->species_id, in->genus_id, in->epithet_rank, in->fullname_rank);
+    if (rc == TDNA_OK) rc = tdna_set_config(a, in->mode, in->min_overlap, in->ambiguous_allowed);
+    if (rc == TDNA_OK) rc = tdna_analyze(a, io);
+    if (rc != TDNA_OK || !aln_out) {
+        std::string keep = g_err;
+        tdna_alignment_destroy(a);
+        g_err = keep;
+        return rc;
+    }
+    *aln_out = a;
     return TDNA_OK;
 }
 
@@ -1103,7 +1228,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     cudaSetDevice(c->device);
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
-                    a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
+                    a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcflag, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_seedlist, a->d_cursor, a->d_lj, a->d_ld,
                     a->x_send, a->x_recv, a->x_state};
     for (void *p : ptrs)
@@ -1144,9 +1269,13 @@ int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const 
     CU(cudaGetLastError());
     CU(DFREE(d_keys));
     CU(DFREE(d_cnts));
-    a->h_species.resize((size_t)a->n);
-    CU(cudaMemcpyAsync(a->h_species.data(), a->d_species, bytes, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));  // the caller's label arrays may be pageable: do not return before the copies have read them
+    // host copy of the species ids (seed list of count kernel (b)): straight from the caller's array when that is host memory
+    if (!is_device_ptr(species_id)) a->h_species.assign(species_id, species_id + a->n);
+    else {
+        a->h_species.resize((size_t)a->n);
+        CU(cudaMemcpyAsync(a->h_species.data(), a->d_species, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));  // do not return before the copies have read the caller's arrays
     a->has_labels = true;
     a->seedlist_valid = false;
     return TDNA_OK;
@@ -1314,7 +1443,7 @@ int32_t tdna_query_distances(tdna_aln *a, const uint8_t *symbols, int32_t len, d
         default: pb = plane_bits<KM_TRANS>(); break;
     }
     const int64_t total = (int64_t)PR * a->W;
-    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(q_sym, q_len, 1, PR, (int64_t)sym_bytes, a->W, a->P, pb, q_planes, d_err);
+    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(q_sym, q_len, 1, 0, PR, (int64_t)sym_bytes, a->W, a->P, a->L, pb, q_planes, d_err);
     const unsigned grid = (unsigned)((a->n + 255) / 256);
     switch (a->kmode) {
         case KM_P_AMBIG: query_from_planes_kernel<KM_P_AMBIG><<<grid, 256, 0, c->stream>>>(q_planes, a->d_planes, a->W, a->n, a->min_overlap, dd, ds, dc); break;
@@ -1540,6 +1669,7 @@ static int stream_part(tdna_aln *a, int part, int nparts, long long *ncand_out) 
     TRY(stream_seed(a, part, nparts));
     return stream_bulk(a, part, nparts, ncand_out);
 }
+
 
 // CSR row pointers d_ptr[0..n] from the per-row record counts: three launches (tdna_kernels.cuh: scan_*_kernel)
 static int row_pointers(tdna_aln *a, const int *cnt) {

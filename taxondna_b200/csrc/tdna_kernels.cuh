@@ -17,16 +17,18 @@ struct PlaneBits {
 };
 __constant__ uint16_t c_symlut[256];  // symbol -> SymBit set; 0x8000 = not in the alphabet
 
+// rows [row0, row0 + rows) (a multiple of the 64-row panel; rows past n are written as empty): the whole alignment, or one chunk of
+// a pipelined upload.  L clamps the row lengths: sites past the alignment's width do not exist.
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len,
-                                                   int64_t n, int64_t npad, int64_t sym_stride, int W, int P, PlaneBits bits,
+                                                   int64_t n, int64_t row0, int64_t rows, int64_t sym_stride, int W, int P, int L, PlaneBits bits,
                                                    uint32_t *__restrict__ planes, int *__restrict__ err) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= npad * W) return;
-    int64_t row = idx % npad;
-    int k = (int)(idx / npad);
+    if (idx >= rows * W) return;
+    int64_t row = row0 + idx % rows;
+    int k = (int)(idx / rows);
     uint32_t w[6] = {0, 0, 0, 0, 0, 0};
     if (row < n) {
-        int l = len[row];
+        int l = min(len[row], L);
         const uint8_t *src = sym + row * sym_stride + 32 * k;  // rows keep the caller's stride: no alignment assumed
         bool bad = false;
 #pragma unroll
@@ -40,6 +42,11 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ s
         if (bad) atomicOr(err, 1);
     }
     for (int p = 0; p < P; p++) planes[plane_index(row, p, k, P, W)] = w[p];
+}
+
+__global__ void __launch_bounds__(256) fill_i32_kernel(int32_t *__restrict__ p, int64_t n, int32_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
 // serialises), one warp stages a row's ~27 symbols, then every thread emits 16-byte units of the b-image and of the a-images.
 __global__ void __launch_bounds__(256) encode_both_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len, int64_t n, int64_t sym_stride,
                                                           int L, int nchunks, int DIMS, EncodeValues v, uint8_t *__restrict__ outA, uint8_t *__restrict__ outB,
-                                                          int64_t a_panels, int *__restrict__ not_clean, uint8_t *__restrict__ panel_gappy) {
+                                                          int64_t a_panels, int *__restrict__ not_clean, uint8_t *__restrict__ panel_gappy, int64_t panel0) {
     __shared__ uint8_t codes[N][ENC_SITES + 1];
     __shared__ uint8_t s_code[256];  // 0..3 A C G T, 4 '-' (when it is a symbol), 5 no contribution, 0x85 outside the alphabet
     {
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) encode_both_kernel(const uint8_t *__restr
     }
     __syncthreads();
     const int c = blockIdx.x;
-    const int64_t panel = blockIdx.y;  // 256-row panel
+    const int64_t panel = panel0 + blockIdx.y;  // 256-row panel (panel0: the first panel of a chunk of a pipelined upload)
     const int s0 = (c * KB) / DIMS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     bool bad = false;
@@ -272,8 +272,8 @@ __global__ void __launch_bounds__(256) encode_both_kernel(const uint8_t *__restr
 }
 
 // panel_gappy -> panel_full; panels beyond the last row are not full (their pairs are out of range anyway)
-__global__ void __launch_bounds__(256) flip_flags_kernel(uint8_t *flags, int64_t npan, int64_t real_panels) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) flip_flags_kernel(uint8_t *flags, int64_t k0, int64_t npan, int64_t real_panels) {
+    int64_t k = k0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < npan) flags[k] = (k < real_panels && flags[k] == 0) ? 1 : 0;
 }
 
@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(256) flip_flags_kernel(uint8_t *flags, int64_t
 // (K2P: only R and Y are inside the model, Sequence.java:1498-1557, but every letter counts towards the K2P-mode shared length
 // that the minOverlap gate tests, :1446-1471 -- one count bounds both.)
 __global__ void __launch_bounds__(256) amb_count_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len, int64_t n, int64_t sym_stride,
-                                                        int L, int k2p, int32_t *__restrict__ amb, uint8_t *__restrict__ panel_amb, int *__restrict__ any) {
-    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+                                                        int L, int k2p, int32_t *__restrict__ amb, uint8_t *__restrict__ panel_amb, int *__restrict__ any, int64_t row0) {
+    const int64_t row = row0 + (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n) return;
     const int lane = threadIdx.x & 31, row_len = min(len[row], L);
     int cnt = 0;
