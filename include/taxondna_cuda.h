@@ -278,7 +278,17 @@ int32_t tdna_best_match_merge_routed(tdna_aln *aln, int32_t part, int32_t nparts
 enum { TDNA_WANT_BEST_MATCH = 1, /* tdna_row_result per row (as tdna_best_match) */
        TDNA_WANT_INTRA = 2,      /* PairwiseDistribution PD_INTRA distances (as tdna_class_distances) */
        TDNA_WANT_INTER = 4,      /* PairwiseDistribution PD_INTER distances */
-       TDNA_WANT_EDGES = 8       /* pairs with 0 <= d <= edge_threshold (as tdna_edges_below) */ };
+       TDNA_WANT_EDGES = 8,      /* pairs with 0 <= d <= edge_threshold (as tdna_edges_below) */
+       TDNA_WANT_HIST_INTRA = 16,/* PD_INTRA as a histogram over the distinct distances (as tdna_class_histogram); excludes TDNA_WANT_INTRA */
+       TDNA_WANT_HIST_INTER = 32 /* PD_INTER as a histogram; excludes TDNA_WANT_INTER */ };
+/* One distinct distance of a class and how many times PairwiseDistribution pushes it (PairwiseDistribution.java:77-103, 161-203;
+ * -1 is dropped, NaN is one entry).  The host layer sorts the entries by (float)d and reads counts, ranges and the threshold
+ * percentile (PairwiseSummary.java:376-418) off the cumulative counts -- the list the reference sorts (4 B per pair: 2 GB for the
+ * congeneric class of 10^6 barcodes) never exists. */
+typedef struct {
+    double d;
+    int64_t count;
+} tdna_hist_entry;
 typedef struct {
     int32_t want;            /* in: TDNA_WANT_* bits */
     int32_t reserved;
@@ -294,6 +304,11 @@ typedef struct {
     int64_t n_intra, n_inter, n_edges; /* out: totals (may exceed the capacities: only the first cap are stored) */
     int64_t n_intra_local, n_inter_local, n_edges_local; /* out: entries THIS rank produced (== the totals on one GPU); with a
                                                             communicator the lists hold this rank's share and the host concatenates */
+    tdna_hist_entry *hist_intra, *hist_inter; /* in: capacity hist_*_cap entries (host or device), unsorted; NULL = count only */
+    int64_t hist_intra_cap, hist_inter_cap;
+    int64_t n_hist_intra, n_hist_inter;       /* out: distinct distances (may exceed the capacity: call again); with a communicator the
+                                                 histograms are COMPLETE on every rank (merged over NVLink) */
+    int64_t hist_intra_pushes, hist_inter_pushes; /* out: sum of the counts = PairwiseDistribution.countValidComparisons() */
 } tdna_analysis;
 int32_t tdna_analyze(tdna_aln *aln, tdna_analysis *io);
 
@@ -319,6 +334,8 @@ int32_t tdna_analyze_host(tdna_ctx *ctx, const tdna_host_list *in, tdna_analysis
 enum { TDNA_OPT_BEST_MATCH_PATH = 1, /* TDNA_PATH_*: how tdna_best_match computes a whole-range request */
        TDNA_OPT_TILE_COLUMNS = 2,    /* 0 = automatic, 64 or 128: column width of a popc count tile */
        TDNA_OPT_COUNT_KERNEL = 3,    /* TDNA_KERNEL_*: which count kernel the streaming pass uses */
+       TDNA_OPT_HIST_SLOTS = 5,      /* first size of a class histogram's table for alignments created from now on (a power of two,
+                                        default 2^18; a pass that fills a table repeats with four times the slots) */
        TDNA_OPT_MULTI = 4            /* 1 (default): whole-range calls are shared by the communicator's ranks; 0: this GPU alone;
                                         2: the collective path even when the communicator has ONE rank (tests on a one-GPU box) */ };
 enum { TDNA_KERNEL_AUTO = 0,   /* the faster eligible one (A/B on ncu evidence) */
@@ -339,6 +356,10 @@ int32_t tdna_set_option(tdna_ctx *ctx, int32_t key, int64_t value);
  *   INTER: same genus id, different epithet, once per pair (:191-198)
  * Two-call protocol: with out == NULL only *n_out is written (the count).  */
 int32_t tdna_class_distances(tdna_aln *aln, int32_t klass, float *out, int64_t cap, int64_t *n_out);
+
+/* The same class as a histogram (SURVEY.md 8b tdna_class_histogram): *n_out distinct distances, the first cap of them in out (host or
+ * device, unsorted), *pushes = the number of distances the reference's list would hold.  O(distinct) memory on device and host. */
+int32_t tdna_class_histogram(tdna_aln *aln, int32_t klass, tdna_hist_entry *out, int64_t cap, int64_t *n_out, int64_t *pushes);
 
 /* ---- Cluster ---------------------------------------------------------------------------- */
 /* All unordered pairs i<j with 0 <= d <= t (Cluster.java:797-804), unsorted.  Two-call protocol

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("TDNA_LIB") or os.path.join(_HERE, "libtaxondna_cuda.s
 PDM_UNCORRECTED, PDM_K2P, PDM_TRANS_ONLY = 0, 1, 2
 PD_INTRA, PD_INTER = 0, 1
 ROW_SELF_VALID, ROW_NONFINITE = 1, 2
-OPT_BEST_MATCH_PATH, OPT_TILE_COLUMNS, OPT_COUNT_KERNEL, OPT_MULTI = 1, 2, 3, 4
+OPT_BEST_MATCH_PATH, OPT_TILE_COLUMNS, OPT_COUNT_KERNEL, OPT_MULTI, OPT_HIST_SLOTS = 1, 2, 3, 4, 5
 COMM_ID_BYTES = 128
 KERNEL_AUTO, KERNEL_POPC, KERNEL_TENSOR = 0, 1, 2
 PATH_AUTO, PATH_DENSE, PATH_STREAM = 0, 1, 2
@@ -28,7 +28,8 @@ class Counts(ctypes.Structure):
     _fields_ = [("shared", ctypes.c_int32), ("c1", ctypes.c_int32), ("c2", ctypes.c_int32), ("c3", ctypes.c_int32)]
 
 
-WANT_BEST_MATCH, WANT_INTRA, WANT_INTER, WANT_EDGES = 1, 2, 4, 8
+WANT_BEST_MATCH, WANT_INTRA, WANT_INTER, WANT_EDGES, WANT_HIST_INTRA, WANT_HIST_INTER = 1, 2, 4, 8, 16, 32
+HIST_ENTRY_DTYPE = np.dtype([("d", "<f8"), ("count", "<i8")])
 
 
 class Analysis(ctypes.Structure):
@@ -38,7 +39,9 @@ class Analysis(ctypes.Structure):
                 ("edge_threshold", ctypes.c_double), ("edge_i", ctypes.c_void_p), ("edge_j", ctypes.c_void_p),
                 ("edge_d", ctypes.c_void_p), ("edge_cap", ctypes.c_int64),
                 ("n_intra", ctypes.c_int64), ("n_inter", ctypes.c_int64), ("n_edges", ctypes.c_int64),
-                ("n_intra_local", ctypes.c_int64), ("n_inter_local", ctypes.c_int64), ("n_edges_local", ctypes.c_int64)]
+                ("n_intra_local", ctypes.c_int64), ("n_inter_local", ctypes.c_int64), ("n_edges_local", ctypes.c_int64),
+                ("hist_intra", ctypes.c_void_p), ("hist_inter", ctypes.c_void_p), ("hist_intra_cap", ctypes.c_int64), ("hist_inter_cap", ctypes.c_int64),
+                ("n_hist_intra", ctypes.c_int64), ("n_hist_inter", ctypes.c_int64), ("hist_intra_pushes", ctypes.c_int64), ("hist_inter_pushes", ctypes.c_int64)]
 
 
 class HostList(ctypes.Structure):
@@ -77,7 +80,7 @@ EXPORTS = [
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
     "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_rows_per_part", "tdna_tensor_code", "tdna_consensus", "tdna_fasta_parse", "tdna_fasta_destroy", "tdna_fasta_count", "tdna_fasta_width", "tdna_fasta_records", "tdna_fasta_symbols", "tdna_alignment_create_from_fasta", "tdna_best_match_part_routed", "tdna_best_match_merge_routed", "tdna_set_option", "tdna_last_tile_pass_ms",
-    "tdna_tensor_dims", "tdna_multi_phase_ms", "tdna_analyze_host", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
+    "tdna_tensor_dims", "tdna_multi_phase_ms", "tdna_analyze_host", "tdna_class_histogram", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -158,6 +161,7 @@ def load():
     L.tdna_best_match_compute.argtypes = [vp, ctypes.POINTER(vp)]
     L.tdna_class_distances.argtypes = [vp, i32, vp, i64, ctypes.POINTER(i64)]
     L.tdna_edges_below.argtypes = [vp, dbl, vp, vp, vp, i64, ctypes.POINTER(i64)]
+    L.tdna_class_histogram.argtypes = [vp, i32, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.tdna_valid_conspecifics.argtypes = [vp, vp]
     L.tdna_set_progress.argtypes = [vp, PROGRESS_FN, vp]
     L.tdna_cancel.argtypes = [vp]
@@ -507,6 +511,19 @@ class Alignment:
         check(self.L.tdna_class_distances(self.h, klass, out.ctypes.data, n.value, ctypes.byref(m)))
         assert m.value == n.value
         return out[: n.value]
+
+    def class_histogram(self, klass):
+        """(entries sorted by d, pushes): the distinct distances of a PairwiseDistribution class with their counts (tdna_class_histogram)."""
+        n, pushes = ctypes.c_int64(), ctypes.c_int64()
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, dtype=HIST_ENTRY_DTYPE)
+            check(self.L.tdna_class_histogram(self.h, klass, out.ctypes.data, cap, ctypes.byref(n), ctypes.byref(pushes)))
+            if n.value <= cap:
+                break
+            cap = int(n.value)
+        out = out[: n.value]
+        return out[np.argsort(out["d"], kind="stable")], pushes.value
 
     def edges_below(self, t):
         n = ctypes.c_int64()

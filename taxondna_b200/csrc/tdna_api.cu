@@ -71,6 +71,7 @@ struct tdna_ctx {
     int opt_best_match_path = TDNA_PATH_AUTO;
     int opt_tile_cn = 0;  // 0 = automatic
     int opt_count_kernel = TDNA_KERNEL_AUTO;
+    uint32_t opt_hist_slots = 1u << 18;
 };
 
 struct tdna_aln {
@@ -140,6 +141,13 @@ struct tdna_aln {
     int x_nranks = 0;
     int64_t res_rows = 0;     // records d_res holds (n, or nranks * rows_per_part once a multi-GPU pass ran)
     long long local_ncls[2] = {0, 0}, local_nedge = 0;  // this rank's share of the class distances / edges of the last pass
+    // class histograms (tdna_class_histogram): open-addressing tables keyed by the fp64 bits of the distance
+    unsigned long long *d_hkey[2] = {nullptr, nullptr}, *d_hcnt[2] = {nullptr, nullptr};
+    uint32_t hist_size = 1u << 18;   // slots per table (a power of two; grown x4 when a pass fills one)
+    uint32_t hist_alloc[2] = {0, 0};
+    unsigned long long *d_hctr = nullptr;  // [0] table-full flag (int), [1] entries, [2] pushes (compaction counters)
+    tdna_hist_entry *d_hent = nullptr;     // staging of compacted entries
+    size_t hent_cap = 0;
 };
 
 namespace {
@@ -1183,6 +1191,7 @@ static int aln_new(tdna_ctx *c, const uint8_t *symbols, int64_t n, int32_t L, in
     a->ld = round_up(n, 16);
     a->row_begin = 0;
     a->row_end = n;
+    a->hist_size = c->opt_hist_slots;
     int rc = aln_build(c, a, symbols, lengths);
     if (rc != TDNA_OK) {
         std::string keep = g_err;
@@ -1230,7 +1239,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
                     a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcflag, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_seedlist, a->d_cursor, a->d_lj, a->d_ld,
-                    a->x_send, a->x_recv, a->x_state};
+                    a->x_send, a->x_recv, a->x_state, a->d_hkey[0], a->d_hkey[1], a->d_hcnt[0], a->d_hcnt[1], a->d_hctr, a->d_hent};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
     delete a;
@@ -2094,8 +2103,103 @@ int32_t tdna_best_match_merge(tdna_aln *a, const int32_t *cand_row, const int32_
     return TDNA_OK;
 }
 
-static int class_distances_dense(tdna_aln *a, int32_t klass, float *out, int64_t cap, int64_t *n_out);
+static int class_distances_dense(tdna_aln *a, int32_t klass, float *out, int64_t cap, int64_t *n_out, bool hist = false);
 static int edges_dense(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out);
+
+// ---- class histograms ------------------------------------------------------------------------------------------------------------
+#define TDNA_E_HIST_FULL 100  // internal: a histogram table filled up -- grow it and repeat the pass
+
+static int hist_prepare(tdna_aln *a, int k) {
+    tdna_ctx *c = a->ctx;
+    if (!a->d_hctr) CU(DMALLOC(&a->d_hctr, 64));
+    if (a->hist_alloc[k] != a->hist_size) {
+        if (a->d_hkey[k]) CU(DFREE(a->d_hkey[k]));
+        if (a->d_hcnt[k]) CU(DFREE(a->d_hcnt[k]));
+        a->d_hkey[k] = a->d_hcnt[k] = nullptr;
+        a->hist_alloc[k] = 0;
+        CU(DMALLOC(&a->d_hkey[k], (size_t)a->hist_size * 8));
+        CU(DMALLOC(&a->d_hcnt[k], (size_t)a->hist_size * 8));
+        a->hist_alloc[k] = a->hist_size;
+    }
+    CU(cudaMemsetAsync(a->d_hkey[k], 0xff, (size_t)a->hist_size * 8, c->stream));
+    CU(cudaMemsetAsync(a->d_hcnt[k], 0, (size_t)a->hist_size * 8, c->stream));
+    CU(cudaMemsetAsync(a->d_hctr, 0, 64, c->stream));
+    return TDNA_OK;
+}
+
+static int hist_staging(tdna_aln *a, size_t entries) {
+    tdna_ctx *c = a->ctx;
+    if (entries <= a->hent_cap) return TDNA_OK;
+    if (a->d_hent) CU(DFREE(a->d_hent));
+    a->d_hent = nullptr;
+    a->hent_cap = 0;
+    CU(DMALLOC(&a->d_hent, entries * sizeof(tdna_hist_entry)));
+    a->hent_cap = entries;
+    return TDNA_OK;
+}
+
+// table k -> (out, cap); with a communicator the tables of all ranks are merged into this rank's first (every rank ends up with
+// the complete histogram).  TDNA_E_HIST_FULL: some table filled up (the same verdict on every rank).
+static int hist_finish(tdna_aln *a, int k, tdna_hist_entry *out, int64_t cap, int64_t *n_out, int64_t *pushes_out) {
+    tdna_ctx *c = a->ctx;
+    const bool multi = c->comm.active();
+    const unsigned grid = (unsigned)c->sm_count * 4;
+    struct { int over; int pad; unsigned long long n, pushes; } h;
+    if (multi) {
+        const NcclApi *nc = c->comm.api;
+        const int G = c->comm.nranks;
+        // this rank's entries, their number on every rank, the entries of every rank; the others' go into this rank's table
+        TRY(hist_staging(a, (size_t)a->hist_size * (size_t)(G + 1)));
+        tdna_hist_entry *mine = a->d_hent + (size_t)a->hist_size * G;
+        CU(cudaMemsetAsync(a->d_hctr + 1, 0, 16, c->stream));
+        hist_compact_kernel<<<grid, 256, 0, c->stream>>>(a->d_hkey[k], a->d_hcnt[k], a->hist_size, mine, (long long)a->hist_size, a->d_hctr + 1, a->d_hctr + 2);
+        c->launches++;
+        // the full flag and the entry count of every rank, all-gathered
+        long long *d_pairs = nullptr;
+        CU(DMALLOC(&d_pairs, (size_t)G * 16));
+        hist_meta_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<const int *>(a->d_hctr), a->d_hctr + 1, d_pairs + 2 * c->comm.rank);
+        c->launches++;
+        NC(nc->AllGather(d_pairs + 2 * c->comm.rank, d_pairs, 16, ncclInt8, c->comm.comm, c->stream));
+        std::vector<long long> meta((size_t)2 * G);
+        CU(cudaMemcpyAsync(meta.data(), d_pairs, (size_t)G * 16, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(DFREE(d_pairs));
+        long long over = 0, maxn = 0;
+        for (int g = 0; g < G; g++) { over += meta[2 * g]; maxn = std::max(maxn, meta[2 * g + 1]); }
+        if (over) return TDNA_E_HIST_FULL;
+        if (maxn > 0) {
+            NC(nc->AllGather(mine, a->d_hent, (size_t)maxn * sizeof(tdna_hist_entry), ncclInt8, c->comm.comm, c->stream));
+            for (int g = 0; g < G; g++) {
+                if (g == c->comm.rank || meta[2 * g + 1] == 0) continue;
+                hist_insert_kernel<<<grid, 256, 0, c->stream>>>(a->d_hent + (size_t)g * maxn, meta[2 * g + 1], a->d_hkey[k], a->d_hcnt[k], a->hist_size - 1,
+                                                               reinterpret_cast<int *>(a->d_hctr));
+                c->launches++;
+            }
+        }
+    }
+    tdna_hist_entry *dout = nullptr;
+    const bool direct = out && cap > 0 && is_device_ptr(out);
+    if (out && cap > 0) {
+        if (direct) dout = out;
+        else { TRY(hist_staging(a, (size_t)std::min<int64_t>(cap, a->hist_size))); dout = a->d_hent; }
+    }
+    const long long dcap = out && cap > 0 ? std::min<int64_t>(cap, a->hist_size) : 0;
+    CU(cudaMemsetAsync(a->d_hctr + 1, 0, 16, c->stream));
+    hist_compact_kernel<<<grid, 256, 0, c->stream>>>(a->d_hkey[k], a->d_hcnt[k], a->hist_size, dout, dcap, a->d_hctr + 1, a->d_hctr + 2);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&h, a->d_hctr, 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (h.over) return TDNA_E_HIST_FULL;  // (single GPU; after a multi-GPU merge: the union did not fit -- the same on every rank)
+    if (dout && !direct) {
+        const long long m = std::min<long long>((long long)h.n, dcap);
+        if (m > 0) CU(cudaMemcpyAsync(out, dout, (size_t)m * sizeof(tdna_hist_entry), cudaMemcpyDefault, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    *n_out = (int64_t)h.n;
+    *pushes_out = (int64_t)h.pushes;
+    return TDNA_OK;
+}
 
 // One streaming pass for any subset of {Best Match, intra, inter, edges}.  TDNA_E_TOO_LARGE: candidate overflow.
 static int analyze_stream(tdna_aln *a, tdna_analysis *io) {
@@ -2103,7 +2207,11 @@ static int analyze_stream(tdna_aln *a, tdna_analysis *io) {
     TRY(ensure_packed(a));
     TRY(ensure_stream_state(a));
     StreamParams &sp = a->sp;
-    sp.want = io->want;
+    // histogram requests are class requests whose pushes are counted per distinct distance instead of listed
+    const bool hist[2] = {(io->want & TDNA_WANT_HIST_INTRA) != 0, (io->want & TDNA_WANT_HIST_INTER) != 0};
+    const int want = (io->want & (TDNA_WANT_BEST_MATCH | TDNA_WANT_INTRA | TDNA_WANT_INTER | TDNA_WANT_EDGES)) | (hist[0] ? TDNA_WANT_INTRA : 0) |
+                     (hist[1] ? TDNA_WANT_INTER : 0);
+    sp.want = want;
     float *dcls[2] = {nullptr, nullptr};
     float *hcls[2] = {io->intra, io->inter};
     int64_t ccap[2] = {io->intra_cap, io->inter_cap};
@@ -2118,13 +2226,15 @@ static int analyze_stream(tdna_aln *a, tdna_analysis *io) {
         if (own_edges) { if (dei) DFREE(dei); if (dej) DFREE(dej); if (ded) DFREE(ded); }
         sp.want = TDNA_WANT_BEST_MATCH;
         sp.cls[0] = sp.cls[1] = nullptr;
+        sp.hkey[0] = sp.hkey[1] = sp.hcnt[0] = sp.hcnt[1] = nullptr;
         sp.ei = sp.ej = nullptr;
         sp.ed = nullptr;
     };
+    sp.hkey[0] = sp.hkey[1] = sp.hcnt[0] = sp.hcnt[1] = nullptr;
     for (int k = 0; k < 2; k++) {
         sp.cls[k] = nullptr;
         sp.cls_cap[k] = 0;
-        if (!(io->want & (k == 0 ? TDNA_WANT_INTRA : TDNA_WANT_INTER)) || !hcls[k] || ccap[k] <= 0) continue;
+        if (hist[k] || !(io->want & (k == 0 ? TDNA_WANT_INTRA : TDNA_WANT_INTER)) || !hcls[k] || ccap[k] <= 0) continue;
         if (is_device_ptr(hcls[k])) dcls[k] = hcls[k];
         else {
             cudaError_t e = DMALLOC(&dcls[k], (size_t)ccap[k] * 4);
@@ -2158,10 +2268,28 @@ static int analyze_stream(tdna_aln *a, tdna_analysis *io) {
     }
     long long ncand = 0;
     const bool multi = c->comm.active();  // the GPUs of the communicator share the pass (every rank makes this same call)
-    if (multi) rc = multi_pass(a, (io->want & TDNA_WANT_BEST_MATCH) != 0);
-    else {
-        rc = stream_part(a, 0, 1, &ncand);
-        for (int attempt = 0; rc == TDNA_E_TOO_LARGE && attempt < 3 && grow_stream_buffers(a); attempt++) rc = stream_part(a, 0, 1, &ncand);
+    for (int hattempt = 0;; hattempt++) {
+        for (int k = 0; k < 2 && rc == TDNA_OK; k++)
+            if (hist[k]) {
+                rc = hist_prepare(a, k);
+                sp.hkey[k] = a->d_hkey[k];
+                sp.hcnt[k] = a->d_hcnt[k];
+                sp.hmask = a->hist_size - 1;
+                sp.hover = reinterpret_cast<int *>(a->d_hctr);
+            }
+        if (rc != TDNA_OK) break;
+        if (multi) rc = multi_pass(a, (want & TDNA_WANT_BEST_MATCH) != 0);
+        else {
+            rc = stream_part(a, 0, 1, &ncand);
+            for (int attempt = 0; rc == TDNA_E_TOO_LARGE && attempt < 3 && grow_stream_buffers(a); attempt++) rc = stream_part(a, 0, 1, &ncand);
+        }
+        if (rc != TDNA_OK) break;
+        if (hist[0]) rc = hist_finish(a, 0, io->hist_intra, io->hist_intra_cap, &io->n_hist_intra, &io->hist_intra_pushes);
+        if (rc == TDNA_OK && hist[1]) rc = hist_finish(a, 1, io->hist_inter, io->hist_inter_cap, &io->n_hist_inter, &io->hist_inter_pushes);
+        if (rc != TDNA_E_HIST_FULL) break;
+        if (hattempt >= 3 || a->hist_size >= (1u << 26)) { rc = fail(TDNA_E_TOO_LARGE, "a class histogram has more than 2^26 distinct distances"); break; }
+        a->hist_size *= 4;  // (every rank saw the same verdict: the tables grow alike)
+        rc = TDNA_OK;
     }
     if (rc == TDNA_OK && (io->want & TDNA_WANT_BEST_MATCH)) {
         if (!multi) {
@@ -2201,6 +2329,28 @@ static int analyze_stream(tdna_aln *a, tdna_analysis *io) {
     return rc;
 }
 
+// class histograms from the materialised matrix (the rank's own row band when a communicator shares the request)
+static int hist_dense(tdna_aln *a, tdna_analysis *io) {
+    const bool hist[2] = {(io->want & TDNA_WANT_HIST_INTRA) != 0, (io->want & TDNA_WANT_HIST_INTER) != 0};
+    if (!hist[0] && !hist[1]) return TDNA_OK;
+    int rc = TDNA_OK;
+    for (int hattempt = 0;; hattempt++) {
+        int64_t dummy = 0;
+        for (int k = 0; k < 2 && rc == TDNA_OK; k++)
+            if (hist[k]) {
+                rc = hist_prepare(a, k);
+                if (rc == TDNA_OK && a->row_end > a->row_begin) rc = class_distances_dense(a, k, nullptr, 0, &dummy, true);
+            }
+        if (rc != TDNA_OK) return rc;
+        if (hist[0]) rc = hist_finish(a, 0, io->hist_intra, io->hist_intra_cap, &io->n_hist_intra, &io->hist_intra_pushes);
+        if (rc == TDNA_OK && hist[1]) rc = hist_finish(a, 1, io->hist_inter, io->hist_inter_cap, &io->n_hist_inter, &io->hist_inter_pushes);
+        if (rc != TDNA_E_HIST_FULL) return rc;
+        if (hattempt >= 3 || a->hist_size >= (1u << 26)) return fail(TDNA_E_TOO_LARGE, "a class histogram has more than 2^26 distinct distances");
+        a->hist_size *= 4;
+        rc = TDNA_OK;
+    }
+}
+
 // several GPUs, dense fallback: Best Match rows from every rank's own band of query rows (all-gathered); class distances and
 // edges of the rank's own band with the totals all-reduced.  Every rank takes this path together (multi_pass's status is shared).
 static int analyze_dense_multi(tdna_aln *a, tdna_analysis *io) {
@@ -2223,6 +2373,7 @@ static int analyze_dense_multi(tdna_aln *a, tdna_analysis *io) {
         if (rc == TDNA_OK && (io->want & TDNA_WANT_INTER)) rc = class_distances_dense(a, TDNA_PD_INTER, io->inter, io->inter_cap, &loc[1]);
         if (rc == TDNA_OK && (io->want & TDNA_WANT_EDGES)) rc = edges_dense(a, io->edge_threshold, io->edge_i, io->edge_j, io->edge_d, io->edge_cap, &loc[2]);
     }
+    if (rc == TDNA_OK) rc = hist_dense(a, io);  // (merged over the ranks inside hist_finish)
     a->row_begin = rb; a->row_end = re; a->mat_valid = false;
     TRY(rc);
     io->n_intra_local = loc[0]; io->n_inter_local = loc[1]; io->n_edges_local = loc[2];
@@ -2251,16 +2402,20 @@ static int analyze_dense(tdna_aln *a, tdna_analysis *io) {
     if (io->want & TDNA_WANT_INTER) TRY(class_distances_dense(a, TDNA_PD_INTER, io->inter, io->inter_cap, &io->n_inter));
     if (io->want & TDNA_WANT_EDGES) TRY(edges_dense(a, io->edge_threshold, io->edge_i, io->edge_j, io->edge_d, io->edge_cap, &io->n_edges));
     io->n_intra_local = io->n_intra; io->n_inter_local = io->n_inter; io->n_edges_local = io->n_edges;
+    TRY(hist_dense(a, io));
     return TDNA_OK;
 }
 
 int32_t tdna_analyze(tdna_aln *a, tdna_analysis *io) {
     if (!a || !io) return fail(TDNA_E_ARG, "null argument");
-    if (io->want == 0 || (io->want & ~(TDNA_WANT_BEST_MATCH | TDNA_WANT_INTRA | TDNA_WANT_INTER | TDNA_WANT_EDGES)))
+    if (io->want == 0 || (io->want & ~(TDNA_WANT_BEST_MATCH | TDNA_WANT_INTRA | TDNA_WANT_INTER | TDNA_WANT_EDGES | TDNA_WANT_HIST_INTRA | TDNA_WANT_HIST_INTER)))
         return fail(TDNA_E_ARG, "bad want mask");
+    if (((io->want & TDNA_WANT_INTRA) && (io->want & TDNA_WANT_HIST_INTRA)) || ((io->want & TDNA_WANT_INTER) && (io->want & TDNA_WANT_HIST_INTER)))
+        return fail(TDNA_E_ARG, "a class is either listed or histogrammed in one pass");
+    io->n_hist_intra = io->n_hist_inter = io->hist_intra_pushes = io->hist_inter_pushes = 0;
     tdna_ctx *c = a->ctx;
     CU(cudaSetDevice(c->device));
-    if (io->want & (TDNA_WANT_BEST_MATCH | TDNA_WANT_INTRA | TDNA_WANT_INTER)) TRY(need_labels(a));
+    if (io->want & (TDNA_WANT_BEST_MATCH | TDNA_WANT_INTRA | TDNA_WANT_INTER | TDNA_WANT_HIST_INTRA | TDNA_WANT_HIST_INTER)) TRY(need_labels(a));
     bool whole = a->row_begin == 0 && a->row_end == a->n;
     if (whole && c->comm.active()) {
         // the communicator's GPUs share the request; every decision below is the same on every rank (labels are part of the contract,
@@ -2297,6 +2452,18 @@ int32_t tdna_class_distances(tdna_aln *a, int32_t klass, float *out, int64_t cap
     return TDNA_OK;
 }
 
+int32_t tdna_class_histogram(tdna_aln *a, int32_t klass, tdna_hist_entry *out, int64_t cap, int64_t *n_out, int64_t *pushes) {
+    if (!a || !n_out) return fail(TDNA_E_ARG, "null argument");
+    if (klass != TDNA_PD_INTRA && klass != TDNA_PD_INTER) return fail(TDNA_E_ARG, "bad class");
+    tdna_analysis io = {};
+    io.want = klass == TDNA_PD_INTRA ? TDNA_WANT_HIST_INTRA : TDNA_WANT_HIST_INTER;
+    if (klass == TDNA_PD_INTRA) { io.hist_intra = out; io.hist_intra_cap = cap; } else { io.hist_inter = out; io.hist_inter_cap = cap; }
+    TRY(tdna_analyze(a, &io));
+    *n_out = klass == TDNA_PD_INTRA ? io.n_hist_intra : io.n_hist_inter;
+    if (pushes) *pushes = klass == TDNA_PD_INTRA ? io.hist_intra_pushes : io.hist_inter_pushes;
+    return TDNA_OK;
+}
+
 int32_t tdna_edges_below(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out) {
     if (!a || !n_out) return fail(TDNA_E_ARG, "null argument");
     if (!a->has_labels) return edges_dense(a, t, ii, jj, d, cap, n_out);  // the streaming state needs the labels
@@ -2329,13 +2496,16 @@ int32_t tdna_best_match(tdna_aln *a, tdna_row_result *out) {
     return TDNA_OK;
 }
 
-static int class_distances_dense(tdna_aln *a, int32_t klass, float *out, int64_t cap, int64_t *n_out) {
+// hist: the pushes go into the class's histogram table (prepared by the caller) instead of a list
+static int class_distances_dense(tdna_aln *a, int32_t klass, float *out, int64_t cap, int64_t *n_out, bool hist) {
     if (!a || !n_out) return fail(TDNA_E_ARG, "null argument");
     if (klass != TDNA_PD_INTRA && klass != TDNA_PD_INTER) return fail(TDNA_E_ARG, "bad class");
     tdna_ctx *c = a->ctx;
     CU(cudaSetDevice(c->device));
     TRY(need_labels(a));
     CU(cudaMemsetAsync(c->d_counter, 0, 8, c->stream));
+    unsigned long long *hk = hist ? a->d_hkey[klass] : nullptr, *hc = hist ? a->d_hcnt[klass] : nullptr;
+    if (hist) { out = nullptr; cap = 0; }
     float *dout = nullptr;
     bool direct = false;
     if (out && cap > 0) {
@@ -2351,7 +2521,7 @@ static int class_distances_dense(tdna_aln *a, int32_t klass, float *out, int64_t
         if (gy > 65535) gy = 65535;
         dim3 grid((unsigned)(b1 - b0), gy);
         class_distances_kernel<<<grid, 256, 0, c->stream>>>(a->d_mat, a->ld, a->n, b0, b1 - b0, klass, a->d_species, a->d_genus, a->d_epi, a->d_full,
-                                                           dout, cap, c->d_counter);
+                                                           dout, cap, c->d_counter, hk, hc, a->hist_size - 1, reinterpret_cast<int *>(a->d_hctr));
         c->launches++;
         CU(cudaGetLastError());
         return TDNA_OK;
@@ -2477,6 +2647,10 @@ int32_t tdna_set_option(tdna_ctx *c, int32_t key, int64_t value) {
         case TDNA_OPT_TILE_COLUMNS:
             if (value != 0 && value != 64 && value != 128) return fail(TDNA_E_ARG, "tile columns must be 0, 64 or 128");
             c->opt_tile_cn = (int)(value / 16);
+            return TDNA_OK;
+        case TDNA_OPT_HIST_SLOTS:
+            if (value < 1024 || value > (1 << 26) || (value & (value - 1))) return fail(TDNA_E_ARG, "histogram slots: a power of two in [2^10, 2^26]");
+            c->opt_hist_slots = (uint32_t)value;
             return TDNA_OK;
         case TDNA_OPT_MULTI:
             if (value < 0 || value > 2) return fail(TDNA_E_ARG, "TDNA_OPT_MULTI is 0, 1 or 2");

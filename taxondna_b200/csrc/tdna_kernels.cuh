@@ -145,6 +145,12 @@ struct StreamParams {
     float *cls[2];               // TDNA_PD_INTRA / TDNA_PD_INTER distances as (float)d, unordered (may be null: count only)
     long long cls_cap[2];
     unsigned long long *ncls;    // [2] pushes so far
+    // histogram mode of a class (tdna_class_histogram / TDNA_WANT_HIST_*): instead of one float per push, the pushes are COUNTED per
+    // distinct fp64 distance in an open-addressing table (key = the bits of d, ~0 = empty) -- O(distinct values) memory however
+    // many pairs the class has (10^6 rows: 5 * 10^8 congeneric pairs, a few thousand distinct distances)
+    unsigned long long *hkey[2], *hcnt[2];
+    uint32_t hmask;              // table size - 1 (a power of two)
+    int *hover;                  // set when a table is full
     uint32_t edge_tfix;          // 16.16 fixed point of the edge threshold, rounded up
     double edge_t;
     int32_t *ei, *ej;            // edge records (may be null: count only)
@@ -385,6 +391,33 @@ template <int KM> __device__ __forceinline__ void stream_emit_converged(bool act
     }
 }
 
+#define TDNA_HIST_EMPTY 0xffffffffffffffffull
+__device__ __forceinline__ void hist_add(unsigned long long *keys, unsigned long long *cnts, uint32_t mask, int *over, double d, int times) {
+    unsigned long long key = (unsigned long long)__double_as_longlong(d);
+    if (d != d) key = 0x7ff8000000000000ull;  // one NaN
+    uint32_t h = (uint32_t)(key >> 32) * 0x9e3779b1u ^ (uint32_t)key * 0x85ebca6bu;
+    h ^= h >> 15;
+    for (uint32_t probe = 0; probe <= mask; probe++) {
+        const uint32_t slot = (h + probe) & mask;
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(keys + slot);  // the common case: the value is there already
+        if (cur == TDNA_HIST_EMPTY) cur = atomicCAS(keys + slot, TDNA_HIST_EMPTY, key);
+        if (cur == TDNA_HIST_EMPTY || cur == key) {
+            atomicAdd(cnts + slot, (unsigned long long)times);  // no return value: a reduction at the L2
+            return;
+        }
+    }
+    *over = 1;
+}
+// the pushes of one class pair: into the class's histogram when it has one, else into its list
+__device__ __forceinline__ void class_push(const StreamParams &sp, int k, double d, int times) {
+    if (sp.hkey[k]) { hist_add(sp.hkey[k], sp.hcnt[k], sp.hmask, sp.hover, d, times); return; }
+    const float f = (float)d;
+    for (int t = 0; t < times; t++) {
+        const unsigned long long pos = atomicAdd(sp.ncls + k, 1ull);
+        if (sp.cls[k] && (long long)pos < sp.cls_cap[k]) sp.cls[k][pos] = f;
+    }
+}
+
 // PairwiseDistribution classes of one valid pair i < j (PairwiseDistribution.java:161-203): pushes (float)d
 template <int KM> __device__ __noinline__ void class_emit(int i, int j, uint32_t a0, uint32_t a1, int min_overlap) {
     const StreamParams &sp = c_sp;
@@ -398,13 +431,10 @@ template <int KM> __device__ __noinline__ void class_emit(int i, int j, uint32_t
     }
     if (!(times[0] | times[1])) return;
     Counts cn = unpack_counts<KM>(a0, a1);
-    const float f = (float)distance_from_counts<KM>(cn, min_overlap);  // the pair is valid: never -1
+    const double d = distance_from_counts<KM>(cn, min_overlap);  // the pair is valid: never -1
 #pragma unroll
     for (int k = 0; k < 2; k++)
-        for (int t = 0; t < times[k]; t++) {
-            const unsigned long long pos = atomicAdd(sp.ncls + k, 1ull);
-            if (sp.cls[k] && (long long)pos < sp.cls_cap[k]) sp.cls[k][pos] = f;
-        }
+        if (times[k]) class_push(sp, k, d, times[k]);
 }
 
 template <int KM, int CN, bool EXTRAS>
@@ -1419,6 +1449,41 @@ __global__ void __launch_bounds__(1024) scan_small_kernel(const int *__restrict_
     for (int64_t i = b; i < e; i++) { ptr[i] = run; run += cnt[i]; }
     if (t == 1023) ptr[m] = s_part[1023];
 }
+// histogram table -> dense (d, count) entries; *n counts every non-empty slot (the caller stores the first cap)
+__global__ void __launch_bounds__(256) hist_compact_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ cnts, uint32_t size,
+                                                           tdna_hist_entry *__restrict__ out, long long cap, unsigned long long *__restrict__ n,
+                                                           unsigned long long *__restrict__ pushes) {
+    unsigned long long local = 0;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < size; s += gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[s];
+        if (k == TDNA_HIST_EMPTY) continue;
+        const unsigned long long pos = atomicAdd(n, 1ull);
+        if (out && (long long)pos < cap) { out[pos].d = __longlong_as_double((long long)k); out[pos].count = (int64_t)cnts[s]; }
+        local += cnts[s];
+    }
+    if (local) atomicAdd(pushes, local);
+}
+__global__ void hist_meta_kernel(const int *__restrict__ over, const unsigned long long *__restrict__ n, long long *__restrict__ dst) {
+    if (threadIdx.x == 0) { dst[0] = *over ? 1 : 0; dst[1] = (long long)*n; }
+}
+// entries of other ranks' histograms into this rank's table (multi-GPU merge)
+__global__ void __launch_bounds__(256) hist_insert_kernel(const tdna_hist_entry *__restrict__ in, long long m, unsigned long long *__restrict__ keys,
+                                                          unsigned long long *__restrict__ cnts, uint32_t mask, int *__restrict__ over) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += (long long)gridDim.x * blockDim.x) {
+        if (in[r].count <= 0) continue;
+        unsigned long long key = (unsigned long long)__double_as_longlong(in[r].d);
+        uint32_t h = (uint32_t)(key >> 32) * 0x9e3779b1u ^ (uint32_t)key * 0x85ebca6bu;
+        h ^= h >> 15;
+        bool done = false;
+        for (uint32_t probe = 0; probe <= mask && !done; probe++) {
+            const uint32_t slot = (h + probe) & mask;
+            unsigned long long cur = atomicCAS(keys + slot, TDNA_HIST_EMPTY, key);
+            if (cur == TDNA_HIST_EMPTY || cur == key) { atomicAdd(cnts + slot, (unsigned long long)in[r].count); done = true; }
+        }
+        if (!done) *over = 1;
+    }
+}
+
 // rows past the end of the list in the last rank's slice: zero records, so that the all-gathered buffer is deterministic
 __global__ void __launch_bounds__(256) zero_rows_kernel(tdna_row_result *__restrict__ res, int64_t q0, int64_t q1) {
     const int64_t words = (q1 - q0) * (int64_t)(sizeof(tdna_row_result) / 8);
@@ -1482,7 +1547,8 @@ __global__ void __launch_bounds__(256) class_distances_kernel(const double *__re
                                                               int64_t rows, int klass, const int32_t *__restrict__ species,
                                                               const int32_t *__restrict__ genus, const int32_t *__restrict__ epi,
                                                               const int32_t *__restrict__ full, float *__restrict__ out, int64_t cap,
-                                                              unsigned long long *__restrict__ counter) {
+                                                              unsigned long long *__restrict__ counter, unsigned long long *__restrict__ hkey,
+                                                              unsigned long long *__restrict__ hcnt, uint32_t hmask, int *__restrict__ hover) {
     const int64_t qb = blockIdx.x;  // grid.x = band rows, grid.y = column slices
     if (qb >= rows) return;
     const int64_t q = row_begin + qb;
@@ -1495,8 +1561,10 @@ __global__ void __launch_bounds__(256) class_distances_kernel(const double *__re
         else                         // _addInter (:183-203)
             in = genus[j] == gq && epi[j] != eq && eq < epi[j];
         if (!in) continue;
-        float f = (float)mat[qb * ld + j];
+        const double dv = mat[qb * ld + j];
+        float f = (float)dv;
         if (f == -1.0f) continue;  // distances_push drops -1 (:79)
+        if (hkey) { hist_add(hkey, hcnt, hmask, hover, dv, 1); continue; }
         unsigned long long pos = atomicAdd(counter, 1ull);
         if (out && (int64_t)pos < cap) out[pos] = f;
     }

@@ -868,13 +868,9 @@ __device__ __forceinline__ void class_emit_value(const StreamParams &sp, int i, 
     if (sp.want & TDNA_WANT_INTER) {
         if (sp.genus[i] == sp.genus[j] && sp.epi[i] != sp.epi[j]) times[1] = 1;
     }
-    const float f = (float)d;
 #pragma unroll
     for (int k = 0; k < 2; k++)
-        for (int t = 0; t < times[k]; t++) {
-            const unsigned long long pos = atomicAdd(sp.ncls + k, 1ull);
-            if (sp.cls[k] && (long long)pos < sp.cls_cap[k]) sp.cls[k][pos] = f;
-        }
+        if (times[k]) class_push(sp, k, d, times[k]);
 }
 __global__ void __launch_bounds__(256) resolve_min_kernel(StreamParams sp, ResolveArgs ra) {
     if (*sp.overflow) return;  // the queue has holes when a push did not fit: the caller falls back to the dense path

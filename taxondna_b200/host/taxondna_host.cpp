@@ -349,6 +349,7 @@ void DistanceEngine::syncConfig() const {
         cfg_overlap_ = o;
         cfg_ambig_ = a;
         class_cached_ = false;
+        hist_cached_ = false;
     }
 }
 tdna_counts DistanceEngine::pair(int64_t i, int64_t j, double *d) const {
@@ -417,6 +418,30 @@ std::vector<float> DistanceEngine::classDistances(int klass) const {
         class_cached_ = true;
     }
     return class_cache_[klass == TDNA_PD_INTRA ? 0 : 1];
+}
+const std::vector<tdna_hist_entry> &DistanceEngine::classHistogram(int klass) const {
+    syncConfig();
+    if (!hist_cached_) {
+        int64_t cap = 1 << 16;
+        for (;;) {
+            tdna_analysis io = {};
+            io.want = TDNA_WANT_HIST_INTRA | TDNA_WANT_HIST_INTER;
+            hist_cache_[0].assign((size_t)cap, tdna_hist_entry{0.0, 0});
+            hist_cache_[1].assign((size_t)cap, tdna_hist_entry{0.0, 0});
+            io.hist_intra = hist_cache_[0].data();
+            io.hist_inter = hist_cache_[1].data();
+            io.hist_intra_cap = io.hist_inter_cap = cap;
+            ck(tdna_analyze(aln_, &io));
+            if (io.n_hist_intra <= cap && io.n_hist_inter <= cap) {
+                hist_cache_[0].resize((size_t)io.n_hist_intra);
+                hist_cache_[1].resize((size_t)io.n_hist_inter);
+                break;
+            }
+            cap = std::max(io.n_hist_intra, io.n_hist_inter);
+        }
+        hist_cached_ = true;
+    }
+    return hist_cache_[klass == TDNA_PD_INTRA ? 0 : 1];
 }
 std::vector<double> DistanceEngine::pairs(const std::vector<int32_t> &ii, const std::vector<int32_t> &jj) const {
     syncConfig();
@@ -901,14 +926,26 @@ PairwiseDistribution::PairwiseDistribution(const SequenceList &list, int type, D
                 last[sp[i]] = i;
             }
         }
-        d_ = list.engine().classDistances(type == PD_INTRA ? TDNA_PD_INTRA : TDNA_PD_INTER);
+        // the class as a histogram over its distinct fp64 distances (tdna_class_histogram); distances_push stores (float) d (:77-103)
+        const auto &h = list.engine().classHistogram(type == PD_INTRA ? TDNA_PD_INTRA : TDNA_PD_INTER);
+        std::vector<std::pair<float, int64_t>> e;
+        e.reserve(h.size());
+        for (const auto &x : h) e.emplace_back((float)x.d, x.count);
         // Arrays.sort(float[]): numeric order, -0.0 < 0.0, NaN last
-        std::sort(d_.begin(), d_.end(), [](float a, float b) {
+        auto less = [](float a, float b) {
             bool na = a != a, nb = b != b;
             if (na || nb) return !na && nb;
             if (a == b) return std::signbit(a) && !std::signbit(b);
             return a < b;
-        });
+        };
+        std::sort(e.begin(), e.end(), [&](const std::pair<float, int64_t> &a, const std::pair<float, int64_t> &b) { return less(a.first, b.first); });
+        for (size_t k = 0; k < e.size();) {  // several doubles round to one float: one run
+            size_t m = k;
+            int64_t cnt = 0;
+            while (m < e.size() && !less(e[k].first, e[m].first)) cnt += e[m++].second;
+            d_.push_run(e[k].first, cnt);
+            k = m;
+        }
     }
     if (delay) delay->end();
 }
@@ -1014,33 +1051,48 @@ std::vector<std::string> PairwiseDistances::getAveragedSequences() const {
     return out;
 }
 
+float FloatRuns::operator[](int64_t k) const {
+    size_t r = (size_t)(std::upper_bound(end_.begin(), end_.end(), k) - end_.begin());
+    return v_[std::min(r, v_.size() - 1)];
+}
+std::vector<float> FloatRuns::expand() const {
+    std::vector<float> out;
+    out.reserve((size_t)size());
+    for (size_t r = 0; r < v_.size(); r++) out.insert(out.end(), (size_t)run_count(r), v_[r]);
+    return out;
+}
+
 static bool pdIdentical(float x, float y) { return (y - x) < 0.0000001; }  // :393-396 (one-sided, float vs double literal)
 int PairwiseDistribution::getZero() const {
-    int c = 0;
-    for (float v : d_) {
-        if (pdIdentical(v, 0.0f)) c++; else break;
+    int64_t c = 0;
+    for (size_t r = 0; r < d_.runs(); r++) {
+        if (pdIdentical(d_.run_value(r), 0.0f)) c += d_.run_count(r); else break;
     }
-    return c;
+    return (int)c;
 }
 int PairwiseDistribution::getOne() const {
-    int c = 0;
-    for (int x = (int)d_.size() - 1; x >= 0; x--) {
-        if (pdIdentical(d_[x], 1.0f)) c++; else break;
+    int64_t c = 0;
+    for (size_t r = d_.runs(); r-- > 0;) {
+        if (pdIdentical(d_.run_value(r), 1.0f)) c += d_.run_count(r); else break;
     }
-    return c;
+    return (int)c;
 }
-std::vector<float> PairwiseDistribution::getDistancesBetween(double from, double to) const {
-    std::vector<float> v;
+// :357-373 -- one sweep over the sorted values with a flag (so NaNs at the end are taken iff the flag is still up): the same sweep
+// over the runs
+FloatRuns PairwiseDistribution::runsBetween(double from, double to) const {
+    FloatRuns v;
     bool count = false;
-    for (float x : d_) {
+    for (size_t r = 0; r < d_.runs(); r++) {
+        const float x = d_.run_value(r);
         if ((double)x >= from) count = true;
         if ((double)x > to) count = false;
-        if (count) v.push_back(x);
+        if (count) v.push_run(x, d_.run_count(r));
     }
     return v;
 }
-int PairwiseDistribution::getBetween(double from, double to) const { return (int)getDistancesBetween(from, to - 0.000001).size(); }
-int PairwiseDistribution::getBetweenIncl(float from, float to) const { return (int)getDistancesBetween((double)from, (double)to).size(); }
+std::vector<float> PairwiseDistribution::getDistancesBetween(double from, double to) const { return runsBetween(from, to).expand(); }
+int PairwiseDistribution::getBetween(double from, double to) const { return (int)runsBetween(from, to - 0.000001).size(); }
+int PairwiseDistribution::getBetweenIncl(float from, float to) const { return (int)runsBetween((double)from, (double)to).size(); }
 float PairwiseDistribution::getMaximumDistance() const { return d_.empty() ? 0.0f : d_.back(); }
 float PairwiseDistribution::getMinimumDistance() const { return d_.empty() ? 0.0f : d_.front(); }
 std::string PairwiseDistribution::getDistributionAsString(double d_from, double d_to, double d_interval, char dir) const {
@@ -1408,31 +1460,31 @@ std::string PairwiseSummary::run(DelayCallback *delay) {
                    " bp overlap will not be counted as a pairwise distance for this analysis.");
     padln(str, "\nRANGES");
     padln(str, "WARNING: These calculations are new to Species Identifier as of June 14, 2012, and have not been comprehensively tested yet. Please use with caution!\n");
-    auto trimIntra = [](const std::vector<float> &dl) {
-        float mx = dl[dl.size() - 1];
-        size_t x = 1;
-        while (x < dl.size()) {
-            float dist = dl[dl.size() - x];
-            if ((double)((float)x / dl.size()) > 0.05) break;
-            mx = dist;
-            x++;
+    // The reference walks the sorted list from one end while (float) x / size <= 0.05 (:204-216, :236-247, :388-404).  The quotient
+    // is non-decreasing in x, so the last x that passes is found by bisection and the value read off the runs: same result, O(log n).
+    auto passes = [](int64_t x, int64_t size) { return !((double)((float)x / (float)size) > 0.05); };
+    auto lastPassing = [&](int64_t lo, int64_t hi, int64_t size) {  // largest x in [lo, hi] that passes, lo - 1 if none (passes is monotone)
+        if (hi < lo || !passes(lo, size)) return lo - 1;
+        while (lo < hi) {
+            int64_t mid = lo + (hi - lo + 1) / 2;
+            if (passes(mid, size)) lo = mid; else hi = mid - 1;
         }
-        return mx;
+        return lo;
     };
-    auto trimInter = [](const std::vector<float> &dl, float start) {
-        float mn = start;
-        int x = 0;
-        for (float dist : dl) {
-            if ((double)((float)x / dl.size()) > 0.05) break;
-            mn = dist;
-            x++;
-        }
-        return mn;
+    auto trimIntra = [&](const FloatRuns &dl) {  // x = 1 .. size - 1: dist = dl[size - x]
+        const int64_t size = dl.size(), x = lastPassing(1, size - 1, size);
+        return x >= 1 ? dl[size - x] : dl[size - 1];
+    };
+    auto trimInter = [&](const FloatRuns &dl, float start) {  // x = 0 .. size - 1: dist = dl[x]
+        const int64_t size = dl.size();
+        if (size == 0) return start;
+        const int64_t x = lastPassing(0, size - 1, size);
+        return x >= 0 ? dl[x] : start;
     };
     if (intra.countValidComparisons() == 0) {
         padln(str, "There are no valid intraspecific pairwise distances (i.e. no two sequences have less than " + mo + " bp overlap).");
     } else {
-        std::vector<float> dl = intra.getDistancesBetween(0, 1);
+        FloatRuns dl = intra.runsBetween(0, 1);
         if (dl.empty()) throw NullPointerException("PairwiseSummary.java:204: no intraspecific distance in [0,1]");
         float mx = trimIntra(dl);
         padln(str, "Intraspecific pairwise distances range between " + pc(intra.getMinimumDistance(), 1) + "% and " + pc(intra.getMaximumDistance(), 1) +
@@ -1445,7 +1497,7 @@ std::string PairwiseSummary::run(DelayCallback *delay) {
     if (inter.countValidComparisons() == 0) {
         padln(str, "There are no valid interspecific pairwise distances (i.e. no two sequences have less than " + mo + " bp overlap).");
     } else {
-        std::vector<float> dl = inter.getDistancesBetween(0, 1);
+        FloatRuns dl = inter.runsBetween(0, 1);
         float mn = trimInter(dl, inter.getMinimumDistance());
         padln(str, "Interspecific, intrageneric pairwise distances range between " + pc(inter.getMinimumDistance(), 1) + "% and " + pc(inter.getMaximumDistance(), 1) +
                        "% (contains " + pc(inter.getBetweenIncl(inter.getMinimumDistance(), inter.getMaximumDistance()), inter.countValidComparisons()) +
@@ -1463,7 +1515,7 @@ std::string PairwiseSummary::run(DelayCallback *delay) {
                        "% to " + pc(intra.getMaximumDistance(), 1) + "% (total width: " + pc(intra.getMaximumDistance() - intra.getMinimumDistance(), 1) + "%)");
     } else {
         int within = intra.getBetweenIncl(min_inter, max_intra) + inter.getBetweenIncl(min_inter, max_intra);
-        std::vector<float> dl_intra = intra.getDistancesBetween(0, 1), dl_inter = inter.getDistancesBetween(0, 1);
+        FloatRuns dl_intra = intra.runsBetween(0, 1), dl_inter = inter.runsBetween(0, 1);
         if (dl_intra.empty()) {
             padln(str, "Total overlap:\t No intraspecific distances present.");
             padln(str, "Overlap with 5% error margs on both ends:\t No intraspecific distances present.");
@@ -1474,12 +1526,9 @@ std::string PairwiseSummary::run(DelayCallback *delay) {
             padln(str, "Total overlap:\t" + pc(overlap, 1) + "% (from " + pc(min_inter, 1) + "% to " + pc(max_intra, 1) + "%, covering " + pc(within, count_comparisons) +
                            "% of all intra and interspecific but intrageneric sequences)");
             min_inter = trimInter(dl_inter, min_inter);
-            size_t x = 1;
-            while (x < dl_intra.size()) {
-                float dist = dl_intra[dl_intra.size() - x];
-                if ((double)((float)x / dl_intra.size()) > 0.05) break;
-                max_intra = dist;
-                x++;
+            {   // (:388-404: the same walk as trimIntra, starting from max_intra)
+                const int64_t size = dl_intra.size(), x = lastPassing(1, size - 1, size);
+                if (x >= 1) max_intra = dl_intra[size - x];
             }
             overlap = std::fabs(max_intra - min_inter);
             within = inter.getBetweenIncl(min_inter, max_intra) + intra.getBetweenIncl(min_inter, max_intra);

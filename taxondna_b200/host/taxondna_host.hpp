@@ -172,6 +172,9 @@ class DistanceEngine {
     std::vector<double> matrix() const;  // n x n, row-major
     std::vector<tdna_row_result> bestMatch() const;
     std::vector<float> classDistances(int klass) const;
+    // the class as (distinct fp64 distance, count) entries, unsorted; both classes come from ONE pass, the second request is served
+    // from the first one's result
+    const std::vector<tdna_hist_entry> &classHistogram(int klass) const;
     std::vector<double> pairs(const std::vector<int32_t> &ii, const std::vector<int32_t> &jj) const;  // one launch for a pair list
     void edgesBelow(double t, std::vector<int32_t> &ii, std::vector<int32_t> &jj, std::vector<double> &d) const;
     std::vector<uint8_t> validConspecifics() const;
@@ -192,6 +195,8 @@ class DistanceEngine {
     int64_t class_cap_[2] = {0, 0};              // label-derived upper bounds of |PD_INTRA|, |PD_INTER|
     mutable std::vector<float> class_cache_[2];  // both classes of the current configuration (one pass serves both)
     mutable bool class_cached_ = false;
+    mutable std::vector<tdna_hist_entry> hist_cache_[2];
+    mutable bool hist_cached_ = false;
 };
 
 // Common/DNA/SortedSequenceList.java:60-162 (+ SortedSequenceComparator :197-261)
@@ -221,6 +226,32 @@ class SortedSequenceList {
 void javaSort(std::vector<int> &a, const std::function<int(int, int)> &cmp);
 
 // Common/DNA/PairwiseDistribution.java:41-402
+// A sorted multiset of floats as runs of equal values: what PairwiseDistribution's float[] holds after Arrays.sort, without the
+// array (the congeneric class of 10^6 barcodes has 5 * 10^8 distances and a few thousand distinct ones).  Built from the device's
+// class histogram (tdna_class_histogram); index k means position k of the reference's sorted array.
+class FloatRuns {
+  public:
+    FloatRuns() = default;
+    void push_run(float v, int64_t count) {  // runs must arrive in the order Arrays.sort(float[]) gives
+        if (count <= 0) return;
+        v_.push_back(v);
+        end_.push_back((end_.empty() ? 0 : end_.back()) + count);
+    }
+    int64_t size() const { return end_.empty() ? 0 : end_.back(); }
+    bool empty() const { return end_.empty(); }
+    size_t runs() const { return v_.size(); }
+    float run_value(size_t r) const { return v_[r]; }
+    int64_t run_count(size_t r) const { return end_[r] - (r ? end_[r - 1] : 0); }
+    float operator[](int64_t k) const;  // the k-th smallest
+    float front() const { return v_.front(); }
+    float back() const { return v_.back(); }
+    std::vector<float> expand() const;
+
+  private:
+    std::vector<float> v_;
+    std::vector<int64_t> end_;  // entries up to and including run r
+};
+
 class PairwiseDistribution {
   public:
     static constexpr int PD_INTRA = 0, PD_INTER = 1;
@@ -235,10 +266,12 @@ class PairwiseDistribution {
     int getBetweenIncl(float from, float to) const;
     float getMaximumDistance() const;
     float getMinimumDistance() const;
-    std::vector<float> getDistancesBetween(double from, double to) const;
+    std::vector<float> getDistancesBetween(double from, double to) const;  // the reference's Vector, expanded (small lists)
+    FloatRuns runsBetween(double from, double to) const;                   // the same selection as runs
+    const FloatRuns &runs() const { return d_; }
 
   private:
-    std::vector<float> d_;  // sorted as Arrays.sort(float[]) sorts (NaN last)
+    FloatRuns d_;  // in the order Arrays.sort(float[]) gives (NaN last)
     int count_sequences_ = 0;
 };
 
