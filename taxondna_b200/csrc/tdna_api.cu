@@ -98,7 +98,7 @@ struct tdna_aln {
     size_t scratch_cap = 0;
     // streaming Best Match (tdna_kernels.cuh "stream epilogue")
     uint8_t *d_needc = nullptr;
-    int4 *d_panel_range = nullptr;
+    int4 *d_panel_range = nullptr, *d_range_rows = nullptr, *d_range_cols = nullptr;  // per 64-row panel; per 128-row / 256-column tile panel
     StreamParams sp = {};
     bool stream_alloc = false;
     void *d_stream_u64 = nullptr;  // ncand + overflow
@@ -107,7 +107,9 @@ struct tdna_aln {
     int sprefix_cn = 0;
     long long *d_ptr = nullptr;  // CSR row pointers [n + 1]
     long long *d_scan = nullptr; // block sums of the row-pointer scan
-    std::vector<int32_t> h_species;            // host copy of the species ids (seed list of count kernel (b))
+    std::vector<int32_t> h_species, h_genus;   // host copies of the species / genus ids (seed list of count kernel (b); class reach)
+    int64_t class_reach = -1;                  // max j - i over the class pairs i < j the labels allow (-1: not computed yet)
+    int64_t tcprefix_reach = -1, tcprefix_class_tiles = 0;  // d_tcprefix[0]: the slot numbering of class-only launches, built for this reach
     int2 *d_seedlist = nullptr;
     int seed_pairs = 0;
     bool seedlist_valid = false;
@@ -240,6 +242,8 @@ int set_stream_symbol(tdna_aln *a, bool seed) {
     return TDNA_OK;
 }
 int ensure_tc(tdna_aln *a);
+static int ensure_class_reach(tdna_aln *a);
+static int ensure_class_prefix(tdna_aln *a);
 template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts);
 
 template <int KM, int CN, int EPI> int launch_kernel(tdna_ctx *c, const TileParams &p) {
@@ -455,9 +459,32 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
         if (phases & 1) CU(cudaEventRecord(c->ev_k0, c->stream));
         for (int ph = 0; ph < 2; ph++)
             if (phases & (1 << ph)) {
-                TRY(set_stream_symbol(a, ph == 0));
                 if (ph == 1) CU(cudaEventRecord(c->ev_b0, c->stream));
-                TRY(launch_tc<false>(a, ph, part, nparts, nullptr));
+                const int want = a->sp.want, row_bits = want & (TDNA_WANT_BEST_MATCH | TDNA_WANT_EDGES), class_bits = want & (TDNA_WANT_INTRA | TDNA_WANT_INTER);
+                bool split = false;
+                if (ph == 1 && row_bits && class_bits) {  // worth it when the tiles that can hold class pairs are a small part of the triangle
+                    TRY(ensure_class_reach(a));
+                    if (a->class_reach >= 0 && a->class_reach < a->n / 2) {
+                        TRY(ensure_class_prefix(a));
+                        split = a->tcprefix_class_tiles * 8 <= a->tcprefix_tiles[1];
+                    }
+                }
+                if (split) {
+                    // per-row outputs and class outputs in two launches: the rows' launch runs the whole triangle with none of the class
+                    // machinery switched on (a class request in the same launch cost every tile of 10^6 rows a third of its time), the
+                    // classes' launch visits only the near-diagonal tiles that can hold a class pair (computed twice: a few per mille)
+                    a->sp.want = row_bits;
+                    int rc = set_stream_symbol(a, false);
+                    if (rc == TDNA_OK) rc = launch_tc<false>(a, ph, part, nparts, nullptr);
+                    a->sp.want = class_bits;
+                    if (rc == TDNA_OK) rc = set_stream_symbol(a, false);
+                    if (rc == TDNA_OK) rc = launch_tc<false>(a, ph, part, nparts, nullptr);
+                    a->sp.want = want;
+                    TRY(rc);
+                } else {
+                    TRY(set_stream_symbol(a, ph == 0));
+                    TRY(launch_tc<false>(a, ph, part, nparts, nullptr));
+                }
                 if (ph == 0) CU(cudaEventRecord(c->ev_s1, c->stream));
             }
         if (phases & 2) {
@@ -654,6 +681,42 @@ int ensure_tc(tdna_aln *a) {
     return 1;
 }
 
+// How far from the diagonal a class pair can lie: for every row, the last row of its species / of its genus (one O(n) walk over the
+// labels, once per label set).  A list sorted by name keeps this at the size of its largest genus.
+static int ensure_class_reach(tdna_aln *a) {
+    if (a->class_reach >= 0 || (int64_t)a->h_species.size() != a->n || (int64_t)a->h_genus.size() != a->n) return TDNA_OK;
+    std::unordered_map<int32_t, int64_t> last_s, last_g;
+    for (int64_t i = 0; i < a->n; i++) { if (a->h_species[i] >= 0) last_s[a->h_species[i]] = i; last_g[a->h_genus[i]] = i; }
+    int64_t reach = 0;
+    for (int64_t i = 0; i < a->n; i++) {
+        if (a->h_species[i] >= 0) reach = std::max(reach, last_s[a->h_species[i]] - i);
+        reach = std::max(reach, last_g[a->h_genus[i]] - i);
+    }
+    a->class_reach = reach;
+    return TDNA_OK;
+}
+// Class pairs stay within class_reach rows of the diagonal: a class-only launch numbers only those columns of each band (the full
+// numbering made every role of every CTA walk -- and skip -- 1.5 * 10^7 slots on 10^6 rows).  d_tcprefix[0], tcprefix_class_tiles.
+static int ensure_class_prefix(tdna_aln *a) {
+    tdna_ctx *c = a->ctx;
+    if (a->tcprefix_reach == a->class_reach && a->d_tcprefix[0]) return TDNA_OK;
+    const int nrt = (int)(round_up(a->n, tc::M) / tc::M), nct = (int)(round_up(a->n, tc::N) / tc::N), nbands = (nrt + TC_BAND - 1) / TC_BAND;
+    std::vector<int64_t> pre(nbands + 1);
+    pre[0] = 0;
+    for (int b = 0; b < nbands; b++) {
+        const int64_t ti0 = (int64_t)b * TC_BAND, tjmin = ti0 >> 1;
+        const int64_t lim = std::min<int64_t>(nct, ((ti0 + TC_BAND) * tc::M - 1 + a->class_reach) / tc::N + 1);
+        const int64_t cols = std::max<int64_t>(lim - tjmin, 0), tri = std::min<int64_t>(cols, TC_BAND >> 1);
+        pre[b + 1] = pre[b] + tri * (tri + 1) + (cols - tri) * TC_BAND;
+    }
+    if (!a->d_tcprefix[0]) CU(DMALLOC(&a->d_tcprefix[0], (size_t)(nbands + 1) * 8));
+    CU(cudaMemcpyAsync(a->d_tcprefix[0], pre.data(), (size_t)(nbands + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    a->tcprefix_reach = a->class_reach;
+    a->tcprefix_class_tiles = pre[nbands];
+    return TDNA_OK;
+}
+
 // Seed pass of kernel (b): which 256-column blocks each pair of row tiles (= one 256-row block) visits.  Always its own diagonal
 // block; plus, from the labels, the block holding the nearest row of a species whose id has the parity the diagonal block lacks
 // (thresholds are max(min conspecific, min even-id species, min odd-id species): a block inside one large species would leave
@@ -757,18 +820,6 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
         p.seed_list = a->d_seedlist;
         p.seed_pairs = a->seed_pairs;
     }
-    int64_t total = p.seed_list ? 2 * (int64_t)p.seed_pairs : a->tcprefix_tiles[phase];   // slots
-    if (CL >= 2) total = (total + 1) / 2;         // pairs of slots
-    // part k of m takes every m-th UNIT of 128 consecutive slots (64 row tiles x 2 column tiles of one band: the panels a
-    // unit shares stay in this GPU's L2); units are dealt cyclically so that work AND candidates (which cluster near the
-    // diagonal) are balanced across the parts
-    p.unit = CL >= 2 ? 64 : 128;
-    if (phase == 0) p.unit = 1;  // the seed pass has a few hundred items in all: deal them one by one, or most parts get none
-    int64_t units_total = (total + p.unit - 1) / p.unit;
-    int64_t my_units = units_total > part ? (units_total - part + nparts - 1) / nparts : 0;
-    p.t_offset = part;
-    p.t_stride = nparts;
-    p.num_tiles = my_units * p.unit;  // items past the end of the list are skipped by the kernel
     p.counts = counts;
     p.extras = a->sp.want != TDNA_WANT_BEST_MATCH;
     p.k2p = a->kmode == KM_K2P ? 1 : 0;
@@ -780,6 +831,31 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
         p.class_only = ((a->sp.want & TDNA_WANT_INTRA) ? 1 : 0) | ((a->sp.want & TDNA_WANT_INTER) ? 2 : 0);
         p.panel_range = a->d_panel_range;
     }
+    p.range_rows = a->d_range_rows;
+    p.range_cols = a->d_range_cols;
+    p.class_reach = a->n;
+    if (p.extras || p.class_only) {
+        TRY(ensure_class_reach(a));
+        if (a->class_reach >= 0) p.class_reach = a->class_reach;
+    }
+    p.col_reach = -1;
+    if (phase && p.class_only && a->class_reach >= 0 && a->class_reach < a->n / 2) {
+        TRY(ensure_class_prefix(a));
+        p.col_reach = a->class_reach;
+        p.prefix = a->d_tcprefix[0];
+    }
+    int64_t total = p.seed_list ? 2 * (int64_t)p.seed_pairs : (p.col_reach >= 0 ? a->tcprefix_class_tiles : a->tcprefix_tiles[phase]);   // slots
+    if (CL >= 2) total = (total + 1) / 2;         // pairs of slots
+    // part k of m takes every m-th UNIT of 128 consecutive slots (64 row tiles x 2 column tiles of one band: the panels a
+    // unit shares stay in this GPU's L2); units are dealt cyclically so that work AND candidates (which cluster near the
+    // diagonal) are balanced across the parts
+    p.unit = CL >= 2 ? 64 : 128;
+    if (phase == 0) p.unit = 1;  // the seed pass has a few hundred items in all: deal them one by one, or most parts get none
+    int64_t units_total = (total + p.unit - 1) / p.unit;
+    int64_t my_units = units_total > part ? (units_total - part + nparts - 1) / nparts : 0;
+    p.t_offset = part;
+    p.t_stride = nparts;
+    p.num_tiles = my_units * p.unit;  // items past the end of the list are skipped by the kernel
     p.planes = a->d_planes;
     p.W32 = a->W;
     {
@@ -1237,7 +1313,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     cudaSetDevice(c->device);
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
-                    a->d_needc, a->d_panel_range, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcflag, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
+                    a->d_needc, a->d_panel_range, a->d_range_rows, a->d_range_cols, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcflag, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_seedlist, a->d_cursor, a->d_lj, a->d_ld,
                     a->x_send, a->x_recv, a->x_state, a->d_hkey[0], a->d_hkey[1], a->d_hcnt[0], a->d_hcnt[1], a->d_hctr, a->d_hent};
     for (void *p : ptrs)
@@ -1274,6 +1350,14 @@ int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const 
     species_count_kernel<<<gq, 256, 0, c->stream>>>(a->d_species, a->n, d_keys, d_cnts, hcap - 1);
     needc_kernel<<<gq, 256, 0, c->stream>>>(a->d_species, a->n, d_keys, d_cnts, hcap - 1, a->d_needc);
     panel_range_kernel<<<(unsigned)panels, 32, 0, c->stream>>>(a->d_species, a->d_genus, a->n, a->d_panel_range);
+    {   // the same per tile panel of count kernel (b)
+        const int64_t nrt = round_up(a->n, tc::M) / tc::M, nct = round_up(a->n, tc::N) / tc::N;
+        if (!a->d_range_rows) CU(DMALLOC(&a->d_range_rows, (size_t)nrt * sizeof(int4)));
+        if (!a->d_range_cols) CU(DMALLOC(&a->d_range_cols, (size_t)nct * sizeof(int4)));
+        tc::tile_range_kernel<<<(unsigned)((nrt + 255) / 256), 256, 0, c->stream>>>(a->d_panel_range, (int64_t)panels, tc::M / PR, a->d_range_rows, nrt);
+        tc::tile_range_kernel<<<(unsigned)((nct + 255) / 256), 256, 0, c->stream>>>(a->d_panel_range, (int64_t)panels, tc::N / PR, a->d_range_cols, nct);
+        c->launches += 2;
+    }
     c->launches += 3;
     CU(cudaGetLastError());
     CU(DFREE(d_keys));
@@ -1284,6 +1368,13 @@ int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const 
         a->h_species.resize((size_t)a->n);
         CU(cudaMemcpyAsync(a->h_species.data(), a->d_species, bytes, cudaMemcpyDeviceToHost, c->stream));
     }
+    if (!is_device_ptr(genus_id)) a->h_genus.assign(genus_id, genus_id + a->n);
+    else {
+        a->h_genus.resize((size_t)a->n);
+        CU(cudaMemcpyAsync(a->h_genus.data(), a->d_genus, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    a->class_reach = -1;
+    a->tcprefix_reach = -1;
     CU(cudaStreamSynchronize(c->stream));  // do not return before the copies have read the caller's arrays
     a->has_labels = true;
     a->seedlist_valid = false;

@@ -34,7 +34,9 @@ constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter
 constexpr int EPI_COLS = N / (EPI_WARPS / 4);      // columns per epilogue warp
 constexpr int THREADS = 64 + EPI_WARPS * 32;       // warp 0 producer, warp 1 MMA issuer, warps 2.. epilogue
 constexpr int MAX_DIMS = 5;                        // K-dimensions per site: 5 (p: A C G T -) or 4 (K2P: A C G T)
-constexpr size_t SMEM = (size_t)NSTAGE * STAGE + 256 /*barriers*/ + 16 * 64 * 4 /*column thresholds, per epilogue warp*/ + 1024 /*alignment*/;
+constexpr int WTAB = 64;                           // slots of an epilogue warp's private class-histogram table (tdna_kernels.cuh: shist_add)
+constexpr size_t SMEM = (size_t)NSTAGE * STAGE + 256 /*barriers*/ + 16 * 64 * 4 /*column thresholds, per epilogue warp*/ +
+                        (size_t)EPI_WARPS * WTAB * 12 /*class-histogram tables*/ + 1024 /*alignment*/;
 
 struct Params {
     const uint8_t *A;   // [a-panel][chunk][16 KB]
@@ -72,6 +74,12 @@ struct Params {
     int seed_pairs;
     int class_only;         // the pass wants class distances and nothing per row: bit 0 = intra, bit 1 = inter.  Tiles whose row and
     const int4 *panel_range;  // column panels share no species / genus id range hold no such pair and are skipped by every role
+    // (min, max) species id and (min, max) genus id per 128-row tile panel and per 256-column tile panel: two loads per tile decide
+    // whether a tile can hold a class pair (the 64-row panels' ranges cost 16 loads per thread and tile -- measurable on 10^6 rows)
+    const int4 *range_rows, *range_cols;
+    int64_t col_reach;      // >= 0: the slot numbering of this launch stops col_reach rows past each band (class-only launches)
+    int64_t class_reach;    // no class pair (i, j > i) has j - i above this (from the labels; n when unknown): tiles further from the
+                            // diagonal are ruled out by arithmetic alone, before any range is loaded
 };
 
 // Tile slot -> (row tile, column tile); false = an empty slot.  The bulk phase walks BANDS of `band` row tiles (64 by
@@ -102,7 +110,9 @@ __device__ __forceinline__ bool slot_coords(const Params &p, const int64_t *pref
     // at eight parts).  Counts are even, so the slot pairs (2u, 2u + 1) of the two-CTA clusters stay adjacent row tiles of one column.
     const int64_t r = t - prefix[lo];
     const int ti0 = lo * p.band, tjmin = ti0 >> 1;
-    const int cols = p.nct - tjmin, tri = min(cols, p.band >> 1);
+    // a class-only launch numbers, per band, only the columns a class pair can reach (col_reach rows past the band's last row)
+    const int lim = p.col_reach >= 0 ? (int)min((int64_t)p.nct, ((int64_t)(ti0 + p.band) * M - 1 + p.col_reach) / N + 1) : p.nct;
+    const int cols = max(lim - tjmin, 0), tri = min(cols, p.band >> 1);
     const int64_t T = (int64_t)tri * (tri + 1);
     if (r < T) {
         int c = (int)((sqrtf(4.0f * (float)r + 1.0f) - 1.0f) * 0.5f);
@@ -139,12 +149,12 @@ template <int CL> __device__ __forceinline__ bool my_tile(const Params &p, int64
     if constexpr (CL == 1) {
         const int64_t l = (int64_t)blockIdx.x + k * gridDim.x;
         if (!slot_coords(p, p.prefix, ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit, ti, tj)) return false;
-        return !p.class_only || may_hold_class_pairs(p, ti, tj, M);
+        return !p.class_only || ((int64_t)tj * N <= (int64_t)ti * M + (M - 1) + p.class_reach && may_hold_class_pairs(p, ti, tj, M));
     } else {
         const int64_t l = (int64_t)(blockIdx.x >> 1) + k * (gridDim.x >> 1);
         const int64_t u = ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit;
         bool ok = slot_coords(p, p.prefix, 2 * u, ti, tj);
-        if (ok && p.class_only) ok = may_hold_class_pairs(p, ti, tj, 2 * M);  // the same answer in both CTAs of the pair
+        if (ok && p.class_only) ok = (int64_t)tj * N <= (int64_t)ti * M + (2 * M - 1) + p.class_reach && may_hold_class_pairs(p, ti, tj, 2 * M);  // the same answer in both CTAs of the pair
         ti += (int)rank;
         return ok;
     }
@@ -298,6 +308,20 @@ __global__ void __launch_bounds__(256) amb_count_kernel(const uint8_t *__restric
     }
 }
 
+// per tile panel (`per` consecutive 64-row panels): the union of the 64-row panels' (min, max) species / genus id ranges
+__global__ void __launch_bounds__(256) tile_range_kernel(const int4 *__restrict__ panel_range, int64_t panels64, int per, int4 *__restrict__ out, int64_t nout) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nout) return;
+    int4 r = make_int4(0x7fffffff, -1, 0x7fffffff, (int)0x80000000);
+    for (int k = 0; k < per; k++) {
+        const int64_t pn = t * per + k;
+        if (pn >= panels64) break;
+        const int4 x = panel_range[pn];
+        r.x = min(r.x, x.x); r.y = max(r.y, x.y); r.z = min(r.z, x.z); r.w = max(r.w, x.w);
+    }
+    out[t] = r;
+}
+
 // ---- tcgen05 / TMEM primitives ---------------------------------------------------------------
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     // K-major, SWIZZLE_NONE: start >> 4 in [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46), version 1 in [46,48)
@@ -319,6 +343,12 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar) {  // arrives on bar w
 }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {  // one accumulator column: lane r of the warp gets row r's value
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return v;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -420,6 +450,8 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
     uint64_t *tempty = tfull + 2;       // [2] accumulator stage drained
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     uint32_t *col_thr = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * STAGE + 256);  // [EPI_WARPS][EPI_COLS]
+    unsigned long long *wtab_keys = reinterpret_cast<unsigned long long *>(col_thr + EPI_WARPS * EPI_COLS);  // [EPI_WARPS][WTAB]
+    unsigned int *wtab_cnts = reinterpret_cast<unsigned int *>(wtab_keys + EPI_WARPS * WTAB);                // [EPI_WARPS][WTAB]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t rank = 0;
@@ -532,6 +564,11 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
         // by warps; the flags of 32 pairs are computed branch-free (~9 instructions per pair) before the rare slow path.
         const int q = warp & 3, g = (warp - 2) >> 2;
         uint32_t *my_thr = col_thr + (warp - 2) * EPI_COLS;  // this warp's column thresholds (warp-private: no CTA barrier)
+        unsigned long long *my_keys = wtab_keys + (warp - 2) * WTAB;
+        unsigned int *my_cnts = wtab_cnts + (warp - 2) * WTAB;
+        for (int s = lane; s < WTAB; s += 32) { my_keys[s] = TDNA_HIST_EMPTY; my_cnts[s] = 0; }
+        __syncwarp();
+        bool wtab_used = false;
         const StreamParams &sp = c_sp;
         const uint32_t wm1 = p.W - 1u;
         int64_t k = 0;
@@ -545,16 +582,10 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             const uint32_t edge_tf = (!COUNTS_MODE && p.extras && (sp.want & TDNA_WANT_EDGES)) ? sp.edge_tfix : 0u;
             const bool k2p_force = GENERAL && p.k2p != 0;  // K2P: 2(ts + tv) >= n may mean w1 <= 0 or w2 <= 0 -> NaN / +Inf must reach the exact path
             bool classes = !COUNTS_MODE && !seed && p.extras && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER));
+            if (classes) classes = (int64_t)tj * N <= (int64_t)ti * M + (M - 1) + p.class_reach;
             if (classes) {  // class pairs only live in tiles whose row and column panels share a species or a genus id range
-                bool may = false;
-                for (int a = 0; a < M / PR; a++)
-                    for (int b = 0; b < N / PR; b++) {
-                        const int pi = ti * (M / PR) + a, pj = tj * (N / PR) + b;
-                        if ((int64_t)pi * PR >= p.n || (int64_t)pj * PR >= p.n) continue;
-                        const int4 ri = sp.panel_range[pi], rj = sp.panel_range[pj];
-                        may |= (ri.x <= rj.y && rj.x <= ri.y) || (ri.z <= rj.w && rj.z <= ri.w);
-                    }
-                classes = may;
+                const int4 ri = __ldg(p.range_rows + ti), rj = __ldg(p.range_cols + tj);
+                classes = (ri.x <= rj.y && rj.x <= ri.y) || (ri.z <= rj.w && rj.z <= ri.w);
             }
             // every pair of the tile is a real pair i < j < n: no range tests in the inner loop
             const bool interior = (int64_t)tj * N > (int64_t)ti * M + M - 1 && (int64_t)tj * N + N <= p.n;
@@ -598,7 +629,11 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                 const int cb = g * (EPI_COLS / 32) + cbi;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + cb * 32), v);
-                if (cbi == EPI_COLS / 32 - 1) {  // this warp's columns of the stage are in registers: hand them back
+                // exact class pairs are read from tensor memory a second time, column by column, in a ROLLED loop below: the stage stays ours
+                // until then (the 32-fold unrolled loop this replaces carried a division and a table insert per copy: 3 * 10^9 warp
+                // instructions and an instruction cache that never hit, 0.25 - 0.5 ms per tile with class pairs)
+                const bool class_here = classes && !(GENERAL && (p.k2p || tile_amb));
+                if (cbi == EPI_COLS / 32 - 1 && !class_here) {  // this warp's columns of the stage are in registers: hand them back
                     fence_before();
                     __syncwarp();
                     if (lane == 0) {
@@ -729,6 +764,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                             }
                         }
                     }
+                    if (!want_bm && edge_tf == 0u) pmask = bmask = smask = 0;  // a class-only launch: no per-row output, no per-row state
                     if (smask && !seed) atomicOr(sp.flags + i, TDNA_ROW_SELF_VALID);
                     if (bmask && !seed) {
                         bad_row += __popc(bmask);
@@ -740,7 +776,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     // here -- a 200-load chain per pair, one lane at a time, stalled the whole tile -- but queued with bit 31 of the
                     // row index set; resolve_emit_kernel emits them, one thread per entry
                     uint32_t cmask = 0;
-                    const bool classes_deferred = GENERAL && classes && (p.k2p || tile_amb);
+                    const bool classes_deferred = classes && !class_here;
                     if (classes_deferred && i < p.n) {
                         const int spi_ = sp.species[i], gi_ = sp.genus[i];
 #pragma unroll
@@ -754,6 +790,9 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         }
                     }
                     pmask |= cmask;
+                    // entries of a launch without per-row output serve the classes only (bit 31 of the column word): the launch that
+                    // produces the rows has queued the same pairs for itself
+                    const int conly = (!want_bm && edge_tf == 0u) ? (int)0x80000000 : 0;
                     if (!seed) {
                         // bulk pass: no fp64, no threshold traffic here -- the pairs that pass the seeded thresholds are queued
                         // (one warp-aggregated atomic) and resolved after the pass (resolve_*_kernel)
@@ -773,26 +812,54 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                             if ((long long)(base + total) <= sp.qcap) {
 #pragma unroll
                                 for (int e = 0; e < 32; e++)
-                                    if (pmask & (1u << e)) { sp.qi[w] = i | (int)((cmask >> e) << 31); sp.qj[w] = jb + e; sp.qv[w] = v[e]; w++; }
+                                    if (pmask & (1u << e)) { sp.qi[w] = i | (int)((cmask >> e) << 31); sp.qj[w] = (jb + e) | conly; sp.qv[w] = v[e]; w++; }
                             } else if (lane == 0) *sp.overflow = 1;
                         }
                         pmask = 0;
                     }
 
-                    if (classes && !classes_deferred) {  // exact accumulators: one fp64 division per class pair, right here
-#pragma unroll
+                    if (class_here) {  // exact accumulators: one fp64 division per class pair, right here
+                        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + cb * 32);
+                        const int spi_ = i < p.n ? sp.species[i] : -1, gi_ = i < p.n ? sp.genus[i] : -1;
+                        const bool hist_mode = sp.hkey[0] || sp.hkey[1];
+#pragma unroll 1
                         for (int e = 0; e < 32; e++) {
+                            __syncwarp();  // lanes that skipped out of the previous column's body rejoin here
+                            const uint32_t val = tmem_ld1(tcol + (uint32_t)e);  // (warp-collective: every lane takes part)
                             const int j = jb + e;
-                            const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1, s = ident + mism;
+                            const uint32_t mism = val >> p.wshift, ident = val & wm1, s = ident + mism;
                             if (j <= i || j >= p.n || (int)s < p.min_overlap) continue;
-                            const bool hit = ((sp.want & TDNA_WANT_INTRA) && sp.species[i] == sp.species[j]) ||
-                                             ((sp.want & TDNA_WANT_INTER) && sp.genus[i] == sp.genus[j]);
-                            if (hit) class_emit<KM_P_AMBIG>(i, j, ident | (s << 16), 0u, p.min_overlap);
+                            const bool hit = ((sp.want & TDNA_WANT_INTRA) && spi_ == sp.species[j]) || ((sp.want & TDNA_WANT_INTER) && gi_ == sp.genus[j]);
+                            if (!hit) continue;
+                            if (!hist_mode) { class_emit<KM_P_AMBIG>(i, j, ident | (s << 16), 0u, p.min_overlap); continue; }
+                            // histogram mode: the pushes of this tile go through the warp's shared-memory table first
+                            int t0 = 0, t1 = 0;
+                            if ((sp.want & TDNA_WANT_INTRA) && spi_ >= 0 && spi_ == sp.species[j]) t0 = 1 + (sp.full[i] == sp.full[j] ? 1 : 0);
+                            if ((sp.want & TDNA_WANT_INTER) && gi_ == sp.genus[j] && sp.epi[i] != sp.epi[j]) t1 = 1;
+                            if (!(t0 | t1)) continue;
+                            Counts cn = {(int)s, (int)ident, 0, 0};
+                            const double d = distance_from_counts<KM_P_AMBIG>(cn, p.min_overlap);
+                            if (t0) { if (sp.hkey[0] && shist_add(my_keys, my_cnts, WTAB - 1, 0, d, t0)) wtab_used = true; else class_push(sp, 0, d, t0); }
+                            if (t1) { if (sp.hkey[1] && shist_add(my_keys, my_cnts, WTAB - 1, 1, d, t1)) wtab_used = true; else class_push(sp, 1, d, t1); }
+                        }
+                        if (cbi == EPI_COLS / 32 - 1) {  // now the stage can go back
+                            fence_before();
+                            __syncwarp();
+                            if (lane == 0) {
+                                if constexpr (PAIR) mbar_arrive_cta(&tempty[as], 0);
+                                else mbar_arrive(&tempty[as]);
+                            }
                         }
                     }
                 }
             }
             if constexpr (!COUNTS_MODE) {
+                if (__any_sync(0xffffffffu, wtab_used)) {  // this tile's class pushes: one global reduction per distinct value
+                    __syncwarp();
+                    shist_flush(sp, my_keys, my_cnts, WTAB, lane, 32);
+                    __syncwarp();
+                    wtab_used = false;
+                }
                 if (bad_row) atomicAdd(sp.inval + i, bad_row);
                 if (!GENERAL && seed && i < p.n) {
                     auto frac_bits = [&](uint32_t ident, uint32_t sh) -> unsigned long long {
@@ -858,8 +925,9 @@ __device__ __forceinline__ double queued_distance(const ResolveArgs &ra, int i, 
     Counts cn = {(int)s, (int)ident, 0, 0};
     return distance_from_counts<KM_P_AMBIG>(cn, ra.min_overlap);
 }
+constexpr int RTAB = 1024;  // slots of the resolve kernel's per-block class-histogram table
 // a queued class pair (bit 31 of the row index): PairwiseDistribution's pushes for it, with the exact distance d >= 0 (or NaN / +Inf)
-__device__ __forceinline__ void class_emit_value(const StreamParams &sp, int i, int j, double d) {
+__device__ __forceinline__ void class_emit_value(const StreamParams &sp, int i, int j, double d, unsigned long long *s_keys, unsigned int *s_cnts) {
     int times[2] = {0, 0};
     if (sp.want & TDNA_WANT_INTRA) {
         const int si = sp.species[i];
@@ -869,13 +937,17 @@ __device__ __forceinline__ void class_emit_value(const StreamParams &sp, int i, 
         if (sp.genus[i] == sp.genus[j] && sp.epi[i] != sp.epi[j]) times[1] = 1;
     }
 #pragma unroll
-    for (int k = 0; k < 2; k++)
-        if (times[k]) class_push(sp, k, d, times[k]);
+    for (int k = 0; k < 2; k++) {
+        if (!times[k]) continue;
+        if (s_keys && sp.hkey[k] && shist_add(s_keys, s_cnts, RTAB - 1, k, d, times[k])) continue;  // (RTAB is defined with the kernel below)
+        class_push(sp, k, d, times[k]);
+    }
 }
 __global__ void __launch_bounds__(256) resolve_min_kernel(StreamParams sp, ResolveArgs ra) {
     if (*sp.overflow) return;  // the queue has holes when a push did not fit: the caller falls back to the dense path
     const long long nq = min((long long)*sp.qn, sp.qcap);
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
+        if (sp.qj[r] < 0) continue;  // a class-only entry
         const int i = sp.qi[r] & 0x7fffffff, j = sp.qj[r];
         uint32_t lhs, den;
         const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den);
@@ -887,14 +959,22 @@ __global__ void __launch_bounds__(256) resolve_min_kernel(StreamParams sp, Resol
     }
 }
 __global__ void __launch_bounds__(256) resolve_emit_kernel(StreamParams sp, ResolveArgs ra) {
+    __shared__ unsigned long long s_keys[RTAB];
+    __shared__ unsigned int s_cnts[RTAB];
+    const bool hist = sp.hkey[0] || sp.hkey[1];
+    if (hist) {
+        for (int s = threadIdx.x; s < RTAB; s += 256) { s_keys[s] = TDNA_HIST_EMPTY; s_cnts[s] = 0; }
+        __syncthreads();
+    }
     if (*sp.overflow) return;
     const long long nq = min((long long)*sp.qn, sp.qcap);
     const bool want_bm = (sp.want & TDNA_WANT_BEST_MATCH) != 0;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
-        const int qi_raw = sp.qi[r], i = qi_raw & 0x7fffffff, j = sp.qj[r];
+        const int qi_raw = sp.qi[r], qj_raw = sp.qj[r], i = qi_raw & 0x7fffffff, j = qj_raw & 0x7fffffff;
         uint32_t lhs, den;
         const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den);
-        if (qi_raw < 0 && !(d < 0.0)) class_emit_value(sp, i, j, d);  // a deferred class pair (valid: NaN / +Inf are kept, -1 is dropped)
+        if (qi_raw < 0 && !(d < 0.0)) class_emit_value(sp, i, j, d, hist ? s_keys : nullptr, s_cnts);  // a deferred class pair (valid: NaN / +Inf are kept, -1 is dropped)
+        if (qj_raw < 0) continue;  // a class-only entry: the rows' launch queued this pair for itself
         if (d < 0.0) {  // queued with an uncertain overlap (ambiguity letters), and the exact overlap is below minOverlap: an invalid pair
             atomicAdd(sp.inval + i, 1);
             atomicAdd(sp.inval + j, 1);
@@ -925,6 +1005,10 @@ __global__ void __launch_bounds__(256) resolve_emit_kernel(StreamParams sp, Reso
         unsigned long long w = pos;
         if (ei) { sp.cq[w] = i; sp.cj[w] = j; sp.cd[w] = d; atomicAdd(sp.cnt + i, 1); w++; }
         if (ej) { sp.cq[w] = j; sp.cj[w] = i; sp.cd[w] = d; atomicAdd(sp.cnt + j, 1); }
+    }
+    if (hist) {  // the block's class pushes: one global reduction per distinct value
+        __syncthreads();
+        shist_flush(sp, s_keys, s_cnts, RTAB, threadIdx.x, 256);
     }
 }
 

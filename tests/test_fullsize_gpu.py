@@ -180,3 +180,59 @@ def test_c2_2185_by_2664_full_matrix(ctx):
     (shared, ident, _, _), dist = aln.pair(7, 1234)
     assert u64(dist) == u64(D[7, 1234])
     aln.close()
+
+
+def test_n_200000_kernel_b_equals_kernel_a(ctx):
+    """2 * 10^10 pairs: the tcgen05 kernel's records against the popc kernel's, byte for byte, plus sampled oracle rows."""
+    import taxondna_b200 as t
+    from taxondna_b200 import synth
+    d = synth.generate("H", names=False, scale_n=200000)
+    n = d["symbols"].shape[0]
+    assert n == 200000
+    aln = t.Alignment(ctx, d["symbols"])
+    aln.set_labels(d["species_id"], d["genus_id"], d["epithet_rank"], d["fullname_rank"])
+    aln.set_config(0, 300, True)
+    out = both_kernels(ctx, aln)
+    assert out["tensor"].tobytes() == out["popc"].tobytes()
+    record_invariants(out["tensor"], n)
+    assert int(out["tensor"]["n_valid"].astype(np.int64).sum()) == n * (n - 1)
+    check_rows_against_oracle(out["tensor"], d["symbols"], d["species_id"], 0, 300, sample_blocks(n, blocks=3, rows=4, seed=5))
+    aln.close()
+
+
+def test_c5_shape_one_million_rows_rows_and_both_histograms_in_one_pass(ctx):
+    """BASELINE.json configs[4] on one GPU: 1,000,000 x 658, 5 * 10^11 pairs, streaming Best Match + the intra / congeneric-inter
+    histograms from ONE pass, nothing O(pairs) anywhere.  Checked through what does not need an N x N oracle: sampled query rows
+    against the oracle, record invariants, and the histograms' totals against the counts the labels imply."""
+    import ctypes
+
+    import taxondna_b200 as t
+    from taxondna_b200 import synth
+    d = synth.generate("C5", names=False)
+    sym = d["symbols"]
+    n = sym.shape[0]
+    assert sym.shape == (1000000, 658)
+    aln = t.Alignment(ctx, sym)
+    aln.set_labels(d["species_id"], d["genus_id"], d["epithet_rank"], d["fullname_rank"])
+    aln.set_config(0, 300, True)
+    rows = np.zeros(n, dtype=t.ROW_RESULT_DTYPE)
+    hi = np.zeros(1 << 16, dtype=t.HIST_ENTRY_DTYPE)
+    he = np.zeros(1 << 16, dtype=t.HIST_ENTRY_DTYPE)
+    io = t.Analysis()
+    io.want = t.WANT_BEST_MATCH | t.WANT_HIST_INTRA | t.WANT_HIST_INTER
+    io.rows = rows.ctypes.data
+    io.hist_intra, io.hist_intra_cap = hi.ctypes.data, hi.size
+    io.hist_inter, io.hist_inter_cap = he.ctypes.data, he.size
+    t.check(ctx.L.tdna_analyze(aln.h, ctypes.byref(io)))
+    assert aln.last_count_kernel() == t.KERNEL_TENSOR
+    record_invariants(rows, n)
+    assert int(rows["n_valid"].astype(np.int64).sum()) == n * (n - 1)  # clean data: every pair is valid
+    # 100,000 species of 10: C(10, 2) intraspecific pairs each; 1,000 genera of 100 species: C(100, 2) * 10 * 10 congeneric pairs each
+    assert io.hist_intra_pushes == 100000 * 45 and int(hi[: io.n_hist_intra]["count"].sum()) == 100000 * 45
+    assert io.hist_inter_pushes == 1000 * 4950 * 100 and int(he[: io.n_hist_inter]["count"].sum()) == 1000 * 4950 * 100
+    assert 0 < io.n_hist_intra <= hi.size and 0 < io.n_hist_inter <= he.size
+    # a conspecific is each row's best match on this data
+    sp = d["species_id"]
+    assert (sp[rows["best"]] == sp).mean() > 0.999
+    check_rows_against_oracle(rows, sym, sp, 0, 300, [(0, 3), (499999, 500002), (n - 3, n)])
+    aln.close()
