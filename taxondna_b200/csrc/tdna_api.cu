@@ -124,7 +124,9 @@ struct tdna_aln {
     bool avoid_tensor = false;  // AUTO: kernel (b)'s queue overflowed on this alignment (static thresholds too loose): use kernel (a)
     // count kernel (b): one-hot int8 operands (tdna_tc.cuh)
     uint8_t *d_tcA = nullptr, *d_tcB = nullptr, *d_tcfull = nullptr, *d_tcpanel_amb = nullptr;
-    int *d_tcflag = nullptr;       // [0] a symbol outside the alphabet met while encoding, [1] some IUPAC ambiguity letter
+    int *d_tcflag = nullptr;       // [0] a symbol outside the alphabet met while encoding, [1] some IUPAC ambiguity letter (or dropped gap),
+                                   // [2] internal gap sites the four-dimension code of uncorrected p left out
+    bool tc_dims5 = false;         // uncorrected p: the list has too many internal gaps for the four-dimension code
     tc::EncodeValues tc_values = {};
     int32_t *d_tcamb = nullptr;  // per row: sites holding a letter the operands cannot express (nullptr state: see tc_has_amb)
     bool tc_has_amb = false;
@@ -558,21 +560,26 @@ static int tc_prepare(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
     if ((a->kmode != KM_P_AMBIG && a->kmode != KM_K2P) || a->L >= 4096) return -1;
     // K2P ignores gap sites: four symbol dimensions -- where a four-dimension code exists (W = 1024 only, i.e. L < 1024); longer K2P
-    // alignments use the five-dimension code with the gap dimension left empty (25 % more K-bytes per site)
-    int dims = a->kmode == KM_K2P ? 4 : 5;
+    // alignments use the five-dimension code with the gap dimension left empty (25 % more K-bytes per site).
+    // Uncorrected p: barcode alignments rarely have INTERNAL gaps (external ones are '_' already), so the operands start with four
+    // dimensions as well -- 20 % fewer K-bytes, MMAs and operand traffic -- and an internal '-' is left out like an ambiguity letter
+    // (counted per row; the pairs it touches are bounded by the accumulator and settled from the bit-planes).  A list with more than
+    // a sprinkling of internal gaps (tc_dims5: decided from the count the encoder returns) gets the five-dimension code, where '-'
+    // is a symbol of its own and every accumulator is exact again.
+    int dims = (a->kmode == KM_K2P || !a->tc_dims5) ? 4 : 5;
     tc::EncodeValues v = {};
     uint32_t W = 0;
     if (!find_code(a->L, dims, v, W)) {
         dims = 5;
         if (!find_code(a->L, dims, v, W)) return -1;
     }
-    v.gap_is_symbol = a->kmode == KM_K2P ? 0 : 1;
+    v.gap_is_symbol = (a->kmode == KM_K2P || dims == 4) ? 0 : 1;
     const int nchunks = (a->L * dims + tc::KB - 1) / tc::KB;
     const int64_t npa = round_up(a->n, tc::M), npb = round_up(a->n, tc::N);
     const size_t npan = (size_t)(npb / tc::M);
     bool ok = cudaSuccess == DMALLOC(&a->d_tcA, (size_t)npa * nchunks * tc::KB) && cudaSuccess == DMALLOC(&a->d_tcB, (size_t)npb * nchunks * tc::KB) &&
               cudaSuccess == DMALLOC(&a->d_tcfull, npan) && cudaSuccess == DMALLOC(&a->d_tcamb, (size_t)a->n * 4) &&
-              cudaSuccess == DMALLOC(&a->d_tcpanel_amb, npan) && cudaSuccess == DMALLOC(&a->d_tcflag, 8);
+              cudaSuccess == DMALLOC(&a->d_tcpanel_amb, npan) && cudaSuccess == DMALLOC(&a->d_tcflag, 16);
     // bulk phase: bands of TC_BAND row tiles; only real tiles are numbered (tdna_tc.cuh: slot_coords): a staircase over the band's
     // first TC_BAND / 2 columns, then TC_BAND slots per column
     const int nrt = (int)(npa / tc::M);
@@ -590,7 +597,7 @@ static int tc_prepare(tdna_aln *a) {
     if (ok) {
         cudaMemsetAsync(a->d_tcfull, 0, npan, c->stream);
         cudaMemsetAsync(a->d_tcpanel_amb, 0, npan, c->stream);
-        cudaMemsetAsync(a->d_tcflag, 0, 8, c->stream);
+        cudaMemsetAsync(a->d_tcflag, 0, 16, c->stream);
         cudaMemcpyAsync(a->d_tcprefix[1], pre.data(), (size_t)(nbands + 1) * 8, cudaMemcpyHostToDevice, c->stream);
         ok = cudaStreamSynchronize(c->stream) == cudaSuccess;  // pre is a stack-lifetime host buffer
     }
@@ -646,7 +653,8 @@ static void tc_encode_range(tdna_aln *a, cudaStream_t stream, int64_t panel0, in
     const int64_t row0 = panel0 * tc::N, rows = std::min<int64_t>(a->n, (panel0 + panels) * tc::N) - row0;
     if (rows > 0)
         tc::amb_count_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, a->kmode == KM_K2P ? 1 : 0, a->d_tcamb,
-                                                                            a->d_tcpanel_amb, a->d_tcflag + 1, row0);
+                                                                            a->d_tcpanel_amb, a->d_tcflag + 1, row0,
+                                                                            (a->kmode != KM_K2P && a->tc_dims == 4) ? 1 : 0);
     if (a->tc_pair) {  // cta_group::2 (experiments): the b-side in 128-row panels as well; whole alignment only
         tc::encode_kernel<false, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npa / tc::M)), 256, 0, stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, a->tc_values, a->d_tcA, a->d_tcflag, a->d_tcfull);
         tc::encode_kernel<true, tc::M><<<dim3((unsigned)nchunks, (unsigned)(npb / tc::M)), 256, 0, stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, nchunks, dims, a->tc_values, a->d_tcB, a->d_tcflag, nullptr);
@@ -660,6 +668,11 @@ static void tc_encode_range(tdna_aln *a, cudaStream_t stream, int64_t panel0, in
     c->launches += 3;
 }
 
+// uncorrected p on the four-dimension code: do the internal gaps it leaves out outnumber a sprinkling (1 site in 2,000)?
+static bool tc_too_gappy(const tdna_aln *a, int gap_sites) {
+    return a->kmode != KM_K2P && a->tc_dims == 4 && !a->tc_dims5 && (int64_t)gap_sites * 2000 > (int64_t)a->n * a->L;
+}
+
 // 1 = ready, -1 = this alignment / configuration is not eligible
 int ensure_tc(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
@@ -668,15 +681,20 @@ int ensure_tc(tdna_aln *a) {
     if (a->tc_state != 0) return a->tc_state;
     if (tc_prepare(a) != 1) { a->tc_state = -1; return -1; }
     tc_encode_range(a, c->stream, 0, round_up(a->n, tc::N) / tc::N);
-    int flags2[2] = {0, 0};
-    cudaMemcpyAsync(flags2, a->d_tcflag, 8, cudaMemcpyDeviceToHost, c->stream);
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) flags2[0] = 1;
-    if (flags2[0]) {  // a symbol outside the alphabet (the pack kernel rejects those first) or a launch failure: the popc kernel handles it
+    int flags3[4] = {0, 0, 0, 0};
+    cudaMemcpyAsync(flags3, a->d_tcflag, 12, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) flags3[0] = 1;
+    if (flags3[0]) {  // a symbol outside the alphabet (the pack kernel rejects those first) or a launch failure: the popc kernel handles it
         tc_release(a);
         a->tc_state = -1;
         return -1;
     }
-    a->tc_has_amb = flags2[1] != 0;
+    if (tc_too_gappy(a, flags3[2])) {  // once per alignment: the same operands again with '-' as a fifth symbol
+        tc_release(a);
+        a->tc_dims5 = true;
+        return ensure_tc(a);
+    }
+    a->tc_has_amb = flags3[1] != 0;
     a->tc_state = 1;
     return 1;
 }
@@ -1230,9 +1248,9 @@ static int aln_build(tdna_ctx *c, tdna_aln *a, const uint8_t *symbols, const int
         c->launches++;
         if (tc_ok) tc_encode_range(a, c->stream, r0 / tc::N, std::min<int64_t>(panels_all, (r0 + R) / tc::N) - r0 / tc::N);
     }
-    int flags[4] = {0, 0, 0, 0};
+    int flags[6] = {0, 0, 0, 0, 0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(flags, d_err, 4, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess && tc_ok) e = cudaMemcpyAsync(flags + 2, a->d_tcflag, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && tc_ok) e = cudaMemcpyAsync(flags + 2, a->d_tcflag, 12, cudaMemcpyDeviceToHost, c->stream);
     cudaError_t e2 = cudaStreamSynchronize(c->copy_stream);  // whatever happened: no copy outlives the call
     cudaError_t e3 = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : e3;
@@ -1241,8 +1259,13 @@ static int aln_build(tdna_ctx *c, tdna_aln *a, const uint8_t *symbols, const int
     if (flags[0] || flags[2]) return fail(TDNA_E_SYMBOL, "a symbol outside the normalised alphabet ACGT RYKMSWBDHVN - _ ?");
     a->packed = true;
     if (tc_ok) {
-        a->tc_has_amb = flags[3] != 0;
-        a->tc_state = 1;
+        if (tc_too_gappy(a, flags[4])) {  // rebuilt with the five-dimension code at first use (ensure_tc)
+            tc_release(a);
+            a->tc_dims5 = true;
+        } else {
+            a->tc_has_amb = flags[3] != 0;
+            a->tc_state = 1;
+        }
     }
     return TDNA_OK;
 }

@@ -291,20 +291,25 @@ __global__ void __launch_bounds__(256) flip_flags_kernel(uint8_t *flags, int64_t
 // (K2P: only R and Y are inside the model, Sequence.java:1498-1557, but every letter counts towards the K2P-mode shared length
 // that the minOverlap gate tests, :1446-1471 -- one count bounds both.)
 __global__ void __launch_bounds__(256) amb_count_kernel(const uint8_t *__restrict__ sym, const int32_t *__restrict__ len, int64_t n, int64_t sym_stride,
-                                                        int L, int k2p, int32_t *__restrict__ amb, uint8_t *__restrict__ panel_amb, int *__restrict__ any, int64_t row0) {
+                                                        int L, int k2p, int32_t *__restrict__ amb, uint8_t *__restrict__ panel_amb, int *__restrict__ any, int64_t row0,
+                                                        int gaps_dropped) {
+    // gaps_dropped: the four-dimension code of uncorrected p leaves internal gaps out of the operands too (any[1] counts those sites:
+    // a list with more than a sprinkling of them is re-encoded with the five-dimension code, where '-' is a symbol of its own)
     const int64_t row = row0 + (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n) return;
     const int lane = threadIdx.x & 31, row_len = min(len[row], L);
-    int cnt = 0;
+    int cnt = 0, gaps = 0;
     for (int site = lane; site < row_len; site += 32) {
         const uint32_t cls = c_symlut[sym[row * sym_stride + site]];
         if ((cls & SB_LET) && __popc(cls & 15u) != 1) cnt++;
+        if (gaps_dropped && (cls & SB_D)) gaps++;
     }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, m);
+    for (int m = 16; m >= 1; m >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, m); gaps += __shfl_xor_sync(0xffffffffu, gaps, m); }
     if (lane == 0) {
-        amb[row] = cnt;
-        if (cnt) { panel_amb[row / M] = 1; *any = 1; }
+        amb[row] = cnt + gaps;
+        if (cnt + gaps) { panel_amb[row / M] = 1; *any = 1; }
+        if (gaps) atomicAdd(any + 1, gaps);
     }
 }
 
@@ -606,13 +611,21 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     else {
                         const uint32_t t = (want_bm && j < p.n) ? __ldcg(sp.thr + j) : 0u;  // <= 2^16
                         if (tile_amb) my_thr[x * 32 + lane] = t | ((j < p.n ? (uint32_t)__ldg(p.amb + j) : 0u) << 20);  // amb[j] < 4096
-                        else my_thr[x * 32 + lane] = full ? (uint32_t)(((unsigned long long)t * (uint32_t)p.L) >> 16) : t;
+                        else if (!full) my_thr[x * 32 + lane] = t;
+                        else {
+                            // shared == L everywhere: mism << 16 <= thr * L  <=>  mism <= (thr * L) >> 16 =: b.  The plain instantiation
+                            // goes one step further and compares the RAW accumulator D = ident + W * mism (ident < W):
+                            // mism <= b  <=>  D < (b + 1) * W -- no shift per pair
+                            const uint32_t b = (uint32_t)(((unsigned long long)t * (uint32_t)p.L) >> 16);
+                            my_thr[x * 32 + lane] = GENERAL ? b : (b + 1u) << p.wshift;
+                        }
                     }
                 }
                 if (want_bm && i < p.n) tf_row = max(tf_row, __ldcg(sp.thr + i));
                 __syncwarp();
             }
             const uint32_t brow = (uint32_t)(((unsigned long long)tf_row * (uint32_t)p.L) >> 16);
+            const uint32_t brow_raw = (brow + 1u) << p.wshift;  // (b <= L < W: no overflow)
             const uint32_t half_l = k2p_force ? ((uint32_t)p.L + 1u) >> 1 : 0xffffffffu;  // 2 * mism >= L
             mbar_wait(&tfull[as], (uint32_t)((k >> 1) & 1));
             fence_after();
@@ -727,8 +740,12 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
 #pragma unroll
                             for (int u = 0; u < 4; u++) {
                                 const int e = e4 * 4 + u;
-                                const uint32_t mism = v[e] >> p.wshift;
-                                if ((mism <= max(brow, cts[u])) | (mism >= half_l)) pmask |= 1u << e;
+                                if constexpr (!GENERAL) {
+                                    if (v[e] < max(brow_raw, cts[u])) pmask |= 1u << e;
+                                } else {
+                                    const uint32_t mism = v[e] >> p.wshift;
+                                    if ((mism <= max(brow, cts[u])) | (mism >= half_l)) pmask |= 1u << e;
+                                }
                             }
                         }
                     } else if (interior) {
