@@ -387,9 +387,10 @@ class Bench:
         ms_per_step = self.max_over_ranks(float(sum(step_ms))) / steps
         value = pairs / (ms_per_step * 1e-3) / 1e9
         used_tensor = streaming and aln.last_count_kernel() == t.KERNEL_TENSOR
+        pass_stats = aln.last_pass_stats() if streaming else None
         out = {"n": n, "L": L, "pairs": pairs, "mode": mode, "kind": kind, "desc": wl["desc"], "value": value, "ms_per_step": ms_per_step,
                "steps": steps, "warmup": warmup, "launches": int(launches), "clocks": clocks, "region_wall_s": t_region,
-               "used_tensor": used_tensor, "rows_mine": rows_mine, "b0": b0, "b1": b1}
+               "used_tensor": used_tensor, "rows_mine": rows_mine, "b0": b0, "b1": b1, "pass_stats": pass_stats}
 
         # ---- the result of the N-GPU pass against ONE GPU's, byte for byte ------------------------------------------
         if world > 1 and streaming:
@@ -634,6 +635,8 @@ def main():
             "roofline": r.get("roofline"), "cpu_baseline": r["cpu_baseline"], "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"],
             "region_wall_s": r["region_wall_s"],
         }
+        if r.get("pass_stats"):
+            line["config"]["pass_stats_rank0"] = r["pass_stats"]
         if "phases_ms" in r:
             line["phases_ms_rank0"] = r["phases_ms"]
         if "parity_vs_1gpu" in r:

@@ -391,6 +391,9 @@ int32_t tdna_last_count_kernel(tdna_aln *aln);
 /* Symbol dimensions per site of the one-hot operands count kernel (b) built for this alignment (5, or 4 when no row has an internal
  * gap / in K2P mode); 0 if they have not been built.  The roofline's algorithmic work per pair is 2 * dims * L int8 operations. */
 int32_t tdna_tensor_dims(tdna_aln *aln);
+/* Sizes of the most recent streaming pass on this GPU: candidate records emitted (two per pair at most) and pairs count kernel (b)
+ * queued for exact resolution (0 on count kernel (a)). */
+int32_t tdna_last_pass_stats(tdna_aln *aln, int64_t *candidates, int64_t *queued);
 /* Device time between the phase marks of the context's most recent multi-GPU pass (CUDA events on its stream), in order: seed launch,
  * MIN all-reduce of the per-row minima, thresholds + bulk launch + queue resolution, routing + exchange of records / state / status,
  * merge of the own rows, all-gather of the row records.  *n_out phases are written (at most cap). */

@@ -80,7 +80,7 @@ EXPORTS = [
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
     "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_rows_per_part", "tdna_tensor_code", "tdna_consensus", "tdna_fasta_parse", "tdna_fasta_destroy", "tdna_fasta_count", "tdna_fasta_width", "tdna_fasta_records", "tdna_fasta_symbols", "tdna_alignment_create_from_fasta", "tdna_best_match_part_routed", "tdna_best_match_merge_routed", "tdna_set_option", "tdna_last_tile_pass_ms",
-    "tdna_tensor_dims", "tdna_multi_phase_ms", "tdna_analyze_host", "tdna_class_histogram", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
+    "tdna_tensor_dims", "tdna_last_pass_stats", "tdna_multi_phase_ms", "tdna_analyze_host", "tdna_class_histogram", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -170,6 +170,7 @@ def load():
     L.tdna_tensor_counts.argtypes = [vp, vp]
     L.tdna_last_count_kernel.argtypes = [vp]
     L.tdna_tensor_dims.argtypes = [vp]
+    L.tdna_last_pass_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.tdna_multi_phase_ms.argtypes = [vp, vp, i32, ctypes.POINTER(i32)]
     L.tdna_analyze.argtypes = [vp, ctypes.POINTER(Analysis)]
     L.tdna_analyze_host.argtypes = [vp, ctypes.POINTER(HostList), ctypes.POINTER(Analysis), vp]
@@ -459,6 +460,11 @@ class Alignment:
 
     def last_count_kernel(self):
         return int(self.L.tdna_last_count_kernel(self.h))
+
+    def last_pass_stats(self):
+        c, q = ctypes.c_int64(), ctypes.c_int64()
+        check(self.L.tdna_last_pass_stats(self.h, ctypes.byref(c), ctypes.byref(q)))
+        return {"candidates": c.value, "queued_pairs": q.value}
 
     def tensor_dims(self):
         return int(self.L.tdna_tensor_dims(self.h))

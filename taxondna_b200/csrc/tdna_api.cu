@@ -119,7 +119,7 @@ struct tdna_aln {
     int32_t *d_lj = nullptr;
     double *d_ld = nullptr;
     long long list_cap = 0;
-    long long last_ncand = 0, last_ncls[2] = {0, 0}, last_nedge = 0;
+    long long last_ncand = 0, last_ncls[2] = {0, 0}, last_nedge = 0, last_queue = 0;
     int last_kernel = 0;  // TDNA_KERNEL_* of the most recent streaming pass
     bool avoid_tensor = false;  // AUTO: kernel (b)'s queue overflowed on this alignment (static thresholds too loose): use kernel (a)
     // count kernel (b): one-hot int8 operands (tdna_tc.cuh)
@@ -438,8 +438,9 @@ static int tc_resolve_queue(tdna_aln *a) {
     while ((1u << wshift) < a->tc_W) wshift++;
     unsigned grid = (unsigned)c->sm_count * 8;
     tc::ResolveArgs ra = {wshift, a->tc_W - 1u, a->min_overlap, (a->kmode == KM_K2P || a->tc_has_amb) ? a->d_planes : nullptr, a->W,
-                          a->kmode == KM_K2P ? 1 : 0};
+                          a->kmode == KM_K2P ? 1 : 0, 0};
     if (a->sp.want & TDNA_WANT_BEST_MATCH) {
+        ra.cached = ra.planes ? 1 : 0;  // resolve_min_kernel leaves the exact counts of the rows' entries in the queue
         tc::resolve_min_kernel<<<grid, 256, 0, c->stream>>>(a->sp, ra);
         stream_thr_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n);
         c->launches += 2;
@@ -1336,7 +1337,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     cudaSetDevice(c->device);
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
-                    a->d_needc, a->d_panel_range, a->d_range_rows, a->d_range_cols, a->sp.qi, a->sp.qj, a->sp.qv, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcflag, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
+                    a->d_needc, a->d_panel_range, a->d_range_rows, a->d_range_cols, a->sp.qi, a->sp.qj, a->sp.qv, a->sp.qx, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcflag, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_seedlist, a->d_cursor, a->d_lj, a->d_ld,
                     a->x_send, a->x_recv, a->x_state, a->d_hkey[0], a->d_hkey[1], a->d_hcnt[0], a->d_hcnt[1], a->d_hctr, a->d_hent};
     for (void *p : ptrs)
@@ -1691,6 +1692,7 @@ static int ensure_stream_state(tdna_aln *a) {
     CU(DMALLOC(&sp.qi, (size_t)qcap * 4));
     CU(DMALLOC(&sp.qj, (size_t)qcap * 4));
     CU(DMALLOC(&sp.qv, (size_t)qcap * 4));
+    CU(DMALLOC(&sp.qx, (size_t)qcap * 4));
     sp.qcap = qcap;
     CU(DMALLOC(&a->d_stream_u64, 64));  // ncand, overflow, ncls[2], nedge, qn
     sp.ncand = reinterpret_cast<unsigned long long *>(a->d_stream_u64);
@@ -1718,7 +1720,7 @@ static bool grow_stream_buffers(tdna_aln *a) {
     if (a->need_queue > qcap) qcap = a->need_queue + a->need_queue / 4;
     a->need_cand = a->need_queue = 0;
     if (cap == sp.cap && qcap == sp.qcap) return false;
-    if (cap * 16 + qcap * 12 > c->budget / 4) return false;
+    if (cap * 16 + qcap * 16 > c->budget / 4) return false;
     if (cap != sp.cap) {
         DFREE(sp.cq); DFREE(sp.cj); DFREE(sp.cd);
         sp.cq = sp.cj = nullptr; sp.cd = nullptr;
@@ -1730,9 +1732,10 @@ static bool grow_stream_buffers(tdna_aln *a) {
         sp.cap = cap;
     }
     if (qcap != sp.qcap) {
-        DFREE(sp.qi); DFREE(sp.qj); DFREE(sp.qv);
-        sp.qi = sp.qj = nullptr; sp.qv = nullptr;
-        if (cudaSuccess != DMALLOC(&sp.qi, (size_t)qcap * 4) || cudaSuccess != DMALLOC(&sp.qj, (size_t)qcap * 4) || cudaSuccess != DMALLOC(&sp.qv, (size_t)qcap * 4)) {
+        DFREE(sp.qi); DFREE(sp.qj); DFREE(sp.qv); DFREE(sp.qx);
+        sp.qi = sp.qj = nullptr; sp.qv = sp.qx = nullptr;
+        if (cudaSuccess != DMALLOC(&sp.qi, (size_t)qcap * 4) || cudaSuccess != DMALLOC(&sp.qj, (size_t)qcap * 4) || cudaSuccess != DMALLOC(&sp.qv, (size_t)qcap * 4) ||
+            cudaSuccess != DMALLOC(&sp.qx, (size_t)qcap * 4)) {
             cudaGetLastError();
             a->stream_broken = true;
             return false;
@@ -1781,6 +1784,7 @@ static int stream_bulk(tdna_aln *a, int part, int nparts, long long *ncand_out) 
         return fail(TDNA_E_TOO_LARGE, "streaming Best Match: candidate buffer overflow");
     }
     a->last_ncand = (long long)h.ncand;
+    a->last_queue = (long long)h.qn;
     a->last_ncls[0] = a->local_ncls[0] = (long long)h.ncls[0];
     a->last_ncls[1] = a->local_ncls[1] = (long long)h.ncls[1];
     a->last_nedge = a->local_nedge = (long long)h.nedge;
@@ -1988,6 +1992,7 @@ static int multi_attempt(tdna_aln *a, bool want_bm, int64_t *status) {
     a->last_ncls[1] = status[3];
     a->last_nedge = status[4];
     a->last_ncand = status[5];
+    a->last_queue = (long long)h.qn;
     return TDNA_OK;
 }
 
@@ -3021,6 +3026,13 @@ int32_t tdna_multi_phase_ms(tdna_ctx *c, float *ms, int32_t cap, int32_t *n_out)
     int k = 0;
     for (; k + 1 < c->n_ph && k < cap; k++) CU(cudaEventElapsedTime(&ms[k], c->ev_ph[k], c->ev_ph[k + 1]));
     *n_out = k;
+    return TDNA_OK;
+}
+
+int32_t tdna_last_pass_stats(tdna_aln *a, int64_t *candidates, int64_t *queued) {
+    if (!a) return fail(TDNA_E_ARG, "null alignment");
+    if (candidates) *candidates = a->last_ncand;
+    if (queued) *queued = a->last_queue;
     return TDNA_OK;
 }
 

@@ -160,7 +160,7 @@ struct StreamParams {
     // count kernel (b) defers its slow path: the epilogue only queues (row, column, raw accumulator) of the pairs that pass
     // the seeded thresholds; tc::resolve_*_kernel turn the queue into candidate records after the pass
     int32_t *qi, *qj;
-    uint32_t *qv;
+    uint32_t *qv, *qx;           // qx: second word of the exact counts resolve_min_kernel leaves for resolve_emit_kernel
     unsigned long long *qn;
     long long qcap;
 };

@@ -922,19 +922,27 @@ struct ResolveArgs {
     const uint32_t *planes;  // non-null: exact counts of the pair from the bit-planes (K2P; alignments with ambiguity letters)
     int W32;
     int k2p;
+    int cached;  // the exact counts of the rows' entries sit in qv / qx already (resolve_min_kernel put them there): no second walk of the planes
 };
-__device__ __forceinline__ double queued_distance(const ResolveArgs &ra, int i, int j, uint32_t val, uint32_t &lhs, uint32_t &den) {
+// exact counts <-> two queue words: (c1 | shared << 16, c2 | c3 << 16), every count <= L <= 65535
+__device__ __forceinline__ double cached_distance(const ResolveArgs &ra, uint32_t w0, uint32_t w1, uint32_t &lhs, uint32_t &den) {
+    Counts c = {(int)(w0 >> 16), (int)(w0 & 0xffffu), (int)(w1 & 0xffffu), (int)(w1 >> 16)};
+    if (ra.k2p) {
+        lhs = (uint32_t)(c.c2 + c.c3) << 16;
+        den = (uint32_t)c.c1;
+        return distance_from_counts<KM_K2P>(c, ra.min_overlap);
+    }
+    lhs = (uint32_t)(c.shared - c.c1) << 16;
+    den = (uint32_t)c.shared;
+    return distance_from_counts<KM_P_AMBIG>(c, ra.min_overlap);
+}
+__device__ __forceinline__ double queued_distance(const ResolveArgs &ra, int i, int j, uint32_t val, uint32_t &lhs, uint32_t &den, uint32_t *w0 = nullptr,
+                                                  uint32_t *w1 = nullptr) {
     if (ra.planes) {
-        if (ra.k2p) {
-            const Counts c = pair_counts_global<KM_K2P>(ra.planes, i, j, ra.W32);
-            lhs = (uint32_t)(c.c2 + c.c3) << 16;
-            den = (uint32_t)c.c1;
-            return distance_from_counts<KM_K2P>(c, ra.min_overlap);
-        }
-        const Counts c = pair_counts_global<KM_P_AMBIG>(ra.planes, i, j, ra.W32);
-        lhs = (uint32_t)(c.shared - c.c1) << 16;
-        den = (uint32_t)c.shared;
-        return distance_from_counts<KM_P_AMBIG>(c, ra.min_overlap);  // -1.0: the queued overlap was uncertain and is too short
+        const Counts c = ra.k2p ? pair_counts_global<KM_K2P>(ra.planes, i, j, ra.W32) : pair_counts_global<KM_P_AMBIG>(ra.planes, i, j, ra.W32);
+        const uint32_t x0 = (uint32_t)c.c1 | ((uint32_t)c.shared << 16), x1 = (uint32_t)c.c2 | ((uint32_t)c.c3 << 16);
+        if (w0) { *w0 = x0; *w1 = x1; }
+        return cached_distance(ra, x0, x1, lhs, den);  // (p: -1.0 when the queued overlap was uncertain and is too short)
     }
     const uint32_t mism = val >> ra.wshift, ident = val & ra.wm1, s = ident + mism;
     lhs = mism << 16;
@@ -966,8 +974,9 @@ __global__ void __launch_bounds__(256) resolve_min_kernel(StreamParams sp, Resol
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
         if (sp.qj[r] < 0) continue;  // a class-only entry
         const int i = sp.qi[r] & 0x7fffffff, j = sp.qj[r];
-        uint32_t lhs, den;
-        const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den);
+        uint32_t lhs, den, w0 = 0, w1 = 0;
+        const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den, &w0, &w1);
+        if (ra.planes) { sp.qv[r] = w0; sp.qx[r] = w1; }  // the exact counts, for resolve_emit_kernel
         if (!(d < __longlong_as_double((long long)TDNA_INF_BITS)) || d < 0.0) continue;
         const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
         const int spi = sp.species[i], spj = sp.species[j];
@@ -989,7 +998,7 @@ __global__ void __launch_bounds__(256) resolve_emit_kernel(StreamParams sp, Reso
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
         const int qi_raw = sp.qi[r], qj_raw = sp.qj[r], i = qi_raw & 0x7fffffff, j = qj_raw & 0x7fffffff;
         uint32_t lhs, den;
-        const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den);
+        const double d = (ra.cached && qj_raw >= 0) ? cached_distance(ra, sp.qv[r], sp.qx[r], lhs, den) : queued_distance(ra, i, j, sp.qv[r], lhs, den);
         if (qi_raw < 0 && !(d < 0.0)) class_emit_value(sp, i, j, d, hist ? s_keys : nullptr, s_cnts);  // a deferred class pair (valid: NaN / +Inf are kept, -1 is dropped)
         if (qj_raw < 0) continue;  // a class-only entry: the rows' launch queued this pair for itself
         if (d < 0.0) {  // queued with an uncertain overlap (ambiguity letters), and the exact overlap is below minOverlap: an invalid pair
