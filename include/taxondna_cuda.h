@@ -336,6 +336,9 @@ enum { TDNA_OPT_BEST_MATCH_PATH = 1, /* TDNA_PATH_*: how tdna_best_match compute
        TDNA_OPT_COUNT_KERNEL = 3,    /* TDNA_KERNEL_*: which count kernel the streaming pass uses */
        TDNA_OPT_HIST_SLOTS = 5,      /* first size of a class histogram's table for alignments created from now on (a power of two,
                                         default 2^18; a pass that fills a table repeats with four times the slots) */
+       TDNA_OPT_SEGMENT_ITEMS = 6,   /* work items (tiles of kernel (a), tile pairs of kernel (b)) per launch of a streaming pass; 0 =
+                                        automatic (~30 ms of work).  Between launches a single-GPU pass honours tdna_cancel and calls
+                                        the progress callback */
        TDNA_OPT_MULTI = 4            /* 1 (default): whole-range calls are shared by the communicator's ranks; 0: this GPU alone;
                                         2: the collective path even when the communicator has ONE rank (tests on a one-GPU box) */ };
 enum { TDNA_KERNEL_AUTO = 0,   /* the faster eligible one (A/B on ncu evidence) */
@@ -372,7 +375,12 @@ int32_t tdna_edges_below(tdna_aln *aln, double t, int32_t *ii, int32_t *jj, doub
  * (SpeciesDetail.getSequencesWithValidConspecificsCount, Common/DNA/SpeciesDetail.java:78-95). */
 int32_t tdna_valid_conspecifics(tdna_aln *aln, uint8_t *has_valid);
 
-/* ---- progress / cancel (DelayCallback, Common/DelayCallback.java:34-56) -------------------- */
+/* ---- progress / cancel (DelayCallback, Common/DelayCallback.java:34-56) --------------------
+ * The callback runs on the calling thread: between row bands of a matrix-shaped request, and between the launches a long streaming
+ * pass is cut into (done / total in work items of the current launch sequence; a 10^6-row pass reports ~30 times).  tdna_cancel may
+ * be called from any thread, or from inside the callback (DelayCallback.delay throwing DelayAbortedException): the call in flight
+ * returns TDNA_E_CANCELLED at its next band / segment boundary and the alignment stays usable.  A pass shared by a communicator is
+ * enqueued whole: there a cancel takes effect at the next call. */
 typedef void (*tdna_progress_fn)(int64_t done, int64_t total, void *user);
 int32_t tdna_set_progress(tdna_ctx *ctx, tdna_progress_fn fn, void *user);
 int32_t tdna_cancel(tdna_ctx *ctx);

@@ -72,6 +72,7 @@ struct tdna_ctx {
     int opt_tile_cn = 0;  // 0 = automatic
     int opt_count_kernel = TDNA_KERNEL_AUTO;
     uint32_t opt_hist_slots = 1u << 18;
+    int64_t opt_segment_items = 0;  // 0 = automatic (segments of ~30 ms)
 };
 
 struct tdna_aln {
@@ -236,11 +237,22 @@ int pack(tdna_aln *a) {
     return TDNA_OK;
 }
 
-// c_sp for the next launch: the seed pass (diagonal blocks) only tightens thresholds and wants Best Match only
-int set_stream_symbol(tdna_aln *a, bool seed) {
+// The StreamParams of the next launch (a __grid_constant__ kernel parameter: nothing is shared between alignments or contexts on one
+// device).  The seed pass (diagonal blocks) only tightens thresholds and wants Best Match only.
+static StreamParams pass_params(const tdna_aln *a, bool seed) {
     StreamParams sp = a->sp;
     if (seed) sp.want = TDNA_WANT_BEST_MATCH | TDNA_WANT_SEED;
-    CU(cudaMemcpyToSymbolAsync(c_sp, &sp, sizeof(StreamParams), 0, cudaMemcpyHostToDevice, a->ctx->stream));
+    return sp;
+}
+// A long tile pass goes out in SEGMENTS of its work list (tens of milliseconds each).  Between segments of a single-GPU pass the
+// host waits for the segment, honours tdna_cancel and reports progress (DelayCallback.delay, Common/DelayCallback.java:34-56) --
+// a 10^6-row pass takes a second.  Passes shared by a communicator are enqueued whole (a cancel there is honoured between passes:
+// every rank would have to take the same decision at the same segment).
+static int segment_boundary(tdna_ctx *c, int64_t done, int64_t total) {
+    if (c->comm.active()) return TDNA_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->cancel) { c->cancel = 0; return fail(TDNA_E_CANCELLED, "cancelled"); }
+    if (c->progress) c->progress(done, total, c->progress_user);
     return TDNA_OK;
 }
 int ensure_tc(tdna_aln *a);
@@ -248,7 +260,7 @@ static int ensure_class_reach(tdna_aln *a);
 static int ensure_class_prefix(tdna_aln *a);
 template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts);
 
-template <int KM, int CN, int EPI> int launch_kernel(tdna_ctx *c, const TileParams &p) {
+template <int KM, int CN, int EPI> int launch_kernel(tdna_ctx *c, const TileParams &p, const StreamParams &sp = StreamParams()) {
     using Cfg = TileCfg<KM, CN>;
     auto kern = count_tile_kernel<KM, CN, EPI>;
     static bool attr_set[64] = {};  // per device: function attributes live in the device's context (one process may drive several)
@@ -259,7 +271,7 @@ template <int KM, int CN, int EPI> int launch_kernel(tdna_ctx *c, const TilePara
     int64_t slots = (int64_t)c->sm_count * Cfg::MIN_CTAS;
     int64_t grid = p.num_tiles < slots ? p.num_tiles : slots;
     if (grid < 1) return TDNA_OK;
-    kern<<<(unsigned)grid, TILE_THREADS, Cfg::SMEM, c->stream>>>(p);
+    kern<<<(unsigned)grid, TILE_THREADS, Cfg::SMEM, c->stream>>>(p, sp);
     c->launches++;
     CU(cudaGetLastError());
     return TDNA_OK;
@@ -378,7 +390,7 @@ template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts,
     if (phases & 1) CU(cudaEventRecord(c->ev_k0, c->stream));
     for (int ph = 0; ph < 2; ph++) {
         if (!(phases & (1 << ph))) continue;
-        TRY(set_stream_symbol(a, ph == 0));
+        const StreamParams sp = pass_params(a, ph == 0);
         TileParams p = {};
         p.planes = a->d_planes;
         p.W = a->W;
@@ -395,12 +407,17 @@ template <int KM, int CN> int launch_stream_t(tdna_aln *a, int part, int nparts,
         // part k of m: a CONTIGUOUS 1/m of the tile list (all tiles cost the same; neighbours in the list share panels in L2)
         int64_t total = a->sprefix_tiles[ph];
         int64_t t0 = total * part / nparts, t1 = total * (part + 1) / nparts;
-        p.t_offset = t0;
         p.t_stride = 1;
-        p.num_tiles = t1 - t0;
         if (ph == 1) CU(cudaEventRecord(c->ev_b0, c->stream));
-        if (ph == 0 || a->sp.want == TDNA_WANT_BEST_MATCH) TRY((launch_kernel<KM, CN, EPI_STREAM>(c, p)));
-        else TRY((launch_kernel<KM, CN, EPI_STREAM_X>(c, p)));
+        // segments of ~30 ms (a 128 x 64 tile of 658 columns takes ~0.1 us of the whole GPU): see segment_boundary
+        const int64_t seg = c->opt_segment_items > 0 ? c->opt_segment_items : std::max<int64_t>(1 << 12, ((int64_t)1 << 18) * 21 / std::max(a->W, 1));
+        for (int64_t s0 = t0; s0 < t1; s0 += seg) {
+            p.t_offset = s0;
+            p.num_tiles = std::min(seg, t1 - s0);
+            if (ph == 0 || a->sp.want == TDNA_WANT_BEST_MATCH) TRY((launch_kernel<KM, CN, EPI_STREAM>(c, p, sp)));
+            else TRY((launch_kernel<KM, CN, EPI_STREAM_X>(c, p, sp)));
+            if (s0 + seg < t1) TRY(segment_boundary(c, s0 + seg - t0, t1 - t0));
+        }
         if (ph == 0) CU(cudaEventRecord(c->ev_s1, c->stream));
     }
     if (phases & 2) {
@@ -433,7 +450,6 @@ static int launch_stream_popc(tdna_aln *a, int part, int nparts, int phases) {
 // kernel (b) after its bulk launch(es): the queued pairs -> minima -> final thresholds -> candidate records
 static int tc_resolve_queue(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
-    TRY(set_stream_symbol(a, false));
     int wshift = 0;
     while ((1u << wshift) < a->tc_W) wshift++;
     unsigned grid = (unsigned)c->sm_count * 8;
@@ -477,15 +493,12 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
                     // machinery switched on (a class request in the same launch cost every tile of 10^6 rows a third of its time), the
                     // classes' launch visits only the near-diagonal tiles that can hold a class pair (computed twice: a few per mille)
                     a->sp.want = row_bits;
-                    int rc = set_stream_symbol(a, false);
-                    if (rc == TDNA_OK) rc = launch_tc<false>(a, ph, part, nparts, nullptr);
+                    int rc = launch_tc<false>(a, ph, part, nparts, nullptr);
                     a->sp.want = class_bits;
-                    if (rc == TDNA_OK) rc = set_stream_symbol(a, false);
                     if (rc == TDNA_OK) rc = launch_tc<false>(a, ph, part, nparts, nullptr);
                     a->sp.want = want;
                     TRY(rc);
                 } else {
-                    TRY(set_stream_symbol(a, ph == 0));
                     TRY(launch_tc<false>(a, ph, part, nparts, nullptr));
                 }
                 if (ph == 0) CU(cudaEventRecord(c->ev_s1, c->stream));
@@ -887,23 +900,32 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.b_rows = tc::B_STAGE / (a->tc_inner * 4);
     int64_t units = CL >= 2 ? c->sm_count / 2 : c->sm_count;
     if (const char *e = exp_env("TDNA_TC_GRID")) { int v = atoi(e); if (v >= 1 && v < units) units = v; }
-    int64_t grid = (p.num_tiles < units ? p.num_tiles : units) * (CL >= 2 ? 2 : 1);
-    if (grid < 1) return TDNA_OK;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(tc::THREADS);
-    cfg.dynamicSmemBytes = tc::SMEM;
-    cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL >= 2 ? 2 : 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, kern, a->tc_mapA, a->tc_mapB, a->tc_mapBh, p));
-    c->launches++;
-    CU(cudaGetLastError());
+    const StreamParams sp = pass_params(a, !COUNTS_MODE && phase == 0);
+    // segments of ~30 ms (an item of two 128 x 256 tiles of 658 columns takes ~0.13 us of the whole GPU): see segment_boundary
+    const int64_t items = p.num_tiles;
+    const int64_t seg = (COUNTS_MODE || phase == 0) ? items : c->opt_segment_items > 0 ? c->opt_segment_items : std::max<int64_t>(units * 64, ((int64_t)1 << 18) * 26 / std::max(p.nchunks, 1) * (CL >= 2 ? 1 : 2));
+    for (int64_t k0 = 0; k0 < items; k0 += seg) {
+        p.k_base = k0;
+        p.num_tiles = std::min(seg, items - k0);
+        int64_t grid = (p.num_tiles < units ? p.num_tiles : units) * (CL >= 2 ? 2 : 1);
+        if (grid < 1) break;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(tc::THREADS);
+        cfg.dynamicSmemBytes = tc::SMEM;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL >= 2 ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, kern, a->tc_mapA, a->tc_mapB, a->tc_mapBh, p, sp));
+        c->launches++;
+        CU(cudaGetLastError());
+        if (k0 + seg < items) TRY(segment_boundary(c, k0 + seg, items));
+    }
     return TDNA_OK;
 }
 
@@ -2775,6 +2797,10 @@ int32_t tdna_set_option(tdna_ctx *c, int32_t key, int64_t value) {
             if (value < 0 || value > 2) return fail(TDNA_E_ARG, "TDNA_OPT_MULTI is 0, 1 or 2");
             c->comm.enabled = value != 0;
             c->comm.force = value == 2;
+            return TDNA_OK;
+        case TDNA_OPT_SEGMENT_ITEMS:
+            if (value < 0) return fail(TDNA_E_ARG, "segment items: 0 (automatic) or a positive count");
+            c->opt_segment_items = value;
             return TDNA_OK;
     }
     return fail(TDNA_E_ARG, "unknown option");

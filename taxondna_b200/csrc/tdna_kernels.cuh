@@ -164,7 +164,8 @@ struct StreamParams {
     unsigned long long *qn;
     long long qcap;
 };
-__constant__ StreamParams c_sp;
+// (the streaming passes take their StreamParams as a __grid_constant__ kernel parameter: it sits in the launch's own constant bank,
+// so two alignments / contexts on one device never share state)
 
 enum { SCHED_RECT = 0, SCHED_SYMMETRIC = 1, SCHED_STREAM = 2 };
 enum { EPI_MATRIX = 0, EPI_MATRIX_COUNTS = 1, EPI_STREAM = 2 /* Best-Match candidates only */, EPI_STREAM_X = 3 /* + classes / edges */ };
@@ -271,8 +272,7 @@ __device__ __forceinline__ void matrix_epilogue(const TileParams &p, uint32_t (&
 #define TDNA_WANT_SEED 0x100  // internal: the diagonal-block pass only tightens the per-row minima / thresholds, it emits nothing
 #define TDNA_INF_BITS 0x7ff0000000000000ull
 
-__device__ __forceinline__ void stream_emit_side(int q, int o, double d, uint32_t lhs, uint32_t den) {
-    const StreamParams &sp = c_sp;
+__device__ __forceinline__ void stream_emit_side(const StreamParams &sp, int q, int o, double d, uint32_t lhs, uint32_t den) {
     if (!(sp.want & TDNA_WANT_BEST_MATCH)) return;
     const uint32_t fresh = *reinterpret_cast<volatile uint32_t *>(sp.thr + q);  // other CTAs tighten it all the time
     if (lhs > fresh * den) return;
@@ -299,29 +299,28 @@ __device__ __forceinline__ void stream_emit_side(int q, int o, double d, uint32_
     }
 }
 
-template <int KM> __device__ __noinline__ void stream_emit(int i, int j, uint32_t a0, uint32_t a1, uint32_t lhs, uint32_t den, int min_overlap) {
+template <int KM> __device__ __noinline__ void stream_emit(const StreamParams &sp, int i, int j, uint32_t a0, uint32_t a1, uint32_t lhs, uint32_t den, int min_overlap) {
     Counts cn = unpack_counts<KM>(a0, a1);
     const double d = distance_from_counts<KM>(cn, min_overlap);
-    if ((c_sp.want & TDNA_WANT_EDGES) && d >= 0 && d <= c_sp.edge_t) {  // Cluster.java:797-804 (NaN fails both tests)
-        const unsigned long long pos = atomicAdd(c_sp.nedge, 1ull);
-        if (c_sp.ei && (long long)pos < c_sp.edge_cap) { c_sp.ei[pos] = i; c_sp.ej[pos] = j; c_sp.ed[pos] = d; }
+    if ((sp.want & TDNA_WANT_EDGES) && d >= 0 && d <= sp.edge_t) {  // Cluster.java:797-804 (NaN fails both tests)
+        const unsigned long long pos = atomicAdd(sp.nedge, 1ull);
+        if (sp.ei && (long long)pos < sp.edge_cap) { sp.ei[pos] = i; sp.ej[pos] = j; sp.ed[pos] = d; }
     }
     if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) {  // NaN / +Inf: the host resolves these rows from tdna_row_distances
-        if (c_sp.want & TDNA_WANT_SEED) return;
-        atomicOr(c_sp.flags + i, TDNA_ROW_NONFINITE);
-        atomicOr(c_sp.flags + j, TDNA_ROW_NONFINITE);
+        if (sp.want & TDNA_WANT_SEED) return;
+        atomicOr(sp.flags + i, TDNA_ROW_NONFINITE);
+        atomicOr(sp.flags + j, TDNA_ROW_NONFINITE);
         return;
     }
-    stream_emit_side(i, j, d, lhs, den);
-    stream_emit_side(j, i, d, lhs, den);
+    stream_emit_side(sp, i, j, d, lhs, den);
+    stream_emit_side(sp, j, i, d, lhs, den);
 }
 
 // The same slow path for callers that enter it CONVERGED (every lane of the warp brings one pair, `active` lanes
 // have one): both sides of the pair are handled together and independent memory operations are issued back to back,
 // so a warp pays ~3 memory latencies per batch of up to 32 candidates instead of ~6 per candidate.
-template <int KM> __device__ __forceinline__ void stream_emit_converged(bool active, int i, int j, uint32_t a0, uint32_t a1, uint32_t lhs, uint32_t den,
+template <int KM> __device__ __forceinline__ void stream_emit_converged(const StreamParams &sp, bool active, int i, int j, uint32_t a0, uint32_t a1, uint32_t lhs, uint32_t den,
                                                                       int min_overlap) {
-    const StreamParams &sp = c_sp;
     const bool seed = (sp.want & TDNA_WANT_SEED) != 0, want_bm = (sp.want & TDNA_WANT_BEST_MATCH) != 0;
     double d = 0.0;
     uint32_t fri = 0, frj = 0;
@@ -469,8 +468,7 @@ __device__ __forceinline__ void class_push(const StreamParams &sp, int k, double
 }
 
 // PairwiseDistribution classes of one valid pair i < j (PairwiseDistribution.java:161-203): pushes (float)d
-template <int KM> __device__ __noinline__ void class_emit(int i, int j, uint32_t a0, uint32_t a1, int min_overlap) {
-    const StreamParams &sp = c_sp;
+template <int KM> __device__ __noinline__ void class_emit(const StreamParams &sp, int i, int j, uint32_t a0, uint32_t a1, int min_overlap) {
     int times[2] = {0, 0};
     if (sp.want & TDNA_WANT_INTRA) {  // _addIntra: conspecific, both named; once per pair, twice when the full names are equal (:172)
         const int si = sp.species[i];
@@ -488,9 +486,8 @@ template <int KM> __device__ __noinline__ void class_emit(int i, int j, uint32_t
 }
 
 template <int KM, int CN, bool EXTRAS>
-__device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&acc)[ModeTraits<KM>::NACC][8][CN], int ti, int tj, int tx, int ty) {
+__device__ __forceinline__ void stream_epilogue(const TileParams &p, const StreamParams &sp, uint32_t (&acc)[ModeTraits<KM>::NACC][8][CN], int ti, int tj, int tx, int ty) {
     constexpr int NACC = ModeTraits<KM>::NACC, TN = 16 * CN;
-    const StreamParams &sp = c_sp;
     const int n = (int)p.n;
     const int i0 = ti * TM + ty * 8, j0 = tj * TN;
     uint32_t tfi[8], tfj[CN];
@@ -547,7 +544,7 @@ __device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&
             const uint32_t lhs = mism << 16;
             bool pass = lhs <= tfi[r] * den || lhs <= tfj[e] * den || force;
             if constexpr (EXTRAS) pass |= lhs <= edge_tf * den;
-            if (pass) stream_emit<KM>(i, j, a0, a1, lhs, den, p.min_overlap);
+            if (pass) stream_emit<KM>(sp, i, j, a0, a1, lhs, den, p.min_overlap);
         }
     }
     if (EXTRAS && (sp.want & (TDNA_WANT_INTRA | TDNA_WANT_INTER))) {
@@ -575,7 +572,7 @@ __device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&
                     if (!hit) continue;
                     uint32_t a1 = 0;
                     if constexpr (NACC == 2) a1 = acc[1][r][e];
-                    class_emit<KM>(i, j, a0, a1, p.min_overlap);
+                    class_emit<KM>(sp, i, j, a0, a1, p.min_overlap);
                 }
             }
         }
@@ -598,7 +595,7 @@ __device__ __forceinline__ void stream_epilogue(const TileParams &p, uint32_t (&
 }
 
 template <int KM, int CN, int EPI>
-__global__ void __launch_bounds__(TILE_THREADS, TileCfg<KM, CN>::MIN_CTAS) count_tile_kernel(TileParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, TileCfg<KM, CN>::MIN_CTAS) count_tile_kernel(const __grid_constant__ TileParams p, const __grid_constant__ StreamParams sp) {
     using Cfg = TileCfg<KM, CN>;
     constexpr int P = Cfg::P, NACC = Cfg::NACC, TN = Cfg::TN;
     extern __shared__ __align__(128) uint32_t smem[];
@@ -704,7 +701,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TileCfg<KM, CN>::MIN_CTAS) count
             const int64_t t = blockIdx.x + (it / nchunks) * gridDim.x;
             int ti, tj;
             tile_coords<TN>(p, prefix, t, ti, tj);
-            if constexpr (EPI == EPI_STREAM || EPI == EPI_STREAM_X) stream_epilogue<KM, CN, EPI == EPI_STREAM_X>(p, acc, ti, tj, tx, ty);
+            if constexpr (EPI == EPI_STREAM || EPI == EPI_STREAM_X) stream_epilogue<KM, CN, EPI == EPI_STREAM_X>(p, sp, acc, ti, tj, tx, ty);
             else matrix_epilogue<KM, CN, EPI == EPI_MATRIX_COUNTS>(p, acc, ti, tj, tx, ty);
         }
     }

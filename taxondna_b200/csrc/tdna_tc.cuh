@@ -35,7 +35,7 @@ constexpr int EPI_COLS = N / (EPI_WARPS / 4);      // columns per epilogue warp
 constexpr int THREADS = 64 + EPI_WARPS * 32;       // warp 0 producer, warp 1 MMA issuer, warps 2.. epilogue
 constexpr int MAX_DIMS = 5;                        // K-dimensions per site: 5 (p: A C G T -) or 4 (K2P: A C G T)
 constexpr int WTAB = 64;                           // slots of an epilogue warp's private class-histogram table (tdna_kernels.cuh: shist_add)
-constexpr size_t SMEM = (size_t)NSTAGE * STAGE + 256 /*barriers*/ + 16 * 64 * 4 /*column thresholds, per epilogue warp*/ +
+constexpr size_t SMEM = (size_t)NSTAGE * STAGE + 256 /*barriers*/ + 2 * 16 * 64 * 4 /*column thresholds + raw bounds, per epilogue warp*/ +
                         (size_t)EPI_WARPS * WTAB * 12 /*class-histogram tables*/ + 1024 /*alignment*/;
 
 struct Params {
@@ -52,9 +52,10 @@ struct Params {
     int nbands;
     const int64_t *prefix;  // bulk phase: [nbands + 1] tile slots before band b
     int64_t num_tiles, t_offset, t_stride;  // this launch's k-th work item is global item ((k / unit) * t_stride + t_offset) * unit + k % unit
+    int64_t k_base;         // first work item of this launch in the part's own list (a long pass goes out in segments)
     int unit;               // work items per scheduling unit (parts take units cyclically: balanced in work AND in candidates)
     tdna_counts *counts;    // verification mode: n x n counts (row-major), else null
-    int extras;             // stream mode: classes / edges wanted (c_sp.want beyond Best Match)
+    int extras;             // stream mode: classes / edges wanted (StreamParams::want beyond Best Match)
     const uint8_t *panel_full;  // [128-row panel] 1 = every row of the panel is valid at every site: pairs of two such panels share L sites
     int L;
     int k2p;                // the accumulator carries (n, ts + tv) of the K2P model; exact counts come from the bit-planes
@@ -147,11 +148,11 @@ __device__ __forceinline__ bool may_hold_class_pairs(const Params &p, int ti, in
 }
 template <int CL> __device__ __forceinline__ bool my_tile(const Params &p, int64_t k, uint32_t rank, int &ti, int &tj) {
     if constexpr (CL == 1) {
-        const int64_t l = (int64_t)blockIdx.x + k * gridDim.x;
+        const int64_t l = p.k_base + (int64_t)blockIdx.x + k * gridDim.x;
         if (!slot_coords(p, p.prefix, ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit, ti, tj)) return false;
         return !p.class_only || ((int64_t)tj * N <= (int64_t)ti * M + (M - 1) + p.class_reach && may_hold_class_pairs(p, ti, tj, M));
     } else {
-        const int64_t l = (int64_t)(blockIdx.x >> 1) + k * (gridDim.x >> 1);
+        const int64_t l = p.k_base + (int64_t)(blockIdx.x >> 1) + k * (gridDim.x >> 1);
         const int64_t u = ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit;
         bool ok = slot_coords(p, p.prefix, 2 * u, ti, tj);
         if (ok && p.class_only) ok = (int64_t)tj * N <= (int64_t)ti * M + (2 * M - 1) + p.class_reach && may_hold_class_pairs(p, ti, tj, 2 * M);  // the same answer in both CTAs of the pair
@@ -298,20 +299,26 @@ __global__ void __launch_bounds__(256) amb_count_kernel(const uint8_t *__restric
     const int64_t row = row0 + (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n) return;
     const int lane = threadIdx.x & 31, row_len = min(len[row], L);
-    int cnt = 0, gaps = 0;
+    int cnt = 0, gaps = 0, oh = 0;  // oh: sites the operands DO express (one unambiguous base; '-' where it is a symbol of its own)
     for (int site = lane; site < row_len; site += 32) {
         const uint32_t cls = c_symlut[sym[row * sym_stride + site]];
-        if ((cls & SB_LET) && __popc(cls & 15u) != 1) cnt++;
-        if (gaps_dropped && (cls & SB_D)) gaps++;
+        if (cls & SB_LET) { if (__popc(cls & 15u) != 1) cnt++; else oh++; }
+        if (cls & SB_D) { if (gaps_dropped) gaps++; else if (!k2p) oh++; }
     }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, m); gaps += __shfl_xor_sync(0xffffffffu, gaps, m); }
+    for (int m = 16; m >= 1; m >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, m);
+        gaps += __shfl_xor_sync(0xffffffffu, gaps, m);
+        oh += __shfl_xor_sync(0xffffffffu, oh, m);
+    }
     if (lane == 0) {
-        amb[row] = cnt + gaps;
+        amb[row] = (cnt + gaps) | (oh << 12);  // both below 4096 (L < 4096): AMB_MASK / AMB_SHIFT
         if (cnt + gaps) { panel_amb[row / M] = 1; *any = 1; }
         if (gaps) atomicAdd(any + 1, gaps);
     }
 }
+constexpr uint32_t AMB_MASK = 0xfffu;
+constexpr int AMB_SHIFT = 12;
 
 // per tile panel (`per` consecutive 64-row panels): the union of the 64-row panels' (min, max) species / genus id ranges
 __global__ void __launch_bounds__(256) tile_range_kernel(const int4 *__restrict__ panel_range, int64_t panels64, int per, int4 *__restrict__ out, int64_t nout) {
@@ -442,7 +449,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 // ambiguity-letter machinery is compiled in (it cost the hot loop 4 % through register pressure alone).
 template <bool COUNTS_MODE, int CL, bool GENERAL>
 __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                                                          const __grid_constant__ CUtensorMap mapBh, Params p) {
+                                                          const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ Params p,
+                                                          const __grid_constant__ StreamParams sp) {
     // CL = 3: the pair runs ONE M = 256 MMA (cta_group::2): each CTA stages its own a-panel and its 128-row HALF of the
     // b-panel, i.e. 32 KB per stage instead of 48 KB -> a six-deep ring, and half the b-operand shared-memory reads
     constexpr bool PAIR = CL == 3;
@@ -455,7 +463,8 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
     uint64_t *tempty = tfull + 2;       // [2] accumulator stage drained
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     uint32_t *col_thr = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * STAGE + 256);  // [EPI_WARPS][EPI_COLS]
-    unsigned long long *wtab_keys = reinterpret_cast<unsigned long long *>(col_thr + EPI_WARPS * EPI_COLS);  // [EPI_WARPS][WTAB]
+    uint32_t *col_raw = col_thr + EPI_WARPS * EPI_COLS;  // [EPI_WARPS][EPI_COLS] tiles with ambiguity letters: the columns' bounds in accumulator units
+    unsigned long long *wtab_keys = reinterpret_cast<unsigned long long *>(col_raw + EPI_WARPS * EPI_COLS);  // [EPI_WARPS][WTAB]
     unsigned int *wtab_cnts = reinterpret_cast<unsigned int *>(wtab_keys + EPI_WARPS * WTAB);                // [EPI_WARPS][WTAB]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -569,12 +578,12 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
         // by warps; the flags of 32 pairs are computed branch-free (~9 instructions per pair) before the rare slow path.
         const int q = warp & 3, g = (warp - 2) >> 2;
         uint32_t *my_thr = col_thr + (warp - 2) * EPI_COLS;  // this warp's column thresholds (warp-private: no CTA barrier)
+        uint32_t *my_raw = col_raw + (warp - 2) * EPI_COLS;
         unsigned long long *my_keys = wtab_keys + (warp - 2) * WTAB;
         unsigned int *my_cnts = wtab_cnts + (warp - 2) * WTAB;
         for (int s = lane; s < WTAB; s += 32) { my_keys[s] = TDNA_HIST_EMPTY; my_cnts[s] = 0; }
         __syncwarp();
         bool wtab_used = false;
-        const StreamParams &sp = c_sp;
         const uint32_t wm1 = p.W - 1u;
         int64_t k = 0;
         for (int64_t kk = 0; kk < my_tiles; kk++, k++) {
@@ -600,8 +609,11 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                               p.panel_full[2 * tj + 1] && (int64_t)ti * M + M <= p.n;
             // some row or column of the tile has ambiguity letters: the accumulators bound the counts (see Params::amb)
             const bool tile_amb = GENERAL && !COUNTS_MODE && p.amb != nullptr && (p.panel_amb[ti] || p.panel_amb[2 * tj] || p.panel_amb[2 * tj + 1]);
-            const uint32_t amb_i = (GENERAL && !COUNTS_MODE && p.amb != nullptr && i < p.n) ? (uint32_t)__ldg(p.amb + i) : 0u;
+            const uint32_t ambw_i = (GENERAL && !COUNTS_MODE && p.amb != nullptr && i < p.n) ? (uint32_t)__ldg(p.amb + i) : 0u;
+            const uint32_t amb_i = ambw_i & AMB_MASK, oh_i = ambw_i >> AMB_SHIFT;  // ambiguity letters / expressible sites of this row
+            const uint32_t amb_rmax = GENERAL ? __reduce_max_sync(0xffffffffu, amb_i) : 0u;
             uint32_t tf_row = edge_tf;
+            uint32_t amb_cmax = 0;  // most ambiguity letters of any of this warp's columns
             if constexpr (!COUNTS_MODE) {
                 __syncwarp();  // the previous tile's reads of my_thr are done
 #pragma unroll
@@ -610,7 +622,17 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     if (seed) my_thr[x * 32 + lane] = (uint32_t)(j < p.n ? __ldg(sp.species + j) : -1);  // seed pass: the columns' species ids
                     else {
                         const uint32_t t = (want_bm && j < p.n) ? __ldcg(sp.thr + j) : 0u;  // <= 2^16
-                        if (tile_amb) my_thr[x * 32 + lane] = t | ((j < p.n ? (uint32_t)__ldg(p.amb + j) : 0u) << 20);  // amb[j] < 4096
+                        if (tile_amb) {
+                            const uint32_t ajw = j < p.n ? (uint32_t)__ldg(p.amb + j) : 0u, aj = ajw & AMB_MASK;
+                            my_thr[x * 32 + lane] = t | (aj << 20);  // amb[j] < 4096
+                            // the pre-test of interior tiles (below): no pair of column j passes its column's threshold with more than
+                            // (thr * S) >> 16 mismatches, S = oh[j] + amb[j] + max amb[i] >= shared' + amb[i] + amb[j] (the sites both rows
+                            // express are among those column j expresses) -- stated on the raw accumulator
+                            if constexpr (GENERAL) {
+                                my_raw[x * 32 + lane] = ((uint32_t)(((unsigned long long)t * ((ajw >> AMB_SHIFT) + aj + amb_rmax)) >> 16) + 1u) << p.wshift;
+                                amb_cmax = max(amb_cmax, aj);
+                            }
+                        }
                         else if (!full) my_thr[x * 32 + lane] = t;
                         else {
                             // shared == L everywhere: mism << 16 <= thr * L  <=>  mism <= (thr * L) >> 16 =: b.  The plain instantiation
@@ -626,6 +648,10 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             }
             const uint32_t brow = (uint32_t)(((unsigned long long)tf_row * (uint32_t)p.L) >> 16);
             const uint32_t brow_raw = (brow + 1u) << p.wshift;  // (b <= L < W: no overflow)
+            // tiles with ambiguity letters: the same bound with L + amb[i] sites, and what K2P's forced pairs need (see the pre-test)
+            if constexpr (GENERAL) amb_cmax = __reduce_max_sync(0xffffffffu, amb_cmax);
+            const uint32_t brow_raw_amb = ((uint32_t)(((unsigned long long)tf_row * (oh_i + amb_i + amb_cmax)) >> 16) + 1u) << p.wshift;
+            const uint32_t force_x2 = 2u * (amb_i + amb_cmax);
             const uint32_t half_l = k2p_force ? ((uint32_t)p.L + 1u) >> 1 : 0xffffffffu;  // 2 * mism >= L
             mbar_wait(&tfull[as], (uint32_t)((k >> 1) & 1));
             fence_after();
@@ -680,7 +706,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                             continue;
                         }
                         // ambiguity letters: an UPPER bound of the distance is all a threshold needs (0 extra sites: the exact value)
-                        const uint32_t aij = (GENERAL && p.amb != nullptr) ? amb_i + (uint32_t)__ldg(p.amb + j) : 0u;
+                        const uint32_t aij = (GENERAL && p.amb != nullptr) ? amb_i + ((uint32_t)__ldg(p.amb + j) & AMB_MASK) : 0u;
                         double d;
                         if (GENERAL && p.k2p) {
                             // only n and ts + tv are known here: d_K2P <= -ln(1 - 2(P+Q)) / 2 (all differences transitions) bounds the
@@ -715,21 +741,59 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         return r;
                     };
                     if (tile_amb) {
+                        // the exact statement of the test for one pair: shared' <= shared <= sb, mism' <= mism
+                        auto amb_pair = [&](int e, uint32_t ct) {
+                            const int j = jb + e;
+                            const uint32_t thr_j = ct & 0xfffffu, extra = amb_i + (ct >> 20);
+                            const uint32_t mism = v[e] >> p.wshift, s = v[e] - mism * wm1, sb = s + extra;
+                            const bool inr = (j > i) & (j < p.n);
+                            const bool sure = (int)s >= p.min_overlap, maybe = (int)sb >= p.min_overlap;
+                            const bool pass = ((mism << 16) <= max(tf_row, thr_j) * sb) | (k2p_force & (2u * (mism + extra) >= s));
+                            if (inr && maybe && (pass || !sure)) pmask |= 1u << e;  // an uncertain overlap is settled by the exact counts
+                            if (inr && !maybe) bmask |= 1u << e;
+                            if (j == i && i < p.n && (int)(s + amb_i) >= p.min_overlap) smask |= 1u << e;  // a row shares all its letters with itself
+                        };
+                        if (GENERAL && interior) {
+                            // Interior tiles (every pair real, no self pair): a PRE-TEST on the raw accumulator D = ident' + W * mism' first --
+                            // five instructions per pair instead of twenty-seven.  A pair can only matter to the exact test when
+                            //   D < max(row bound, column bound)       (it may pass a threshold: see the column staging above), or
+                            //   ident' < minOverlap                     (its overlap may be short or uncertain: shared' >= ident'), or
+                            //   K2P: shared' < minOverlap, or 2 mism' + 2 (amb[i] + max amb[j]) >= shared'   (a forced pair),
+                            // and only the columns some lane flags go through the exact test (a warp-uniform branch per column).
+                            uint32_t m1 = 0;
+                            const uint32_t cr_addr = smem_u32(my_raw + cbi * 32), mo_u = (uint32_t)max(p.min_overlap, 0);
 #pragma unroll
-                        for (int e4 = 0; e4 < 8; e4++) {
-                            const uint4 ct = lds4(ct_addr + e4 * 16);
-                            const uint32_t cts[4] = {ct.x, ct.y, ct.z, ct.w};
+                            for (int e4 = 0; e4 < 8; e4++) {
+                                const uint4 cr = lds4(cr_addr + e4 * 16);
+                                const uint32_t crs[4] = {cr.x, cr.y, cr.z, cr.w};
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const int e = e4 * 4 + u, j = jb + e;
-                                const uint32_t thr_j = cts[u] & 0xfffffu, extra = amb_i + (cts[u] >> 20);
-                                const uint32_t mism = v[e] >> p.wshift, s = v[e] - mism * wm1, sb = s + extra;  // shared' <= shared <= sb
-                                const bool inr = (j > i) & (j < p.n);
-                                const bool sure = (int)s >= p.min_overlap, maybe = (int)sb >= p.min_overlap;
-                                const bool pass = ((mism << 16) <= max(tf_row, thr_j) * sb) | (k2p_force & (2u * (mism + extra) >= s));
-                                if (inr && maybe && (pass || !sure)) pmask |= 1u << e;  // an uncertain overlap is settled by the exact counts
-                                if (inr && !maybe) bmask |= 1u << e;
-                                if (j == i && i < p.n && (int)(s + amb_i) >= p.min_overlap) smask |= 1u << e;  // a row shares all its letters with itself
+                                for (int u = 0; u < 4; u++) {
+                                    const int e = e4 * 4 + u;
+                                    bool hit = v[e] < max(brow_raw_amb, crs[u]);
+                                    if (k2p_force) {
+                                        const uint32_t mism = v[e] >> p.wshift, s = v[e] - mism * wm1;
+                                        hit |= (s < mo_u) | (2u * mism + force_x2 >= s);
+                                    } else hit |= (v[e] & wm1) < mo_u;
+                                    if (hit) m1 |= 1u << e;
+                                }
+                            }
+                            const uint32_t uni = __reduce_or_sync(0xffffffffu, m1);
+                            if (uni) {
+#pragma unroll
+                                for (int e = 0; e < 32; e++)
+                                    if (uni & (1u << e)) {
+                                        uint32_t ct;
+                                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ct) : "r"(ct_addr + e * 4));
+                                        amb_pair(e, ct);
+                                    }
+                            }
+                        } else {
+#pragma unroll
+                            for (int e4 = 0; e4 < 8; e4++) {
+                                const uint4 ct = lds4(ct_addr + e4 * 16);
+                                const uint32_t cts[4] = {ct.x, ct.y, ct.z, ct.w};
+#pragma unroll
+                                for (int u = 0; u < 4; u++) amb_pair(e4 * 4 + u, cts[u]);
                             }
                         }
                     } else if (full) {
@@ -803,7 +867,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                             const bool hit = ((sp.want & TDNA_WANT_INTRA) && spi_ == sp.species[j]) || ((sp.want & TDNA_WANT_INTER) && gi_ == sp.genus[j]);
                             if (!hit) continue;
                             const uint32_t mism = v[e] >> p.wshift, s = v[e] - mism * wm1;
-                            if ((int)(s + (tile_amb ? amb_i + (uint32_t)__ldg(p.amb + j) : 0u)) >= p.min_overlap) cmask |= 1u << e;
+                            if ((int)(s + (tile_amb ? amb_i + ((uint32_t)__ldg(p.amb + j) & AMB_MASK) : 0u)) >= p.min_overlap) cmask |= 1u << e;
                         }
                     }
                     pmask |= cmask;
@@ -848,7 +912,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                             if (j <= i || j >= p.n || (int)s < p.min_overlap) continue;
                             const bool hit = ((sp.want & TDNA_WANT_INTRA) && spi_ == sp.species[j]) || ((sp.want & TDNA_WANT_INTER) && gi_ == sp.genus[j]);
                             if (!hit) continue;
-                            if (!hist_mode) { class_emit<KM_P_AMBIG>(i, j, ident | (s << 16), 0u, p.min_overlap); continue; }
+                            if (!hist_mode) { class_emit<KM_P_AMBIG>(sp, i, j, ident | (s << 16), 0u, p.min_overlap); continue; }
                             // histogram mode: the pushes of this tile go through the warp's shared-memory table first
                             int t0 = 0, t1 = 0;
                             if ((sp.want & TDNA_WANT_INTRA) && spi_ >= 0 && spi_ == sp.species[j]) t0 = 1 + (sp.full[i] == sp.full[j] ? 1 : 0);
