@@ -370,6 +370,41 @@ int32_t tdna_class_histogram(tdna_aln *aln, int32_t klass, tdna_hist_entry *out,
 int32_t tdna_edges_below(tdna_aln *aln, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap,
                          int64_t *n_out);
 
+/* ---- per-row extremes among the congeners ------------------------------------------------------------------
+ * ExtremePairwise.run (SpeciesIdentifier/ExtremePairwise.java:99-170) and DistanceAnalysis.run (SpeciesIdentifier/
+ * DistanceAnalysis.java:183-230) call sortAgainst for every query and then read only the query's conspecifics and its congeneric,
+ * allospecific entries off the sorted list.  One launch evaluates, for every NAMED query row q, its pairs with the rows of the same
+ * genus id (both named) and returns what the two modules read, in the well-formed case (the comparator is
+ * consistent), plus the evidence the host layer needs to tell that it is (near_*, flags); other rows are re-resolved on the host
+ * with the exact sort, as for tdna_row_result.
+ *   conspecific: species id equal (>= 0), j != q.   congeneric, allospecific: genus id equal, species ids differ (both >= 0). */
+typedef struct {
+    double d_max_intra;  /* the LAST valid conspecific of the sorted list (ExtremePairwise.java:149-163): the largest distance; -1.0 if none */
+    double d_min_inter;  /* the FIRST valid congeneric, allospecific entry (:121-146; DistanceAnalysis.java:203-219 "closest"); -1.0 if none */
+    double sum_inter;    /* the congeneric, allospecific distances added up in sorted order (DistanceAnalysis.java:217, average()) */
+    int32_t max_intra, min_inter;       /* their rows (of equal distances: the last / the first in list order); -1 if none */
+    int32_t shared_intra, shared_inter; /* getOverlap(query, that row) (ExtremePairwise.java:178, 192) */
+    int32_t n_intra, n_inter;           /* valid named entries of each class */
+    int32_t near_intra, near_inter;     /* entries of the class with 0 < |d - d_ref| < 2e-5 */
+    int32_t near_order;                 /* neighbours in the sorted congeneric entries with 0 < difference < 2e-5 (the sum's order) */
+    int32_t flags;                      /* TDNA_ROW_SELF_VALID, TDNA_ROW_NONFINITE, TDNA_EXT_* */
+} tdna_extreme_result;                  /* 64 bytes, no padding */
+enum { TDNA_EXT_UNNAMED = 16,   /* the query has no species name: nothing else is filled in */
+       TDNA_EXT_TOO_MANY = 32  /* the query's genus has more than 4,096 rows: resolve on the host */ };
+/* out: n records, host or device.  Needs the labels. */
+int32_t tdna_row_extremes(tdna_aln *aln, tdna_extreme_result *out);
+
+/* ---- SequenceMatrix callers ------------------------------------------------------------------------------
+ * SequenceMatrix compares the sequences of MANY small per-gene alignments: FindDistances (SequenceMatrix/FindDistances.java:196-246)
+ * runs getPairwise on every (sequence of any gene, sequence of any gene) and keeps `from <= d <= to`; DisplayDistancesMode
+ * (SequenceMatrix/DisplayDistancesMode.java:255-290, minOverlap forced to 1 :163) runs it on every (taxon's sequence of a gene, the
+ * reference taxon's sequence of that gene).  Here all the genes' sequences form ONE ragged alignment (lengths[] per row: every
+ * comparison stops at the shorter sequence, Sequence.java:1417-1419), so that either caller is one call: tdna_pairs (explicit pair
+ * list) for DisplayDistancesMode, and this for FindDistances --
+ * all unordered pairs i < j with lo <= d <= hi, d exactly as Sequence.getPairwise returns it (lo <= -1 admits the pairs below
+ * minOverlap; NaN never matches), unsorted.  Two-call protocol as tdna_edges_below (ii == NULL -> count only). */
+int32_t tdna_pairs_between(tdna_aln *aln, double lo, double hi, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out);
+
 /* ---- SpeciesDetail ----------------------------------------------------- */
 /* has_valid[i] = 1 iff some OTHER row of the same species has getSharedLength >= minOverlap
  * (SpeciesDetail.getSequencesWithValidConspecificsCount, Common/DNA/SpeciesDetail.java:78-95). */

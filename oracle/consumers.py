@@ -1501,3 +1501,137 @@ def consensus_of_bin(seqs):
         cons = s if cons is None else get_consensus(cons, s)
     return cons
 
+
+
+# --------------------------------------------------------------------------
+# SequenceMatrix's two distance callers: many small per-gene alignments
+# --------------------------------------------------------------------------
+class OGrid:
+    """The (taxon, charset) -> Sequence grid the callers read through TableManager (SequenceMatrix/TableManager.java:254-371):
+    `charsets` and `taxa` in display order, cells[(charset, taxon)] = OSeq (absent = no sequence)."""
+
+    def __init__(self, charsets, taxa, cells):
+        self.charsets, self.taxa, self.cells = list(charsets), list(taxa), dict(cells)
+
+    def sequence_list_by_column(self, col):  # TableManager.getSequenceListByColumn :359-371
+        return [(t, self.cells[(col, t)]) for t in self.taxa if (col, t) in self.cells]
+
+
+def find_distances(grid, cfg, d_from, d_to, col_to_use=None, threads=1):
+    """FindDistances.displayResults (SequenceMatrix/FindDistances.java:123-289): every sequence of the chosen columns against every
+    other one, pairs with from <= getPairwise <= to kept in BOTH directions, Collections.sort by PairwiseDistance.compareTo.
+    Returns (text of text_main, [(outer row, inner row, d)] in output order); a row is an index into the (column, taxon) enumeration."""
+    cols = list(grid.charsets) if col_to_use is None else [col_to_use]  # :168-176
+    rows = [(c, t, s) for c in cols for (t, s) in grid.sequence_list_by_column(c)]
+    results = []
+    if rows:
+        D = Dist([s for (_, _, s) in rows], cfg, threads=threads)
+        for a in range(len(rows)):  # :200-244 (outer column, outer sequence, inner column, inner sequence)
+            for b in range(len(rows)):
+                if a == b:  # Sequence.equals compares the UUIDs (Sequence.java:495-503)
+                    continue
+                d = D.pairwise(a, b)
+                if d_from <= d <= d_to:  # :227 (NaN fails)
+                    results.append((a, b, d))
+
+    def cmp(p1, p2):  # PairwiseDistance.compareTo (Common/DNA/PairwiseDistance.java:58-63)
+        return _java_long_to_int(make_long(p1[2] - p2[2]))
+
+    java_sort(results, cmp)  # :249
+    buff = []
+    for (a, b, d) in results:  # :251-262: the copies were renamed "<display name> (from <column>)" (:231-235)
+        na = (rows[a][2].display_name() + " (from " + rows[a][0] + ")").replace("\n", " ").strip()
+        nb = (rows[b][2].display_name() + " (from " + rows[b][0] + ")").replace("\n", " ").strip()
+        buff.append(na + "\t" + nb + "\t" + java_double_str(percentage(d, 1)) + "%\n")
+    method = {PDM_UNCORRECTED: "uncorrected pairwise distances", PDM_K2P: "K2P distances", PDM_TRANS_ONLY: "transversions only"}.get(cfg.mode, "(unknown)")
+    text = (str(len(results)) + " sequence pairs found with distances between " + java_double_str(percentage(d_from, 1)) + "% and " +
+            java_double_str(percentage(d_to, 1)) + "%.\nNote that distances were calculated using " + method +
+            " and sequence overlaps of less than " + str(cfg.min_overlap) + " bp weren't counted.\n\n" + "".join(buff))
+    return text, results
+
+
+DIST_ILLEGAL, DIST_NO_COMPARE_SEQ, DIST_SEQ_NA, DIST_NO_OVERLAP, DIST_SEQ_ON_TOP, DIST_CANCELLED = -32.0, -64.0, -128.0, -256.0, -1024.0, -2048.0
+
+
+def display_distances(grid, mode, ref_taxon, selected_col, cancelled=(), threads=1):
+    """DisplayDistancesMode.getSortedSequences (SequenceMatrix/DisplayDistancesMode.java:217-398): per column, every taxon's
+    sequence against the reference taxon's (minOverlap forced to 1, :163), normalised per column, taxa sorted by their mean
+    normalised distance over the other columns, per-column ranks.
+    Returns dict(columns, taxa, distances, norm_distances, scores, ranks) with [column][taxon] tables in the sorted taxon order."""
+    cfg = Config(mode, 1, True)
+    columns = sorted(grid.charsets)  # getSortedColumns :196-213
+    if selected_col in columns:
+        columns.remove(selected_col)
+        columns.insert(0, selected_col)
+    taxa = list(grid.taxa)
+    # one Dist over all cells: a row per (column, taxon)
+    index, seqs = {}, []
+    for c in columns:
+        for t in taxa:
+            if (c, t) in grid.cells:
+                index[(c, t)] = len(seqs)
+                seqs.append(grid.cells[(c, t)])
+    D = Dist(seqs, cfg, threads=threads) if seqs else None
+    nx, ny = len(columns), len(taxa)
+    dist = [[0.0] * ny for _ in range(nx)]
+    mx, mn = [-1.0] * nx, [2.0] * nx
+    for x, c in enumerate(columns):  # pass 1 :255-290
+        for y, t in enumerate(taxa):
+            if (c, ref_taxon) not in index:
+                d = DIST_NO_COMPARE_SEQ
+            elif t == ref_taxon:
+                d = DIST_SEQ_ON_TOP
+            elif (c, t) not in index:
+                d = DIST_CANCELLED if (c, t) in cancelled else DIST_SEQ_NA
+            else:
+                d = D.pairwise(index[(c, t)], index[(c, ref_taxon)])
+                if d < 0:
+                    d = DIST_NO_OVERLAP
+            dist[x][y] = d
+            if d >= 0:
+                if d > mx[x]:
+                    mx[x] = d
+                if d < mn[x]:
+                    mn[x] = d
+    norm = [[0.0] * ny for _ in range(nx)]
+    for x in range(nx):  # pass 2 :293-300 (0/0 = NaN, x/0 = Inf as in Java)
+        for y in range(ny):
+            if dist[x][y] >= 0:
+                num, den = dist[x][y] - mn[x], mx[x] - mn[x]
+                norm[x][y] = (num / den) if den != 0 else (math.nan if num == 0 or num != num else math.copysign(math.inf, num))
+            else:
+                norm[x][y] = dist[x][y]
+    scores = []
+    for y, t in enumerate(taxa):  # pass 3 :305-326
+        total, count = 0.0, 0
+        for x, c in enumerate(columns):
+            if c == selected_col:
+                continue
+            if dist[x][y] >= 0:
+                total += norm[x][y]
+                count += 1
+        total = (total / count) if count else math.nan  # 0.0 / 0
+        scores.append((t, total))
+
+    def jlong(v):  # (long) (d * 100000): NaN -> 0, saturating
+        if v != v:
+            return 0
+        return make_long(v)
+
+    def cmp(s1, s2):  # Score.compareTo :106-127
+        if s1[0] == ref_taxon:
+            return -1
+        if s2[0] == ref_taxon:
+            return +1
+        return _java_long_to_int(jlong(s1[1]) - jlong(s2[1]))
+
+    java_sort(scores, cmp)  # :329
+    order = [taxa.index(t) for (t, _) in scores]  # sequencesList.indexOf(seqName): the first taxon of that name
+    dist2 = [[dist[x][o] for o in order] for x in range(nx)]
+    norm2 = [[norm[x][o] for o in order] for x in range(nx)]
+    ranks = [[0] * ny for _ in range(nx)]
+    for x in range(nx):  # :371-385
+        ll = sorted(v for v in dist2[x] if v >= 0)
+        for y in range(ny):
+            ranks[x][y] = ll.index(dist2[x][y]) if dist2[x][y] >= 0 else int(math.floor(dist2[x][y]))
+    return dict(columns=columns, taxa=[t for (t, _) in scores], distances=dist2, norm_distances=norm2, scores=[s for (_, s) in scores], ranks=ranks)

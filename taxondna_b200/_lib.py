@@ -33,6 +33,10 @@ class Counts(ctypes.Structure):
 
 WANT_BEST_MATCH, WANT_INTRA, WANT_INTER, WANT_EDGES, WANT_HIST_INTRA, WANT_HIST_INTER = 1, 2, 4, 8, 16, 32
 HIST_ENTRY_DTYPE = np.dtype([("d", "<f8"), ("count", "<i8")])
+EXTREME_RESULT_DTYPE = np.dtype([("d_max_intra", "<f8"), ("d_min_inter", "<f8"), ("sum_inter", "<f8"), ("max_intra", "<i4"), ("min_inter", "<i4"),
+                                 ("shared_intra", "<i4"), ("shared_inter", "<i4"), ("n_intra", "<i4"), ("n_inter", "<i4"), ("near_intra", "<i4"),
+                                 ("near_inter", "<i4"), ("near_order", "<i4"), ("flags", "<i4")])
+EXT_UNNAMED, EXT_TOO_MANY = 16, 32
 
 
 class Analysis(ctypes.Structure):
@@ -80,7 +84,7 @@ EXPORTS = [
     "tdna_abi_version", "tdna_init", "tdna_shutdown", "tdna_last_error", "tdna_stream", "tdna_set_memory_budget",
     "tdna_launch_count", "tdna_alignment_create", "tdna_alignment_destroy", "tdna_alignment_set_labels",
     "tdna_set_config", "tdna_set_row_range", "tdna_pair", "tdna_pairs", "tdna_row_distances", "tdna_query_distances", "tdna_matrix", "tdna_matrix_compute",
-    "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below",
+    "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below", "tdna_pairs_between", "tdna_row_extremes",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
     "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_rows_per_part", "tdna_tensor_code", "tdna_consensus", "tdna_fasta_parse", "tdna_fasta_destroy", "tdna_fasta_count", "tdna_fasta_width", "tdna_fasta_records", "tdna_fasta_symbols", "tdna_alignment_create_from_fasta", "tdna_best_match_part_routed", "tdna_best_match_merge_routed", "tdna_set_option", "tdna_last_tile_pass_ms",
     "tdna_tensor_dims", "tdna_last_pass_stats", "tdna_multi_phase_ms", "tdna_analyze_host", "tdna_class_histogram", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
@@ -164,6 +168,8 @@ def load():
     L.tdna_best_match_compute.argtypes = [vp, ctypes.POINTER(vp)]
     L.tdna_class_distances.argtypes = [vp, i32, vp, i64, ctypes.POINTER(i64)]
     L.tdna_edges_below.argtypes = [vp, dbl, vp, vp, vp, i64, ctypes.POINTER(i64)]
+    L.tdna_row_extremes.argtypes = [vp, vp]
+    L.tdna_pairs_between.argtypes = [vp, dbl, dbl, vp, vp, vp, i64, ctypes.POINTER(i64)]
     L.tdna_class_histogram.argtypes = [vp, i32, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.tdna_valid_conspecifics.argtypes = [vp, vp]
     L.tdna_set_progress.argtypes = [vp, PROGRESS_FN, vp]
@@ -541,6 +547,22 @@ class Alignment:
         ii, jj, dd = np.empty(k, np.int32), np.empty(k, np.int32), np.empty(k, np.float64)
         m = ctypes.c_int64()
         check(self.L.tdna_edges_below(self.h, float(t), ii.ctypes.data, jj.ctypes.data, dd.ctypes.data, n.value, ctypes.byref(m)))
+        return ii[: n.value], jj[: n.value], dd[: n.value]
+
+    def row_extremes(self):
+        """tdna_row_extremes: one record per row (EXTREME_RESULT_DTYPE)."""
+        out = np.zeros(self.n, dtype=EXTREME_RESULT_DTYPE)
+        check(self.L.tdna_row_extremes(self.h, out.ctypes.data))
+        return out
+
+    def pairs_between(self, lo, hi):
+        """All unordered pairs i < j with lo <= d <= hi (FindDistances.java:227), unsorted: (ii, jj, d)."""
+        n = ctypes.c_int64()
+        check(self.L.tdna_pairs_between(self.h, float(lo), float(hi), None, None, None, 0, ctypes.byref(n)))
+        k = max(n.value, 1)
+        ii, jj, dd = np.empty(k, np.int32), np.empty(k, np.int32), np.empty(k, np.float64)
+        m = ctypes.c_int64()
+        check(self.L.tdna_pairs_between(self.h, float(lo), float(hi), ii.ctypes.data, jj.ctypes.data, dd.ctypes.data, n.value, ctypes.byref(m)))
         return ii[: n.value], jj[: n.value], dd[: n.value]
 
     def valid_conspecifics(self):

@@ -153,6 +153,10 @@ struct tdna_aln {
     unsigned long long *d_hctr = nullptr;  // [0] table-full flag (int), [1] entries, [2] pushes (compaction counters)
     tdna_hist_entry *d_hent = nullptr;     // staging of compacted entries
     size_t hent_cap = 0;
+    // tdna_row_extremes: member lists by genus (slot of each row's genus, start of each slot, rows ascending), built from the labels
+    int32_t *d_gslot = nullptr, *d_gmem = nullptr;
+    int64_t *d_gstart = nullptr;
+    bool genus_lists_valid = false;
 };
 
 namespace {
@@ -1041,6 +1045,21 @@ int need_labels(tdna_aln *a) {
     return TDNA_OK;
 }
 
+template <int KM> int launch_row_extremes(tdna_aln *a, tdna_extreme_result *d_out) {
+    tdna_ctx *c = a->ctx;
+    constexpr int SMEM = EXT_CAP * 12;
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device & 63]) {
+        CU(cudaFuncSetAttribute(row_extremes_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set[c->device & 63] = true;
+    }
+    row_extremes_kernel<KM><<<(unsigned)a->n, EXT_THREADS, SMEM, c->stream>>>(a->d_planes, a->W, a->n, a->min_overlap, a->d_species, a->d_genus, a->d_gslot,
+                                                                               a->d_gstart, a->d_gmem, d_out);
+    c->launches++;
+    CU(cudaGetLastError());
+    return TDNA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1361,7 +1380,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
                     a->d_needc, a->d_panel_range, a->d_range_rows, a->d_range_cols, a->sp.qi, a->sp.qj, a->sp.qv, a->sp.qx, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcflag, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_seedlist, a->d_cursor, a->d_lj, a->d_ld,
-                    a->x_send, a->x_recv, a->x_state, a->d_hkey[0], a->d_hkey[1], a->d_hcnt[0], a->d_hcnt[1], a->d_hctr, a->d_hent};
+                    a->x_send, a->x_recv, a->x_state, a->d_hkey[0], a->d_hkey[1], a->d_hcnt[0], a->d_hcnt[1], a->d_hctr, a->d_hent, a->d_gslot, a->d_gmem, a->d_gstart};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
     delete a;
@@ -1424,6 +1443,7 @@ int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const 
     CU(cudaStreamSynchronize(c->stream));  // do not return before the copies have read the caller's arrays
     a->has_labels = true;
     a->seedlist_valid = false;
+    a->genus_lists_valid = false;
     return TDNA_OK;
 }
 
@@ -2245,7 +2265,7 @@ int32_t tdna_best_match_merge(tdna_aln *a, const int32_t *cand_row, const int32_
 }
 
 static int class_distances_dense(tdna_aln *a, int32_t klass, float *out, int64_t cap, int64_t *n_out, bool hist = false);
-static int edges_dense(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out);
+static int edges_dense(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out, double lo = 0.0);
 
 // ---- class histograms ------------------------------------------------------------------------------------------------------------
 #define TDNA_E_HIST_FULL 100  // internal: a histogram table filled up -- grow it and repeat the pass
@@ -2617,6 +2637,11 @@ int32_t tdna_edges_below(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double
     return TDNA_OK;
 }
 
+int32_t tdna_pairs_between(tdna_aln *a, double lo, double hi, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out) {
+    if (!a || !n_out) return fail(TDNA_E_ARG, "null argument");
+    return edges_dense(a, hi, ii, jj, d, cap, n_out, lo);  // row bands of the matrix (the lists these callers hold are small)
+}
+
 int32_t tdna_best_match_compute(tdna_aln *a, const tdna_row_result **out_dev) {
     if (!a) return fail(TDNA_E_ARG, "null alignment");
     tdna_analysis io = {};
@@ -2682,7 +2707,7 @@ static int class_distances_dense(tdna_aln *a, int32_t klass, float *out, int64_t
     return rc;
 }
 
-static int edges_dense(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out) {
+static int edges_dense(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *d, int64_t cap, int64_t *n_out, double lo) {
     if (!a || !n_out) return fail(TDNA_E_ARG, "null argument");
     tdna_ctx *c = a->ctx;
     CU(cudaSetDevice(c->device));
@@ -2699,7 +2724,7 @@ static int edges_dense(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *
         unsigned gy = (unsigned)((a->n + 256 * 8 - 1) / (256 * 8));
         if (gy > 65535) gy = 65535;
         dim3 grid((unsigned)(b1 - b0), gy);
-        edges_kernel<<<grid, 256, 0, c->stream>>>(a->d_mat, a->ld, a->n, b0, b1 - b0, t, di, dj, dd, cap, c->d_counter);
+        edges_kernel<<<grid, 256, 0, c->stream>>>(a->d_mat, a->ld, a->n, b0, b1 - b0, lo, t, di, dj, dd, cap, c->d_counter);
         c->launches++;
         CU(cudaGetLastError());
         return TDNA_OK;
@@ -2721,6 +2746,63 @@ static int edges_dense(tdna_aln *a, double t, int32_t *ii, int32_t *jj, double *
     if (dd) DFREE(dd);
     *n_out = (int64_t)cnt;
     return rc;
+}
+
+// ---- per-row extremes among the congeners (tdna_kernels.cuh: row_extremes_kernel) ---------------------------------------------
+static int ensure_genus_lists(tdna_aln *a) {
+    if (a->genus_lists_valid) return TDNA_OK;
+    tdna_ctx *c = a->ctx;
+    const int64_t n = a->n;
+    if ((int64_t)a->h_genus.size() != n) return fail(TDNA_E_STATE, "labels are not set");
+    std::unordered_map<int32_t, int32_t> slot_of;
+    std::vector<int32_t> gslot((size_t)n);
+    std::vector<int64_t> gstart;
+    for (int64_t i = 0; i < n; i++) {
+        auto it = slot_of.emplace(a->h_genus[i], (int32_t)slot_of.size()).first;
+        gslot[i] = it->second;
+    }
+    gstart.assign(slot_of.size() + 1, 0);
+    for (int64_t i = 0; i < n; i++) gstart[gslot[i] + 1]++;
+    for (size_t g = 0; g < slot_of.size(); g++) gstart[g + 1] += gstart[g];
+    std::vector<int64_t> cursor(gstart.begin(), gstart.end() - 1);
+    std::vector<int32_t> gmem((size_t)n);
+    for (int64_t i = 0; i < n; i++) gmem[cursor[gslot[i]]++] = (int32_t)i;  // ascending list positions within a genus
+    if (!a->d_gslot) CU(DMALLOC(&a->d_gslot, (size_t)n * 4));
+    if (!a->d_gmem) CU(DMALLOC(&a->d_gmem, (size_t)n * 4));
+    if (a->d_gstart) { CU(DFREE(a->d_gstart)); a->d_gstart = nullptr; }
+    CU(DMALLOC(&a->d_gstart, gstart.size() * 8));
+    CU(cudaMemcpyAsync(a->d_gslot, gslot.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(a->d_gmem, gmem.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(a->d_gstart, gstart.data(), gstart.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // the vectors are stack-lifetime
+    a->genus_lists_valid = true;
+    return TDNA_OK;
+}
+
+int32_t tdna_row_extremes(tdna_aln *a, tdna_extreme_result *out) {
+    if (!a || !out) return fail(TDNA_E_ARG, "null argument");
+    tdna_ctx *c = a->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(need_labels(a));
+    TRY(ensure_packed(a));
+    if (a->n == 0) return TDNA_OK;
+    if (a->n > 0x7fffffff) return fail(TDNA_E_TOO_LARGE, "too many rows");
+    TRY(ensure_genus_lists(a));
+    const bool dev = is_device_ptr(out);
+    tdna_extreme_result *d_out = out;
+    if (!dev) {
+        TRY(ensure_scratch(a, (size_t)a->n * sizeof(tdna_extreme_result)));
+        d_out = reinterpret_cast<tdna_extreme_result *>(a->d_scratch);
+    }
+    switch (a->kmode) {
+        case KM_P_AMBIG: TRY(launch_row_extremes<KM_P_AMBIG>(a, d_out)); break;
+        case KM_P_NOAMBIG: TRY(launch_row_extremes<KM_P_NOAMBIG>(a, d_out)); break;
+        case KM_K2P: TRY(launch_row_extremes<KM_K2P>(a, d_out)); break;
+        default: TRY(launch_row_extremes<KM_TRANS>(a, d_out)); break;
+    }
+    if (!dev) CU(cudaMemcpyAsync(out, d_out, (size_t)a->n * sizeof(tdna_extreme_result), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TDNA_OK;
 }
 
 int32_t tdna_valid_conspecifics(tdna_aln *a, uint8_t *has_valid) {

@@ -1618,18 +1618,118 @@ __global__ void __launch_bounds__(256) class_distances_kernel(const double *__re
 }
 
 __global__ void __launch_bounds__(256) edges_kernel(const double *__restrict__ mat, int64_t ld, int64_t n, int64_t row_begin, int64_t rows,
-                                                    double t, int32_t *__restrict__ ii, int32_t *__restrict__ jj, double *__restrict__ dd,
+                                                    double lo, double t, int32_t *__restrict__ ii, int32_t *__restrict__ jj, double *__restrict__ dd,
                                                     int64_t cap, unsigned long long *__restrict__ counter) {
     const int64_t qb = blockIdx.x;
     if (qb >= rows) return;
     const int64_t q = row_begin + qb;
     for (int64_t j = q + 1 + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.y * blockDim.x) {
         double d = mat[qb * ld + j];
-        if (d >= 0 && d <= t) {  // Cluster.java:797-804
+        if (d >= lo && d <= t) {  // lo = 0: Cluster.java:797-804; any lo: FindDistances.java:227 (NaN fails both tests, -1 is a value)
             unsigned long long pos = atomicAdd(counter, 1ull);
             if (ii && (int64_t)pos < cap) { ii[pos] = (int32_t)q; jj[pos] = (int32_t)j; dd[pos] = d; }
         }
     }
+}
+
+// ---- per-row extremes among a row's congeners (ExtremePairwise.java:99-170, DistanceAnalysis.java:183-230) -----------------------
+// Both modules sort the whole list against every query (N x sortAgainst) and then only look at the query's conspecifics and at its
+// congeneric, allospecific entries.  One CTA per query row: the rows of the query's genus (member lists by genus, ascending list
+// position) are evaluated straight from the bit-planes, the valid named entries of the two classes are sorted in shared memory by
+// (class, distance, list position) -- the order SortedSequenceList gives them when its comparator is consistent -- and one thread
+// reads the record off the sorted entries.  O(sum of genus sizes squared) pair evaluations instead of O(N^2).
+constexpr int EXT_CAP = 4096;      // entries per query (conspecifics + congeners); larger genera are left to the host
+constexpr int EXT_THREADS = 128;
+template <int KM>
+__global__ void __launch_bounds__(EXT_THREADS) row_extremes_kernel(const uint32_t *__restrict__ planes, int W, int64_t n, int min_overlap,
+                                                                   const int32_t *__restrict__ species, const int32_t *__restrict__ genus,
+                                                                   const int32_t *__restrict__ gslot, const int64_t *__restrict__ gstart,
+                                                                   const int32_t *__restrict__ gmem, tdna_extreme_result *__restrict__ out) {
+    extern __shared__ unsigned long long ext_smem[];
+    unsigned long long *key = ext_smem;                                   // [EXT_CAP] (class << 63) | fp64 bits of d
+    int32_t *col = reinterpret_cast<int32_t *>(ext_smem + EXT_CAP);       // [EXT_CAP]
+    __shared__ int s_count, s_flags;
+    const int64_t q = blockIdx.x;
+    if (q >= n) return;
+    tdna_extreme_result r = {};
+    r.d_max_intra = r.d_min_inter = -1.0;
+    r.max_intra = r.min_inter = -1;
+    const int spq = species[q];
+    if (spq < 0) {  // "Unable to identify species name" (ExtremePairwise.java:109-112)
+        if (threadIdx.x == 0) { r.flags = TDNA_EXT_UNNAMED; out[q] = r; }
+        return;
+    }
+    if (threadIdx.x == 0) { s_count = 0; s_flags = 0; }
+    __syncthreads();
+    const int64_t m0 = gstart[gslot[q]], m1 = gstart[gslot[q] + 1];
+    int myflags = 0;
+    if (m1 - m0 > EXT_CAP) myflags |= TDNA_EXT_TOO_MANY;
+    else
+        for (int64_t m = m0 + threadIdx.x; m < m1; m += EXT_THREADS) {
+            const int j = gmem[m];
+            const Counts c = pair_counts_global<KM>(planes, q, j, W);
+            const double d = distance_from_counts<KM>(c, min_overlap);
+            if (j == q) { if (!(d < 0.0)) myflags |= TDNA_ROW_SELF_VALID; continue; }
+            const int spj = species[j];
+            if (spj < 0 || d < 0.0) continue;  // nameless entries are skipped by both modules; -1 never enters the sorted list
+            if (!(d < __longlong_as_double((long long)TDNA_INF_BITS))) { myflags |= TDNA_ROW_NONFINITE; continue; }
+            const int slot = atomicAdd(&s_count, 1);
+            key[slot] = (unsigned long long)__double_as_longlong(d) | (spj == spq ? 0ull : 1ull << 63);
+            col[slot] = j;
+        }
+    if (myflags) atomicOr(&s_flags, myflags);
+    __syncthreads();
+    const int cnt = s_count;
+    int padded = 1;
+    while (padded < cnt) padded <<= 1;
+    for (int k = cnt + threadIdx.x; k < padded; k += EXT_THREADS) { key[k] = ~0ull; col[k] = 0x7fffffff; }
+    __syncthreads();
+    for (int size = 2; size <= padded; size <<= 1)  // bitonic sort by (key, column)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (padded >> 1); t += EXT_THREADS) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long ka = key[lo], kb = key[hi];
+                const int ca = col[lo], cb = col[hi];
+                const bool gt = ka > kb || (ka == kb && ca > cb);
+                if (gt == up) { key[lo] = kb; key[hi] = ka; col[lo] = cb; col[hi] = ca; }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x != 0) return;
+    r.flags = s_flags;
+    const double near = 2e-5;  // twice Settings' quantum: inside it the comparator's ties are not transitive
+    int k = 0;
+    for (; k < cnt && !(key[k] >> 63); k++) {}  // [0, k): conspecifics, ascending
+    r.n_intra = k;
+    r.n_inter = cnt - k;
+    if (k > 0) {  // the LAST valid conspecific of the sorted list: the largest distance, and of equal distances the last in list order
+        const double dmax = __longlong_as_double((long long)key[k - 1]);
+        r.d_max_intra = dmax;
+        r.max_intra = col[k - 1];
+        for (int x = k - 2; x >= 0; x--) {
+            const double d = __longlong_as_double((long long)key[x]);
+            if (!(dmax - d < near)) break;
+            if (d != dmax) r.near_intra++;
+        }
+        r.shared_intra = pair_counts_global<KM>(planes, q, r.max_intra, W).shared;
+    }
+    if (cnt > k) {  // the FIRST valid congeneric, allospecific entry; the sum in the order the sorted list holds them
+        const double dmin = __longlong_as_double((long long)(key[k] & 0x7fffffffffffffffull));
+        r.d_min_inter = dmin;
+        r.min_inter = col[k];
+        double sum = 0.0, prev = dmin;
+        for (int x = k; x < cnt; x++) {
+            const double d = __longlong_as_double((long long)(key[x] & 0x7fffffffffffffffull));
+            sum = __dadd_rn(sum, d);
+            if (d != dmin && d - dmin < near) r.near_inter++;
+            if (d != prev && d - prev < near) r.near_order++;
+            prev = d;
+        }
+        r.sum_inter = sum;
+        r.shared_inter = pair_counts_global<KM>(planes, q, r.min_inter, W).shared;
+    }
+    out[q] = r;
 }
 
 // SpeciesDetail.getSequencesWithValidConspecificsCount's inner test (SpeciesDetail.java:78-95):

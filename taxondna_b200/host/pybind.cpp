@@ -191,6 +191,8 @@ PYBIND11_MODULE(_host, m) {
     py::class_<ExtremePairwise>(m, "ExtremePairwise")
         .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
         .def("run", [](ExtremePairwise &e) { return e.run(nullptr); })
+        .def_readwrite("force_exact", &ExtremePairwise::force_exact)
+        .def_readonly("rows_resolved_on_host", &ExtremePairwise::rows_resolved_on_host)
         .def("rows", [](const ExtremePairwise &e) {
             std::vector<std::pair<int, int>> out;
             for (auto &r : e.rows()) out.emplace_back(r.largest_intra, r.smallest_inter);
@@ -217,5 +219,36 @@ PYBIND11_MODULE(_host, m) {
 
     py::class_<DistanceAnalysis>(m, "DistanceAnalysis")
         .def(py::init<const SequenceList &>(), py::keep_alive<1, 2>())
+        .def_readwrite("force_exact", &DistanceAnalysis::force_exact)
+        .def_readonly("rows_resolved_on_host", &DistanceAnalysis::rows_resolved_on_host)
         .def("run", [](DistanceAnalysis &d) { return d.run(nullptr); });
+    py::class_<SequenceGrid>(m, "SequenceGrid")
+        .def(py::init<const std::vector<std::string> &, const std::vector<std::string> &>())
+        .def("setSequence", &SequenceGrid::setSequence)
+        .def("setCancelled", &SequenceGrid::setCancelled)
+        .def("getCharsets", &SequenceGrid::getCharsets)
+        .def("getSequenceNames", &SequenceGrid::getSequenceNames)
+        .def("getSequence", &SequenceGrid::getSequence);
+
+    py::class_<FindDistances>(m, "FindDistances")
+        .def(py::init<const SequenceGrid &>(), py::keep_alive<1, 2>())
+        .def("displayResults", [](FindDistances &f, double from, double to, const std::string &col) { return f.displayResults(from, to, col, nullptr); },
+             py::arg("from_"), py::arg("to"), py::arg("colName") = std::string())
+        .def("results", [](const FindDistances &f) {
+            std::vector<std::tuple<int, int, double>> out;
+            for (auto &r : f.results()) out.emplace_back(r.outer, r.inner, r.distance);
+            return out;
+        });
+
+    py::class_<DisplayDistancesMode>(m, "DisplayDistancesMode")
+        .def(py::init<const SequenceGrid &>(), py::keep_alive<1, 2>())
+        .def("setDistanceMethod", &DisplayDistancesMode::setDistanceMethod)
+        .def("activateDisplay", &DisplayDistancesMode::activateDisplay)
+        .def("deactivateDisplay", &DisplayDistancesMode::deactivateDisplay)
+        .def("getSortedSequences", &DisplayDistancesMode::getSortedSequences)
+        .def("columns", &DisplayDistancesMode::columns)
+        .def("distances", &DisplayDistancesMode::distances)
+        .def("normDistances", &DisplayDistancesMode::normDistances)
+        .def("ranks", &DisplayDistancesMode::ranks)
+        .def("scores", &DisplayDistancesMode::scores);
 }

@@ -10,6 +10,7 @@
 #include <fstream>
 #include <functional>
 #include <map>
+#include <mutex>
 #include <set>
 #include <regex>
 #include <sstream>
@@ -265,6 +266,14 @@ static void ck(int rc) {
 }
 static tdna_ctx *g_ctx = nullptr;
 static std::atomic<uint64_t> g_gen{1};
+// live engines by generation: a Sequence remembers the engine it was last uploaded with; the engine may be gone by the time it asks
+static std::mutex g_live_mutex;
+static std::unordered_map<uint64_t, const DistanceEngine *> g_live;
+bool DistanceEngine::isLive(const DistanceEngine *e, uint64_t gen) {
+    std::lock_guard<std::mutex> lock(g_live_mutex);
+    auto it = g_live.find(gen);
+    return it != g_live.end() && it->second == e;
+}
 tdna_ctx *DistanceEngine::context() {
     if (!g_ctx) {
         const char *dev = std::getenv("TDNA_DEVICE");
@@ -290,6 +299,7 @@ static void packSymbols(const std::vector<const Sequence *> &seqs, std::vector<u
 DistanceEngine::DistanceEngine(const SequenceList &list) {
     n_ = list.count();
     gen_ = g_gen++;
+    { std::lock_guard<std::mutex> lock(g_live_mutex); g_live[gen_] = this; }
     if (n_ == 0) return;
     std::vector<const Sequence *> ptrs;
     for (auto &s : list.sequences()) ptrs.push_back(s.get());
@@ -339,6 +349,7 @@ DistanceEngine::DistanceEngine(const SequenceList &list) {
     for (auto &kv : perGenus) class_cap_[1] += kv.second * (kv.second - 1) / 2;
 }
 DistanceEngine::~DistanceEngine() {
+    { std::lock_guard<std::mutex> lock(g_live_mutex); g_live.erase(gen_); }
     if (aln_) tdna_alignment_destroy(aln_);
 }
 void DistanceEngine::syncConfig() const {
@@ -462,6 +473,25 @@ void DistanceEngine::edgesBelow(double t, std::vector<int32_t> &ii, std::vector<
     jj.resize((size_t)cnt);
     d.resize((size_t)cnt);
 }
+void DistanceEngine::pairsBetween(double lo, double hi, std::vector<int32_t> &ii, std::vector<int32_t> &jj, std::vector<double> &d) const {
+    syncConfig();
+    int64_t cnt = 0;
+    ck(tdna_pairs_between(aln_, lo, hi, nullptr, nullptr, nullptr, 0, &cnt));
+    ii.resize((size_t)std::max<int64_t>(cnt, 1));
+    jj.resize(ii.size());
+    d.resize(ii.size());
+    int64_t got = 0;
+    ck(tdna_pairs_between(aln_, lo, hi, ii.data(), jj.data(), d.data(), cnt, &got));
+    ii.resize((size_t)cnt);
+    jj.resize((size_t)cnt);
+    d.resize((size_t)cnt);
+}
+std::vector<tdna_extreme_result> DistanceEngine::rowExtremes() const {
+    syncConfig();
+    std::vector<tdna_extreme_result> v((size_t)n_);
+    if (n_ > 0) ck(tdna_row_extremes(aln_, v.data()));
+    return v;
+}
 std::vector<uint8_t> DistanceEngine::validConspecifics() const {
     syncConfig();
     std::vector<uint8_t> v(n_);
@@ -473,7 +503,7 @@ std::vector<uint8_t> DistanceEngine::validConspecifics() const {
 // free-standing sequences (the reference's own KATs build two and compare them, Sequence.java:1913-1955)
 // get a transient two-row alignment.  Either way the arithmetic is the CUDA library's.
 tdna_counts Sequence::pairCounts(const Sequence &o, double *d, int mode) const {
-    if (home_ && home_ == o.home_ && home_gen_ == home_->generation() && o.home_gen_ == home_gen_ && mode == g_method)
+    if (home_ && home_ == o.home_ && o.home_gen_ == home_gen_ && mode == g_method && DistanceEngine::isLive(home_, home_gen_))
         return home_->pair(home_row_, o.home_row_, d);
     std::vector<uint8_t> sym;
     std::vector<int32_t> len;
@@ -493,7 +523,10 @@ double Sequence::getPairwiseNoBuffer(const Sequence &o) const {
     pairCounts(o, &d, g_method);
     return d;
 }
-double Sequence::getPairwise(const Sequence &o) const { return getPairwiseNoBuffer(o); }  // the cache (:1587-1672) is gone: one launch is cheaper than its Hashtable
+// The cache (:1587-1672) is gone: whole analyses are single calls on the list's engine.  A caller that LOOPS over free-standing
+// sequences pays an upload and a launch per pair here (~100 us, two orders of magnitude above a Hashtable hit): put them in a
+// SequenceList and use its engine (pairs / rowDistances) instead.
+double Sequence::getPairwise(const Sequence &o) const { return getPairwiseNoBuffer(o); }
 int Sequence::getSharedLength(const Sequence &o) const { return pairCounts(o, nullptr, g_method).shared; }
 int Sequence::countIdentical(const Sequence &o) const { return pairCounts(o, nullptr, PDM_UNCORRECTED).c1; }
 int Sequence::countTransversions(const Sequence &o) const { return pairCounts(o, nullptr, PDM_TRANS_ONLY).c1; }
@@ -1622,16 +1655,32 @@ void Cluster::run(DelayCallback *delay) {
 // ------------------------------------------------------------------------------------------------
 // ExtremePairwise.run (ExtremePairwise.java:72-210)
 // ------------------------------------------------------------------------------------------------
+// One tdna_row_extremes launch gives every query's record (the conspecifics and congeners only: O(sum of genus sizes squared) pair
+// evaluations); a query whose record is not provably what the sorted list would show -- near ties around an extreme, NaN, the
+// query not heading its own list, a genus beyond the kernel's capacity, ambiguity codes switched off (d(q, q) need not be 0 then) --
+// is resolved with the exact sort as before.
+static bool extreme_record_decides(const tdna_extreme_result &e) {
+    if (e.flags & (TDNA_ROW_NONFINITE | TDNA_EXT_TOO_MANY)) return false;
+    if (!(e.flags & TDNA_ROW_SELF_VALID) && (e.n_intra + e.n_inter) > 0) return false;  // entry 0 would not be the query (:149 skips it)
+    if (Sequence::getPairwiseDistanceMethod() == Sequence::PDM_UNCORRECTED && !Sequence::areAmbiguousBasesAllowed()) return false;
+    return true;
+}
 std::string ExtremePairwise::run(DelayCallback *delay) {
     const SequenceList &list = *list_;
     rows_.clear();
+    rows_resolved_on_host = 0;
     std::string results = "Sequence name\tLargest conspecific match\tDistance\tOverlap\tClosest congeneric, interspecific match\tDistance\tOverlap\n";
     if (delay) delay->begin();
     SortedSequenceList sorted(list);
     const int total_sequences = list.count();
+    std::vector<tdna_extreme_result> ext;
+    if (!force_exact && total_sequences > 0) ext = list.engine().rowExtremes();
     auto entry = [&](int x) {  // display name, distance as a percentage, overlap
         return sorted.get(x)->getDisplayName() + "\t" + javaDouble(Settings::percentage(sorted.getDistance(x), 1)) + "\t" +
                std::to_string(sorted.getOverlap(x)) + "\t";
+    };
+    auto entry_of = [&](int row, double d, int shared) {
+        return list.get(row)->getDisplayName() + "\t" + javaDouble(Settings::percentage(d, 1)) + "\t" + std::to_string(shared) + "\t";
     };
     for (int count = 0; count < total_sequences; count++) {
         if (delay) delay->delay(count, total_sequences);
@@ -1642,6 +1691,16 @@ std::string ExtremePairwise::run(DelayCallback *delay) {
             rows_.push_back(Row{-2, -2});
             continue;
         }
+        if (!ext.empty() && extreme_record_decides(ext[count]) && ext[count].near_intra == 0 && ext[count].near_inter == 0) {
+            const tdna_extreme_result &e = ext[count];
+            results += seq->getDisplayName() + "\t";
+            results += e.max_intra < 0 ? std::string("No matching conspecific sequence\tN/A\tN/A\t") : entry_of(e.max_intra, e.d_max_intra, e.shared_intra);
+            results += e.min_inter < 0 ? std::string("No matching congeneric, interspecific sequence\tN/A\tN/A\t") : entry_of(e.min_inter, e.d_min_inter, e.shared_inter);
+            results += '\n';
+            rows_.push_back(Row{e.max_intra, e.min_inter});
+            continue;
+        }
+        rows_resolved_on_host++;
         sorted.sortAgainst(seq, nullptr);
         int largest = -1, smallest = -1;  // entries of the sorted list
         const std::string &genus1 = seq->getGenusName();
@@ -1740,11 +1799,24 @@ std::string DistanceAnalysis::run(DelayCallback *delay) {
     std::set<std::string> species_seen;
     struct PerSeq { int q; double avg, closest; };
     std::vector<PerSeq> per_seq;
+    rows_resolved_on_host = 0;
+    std::vector<tdna_extreme_result> ext;  // one launch: every query's closest / summed congeneric, allospecific distance
+    if (!force_exact && n > 0) ext = list.engine().rowExtremes();
     for (int current_seq = 0; current_seq < n; current_seq++) {
         if (delay) delay->delay(current_seq, n);
         const SequencePtr &query = list.get(current_seq);
         const std::string qname = *query->getSpeciesName();
         if (species_seen.insert(qname).second) species_order.push_back(qname);
+        if (!ext.empty()) {
+            const tdna_extreme_result &e = ext[current_seq];
+            // the record decides when the sorted order of the congeneric entries is beyond doubt (it fixes "closest" and the order of
+            // the sum): no near ties among them, no NaN
+            if (!(e.flags & (TDNA_ROW_NONFINITE | TDNA_EXT_TOO_MANY)) && e.near_inter == 0 && e.near_order == 0) {
+                if (e.n_inter > 0) per_seq.push_back(PerSeq{current_seq, e.sum_inter / e.n_inter, e.d_min_inter});
+                continue;
+            }
+        }
+        rows_resolved_on_host++;
         ssl.sortAgainst(query, nullptr);
         double closest = -1;
         std::vector<double> inters;
@@ -1760,16 +1832,16 @@ std::string DistanceAnalysis::run(DelayCallback *delay) {
         if (closest != -1) per_seq.push_back(PerSeq{current_seq, average(inters), closest});
     }
     std::map<std::string, std::vector<double>> genera_all, genera_smallest;  // std::string order == String.compareTo for the names the parser accepts
+    std::unordered_map<std::string, std::vector<size_t>> by_species;  // the entries of a species, in order (the reference rescans them all)
+    for (size_t k = 0; k < per_seq.size(); k++) by_species[*list.get(per_seq[k].q)->getSpeciesName()].push_back(k);
     for (const std::string &sp : species_order) {
         std::optional<std::string> genus;
         std::vector<double> d_all, d_small;
-        for (const PerSeq &e : per_seq) {
-            const SequencePtr &seq = list.get(e.q);
-            if (*seq->getSpeciesName() == sp) {
-                genus = seq->getGenusName();
-                d_all.push_back(e.avg);
-                d_small.push_back(e.closest);
-            }
+        for (size_t k : by_species[sp]) {
+            const PerSeq &e = per_seq[k];
+            genus = list.get(e.q)->getGenusName();
+            d_all.push_back(e.avg);
+            d_small.push_back(e.closest);
         }
         if (!genus) genus = sp.substr(0, sp.find(' '));
         if (!d_all.empty()) {
@@ -1792,6 +1864,190 @@ std::string DistanceAnalysis::run(DelayCallback *delay) {
 
 std::vector<std::string> Cluster::consensusSequences() const {
     return list_->engine().consensus(clusters_);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SequenceMatrix: the grid, FindDistances.displayResults (FindDistances.java:123-289), DisplayDistancesMode.getSortedSequences
+// (DisplayDistancesMode.java:217-398)
+// ------------------------------------------------------------------------------------------------
+void SequenceGrid::setSequence(const std::string &colName, const std::string &seqName, const SequencePtr &seq) {
+    for (auto &c : cells_)
+        if (c.first.first == colName && c.first.second == seqName) { c.second = seq; return; }
+    cells_.push_back({{colName, seqName}, seq});
+}
+void SequenceGrid::setCancelled(const std::string &colName, const std::string &seqName) { cancelled_.push_back({colName, seqName}); }
+SequencePtr SequenceGrid::getSequence(const std::string &colName, const std::string &seqName) const {
+    for (auto &c : cells_)
+        if (c.first.first == colName && c.first.second == seqName) return c.second;
+    return nullptr;
+}
+bool SequenceGrid::isSequenceCancelled(const std::string &colName, const std::string &seqName) const {
+    for (auto &c : cancelled_)
+        if (c.first == colName && c.second == seqName) return true;
+    return false;
+}
+std::vector<std::pair<std::string, SequencePtr>> SequenceGrid::getSequenceListByColumn(const std::string &colName) const {
+    std::map<std::string, SequencePtr> byTaxon;
+    for (auto &c : cells_)
+        if (c.first.first == colName && c.second) byTaxon[c.first.second] = c.second;
+    std::vector<std::pair<std::string, SequencePtr>> out;
+    for (auto &t : taxa_) {
+        auto it = byTaxon.find(t);
+        if (it != byTaxon.end()) out.push_back({t, it->second});
+    }
+    return out;
+}
+
+std::string FindDistances::displayResults(double from, double to, const std::string &colName, DelayCallback *delay) {
+    results_.clear();
+    std::vector<std::string> cols;  // :168-176
+    if (colName.empty()) cols = grid_->getCharsets(); else cols.push_back(colName);
+    if (delay) delay->begin();
+    // one row per (column, sequence) in the order of the reference's outer loops (:200-207): the whole grid is ONE ragged alignment
+    std::vector<SequencePtr> rows;
+    std::vector<int> col_of;
+    for (size_t c = 0; c < cols.size(); c++)
+        for (auto &ts : grid_->getSequenceListByColumn(cols[c])) { rows.push_back(ts.second); col_of.push_back((int)c); }
+    std::vector<double> dist;
+    if (!rows.empty()) {
+        SequenceList flat(rows);
+        std::vector<int32_t> ii, jj;
+        std::vector<double> d;
+        flat.engine().pairsBetween(from, to, ii, jj, d);  // the pairs of :213-229, each unordered pair once
+        // both directions, in the order the four nested loops meet them: (outer row, inner row) ascending
+        std::vector<Result> found;
+        found.reserve(2 * ii.size());
+        for (size_t k = 0; k < ii.size(); k++) { found.push_back({ii[k], jj[k], d[k]}); found.push_back({jj[k], ii[k], d[k]}); }
+        std::sort(found.begin(), found.end(), [](const Result &a, const Result &b) { return a.outer != b.outer ? a.outer < b.outer : a.inner < b.inner; });
+        std::vector<int> order(found.size());
+        for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+        if (!order.empty())  // Collections.sort(results) with PairwiseDistance.compareTo (:249; PairwiseDistance.java:58-63)
+            javaSort(order, [&](int a, int b) -> int { return (int)(int32_t)(uint32_t)(uint64_t)Settings::makeLongFromDouble(found[a].distance - found[b].distance); });
+        for (int k : order) results_.push_back(found[k]);
+    }
+    std::string buff;
+    auto renamed = [&](int row) {  // :231-235: a copy renamed "<display name> (from <column>)"; getFullName() returns the trimmed name
+        Sequence copy(*rows[row]);
+        copy.changeName(copy.getDisplayName() + " (from " + cols[col_of[row]] + ")");
+        return copy.getFullName();
+    };
+    for (auto &r : results_) buff += renamed(r.outer) + "\t" + renamed(r.inner) + "\t" + javaDouble(Settings::percentage(r.distance, 1)) + "%\n";
+    std::string pdm_method = "(unknown)";
+    const int id = Sequence::getPairwiseDistanceMethod();
+    if (id == Sequence::PDM_UNCORRECTED) pdm_method = "uncorrected pairwise distances";
+    else if (id == Sequence::PDM_K2P) pdm_method = "K2P distances";
+    else if (id == Sequence::PDM_TRANS_ONLY) pdm_method = "transversions only";
+    if (delay) delay->end();
+    return std::to_string(results_.size()) + " sequence pairs found with distances between " + javaDouble(Settings::percentage(from, 1)) + "% and " +
+           javaDouble(Settings::percentage(to, 1)) + "%.\nNote that distances were calculated using " + pdm_method +
+           " and sequence overlaps of less than " + std::to_string(Sequence::getMinOverlap()) + " bp weren't counted.\n\n" + buff;
+}
+
+void DisplayDistancesMode::activateDisplay(const std::string &selected_colName) {
+    oldOverlap_ = Sequence::getMinOverlap();
+    oldDistanceMode_ = Sequence::getPairwiseDistanceMethod();
+    Sequence::setMinOverlap(1);
+    Sequence::setPairwiseDistanceMethod(currentDistanceMethod_);
+    selected_colName_ = selected_colName;
+}
+void DisplayDistancesMode::deactivateDisplay() {
+    Sequence::setMinOverlap(oldOverlap_);
+    Sequence::setPairwiseDistanceMethod(oldDistanceMode_);
+}
+std::vector<std::string> DisplayDistancesMode::getSortedSequences(const std::string &seqName_top) {
+    columns_ = grid_->getCharsets();  // getSortedColumns :196-213: sorted, the selected column first
+    std::sort(columns_.begin(), columns_.end());
+    {
+        auto it = std::find(columns_.begin(), columns_.end(), selected_colName_);
+        if (it != columns_.end()) { columns_.erase(it); columns_.insert(columns_.begin(), selected_colName_); }
+        else if (!columns_.empty()) selected_colName_ = columns_[0];
+    }
+    std::vector<std::string> taxa = grid_->getSequenceNames();
+    const size_t nx = columns_.size(), ny = taxa.size();
+    // every (taxon, reference) comparison of every gene in ONE launch over one ragged alignment of all the cells
+    std::vector<SequencePtr> rows;
+    std::map<std::pair<size_t, size_t>, int> index;
+    for (size_t x = 0; x < nx; x++)
+        for (size_t y = 0; y < ny; y++)
+            if (SequencePtr s = grid_->getSequence(columns_[x], taxa[y])) { index[{x, y}] = (int)rows.size(); rows.push_back(s); }
+    size_t ytop = ny;
+    for (size_t y = 0; y < ny; y++)
+        if (taxa[y] == seqName_top) { ytop = y; break; }
+    std::vector<int32_t> qi, qj;
+    std::map<std::pair<size_t, size_t>, size_t> slot;
+    for (size_t x = 0; x < nx; x++) {
+        auto top = ytop < ny ? index.find({x, ytop}) : index.end();
+        if (top == index.end()) continue;
+        for (size_t y = 0; y < ny; y++) {
+            if (taxa[y] == seqName_top) continue;
+            auto it = index.find({x, y});
+            if (it == index.end()) continue;
+            slot[{x, y}] = qi.size();
+            qi.push_back(it->second);
+            qj.push_back(top->second);
+        }
+    }
+    std::vector<double> d;
+    if (!qi.empty()) {
+        SequenceList flat(rows);
+        d = flat.engine().pairs(qi, qj);
+    }
+    std::vector<std::vector<double>> dist(nx, std::vector<double>(ny, DIST_ILLEGAL)), norm(nx, std::vector<double>(ny, 0.0));
+    std::vector<double> mx(nx, -1.0), mn(nx, +2.0);
+    for (size_t x = 0; x < nx; x++)  // pass 1 :255-290
+        for (size_t y = 0; y < ny; y++) {
+            double v;
+            const bool has_top = ytop < ny && index.count({x, ytop});
+            if (!has_top) v = DIST_NO_COMPARE_SEQ;
+            else if (taxa[y] == seqName_top) v = DIST_SEQ_ON_TOP;
+            else if (!index.count({x, y})) v = grid_->isSequenceCancelled(columns_[x], taxa[y]) ? DIST_CANCELLED : DIST_SEQ_NA;
+            else { v = d[slot[{x, y}]]; if (v < 0) v = DIST_NO_OVERLAP; }
+            dist[x][y] = v;
+            if (v >= 0) { if (v > mx[x]) mx[x] = v; if (v < mn[x]) mn[x] = v; }
+        }
+    for (size_t x = 0; x < nx; x++)  // pass 2 :293-300
+        for (size_t y = 0; y < ny; y++) norm[x][y] = dist[x][y] >= 0 ? (dist[x][y] - mn[x]) / (mx[x] - mn[x]) : dist[x][y];
+    std::vector<double> total(ny);
+    for (size_t y = 0; y < ny; y++) {  // pass 3 :305-326
+        double totalScore = 0.0;
+        int count = 0;
+        for (size_t x = 0; x < nx; x++) {
+            if (columns_[x] == selected_colName_) continue;
+            if (dist[x][y] >= 0) { totalScore += norm[x][y]; count++; }
+        }
+        total[y] = totalScore / count;  // 0.0 / 0 = NaN, as in Java
+    }
+    std::vector<int> order(ny);
+    for (size_t y = 0; y < ny; y++) order[y] = (int)y;
+    if (!order.empty())  // Collections.sort(scores), Score.compareTo :106-127
+        javaSort(order, [&](int a, int b) -> int {
+            if (taxa[a] == seqName_top) return -1;
+            if (taxa[b] == seqName_top) return +1;
+            return (int)(int32_t)(uint32_t)(uint64_t)(Settings::makeLongFromDouble(total[a]) - Settings::makeLongFromDouble(total[b]));
+        });
+    distances_.assign(nx, std::vector<double>(ny));
+    norm_distances_.assign(nx, std::vector<double>(ny));
+    ranks_.assign(nx, std::vector<int>(ny));
+    scores_.clear();
+    std::vector<std::string> sorted;
+    for (size_t k = 0; k < ny; k++) {
+        // sequencesList.indexOf(seqName) :345: the FIRST taxon of that name
+        size_t old = (size_t)(std::find(taxa.begin(), taxa.end(), taxa[order[k]]) - taxa.begin());
+        for (size_t x = 0; x < nx; x++) { distances_[x][k] = dist[x][old]; norm_distances_[x][k] = norm[x][old]; }
+        sorted.push_back(taxa[order[k]]);
+        scores_.push_back(total[order[k]]);
+    }
+    for (size_t x = 0; x < nx; x++) {  // :371-385
+        std::vector<double> ll;
+        for (size_t y = 0; y < ny; y++)
+            if (distances_[x][y] >= 0) ll.push_back(distances_[x][y]);
+        std::sort(ll.begin(), ll.end());
+        for (size_t y = 0; y < ny; y++) {
+            if (distances_[x][y] >= 0) ranks_[x][y] = (int)(std::find(ll.begin(), ll.end(), distances_[x][y]) - ll.begin());
+            else ranks_[x][y] = (int)std::floor(distances_[x][y]);
+        }
+    }
+    return sorted;
 }
 
 }  // namespace taxondna

@@ -177,13 +177,17 @@ class DistanceEngine {
     const std::vector<tdna_hist_entry> &classHistogram(int klass) const;
     std::vector<double> pairs(const std::vector<int32_t> &ii, const std::vector<int32_t> &jj) const;  // one launch for a pair list
     void edgesBelow(double t, std::vector<int32_t> &ii, std::vector<int32_t> &jj, std::vector<double> &d) const;
+    // unordered pairs i < j with lo <= getPairwise <= hi (tdna_pairs_between)
+    void pairsBetween(double lo, double hi, std::vector<int32_t> &ii, std::vector<int32_t> &jj, std::vector<double> &d) const;
     std::vector<uint8_t> validConspecifics() const;
+    std::vector<tdna_extreme_result> rowExtremes() const;  // one launch: tdna_row_extremes
     // consensus sequence (normalised alphabet) of every bin of list positions: one launch (tdna_consensus)
     std::vector<std::string> consensus(const std::vector<std::vector<int>> &bins) const;
     const std::vector<int32_t> &speciesId() const { return species_id_; }
     static tdna_ctx *context();  // process-wide, device from $TDNA_DEVICE (default 0)
     static int64_t launchCount();
     uint64_t generation() const { return gen_; }
+    static bool isLive(const DistanceEngine *e, uint64_t gen);  // is `e` still the engine of generation `gen`?
 
   private:
     tdna_aln *aln_ = nullptr;
@@ -393,6 +397,8 @@ class ExtremePairwise {
     explicit ExtremePairwise(const SequenceList &list) : list_(&list) {}
     std::string run(DelayCallback *delay = nullptr);
     const std::vector<Row> &rows() const { return rows_; }
+    int rows_resolved_on_host = 0;  // queries whose device record was not provably the sort's outcome
+    bool force_exact = false;       // resolve every query with the exact sort (validation switch)
 
   private:
     const SequenceList *list_;
@@ -434,9 +440,80 @@ class DistanceAnalysis {
   public:
     explicit DistanceAnalysis(const SequenceList &list) : list_(&list) {}
     std::string run(DelayCallback *delay = nullptr);
+    int rows_resolved_on_host = 0;
+    bool force_exact = false;
 
   private:
     const SequenceList *list_;
+};
+
+// ---- SequenceMatrix's two distance callers: many small per-gene alignments in one launch --------------
+// The (taxon, charset) -> Sequence grid they read through TableManager (SequenceMatrix/TableManager.java:254-371): charsets and
+// taxa in display order; a missing cell is a taxon without a sequence for that gene.
+class SequenceGrid {
+  public:
+    SequenceGrid(const std::vector<std::string> &charsets, const std::vector<std::string> &taxa) : charsets_(charsets), taxa_(taxa) {}
+    void setSequence(const std::string &colName, const std::string &seqName, const SequencePtr &seq);
+    void setCancelled(const std::string &colName, const std::string &seqName);  // TableManager.isSequenceCancelled
+    const std::vector<std::string> &getCharsets() const { return charsets_; }
+    const std::vector<std::string> &getSequenceNames() const { return taxa_; }
+    SequencePtr getSequence(const std::string &colName, const std::string &seqName) const;  // null when absent
+    bool isSequenceCancelled(const std::string &colName, const std::string &seqName) const;
+    // TableManager.getSequenceListByColumn :359-371 (taxa in display order, absent cells skipped)
+    std::vector<std::pair<std::string, SequencePtr>> getSequenceListByColumn(const std::string &colName) const;
+
+  private:
+    std::vector<std::string> charsets_, taxa_;
+    std::vector<std::pair<std::pair<std::string, std::string>, SequencePtr>> cells_;
+    std::vector<std::pair<std::string, std::string>> cancelled_;
+};
+
+// SequenceMatrix/FindDistances.java:123-289: every sequence of the chosen genes against every other one, the pairs with
+// from <= getPairwise <= to in both directions, sorted by PairwiseDistance.compareTo.  All genes' sequences form one ragged
+// alignment on the device; the O(N^2) loop of :200-244 is one tdna_pairs_between call.
+class FindDistances {
+  public:
+    struct Result {
+        int outer, inner;  // rows of the (column, taxon) enumeration
+        double distance;
+    };
+    explicit FindDistances(const SequenceGrid &grid) : grid_(&grid) {}
+    // from / to as fractions (the text fields hold percentages, :136-164); colName empty = "All genes".  Returns text_main's content.
+    std::string displayResults(double from, double to, const std::string &colName = std::string(), DelayCallback *delay = nullptr);
+    const std::vector<Result> &results() const { return results_; }
+
+  private:
+    const SequenceGrid *grid_;
+    std::vector<Result> results_;
+};
+
+// SequenceMatrix/DisplayDistancesMode.java:163-398: per gene, every taxon's sequence against the reference taxon's; normalised per
+// gene, taxa sorted by their mean normalised distance over the other genes, per-gene ranks.  The distances of all genes are one
+// tdna_pairs launch.
+class DisplayDistancesMode {
+  public:
+    static constexpr double DIST_ILLEGAL = -32.0, DIST_NO_COMPARE_SEQ = -64.0, DIST_SEQ_NA = -128.0, DIST_NO_OVERLAP = -256.0,
+                            DIST_SEQ_ON_TOP = -1024.0, DIST_CANCELLED = -2048.0;  // :50-55
+    explicit DisplayDistancesMode(const SequenceGrid &grid) : grid_(&grid) {}
+    void setDistanceMethod(int pdm) { currentDistanceMethod_ = pdm; }  // the menu (:60-63; "Transversions only" is the default)
+    void activateDisplay(const std::string &selected_colName);         // :157-171: minOverlap := 1, the menu's distance method
+    void deactivateDisplay();                                          // :173-179: both statics restored
+    // :217-398; returns the taxa in sorted order
+    std::vector<std::string> getSortedSequences(const std::string &referenceTaxon);
+    const std::vector<std::string> &columns() const { return columns_; }
+    const std::vector<std::vector<double>> &distances() const { return distances_; }       // [column][taxon]
+    const std::vector<std::vector<double>> &normDistances() const { return norm_distances_; }
+    const std::vector<std::vector<int>> &ranks() const { return ranks_; }
+    const std::vector<double> &scores() const { return scores_; }
+
+  private:
+    const SequenceGrid *grid_;
+    int currentDistanceMethod_ = Sequence::PDM_TRANS_ONLY, oldOverlap_ = 0, oldDistanceMode_ = 0;
+    std::string selected_colName_;
+    std::vector<std::string> columns_;
+    std::vector<std::vector<double>> distances_, norm_distances_;
+    std::vector<std::vector<int>> ranks_;
+    std::vector<double> scores_;
 };
 
 // Common/DNA/SpeciesDetails.java / SpeciesDetail.java:78-95

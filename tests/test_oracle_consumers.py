@@ -169,3 +169,34 @@ def test_consumer_digests_of_the_reference_fixture(golden_dir):
     text = gzip.open(os.path.join(golden_dir, "diptera_small_nogaps.fasta.gz"), "rt", encoding="latin-1").read()
     assert mod.digests(text, PDM_UNCORRECTED) == want["p"]
     assert mod.digests(text, PDM_K2P) == want["k2p"]
+
+
+def test_sequence_matrix_callers_hand_derived():
+    """FindDistances / DisplayDistancesMode restatements on a grid small enough to work out by hand (SequenceMatrix/
+    FindDistances.java:196-262, DisplayDistancesMode.java:255-385)."""
+    cells = {("g1", "Aus bus"): C.OSeq("Aus bus", "AAAAAAAAAA"), ("g1", "Aus cus"): C.OSeq("Aus cus", "AAAAAAAAAT"),
+             ("g1", "Aus dus"): C.OSeq("Aus dus", "AAAAAAAATT"),
+             ("g2", "Aus bus"): C.OSeq("Aus bus", "CCCCC"), ("g2", "Aus dus"): C.OSeq("Aus dus", "CCCCG")}
+    grid = C.OGrid(["g1", "g2"], ["Aus bus", "Aus cus", "Aus dus"], cells)
+    cfg = C.Config(C.PDM_UNCORRECTED, 1, True)
+    # rows: g1 bus, cus, dus (0..2), g2 bus, dus (3, 4).  1.0 - 9/10 = 0.09999999999999998 is inside [0, 0.1] and prints as 9.99 %
+    # (Settings.percentage truncates twice); every cross-gene pair compares A's with C's over five columns: 1.0
+    text, res = C.find_distances(grid, cfg, 0.0, 0.1)
+    assert [(a, b) for a, b, _ in res] == [(0, 1), (1, 0), (1, 2), (2, 1)]
+    assert all(d == 1.0 - 9 / 10 for _, _, d in res)
+    assert text == ("4 sequence pairs found with distances between 0.0% and 10.0%.\nNote that distances were calculated using uncorrected pairwise "
+                    "distances and sequence overlaps of less than 1 bp weren't counted.\n\n"
+                    "Aus bus (from g1)\tAus cus (from g1)\t9.99%\nAus cus (from g1)\tAus bus (from g1)\t9.99%\n"
+                    "Aus cus (from g1)\tAus dus (from g1)\t9.99%\nAus dus (from g1)\tAus cus (from g1)\t9.99%\n")
+    text, res = C.find_distances(grid, cfg, 0.15, 0.25, "g2")
+    assert [(a, b, d) for a, b, d in res] == [(0, 1, 1.0 - 4 / 5), (1, 0, 1.0 - 4 / 5)]
+    # DisplayDistancesMode against "Aus bus", gene g1 selected: g1 = [ON_TOP, 0.1-, 0.2-], g2 = [ON_TOP, SEQ_NA, 0.2-]
+    r = C.display_distances(grid, C.PDM_UNCORRECTED, "Aus bus", "g1")
+    assert r["columns"] == ["g1", "g2"]
+    d1, d2 = 1.0 - 9 / 10, 1.0 - 8 / 10
+    # scores over the OTHER genes (g2): bus NaN (no distance), cus NaN, dus (0.2 - 0.2) / (0.2 - 0.2) = NaN: all tie at (long) NaN = 0
+    assert r["taxa"] == ["Aus bus", "Aus cus", "Aus dus"]
+    assert r["distances"][0] == [C.DIST_SEQ_ON_TOP, d1, d2]
+    assert r["distances"][1] == [C.DIST_SEQ_ON_TOP, C.DIST_SEQ_NA, 1.0 - 4 / 5]
+    assert r["norm_distances"][0][1:] == [0.0, 1.0]
+    assert r["ranks"][0] == [-1024, 0, 1] and r["ranks"][1] == [-1024, -128, 0]
