@@ -1378,7 +1378,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     cudaSetDevice(c->device);
     if (c->mat_owner == a) c->mat_owner = nullptr;
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
-                    a->d_needc, a->d_panel_range, a->d_range_rows, a->d_range_cols, a->sp.qi, a->sp.qj, a->sp.qv, a->sp.qx, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcflag, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
+                    a->d_needc, a->d_panel_range, a->d_range_rows, a->d_range_cols, a->sp.q, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcflag, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_seedlist, a->d_cursor, a->d_lj, a->d_ld,
                     a->x_send, a->x_recv, a->x_state, a->d_hkey[0], a->d_hkey[1], a->d_hcnt[0], a->d_hcnt[1], a->d_hctr, a->d_hent, a->d_gslot, a->d_gmem, a->d_gstart};
     for (void *p : ptrs)
@@ -1727,14 +1727,11 @@ static int ensure_stream_state(tdna_aln *a) {
     CU(DMALLOC(&sp.cj, (size_t)cap * 4));
     CU(DMALLOC(&sp.cd, (size_t)cap * 8));
     // kernel (b)'s queue holds every pair that passes the SEEDED threshold of either of its rows (about four times the final
-    // candidates): 256 per row, 12 bytes each
+    // candidates): 256 per row, 16 bytes each
     long long qcap = (long long)n * 256;
     if (qcap < (1ll << 22)) qcap = 1ll << 22;
-    if (qcap * 12 > c->budget / 2) qcap = c->budget / 24;
-    CU(DMALLOC(&sp.qi, (size_t)qcap * 4));
-    CU(DMALLOC(&sp.qj, (size_t)qcap * 4));
-    CU(DMALLOC(&sp.qv, (size_t)qcap * 4));
-    CU(DMALLOC(&sp.qx, (size_t)qcap * 4));
+    if (qcap * 16 > c->budget / 2) qcap = c->budget / 32;
+    CU(DMALLOC(&sp.q, (size_t)qcap * 16));
     sp.qcap = qcap;
     CU(DMALLOC(&a->d_stream_u64, 64));  // ncand, overflow, ncls[2], nedge, qn
     sp.ncand = reinterpret_cast<unsigned long long *>(a->d_stream_u64);
@@ -1774,10 +1771,9 @@ static bool grow_stream_buffers(tdna_aln *a) {
         sp.cap = cap;
     }
     if (qcap != sp.qcap) {
-        DFREE(sp.qi); DFREE(sp.qj); DFREE(sp.qv); DFREE(sp.qx);
-        sp.qi = sp.qj = nullptr; sp.qv = sp.qx = nullptr;
-        if (cudaSuccess != DMALLOC(&sp.qi, (size_t)qcap * 4) || cudaSuccess != DMALLOC(&sp.qj, (size_t)qcap * 4) || cudaSuccess != DMALLOC(&sp.qv, (size_t)qcap * 4) ||
-            cudaSuccess != DMALLOC(&sp.qx, (size_t)qcap * 4)) {
+        DFREE(sp.q);
+        sp.q = nullptr;
+        if (cudaSuccess != DMALLOC(&sp.q, (size_t)qcap * 16)) {
             cudaGetLastError();
             a->stream_broken = true;
             return false;

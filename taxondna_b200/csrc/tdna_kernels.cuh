@@ -159,8 +159,11 @@ struct StreamParams {
     unsigned long long *nedge;
     // count kernel (b) defers its slow path: the epilogue only queues (row, column, raw accumulator) of the pairs that pass
     // the seeded thresholds; tc::resolve_*_kernel turn the queue into candidate records after the pass
-    int32_t *qi, *qj;
-    uint32_t *qv, *qx;           // qx: second word of the exact counts resolve_min_kernel leaves for resolve_emit_kernel
+    // one 16-byte record per entry (x = row, bit 31: a deferred class pair; y = column, bit 31: a class-only entry; z = raw accumulator;
+    // z, w = the exact counts once resolve_min_kernel has left them for resolve_emit_kernel): a lane's entries are contiguous, so its
+    // stores fill whole 32-byte sectors (separate 4-byte arrays made every push a partial-sector write: 1.1 GB of L2 write sectors and
+    // 4.9 GB of DRAM fills for a 190 MB queue, profiles/r2n_*)
+    uint4 *q;
     unsigned long long *qn;
     long long qcap;
 };

@@ -893,7 +893,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                             if ((long long)(base + total) <= sp.qcap) {
 #pragma unroll
                                 for (int e = 0; e < 32; e++)
-                                    if (pmask & (1u << e)) { sp.qi[w] = i | (int)((cmask >> e) << 31); sp.qj[w] = (jb + e) | conly; sp.qv[w] = v[e]; w++; }
+                                    if (pmask & (1u << e)) { sp.q[w] = make_uint4((uint32_t)(i | (int)((cmask >> e) << 31)), (uint32_t)((jb + e) | conly), v[e], 0u); w++; }
                             } else if (lane == 0) *sp.overflow = 1;
                         }
                         pmask = 0;
@@ -1036,11 +1036,12 @@ __global__ void __launch_bounds__(256) resolve_min_kernel(StreamParams sp, Resol
     if (*sp.overflow) return;  // the queue has holes when a push did not fit: the caller falls back to the dense path
     const long long nq = min((long long)*sp.qn, sp.qcap);
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
-        if (sp.qj[r] < 0) continue;  // a class-only entry
-        const int i = sp.qi[r] & 0x7fffffff, j = sp.qj[r];
+        const uint4 ent = sp.q[r];
+        if ((int)ent.y < 0) continue;  // a class-only entry
+        const int i = (int)(ent.x & 0x7fffffffu), j = (int)ent.y;
         uint32_t lhs, den, w0 = 0, w1 = 0;
-        const double d = queued_distance(ra, i, j, sp.qv[r], lhs, den, &w0, &w1);
-        if (ra.planes) { sp.qv[r] = w0; sp.qx[r] = w1; }  // the exact counts, for resolve_emit_kernel
+        const double d = queued_distance(ra, i, j, ent.z, lhs, den, &w0, &w1);
+        if (ra.planes) sp.q[r] = make_uint4(ent.x, ent.y, w0, w1);  // the exact counts, for resolve_emit_kernel
         if (!(d < __longlong_as_double((long long)TDNA_INF_BITS)) || d < 0.0) continue;
         const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
         const int spi = sp.species[i], spj = sp.species[j];
@@ -1060,9 +1061,10 @@ __global__ void __launch_bounds__(256) resolve_emit_kernel(StreamParams sp, Reso
     const long long nq = min((long long)*sp.qn, sp.qcap);
     const bool want_bm = (sp.want & TDNA_WANT_BEST_MATCH) != 0;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nq; r += (long long)gridDim.x * blockDim.x) {
-        const int qi_raw = sp.qi[r], qj_raw = sp.qj[r], i = qi_raw & 0x7fffffff, j = qj_raw & 0x7fffffff;
+        const uint4 ent = sp.q[r];
+        const int qi_raw = (int)ent.x, qj_raw = (int)ent.y, i = qi_raw & 0x7fffffff, j = qj_raw & 0x7fffffff;
         uint32_t lhs, den;
-        const double d = (ra.cached && qj_raw >= 0) ? cached_distance(ra, sp.qv[r], sp.qx[r], lhs, den) : queued_distance(ra, i, j, sp.qv[r], lhs, den);
+        const double d = (ra.cached && qj_raw >= 0) ? cached_distance(ra, ent.z, ent.w, lhs, den) : queued_distance(ra, i, j, ent.z, lhs, den);
         if (qi_raw < 0 && !(d < 0.0)) class_emit_value(sp, i, j, d, hist ? s_keys : nullptr, s_cnts);  // a deferred class pair (valid: NaN / +Inf are kept, -1 is dropped)
         if (qj_raw < 0) continue;  // a class-only entry: the rows' launch queued this pair for itself
         if (d < 0.0) {  // queued with an uncertain overlap (ambiguity letters), and the exact overlap is below minOverlap: an invalid pair
