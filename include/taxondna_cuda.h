@@ -336,6 +336,8 @@ enum { TDNA_OPT_BEST_MATCH_PATH = 1, /* TDNA_PATH_*: how tdna_best_match compute
        TDNA_OPT_COUNT_KERNEL = 3,    /* TDNA_KERNEL_*: which count kernel the streaming pass uses */
        TDNA_OPT_HIST_SLOTS = 5,      /* first size of a class histogram's table for alignments created from now on (a power of two,
                                         default 2^18; a pass that fills a table repeats with four times the slots) */
+       TDNA_OPT_PIPELINE_CHUNKS = 7, /* tdna_analyze_host: at most this many row chunks for a pass PIPELINED with the upload (region
+                                        launches per chunk; 0 = default = one pass after the upload, which measured faster) */
        TDNA_OPT_SEGMENT_ITEMS = 6,   /* work items (tiles of kernel (a), tile pairs of kernel (b)) per launch of a streaming pass; 0 =
                                         automatic (~30 ms of work).  Between launches a single-GPU pass honours tdna_cancel and calls
                                         the progress callback */
@@ -437,6 +439,13 @@ int32_t tdna_tensor_dims(tdna_aln *aln);
 /* Sizes of the most recent streaming pass on this GPU: candidate records emitted (two per pair at most) and pairs count kernel (b)
  * queued for exact resolution (0 on count kernel (a)). */
 int32_t tdna_last_pass_stats(tdna_aln *aln, int64_t *candidates, int64_t *queued);
+/* How many tdna_analyze_host calls on this context ran their pass pipelined with the upload (Best Match rows on one GPU from host
+ * symbols, 16,384 to 131,072 rows, count kernel (b)): region launches per row chunk instead of one pass after the upload. */
+int64_t tdna_pipelined_passes(tdna_ctx *ctx);
+/* Host wall clock of the context's most recent tdna_analyze_host call, in milliseconds since its entry, at: labels + plan done, buffers
+ * ready, every upload chunk enqueued, the first chunk's verdict in, every chunk's kernels enqueued, the upload's final
+ * synchronisation, the pass finished, the analysis returned, the call returned (-1: a mark the call did not pass). */
+int32_t tdna_host_call_phase_ms(tdna_ctx *ctx, double *ms, int32_t cap, int32_t *n_out);
 /* Device time between the phase marks of the context's most recent multi-GPU pass (CUDA events on its stream), in order: seed launch,
  * MIN all-reduce of the per-row minima, thresholds + bulk launch + queue resolution, routing + exchange of records / state / status,
  * merge of the own rows, all-gather of the row records.  *n_out phases are written (at most cap). */

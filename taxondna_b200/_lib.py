@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("TDNA_LIB") or os.path.join(_HERE, "libtaxondna_cuda.s
 PDM_UNCORRECTED, PDM_K2P, PDM_TRANS_ONLY = 0, 1, 2
 PD_INTRA, PD_INTER = 0, 1
 ROW_SELF_VALID, ROW_NONFINITE = 1, 2
-OPT_BEST_MATCH_PATH, OPT_TILE_COLUMNS, OPT_COUNT_KERNEL, OPT_MULTI, OPT_HIST_SLOTS, OPT_SEGMENT_ITEMS = 1, 2, 3, 4, 5, 6
+OPT_BEST_MATCH_PATH, OPT_TILE_COLUMNS, OPT_COUNT_KERNEL, OPT_MULTI, OPT_HIST_SLOTS, OPT_SEGMENT_ITEMS, OPT_PIPELINE_CHUNKS = 1, 2, 3, 4, 5, 6, 7
 COMM_ID_BYTES = 128
 KERNEL_AUTO, KERNEL_POPC, KERNEL_TENSOR = 0, 1, 2
 PATH_AUTO, PATH_DENSE, PATH_STREAM = 0, 1, 2
@@ -87,7 +87,7 @@ EXPORTS = [
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below", "tdna_pairs_between", "tdna_row_extremes",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
     "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_rows_per_part", "tdna_tensor_code", "tdna_consensus", "tdna_fasta_parse", "tdna_fasta_destroy", "tdna_fasta_count", "tdna_fasta_width", "tdna_fasta_records", "tdna_fasta_symbols", "tdna_alignment_create_from_fasta", "tdna_best_match_part_routed", "tdna_best_match_merge_routed", "tdna_set_option", "tdna_last_tile_pass_ms",
-    "tdna_tensor_dims", "tdna_last_pass_stats", "tdna_multi_phase_ms", "tdna_analyze_host", "tdna_class_histogram", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
+    "tdna_tensor_dims", "tdna_last_pass_stats", "tdna_pipelined_passes", "tdna_host_call_phase_ms", "tdna_multi_phase_ms", "tdna_analyze_host", "tdna_class_histogram", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)
@@ -179,6 +179,9 @@ def load():
     L.tdna_tensor_counts.argtypes = [vp, vp]
     L.tdna_last_count_kernel.argtypes = [vp]
     L.tdna_tensor_dims.argtypes = [vp]
+    L.tdna_host_call_phase_ms.argtypes = [vp, vp, i32, ctypes.POINTER(i32)]
+    L.tdna_pipelined_passes.argtypes = [vp]
+    L.tdna_pipelined_passes.restype = i64
     L.tdna_last_pass_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.tdna_multi_phase_ms.argtypes = [vp, vp, i32, ctypes.POINTER(i32)]
     L.tdna_analyze.argtypes = [vp, ctypes.POINTER(Analysis)]
@@ -281,6 +284,16 @@ class Context:
 
     def launch_count(self):
         return int(self.L.tdna_launch_count(self.h))
+
+    def host_call_phase_ms(self):
+        ms = (ctypes.c_double * 12)()
+        k = ctypes.c_int32()
+        check(self.L.tdna_host_call_phase_ms(self.h, ms, 12, ctypes.byref(k)))
+        names = ("labels+plan", "buffers", "uploads_enqueued", "first_chunk_verdict", "chunks_enqueued", "upload_synced", "pass_done", "analysis_done", "returned")
+        return {nm: round(ms[i], 4) for i, nm in zip(range(k.value), names)}
+
+    def pipelined_passes(self):
+        return int(self.L.tdna_pipelined_passes(self.h))
 
     def set_progress(self, fn):
         self._cb = PROGRESS_FN(lambda done, total, user: fn(done, total)) if fn else PROGRESS_FN()

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -38,14 +39,16 @@ int fail(int code, const std::string &msg) {
 int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 }  // namespace
 
-// Per-alignment buffers come from the device's stream-ordered pool (release threshold = never), so
-// creating and destroying an alignment per analysis costs microseconds, not cudaMalloc/cudaFree syncs.
-#define DMALLOC(ptr, bytes) cudaMallocAsync((void **)(ptr), (bytes), c->stream)
+// Per-alignment buffers come from a stream-ordered pool of the CONTEXT'S OWN (release threshold = never: creating and destroying an
+// alignment per analysis costs microseconds, not cudaMalloc/cudaFree syncs).  The device's default pool -- which other users of
+// cudaMallocAsync in the process share -- is left as it is.
+#define DMALLOC(ptr, bytes) cudaMallocFromPoolAsync((void **)(ptr), (bytes), c->pool, c->stream)
 #define DFREE(ptr) cudaFreeAsync((ptr), c->stream)
 
 struct tdna_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
     int64_t budget = 64ll << 30;
     int64_t launches = 0;
     int sm_count = 148;
@@ -73,7 +76,22 @@ struct tdna_ctx {
     int opt_count_kernel = TDNA_KERNEL_AUTO;
     uint32_t opt_hist_slots = 1u << 18;
     int64_t opt_segment_items = 0;  // 0 = automatic (segments of ~30 ms)
+    // tdna_analyze_host: row chunks of the pass pipelined with the upload; 0 (default): not pipelined -- measured on 50,000 x 658:
+    // 3.54 ms without, 3.62 - 3.82 ms with 2 - 8 chunks: the upload is 0.65 ms, the first chunk's verdict and a seed
+    // launch per chunk cost as much as the overlap gains
+    int opt_pipeline_chunks = 0;
+    // records / queue entries per row the streaming buffers of NEW alignments start with: raised to what a pass on this context
+    // needed (a host that creates an alignment per analysis would otherwise overflow and retry every time)
+    double hint_cand_per_row = 64, hint_queue_per_row = 256;
+    cudaStream_t enc_stream = nullptr;   // pipelined tdna_analyze_host: pack + encode of the arriving chunks, beside the tile launches
+    cudaEvent_t ev_enc[16] = {};
+    double hc_t[12] = {};            // host wall-clock marks of the most recent tdna_analyze_host call (tdna_host_call_phase_ms)
+    int64_t pipelined_passes = 0;   // tdna_analyze_host calls whose pass ran pipelined with the upload (tdna_pipelined_passes)
 };
+
+static inline void hc_mark(tdna_ctx *c, int k) {
+    c->hc_t[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 struct tdna_aln {
     tdna_ctx *ctx = nullptr;
@@ -157,6 +175,15 @@ struct tdna_aln {
     int32_t *d_gslot = nullptr, *d_gmem = nullptr;
     int64_t *d_gstart = nullptr;
     bool genus_lists_valid = false;
+    std::vector<int2> h_seedlist;  // host copy of the seed list (the pipelined pass re-orders it by row chunk)
+    // the pass pipelined with the upload (tdna_analyze_host, pipeline_*): per-launch overrides consulted by launch_tc_cl
+    const int64_t *pl_reg_start = nullptr, *pl_reg_prefix = nullptr;  // device: the region's runs of slot pairs
+    int pl_reg_n = 0;
+    int64_t pl_reg_items = 0;
+    const int2 *pl_seed_list = nullptr;
+    int pl_seed_pairs = -1;  // -1: no override
+    int pl_general = -1;     // -1: the instantiation follows tc_has_amb; 0 / 1: decided from the first chunk's flags
+    void *d_plbuf = nullptr;
 };
 
 namespace {
@@ -357,7 +384,8 @@ int launch_tiles(tdna_aln *a, int64_t b0, int64_t b1, bool symmetric, double *ou
 // ---- streaming Best Match: the tile pass --------------------------------------------------------
 // Triangle tiles in two launches: the diagonal blocks first (list neighbours -- conspecifics and
 // congeners when the list is sorted by name -- so the per-row thresholds are tight before the bulk),
-// then everything right of them, row-tile major.  Part k of m takes global tiles k, k+m, k+2m, ...
+// then everything right of them, row-tile major.  Kernel (a): part k of m takes the k-th contiguous 1/m of the tile list; kernel (b): units of
+// 64 tile pairs dealt cyclically (launch_tc_cl).
 template <int CN> int stream_prefixes(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
     constexpr int TN = 16 * CN, R = TM / TN;
@@ -819,6 +847,7 @@ static int build_seed_list(tdna_aln *a) {
     CU(cudaMemcpyAsync(a->d_seedlist, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     a->seed_pairs = (int)list.size();
+    a->h_seedlist = list;
     a->seedlist_valid = true;
     return TDNA_OK;
 }
@@ -826,7 +855,8 @@ static int build_seed_list(tdna_aln *a) {
 template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int part, int nparts, tdna_counts *counts) {
     tdna_ctx *c = a->ctx;
     // the plain instantiation serves uncorrected p on alignments without ambiguity letters (exact accumulators everywhere)
-    const bool general = !COUNTS_MODE && (a->kmode == KM_K2P || a->tc_has_amb);
+    const bool has_amb = a->pl_general >= 0 ? a->pl_general != 0 : a->tc_has_amb;
+    const bool general = !COUNTS_MODE && (a->kmode == KM_K2P || has_amb);
     auto kern = tc::tile_kernel<COUNTS_MODE, CL, false>;
     if constexpr (!COUNTS_MODE) {
         if (general) kern = tc::tile_kernel<COUNTS_MODE, CL, true>;
@@ -851,7 +881,10 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.band = phase ? TC_BAND : 0;
     p.nbands = (p.nrt + TC_BAND - 1) / TC_BAND;
     p.prefix = a->d_tcprefix[1];
-    if (!COUNTS_MODE && phase == 0 && a->has_labels) {
+    if (!COUNTS_MODE && phase == 0 && a->pl_seed_pairs >= 0) {  // the pipelined pass: the items of the chunk that has just arrived
+        p.seed_list = a->pl_seed_list;
+        p.seed_pairs = a->pl_seed_pairs;
+    } else if (!COUNTS_MODE && phase == 0 && a->has_labels) {
         TRY(build_seed_list(a));
         p.seed_list = a->d_seedlist;
         p.seed_pairs = a->seed_pairs;
@@ -861,7 +894,7 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.k2p = a->kmode == KM_K2P ? 1 : 0;
     p.panel_full = a->d_tcfull;
     p.L = a->L;
-    p.amb = a->tc_has_amb ? a->d_tcamb : nullptr;
+    p.amb = has_amb ? a->d_tcamb : nullptr;
     p.panel_amb = a->d_tcpanel_amb;
     if (!COUNTS_MODE && a->d_panel_range && (a->sp.want & ~(TDNA_WANT_INTRA | TDNA_WANT_INTER)) == 0 && !exp_env("TDNA_TC_NOSKIP")) {
         p.class_only = ((a->sp.want & TDNA_WANT_INTRA) ? 1 : 0) | ((a->sp.want & TDNA_WANT_INTER) ? 2 : 0);
@@ -892,6 +925,13 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.t_offset = part;
     p.t_stride = nparts;
     p.num_tiles = my_units * p.unit;  // items past the end of the list are skipped by the kernel
+    const bool region = !COUNTS_MODE && phase == 1 && CL == 2 && a->pl_reg_n > 0;
+    if (region) {  // (one part only: tdna_analyze_host pipelines on a single GPU)
+        p.reg_start = a->pl_reg_start;
+        p.reg_prefix = a->pl_reg_prefix;
+        p.reg_n = a->pl_reg_n;
+        p.num_tiles = a->pl_reg_items;
+    }
     p.planes = a->d_planes;
     p.W32 = a->W;
     {
@@ -907,7 +947,7 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     const StreamParams sp = pass_params(a, !COUNTS_MODE && phase == 0);
     // segments of ~30 ms (an item of two 128 x 256 tiles of 658 columns takes ~0.13 us of the whole GPU): see segment_boundary
     const int64_t items = p.num_tiles;
-    const int64_t seg = (COUNTS_MODE || phase == 0) ? items : c->opt_segment_items > 0 ? c->opt_segment_items : std::max<int64_t>(units * 64, ((int64_t)1 << 18) * 26 / std::max(p.nchunks, 1) * (CL >= 2 ? 1 : 2));
+    const int64_t seg = (COUNTS_MODE || phase == 0 || region) ? items : c->opt_segment_items > 0 ? c->opt_segment_items : std::max<int64_t>(units * 64, ((int64_t)1 << 18) * 26 / std::max(p.nchunks, 1) * (CL >= 2 ? 1 : 2));
     for (int64_t k0 = 0; k0 < items; k0 += seg) {
         p.k_base = k0;
         p.num_tiles = std::min(seg, items - k0);
@@ -1077,26 +1117,41 @@ int32_t tdna_init(int32_t device, tdna_ctx **out) {
     CU(cudaSetDevice(device));
     tdna_ctx *c = new tdna_ctx();
     c->device = device;
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    c->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaMalloc(&c->d_counter, 64));
-    CU(cudaEventCreate(&c->ev_k0));
-    CU(cudaEventCreate(&c->ev_k1));
-    CU(cudaEventCreate(&c->ev_s1));
-    CU(cudaEventCreate(&c->ev_b0));
-    for (cudaEvent_t &e : c->ev_ph) CU(cudaEventCreate(&e));
-    CU(cudaMallocHost(&c->h_status, 64 * sizeof(int64_t)));
-    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (cudaEvent_t &e : c->ev_copy) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    cudaMemPool_t pool;
-    CU(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long keep = ~0ull;
-    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    uint16_t lut[256];
-    build_lut(lut);
-    CU(cudaMemcpyToSymbol(c_symlut, lut, sizeof(lut)));
+    auto body = [&]() -> int {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        c->sm_count = prop.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&c->d_counter, 64));
+        CU(cudaEventCreate(&c->ev_k0));
+        CU(cudaEventCreate(&c->ev_k1));
+        CU(cudaEventCreate(&c->ev_s1));
+        CU(cudaEventCreate(&c->ev_b0));
+        for (cudaEvent_t &e : c->ev_ph) CU(cudaEventCreate(&e));
+        CU(cudaMallocHost(&c->h_status, 64 * sizeof(int64_t)));
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : c->ev_copy) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&c->enc_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : c->ev_enc) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        CU(cudaMemPoolCreate(&c->pool, &props));
+        unsigned long long keep = ~0ull;
+        CU(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        uint16_t lut[256];
+        build_lut(lut);
+        CU(cudaMemcpyToSymbol(c_symlut, lut, sizeof(lut)));  // the same table for every context of the process: idempotent
+        return TDNA_OK;
+    };
+    const int rc = body();
+    if (rc != TDNA_OK) {  // nothing half-built survives a failed init
+        const std::string why = tdna_last_error();
+        tdna_shutdown(c);
+        return fail(rc, why);
+    }
     *out = c;
     return TDNA_OK;
 }
@@ -1111,11 +1166,14 @@ int32_t tdna_shutdown(tdna_ctx *c) {
     if (c->h_status) cudaFreeHost(c->h_status);
     for (cudaEvent_t e : c->ev_copy) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (cudaEvent_t e : c->ev_enc) if (e) cudaEventDestroy(e);
+    if (c->enc_stream) cudaStreamDestroy(c->enc_stream);
     for (cudaEvent_t e : {c->ev_k0, c->ev_k1, c->ev_s1, c->ev_b0})
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_ph)
         if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->pool) cudaMemPoolDestroy(c->pool);
     delete c;
     return TDNA_OK;
 }
@@ -1233,13 +1291,17 @@ int32_t tdna_cancel(tdna_ctx *c) {
 //  - one GPU, host symbols, 8,192+ rows: the upload runs in row chunks on a copy stream while the context's stream packs each
 //    chunk that has arrived into bit-planes AND encodes count kernel (b)'s operand panels for the default configuration (the GPU
 //    would idle through the PCIe time otherwise): both are ready when the last chunk lands.
-static int aln_build(tdna_ctx *c, tdna_aln *a, const uint8_t *symbols, const int32_t *lengths) {
+// hook (optional): called after each row chunk of a chunked upload has been packed and encoded (enqueued), with the chunk's index
+// and rows; chunk_rows > 0 fixes the chunk size (the pipelined pass wants whole bands of row tiles)
+using ChunkHook = std::function<int(int, int64_t, int64_t)>;
+static int aln_build(tdna_ctx *c, tdna_aln *a, const uint8_t *symbols, const int32_t *lengths, const ChunkHook *hook = nullptr, int64_t chunk_rows = 0,
+                     const std::function<int(tdna_aln *)> *pre = nullptr) {
     const int64_t n = a->n, row_stride = a->sym_stride;
     const int32_t L = a->L;
     const size_t sym_bytes = (size_t)(n - 1) * row_stride + L;
     const int G = c->comm.active() ? c->comm.nranks : 1;
     const bool host_sym = !is_device_ptr(symbols);
-    const bool chunked = G == 1 && host_sym && n >= 8192;
+    const bool chunked = G == 1 && host_sym && n >= 8192 && (chunk_rows == 0 || (n + chunk_rows - 1) / chunk_rows <= 15);
     if (G > 1 && n >= 1024 * (int64_t)G && host_sym) {
         const NcclApi *nc = c->comm.api;
         const int64_t rs = (n + G - 1) / G;
@@ -1263,6 +1325,7 @@ static int aln_build(tdna_ctx *c, tdna_aln *a, const uint8_t *symbols, const int
     }
     if (!chunked) {
         CU(cudaStreamSynchronize(c->stream));  // the caller's buffers have been read
+        if (pre) TRY((*pre)(a));
         return pack(a);
     }
     PlaneBits pb;
@@ -1271,33 +1334,64 @@ static int aln_build(tdna_ctx *c, tdna_aln *a, const uint8_t *symbols, const int
     if (!tc_ok) CU(cudaStreamSynchronize(c->stream));
     int *d_err = reinterpret_cast<int *>(c->d_counter);
     CU(cudaMemsetAsync(d_err, 0, 8, c->stream));
+    hc_mark(c, 2);
+    // labels and the plan of a pipelined pass (tdna_analyze_host) go first: their small pageable copies would otherwise queue behind
+    // the symbols on the copy engine (measured: 0.6 ms)
+    int pre_rc = TDNA_OK;
+    if (pre) pre_rc = (*pre)(a);
     const int C = 8;
-    const int64_t R = round_up((n + C - 1) / C, tc::N);
+    const int64_t R = chunk_rows > 0 ? chunk_rows : round_up((n + C - 1) / C, tc::N);
     const int64_t panels_all = round_up(n, tc::N) / tc::N;
     cudaError_t e = cudaSuccess;
-    for (int ch = 0; ch < C && e == cudaSuccess; ch++) {
+    int hook_rc = TDNA_OK;
+    for (int ch = 0; ch < 15 && e == cudaSuccess; ch++) {  // every copy is enqueued first: none waits for a host decision below
         const int64_t r0 = ch * R, r1 = std::min<int64_t>(n, r0 + R);
         if (r0 >= n) break;
         const size_t off = (size_t)r0 * row_stride;
         const size_t bytes = r1 == n ? (size_t)(r1 - r0 - 1) * row_stride + L : (size_t)(r1 - r0) * row_stride;
         e = cudaMemcpyAsync(a->d_sym + off, symbols + off, bytes, cudaMemcpyHostToDevice, c->copy_stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev_copy[ch], c->copy_stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->ev_copy[ch], 0);
+    }
+    hc_mark(c, 3);
+    // A pipelined pass packs and encodes on a stream of its own, so that the small encode kernels run BESIDE the persistent tile
+    // kernels of the earlier chunks instead of between them (0.5 ms on 50,000 x 658); the pass's stream waits for a chunk's operands.
+    const bool side = hook != nullptr && tc_ok && pre_rc == TDNA_OK;
+    cudaStream_t es = side ? c->enc_stream : c->stream;
+    if (side) {  // buffers, lengths and the zeroed flags were prepared on the pass's stream
+        e = cudaEventRecord(c->ev_enc[15], c->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(es, c->ev_enc[15], 0);
+    }
+    for (int ch = 0; ch < 15 && e == cudaSuccess && hook_rc == TDNA_OK && pre_rc == TDNA_OK; ch++) {
+        const int64_t r0 = ch * R, r1 = std::min<int64_t>(n, r0 + R);
+        if (r0 >= n) break;
+        if (ch == 1) hc_mark(c, 4);
+        e = cudaStreamWaitEvent(es, c->ev_copy[ch], 0);
         if (e != cudaSuccess) break;
         const int64_t prows = std::min<int64_t>(a->npad, r0 + R) - r0;  // whole 64-row panels (the last chunk runs to npad)
         const int64_t total = prows * a->W;
-        pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(a->d_sym, a->d_len, n, r0, prows, row_stride, a->W, a->P, L, pb, a->d_planes, d_err);
+        pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, es>>>(a->d_sym, a->d_len, n, r0, prows, row_stride, a->W, a->P, L, pb, a->d_planes, d_err);
         c->launches++;
-        if (tc_ok) tc_encode_range(a, c->stream, r0 / tc::N, std::min<int64_t>(panels_all, (r0 + R) / tc::N) - r0 / tc::N);
+        if (tc_ok) tc_encode_range(a, es, r0 / tc::N, std::min<int64_t>(panels_all, (r0 + R) / tc::N) - r0 / tc::N);
+        if (side) {
+            e = cudaEventRecord(c->ev_enc[ch], es);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->ev_enc[ch], 0);
+            if (e != cudaSuccess) break;
+        }
+        if (hook && tc_ok) hook_rc = (*hook)(ch, r0, r1);
     }
+    if (pre_rc != TDNA_OK) hook_rc = pre_rc;
+    hc_mark(c, 5);
     int flags[6] = {0, 0, 0, 0, 0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(flags, d_err, 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess && tc_ok) e = cudaMemcpyAsync(flags + 2, a->d_tcflag, 12, cudaMemcpyDeviceToHost, c->stream);
+    if (side) cudaStreamSynchronize(es);
     cudaError_t e2 = cudaStreamSynchronize(c->copy_stream);  // whatever happened: no copy outlives the call
     cudaError_t e3 = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : e3;
+    hc_mark(c, 6);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TDNA_E_CUDA, cudaGetErrorString(e));
+    if (hook_rc != TDNA_OK) return hook_rc;
     if (flags[0] || flags[2]) return fail(TDNA_E_SYMBOL, "a symbol outside the normalised alphabet ACGT RYKMSWBDHVN - _ ?");
     a->packed = true;
     if (tc_ok) {
@@ -1312,7 +1406,8 @@ static int aln_build(tdna_ctx *c, tdna_aln *a, const uint8_t *symbols, const int
     return TDNA_OK;
 }
 
-static int aln_new(tdna_ctx *c, const uint8_t *symbols, int64_t n, int32_t L, int64_t row_stride, const int32_t *lengths, tdna_aln **out) {
+static int aln_new(tdna_ctx *c, const uint8_t *symbols, int64_t n, int32_t L, int64_t row_stride, const int32_t *lengths, tdna_aln **out,
+                   const std::function<int(tdna_aln *)> *pre = nullptr, const ChunkHook *hook = nullptr, int64_t chunk_rows = 0, const int *cfg = nullptr) {
     if (!c || !symbols || !out) return fail(TDNA_E_ARG, "null argument");
     if (n < 1 || n > 0x7fffffff) return fail(TDNA_E_ARG, "n out of range");
     if (L < 1 || L > 65535) return fail(TDNA_E_ARG, "L must be in [1, 65535] (two 16-bit counts share an accumulator)");
@@ -1333,7 +1428,8 @@ static int aln_new(tdna_ctx *c, const uint8_t *symbols, int64_t n, int32_t L, in
     a->row_begin = 0;
     a->row_end = n;
     a->hist_size = c->opt_hist_slots;
-    int rc = aln_build(c, a, symbols, lengths);
+    if (cfg) { a->mode = cfg[0]; a->min_overlap = cfg[1]; a->ambig = cfg[2]; }  // tdna_analyze_host: planes and operands are built once, for the right mode
+    int rc = aln_build(c, a, symbols, lengths, hook, chunk_rows, pre);
     if (rc != TDNA_OK) {
         std::string keep = g_err;
         tdna_alignment_destroy(a);
@@ -1351,24 +1447,244 @@ int32_t tdna_alignment_create(tdna_ctx *c, const uint8_t *symbols, int64_t n, in
 
 // Create + labels + configuration + analysis in ONE call from host buffers: one downcall for a host that has just loaded or edited
 // its list (the upload itself is chunked and overlapped with packing / operand encoding inside tdna_alignment_create's path).
+// ---- the pass pipelined with the upload ---------------------------------------------------------------------------------------
+// tdna_analyze_host on one GPU, Best Match rows from count kernel (b): the upload goes in row chunks of whole BANDS (64 row tiles);
+// as soon as a chunk has been packed and encoded, the seed items whose blocks have all arrived run, the thresholds of the rows so
+// far are rebuilt (they only ever decrease: every earlier test stays valid) and ONE region launch computes the tiles whose column
+// tile lies in that chunk -- per band, a run of consecutive slots of the usual numbering.  The PCIe time hides behind the tiles of
+// the earlier chunks.  Which instantiation runs (plain / GENERAL) is decided from the FIRST chunk's flags; if a later chunk
+// contradicts it (its first ambiguity letter, too many internal gaps for the four-dimension code), or a buffer overflows, the
+// result is dropped and the ordinary pass runs on the alignment, which is complete and resident by then.
+static int set_labels_impl(tdna_aln *a, const int32_t *species_id, const int32_t *genus_id, const int32_t *epithet_rank, const int32_t *fullname_rank,
+                           bool wait);
+static int ensure_stream_state(tdna_aln *a);
+static int stream_merge(tdna_aln *a, const int32_t *cq, const int32_t *cj, const double *cd, long long ncand, const int32_t *inval,
+                        const int32_t *flags, bool counts_ready);
+struct Pipeline {
+    bool active = false;      // region launches are going out
+    bool abandoned = false;   // decided against (or gave up): the ordinary pass follows the upload
+    int64_t chunk_rows = 0;
+    int bands_per_chunk = 1, nchunks = 0;
+    std::vector<int64_t> seed_off;                 // [nchunks + 1] into the chunk-ordered seed list
+    std::vector<int64_t> reg_off, reg_n, reg_items;  // per chunk: offset of its tables in d_plbuf (int64 words), runs, items
+    int2 *d_seeds = nullptr;
+    int64_t *d_tables = nullptr;
+};
+
+static int pipeline_plan(tdna_aln *a, Pipeline &pl) {
+    tdna_ctx *c = a->ctx;
+    const int band = TC_BAND;
+    const int nrt = (int)(round_up(a->n, tc::M) / tc::M);
+    const int64_t nct = round_up(a->n, tc::N) / tc::N;
+    const int nbands = (nrt + band - 1) / band;
+    const int maxc = std::max(1, c->opt_pipeline_chunks);
+    pl.bands_per_chunk = (nbands + maxc - 1) / maxc;
+    pl.chunk_rows = (int64_t)pl.bands_per_chunk * band * tc::M;
+    pl.nchunks = (nbands + pl.bands_per_chunk - 1) / pl.bands_per_chunk;
+    // the seed list, ordered by the chunk in which BOTH blocks of an item have arrived
+    TRY(build_seed_list(a));
+    const int64_t blocks_per_chunk = pl.chunk_rows / tc::N;
+    std::vector<std::vector<int2>> by_chunk((size_t)pl.nchunks);
+    for (const int2 &it : a->h_seedlist) {
+        const int64_t blk = std::max<int64_t>(it.x / 2, it.y);
+        by_chunk[(size_t)std::min<int64_t>(pl.nchunks - 1, blk / blocks_per_chunk)].push_back(it);
+    }
+    std::vector<int2> ordered;
+    pl.seed_off.assign((size_t)pl.nchunks + 1, 0);
+    for (int ch = 0; ch < pl.nchunks; ch++) {
+        ordered.insert(ordered.end(), by_chunk[ch].begin(), by_chunk[ch].end());
+        pl.seed_off[ch + 1] = (int64_t)ordered.size();
+    }
+    // the regions: for chunk ch (bands [B0, B1), column tiles [cj0, cj1)), one run of slot pairs per band b < B1
+    std::vector<int64_t> pre((size_t)nbands + 1, 0);
+    auto before = [&](int b, int64_t crel) {  // slots of band b before its column crel (relative to the band's first column)
+        const int64_t tjmin = ((int64_t)b * band) >> 1, cols = std::max<int64_t>(nct - tjmin, 0), tri = std::min<int64_t>(cols, band >> 1);
+        return crel <= tri ? crel * (crel + 1) : tri * (tri + 1) + (crel - tri) * band;
+    };
+    for (int b = 0; b < nbands; b++) {
+        const int64_t tjmin = ((int64_t)b * band) >> 1, cols = std::max<int64_t>(nct - tjmin, 0);
+        pre[b + 1] = pre[b] + before(b, cols);
+    }
+    std::vector<int64_t> tables;
+    pl.reg_off.assign((size_t)pl.nchunks, 0);
+    pl.reg_n.assign((size_t)pl.nchunks, 0);
+    pl.reg_items.assign((size_t)pl.nchunks, 0);
+    for (int ch = 0; ch < pl.nchunks; ch++) {
+        const int B0 = ch * pl.bands_per_chunk, B1 = std::min(nbands, B0 + pl.bands_per_chunk);
+        const int64_t cj0 = ((int64_t)B0 * band) >> 1, cj1 = std::min<int64_t>(nct, ((int64_t)B1 * band) >> 1);
+        std::vector<int64_t> start, prefix(1, 0);
+        for (int b = 0; b < B1; b++) {
+            const int64_t tjmin = ((int64_t)b * band) >> 1;
+            const int64_t lo = std::max(cj0, tjmin) - tjmin, hi = cj1 - tjmin;
+            if (hi <= lo) continue;
+            const int64_t s0 = pre[b] + before(b, lo), s1 = pre[b] + before(b, hi);
+            if (s1 <= s0) continue;
+            start.push_back(s0 / 2);  // slot counts are even: pairs (2u, 2u + 1) never straddle a run
+            prefix.push_back(prefix.back() + (s1 - s0) / 2);
+        }
+        pl.reg_off[ch] = (int64_t)tables.size();
+        pl.reg_n[ch] = (int64_t)start.size();
+        pl.reg_items[ch] = prefix.back();
+        tables.insert(tables.end(), start.begin(), start.end());
+        tables.insert(tables.end(), prefix.begin(), prefix.end());
+    }
+    const size_t tbytes = tables.size() * 8, sbytes = ordered.size() * sizeof(int2);
+    if (a->d_plbuf) { CU(DFREE(a->d_plbuf)); a->d_plbuf = nullptr; }
+    CU(DMALLOC(&a->d_plbuf, tbytes + sbytes + 16));
+    pl.d_tables = reinterpret_cast<int64_t *>(a->d_plbuf);
+    pl.d_seeds = reinterpret_cast<int2 *>(reinterpret_cast<char *>(a->d_plbuf) + tbytes);
+    CU(cudaMemcpyAsync(pl.d_tables, tables.data(), tbytes, cudaMemcpyHostToDevice, c->stream));
+    if (sbytes) CU(cudaMemcpyAsync(pl.d_seeds, ordered.data(), sbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // stack-lifetime host buffers
+    return TDNA_OK;
+}
+
+static void pipeline_clear(tdna_aln *a) {
+    a->pl_reg_start = a->pl_reg_prefix = nullptr;
+    a->pl_reg_n = 0;
+    a->pl_reg_items = 0;
+    a->pl_seed_list = nullptr;
+    a->pl_seed_pairs = -1;
+    a->pl_general = -1;
+}
+
+static int pipeline_chunk(tdna_aln *a, Pipeline &pl, int ch, int64_t r0, int64_t r1) {
+    tdna_ctx *c = a->ctx;
+    if (pl.abandoned) return TDNA_OK;
+    if (ch == 0) {
+        int f[3] = {0, 0, 0};
+        CU(cudaMemcpyAsync(f, a->d_tcflag, 12, cudaMemcpyDeviceToHost, c->stream));  // (the stream waits for the first chunk's operands)
+        CU(cudaStreamSynchronize(c->stream));  // ~ the first chunk's upload: every later copy is in flight already
+        if (f[0]) return TDNA_OK;              // a symbol outside the alphabet: aln_build reports it
+        if (a->kmode != KM_K2P && a->tc_dims == 4 && (int64_t)f[2] * 2000 > (r1 - r0) * (int64_t)a->L) { pl.abandoned = true; return TDNA_OK; }  // see tc_too_gappy
+        if (!a->tc_maps || a->tc_pair) { pl.abandoned = true; return TDNA_OK; }  // region launches exist for the multicast pairs only
+        a->pl_general = f[1] ? 1 : 0;
+        TRY(ensure_stream_state(a));
+        a->sp.species = a->d_species;
+        a->sp.genus = a->d_genus;
+        a->sp.epi = a->d_epi;
+        a->sp.full = a->d_full;
+        a->sp.panel_range = a->d_panel_range;
+        a->sp.want = TDNA_WANT_BEST_MATCH;
+        stream_init_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, c->stream>>>(a->sp, a->n, a->d_needc);
+        c->launches++;
+        CU(cudaGetLastError());
+        a->last_kernel = TDNA_KERNEL_TENSOR;
+        c->ev_valid = false;
+        pl.active = true;
+    }
+    if (ch >= pl.nchunks) return TDNA_OK;
+    a->pl_seed_list = pl.d_seeds + pl.seed_off[ch];
+    a->pl_seed_pairs = (int)(pl.seed_off[ch + 1] - pl.seed_off[ch]);
+    a->pl_reg_n = 0;
+    if (a->pl_seed_pairs > 0) TRY(launch_tc<false>(a, 0, 0, 1, nullptr));
+    const int64_t rows = std::min<int64_t>(a->n, r1);
+    stream_thr_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c->stream>>>(a->sp, rows);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (pl.reg_items[ch] > 0) {
+        a->pl_reg_start = pl.d_tables + pl.reg_off[ch];
+        a->pl_reg_prefix = a->pl_reg_start + pl.reg_n[ch];
+        a->pl_reg_n = (int)pl.reg_n[ch];
+        a->pl_reg_items = pl.reg_items[ch];
+        TRY(launch_tc<false>(a, 1, 0, 1, nullptr));
+        a->pl_reg_n = 0;
+    }
+    return TDNA_OK;
+}
+
+// after the upload: the queue -> records -> rows.  TDNA_E_TOO_LARGE: a buffer overflowed (the ordinary pass retries with larger ones)
+static int pipeline_finish(tdna_aln *a, tdna_analysis *io) {
+    tdna_ctx *c = a->ctx;
+    a->pl_seed_pairs = -1;
+    TRY(tc_resolve_queue(a));
+    struct { unsigned long long ncand; int overflow; int pad; unsigned long long ncls[2]; unsigned long long nedge; unsigned long long qn; } h;
+    CU(cudaMemcpyAsync(&h, a->d_stream_u64, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (h.overflow) {
+        a->need_cand = (long long)h.ncand;
+        a->need_queue = (long long)h.qn;
+        return TDNA_E_TOO_LARGE;
+    }
+    a->last_ncand = (long long)h.ncand;
+    a->last_queue = (long long)h.qn;
+    a->last_ncls[0] = a->last_ncls[1] = a->local_ncls[0] = a->local_ncls[1] = 0;
+    a->last_nedge = a->local_nedge = 0;
+    TRY(ensure_res(a, a->n));
+    TRY(stream_merge(a, a->sp.cq, a->sp.cj, a->sp.cd, (long long)h.ncand, a->sp.inval, a->sp.flags, true));
+    if (io->rows) CU(cudaMemcpyAsync(io->rows, a->d_res, (size_t)a->n * sizeof(tdna_row_result), cudaMemcpyDefault, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    io->n_intra = io->n_inter = io->n_edges = io->n_intra_local = io->n_inter_local = io->n_edges_local = 0;
+    io->n_hist_intra = io->n_hist_inter = io->hist_intra_pushes = io->hist_inter_pushes = 0;
+    c->pipelined_passes++;
+    return TDNA_OK;
+}
+
+// Create + labels + configuration + analysis in ONE call from host buffers: one downcall for a host that has just loaded or edited
+// its list.  Configuration and labels go first (they are known before the symbols arrive: the planes and operands are built once,
+// for the right mode), the upload is chunked and overlapped with packing / operand encoding, and -- Best Match rows on one GPU -- with
+// the pass itself (above).
 int32_t tdna_analyze_host(tdna_ctx *c, const tdna_host_list *in, tdna_analysis *io, tdna_aln **aln_out) {
     if (!c || !in || !io) return fail(TDNA_E_ARG, "null argument");
     if (aln_out) *aln_out = nullptr;
     if (in->mode < 0 || in->mode > 2) return fail(TDNA_E_ARG, "mode must be 0, 1 or 2");
     const bool labels = in->species_id && in->genus_id && in->epithet_rank && in->fullname_rank;
+    const bool want_pipeline = labels && io->want == TDNA_WANT_BEST_MATCH && !c->comm.active() && c->opt_best_match_path != TDNA_PATH_DENSE &&
+                               c->opt_count_kernel != TDNA_KERNEL_POPC && in->n >= 16384 && in->n <= (1 << 17) && in->L < 4096 &&
+                               (in->mode == TDNA_PDM_K2P || (in->mode == TDNA_PDM_UNCORRECTED && in->ambiguous_allowed)) &&
+                               in->symbols && !is_device_ptr(in->symbols) && !(TC_BAND & 1) && c->opt_pipeline_chunks > 0;
+    for (double &x : c->hc_t) x = 0;
+    hc_mark(c, 0);
+    Pipeline pl;
+    const int cfg[3] = {in->mode, in->min_overlap, in->ambiguous_allowed ? 1 : 0};
+    const std::function<int(tdna_aln *)> pre = [&](tdna_aln *a) -> int {
+        if (labels) TRY(set_labels_impl(a, in->species_id, in->genus_id, in->epithet_rank, in->fullname_rank, false));
+        if (want_pipeline) TRY(pipeline_plan(a, pl));
+        hc_mark(c, 1);
+        return TDNA_OK;
+    };
+    tdna_aln *built = nullptr;
+    const ChunkHook hook = [&](int ch, int64_t r0, int64_t r1) -> int {
+        // (the alignment under construction: aln_build hands no pointer, the plan was made on it)
+        return built ? pipeline_chunk(built, pl, ch, r0, r1) : TDNA_OK;
+    };
     tdna_aln *a = nullptr;
-    TRY(aln_new(c, in->symbols, in->n, in->L, in->row_stride, in->lengths, &a));
-    int rc = TDNA_OK;
-    if (labels) rc = tdna_alignment_set_labels(a, in->species_id, in->genus_id, in->epithet_rank, in->fullname_rank);
+    const std::function<int(tdna_aln *)> pre2 = [&](tdna_aln *x) -> int { built = x; return pre(x); };
+    int64_t chunk_rows = 0;
+    if (want_pipeline) {  // whole bands of row tiles, at most eight chunks (pipeline_plan makes the same choice)
+        const int64_t band_rows = (int64_t)TC_BAND * tc::M, nbands = (in->n + band_rows - 1) / band_rows;
+        const int64_t maxc = std::max(1, c->opt_pipeline_chunks);
+        chunk_rows = ((nbands + maxc - 1) / maxc) * band_rows;
+    }
+    int rc = aln_new(c, in->symbols, in->n, in->L, in->row_stride, in->lengths, &a, &pre2, want_pipeline ? &hook : nullptr, chunk_rows, cfg);
+    if (rc != TDNA_OK) return rc;
+    bool done = false;
+    if (pl.active) {
+        // the first chunk's verdict must hold for the whole list: the operands were kept (not too gappy for their code) and no
+        // ambiguity letter turned up after a plain start
+        const bool consistent = a->tc_state == 1 && !(a->tc_has_amb && a->pl_general == 0);
+        if (consistent) {
+            rc = pipeline_finish(a, io);
+            done = rc == TDNA_OK;
+            if (rc == TDNA_E_TOO_LARGE) rc = TDNA_OK;  // the ordinary pass below grows the buffers
+        }
+    }
+    hc_mark(c, 7);
+    pipeline_clear(a);
     if (rc == TDNA_OK) rc = tdna_set_config(a, in->mode, in->min_overlap, in->ambiguous_allowed);
-    if (rc == TDNA_OK) rc = tdna_analyze(a, io);
+    if (rc == TDNA_OK && !done) {
+        rc = tdna_analyze(a, io);
+    }
+    hc_mark(c, 8);
     if (rc != TDNA_OK || !aln_out) {
         std::string keep = g_err;
         tdna_alignment_destroy(a);
         g_err = keep;
+        hc_mark(c, 9);
         return rc;
     }
     *aln_out = a;
+    hc_mark(c, 9);
     return TDNA_OK;
 }
 
@@ -1380,7 +1696,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
                     a->d_needc, a->d_panel_range, a->d_range_rows, a->d_range_cols, a->sp.q, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcflag, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_seedlist, a->d_cursor, a->d_lj, a->d_ld,
-                    a->x_send, a->x_recv, a->x_state, a->d_hkey[0], a->d_hkey[1], a->d_hcnt[0], a->d_hcnt[1], a->d_hctr, a->d_hent, a->d_gslot, a->d_gmem, a->d_gstart};
+                    a->x_send, a->x_recv, a->x_state, a->d_hkey[0], a->d_hkey[1], a->d_hcnt[0], a->d_hcnt[1], a->d_hctr, a->d_hent, a->d_gslot, a->d_gmem, a->d_gstart, a->d_plbuf};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
     delete a;
@@ -1389,6 +1705,12 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
 
 int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const int32_t *genus_id, const int32_t *epithet_rank,
                                   const int32_t *fullname_rank) {
+    return set_labels_impl(a, species_id, genus_id, epithet_rank, fullname_rank, true);
+}
+// wait = false (tdna_analyze_host): everything is enqueued and the call returns; the caller synchronises the stream before it
+// returns to ITS caller (the label arrays may be pinned memory, which an asynchronous copy reads later)
+static int set_labels_impl(tdna_aln *a, const int32_t *species_id, const int32_t *genus_id, const int32_t *epithet_rank, const int32_t *fullname_rank,
+                           bool wait) {
     if (!a || !species_id || !genus_id || !epithet_rank || !fullname_rank) return fail(TDNA_E_ARG, "null argument");
     tdna_ctx *c = a->ctx;
     CU(cudaSetDevice(c->device));
@@ -1440,7 +1762,8 @@ int32_t tdna_alignment_set_labels(tdna_aln *a, const int32_t *species_id, const 
     }
     a->class_reach = -1;
     a->tcprefix_reach = -1;
-    CU(cudaStreamSynchronize(c->stream));  // do not return before the copies have read the caller's arrays
+    const bool device_labels = is_device_ptr(species_id) || is_device_ptr(genus_id);  // their host copies are still in flight
+    if (wait || device_labels) CU(cudaStreamSynchronize(c->stream));  // do not return before the copies have read the caller's arrays
     a->has_labels = true;
     a->seedlist_valid = false;
     a->genus_lists_valid = false;
@@ -1713,7 +2036,7 @@ static int ensure_stream_state(tdna_aln *a) {
     if (a->stream_alloc) return TDNA_OK;
     tdna_ctx *c = a->ctx;
     size_t n = (size_t)a->n;
-    long long cap = (long long)n * 64;
+    long long cap = (long long)((double)n * c->hint_cand_per_row);
     if (cap < (1ll << 22)) cap = 1ll << 22;
     if (cap * 16 > c->budget / 2) cap = c->budget / 32;
     StreamParams &sp = a->sp;
@@ -1728,7 +2051,7 @@ static int ensure_stream_state(tdna_aln *a) {
     CU(DMALLOC(&sp.cd, (size_t)cap * 8));
     // kernel (b)'s queue holds every pair that passes the SEEDED threshold of either of its rows (about four times the final
     // candidates): 256 per row, 16 bytes each
-    long long qcap = (long long)n * 256;
+    long long qcap = (long long)((double)n * c->hint_queue_per_row);
     if (qcap < (1ll << 22)) qcap = 1ll << 22;
     if (qcap * 16 > c->budget / 2) qcap = c->budget / 32;
     CU(DMALLOC(&sp.q, (size_t)qcap * 16));
@@ -1760,6 +2083,10 @@ static bool grow_stream_buffers(tdna_aln *a) {
     a->need_cand = a->need_queue = 0;
     if (cap == sp.cap && qcap == sp.qcap) return false;
     if (cap * 16 + qcap * 16 > c->budget / 4) return false;
+    if (a->n > 0) {  // the next alignment on this context starts there (bounded: 4,096 entries per row)
+        c->hint_cand_per_row = std::min(4096.0, std::max(c->hint_cand_per_row, (double)cap / (double)a->n));
+        c->hint_queue_per_row = std::min(4096.0, std::max(c->hint_queue_per_row, (double)qcap / (double)a->n));
+    }
     if (cap != sp.cap) {
         DFREE(sp.cq); DFREE(sp.cj); DFREE(sp.cd);
         sp.cq = sp.cj = nullptr; sp.cd = nullptr;
@@ -2876,6 +3203,10 @@ int32_t tdna_set_option(tdna_ctx *c, int32_t key, int64_t value) {
             c->comm.enabled = value != 0;
             c->comm.force = value == 2;
             return TDNA_OK;
+        case TDNA_OPT_PIPELINE_CHUNKS:
+            if (value < 0 || value > 15) return fail(TDNA_E_ARG, "pipeline chunks: 0 (off) to 15");
+            c->opt_pipeline_chunks = (int)value;
+            return TDNA_OK;
         case TDNA_OPT_SEGMENT_ITEMS:
             if (value < 0) return fail(TDNA_E_ARG, "segment items: 0 (automatic) or a positive count");
             c->opt_segment_items = value;
@@ -3129,6 +3460,16 @@ int32_t tdna_multi_phase_ms(tdna_ctx *c, float *ms, int32_t cap, int32_t *n_out)
     CU(cudaStreamSynchronize(c->stream));
     int k = 0;
     for (; k + 1 < c->n_ph && k < cap; k++) CU(cudaEventElapsedTime(&ms[k], c->ev_ph[k], c->ev_ph[k + 1]));
+    *n_out = k;
+    return TDNA_OK;
+}
+
+int64_t tdna_pipelined_passes(tdna_ctx *c) { return c ? c->pipelined_passes : 0; }
+
+int32_t tdna_host_call_phase_ms(tdna_ctx *c, double *ms, int32_t cap, int32_t *n_out) {
+    if (!c || !ms || !n_out) return fail(TDNA_E_ARG, "null argument");
+    int k = 0;
+    for (int i = 1; i < 10 && k < cap; i++, k++) ms[k] = (c->hc_t[i] > 0 && c->hc_t[0] > 0) ? c->hc_t[i] - c->hc_t[0] : -1.0;
     *n_out = k;
     return TDNA_OK;
 }

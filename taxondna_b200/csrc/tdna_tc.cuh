@@ -53,6 +53,11 @@ struct Params {
     const int64_t *prefix;  // bulk phase: [nbands + 1] tile slots before band b
     int64_t num_tiles, t_offset, t_stride;  // this launch's k-th work item is global item ((k / unit) * t_stride + t_offset) * unit + k % unit
     int64_t k_base;         // first work item of this launch in the part's own list (a long pass goes out in segments)
+    // a REGION launch (the pass pipelined with the upload, tdna_analyze_host): the launch's items are reg_n runs of consecutive slot
+    // pairs -- per band, the columns of the row chunk that has just arrived; item l lies in run k with reg_prefix[k] <= l <
+    // reg_prefix[k + 1] and is slot pair reg_start[k] + l - reg_prefix[k]
+    const int64_t *reg_start, *reg_prefix;
+    int reg_n;
     int unit;               // work items per scheduling unit (parts take units cyclically: balanced in work AND in candidates)
     tdna_counts *counts;    // verification mode: n x n counts (row-major), else null
     int extras;             // stream mode: classes / edges wanted (StreamParams::want beyond Best Match)
@@ -153,7 +158,15 @@ template <int CL> __device__ __forceinline__ bool my_tile(const Params &p, int64
         return !p.class_only || ((int64_t)tj * N <= (int64_t)ti * M + (M - 1) + p.class_reach && may_hold_class_pairs(p, ti, tj, M));
     } else {
         const int64_t l = p.k_base + (int64_t)(blockIdx.x >> 1) + k * (gridDim.x >> 1);
-        const int64_t u = ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit;
+        int64_t u;
+        if (p.reg_n) {
+            int lo = 0, hi = p.reg_n;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(p.reg_prefix + mid) <= l) lo = mid; else hi = mid;
+            }
+            u = __ldg(p.reg_start + lo) + (l - __ldg(p.reg_prefix + lo));
+        } else u = ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit;
         bool ok = slot_coords(p, p.prefix, 2 * u, ti, tj);
         if (ok && p.class_only) ok = (int64_t)tj * N <= (int64_t)ti * M + (2 * M - 1) + p.class_reach && may_hold_class_pairs(p, ti, tj, 2 * M);  // the same answer in both CTAs of the pair
         ti += (int)rank;

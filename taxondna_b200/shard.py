@@ -1,12 +1,12 @@
-"""Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL over NVLink on GPUs, gloo in the
-CPU tests).  Two decompositions of the pair space:
+"""Host-side helpers for multi-GPU layouts that run OUTSIDE the library (one process per GPU, torch.distributed; NCCL over NVLink on
+GPUs, gloo in the CPU tests).  The streaming passes need none of this any more: with a communicator (tdna_comm_init /
+tdna_init_multi) the library shares a whole-range call among the ranks itself -- units of 64 tile pairs dealt cyclically, the
+candidate records routed to the rank that owns their row.  What is left here:
 
-* streaming Best Match: rank r takes tiles r, r+world, ... of the triangle (tdna_best_match_part);
-  the ranks then exchange their candidate records and per-row counters ONCE (exchange_candidates)
-  and every rank finalises all rows from the union (tdna_best_match_merge).
-* matrix-shaped outputs: rank r owns the contiguous row band row_band(n, r, world) against every
-  column; per-row records are all_gathered (gather_rows), variable-length outputs concatenated
-  (gather_varlen)."""
+* matrix-shaped outputs: rank r owns the contiguous row band row_band(n, r, world) against every column; per-row records are
+  all_gathered (gather_rows), variable-length outputs concatenated (gather_varlen);
+* exchange_candidates: the gathered exchange of the low-level part / merge entry points (tdna_best_match_part ->
+  tdna_best_match_merge), kept for hosts that run the exchange themselves and exercised over gloo by tests/test_multigpu_cpu.py."""
 import numpy as np
 
 TILE = 128  # row bands start on tile boundaries (include/taxondna_cuda.h: tdna_set_row_range)

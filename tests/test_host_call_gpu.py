@@ -14,8 +14,22 @@ pytestmark = pytest.mark.gpu
 def ctx():
     import taxondna_b200 as t
     c = t.Context(0)
+    c.set_option(t.OPT_PIPELINE_CHUNKS, 8)  # the pass pipelined with the upload (off by default: it measured slower) is what these tests stress
     yield c
     c.close()
+
+
+def test_default_is_one_pass_after_the_upload():
+    import taxondna_b200 as t
+    c = t.Context(0)
+    try:
+        sym, labels = labelled("H", 17000)
+        ref = separate(c, sym, labels, 0, 300)
+        got = t.best_match_host(c, sym, labels, 0, 300)
+        assert got.tobytes() == ref["rows"].tobytes()
+        assert c.pipelined_passes() == 0
+    finally:
+        c.close()
 
 
 def labelled(cfg, n, seed=None):
@@ -34,12 +48,32 @@ def separate(ctx, sym, labels, mode, mo, lengths=None):
     return r
 
 
-@pytest.mark.parametrize("cfg,n,mode", [("H", 20000, 0), ("H", 16500, 1), ("Hg", 17000, 0), ("Hg", 17000, 1), ("H", 3000, 0)])
+@pytest.mark.parametrize("cfg,n,mode", [("H", 20000, 0), ("H", 16500, 1), ("Hg", 17000, 0), ("Hg", 17000, 1), ("H", 3000, 0), ("H", 41000, 0), ("Hg", 33000, 1)])
 def test_one_call_equals_the_separate_calls(ctx, cfg, n, mode):
     import taxondna_b200 as t
     sym, labels = labelled(cfg, n)
     ref = separate(ctx, sym, labels, mode, 300)
+    before = ctx.pipelined_passes()
     got = t.best_match_host(ctx, sym, labels, mode, 300)
+    assert got.tobytes() == ref["rows"].tobytes()
+    # 16,384+ rows: the pass ran in region launches while the row chunks were still arriving (Hg in p: the first chunk's internal
+    # gaps send the list to the five-dimension code, i.e. to the ordinary pass)
+    if n >= 16384 and not (cfg == "Hg" and mode == 0):
+        assert ctx.pipelined_passes() == before + 1
+    if n < 16384:
+        assert ctx.pipelined_passes() == before
+
+
+def test_a_shuffled_list_overflows_the_pipelined_pass_and_still_matches(ctx):
+    """Rows in random order: the diagonal blocks hold unrelated rows, the seeded thresholds stay loose, the queue overflows -- the
+    pipelined pass gives up and the ordinary pass (larger buffers, kernel (a), the dense path) takes over."""
+    import taxondna_b200 as t
+    sym, labels = labelled("H", 17000)
+    perm = np.random.default_rng(9).permutation(sym.shape[0])
+    sym = np.ascontiguousarray(sym[perm])
+    labels = [np.ascontiguousarray(l[perm]) for l in labels]
+    ref = separate(ctx, sym, labels, 0, 300)
+    got = t.best_match_host(ctx, sym, labels, 0, 300)
     assert got.tobytes() == ref["rows"].tobytes()
 
 
@@ -54,8 +88,10 @@ def test_letters_that_arrive_late_switch_the_instantiation(ctx):
     block[m] = rng.choice(np.frombuffer(b"RYKMSWBDHVN", dtype=np.uint8), size=int(m.sum()))
     sym[late] = block
     ref = separate(ctx, sym, labels, 0, 300)
+    before = ctx.pipelined_passes()
     got = t.best_match_host(ctx, sym, labels, 0, 300)
     assert got.tobytes() == ref["rows"].tobytes()
+    assert ctx.pipelined_passes() == before  # the plain start was contradicted by the last chunk: the ordinary pass ran
 
 
 def test_ragged_rows_and_the_returned_alignment(ctx):
