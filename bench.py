@@ -50,6 +50,9 @@ WORKLOADS = {
     # H's shape with C4's noise (8 % '?', 8 % '-', 4 % IUPAC letters): no tile is free of gaps / ambiguity letters (the GENERAL instantiation)
     "Hg": dict(config="Hg", mode=0, kind="bestmatch", desc="synthetic COI with 20% ?/-/IUPAC noise, uncorrected p: streaming per-query Best Match summaries"),
     "HgK": dict(config="Hg", mode=1, kind="bestmatch", desc="synthetic COI with 20% ?/-/IUPAC noise, K2P: streaming per-query Best Match summaries"),
+    # transversions only (PDM_TRANS_ONLY): six K-bytes per site on count kernel (b), exact for every letter
+    "Ht": dict(config="H", mode=2, kind="bestmatch", desc="synthetic COI, transversions only: streaming per-query Best Match summaries"),
+    "Hgt": dict(config="Hg", mode=2, kind="bestmatch", desc="synthetic COI with 20% ?/-/IUPAC noise, transversions only: streaming per-query Best Match summaries"),
 }
 POPC_PER_PAIR_WORD = {0: 2, 1: 4, 2: 2}  # C = 2 (p), 4 (K2P), 2 (trans-only)
 

@@ -345,10 +345,10 @@ enum { TDNA_OPT_BEST_MATCH_PATH = 1, /* TDNA_PATH_*: how tdna_best_match compute
                                         2: the collective path even when the communicator has ONE rank (tests on a one-GPU box) */ };
 enum { TDNA_KERNEL_AUTO = 0,   /* the faster eligible one (A/B on ncu evidence) */
        TDNA_KERNEL_POPC = 1,   /* (a) bit-planes + LOP3/POPC, any alphabet, any mode */
-       TDNA_KERNEL_TENSOR = 2  /* (b) one-hot int8 contraction on tcgen05/TMEM: uncorrected p with ambiguity allowed, or K2P;
-                                  L < 4096.  Pairs that involve IUPAC ambiguity letters are only BOUNDED by it (enough for the
-                                  candidate filter); their exact counts come from the bit-planes.  TDNA_E_STATE if the
-                                  configuration is not eligible */ };
+       TDNA_KERNEL_TENSOR = 2  /* (b) int8 contraction on tcgen05/TMEM: uncorrected p with ambiguity allowed, K2P, or transversions
+                                  only; L < 4096.  In p and K2P, pairs that involve IUPAC ambiguity letters are only BOUNDED by it
+                                  (enough for the candidate filter) and their exact counts come from the bit-planes; transversions
+                                  only is exact for every letter.  TDNA_E_STATE if the configuration is not eligible */ };
 enum { TDNA_PATH_AUTO = 0,   /* streaming; falls back to the dense path if the candidate buffer overflows */
        TDNA_PATH_DENSE = 1,  /* materialise row bands of the fp64 matrix, sweep them */
        TDNA_PATH_STREAM = 2  /* streaming only (TDNA_E_TOO_LARGE on overflow) */ };
@@ -433,8 +433,8 @@ int32_t tdna_time_matrix_kernel(tdna_aln *aln, int32_t reps, float *ms_per_launc
  * row symbol x and a column symbol y contribute W - (W-1)[x == y] to the int32 accumulator.  Host arithmetic only (no device). */
 int32_t tdna_tensor_code(int32_t L, int32_t dims, int32_t *code, uint32_t *W);
 int32_t tdna_last_count_kernel(tdna_aln *aln);
-/* Symbol dimensions per site of the one-hot operands count kernel (b) built for this alignment (5, or 4 when no row has an internal
- * gap / in K2P mode); 0 if they have not been built.  The roofline's algorithmic work per pair is 2 * dims * L int8 operations. */
+/* K-dimensions per site of the operands count kernel (b) built for this alignment (5, or 4 when no row has an internal gap / in K2P
+ * mode; 6 for transversions only); 0 if they have not been built.  The roofline's algorithmic work per pair is 2 * dims * L int8 operations. */
 int32_t tdna_tensor_dims(tdna_aln *aln);
 /* Sizes of the most recent streaming pass on this GPU: candidate records emitted (two per pair at most) and pairs count kernel (b)
  * queued for exact resolution (0 on count kernel (a)). */

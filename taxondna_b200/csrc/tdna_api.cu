@@ -486,7 +486,7 @@ static int tc_resolve_queue(tdna_aln *a) {
     while ((1u << wshift) < a->tc_W) wshift++;
     unsigned grid = (unsigned)c->sm_count * 8;
     tc::ResolveArgs ra = {wshift, a->tc_W - 1u, a->min_overlap, (a->kmode == KM_K2P || a->tc_has_amb) ? a->d_planes : nullptr, a->W,
-                          a->kmode == KM_K2P ? 1 : 0, 0};
+                          a->kmode == KM_K2P ? 1 : 0, a->kmode == KM_TRANS ? 1 : 0, 0};
     if (a->sp.want & TDNA_WANT_BEST_MATCH) {
         ra.cached = ra.planes ? 1 : 0;  // resolve_min_kernel leaves the exact counts of the rows' entries in the queue
         tc::resolve_min_kernel<<<grid, 256, 0, c->stream>>>(a->sp, ra);
@@ -506,7 +506,7 @@ int launch_stream(tdna_aln *a, int part, int nparts, int phases) {
     bool tensor = c->opt_count_kernel == TDNA_KERNEL_TENSOR || (c->opt_count_kernel == TDNA_KERNEL_AUTO && !a->avoid_tensor && ensure_tc(a) == 1);
     a->last_kernel = tensor ? TDNA_KERNEL_TENSOR : TDNA_KERNEL_POPC;
     if (tensor) {
-        if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p (ambiguity allowed) or K2P, and L < 4096");
+        if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p with ambiguity allowed, K2P or transversions only, and L < 4096");
         if (phases & 1) CU(cudaEventRecord(c->ev_k0, c->stream));
         for (int ph = 0; ph < 2; ph++)
             if (phases & (1 << ph)) {
@@ -604,7 +604,7 @@ static void tc_release(tdna_aln *a) {
 // the tensor maps.  1 = ready to be encoded into, -1 = this alignment / configuration is not eligible.
 static int tc_prepare(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
-    if ((a->kmode != KM_P_AMBIG && a->kmode != KM_K2P) || a->L >= 4096) return -1;
+    if (a->kmode == KM_P_NOAMBIG || a->L >= 4096) return -1;
     // K2P ignores gap sites: four symbol dimensions -- where a four-dimension code exists (W = 1024 only, i.e. L < 1024); longer K2P
     // alignments use the five-dimension code with the gap dimension left empty (25 % more K-bytes per site).
     // Uncorrected p: barcode alignments rarely have INTERNAL gaps (external ones are '_' already), so the operands start with four
@@ -615,11 +615,31 @@ static int tc_prepare(tdna_aln *a) {
     int dims = (a->kmode == KM_K2P || !a->tc_dims5) ? 4 : 5;
     tc::EncodeValues v = {};
     uint32_t W = 0;
-    if (!find_code(a->L, dims, v, W)) {
-        dims = 5;
-        if (!find_code(a->L, dims, v, W)) return -1;
+    if (a->kmode == KM_TRANS) {
+        // transversions only: six dimensions with entries 0, 1 and r = sqrt(W) (tdna_tc.cuh: EncodeValues); every symbol is expressed
+        // exactly, so there is no ambiguity-letter machinery and the plain instantiation always runs
+        dims = 6;
+        int r = 16;
+        while (r * r <= a->L) r *= 2;  // W = 256, 1024, 4096: the smallest above L
+        W = (uint32_t)(r * r);
+        v.trans = 1;
+        const int8_t rr = (int8_t)r;
+        const int8_t ta[4][6] = {{1, 0, rr, 0, 0, 1}, {0, 1, 0, rr, 0, 1}, {0, 0, 0, 0, 1, 1}, {0, 0, 0, 0, 0, 1}};
+        const int8_t tb[4][6] = {{1, 0, 0, rr, 1, 0}, {0, 1, rr, 0, 1, 0}, {0, 0, 0, 0, 0, 1}, {0, 0, 0, 0, 1, 0}};
+        for (int code = 0; code < 4; code++)
+            for (int d = 0; d < 6; d++) { v.ta[code][d] = ta[code][d]; v.tb[code][d] = tb[code][d]; }
+        // shared == L for every pair of two rows needs every site of both in AGRCTY or '-' (any other letter is only "shared" with a gap)
+        v.breaks_full[3] = v.breaks_full[4] = v.breaks_full[5] = 1;
+    } else {
+        if (!find_code(a->L, dims, v, W)) {
+            dims = 5;
+            if (!find_code(a->L, dims, v, W)) return -1;
+        }
+        v.gap_is_symbol = (a->kmode == KM_K2P || dims == 4) ? 0 : 1;
+        for (int code = 0; code < dims; code++)  // one-hot: row (b + a [dim == code]), column (d + c [dim == code])
+            for (int d = 0; d < dims; d++) { v.ta[code][d] = (int8_t)(v.b + (d == code ? v.a : 0)); v.tb[code][d] = (int8_t)(v.d + (d == code ? v.c : 0)); }
+        for (int code = dims; code < 6; code++) v.breaks_full[code] = 1;  // a site without contribution ('_', '?', past the row's end; '-' when it is not a symbol)
     }
-    v.gap_is_symbol = (a->kmode == KM_K2P || dims == 4) ? 0 : 1;
     const int nchunks = (a->L * dims + tc::KB - 1) / tc::KB;
     const int64_t npa = round_up(a->n, tc::M), npb = round_up(a->n, tc::N);
     const size_t npan = (size_t)(npb / tc::M);
@@ -697,7 +717,8 @@ static void tc_encode_range(tdna_aln *a, cudaStream_t stream, int64_t panel0, in
     const int nchunks = a->tc_nchunks, dims = a->tc_dims;
     const int64_t npa = round_up(a->n, tc::M), npb = round_up(a->n, tc::N);
     const int64_t row0 = panel0 * tc::N, rows = std::min<int64_t>(a->n, (panel0 + panels) * tc::N) - row0;
-    if (rows > 0)
+    if (rows > 0 && a->kmode == KM_TRANS) cudaMemsetAsync(a->d_tcamb + row0, 0, (size_t)rows * 4, stream);  // every symbol is expressed exactly
+    else if (rows > 0)
         tc::amb_count_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(a->d_sym, a->d_len, a->n, a->sym_stride, a->L, a->kmode == KM_K2P ? 1 : 0, a->d_tcamb,
                                                                             a->d_tcpanel_amb, a->d_tcflag + 1, row0,
                                                                             (a->kmode != KM_K2P && a->tc_dims == 4) ? 1 : 0);
@@ -716,13 +737,13 @@ static void tc_encode_range(tdna_aln *a, cudaStream_t stream, int64_t panel0, in
 
 // uncorrected p on the four-dimension code: do the internal gaps it leaves out outnumber a sprinkling (1 site in 2,000)?
 static bool tc_too_gappy(const tdna_aln *a, int gap_sites) {
-    return a->kmode != KM_K2P && a->tc_dims == 4 && !a->tc_dims5 && (int64_t)gap_sites * 2000 > (int64_t)a->n * a->L;
+    return a->kmode == KM_P_AMBIG && a->tc_dims == 4 && !a->tc_dims5 && (int64_t)gap_sites * 2000 > (int64_t)a->n * a->L;
 }
 
 // 1 = ready, -1 = this alignment / configuration is not eligible
 int ensure_tc(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
-    if ((a->kmode != KM_P_AMBIG && a->kmode != KM_K2P) || a->L >= 4096) return -1;
+    if (a->kmode == KM_P_NOAMBIG || a->L >= 4096) return -1;
     if (a->tc_state == 1 && a->tc_kmode != a->kmode) tc_release(a);  // the operands encode the mode's valid-symbol set: rebuild
     if (a->tc_state != 0) return a->tc_state;
     if (tc_prepare(a) != 1) { a->tc_state = -1; return -1; }
@@ -892,6 +913,7 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     p.counts = counts;
     p.extras = a->sp.want != TDNA_WANT_BEST_MATCH;
     p.k2p = a->kmode == KM_K2P ? 1 : 0;
+    p.trans = a->kmode == KM_TRANS ? 1 : 0;
     p.panel_full = a->d_tcfull;
     p.L = a->L;
     p.amb = has_amb ? a->d_tcamb : nullptr;
@@ -3224,8 +3246,8 @@ int32_t tdna_tensor_counts(tdna_aln *a, tdna_counts *out) {
     tdna_ctx *c = a->ctx;
     CU(cudaSetDevice(c->device));
     TRY(ensure_packed(a));
-    if (a->kmode != KM_P_AMBIG) return fail(TDNA_E_STATE, "tdna_tensor_counts: uncorrected p only (for K2P the accumulator carries n and ts + tv)");
-    if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p (ambiguity allowed) or K2P, and L < 4096");
+    if (a->kmode != KM_P_AMBIG && a->kmode != KM_TRANS) return fail(TDNA_E_STATE, "tdna_tensor_counts: uncorrected p or transversions only (for K2P the accumulator carries n and ts + tv)");
+    if (ensure_tc(a) != 1) return fail(TDNA_E_STATE, "count kernel (b) needs uncorrected p with ambiguity allowed, K2P or transversions only, and L < 4096");
     if (a->tc_has_amb) return fail(TDNA_E_STATE, "tdna_tensor_counts: the alignment has IUPAC ambiguity letters -- kernel (b) only bounds such pairs (exact counts come from the bit-planes)");
     tdna_counts *dc = out;
     bool own = !is_device_ptr(out);

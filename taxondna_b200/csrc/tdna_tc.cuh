@@ -33,7 +33,7 @@ constexpr int STAGE = A_STAGE + B_STAGE;
 constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter
 constexpr int EPI_COLS = N / (EPI_WARPS / 4);      // columns per epilogue warp
 constexpr int THREADS = 64 + EPI_WARPS * 32;       // warp 0 producer, warp 1 MMA issuer, warps 2.. epilogue
-constexpr int MAX_DIMS = 5;                        // K-dimensions per site: 5 (p: A C G T -) or 4 (K2P: A C G T)
+constexpr int MAX_DIMS = 6;                        // K-dimensions per site: 4 or 5 (one-hot A C G T [-]), 6 (transversions only)
 constexpr int WTAB = 64;                           // slots of an epilogue warp's private class-histogram table (tdna_kernels.cuh: shist_add)
 constexpr size_t SMEM = (size_t)NSTAGE * STAGE + 256 /*barriers*/ + 2 * 16 * 64 * 4 /*column thresholds + raw bounds, per epilogue warp*/ +
                         (size_t)EPI_WARPS * WTAB * 12 /*class-histogram tables*/ + 1024 /*alignment*/;
@@ -64,6 +64,7 @@ struct Params {
     const uint8_t *panel_full;  // [128-row panel] 1 = every row of the panel is valid at every site: pairs of two such panels share L sites
     int L;
     int k2p;                // the accumulator carries (n, ts + tv) of the K2P model; exact counts come from the bit-planes
+    int trans;              // transversions only: mism = transversions, ident = shared - transversions (exact); d = transv / shared
     const uint32_t *planes; // K2P: the popc kernel's planes, for the exact counts of queued / class pairs
     int W32;
     int a_rows, b_rows;     // rows of the tensor-map view per a / b stage block (view row = inner box width)
@@ -178,7 +179,31 @@ template <int CL> __device__ __forceinline__ bool my_tile(const Params &p, int64
 struct EncodeValues {
     int a, b, c, d;
     int gap_is_symbol;  // uncorrected p: '-' is the fifth symbol; K2P ignores gap sites (Sequence.java:1446-1471): no contribution
+    // What the encoders read: per symbol CODE (0 .. 5; 5 = no contribution) the row-side and the column-side int8 vector over the
+    // K-dimensions of a site.  One-hot codes (p, K2P): code = symbol, ta[code][dim] = b + a [dim == code], tb = d + c [dim == code].
+    // Transversions only (trans = 1, six dimensions, W = r^2): code 0 purine {A G R}, 1 pyrimidine {C T Y}, 2 '-', 3 any other letter;
+    //   row    purine (1 0 r 0 | 0 1)  pyrimidine (0 1 0 r | 0 1)  '-' (0 0 0 0 | 1 1)  other (0 0 0 0 | 0 1)
+    //   column purine (1 0 0 r | 1 0)  pyrimidine (0 1 r 0 | 1 0)  '-' (0 0 0 0 | 0 1)  other (0 0 0 0 | 1 0)
+    // so that u . v = [both in AGRCTY] + (W - 1) [purine x pyrimidine] + [both valid, one a '-'] = (shared - transv) + W * transv:
+    // the accumulator decodes like uncorrected p's with ident := shared - transversions (countTransversions :1352-1371,
+    // getSharedLength in that mode :1446-1451, 1472-1478) -- EXACT for every letter, no ambiguity-letter machinery.
+    int trans;
+    int8_t ta[6][8], tb[6][8];
+    uint8_t breaks_full[6];  // a site holding this code keeps its 128-row panel from being "full" (shared == L for pairs of full panels)
 };
+// the symbol-class word of the pack kernel's table -> code
+__device__ __forceinline__ uint32_t symbol_code(uint32_t cls, const EncodeValues &v) {
+    if (v.trans) {
+        if (cls & SB_U) return (cls & SB_PU) ? 0u : 1u;
+        if (cls & SB_D) return 2u;
+        if (cls & SB_LET) return 3u;
+        return (cls & 0x8000u) ? 0x85u : 5u;
+    }
+    const uint32_t bases = cls & 15u;
+    if (cls & SB_LET) return __popc(bases) == 1 ? (uint32_t)__ffs((int)bases) - 1u : 5u;  // an ambiguity letter contributes nothing here
+    if (cls & SB_D) return v.gap_is_symbol ? 4u : 5u;
+    return (cls & 0x8000u) ? 0x85u : 5u;
+}
 // one CTA = one operand block (panel x K-chunk): the ~27 sites the chunk covers are staged as symbol codes in shared
 // memory (coalesced 27-byte runs per row), then every thread emits 16-byte units in memory order (coalesced uint4 stores)
 constexpr int ENC_SITES = KB / 4 + 3;
@@ -199,16 +224,12 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
             const int site = s0 + s;
             uint32_t code = 5;
             if (site < row_len) {
-                const uint32_t cls = c_symlut[sym[row * sym_stride + site]];  // the pack kernel's table: IUPAC mask in bits 0..3 (A C G T)
-                const uint32_t bases = cls & 15u;
-                if (cls & SB_LET) {  // an ambiguity letter contributes nothing here: amb_count_kernel counts it, the filter allows for it
-                    if (__popc(bases) == 1) code = (uint32_t)__ffs((int)bases) - 1u;
-                } else if (cls & SB_D) code = v.gap_is_symbol ? 4u : 5u;
-                else if (cls & 0x8000u) bad = true;
+                code = symbol_code(c_symlut[sym[row * sym_stride + site]], v);  // the pack kernel's table: IUPAC mask in bits 0..3 (A C G T)
+                if (code & 0x80u) { bad = true; code = 5; }
             }
             codes[row_l][s] = (uint8_t)code;
             // a site of the alignment of an existing row that contributes nothing: the panel is not "full"
-            if (row < n && site < L && code >= 5u) gappy = true;
+            if (row < n && site < L && v.breaks_full[code]) gappy = true;
         }
     }
     if (bad) atomicOr(not_clean, 1);
@@ -217,7 +238,6 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
     }
     __syncthreads();
     uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)panel * nchunks + c) * (size_t)(ROWS * KB));
-    const int va = BSIDE ? v.c : v.a, vb = BSIDE ? v.d : v.b;
     for (int u = threadIdx.x; u < ROWS * (KB / 16); u += 256) {
         const int row_l = u % ROWS, k16 = u / ROWS;  // u = (k16 * (ROWS / 8) + rg) * 8 + r, row = rg * 8 + r
         uint32_t w[4] = {0, 0, 0, 0};
@@ -225,7 +245,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
 #pragma unroll
         for (int b = 0; b < 16; b++) {
             const int code = codes[row_l][site];
-            const int val = code < DIMS ? vb + (dim == code ? va : 0) : 0;
+            const int val = BSIDE ? v.tb[code][dim] : v.ta[code][dim];
             w[b >> 2] |= (uint32_t)(val & 0xff) << (8 * (b & 3));
             if (++dim == DIMS) { dim = 0; site++; }
         }
@@ -240,15 +260,10 @@ __global__ void __launch_bounds__(256) encode_both_kernel(const uint8_t *__restr
                                                           int L, int nchunks, int DIMS, EncodeValues v, uint8_t *__restrict__ outA, uint8_t *__restrict__ outB,
                                                           int64_t a_panels, int *__restrict__ not_clean, uint8_t *__restrict__ panel_gappy, int64_t panel0) {
     __shared__ uint8_t codes[N][ENC_SITES + 1];
-    __shared__ uint8_t s_code[256];  // 0..3 A C G T, 4 '-' (when it is a symbol), 5 no contribution, 0x85 outside the alphabet
-    {
-        const uint32_t cls = c_symlut[threadIdx.x], bases = cls & 15u;
-        uint32_t code = 5;
-        if (cls & SB_LET) { if (__popc(bases) == 1) code = (uint32_t)__ffs((int)bases) - 1u; }
-        else if (cls & SB_D) code = v.gap_is_symbol ? 4u : 5u;
-        else if (cls & 0x8000u) code = 0x85u;
-        s_code[threadIdx.x] = (uint8_t)code;
-    }
+    __shared__ uint8_t s_code[256];  // the symbol's code (EncodeValues), 5 no contribution, 0x85 outside the alphabet
+    __shared__ int8_t s_ta[6][8], s_tb[6][8];
+    s_code[threadIdx.x] = (uint8_t)symbol_code(c_symlut[threadIdx.x], v);
+    if (threadIdx.x < 48) { s_ta[threadIdx.x >> 3][threadIdx.x & 7] = v.ta[threadIdx.x >> 3][threadIdx.x & 7]; s_tb[threadIdx.x >> 3][threadIdx.x & 7] = v.tb[threadIdx.x >> 3][threadIdx.x & 7]; }
     __syncthreads();
     const int c = blockIdx.x;
     const int64_t panel = panel0 + blockIdx.y;  // 256-row panel (panel0: the first panel of a chunk of a pipelined upload)
@@ -266,32 +281,32 @@ __global__ void __launch_bounds__(256) encode_both_kernel(const uint8_t *__restr
             if (s0 + s < row_len) code = s_code[__ldg(src + s)];
             if (code & 0x80u) { bad = true; code = 5; }
             codes[row_l][s] = (uint8_t)code;
-            if (row < n && s0 + s < L && code >= 5u) gappy |= 1u << (row_l >> 7);
+            if (row < n && s0 + s < L && v.breaks_full[code]) gappy |= 1u << (row_l >> 7);
         }
     }
     if (bad) atomicOr(not_clean, 1);
     if (gappy & 1u) panel_gappy[2 * panel] = 1;
     if (gappy & 2u) panel_gappy[2 * panel + 1] = 1;
     __syncthreads();
-    auto unit = [&](int row_l, int k16, int va, int vb) {
+    auto unit = [&](int row_l, int k16, const int8_t (*tab)[8]) {
         uint32_t w[4] = {0, 0, 0, 0};
         int kk = c * KB + k16 * 16, site = kk / DIMS - s0, dim = kk % DIMS;
 #pragma unroll
         for (int b = 0; b < 16; b++) {
             const int code = codes[row_l][site];
-            const int val = code < DIMS ? vb + (dim == code ? va : 0) : 0;
+            const int val = tab[code][dim];
             w[b >> 2] |= (uint32_t)(val & 0xff) << (8 * (b & 3));
             if (++dim == DIMS) { dim = 0; site++; }
         }
         return make_uint4(w[0], w[1], w[2], w[3]);
     };
     uint4 *dstB = reinterpret_cast<uint4 *>(outB + ((size_t)panel * nchunks + c) * (size_t)(N * KB));
-    for (int u = threadIdx.x; u < N * (KB / 16); u += 256) dstB[u] = unit(u % N, u / N, v.c, v.d);
+    for (int u = threadIdx.x; u < N * (KB / 16); u += 256) dstB[u] = unit(u % N, u / N, s_tb);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         if (2 * panel + h >= a_panels) break;
         uint4 *dstA = reinterpret_cast<uint4 *>(outA + ((size_t)(2 * panel + h) * nchunks + c) * (size_t)(M * KB));
-        for (int u = threadIdx.x; u < M * (KB / 16); u += 256) dstA[u] = unit(h * M + u % M, u / M, v.a, v.b);
+        for (int u = threadIdx.x; u < M * (KB / 16); u += 256) dstA[u] = unit(h * M + u % M, u / M, s_ta);
     }
 }
 
@@ -412,6 +427,17 @@ __device__ __noinline__ unsigned long long exact_seed_bits(const Params &p, int 
     else d = distance_from_counts<KM_P_AMBIG>(pair_counts_global<KM_P_AMBIG>(p.planes, i, j, p.W32), p.min_overlap);
     if (!(d < __longlong_as_double((long long)TDNA_INF_BITS)) || d < 0.0) return TDNA_INF_BITS;
     return (unsigned long long)__double_as_longlong(d);
+}
+
+// the distance of a pair whose accumulator is exact: 1 - ident / shared (uncorrected p, Sequence.java:1711) or transversions / shared
+// (transversions only, :1708; ident carries shared - transversions there)
+__device__ __forceinline__ double exact_acc_distance(int trans, uint32_t ident, uint32_t s, int min_overlap) {
+    if (trans) {
+        Counts cn = {(int)s, (int)(s - ident), 0, 0};
+        return distance_from_counts<KM_TRANS>(cn, min_overlap);
+    }
+    Counts cn = {(int)s, (int)ident, 0, 0};
+    return distance_from_counts<KM_P_AMBIG>(cn, min_overlap);
 }
 
 // ---- the tile kernel ---------------------------------------------------------------------------
@@ -702,7 +728,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                     for (int e = 0; e < 32; e++) {
                         const uint32_t mism = v[e] >> p.wshift, ident = v[e] & wm1;
                         if (i < p.n && jb + e < p.n) {
-                            tdna_counts o = {(int)(ident + mism), (int)ident, 0, 0};
+                            tdna_counts o = {(int)(ident + mism), p.trans ? (int)mism : (int)ident, 0, 0};
                             p.counts[(size_t)i * p.n + jb + e] = o;
                         }
                     }
@@ -925,14 +951,17 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                             if (j <= i || j >= p.n || (int)s < p.min_overlap) continue;
                             const bool hit = ((sp.want & TDNA_WANT_INTRA) && spi_ == sp.species[j]) || ((sp.want & TDNA_WANT_INTER) && gi_ == sp.genus[j]);
                             if (!hit) continue;
-                            if (!hist_mode) { class_emit<KM_P_AMBIG>(sp, i, j, ident | (s << 16), 0u, p.min_overlap); continue; }
+                            if (!hist_mode) {
+                                if (p.trans) class_emit<KM_TRANS>(sp, i, j, mism | (s << 16), 0u, p.min_overlap);
+                                else class_emit<KM_P_AMBIG>(sp, i, j, ident | (s << 16), 0u, p.min_overlap);
+                                continue;
+                            }
                             // histogram mode: the pushes of this tile go through the warp's shared-memory table first
                             int t0 = 0, t1 = 0;
                             if ((sp.want & TDNA_WANT_INTRA) && spi_ >= 0 && spi_ == sp.species[j]) t0 = 1 + (sp.full[i] == sp.full[j] ? 1 : 0);
                             if ((sp.want & TDNA_WANT_INTER) && gi_ == sp.genus[j] && sp.epi[i] != sp.epi[j]) t1 = 1;
                             if (!(t0 | t1)) continue;
-                            Counts cn = {(int)s, (int)ident, 0, 0};
-                            const double d = distance_from_counts<KM_P_AMBIG>(cn, p.min_overlap);
+                            const double d = exact_acc_distance(p.trans, ident, s, p.min_overlap);
                             if (t0) { if (sp.hkey[0] && shist_add(my_keys, my_cnts, WTAB - 1, 0, d, t0)) wtab_used = true; else class_push(sp, 0, d, t0); }
                             if (t1) { if (sp.hkey[1] && shist_add(my_keys, my_cnts, WTAB - 1, 1, d, t1)) wtab_used = true; else class_push(sp, 1, d, t1); }
                         }
@@ -958,8 +987,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                 if (!GENERAL && seed && i < p.n) {
                     auto frac_bits = [&](uint32_t ident, uint32_t sh) -> unsigned long long {
                         if (sh == 0) return TDNA_INF_BITS;
-                        Counts cn = {(int)sh, (int)ident, 0, 0};
-                        return (unsigned long long)__double_as_longlong(distance_from_counts<KM_P_AMBIG>(cn, p.min_overlap));
+                        return (unsigned long long)__double_as_longlong(exact_acc_distance(p.trans, ident, sh, p.min_overlap));
                     };
                     seed_c = frac_bits(fc_i, fc_s);
                     seed_p0 = frac_bits(f0_i, f0_s);
@@ -999,6 +1027,7 @@ struct ResolveArgs {
     const uint32_t *planes;  // non-null: exact counts of the pair from the bit-planes (K2P; alignments with ambiguity letters)
     int W32;
     int k2p;
+    int trans;   // transversions only (exact accumulators: d = transv / shared)
     int cached;  // the exact counts of the rows' entries sit in qv / qx already (resolve_min_kernel put them there): no second walk of the planes
 };
 // exact counts <-> two queue words: (c1 | shared << 16, c2 | c3 << 16), every count <= L <= 65535
@@ -1024,8 +1053,7 @@ __device__ __forceinline__ double queued_distance(const ResolveArgs &ra, int i, 
     const uint32_t mism = val >> ra.wshift, ident = val & ra.wm1, s = ident + mism;
     lhs = mism << 16;
     den = s;
-    Counts cn = {(int)s, (int)ident, 0, 0};
-    return distance_from_counts<KM_P_AMBIG>(cn, ra.min_overlap);
+    return exact_acc_distance(ra.trans, ident, s, ra.min_overlap);
 }
 constexpr int RTAB = 1024;  // slots of the resolve kernel's per-block class-histogram table
 // a queued class pair (bit 31 of the row index): PairwiseDistribution's pushes for it, with the exact distance d >= 0 (or NaN / +Inf)

@@ -246,3 +246,81 @@ def test_species_blocks_wider_than_the_seed_window(ctx, reps, L):
     assert got["tensor"].tobytes() == got["dense"].tobytes() and got["popc"].tobytes() == got["dense"].tobytes()
     assert (got["dense"]["n_valid"] == n - 1).all()
     aln.close()
+
+
+# ---- transversions only (PDM_TRANS_ONLY) on count kernel (b): six dimensions, exact for every letter (tdna_tc.cuh: EncodeValues) ----
+def trans_alignment(rng, n_species, reps, L, ambig, gaps):
+    from test_gpu_parity import labelled_alignment
+    sym, sp, gen, epi, full = labelled_alignment(rng, n_species, reps, L, unnamed=3, dup=6, gappy=False)
+    m = rng.random(sym.shape) < 0.06  # transversions need more divergence than the generator's default to be interesting
+    sym[m] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(m.sum()))
+    if ambig:
+        sprinkle_ambiguity(rng, sym, ambig)
+    if gaps:  # internal gaps, '?' and external runs: a letter outside AGRCTY is only "shared" with a gap (Sequence.java:1446-1451, 1472-1478)
+        m = rng.random(sym.shape) < gaps
+        sym[m] = ord("-")
+        m = rng.random(sym.shape) < gaps / 2
+        sym[m] = ord("?")
+        for r in range(0, sym.shape[0], 5):
+            k = int(rng.integers(1, L // 5))
+            sym[r, :k] = ord("_")
+    return sym, sp, gen, epi, full
+
+
+@pytest.mark.parametrize("n,L,ambig,gaps", [(130, 200, 0.0, 0.0), (300, 658, 0.04, 0.03), (257, 1539, 0.02, 0.05), (140, 2664, 0.05, 0.02)])
+def test_transversion_counts_from_the_tensor_kernel_equal_the_oracle(ctx, n, L, ambig, gaps):
+    import taxondna_b200 as t
+    rng = np.random.default_rng(n + L)
+    sym, *_ = trans_alignment(rng, n // 5, 5, L, ambig, gaps)
+    n = sym.shape[0]
+    lens = rng.integers(L // 2, L + 1, size=n).astype(np.int32)
+    aln = t.Alignment(ctx, sym, lens)
+    aln.set_config(t.PDM_TRANS_ONLY, max(1, L // 3), True)
+    got = aln.tensor_counts()
+    ref = oracle.all_pairs(sym, lens, 2, max(1, L // 3), True, threads=8)
+    iu = np.triu_indices(n, 0)
+    assert np.array_equal(got["shared"][iu], ref["shared"][iu]), "shared"
+    assert np.array_equal(got["c1"][iu], ref["c1"][iu]), "transversions"
+    assert aln.tensor_dims() == 6
+    aln.close()
+
+
+@pytest.mark.parametrize("shuffle,ragged,L,ambig,gaps", [(False, False, 658, 0.0, 0.0), (False, False, 658, 0.03, 0.03), (True, True, 500, 0.05, 0.04),
+                                                         (False, True, 2664, 0.04, 0.02), (False, False, 250, 0.0, 0.0)])
+def test_transversions_only_streaming_on_the_tensor_kernel(ctx, shuffle, ragged, L, ambig, gaps):
+    import taxondna_b200 as t
+    from test_stream_gpu import first_difference
+    rng = np.random.default_rng(23 + L)
+    sym, sp, gen, epi, full = trans_alignment(rng, 36, 9, L, ambig, gaps)
+    n = sym.shape[0]
+    lens = rng.integers(L // 2, L + 1, size=n).astype(np.int32) if ragged else None
+    if shuffle:
+        perm = rng.permutation(n)
+        sym, sp, gen, epi = sym[perm], sp[perm], gen[perm], epi[perm]
+        if lens is not None:
+            lens = lens[perm]
+    aln = t.Alignment(ctx, sym, lens)
+    aln.set_labels(sp, gen, epi, full)
+    aln.set_config(t.PDM_TRANS_ONLY, L // 2, True)
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_DENSE)
+    dense = aln.best_match()
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_STREAM)
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_POPC)
+    a = aln.analyze(best_match=True, intra=True, inter=True, edges=0.01)
+    ha = {k: aln.class_histogram(kl)[0] for k, kl in (("hist_intra", t.PD_INTRA), ("hist_inter", t.PD_INTER))}
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)  # AUTO takes kernel (b) for this mode too
+    b = aln.analyze(best_match=True, intra=True, inter=True, edges=0.01)
+    assert aln.last_count_kernel() == t.KERNEL_TENSOR
+    hb = {k: aln.class_histogram(kl)[0] for k, kl in (("hist_intra", t.PD_INTRA), ("hist_inter", t.PD_INTER))}
+    assert aln.last_count_kernel() == t.KERNEL_TENSOR
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+    assert first_difference(dense, a["rows"]) is None
+    assert first_difference(a["rows"], b["rows"]) is None, first_difference(a["rows"], b["rows"])
+    assert np.array_equal(np.sort(a["intra"]).view(np.uint32), np.sort(b["intra"]).view(np.uint32))
+    assert np.array_equal(np.sort(a["inter"]).view(np.uint32), np.sort(b["inter"]).view(np.uint32))
+    assert sorted(zip(a["edge_i"].tolist(), a["edge_j"].tolist(), a["edge_d"].tolist())) == \
+        sorted(zip(b["edge_i"].tolist(), b["edge_j"].tolist(), b["edge_d"].tolist()))
+    for k in ("hist_intra", "hist_inter"):
+        ea, eb = ha[k], hb[k]
+        assert sorted(zip(ea["d"].view(np.uint64).tolist(), ea["count"].tolist())) == sorted(zip(eb["d"].view(np.uint64).tolist(), eb["count"].tolist())), k
+    aln.close()
