@@ -261,9 +261,17 @@ __global__ void __launch_bounds__(256) encode_both_kernel(const uint8_t *__restr
                                                           int64_t a_panels, int *__restrict__ not_clean, uint8_t *__restrict__ panel_gappy, int64_t panel0) {
     __shared__ uint8_t codes[N][ENC_SITES + 1];
     __shared__ uint8_t s_code[256];  // the symbol's code (EncodeValues), 5 no contribution, 0x85 outside the alphabet
-    __shared__ int8_t s_ta[6][8], s_tb[6][8];
+    __shared__ unsigned long long s_ta[6], s_tb[6];  // a code's operand bytes over the K-dimensions of a site, packed (dimension d in byte d)
     s_code[threadIdx.x] = (uint8_t)symbol_code(c_symlut[threadIdx.x], v);
-    if (threadIdx.x < 48) { s_ta[threadIdx.x >> 3][threadIdx.x & 7] = v.ta[threadIdx.x >> 3][threadIdx.x & 7]; s_tb[threadIdx.x >> 3][threadIdx.x & 7] = v.tb[threadIdx.x >> 3][threadIdx.x & 7]; }
+    if (threadIdx.x < 6) {
+        unsigned long long wa = 0, wb = 0;
+        for (int d = 0; d < 8; d++) {
+            wa |= (unsigned long long)(uint8_t)v.ta[threadIdx.x][d] << (8 * d);
+            wb |= (unsigned long long)(uint8_t)v.tb[threadIdx.x][d] << (8 * d);
+        }
+        s_ta[threadIdx.x] = wa;
+        s_tb[threadIdx.x] = wb;
+    }
     __syncthreads();
     const int c = blockIdx.x;
     const int64_t panel = panel0 + blockIdx.y;  // 256-row panel (panel0: the first panel of a chunk of a pipelined upload)
@@ -288,15 +296,15 @@ __global__ void __launch_bounds__(256) encode_both_kernel(const uint8_t *__restr
     if (gappy & 1u) panel_gappy[2 * panel] = 1;
     if (gappy & 2u) panel_gappy[2 * panel + 1] = 1;
     __syncthreads();
-    auto unit = [&](int row_l, int k16, const int8_t (*tab)[8]) {
+    auto unit = [&](int row_l, int k16, const unsigned long long *tab) {
         uint32_t w[4] = {0, 0, 0, 0};
         int kk = c * KB + k16 * 16, site = kk / DIMS - s0, dim = kk % DIMS;
+        unsigned long long tw = tab[codes[row_l][site]] >> (8 * dim);  // one table word per SITE, a byte of it per K-byte
 #pragma unroll
         for (int b = 0; b < 16; b++) {
-            const int code = codes[row_l][site];
-            const int val = tab[code][dim];
-            w[b >> 2] |= (uint32_t)(val & 0xff) << (8 * (b & 3));
-            if (++dim == DIMS) { dim = 0; site++; }
+            w[b >> 2] |= ((uint32_t)tw & 0xffu) << (8 * (b & 3));
+            tw >>= 8;
+            if (++dim == DIMS) { dim = 0; site++; tw = tab[codes[row_l][site]]; }
         }
         return make_uint4(w[0], w[1], w[2], w[3]);
     };
