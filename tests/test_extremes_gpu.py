@@ -128,3 +128,39 @@ def test_host_modules_use_the_records_and_agree_with_the_exact_sort():
     assert da.rows_resolved_on_host < n
     da.force_exact = True
     assert da.run() == fast
+
+
+def test_a_genus_beyond_the_kernels_capacity_is_left_to_the_host():
+    """More than 4,096 rows in one genus: the record says so (TDNA_EXT_TOO_MANY) and the host module sorts such queries exactly."""
+    import taxondna_b200 as t
+    rng = np.random.default_rng(41)
+    n, L = 4200, 64
+    root = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=L)
+    sym = np.tile(root, (n, 1))
+    m = rng.random(sym.shape) < 0.1
+    sym[m] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(m.sum()))
+    species = (np.arange(n) // 7).astype(np.int32)
+    genus = np.zeros(n, dtype=np.int32)
+    genus[-50:] = 1  # a second, small genus
+    ctx = t.Context(0)
+    aln = t.Alignment(ctx, sym)
+    try:
+        aln.set_labels(species, genus, species, np.arange(n, dtype=np.int32))
+        aln.set_config(0, 30, True)
+        rec = aln.row_extremes()
+        d = aln.matrix()
+    finally:
+        aln.close()
+        ctx.close()
+    assert ((rec["flags"][:-50] & t.EXT_TOO_MANY) != 0).all()
+    small = rec[-50:]
+    assert ((small["flags"] & t.EXT_TOO_MANY) == 0).all()
+    for q in range(n - 50, n):  # the small genus is decided on the device: check it against the matrix
+        r = rec[q]
+        cons = [j for j in range(n - 50, n) if j != q and species[j] == species[q] and d[q, j] >= 0]
+        inter = [j for j in range(n - 50, n) if species[j] != species[q] and d[q, j] >= 0]
+        assert r["n_intra"] == len(cons) and r["n_inter"] == len(inter)
+        if cons:
+            assert r["d_max_intra"] == max(d[q, j] for j in cons)
+        if inter:
+            assert r["d_min_inter"] == min(d[q, j] for j in inter)
