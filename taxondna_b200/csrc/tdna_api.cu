@@ -77,12 +77,15 @@ struct tdna_ctx {
     uint32_t opt_hist_slots = 1u << 18;
     int64_t opt_segment_items = 0;  // 0 = automatic (segments of ~30 ms)
     // tdna_analyze_host: row chunks of the pass pipelined with the upload; 0 (default): not pipelined -- measured on 50,000 x 658:
-    // 3.54 ms without, 3.62 - 3.82 ms with 2 - 8 chunks: the upload is 0.65 ms, the first chunk's verdict and a seed
-    // launch per chunk cost as much as the overlap gains
+    // 3.55 ms without, 3.57 - 3.78 ms with 3 - 8 chunks: the upload is 0.65 ms, a seed launch per chunk and the
+    // encode kernels waiting for the persistent tile CTAs cost as much as the overlap gains
     int opt_pipeline_chunks = 0;
     // records / queue entries per row the streaming buffers of NEW alignments start with: raised to what a pass on this context
     // needed (a host that creates an alignment per analysis would otherwise overflow and retry every time)
     double hint_cand_per_row = 64, hint_queue_per_row = 256;
+    // what the previous list built on this context looked like to count kernel (b) (-1: none yet): a pipelined tdna_analyze_host
+    // starts its region launches on that assumption instead of waiting for the first chunk's flags, and checks it at the end
+    int hint_has_amb = -1, hint_dims5 = -1;
     cudaStream_t enc_stream = nullptr;   // pipelined tdna_analyze_host: pack + encode of the arriving chunks, beside the tile launches
     cudaEvent_t ev_enc[16] = {};
     double hc_t[12] = {};            // host wall-clock marks of the most recent tdna_analyze_host call (tdna_host_call_phase_ms)
@@ -1420,9 +1423,12 @@ static int aln_build(tdna_ctx *c, tdna_aln *a, const uint8_t *symbols, const int
         if (tc_too_gappy(a, flags[4])) {  // rebuilt with the five-dimension code at first use (ensure_tc)
             tc_release(a);
             a->tc_dims5 = true;
+            c->hint_dims5 = 1;
         } else {
             a->tc_has_amb = flags[3] != 0;
             a->tc_state = 1;
+            c->hint_has_amb = a->tc_has_amb ? 1 : 0;
+            if (a->kmode == KM_P_AMBIG) c->hint_dims5 = a->tc_dims == 5 ? 1 : 0;
         }
     }
     return TDNA_OK;
@@ -1574,13 +1580,13 @@ static int pipeline_chunk(tdna_aln *a, Pipeline &pl, int ch, int64_t r0, int64_t
     tdna_ctx *c = a->ctx;
     if (pl.abandoned) return TDNA_OK;
     if (ch == 0) {
-        int f[3] = {0, 0, 0};
-        CU(cudaMemcpyAsync(f, a->d_tcflag, 12, cudaMemcpyDeviceToHost, c->stream));  // (the stream waits for the first chunk's operands)
-        CU(cudaStreamSynchronize(c->stream));  // ~ the first chunk's upload: every later copy is in flight already
-        if (f[0]) return TDNA_OK;              // a symbol outside the alphabet: aln_build reports it
-        if (a->kmode != KM_K2P && a->tc_dims == 4 && (int64_t)f[2] * 2000 > (r1 - r0) * (int64_t)a->L) { pl.abandoned = true; return TDNA_OK; }  // see tc_too_gappy
+        // Which instantiation (plain / GENERAL) and which code (four / five dimensions) -- known for certain only when the LAST chunk
+        // has been encoded.  The pass starts on what the previous list on this context turned out to be (a host re-analysing an
+        // edited list: the same answer nearly always) and tdna_analyze_host checks the assumption once the upload is complete;
+        // waiting for the first chunk's flags instead cost a host round trip of 0.1 ms before the first launch.
+        if (c->hint_has_amb < 0 || (a->kmode == KM_P_AMBIG && c->hint_dims5 != 0)) { pl.abandoned = true; return TDNA_OK; }
         if (!a->tc_maps || a->tc_pair) { pl.abandoned = true; return TDNA_OK; }  // region launches exist for the multicast pairs only
-        a->pl_general = f[1] ? 1 : 0;
+        a->pl_general = c->hint_has_amb;
         TRY(ensure_stream_state(a));
         a->sp.species = a->d_species;
         a->sp.genus = a->d_genus;
@@ -1684,7 +1690,7 @@ int32_t tdna_analyze_host(tdna_ctx *c, const tdna_host_list *in, tdna_analysis *
     if (pl.active) {
         // the first chunk's verdict must hold for the whole list: the operands were kept (not too gappy for their code) and no
         // ambiguity letter turned up after a plain start
-        const bool consistent = a->tc_state == 1 && !(a->tc_has_amb && a->pl_general == 0);
+        const bool consistent = a->tc_state == 1 && !(a->tc_has_amb && a->pl_general == 0);  // (GENERAL assumed, no letter found: still exact)
         if (consistent) {
             rc = pipeline_finish(a, io);
             done = rc == TDNA_OK;

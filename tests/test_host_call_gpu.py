@@ -54,13 +54,14 @@ def test_one_call_equals_the_separate_calls(ctx, cfg, n, mode):
     sym, labels = labelled(cfg, n)
     ref = separate(ctx, sym, labels, mode, 300)
     before = ctx.pipelined_passes()
-    got = t.best_match_host(ctx, sym, labels, mode, 300)
-    assert got.tobytes() == ref["rows"].tobytes()
-    # 16,384+ rows: the pass ran in region launches while the row chunks were still arriving (Hg in p: the first chunk's internal
-    # gaps send the list to the five-dimension code, i.e. to the ordinary pass)
+    for _ in range(2):  # the second call starts on what the first one learned about the list (ambiguity letters? internal gaps?)
+        got = t.best_match_host(ctx, sym, labels, mode, 300)
+        assert got.tobytes() == ref["rows"].tobytes()
+    # 16,384+ rows: the pass ran in region launches while the row chunks were still arriving (Hg in p: its internal gaps send the
+    # list to the five-dimension code, i.e. to the ordinary pass)
     if n >= 16384 and not (cfg == "Hg" and mode == 0):
-        assert ctx.pipelined_passes() == before + 1
-    if n < 16384:
+        assert ctx.pipelined_passes() >= before + 1
+    else:
         assert ctx.pipelined_passes() == before
 
 
@@ -87,11 +88,23 @@ def test_letters_that_arrive_late_switch_the_instantiation(ctx):
     block = sym[late]
     block[m] = rng.choice(np.frombuffer(b"RYKMSWBDHVN", dtype=np.uint8), size=int(m.sum()))
     sym[late] = block
-    ref = separate(ctx, sym, labels, 0, 300)
+    clean, clean_labels = labelled("H", 17000)
+    t.best_match_host(ctx, clean, clean_labels, 0, 300)  # the context now expects a list without ambiguity letters
+    a = t.Alignment(ctx, sym)
+    a.set_labels(*labels)
+    a.set_config(0, 300, True)
+    ctx.set_option(t.OPT_PIPELINE_CHUNKS, 0)
+    ref = a.best_match()  # (built with the option off so that the expectation stays what the clean list left)
+    a.close()
+    ctx.set_option(t.OPT_PIPELINE_CHUNKS, 8)
+    t.best_match_host(ctx, clean, clean_labels, 0, 300)
     before = ctx.pipelined_passes()
     got = t.best_match_host(ctx, sym, labels, 0, 300)
-    assert got.tobytes() == ref["rows"].tobytes()
+    assert got.tobytes() == ref.tobytes()
     assert ctx.pipelined_passes() == before  # the plain start was contradicted by the last chunk: the ordinary pass ran
+    got = t.best_match_host(ctx, sym, labels, 0, 300)
+    assert got.tobytes() == ref.tobytes()
+    assert ctx.pipelined_passes() == before + 1  # ... and the next call starts on the GENERAL instantiation
 
 
 def test_ragged_rows_and_the_returned_alignment(ctx):
