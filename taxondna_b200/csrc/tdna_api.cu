@@ -766,6 +766,7 @@ int ensure_tc(tdna_aln *a) {
     }
     a->tc_has_amb = flags3[1] != 0;
     a->tc_state = 1;
+    if (a->kmode == KM_P_AMBIG) c->hint_dims5 = (int64_t)flags3[2] * 2000 > (int64_t)a->n * a->L ? 1 : 0;  // the next list's first code
     return 1;
 }
 
@@ -1428,7 +1429,8 @@ static int aln_build(tdna_ctx *c, tdna_aln *a, const uint8_t *symbols, const int
             a->tc_has_amb = flags[3] != 0;
             a->tc_state = 1;
             c->hint_has_amb = a->tc_has_amb ? 1 : 0;
-            if (a->kmode == KM_P_AMBIG) c->hint_dims5 = a->tc_dims == 5 ? 1 : 0;
+            // five dimensions are right for any list; four are cheaper when it has hardly any internal gap (tc_too_gappy's measure)
+            if (a->kmode == KM_P_AMBIG) c->hint_dims5 = (int64_t)flags[4] * 2000 > (int64_t)a->n * a->L ? 1 : 0;
         }
     }
     return TDNA_OK;
@@ -1456,6 +1458,7 @@ static int aln_new(tdna_ctx *c, const uint8_t *symbols, int64_t n, int32_t L, in
     a->row_begin = 0;
     a->row_end = n;
     a->hist_size = c->opt_hist_slots;
+    a->tc_dims5 = c->hint_dims5 == 1;  // uncorrected p: start on the code the previous list on this context ended up with
     if (cfg) { a->mode = cfg[0]; a->min_overlap = cfg[1]; a->ambig = cfg[2]; }  // tdna_analyze_host: planes and operands are built once, for the right mode
     int rc = aln_build(c, a, symbols, lengths, hook, chunk_rows, pre);
     if (rc != TDNA_OK) {

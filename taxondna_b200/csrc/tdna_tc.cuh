@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(256) amb_count_kernel(const uint8_t *__restric
     for (int site = lane; site < row_len; site += 32) {
         const uint32_t cls = c_symlut[sym[row * sym_stride + site]];
         if (cls & SB_LET) { if (__popc(cls & 15u) != 1) cnt++; else oh++; }
-        if (cls & SB_D) { if (gaps_dropped) gaps++; else if (!k2p) oh++; }
+        if (cls & SB_D) gaps++;
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
@@ -348,9 +348,11 @@ __global__ void __launch_bounds__(256) amb_count_kernel(const uint8_t *__restric
         oh += __shfl_xor_sync(0xffffffffu, oh, m);
     }
     if (lane == 0) {
-        amb[row] = (cnt + gaps) | (oh << 12);  // both below 4096 (L < 4096): AMB_MASK / AMB_SHIFT
-        if (cnt + gaps) { panel_amb[row / M] = 1; *any = 1; }
-        if (gaps) atomicAdd(any + 1, gaps);
+        const int dropped = gaps_dropped ? gaps : 0;  // internal gaps the operands leave out
+        if (!gaps_dropped && !k2p) oh += gaps;        // ... or express as a symbol of their own
+        amb[row] = (cnt + dropped) | (oh << 12);  // both below 4096 (L < 4096): AMB_MASK / AMB_SHIFT
+        if (cnt + dropped) { panel_amb[row / M] = 1; *any = 1; }
+        if (gaps) atomicAdd(any + 1, gaps);  // internal gap sites, whichever code is in use (the next list's code is chosen from this)
     }
 }
 constexpr uint32_t AMB_MASK = 0xfffu;
