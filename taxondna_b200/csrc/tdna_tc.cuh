@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
             // cross-multiplication (both below 2^12), so the fp64 division happens three times per row instead of once per pair
             uint32_t fc_i = 0, fc_s = 0, f0_i = 0, f0_s = 0, f1_i = 0, f1_s = 0;
             const int spi = (seed && i < p.n) ? __ldg(sp.species + i) : -1;
-#pragma unroll
+#pragma unroll 1
             for (int cbi = 0; cbi < EPI_COLS / 32; cbi++) {
                 const int cb = g * (EPI_COLS / 32) + cbi;
                 uint32_t v[32];
