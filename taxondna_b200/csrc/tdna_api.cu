@@ -80,6 +80,8 @@ struct tdna_ctx {
     // 3.55 ms without, 3.57 - 3.78 ms with 3 - 8 chunks: the upload is 0.65 ms, a seed launch per chunk and the
     // encode kernels waiting for the persistent tile CTAs cost as much as the overlap gains
     int opt_pipeline_chunks = 0;
+    int opt_cluster = 2;  // CTAs per cluster of count kernel (b)'s bulk launch: 2 (pairs sharing the b-block) or 4 (2 x 2 tiles sharing a- and b-blocks)
+    int max_quads = -1;   // resident clusters of four (cudaOccupancyMaxActiveClusters), queried once
     // records / queue entries per row the streaming buffers of NEW alignments start with: raised to what a pass on this context
     // needed (a host that creates an alignment per analysis would otherwise overflow and retry every time)
     double hint_cand_per_row = 64, hint_queue_per_row = 256;
@@ -155,11 +157,14 @@ struct tdna_aln {
     int tc_state = 0;  // 0 = not built, 1 = ready, -1 = not eligible
     int tc_nchunks = 0, tc_kmode = -1, tc_dims = 5;
     uint32_t tc_W = 0;
+    CUtensorMap tc_mapAh;  // CL = 4: half an a-block
     CUtensorMap tc_mapA, tc_mapB, tc_mapBh;  // [.., 256 x uint32] views of d_tcA / d_tcB, boxes of one operand block (Bh: half a b-block)
     bool tc_maps = false, tc_pair = false;
     int tc_inner = 256;
     int64_t *d_tcprefix[2] = {nullptr, nullptr};
     int64_t tcprefix_tiles[2] = {0, 0};
+    int64_t *d_tcprefix4 = nullptr;  // CL = 4: quads (2 x 2 tiles) before each band
+    int64_t tcprefix4_total = 0;
     // in-library multi-GPU pass (tdna_comm_init): exchange segments, reduced per-row state, the all-gathered row records
     long long *x_send = nullptr, *x_recv = nullptr, *x_state = nullptr;
     int64_t x_seg = 0;        // records per exchange segment (same on every rank: derived from n, the rank count and x_scale only)
@@ -598,7 +603,7 @@ bool find_code(int L, int dims, tc::EncodeValues &out, uint32_t &Wout) {
 static void tc_release(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
     for (void **p : {(void **)&a->d_tcA, (void **)&a->d_tcB, (void **)&a->d_tcfull, (void **)&a->d_tcamb, (void **)&a->d_tcpanel_amb, (void **)&a->d_tcprefix[1],
-                     (void **)&a->d_tcflag})
+                     (void **)&a->d_tcflag, (void **)&a->d_tcprefix4})
         if (*p) { DFREE(*p); *p = nullptr; }
     a->tc_state = 0;
 }
@@ -663,6 +668,16 @@ static int tc_prepare(tdna_aln *a) {
         pre[b + 1] = pre[b] + tri * (tri + 1) + (cols - tri) * TC_BAND;
     }
     ok = ok && cudaSuccess == DMALLOC(&a->d_tcprefix[1], (size_t)(nbands + 1) * 8);
+    // CL = 4 (tdna_tc.cuh: my_tile<4>): per band, super columns of two column tiles from the band's diagonal on, TC_BAND / 2 row pairs each
+    std::vector<int64_t> pre4(nbands + 1);
+    pre4[0] = 0;
+    for (int b = 0; b < nbands; b++) {
+        const int64_t scmin = ((int64_t)b * TC_BAND) >> 2, nsc = (nct + 1) >> 1;
+        pre4[b + 1] = pre4[b] + std::max<int64_t>(nsc - scmin, 0) * (TC_BAND >> 1);
+    }
+    ok = ok && cudaSuccess == DMALLOC(&a->d_tcprefix4, (size_t)(nbands + 1) * 8);
+    if (ok) cudaMemcpyAsync(a->d_tcprefix4, pre4.data(), (size_t)(nbands + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+    a->tcprefix4_total = pre4[nbands];
     if (ok) {
         cudaMemsetAsync(a->d_tcfull, 0, npan, c->stream);
         cudaMemsetAsync(a->d_tcpanel_amb, 0, npan, c->stream);
@@ -682,7 +697,7 @@ static int tc_prepare(tdna_aln *a) {
     a->tc_kmode = a->kmode;
     a->tc_dims = dims;
     a->tc_values = v;
-    a->tc_pair = tc_pair_mode();
+    a->tc_pair = tc_pair_mode() || c->opt_cluster == 3;
     {   // tensor maps for the tiled TMA loads (driver entry point through the runtime: no -lcuda)
         typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -704,7 +719,10 @@ static int tc_prepare(tdna_aln *a) {
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             CUresult r3 = enc(&a->tc_mapBh, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, a->d_tcB, dimsB, strides, boxA, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            a->tc_maps = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS && r3 == CUDA_SUCCESS);
+            cuuint32_t boxAh[2] = {(cuuint32_t)inner, (cuuint32_t)(tc::A_STAGE / rowb / 2)};
+            CUresult r4 = enc(&a->tc_mapAh, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, a->d_tcA, dimsA, strides, boxAh, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            a->tc_maps = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS && r3 == CUDA_SUCCESS && r4 == CUDA_SUCCESS);
         }
         cudaGetLastError();
     }
@@ -940,11 +958,14 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
         p.prefix = a->d_tcprefix[0];
     }
     int64_t total = p.seed_list ? 2 * (int64_t)p.seed_pairs : (p.col_reach >= 0 ? a->tcprefix_class_tiles : a->tcprefix_tiles[phase]);   // slots
-    if (CL >= 2) total = (total + 1) / 2;         // pairs of slots
+    if (CL == 4) {  // quads of 2 x 2 tiles, numbered per band (only the rows' bulk launch comes here: launch_tc)
+        total = a->tcprefix4_total;
+        p.prefix = a->d_tcprefix4;
+    } else if (CL >= 2) total = (total + 1) / 2;  // pairs of slots
     // part k of m takes every m-th UNIT of 128 consecutive slots (64 row tiles x 2 column tiles of one band: the panels a
     // unit shares stay in this GPU's L2); units are dealt cyclically so that work AND candidates (which cluster near the
     // diagonal) are balanced across the parts
-    p.unit = CL >= 2 ? 64 : 128;
+    p.unit = CL == 4 ? 32 : (CL >= 2 ? 64 : 128);
     if (phase == 0) p.unit = 1;  // the seed pass has a few hundred items in all: deal them one by one, or most parts get none
     int64_t units_total = (total + p.unit - 1) / p.unit;
     int64_t my_units = units_total > part ? (units_total - part + nparts - 1) / nparts : 0;
@@ -968,16 +989,35 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     if (const char *e = exp_env("TDNA_TC_HINTS")) p.hints = atoi(e);
     p.a_rows = tc::A_STAGE / (a->tc_inner * 4);
     p.b_rows = tc::B_STAGE / (a->tc_inner * 4);
-    int64_t units = CL >= 2 ? c->sm_count / 2 : c->sm_count;
+    int64_t units = CL == 4 ? c->sm_count / 4 : (CL >= 2 ? c->sm_count / 2 : c->sm_count);
+    if (CL == 4) {  // clusters of four whole-SM CTAs must fit their GPCs: ask how many can be resident at once
+        if (c->max_quads < 0) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3((unsigned)(c->sm_count / 4 * 4));
+            q.blockDim = dim3(tc::THREADS);
+            q.dynamicSmemBytes = tc::SMEM;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 4;
+            qa[0].val.clusterDim.y = qa[0].val.clusterDim.z = 1;
+            q.attrs = qa;
+            q.numAttrs = 1;
+            int nq = 0;
+            if (cudaOccupancyMaxActiveClusters(&nq, kern, &q) != cudaSuccess || nq < 1) { cudaGetLastError(); nq = 0; }
+            c->max_quads = nq;
+        }
+        if (c->max_quads < 1) return fail(TDNA_E_STATE, "clusters of four CTAs cannot be resident on this device");
+        units = std::min<int64_t>(units, c->max_quads);
+    }
     if (const char *e = exp_env("TDNA_TC_GRID")) { int v = atoi(e); if (v >= 1 && v < units) units = v; }
     const StreamParams sp = pass_params(a, !COUNTS_MODE && phase == 0);
     // segments of ~30 ms (an item of two 128 x 256 tiles of 658 columns takes ~0.13 us of the whole GPU): see segment_boundary
     const int64_t items = p.num_tiles;
-    const int64_t seg = (COUNTS_MODE || phase == 0 || region) ? items : c->opt_segment_items > 0 ? c->opt_segment_items : std::max<int64_t>(units * 64, ((int64_t)1 << 18) * 26 / std::max(p.nchunks, 1) * (CL >= 2 ? 1 : 2));
+    const int64_t seg = (COUNTS_MODE || phase == 0 || region) ? items : c->opt_segment_items > 0 ? c->opt_segment_items : std::max<int64_t>(units * 64, ((int64_t)1 << 18) * 26 / std::max(p.nchunks, 1) * (CL >= 2 ? 1 : 2) / (CL == 4 ? 2 : 1));
     for (int64_t k0 = 0; k0 < items; k0 += seg) {
         p.k_base = k0;
         p.num_tiles = std::min(seg, items - k0);
-        int64_t grid = (p.num_tiles < units ? p.num_tiles : units) * (CL >= 2 ? 2 : 1);
+        int64_t grid = (p.num_tiles < units ? p.num_tiles : units) * (CL == 4 ? 4 : (CL >= 2 ? 2 : 1));
         if (grid < 1) break;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
@@ -986,12 +1026,12 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
         cfg.stream = c->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = CL >= 2 ? 2 : 1;
+        attr[0].val.clusterDim.x = CL == 4 ? 4 : (CL >= 2 ? 2 : 1);
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        CU(cudaLaunchKernelEx(&cfg, kern, a->tc_mapA, a->tc_mapB, a->tc_mapBh, p, sp));
+        CU(cudaLaunchKernelEx(&cfg, kern, a->tc_mapA, CL == 4 ? a->tc_mapAh : a->tc_mapB, a->tc_mapBh, p, sp));
         c->launches++;
         CU(cudaGetLastError());
         if (k0 + seg < items) TRY(segment_boundary(c, k0 + seg, items));
@@ -1007,6 +1047,12 @@ template <bool COUNTS_MODE> int launch_tc(tdna_aln *a, int phase, int part, int 
     else if (cl == 3) cl = 2;
     if (!a->tc_maps || (TC_BAND & 1)) { if (a->tc_pair) return fail(TDNA_E_STATE, "cta_group::2 needs the tensor maps"); cl = 1; }
     if (cl == 3) return launch_tc_cl<COUNTS_MODE, 3>(a, phase, part, nparts, counts);
+    if constexpr (!COUNTS_MODE) {
+        // clusters of four (TDNA_OPT_CLUSTER = 4): the bulk launch that produces per-row output; seed, class-only and region launches
+        // keep the pairs
+        const bool rows_launch = phase == 1 && (a->sp.want & (TDNA_WANT_BEST_MATCH | TDNA_WANT_EDGES)) != 0 && a->pl_reg_n == 0;
+        if (cl == 2 && a->ctx->opt_cluster == 4 && rows_launch && (TC_BAND % 4) == 0) return launch_tc_cl<COUNTS_MODE, 4>(a, phase, part, nparts, counts);
+    }
     if (cl == 2) return launch_tc_cl<COUNTS_MODE, 2>(a, phase, part, nparts, counts);
     return launch_tc_cl<COUNTS_MODE, 1>(a, phase, part, nparts, counts);
 }
@@ -1727,7 +1773,7 @@ int32_t tdna_alignment_destroy(tdna_aln *a) {
     void *ptrs[] = {a->d_sym, a->d_len, a->d_planes, a->d_species, a->d_genus, a->d_epi, a->d_full, a->d_res, a->d_prefix, a->d_scratch,
                     a->d_needc, a->d_panel_range, a->d_range_rows, a->d_range_cols, a->sp.q, a->d_tcA, a->d_tcB, a->d_tcfull, a->d_tcamb, a->d_tcpanel_amb, a->d_tcflag, a->d_tcprefix[0], a->d_tcprefix[1], a->sp.thr, a->sp.mC, a->sp.inval, a->sp.flags, a->sp.cnt, a->sp.cq, a->sp.cj, a->sp.cd,
                     a->d_stream_u64, a->d_sprefix[0], a->d_sprefix[1], a->d_ptr, a->d_scan, a->d_seedlist, a->d_cursor, a->d_lj, a->d_ld,
-                    a->x_send, a->x_recv, a->x_state, a->d_hkey[0], a->d_hkey[1], a->d_hcnt[0], a->d_hcnt[1], a->d_hctr, a->d_hent, a->d_gslot, a->d_gmem, a->d_gstart, a->d_plbuf};
+                    a->x_send, a->x_recv, a->x_state, a->d_hkey[0], a->d_hkey[1], a->d_hcnt[0], a->d_hcnt[1], a->d_hctr, a->d_hent, a->d_gslot, a->d_gmem, a->d_gstart, a->d_plbuf, a->d_tcprefix4};
     for (void *p : ptrs)
         if (p) DFREE(p);  // stream-ordered: runs after everything queued on the context's stream
     delete a;
@@ -3237,6 +3283,10 @@ int32_t tdna_set_option(tdna_ctx *c, int32_t key, int64_t value) {
             if (value < 0 || value > 2) return fail(TDNA_E_ARG, "TDNA_OPT_MULTI is 0, 1 or 2");
             c->comm.enabled = value != 0;
             c->comm.force = value == 2;
+            return TDNA_OK;
+        case TDNA_OPT_CLUSTER:
+            if (value != 2 && value != 3 && value != 4) return fail(TDNA_E_ARG, "cluster mode: 2, 3 or 4");
+            c->opt_cluster = (int)value;
             return TDNA_OK;
         case TDNA_OPT_PIPELINE_CHUNKS:
             if (value < 0 || value > 15) return fail(TDNA_E_ARG, "pipeline chunks: 0 (off) to 15");

@@ -152,7 +152,29 @@ __device__ __forceinline__ bool may_hold_class_pairs(const Params &p, int ti, in
     const int4 a = range_union(p, (int64_t)ti * M, rows), b = range_union(p, (int64_t)tj * N, N);
     return ((p.class_only & 1) && a.x <= b.y && b.x <= a.y) || ((p.class_only & 2) && a.z <= b.w && b.z <= a.w);
 }
-template <int CL> __device__ __forceinline__ bool my_tile(const Params &p, int64_t k, uint32_t rank, int &ti, int &tj) {
+// CL = 4: clusters of FOUR CTAs on a block of 2 x 2 tiles (row tiles ti0, ti0 + 1; column tiles 2 sc, 2 sc + 1): rank = 2 r + c owns tile
+// (ti0 + r, 2 sc + c), fetches HALF of its row tile's a-block for both CTAs of its row and half of its column tile's b-block for both
+// CTAs of its column -- 24 KB of L2 reads per CTA and K-chunk instead of 32 KB.  (The pass is bound by the L2 -> SM fabric: ncu reads
+// 12.2 TB/s of L2 reads on 50,000 x 658, the chip's measured cap.)  Quads are numbered per band: super column outer, row pair inner;
+// prefix[b] = quads before band b.  Return: 0 = nothing to do (the same answer in all four CTAs), 1 = run, 2 = run the loads and the
+// MMAs for the cluster's sake but this CTA's own tile lies outside the triangle / the list: no epilogue work.
+template <int CL> __device__ __forceinline__ int my_tile(const Params &p, int64_t k, uint32_t rank, int &ti, int &tj) {
+    if constexpr (CL == 4) {
+        const int64_t l = p.k_base + (int64_t)(blockIdx.x >> 2) + k * (gridDim.x >> 2);
+        const int64_t u = ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit;
+        int lo = 0, hi = p.nbands;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(p.prefix + mid) <= u) lo = mid; else hi = mid;
+        }
+        const int64_t q = u - __ldg(p.prefix + lo);
+        const int rows2 = p.band >> 1, scmin = (lo * p.band) >> 2, nsc = (p.nct + 1) >> 1;
+        const int sc = scmin + (int)(q / rows2), ti0 = lo * p.band + 2 * (int)(q % rows2);
+        if (u >= __ldg(p.prefix + p.nbands) || sc >= nsc || ti0 >= p.nrt || min(2 * sc + 1, p.nct - 1) < (ti0 >> 1)) return 0;
+        ti = ti0 + (int)(rank >> 1);
+        tj = 2 * sc + (int)(rank & 1);
+        return (ti < p.nrt && tj < p.nct && tj >= (ti >> 1)) ? 1 : 2;
+    } else
     if constexpr (CL == 1) {
         const int64_t l = p.k_base + (int64_t)blockIdx.x + k * gridDim.x;
         if (!slot_coords(p, p.prefix, ((l / p.unit) * p.t_stride + p.t_offset) * p.unit + l % p.unit, ti, tj)) return false;
@@ -519,11 +541,12 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t rank = 0;
     if constexpr (CL >= 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const int64_t units = CL == 1 ? gridDim.x : (gridDim.x >> 1), first = CL == 1 ? blockIdx.x : (blockIdx.x >> 1);
+    constexpr int CSHIFT = CL == 1 ? 0 : (CL == 4 ? 2 : 1);  // CTAs per work item: 1, 2 or 4
+    const int64_t units = gridDim.x >> CSHIFT, first = blockIdx.x >> CSHIFT;
     const int64_t my_tiles = (p.num_tiles > first) ? (p.num_tiles - first + units - 1) / units : 0;  // tiles (CL = 1) or tile pairs (CL = 2)
 
     if (tid == 0) {
-        for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL == 2 ? 2 : 1); }
+        for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL == 4 ? 4 : (CL == 2 ? 2 : 1)); }
         for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -562,6 +585,14 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         continue;
                     }
                     mbar_expect_tx(&full[slot], STG);
+                    if constexpr (CL == 4) {  // half of the row tile's a-block to the two CTAs of this row, half of the column tile's b-block to the two of this column
+                        const uint32_t r = rank >> 1, cx = rank & 1;
+                        tma_load_2d_mc(sa + cx * (A_STAGE / 2), &mapB /* CL = 4: the half-a-block view of the a-side */, 0,
+                                       (int)(((int64_t)ti * p.nchunks + c) * p.a_rows + cx * (p.a_rows / 2)), &full[slot], (uint16_t)(3u << (2 * r)));
+                        tma_load_2d_mc(sb + r * (B_STAGE / 2), &mapBh, 0, (int)(((int64_t)tj * p.nchunks + c) * p.b_rows + r * (p.b_rows / 2)),
+                                       &full[slot], (uint16_t)(5u << cx));
+                        continue;
+                    }
                     if constexpr (CL == 2) {  // own a-panel; own half of the b-panel stage to both CTAs (same offsets, same barrier)
                         tma_load_2d(sa, &mapA, 0, (int)(((int64_t)ti * p.nchunks + c) * p.a_rows), &full[slot]);
                         tma_load_2d_mc(sb + rank * (B_STAGE / 2), &mapBh, 0, (int)(((int64_t)tj * p.nchunks + c) * p.b_rows + rank * (p.b_rows / 2)),
@@ -612,6 +643,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
                         }
                     }
                     if constexpr (PAIR) mma_commit_pair(&empty[slot]);                     // the stage of BOTH CTAs may be refilled
+                    else if constexpr (CL == 4) mma_commit_mc(&empty[slot], (uint16_t)15);  // every CTA of the quad waits for all four before it refills a stage
                     else if constexpr (CL == 2) mma_commit_mc(&empty[slot], (uint16_t)3);  // both CTAs write into this stage: tell both
                     else mma_commit(&empty[slot]);  // the stage may be refilled once these MMAs have read it
                 }
@@ -637,8 +669,17 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const __grid_constant_
         int64_t k = 0;
         for (int64_t kk = 0; kk < my_tiles; kk++, k++) {
             int ti, tj;
-            if (!my_tile<CL>(p, kk, rank, ti, tj)) { k--; continue; }
+            const int tile_state = my_tile<CL>(p, kk, rank, ti, tj);
+            if (!tile_state) { k--; continue; }
             const int as = (int)(k & 1);
+            if (tile_state == 2) {  // CL = 4: this CTA's tile lies outside; its MMAs ran for the cluster's sake -- hand the accumulator back
+                mbar_wait(&tfull[as], (uint32_t)((k >> 1) & 1));
+                fence_after();
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+                continue;
+            }
             const int i = ti * M + q * 32 + lane, j0 = tj * N;
             const bool seed = !COUNTS_MODE && (sp.want & TDNA_WANT_SEED) != 0;  // diagonal-block pre-pass: thresholds only
             const bool want_bm = !COUNTS_MODE && (sp.want & TDNA_WANT_BEST_MATCH);

@@ -324,3 +324,32 @@ def test_transversions_only_streaming_on_the_tensor_kernel(ctx, shuffle, ragged,
         ea, eb = ha[k], hb[k]
         assert sorted(zip(ea["d"].view(np.uint64).tolist(), ea["count"].tolist())) == sorted(zip(eb["d"].view(np.uint64).tolist(), eb["count"].tolist())), k
     aln.close()
+
+
+@pytest.mark.parametrize("mode,cfg,n", [(0, "C3", 3000), (1, "Hg", 2600), (2, "C3", 1500)])
+def test_cluster_variants_of_the_bulk_launch_give_the_same_bytes(ctx, mode, cfg, n):
+    """TDNA_OPT_CLUSTER: pairs of CTAs sharing a b-block by multicast (2, the default), cta_group::2 MMAs (3), clusters of 2 x 2 tiles
+    (4).  The variants differ in how operands reach shared memory, not in what is computed (A/B, the pairs win)."""
+    import taxondna_b200 as t
+    from taxondna_b200 import synth
+    d = synth.generate(cfg, names=False, scale_n=n, seed=77)
+    ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_STREAM)
+    ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_TENSOR)
+    out = {}
+    try:
+        for cl in (2, 3, 4):
+            ctx.set_option(t.OPT_CLUSTER, cl)
+            aln = t.Alignment(ctx, d["symbols"])  # (mode 3 encodes the b-side in 128-row panels: a fresh alignment per mode)
+            aln.set_labels(d["species_id"], d["genus_id"], d["epithet_rank"], d["fullname_rank"])
+            aln.set_config(mode, 300, True)
+            out[cl] = aln.analyze(best_match=True, intra=True, edges=0.02)
+            assert aln.last_count_kernel() == t.KERNEL_TENSOR
+            aln.close()
+    finally:
+        ctx.set_option(t.OPT_CLUSTER, 2)
+        ctx.set_option(t.OPT_COUNT_KERNEL, t.KERNEL_AUTO)
+        ctx.set_option(t.OPT_BEST_MATCH_PATH, t.PATH_AUTO)
+    for cl in (3, 4):
+        assert out[cl]["rows"].tobytes() == out[2]["rows"].tobytes(), cl
+        assert np.array_equal(np.sort(out[cl]["intra"]).view(np.uint32), np.sort(out[2]["intra"]).view(np.uint32))
+        assert sorted(zip(out[cl]["edge_i"].tolist(), out[cl]["edge_j"].tolist())) == sorted(zip(out[2]["edge_i"].tolist(), out[2]["edge_j"].tolist()))
