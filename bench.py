@@ -213,7 +213,9 @@ def run_reference(args):
         "impl": "reference", "metric": "pairwise distances/s", "value": v, "unit": "Gpairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / max(1, args.steps) * 1e3, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "int32 counts + f64 distance", "data": "synthetic",
-        "config": {"workload": "%s x %s bp: %s" % (format(n, ","), format(L, ","), wl["desc"]), "n": n, "L": L, "mode": wl["mode"]},
+        "config": {"workload": "%s x %s bp: %s" % (format(n, ","), format(L, ","), wl["desc"]), "n": n, "L": L, "count_kernel": "cpu (per-pair char loops)",
+                   "mode": ["uncorrected", "K2P", "trans-only"][wl["mode"]], "min_overlap": 300, "pairs": n * (n - 1) // 2, "step": wl["kind"],
+                   "l2": "n/a (host cores)", "parallelism": "%d host threads, a sample of the query rows per step" % threads},
         "cpu_baseline": {"value": v, "unit": "Gpairs/s", "cores": threads, "kind": "port",
                          "sample": "first %d query rows x all later columns per step (%d pairs/step), C restatement of Sequence.getPairwiseNoBuffer (no JVM in image), %d pthreads" % (rows, pairs // max(1, args.steps), threads)},
         "e2e": {"value": v, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
