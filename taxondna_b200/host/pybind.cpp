@@ -240,7 +240,14 @@ PYBIND11_MODULE(_host, m) {
             return out;
         });
 
-    py::class_<DisplayDistancesMode>(m, "DisplayDistancesMode")
+    auto ddm = py::class_<DisplayDistancesMode>(m, "DisplayDistancesMode");
+    ddm.attr("DIST_ILLEGAL") = (double)DisplayDistancesMode::DIST_ILLEGAL;
+    ddm.attr("DIST_NO_COMPARE_SEQ") = (double)DisplayDistancesMode::DIST_NO_COMPARE_SEQ;
+    ddm.attr("DIST_SEQ_NA") = (double)DisplayDistancesMode::DIST_SEQ_NA;
+    ddm.attr("DIST_NO_OVERLAP") = (double)DisplayDistancesMode::DIST_NO_OVERLAP;
+    ddm.attr("DIST_SEQ_ON_TOP") = (double)DisplayDistancesMode::DIST_SEQ_ON_TOP;
+    ddm.attr("DIST_CANCELLED") = (double)DisplayDistancesMode::DIST_CANCELLED;
+    ddm
         .def(py::init<const SequenceGrid &>(), py::keep_alive<1, 2>())
         .def("setDistanceMethod", &DisplayDistancesMode::setDistanceMethod)
         .def("activateDisplay", &DisplayDistancesMode::activateDisplay)

@@ -164,3 +164,30 @@ def test_a_genus_beyond_the_kernels_capacity_is_left_to_the_host():
             assert r["d_max_intra"] == max(d[q, j] for j in cons)
         if inter:
             assert r["d_min_inter"] == min(d[q, j] for j in inter)
+
+
+def test_row_extremes_edge_cases():
+    """A single row, rows without species names, a species alone in its genus."""
+    import taxondna_b200 as t
+    ctx = t.Context(0)
+    try:
+        sym = np.frombuffer(b"ACGTACGTACGT" * 3, dtype=np.uint8).reshape(3, 12).copy()
+        sym[1, 0] = ord("T")
+        sym[2, 0:2] = np.frombuffer(b"GG", dtype=np.uint8)
+        a = t.Alignment(ctx, sym[:1])
+        a.set_labels(np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32))
+        a.set_config(0, 1, True)
+        r = a.row_extremes()
+        assert r["max_intra"][0] == -1 and r["min_inter"][0] == -1 and r["n_intra"][0] == 0 and (r["flags"][0] & t.ROW_SELF_VALID)
+        a.close()
+        a = t.Alignment(ctx, sym)
+        # row 0 and 1: one species; row 2: unnamed, same genus id
+        a.set_labels(np.array([5, 5, -1], np.int32), np.array([2, 2, 2], np.int32), np.array([0, 0, 0], np.int32), np.arange(3, dtype=np.int32))
+        a.set_config(0, 1, True)
+        r = a.row_extremes()
+        assert r["flags"][2] & t.EXT_UNNAMED
+        assert r["max_intra"][0] == 1 and r["max_intra"][1] == 0 and r["min_inter"][0] == -1  # the unnamed congener is skipped
+        assert r["d_max_intra"][0] == 1.0 - 11 / 12 and r["shared_intra"][0] == 12
+        a.close()
+    finally:
+        ctx.close()

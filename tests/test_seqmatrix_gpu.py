@@ -129,3 +129,48 @@ def test_pairs_between_against_the_matrix():
     finally:
         aln.close()
         ctx.close()
+
+
+def test_edge_cases_of_pairs_between_and_the_grid_callers(H):
+    """One sequence, nothing in range, a capacity below the count (two-call protocol), an empty grid, a gene nobody has."""
+    import ctypes
+    import taxondna_b200 as t
+    ctx = t.Context(0)
+    try:
+        one = t.Alignment(ctx, np.frombuffer(b"ACGTACGTAC", dtype=np.uint8).reshape(1, 10))
+        one.set_config(0, 1, True)
+        ii, jj, dd = one.pairs_between(-1.0, 1.0)
+        assert ii.size == 0
+        one.close()
+        sym = np.frombuffer(b"AAAAAAAAAA" b"AAAAAAAAAT" b"AAAAAAAATT" b"??????????", dtype=np.uint8).reshape(4, 10)
+        a = t.Alignment(ctx, sym)
+        a.set_config(0, 1, True)
+        assert a.pairs_between(0.5, 0.9)[0].size == 0           # nothing in range
+        ii, jj, dd = a.pairs_between(-1.0, -1.0)                 # only the pairs below minOverlap: everything against the all-'?' row
+        assert sorted(zip(ii.tolist(), jj.tolist())) == [(0, 3), (1, 3), (2, 3)] and (dd == -1.0).all()
+        n = ctypes.c_int64()
+        buf_i, buf_j, buf_d = np.full(2, -7, np.int32), np.full(2, -7, np.int32), np.zeros(2)
+        t.check(ctx.L.tdna_pairs_between(a.h, 0.0, 1.0, buf_i.ctypes.data, buf_j.ctypes.data, buf_d.ctypes.data, 2, ctypes.byref(n)))
+        assert n.value == 3 and (buf_i >= 0).all()             # three pairs match, the first two that arrived were stored
+        a.close()
+    finally:
+        ctx.close()
+    H.Sequence.setPairwiseDistanceMethod(0)
+    H.Sequence.setMinOverlap(1)
+    empty = H.SequenceGrid(["g1"], ["Aus bus"])
+    text = H.FindDistances(empty).displayResults(0.0, 0.5, "")
+    assert text.startswith("0 sequence pairs found with distances between 0.0% and 50.0%.")
+    grid = H.SequenceGrid(["g1", "g2"], ["Aus bus", "Aus cus"])
+    grid.setSequence("g1", "Aus bus", H.Sequence("Aus bus", "ACGTACGTAC"))
+    text = H.FindDistances(grid).displayResults(0.0, 0.5, "")  # one sequence in all: it is never compared to itself
+    assert text.startswith("0 sequence pairs found")
+    ddm = H.DisplayDistancesMode(grid)
+    ddm.setDistanceMethod(0)
+    ddm.activateDisplay("g1")
+    order = ddm.getSortedSequences("Aus bus")
+    ddm.deactivateDisplay()
+    assert order[0] == "Aus bus"
+    d = ddm.distances()
+    assert d[0] == [H.DisplayDistancesMode.DIST_SEQ_ON_TOP, H.DisplayDistancesMode.DIST_SEQ_NA]   # g1: the reference itself, a taxon without the gene
+    assert d[1] == [H.DisplayDistancesMode.DIST_NO_COMPARE_SEQ] * 2                                # g2: the reference taxon has no sequence
+    H.Sequence.setMinOverlap(300)
