@@ -263,6 +263,8 @@ class Bench:
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+        if os.environ.get("TDNA_BENCH_TORCH_THREADS"):
+            torch.set_num_threads(int(os.environ["TDNA_BENCH_TORCH_THREADS"]))
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
@@ -360,7 +362,7 @@ class Bench:
             step_device()
         self.barrier()
         sampler = ClockSampler(self.local)
-        if rank == 0 and full:
+        if rank == 0 and full and not os.environ.get("TDNA_BENCH_NOSAMPLER"):
             sampler.start()
         launches0 = ctx.launch_count()
         step_ms, tile_ms, phase_ms = [], [], []
@@ -388,7 +390,7 @@ class Bench:
         self.barrier()
         t_region = time.perf_counter() - t_region0
         launches = ctx.launch_count() - launches0
-        clocks = sampler.stop() if (rank == 0 and full) else None
+        clocks = sampler.stop() if (rank == 0 and full and not os.environ.get("TDNA_BENCH_NOSAMPLER")) else None
         ms_per_step = self.max_over_ranks(float(sum(step_ms))) / steps
         value = pairs / (ms_per_step * 1e-3) / 1e9
         used_tensor = streaming and aln.last_count_kernel() == t.KERNEL_TENSOR
@@ -550,13 +552,20 @@ class Bench:
             same = out_host.numpy().tobytes() == check
             step_e2e_one_call()
             self.barrier()
+            one_steps = max(e2e_steps, steps)  # all K steps: a call is a few milliseconds
+            per_call = []
             t0 = time.perf_counter()
-            for _ in range(e2e_steps):
+            for _ in range(one_steps):
+                t1 = time.perf_counter()
                 step_e2e_one_call()
+                per_call.append((time.perf_counter() - t1) * 1e3)
+                if os.environ.get("TDNA_BENCH_DEBUG") and per_call[-1] > 4.5:
+                    print("slow one-call step: %.2f ms %s" % (per_call[-1], ctx.host_call_phase_ms()), file=sys.stderr, flush=True)
             self.barrier()
-            s1 = self.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+            s1 = self.max_over_ranks((time.perf_counter() - t0) / one_steps)
             out["e2e"] = {"value": pairs / s1 / 1e9, "unit": "Gpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                          "ms_per_step": s1 * 1e3, "steps": e2e_steps, "api": "tdna_analyze_host (one call: host list in, row records out)",
+                          "ms_per_step": s1 * 1e3, "steps": one_steps, "api": "tdna_analyze_host (one call: host list in, row records out)",
+                          "ms_per_call_this_rank": {"min": min(per_call), "median": sorted(per_call)[len(per_call) // 2], "max": max(per_call)},
                           "same_bytes_as_separate_calls": bool(same), "separate_calls": sep}
 
         out["cpu_baseline"] = None
