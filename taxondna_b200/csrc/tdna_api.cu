@@ -2113,7 +2113,9 @@ static int ensure_stream_state(tdna_aln *a) {
     if (a->stream_alloc) return TDNA_OK;
     tdna_ctx *c = a->ctx;
     size_t n = (size_t)a->n;
-    long long cap = (long long)((double)n * c->hint_cand_per_row);
+    // (the hints of an earlier list never ask for more than 2^28 entries -- 4 GB -- beyond the default: a short, hostile list must not
+    // size the buffers of a long one)
+    long long cap = std::min<long long>((long long)((double)n * c->hint_cand_per_row), std::max<long long>((long long)n * 64, 1ll << 28));
     if (cap < (1ll << 22)) cap = 1ll << 22;
     if (cap * 16 > c->budget / 2) cap = c->budget / 32;
     StreamParams &sp = a->sp;
@@ -2128,7 +2130,7 @@ static int ensure_stream_state(tdna_aln *a) {
     CU(DMALLOC(&sp.cd, (size_t)cap * 8));
     // kernel (b)'s queue holds every pair that passes the SEEDED threshold of either of its rows (about four times the final
     // candidates): 256 per row, 16 bytes each
-    long long qcap = (long long)((double)n * c->hint_queue_per_row);
+    long long qcap = std::min<long long>((long long)((double)n * c->hint_queue_per_row), std::max<long long>((long long)n * 256, 1ll << 28));
     if (qcap < (1ll << 22)) qcap = 1ll << 22;
     if (qcap * 16 > c->budget / 2) qcap = c->budget / 32;
     CU(DMALLOC(&sp.q, (size_t)qcap * 16));
