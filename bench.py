@@ -552,7 +552,7 @@ class Bench:
             same = out_host.numpy().tobytes() == check
             step_e2e_one_call()
             self.barrier()
-            one_steps = max(e2e_steps, steps)  # all K steps: a call is a few milliseconds
+            one_steps = int(os.environ.get("TDNA_BENCH_E2E_STEPS", max(e2e_steps, steps)))  # all K steps: a call is a few milliseconds
             per_call = []
             t0 = time.perf_counter()
             for _ in range(one_steps):
