@@ -20,6 +20,10 @@
  *  - There is NO CPU fallback: without a CUDA device tdna_init fails with TDNA_E_CUDA.
  *  - Row index == position in the SequenceList order the host layer passed (SORT_BYNAME in the
  *    GUI, SpeciesIdentifier/SequencePanel.java:46,177-249).
+ *  - Numerics: integer counts, uncorrected p and transversion distances are bit-exact (fp64, the reference's operation order, no
+ *    FMA contraction).  K2P distances (Sequence.java:1559-1570) use a restatement of fdlibm's log (= StrictMath.log): bit-identical
+ *    to that, and within 1 ulp of the log terms of any conforming JVM's Math.log (:1564), which HotSpot may intrinsify -- a last-bit
+ *    difference can only matter where Settings.makeLongFromDouble truncates d * 10^5 within an ulp of an integer.
  */
 #ifndef TAXONDNA_CUDA_H
 #define TAXONDNA_CUDA_H
