@@ -560,7 +560,7 @@ class Bench:
                 step_e2e_one_call()
                 per_call.append((time.perf_counter() - t1) * 1e3)
                 if os.environ.get("TDNA_BENCH_DEBUG") and per_call[-1] > 4.5:
-                    print("slow one-call step: %.2f ms %s" % (per_call[-1], ctx.host_call_phase_ms()), file=sys.stderr, flush=True)
+                    print("slow one-call step: %.2f ms %s tile pass %.3f ms" % (per_call[-1], ctx.host_call_phase_ms(), ctx.last_tile_pass_ms()), file=sys.stderr, flush=True)
             self.barrier()
             s1 = self.max_over_ranks((time.perf_counter() - t0) / one_steps)
             out["e2e"] = {"value": pairs / s1 / 1e9, "unit": "Gpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
