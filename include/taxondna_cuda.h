@@ -439,6 +439,13 @@ int32_t tdna_time_matrix_kernel(tdna_aln *aln, int32_t reps, float *ms_per_launc
  * row symbol x and a column symbol y contribute W - (W-1)[x == y] to the int32 accumulator.  Host arithmetic only (no device). */
 int32_t tdna_tensor_code(int32_t L, int32_t dims, int32_t *code, uint32_t *W);
 int32_t tdna_last_count_kernel(tdna_aln *aln);
+/* The operand tables count kernel (b) encodes with for a mode and width (host arithmetic only): per symbol CODE (6 rows of 8 bytes) the
+ * row-side and the column-side int8 vector over the *dims K-dimensions of a site, and the accumulator's radix W.  Codes -- one-hot
+ * modes (uncorrected p, K2P): 0..3 = A C G T, 4 = '-' where it is a symbol of its own (five dimensions), others contribute nothing;
+ * transversions only: 0 purine {A G R}, 1 pyrimidine {C T Y}, 2 '-', 3 any other letter.  row . column = ident + W * mism of the site
+ * (transversions only: (shared - transv) + W * transv).  five_dims: uncorrected p with '-' as a fifth symbol. */
+int32_t tdna_tensor_tables(int32_t mode, int32_t ambiguous_allowed, int32_t L, int32_t five_dims, int8_t *row_side, int8_t *col_side, int32_t *dims,
+                           uint32_t *W);
 /* K-dimensions per site of the operands count kernel (b) built for this alignment (5, or 4 when no row has an internal gap / in K2P
  * mode; 6 for transversions only); 0 if they have not been built.  The roofline's algorithmic work per pair is 2 * dims * L int8 operations. */
 int32_t tdna_tensor_dims(tdna_aln *aln);

@@ -87,7 +87,7 @@ EXPORTS = [
     "tdna_best_match", "tdna_best_match_compute", "tdna_class_distances", "tdna_edges_below", "tdna_pairs_between", "tdna_row_extremes",
     "tdna_valid_conspecifics", "tdna_set_progress", "tdna_cancel", "tdna_time_matrix_kernel", "tdna_measure_int_peaks",
     "tdna_analyze", "tdna_tensor_counts", "tdna_last_count_kernel", "tdna_best_match_seed", "tdna_best_match_part", "tdna_best_match_merge", "tdna_best_match_part_packed", "tdna_best_match_merge_gathered", "tdna_rows_per_part", "tdna_tensor_code", "tdna_consensus", "tdna_fasta_parse", "tdna_fasta_destroy", "tdna_fasta_count", "tdna_fasta_width", "tdna_fasta_records", "tdna_fasta_symbols", "tdna_alignment_create_from_fasta", "tdna_best_match_part_routed", "tdna_best_match_merge_routed", "tdna_set_option", "tdna_last_tile_pass_ms",
-    "tdna_tensor_dims", "tdna_last_pass_stats", "tdna_pipelined_passes", "tdna_host_call_phase_ms", "tdna_multi_phase_ms", "tdna_analyze_host", "tdna_class_histogram", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
+    "tdna_tensor_dims", "tdna_tensor_tables", "tdna_last_pass_stats", "tdna_pipelined_passes", "tdna_host_call_phase_ms", "tdna_multi_phase_ms", "tdna_analyze_host", "tdna_class_histogram", "tdna_comm_unique_id", "tdna_comm_init", "tdna_comm_destroy", "tdna_comm_info", "tdna_init_multi",
 ]
 
 PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p)

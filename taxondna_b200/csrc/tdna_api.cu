@@ -600,6 +600,42 @@ bool find_code(int L, int dims, tc::EncodeValues &out, uint32_t &Wout) {
     return false;
 }
 
+// The operand code of count kernel (b) for a mode and an alignment width: the K-dimensions per site, the radix W of the accumulator
+// and the row- / column-side int8 vector of every symbol code (tdna_tc.cuh: EncodeValues).  Host arithmetic only.
+static bool tc_code_for(int kmode, int L, bool dims5, tc::EncodeValues &v, uint32_t &W, int &dims_out) {
+    if (kmode == KM_P_NOAMBIG || L >= 4096 || L < 1) return false;
+    int dims = (kmode == KM_K2P || !dims5) ? 4 : 5;
+    v = tc::EncodeValues();
+    W = 0;
+    if (kmode == KM_TRANS) {
+        // transversions only: six dimensions with entries 0, 1 and r = sqrt(W) (tdna_tc.cuh: EncodeValues); every symbol is expressed
+        // exactly, so there is no ambiguity-letter machinery and the plain instantiation always runs
+        dims = 6;
+        int r = 16;
+        while (r * r <= L) r *= 2;  // W = 256, 1024, 4096: the smallest above L
+        W = (uint32_t)(r * r);
+        v.trans = 1;
+        const int8_t rr = (int8_t)r;
+        const int8_t ta[4][6] = {{1, 0, rr, 0, 0, 1}, {0, 1, 0, rr, 0, 1}, {0, 0, 0, 0, 1, 1}, {0, 0, 0, 0, 0, 1}};
+        const int8_t tb[4][6] = {{1, 0, 0, rr, 1, 0}, {0, 1, rr, 0, 1, 0}, {0, 0, 0, 0, 0, 1}, {0, 0, 0, 0, 1, 0}};
+        for (int code = 0; code < 4; code++)
+            for (int d = 0; d < 6; d++) { v.ta[code][d] = ta[code][d]; v.tb[code][d] = tb[code][d]; }
+        // shared == L for every pair of two rows needs every site of both in AGRCTY or '-' (any other letter is only "shared" with a gap)
+        v.breaks_full[3] = v.breaks_full[4] = v.breaks_full[5] = 1;
+    } else {
+        if (!find_code(L, dims, v, W)) {
+            dims = 5;
+            if (!find_code(L, dims, v, W)) return false;
+        }
+        v.gap_is_symbol = (kmode == KM_K2P || dims == 4) ? 0 : 1;
+        for (int code = 0; code < dims; code++)  // one-hot: row (b + a [dim == code]), column (d + c [dim == code])
+            for (int d = 0; d < dims; d++) { v.ta[code][d] = (int8_t)(v.b + (d == code ? v.a : 0)); v.tb[code][d] = (int8_t)(v.d + (d == code ? v.c : 0)); }
+        for (int code = dims; code < 6; code++) v.breaks_full[code] = 1;  // a site without contribution ('_', '?', past the row's end; '-' when it is not a symbol)
+    }
+    dims_out = dims;
+    return true;
+}
+
 static void tc_release(tdna_aln *a) {
     tdna_ctx *c = a->ctx;
     for (void **p : {(void **)&a->d_tcA, (void **)&a->d_tcB, (void **)&a->d_tcfull, (void **)&a->d_tcamb, (void **)&a->d_tcpanel_amb, (void **)&a->d_tcprefix[1],
@@ -620,34 +656,10 @@ static int tc_prepare(tdna_aln *a) {
     // (counted per row; the pairs it touches are bounded by the accumulator and settled from the bit-planes).  A list with more than
     // a sprinkling of internal gaps (tc_dims5: decided from the count the encoder returns) gets the five-dimension code, where '-'
     // is a symbol of its own and every accumulator is exact again.
-    int dims = (a->kmode == KM_K2P || !a->tc_dims5) ? 4 : 5;
+    int dims = 0;
     tc::EncodeValues v = {};
     uint32_t W = 0;
-    if (a->kmode == KM_TRANS) {
-        // transversions only: six dimensions with entries 0, 1 and r = sqrt(W) (tdna_tc.cuh: EncodeValues); every symbol is expressed
-        // exactly, so there is no ambiguity-letter machinery and the plain instantiation always runs
-        dims = 6;
-        int r = 16;
-        while (r * r <= a->L) r *= 2;  // W = 256, 1024, 4096: the smallest above L
-        W = (uint32_t)(r * r);
-        v.trans = 1;
-        const int8_t rr = (int8_t)r;
-        const int8_t ta[4][6] = {{1, 0, rr, 0, 0, 1}, {0, 1, 0, rr, 0, 1}, {0, 0, 0, 0, 1, 1}, {0, 0, 0, 0, 0, 1}};
-        const int8_t tb[4][6] = {{1, 0, 0, rr, 1, 0}, {0, 1, rr, 0, 1, 0}, {0, 0, 0, 0, 0, 1}, {0, 0, 0, 0, 1, 0}};
-        for (int code = 0; code < 4; code++)
-            for (int d = 0; d < 6; d++) { v.ta[code][d] = ta[code][d]; v.tb[code][d] = tb[code][d]; }
-        // shared == L for every pair of two rows needs every site of both in AGRCTY or '-' (any other letter is only "shared" with a gap)
-        v.breaks_full[3] = v.breaks_full[4] = v.breaks_full[5] = 1;
-    } else {
-        if (!find_code(a->L, dims, v, W)) {
-            dims = 5;
-            if (!find_code(a->L, dims, v, W)) return -1;
-        }
-        v.gap_is_symbol = (a->kmode == KM_K2P || dims == 4) ? 0 : 1;
-        for (int code = 0; code < dims; code++)  // one-hot: row (b + a [dim == code]), column (d + c [dim == code])
-            for (int d = 0; d < dims; d++) { v.ta[code][d] = (int8_t)(v.b + (d == code ? v.a : 0)); v.tb[code][d] = (int8_t)(v.d + (d == code ? v.c : 0)); }
-        for (int code = dims; code < 6; code++) v.breaks_full[code] = 1;  // a site without contribution ('_', '?', past the row's end; '-' when it is not a symbol)
-    }
+    if (!tc_code_for(a->kmode, a->L, a->tc_dims5, v, W, dims)) return -1;
     const int nchunks = (a->L * dims + tc::KB - 1) / tc::KB;
     const int64_t npa = round_up(a->n, tc::M), npb = round_up(a->n, tc::N);
     const size_t npan = (size_t)(npb / tc::M);
@@ -3532,6 +3544,20 @@ int32_t tdna_tensor_code(int32_t L, int32_t dims, int32_t *code, uint32_t *W) {
     uint32_t w = 0;
     if (!find_code(L, dims, v, w)) return fail(TDNA_E_STATE, "no code with int8 entries for this width and dimension count");
     code[0] = v.a; code[1] = v.b; code[2] = v.c; code[3] = v.d;
+    *W = w;
+    return TDNA_OK;
+}
+
+int32_t tdna_tensor_tables(int32_t mode, int32_t ambiguous_allowed, int32_t L, int32_t five_dims, int8_t *row_side, int8_t *col_side, int32_t *dims, uint32_t *W) {
+    if (!row_side || !col_side || !dims || !W) return fail(TDNA_E_ARG, "null argument");
+    const int kmode = mode == TDNA_PDM_K2P ? KM_K2P : (mode == TDNA_PDM_TRANS_ONLY ? KM_TRANS : (ambiguous_allowed ? KM_P_AMBIG : KM_P_NOAMBIG));
+    tc::EncodeValues v;
+    uint32_t w = 0;
+    int d = 0;
+    if (!tc_code_for(kmode, L, five_dims != 0, v, w, d)) return fail(TDNA_E_STATE, "count kernel (b) has no code for this mode / width");
+    for (int code = 0; code < 6; code++)
+        for (int k = 0; k < 8; k++) { row_side[code * 8 + k] = v.ta[code][k]; col_side[code * 8 + k] = v.tb[code][k]; }
+    *dims = d;
     *W = w;
     return TDNA_OK;
 }
