@@ -273,6 +273,8 @@ class Bench:
         self.ctx.set_option(t.OPT_COUNT_KERNEL, {"auto": t.KERNEL_AUTO, "popc": t.KERNEL_POPC, "tensor": t.KERNEL_TENSOR}[args.kernel])
         if self.world > 1:
             self.ctx.comm_init_torch(dist, self.dev)  # from here on whole-range library calls are collective over the ranks
+        if os.environ.get("TDNA_BENCH_UNIT"):
+            self.ctx.set_option(t.OPT_UNIT_ITEMS, int(os.environ["TDNA_BENCH_UNIT"]))
         self.stream = torch.cuda.ExternalStream(self.ctx.stream_ptr(), device=self.dev)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
         self.L_ = t.load()

@@ -340,6 +340,7 @@ enum { TDNA_OPT_BEST_MATCH_PATH = 1, /* TDNA_PATH_*: how tdna_best_match compute
        TDNA_OPT_COUNT_KERNEL = 3,    /* TDNA_KERNEL_*: which count kernel the streaming pass uses */
        TDNA_OPT_HIST_SLOTS = 5,      /* first size of a class histogram's table for alignments created from now on (a power of two,
                                         default 2^18; a pass that fills a table repeats with four times the slots) */
+       TDNA_OPT_UNIT_ITEMS = 9,      /* several GPUs: tile pairs per unit of the cyclic dealing of the triangle (0 = default) */
        TDNA_OPT_CLUSTER = 8,         /* count kernel (b), bulk launch: 2 = pairs of CTAs sharing a b-block by TMA multicast; 4 = clusters of
                                         2 x 2 tiles sharing a- and b-blocks (a quarter less L2 traffic) */
        TDNA_OPT_PIPELINE_CHUNKS = 7, /* tdna_analyze_host: at most this many row chunks for a pass PIPELINED with the upload (region

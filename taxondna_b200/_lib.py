@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("TDNA_LIB") or os.path.join(_HERE, "libtaxondna_cuda.s
 PDM_UNCORRECTED, PDM_K2P, PDM_TRANS_ONLY = 0, 1, 2
 PD_INTRA, PD_INTER = 0, 1
 ROW_SELF_VALID, ROW_NONFINITE = 1, 2
-OPT_BEST_MATCH_PATH, OPT_TILE_COLUMNS, OPT_COUNT_KERNEL, OPT_MULTI, OPT_HIST_SLOTS, OPT_SEGMENT_ITEMS, OPT_PIPELINE_CHUNKS, OPT_CLUSTER = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_BEST_MATCH_PATH, OPT_TILE_COLUMNS, OPT_COUNT_KERNEL, OPT_MULTI, OPT_HIST_SLOTS, OPT_SEGMENT_ITEMS, OPT_PIPELINE_CHUNKS, OPT_CLUSTER, OPT_UNIT_ITEMS = 1, 2, 3, 4, 5, 6, 7, 8, 9
 COMM_ID_BYTES = 128
 KERNEL_AUTO, KERNEL_POPC, KERNEL_TENSOR = 0, 1, 2
 PATH_AUTO, PATH_DENSE, PATH_STREAM = 0, 1, 2

@@ -80,6 +80,7 @@ struct tdna_ctx {
     // 3.55 ms without, 3.57 - 3.78 ms with 3 - 8 chunks: the upload is 0.65 ms, a seed launch per chunk and the
     // encode kernels waiting for the persistent tile CTAs cost as much as the overlap gains
     int opt_pipeline_chunks = 0;
+    int opt_unit_items = 0;  // work items per dealing unit of a multi-GPU tile pass; 0 = default (64 tile pairs)
     int opt_cluster = 2;  // CTAs per cluster of count kernel (b)'s bulk launch: 2 (pairs sharing the b-block) or 4 (2 x 2 tiles sharing a- and b-blocks)
     int max_quads = -1;   // resident clusters of four (cudaOccupancyMaxActiveClusters), queried once
     // records / queue entries per row the streaming buffers of NEW alignments start with: raised to what a pass on this context
@@ -978,6 +979,7 @@ template <bool COUNTS_MODE, int CL> int launch_tc_cl(tdna_aln *a, int phase, int
     // unit shares stay in this GPU's L2); units are dealt cyclically so that work AND candidates (which cluster near the
     // diagonal) are balanced across the parts
     p.unit = CL == 4 ? 32 : (CL >= 2 ? 64 : 128);
+    if (c->opt_unit_items > 0 && CL == 2) p.unit = c->opt_unit_items;
     if (phase == 0) p.unit = 1;  // the seed pass has a few hundred items in all: deal them one by one, or most parts get none
     int64_t units_total = (total + p.unit - 1) / p.unit;
     int64_t my_units = units_total > part ? (units_total - part + nparts - 1) / nparts : 0;
@@ -3297,6 +3299,10 @@ int32_t tdna_set_option(tdna_ctx *c, int32_t key, int64_t value) {
             if (value < 0 || value > 2) return fail(TDNA_E_ARG, "TDNA_OPT_MULTI is 0, 1 or 2");
             c->comm.enabled = value != 0;
             c->comm.force = value == 2;
+            return TDNA_OK;
+        case TDNA_OPT_UNIT_ITEMS:
+            if (value < 0 || value > 4096) return fail(TDNA_E_ARG, "unit items: 0 (default) to 4096");
+            c->opt_unit_items = (int)value;
             return TDNA_OK;
         case TDNA_OPT_CLUSTER:
             if (value != 2 && value != 3 && value != 4) return fail(TDNA_E_ARG, "cluster mode: 2, 3 or 4");
